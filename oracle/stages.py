@@ -1,0 +1,296 @@
+"""Literal Python-3 restatement of the reference stage code (TEST INFRASTRUCTURE ONLY).
+
+Every function names the reference lines it follows (paths relative to the
+cellranger-atac 1.2.0 checkout).  The per-base / per-fragment Python loops are
+kept on purpose: this file is both the bit-exactness checker for small inputs
+and the timed "reference-shaped" CPU baseline.  Vectorised equivalents that
+finish on large inputs live in ``oracle/fast.py`` and ``oracle/fast.c`` and are
+themselves checked against this file.
+
+Python-2 semantics that had to be written out explicitly:
+  * ``None >= 1`` is False in py2 (count_cut_sites/__init__.py:42,47)
+  * ``str < float`` is always False in py2 (utils.py:112) -> no filtering
+  * ``from __future__ import division`` is on in all three stages
+"""
+import bisect
+from collections import Counter, OrderedDict
+
+import numpy as np
+
+WINDOW_SIZE = 400            # lib/python/constants.py:68
+PEAK_MERGE_DISTANCE = 500    # lib/python/constants.py:70
+PEAK_ODDS_RATIO = 1 / 5      # lib/python/constants.py:71
+
+
+# --------------------------------------------------------------------------- #
+# fragments text                                                              #
+# --------------------------------------------------------------------------- #
+def parse_fragments(lines):
+    """lib/python/tools/io.py:75-79 (open_fragment_file): yield
+    (contig, start, stop, barcode, dup_count) from text lines."""
+    for line in lines:
+        if isinstance(line, bytes):
+            line = line.decode("ascii")
+        contig, start, stop, barcode, dup_count = line.strip().split("\t")
+        yield contig, int(start), int(stop), barcode, int(dup_count)
+
+
+# --------------------------------------------------------------------------- #
+# COUNT_CUT_SITES                                                             #
+# --------------------------------------------------------------------------- #
+def pileup(chrom_len, fragments):
+    """count_cut_sites/__init__.py:94-101: windowed cut-site counts for ONE contig.
+    ``fragments`` yields (start, stop)."""
+    half_window = WINDOW_SIZE // 2
+    Cuts = np.zeros(chrom_len, dtype="int32")
+    for start, stop in fragments:
+        Cuts[max(0, start - half_window): min(start + half_window + 1, chrom_len)] += 1
+        Cuts[max(0, stop - half_window): min(stop + half_window + 1, chrom_len)] += 1
+    return Cuts
+
+
+def count_dict_from_cuts(Cuts):
+    """count_cut_sites/__init__.py:104: Counter(v for v in Cuts if v > 0)."""
+    return Counter(int(v) for v in Cuts if v > 0)
+
+
+def bedgraph_rows(chrom, contig_len, Cuts, min_counts=1):
+    """count_cut_sites/__init__.py:27-48 (write_chrom_bedgraph) returning the rows
+    instead of writing them.  Zeros are skipped WITHOUT closing the open run
+    (:36-37), so equal non-zero values either side of a zero gap form one row."""
+    rows = []
+    last_count = None
+    last_start = None
+    last_pos = None
+    for pos in range(contig_len):
+        count = int(Cuts[pos])
+        if count == 0:
+            continue
+        if last_count == count:
+            last_pos = pos
+        else:
+            if last_count is not None and last_count >= min_counts:   # py2: None >= 1 is False
+                rows.append((chrom, last_start, last_pos + 1, last_count))
+            last_start = pos
+            last_pos = pos
+            last_count = count
+    if last_count is not None and last_count >= min_counts:
+        rows.append((chrom, last_start, last_pos + 1, last_count))
+    return rows
+
+
+def format_bedgraph(rows):
+    """count_cut_sites/__init__.py:43: '{}\\t{}\\t{}\\t{}\\n'."""
+    return "".join("{}\t{}\t{}\t{}\n".format(*r) for r in rows)
+
+
+def merge_count_dicts(dicts):
+    """count_cut_sites/__init__.py:77-81: Counter += per chunk."""
+    total = Counter()
+    for d in dicts:
+        total += d
+    return total
+
+
+# --------------------------------------------------------------------------- #
+# DETECT_PEAKS                                                                #
+# --------------------------------------------------------------------------- #
+def cut_site_counter_from_bedgraph(rows, threshold=1, contig=None):
+    """lib/python/utils.py:105-115 on already-split rows.  The reference compares
+    the *string* count with the float threshold (:112); in Python 2 a number
+    orders before every str, so the test is always False and nothing is filtered."""
+    for chrom, start, stop, count in rows:
+        if contig is not None and chrom != contig:
+            continue
+        for pos in range(int(start), int(stop)):
+            yield chrom, pos, int(count)
+
+
+def identify_peaks(site_iter, threshold):
+    """detect_peaks/__init__.py:40-62 returning (peaks, total_peaks_detected)."""
+    peaks = []
+    window = None
+    for chrom, pos, windowed_count in site_iter:
+        if windowed_count < threshold:
+            continue
+        if window is None:
+            window = [chrom, pos, pos + 1]
+        elif pos - PEAK_MERGE_DISTANCE <= window[2] and chrom == window[0]:
+            window[2] = pos + 1
+        else:
+            peaks.append(tuple(window))
+            window = [chrom, pos, pos + 1]
+    if window is not None:
+        peaks.append(tuple(window))
+    return peaks, len(peaks)
+
+
+def sort_and_uniq_peaks(peaks, fai_contig_order):
+    """lib/python/tools/regions.py:392-417: ``bedtools sort -g genome.fa.fai`` then
+    ``uniq``.  bedtools sort -g orders by the .fai contig order, then start (then
+    end for ties, which cannot occur for non-overlapping peaks)."""
+    rank = {c: i for i, c in enumerate(fai_contig_order)}
+    out = sorted(peaks, key=lambda p: (rank[p[0]], p[1], p[2]))
+    uniq = []
+    for p in out:
+        if not uniq or uniq[-1] != p:
+            uniq.append(p)
+    return uniq
+
+
+def detect_peaks_contig(chrom, chrom_len, fragments, threshold):
+    """COUNT_CUT_SITES.main + DETECT_PEAKS.main for one contig through the
+    bedgraph, exactly as the two stages chain (count_cut_sites/__init__.py:85-112,
+    detect_peaks/__init__.py:85-97)."""
+    Cuts = pileup(chrom_len, fragments)
+    cd = count_dict_from_cuts(Cuts)
+    rows = bedgraph_rows(chrom, chrom_len, Cuts) if len(cd) else []
+    text_rows = [(c, str(s), str(e), str(v)) for c, s, e, v in rows]
+    peaks, _ = identify_peaks(cut_site_counter_from_bedgraph(text_rows, threshold, chrom), threshold)
+    return Cuts, cd, rows, peaks
+
+
+def peak_metrics(peaks, threshold, params):
+    """detect_peaks/__init__.py:113-129 (join): metrics dict.  bases_in_peaks is
+    sum(len(fasta[chrom][start:end])) = sum(end-start) because end <= contig_len."""
+    m = OrderedDict()
+    m["total_peaks_detected"] = len(peaks)
+    m["bases_in_peaks"] = int(sum(e - s for _, s, e in peaks))
+    if params is not None:
+        for name, val in zip(("p_zero_noise", "mean_bg_noise", "alpha_bg_noise", "p_signal",
+                              "frac_zero_noise", "frac_bg_noise"), params):
+            m["peakcaller_{}".format(name)] = float(val)
+    m["peakcaller_threshold"] = threshold
+    return m
+
+
+# --------------------------------------------------------------------------- #
+# tenkit Regions (only what GENERATE_PEAK_MATRIX touches)                     #
+# --------------------------------------------------------------------------- #
+class Regions(object):
+    """tenkit/lib/python/tenkit/regions.py:28-43,91-110,136-145."""
+
+    def __init__(self, regions=None, merge=True):
+        if regions is not None and not (regions == []):
+            sorted_regions = sorted(regions)
+            self.starts = [r[0] for r in sorted_regions]
+            self.ends = [r[1] for r in sorted_regions]
+            if merge:
+                self.make_regions_non_overlapping()
+        else:
+            self.starts = []
+            self.ends = []
+
+    def make_regions_non_overlapping(self):
+        new_starts = [self.starts[0]]
+        new_ends = [self.ends[0]]
+        last_index = 0
+        for n in range(1, len(self.starts)):
+            this_start = self.starts[n]
+            this_end = self.ends[n]
+            last_end = new_ends[last_index]
+            if this_start >= last_end:
+                new_starts.append(this_start)
+                new_ends.append(this_end)
+                last_index += 1
+            else:
+                new_ends[last_index] = max(this_end, last_end)
+        self.starts = new_starts
+        self.ends = new_ends
+
+    def get_region_containing_point(self, pt):
+        check_index = bisect.bisect(self.starts, pt) - 1
+        if check_index == -1:
+            return None
+        if pt >= self.starts[check_index] and pt < self.ends[check_index]:
+            return (self.starts[check_index], self.ends[check_index])
+        return None
+
+
+def get_target_regions(peak_lines):
+    """tenkit/lib/python/tenkit/bio_io.py:736-766."""
+    targets = {}
+    for line in peak_lines:
+        info = line.strip().split("\t")
+        if (line.startswith("browser") or line.startswith("track") or line.startswith("-browser")
+                or line.startswith("-track") or line.startswith("#")):
+            continue
+        if len(line.strip()) == 0:
+            continue
+        targets.setdefault(info[0], []).append((int(info[1]), int(info[2])))
+    return {chrom: Regions(regions=se) for chrom, se in targets.items()}
+
+
+# --------------------------------------------------------------------------- #
+# GENERATE_PEAK_MATRIX                                                        #
+# --------------------------------------------------------------------------- #
+def get_chunks(num, chunks):
+    """lib/python/utils.py:133-136."""
+    bounds = np.linspace(0, num, chunks + 1, dtype=int, endpoint=True).tolist()
+    return [(s, e) for s, e in zip(bounds, bounds[1:]) if s != e]
+
+
+def peak_matrix_chunk(peak_lines, barcodes, fragments):
+    """generate_peak_matrix/__init__.py:92-119 for one barcode chunk.
+
+    peak_lines: lines of peaks.bed; barcodes: the chunk's barcode list (column
+    order); fragments: iterable of (contig, start, stop, barcode, dup).
+    Returns canonical CSC (indptr int64[B+1], indices int64[nnz], data int64[nnz],
+    shape) exactly as ``csc_matrix(coo_matrix(...))`` yields it: row indices
+    sorted within each column, duplicates summed.  A merged region (overlapping
+    user peaks) raises KeyError like the reference (:114)."""
+    peak_lines = list(peak_lines)
+    full_peaks = get_target_regions(peak_lines)
+    peaks_dict = OrderedDict(("{}:{}-{}".format(*peak.strip("\n").split("\t")), num)
+                             for num, peak in enumerate(peak_lines))
+    barcodes_dict = OrderedDict((bc.strip("\n"), num) for num, bc in enumerate(barcodes))
+    peak_bc_counts = Counter()
+    for contig, start, stop, barcode, _ in fragments:
+        if barcode not in barcodes_dict:
+            continue
+        for pos in (start, stop):
+            if contig in full_peaks.keys():
+                peak = full_peaks[contig].get_region_containing_point(pos)
+                if peak is not None:
+                    peak_bc_counts[barcodes_dict[barcode],
+                                   peaks_dict["{}:{}-{}".format(contig, peak[0], peak[1])]] += 1
+    n_rows, n_cols = len(peaks_dict), len(barcodes_dict)
+    return coo_to_csc(peak_bc_counts, n_rows, n_cols)
+
+
+def coo_to_csc(counter, n_rows, n_cols):
+    """scipy ``csc_matrix(coo_matrix((data,(row,col))))`` (generate_peak_matrix/
+    __init__.py:119): canonical CSC.  Restated without scipy so the layout is
+    explicit; tests compare it with scipy itself."""
+    items = sorted(((col, row, val) for (col, row), val in counter.items()))
+    indptr = np.zeros(n_cols + 1, dtype=np.int64)
+    indices = np.zeros(len(items), dtype=np.int64)
+    data = np.zeros(len(items), dtype=np.int64)
+    for k, (col, row, val) in enumerate(items):
+        indptr[col + 1] += 1
+        indices[k] = row
+        data[k] = val
+    indptr = np.cumsum(indptr)
+    return indptr, indices, data, (n_rows, n_cols)
+
+
+def hstack_csc(chunks):
+    """generate_peak_matrix/__init__.py:62-72: scipy hstack of the chunk matrices."""
+    indptr = [np.zeros(1, dtype=np.int64)]
+    indices, data = [], []
+    off = 0
+    n_rows = None
+    for ip, ix, d, shape in chunks:
+        n_rows = shape[0]
+        indptr.append(ip[1:] + off)
+        off += ip[-1]
+        indices.append(ix)
+        data.append(d)
+    indptr = np.concatenate(indptr)
+    return (indptr, np.concatenate(indices) if indices else np.zeros(0, np.int64),
+            np.concatenate(data) if data else np.zeros(0, np.int64), (n_rows, len(indptr) - 1))
+
+
+def feature_names(peak_lines):
+    """cellranger/atac/feature_ref.py:58-68: id = name = 'chr:start-end'."""
+    return ["{}:{}-{}".format(*line.strip("\n").split("\t")) for line in peak_lines]

@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json by EXECUTING THE REFERENCE'S OWN CODE.
+
+Run in the build container only (needs /root/reference; the GPU box never runs
+this).  No reference source is copied into the repository: each stage module is
+read from /root/reference at generation time, its import statements are dropped
+with ``ast``, three mechanical py2->py3 token shims are applied
+(``xrange``->``range``, ``.iteritems()``->``.items()``, open mode ``'rU'``->``'r'``)
+and the module body is exec'd in a namespace whose I/O collaborators (martian,
+ReferenceManager, pysam-backed fragment iterators, pickle/h5 writers) are
+stubs that feed in-memory data and capture results.  The arithmetic that is
+executed -- the pileup slice adds, the Counter, write_chrom_bedgraph,
+cut_site_counter_from_bedgraph, identify_peaks, estimate_final_threshold,
+tenkit Regions bisect, the (barcode, peak) Counter and scipy's COO->CSC -- is
+the reference's, unmodified.
+
+Python-2 comparison semantics are supplied by value wrappers, not code edits:
+  * ``None >= min_counts``   -> False   (count_cut_sites/__init__.py:42,47)
+  * ``"12" < threshold``     -> False   (lib/python/utils.py:112, str vs float)
+
+Usage: python tests/golden/make_golden.py            (writes next to this file)
+"""
+import ast
+import io
+import re
+import json
+import os
+import sys
+import tempfile
+import time
+import types
+from collections import Counter, OrderedDict
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# --------------------------------------------------------------------------- py2 value shims
+class Py2Int(int):
+    """int that answers ``None >= self`` with False like CPython 2."""
+    def __le__(self, other):
+        if other is None:
+            return False
+        return int.__le__(self, other)
+
+
+class Py2Float(float):
+    """float that answers ``some_str < self`` with False like CPython 2
+    (numbers order before every other type)."""
+    def __gt__(self, other):
+        if isinstance(other, str):
+            return False
+        return float.__gt__(self, other)
+
+
+# --------------------------------------------------------------------------- loader
+def load_reference_module(relpath, namespace, keep_funcs=None):
+    src = open(os.path.join(REF, relpath)).read()
+    src = src.replace("xrange(", "range(").replace(".iteritems()", ".items()").replace("'rU'", "'r'")
+    if keep_funcs is not None:
+        # files with py2-only syntax elsewhere cannot be parsed whole: cut out the
+        # wanted top-level def/class blocks by indentation first
+        lines = src.split("\n")
+        picked, i = [], 0
+        while i < len(lines):
+            m = re.match(r"(def|class)\s+(\w+)", lines[i])
+            if m and m.group(2) in keep_funcs:
+                j = i + 1
+                while j < len(lines) and (lines[j].strip() == "" or lines[j][0] in " \t#"):
+                    j += 1
+                picked.append("\n".join(lines[i:j]))
+                i = j
+            else:
+                i += 1
+        src = "\n\n".join(picked)
+    tree = ast.parse(src)
+    body = []
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            continue
+        if keep_funcs is not None:
+            if not (isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in keep_funcs):
+                continue
+        body.append(node)
+    tree.body = body
+    code = compile(tree, os.path.join(REF, relpath), "exec")
+    exec(code, namespace)
+    return namespace
+
+
+class Record(object):
+    """stand-in for martian.Record"""
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def coerce_strings(self):
+        pass
+
+
+class FakePickle(object):
+    def __init__(self):
+        self.store = {}
+
+    def dump(self, obj, f):
+        self.store[f.name] = obj
+
+    def load(self, f):
+        return self.store[f.name]
+
+
+class FakeRefMgr(object):
+    contig_lengths = {}
+    primary = []
+
+    def __init__(self, path):
+        pass
+
+    def get_contig_lengths(self):
+        return dict(FakeRefMgr.contig_lengths)
+
+    def primary_contigs(self, allow_sex_chromosomes=False):
+        return list(FakeRefMgr.primary)
+
+
+# --------------------------------------------------------------------------- stage runners
+def run_count_cut_sites(contig, contig_len, frags, tmpdir):
+    """reference COUNT_CUT_SITES.main on in-memory fragments of one contig."""
+    fp = FakePickle()
+    FakeRefMgr.contig_lengths = {contig: contig_len}
+
+    def parsed_fragments_from_contig(contig=None, filename=None, index=None):
+        for s, e in frags:
+            yield contig, s, e, "BC", 1
+
+    ns = {"np": np, "Counter": Counter, "pickle": fp, "ReferenceManager": FakeRefMgr,
+          "parsed_fragments_from_contig": parsed_fragments_from_contig, "WINDOW_SIZE": 400,
+          "combine_csv": None}
+    load_reference_module("mro/atac/stages/processing/count_cut_sites/__init__.py", ns)
+    # py2: `None >= min_counts` must be False -> rebind the default through a wrapper value
+    wcb = ns["write_chrom_bedgraph"]
+    ns["write_chrom_bedgraph"] = lambda chrom, L, Cuts, out, min_counts=1: wcb(chrom, L, Cuts, out, Py2Int(min_counts))
+    outs = Record(cut_sites=os.path.join(tmpdir, "cs.bedgraph"), count_dict=os.path.join(tmpdir, "cd.pickle"))
+    args = Record(fragments="frag.tsv.gz", fragments_index="frag.tsv.gz.tbi", reference_path="ref", contig=contig)
+    ns["main"](args, outs)
+    cd = fp.store[outs.count_dict]
+    bedgraph = open(outs.cut_sites).read() if outs.cut_sites is not None else None
+    return {int(k): int(v) for k, v in cd.items()}, bedgraph, fp
+
+
+def run_detect_peaks_main(bedgraph_text, contig, threshold, tmpdir):
+    """reference DETECT_PEAKS.main (utils.cut_site_counter_from_bedgraph + identify_peaks)."""
+    ns = {"Counter": Counter, "json": json, "PEAK_MERGE_DISTANCE": 500, "PEAK_ODDS_RATIO": 1 / 5}
+    load_reference_module("lib/python/utils.py", ns, keep_funcs={"cut_site_counter_from_bedgraph"})
+    load_reference_module("mro/atac/stages/processing/detect_peaks/__init__.py", ns,
+                          keep_funcs={"identify_peaks", "main"})
+    bg = os.path.join(tmpdir, "all.bedgraph")
+    with open(bg, "w") as f:
+        f.write(bedgraph_text)
+    outs = Record(peaks=os.path.join(tmpdir, "peaks.bed"), peak_metrics=os.path.join(tmpdir, "pm.json"))
+    # split passes `threshold` as a float through JSON; wrap it for the py2 str<float rule
+    args = Record(cut_sites=bg, threshold=Py2Float(threshold), contig=contig)
+    ns["main"](args, outs)
+    return open(outs.peaks).read(), json.load(open(outs.peak_metrics))
+
+
+def reference_em():
+    sys.path.insert(0, os.path.join(REF, "lib/python"))
+    import analysis.peaks as ref_peaks
+    return ref_peaks
+
+
+def run_generate_peak_matrix_main(peaks_text, barcodes, frag_rows, tmpdir):
+    """reference GENERATE_PEAK_MATRIX.main for one barcode chunk; captures the scipy CSC."""
+    from scipy.sparse import csc_matrix, coo_matrix, hstack
+    captured = {}
+
+    class CountMatrix(object):
+        def __init__(self, feature_ref, bcs, matrix):
+            captured["bcs"] = list(bcs)
+            captured["m"] = matrix
+            captured["features"] = feature_ref
+
+        def save_h5_file(self, filename, sw_version=None):
+            captured["h5"] = filename
+
+    tk_ns = {}
+    load_reference_module("tenkit/lib/python/tenkit/regions.py", tk_ns, keep_funcs={"Regions"})
+    import bisect as _bisect
+    tk_ns["bisect"] = _bisect
+    tk_ns["Region"] = __import__("collections").namedtuple("Region", "start end")
+    load_reference_module("tenkit/lib/python/tenkit/bio_io.py", tk_ns,
+                          keep_funcs={"get_target_regions_dict", "get_target_regions"})
+    tk_bio = types.SimpleNamespace(get_target_regions=tk_ns["get_target_regions"])
+
+    def open_fragment_file(filename):
+        for r in frag_rows:
+            yield r
+
+    feat_ns = {}
+    ns = {"os": os, "csc_matrix": csc_matrix, "coo_matrix": coo_matrix, "hstack": hstack,
+          "OrderedDict": OrderedDict, "Counter": Counter,
+          "utils": types.SimpleNamespace(generate_genome_tag=lambda p: ["GRCh38"], get_chunks=None),
+          "tk_bio": tk_bio, "cr_matrix": types.SimpleNamespace(CountMatrix=CountMatrix),
+          "atac_feature_ref": types.SimpleNamespace(
+              from_peaks_bed=lambda path, genomes: ["{}:{}-{}".format(*l.strip("\n").split("\t")) for l in open(path)]),
+          "atac_matrix": None, "cr_lib_constants": None,
+          "open_fragment_file": open_fragment_file,
+          "martian": types.SimpleNamespace(get_pipelines_version=lambda: "golden")}
+    load_reference_module("mro/atac/stages/processing/generate_peak_matrix/__init__.py", ns)
+    pk = os.path.join(tmpdir, "peaks_in.bed")
+    with open(pk, "w") as f:
+        f.write(peaks_text)
+    bcf = os.path.join(tmpdir, "barcodes.txt")
+    with open(bcf, "w") as f:
+        f.write("\n".join(barcodes))
+    args = Record(fragments="frag.tsv.gz", peaks=pk, barcodes=bcf, reference_path="ref")
+    outs = Record(raw_matrix=os.path.join(tmpdir, "m.h5"), raw_matrix_mex=None)
+    ns["main"](args, outs)
+    if outs.raw_matrix is None:
+        return None
+    m = captured["m"]
+    assert m.has_sorted_indices or True
+    m.sort_indices()
+    return dict(indptr=m.indptr.tolist(), indices=m.indices.tolist(), data=m.data.tolist(),
+                shape=list(m.shape), barcodes=captured["bcs"], features=captured["features"])
+
+
+# --------------------------------------------------------------------------- case builders
+def random_contig_case(rng, L, n_frag, piles):
+    starts = rng.integers(0, L, size=n_frag)
+    lens = np.clip(rng.normal(250, 150, size=n_frag).astype(int), 0, 1200)
+    stops = np.minimum(starts + lens, L)
+    frags = list(zip(starts.tolist(), stops.tolist()))
+    for _ in range(piles):
+        s = int(rng.integers(0, L))
+        e = min(L, s + int(rng.integers(0, 600)))
+        frags += [(s, e)] * int(rng.integers(2, 25))
+    frags.sort()
+    return frags
+
+
+def make_cut_site_cases(tmpdir):
+    rng = np.random.default_rng(20191)
+    cases = []
+    fixed = [
+        ("GV1_zero_gap", 10000, [(2000, 2000)] * 4 + [(5000, 5000)] * 4, [5, 8, 9]),
+        ("GV2_single", 5000, [(1000, 1500)], [1, 2]),
+        ("edge_clip", 1000, [(0, 0), (0, 1000), (999, 1000), (1000, 1000), (5, 400), (5, 400)], [1, 2, 3]),
+        ("empty", 3000, [], [1]),
+        ("zero_gap_unequal", 12000, [(2000, 2000)] * 4 + [(6000, 6000)] * 5, [4, 5]),
+        ("zero_gap_chain", 20000, [(2000, 2000)] * 6 + [(5000, 5000)] * 6 + [(9000, 9000)] * 6 + [(9001, 15000)] * 3, [3, 6, 7, 12]),
+        ("merge_boundary", 8000, [(1000, 1000)] * 5 + [(1901, 1901)] * 5 + [(2803, 2803)] * 5, [5]),
+    ]
+    for name, L, frags, thrs in fixed:
+        cases.append((name, L, sorted(frags), thrs))
+    for k in range(14):
+        L = int(rng.integers(3000, 20000))
+        frags = random_contig_case(rng, L, int(rng.integers(5, 400)), int(rng.integers(0, 6)))
+        thrs = sorted(set(int(t) for t in rng.integers(1, 20, size=3)))
+        cases.append(("rand%02d" % k, L, frags, thrs))
+    out = []
+    for name, L, frags, thrs in cases:
+        cd, bedgraph, _ = run_count_cut_sites("chr1", L, frags, tmpdir)
+        peaks = {}
+        if bedgraph is not None:
+            for t in thrs:
+                text, metrics = run_detect_peaks_main(bedgraph, "chr1", float(t), tmpdir)
+                peaks[str(t)] = dict(bed=text, total_peaks_detected=metrics["total_peaks_detected"])
+        out.append(dict(name=name, contig="chr1", contig_len=L, fragments=[list(f) for f in frags],
+                        count_dict={str(k): v for k, v in sorted(cd.items())}, bedgraph=bedgraph, peaks=peaks))
+    return out
+
+
+def gv4_histogram():
+    """SURVEY.md section 8c GV4."""
+    rng = np.random.default_rng(0)
+    L = 20000000
+    centres = rng.integers(1000, L - 1000, size=2000)
+    normals = rng.normal(0, 150, size=(2000, 300))
+    uniforms = rng.integers(0, L, size=400000)
+    cuts = np.concatenate([uniforms, np.clip((centres[:, None] + normals.astype(int)).ravel(), 0, L - 1)])
+    c = np.bincount(cuts, minlength=L + 1)
+    S = np.concatenate(([0], np.cumsum(c)))
+    p = np.arange(L)
+    W = S[np.minimum(p + 201, L + 1)] - S[np.maximum(p - 200, 0)]
+    b = np.bincount(W[W > 0])
+    return {int(k): int(b[k]) for k in np.nonzero(b)[0]}
+
+
+def synth_histogram(seed, L, n_uniform, n_peaks, per_peak, sd):
+    rng = np.random.default_rng(seed)
+    centres = rng.integers(1000, L - 1000, size=n_peaks)
+    cuts = np.concatenate([rng.integers(0, L, size=n_uniform),
+                           np.clip((centres[:, None] + rng.normal(0, sd, size=(n_peaks, per_peak)).astype(int)).ravel(), 0, L - 1)])
+    c = np.bincount(cuts, minlength=L + 1)
+    S = np.concatenate(([0], np.cumsum(c)))
+    p = np.arange(L)
+    W = S[np.minimum(p + 201, L + 1)] - S[np.maximum(p - 200, 0)]
+    b = np.bincount(W[W > 0])
+    return {int(k): int(b[k]) for k in np.nonzero(b)[0]}
+
+
+def make_em_cases():
+    ref = reference_em()
+    cases = []
+    hists = [("GV4", gv4_histogram()),
+             ("all_above_15", synth_histogram(11, 4000000, 600000, 800, 400, 120)),
+             ("medium", synth_histogram(14, 5000000, 250000, 800, 400, 120)),
+             ("sparse", synth_histogram(12, 8000000, 90000, 500, 250, 200)),
+             ("many_peaks", synth_histogram(13, 6000000, 300000, 3000, 150, 100)),
+             ("gate_few_bins", {k: 100000 for k in range(1, 20)}),
+             ("gate_few_bases", {k: 10 for k in range(1, 60)})]
+    for name, cd in hists:
+        t0 = time.time()
+        try:
+            thr, params = ref.estimate_final_threshold(dict(cd), 1 / 5)
+        except Exception as exc:      # the reference itself fails on this histogram: record how
+            print("EM case %-14s raises %s" % (name, type(exc).__name__), flush=True)
+            cases.append(dict(name=name, values=sorted(cd), weights=[cd[k] for k in sorted(cd)],
+                              raises=type(exc).__name__))
+            continue
+        dt = time.time() - t0
+        print("EM case %-14s bins=%4d thr=%s  %.1fs" % (name, len(cd), thr, dt), flush=True)
+        cases.append(dict(name=name, values=sorted(cd), weights=[cd[k] for k in sorted(cd)],
+                          threshold=None if thr is None else int(thr),
+                          params=None if params is None else [float(x) for x in params]))
+    return cases
+
+
+def make_matrix_cases(tmpdir):
+    rng = np.random.default_rng(77)
+    cases = []
+    gv3 = dict(name="GV3",
+               peaks="chr1\t100\t200\nchr1\t300\t400\nchr2\t50\t60\n",
+               barcodes=["A", "B", "C", "D"],
+               frags=[("chr1", 150, 350, "A", 1), ("chr1", 100, 200, "A", 3), ("chr1", 199, 300, "B", 1),
+                      ("chr1", 120, 180, "A", 1), ("chr2", 10, 50, "C", 1), ("chr3", 5, 9, "D", 1),
+                      ("chr2", 59, 60, "B", 2)])
+    cases.append(gv3)
+    touching = dict(name="touching_peaks",
+                    peaks="chr1\t100\t200\nchr1\t200\t300\nchr2\t0\t10\n",
+                    barcodes=["X-1", "Y-1"],
+                    frags=[("chr1", 199, 200, "X-1", 1), ("chr1", 200, 299, "X-1", 1), ("chr1", 300, 301, "Y-1", 1),
+                           ("chr2", 0, 9, "Y-1", 1), ("chr2", 9, 10, "Y-1", 1), ("chr1", 99, 100, "Y-1", 1)])
+    cases.append(touching)
+    for k in range(6):
+        contigs = ["chr1", "chr2", "chrX"][: int(rng.integers(1, 4))]
+        peak_rows = []
+        for c in contigs:
+            pos = 0
+            for _ in range(int(rng.integers(1, 30))):
+                pos += int(rng.integers(1, 800))
+                ln = int(rng.integers(1, 900))
+                peak_rows.append((c, pos, pos + ln))
+                pos += ln + int(rng.integers(0, 3) == 0)   # sometimes touching the next one
+        n_bc = int(rng.integers(1, 12))
+        universe = ["".join(rng.choice(list("ACGT"), size=16)) + "-1" for _ in range(n_bc + 2)]
+        chunk_bcs = universe[:n_bc]
+        frags = []
+        for _ in range(int(rng.integers(10, 500))):
+            c = contigs[int(rng.integers(0, len(contigs)))]
+            s = int(rng.integers(0, 30000))
+            e = s + int(rng.integers(0, 1200))
+            frags.append((c, s, e, universe[int(rng.integers(0, len(universe)))], int(rng.integers(1, 5))))
+        frags.sort(key=lambda r: (contigs.index(r[0]), r[1], r[2]))
+        cases.append(dict(name="rand%02d" % k, peaks="".join("%s\t%d\t%d\n" % r for r in peak_rows),
+                          barcodes=chunk_bcs, frags=frags))
+    out = []
+    for case in cases:
+        res = run_generate_peak_matrix_main(case["peaks"], case["barcodes"], case["frags"], tmpdir)
+        out.append(dict(name=case["name"], peaks=case["peaks"], barcodes=case["barcodes"],
+                        fragments=[list(r) for r in case["frags"]], result=res))
+    return out
+
+
+def main():
+    only = set(sys.argv[1:])
+    with tempfile.TemporaryDirectory() as tmpdir:
+        if not only or "cut_sites" in only:
+            with open(os.path.join(HERE, "cut_sites.json"), "w") as f:
+                json.dump(make_cut_site_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "matrix" in only:
+            with open(os.path.join(HERE, "matrix.json"), "w") as f:
+                json.dump(make_matrix_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "em" in only:
+            with open(os.path.join(HERE, "em.json"), "w") as f:
+                json.dump(make_em_cases(), f, separators=(",", ":"))
+
+
+if __name__ == "__main__":
+    main()
