@@ -1,0 +1,321 @@
+"""ctypes binding of libcratac.so (include/cratac.h).
+
+Modelled on the reference's one ctypes shim,
+tenkit/lib/python/striped_smith_waterman/ssw_wrap.py:54-72: ``cdll.LoadLibrary``,
+explicit ``argtypes``/``restype`` for every symbol, an opaque handle and an
+explicit destroy.  There is no CPU fallback: a missing library or a missing
+CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.environ.get("CRATAC_LIB", os.path.join(_PKG_ROOT, "lib", "libcratac.so"))
+
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_vp = ctypes.c_void_p
+c_cp = ctypes.c_char_p
+P = ctypes.POINTER
+
+
+class CratacError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libcratac error %d: %s" % (code, message))
+        self.code = code
+
+
+ERR_CUDA, ERR_ARG, ERR_PARSE, ERR_UNSORTED, ERR_CONTIG, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
+ERR_EM_ZERODIV, ERR_EM_INDEX, ERR_PEAKS_OVERLAP, ERR_INTERNAL, ERR_IO = -7, -8, -9, -10, -11
+BC_ORDER_PY2SET, BC_ORDER_FIRST_SEEN, BC_ORDER_SORTED = 0, 1, 2
+
+
+class RunResult(ctypes.Structure):
+    _fields_ = [("n_fragments", c_i64), ("n_barcodes", c_i64), ("n_bins", c_i64), ("threshold", c_i64),
+                ("has_params", c_i64), ("n_peaks", c_i64), ("nnz", c_i64), ("em_iterations", c_i64),
+                ("em_inner_iterations", c_i64), ("params", c_dbl * 6)]
+
+
+# symbol -> (restype, argtypes); every entry of include/cratac.h
+SIGNATURES = {
+    "cratac_last_error": (c_cp, []),
+    "cratac_abi_version": (c_int, []),
+    "cratac_create": (c_int, [c_int, c_int, P(c_cp), P(c_i64), P(c_i32), P(c_vp)]),
+    "cratac_destroy": (None, [c_vp]),
+    "cratac_set_option": (c_int, [c_vp, c_cp, c_i64]),
+    "cratac_launch_count": (c_i64, [c_vp, c_int]),
+    "cratac_synchronize": (c_int, [c_vp]),
+    "cratac_decode_host": (c_int, [c_vp, c_vp, c_i64]),
+    "cratac_decode_device": (c_int, [c_vp, c_vp, c_i64]),
+    "cratac_set_fragments": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_cp)]),
+    "cratac_num_fragments": (c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "cratac_get_fragments": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cratac_get_barcodes": (c_int, [c_vp, c_vp, c_i64]),
+    "cratac_max_barcode_len": (c_int, [c_vp, P(c_i64)]),
+    "cratac_count_cut_sites": (c_int, [c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
+    "cratac_window_counts": (c_int, [c_vp, c_int, c_vp]),
+    "cratac_bedgraph_rows": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
+    "cratac_fit_threshold": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, P(c_dbl), P(c_int), P(c_i64), P(c_i64), P(c_i64)]),
+    "cratac_fit_threshold_device": (c_int, [c_vp, c_dbl, P(c_dbl), P(c_int), P(c_i64)]),
+    "cratac_call_peaks": (c_int, [c_vp, c_i64, P(c_i64)]),
+    "cratac_get_peaks": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cratac_set_peaks": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cratac_peak_matrix": (c_int, [c_vp, P(c_i64)]),
+    "cratac_get_matrix": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cratac_matrix_device": (c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp)]),
+    "cratac_hist_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
+    "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
+    "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
+    "cratac_py2_set_order": (c_int, [c_i64, P(c_cp), c_vp]),
+    "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
+    "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libcratac.so and declare every signature.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libcratac.so not found at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C cellranger-atac_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.cdll.LoadLibrary(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CratacError(rc, load().cratac_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(c_vp)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context(object):
+    """One GPU context.  contigs: list of (name, length) in genome.fa.fai order."""
+
+    def __init__(self, contigs, primary=None, device=0):
+        lib = load()
+        self._lib = lib
+        self.contig_names = [c[0] for c in contigs]
+        self.contig_lens = [int(c[1]) for c in contigs]
+        n = len(contigs)
+        names = (c_cp * n)(*[s.encode("ascii") for s in self.contig_names])
+        lens = (c_i64 * n)(*self.contig_lens)
+        if primary is None:
+            prim = None
+        else:
+            pset = set(primary)
+            prim = (c_i32 * n)(*[1 if s in pset else 0 for s in self.contig_names])
+        self.primary = list(primary) if primary is not None else list(self.contig_names)
+        h = c_vp()
+        check(lib.cratac_create(int(device), n, names, lens, prim, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cratac_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_option(self, key, value):
+        check(self._lib.cratac_set_option(self._h, key.encode(), int(value)))
+
+    def launch_count(self, reset=False):
+        return int(self._lib.cratac_launch_count(self._h, 1 if reset else 0))
+
+    def synchronize(self):
+        check(self._lib.cratac_synchronize(self._h))
+
+    # ---- decode
+    def decode_host(self, text):
+        """text: bytes / bytearray / numpy uint8 array / (address, nbytes) of decompressed fragments.tsv."""
+        addr, n, keep = _buffer(text)
+        check(self._lib.cratac_decode_host(self._h, addr, n))
+        return self.num_fragments()
+
+    def decode_device(self, dev_ptr, nbytes):
+        check(self._lib.cratac_decode_device(self._h, c_vp(int(dev_ptr)), int(nbytes)))
+        return self.num_fragments()
+
+    def set_fragments(self, chrom, start, end, bc, dup, barcodes):
+        chrom, start, end, bc = _i32(chrom), _i32(start), _i32(end), _i32(bc)
+        dup = None if dup is None else _i32(dup)
+        nb = len(barcodes)
+        arr = (c_cp * max(nb, 1))(*[b.encode("ascii") for b in barcodes])
+        check(self._lib.cratac_set_fragments(self._h, chrom.size, _ptr(chrom), _ptr(start), _ptr(end), _ptr(bc), _ptr(dup), nb, arr))
+
+    def num_fragments(self):
+        n, b = c_i64(), c_i64()
+        check(self._lib.cratac_num_fragments(self._h, ctypes.byref(n), ctypes.byref(b)))
+        return n.value, b.value
+
+    def get_fragments(self):
+        n, _ = self.num_fragments()
+        out = [np.zeros(n, dtype=np.int32) for _ in range(5)]
+        check(self._lib.cratac_get_fragments(self._h, *[_ptr(a) for a in out]))
+        return dict(chrom=out[0], start=out[1], end=out[2], bc=out[3], dup=out[4])
+
+    def get_barcodes(self):
+        ln = c_i64()
+        check(self._lib.cratac_max_barcode_len(self._h, ctypes.byref(ln)))
+        _, nb = self.num_fragments()
+        stride = ln.value + 1
+        buf = np.zeros(max(nb, 1) * stride, dtype=np.uint8)
+        check(self._lib.cratac_get_barcodes(self._h, _ptr(buf), stride))
+        raw = buf.tobytes()
+        return [raw[j * stride:(j + 1) * stride].split(b"\0", 1)[0].decode("ascii") for j in range(nb)]
+
+    # ---- COUNT_CUT_SITES
+    def count_cut_sites(self):
+        """-> (values int64[], weights int64[]) of Counter(v for v in Cuts if v > 0), ascending."""
+        cap = 1 << 20
+        v = np.zeros(cap, dtype=np.int64)
+        w = np.zeros(cap, dtype=np.int64)
+        n = c_i64()
+        check(self._lib.cratac_count_cut_sites(self._h, _ptr(v), _ptr(w), cap, ctypes.byref(n)))
+        return v[:n.value].copy(), w[:n.value].copy()
+
+    def window_counts(self, contig):
+        ci = self.contig_names.index(contig) if isinstance(contig, str) else int(contig)
+        W = np.zeros(self.contig_lens[ci], dtype=np.int32)
+        check(self._lib.cratac_window_counts(self._h, ci, _ptr(W)))
+        return W
+
+    def bedgraph_rows(self, contig):
+        ci = self.contig_names.index(contig) if isinstance(contig, str) else int(contig)
+        n = c_i64()
+        z = np.zeros(1, dtype=np.int64)
+        check(self._lib.cratac_bedgraph_rows(self._h, ci, _ptr(z), _ptr(z), _ptr(z), 0, ctypes.byref(n)))
+        s, e, c = (np.zeros(max(n.value, 1), dtype=np.int64) for _ in range(3))
+        check(self._lib.cratac_bedgraph_rows(self._h, ci, _ptr(s), _ptr(e), _ptr(c), n.value, ctypes.byref(n)))
+        return s[:n.value], e[:n.value], c[:n.value]
+
+    # ---- threshold
+    def fit_threshold(self, values, weights, odds_ratio=0.2):
+        """-> (threshold or None, params tuple or None, stats dict) like estimate_final_threshold."""
+        values = np.ascontiguousarray(values, dtype=np.int64)
+        weights = np.ascontiguousarray(weights, dtype=np.int64)
+        params = (c_dbl * 6)()
+        has = c_int()
+        thr, it, inner = c_i64(), c_i64(), c_i64()
+        check(self._lib.cratac_fit_threshold(self._h, _ptr(values), _ptr(weights), values.size, float(odds_ratio), params,
+                                             ctypes.byref(has), ctypes.byref(thr), ctypes.byref(it), ctypes.byref(inner)))
+        return _fit_result(thr.value, has.value, params, it.value, inner.value)
+
+    def fit_threshold_device(self, odds_ratio=0.2):
+        params = (c_dbl * 6)()
+        has = c_int()
+        thr = c_i64()
+        check(self._lib.cratac_fit_threshold_device(self._h, float(odds_ratio), params, ctypes.byref(has), ctypes.byref(thr)))
+        return _fit_result(thr.value, has.value, params, None, None)
+
+    # ---- peaks
+    def call_peaks(self, threshold=None):
+        n = c_i64()
+        check(self._lib.cratac_call_peaks(self._h, -1 if threshold is None else int(threshold), ctypes.byref(n)))
+        return self.get_peaks(n.value)
+
+    def get_peaks(self, n):
+        c, s, e = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        if n:
+            check(self._lib.cratac_get_peaks(self._h, _ptr(c), _ptr(s), _ptr(e)))
+        return c, s, e
+
+    def set_peaks(self, chrom, start, end):
+        chrom, start, end = _i32(chrom), _i32(start), _i32(end)
+        check(self._lib.cratac_set_peaks(self._h, chrom.size, _ptr(chrom), _ptr(start), _ptr(end)))
+
+    # ---- matrix
+    def peak_matrix(self):
+        """-> (indptr int64[B+1], indices int64[nnz], data int32[nnz]) canonical CSC, rows = peaks."""
+        nnz = c_i64()
+        check(self._lib.cratac_peak_matrix(self._h, ctypes.byref(nnz)))
+        return self.get_matrix(nnz.value)
+
+    def get_matrix(self, nnz):
+        _, nb = self.num_fragments()
+        indptr = np.zeros(nb + 1, dtype=np.int64)
+        indices = np.zeros(nnz, dtype=np.int64)
+        data = np.zeros(nnz, dtype=np.int32)
+        check(self._lib.cratac_get_matrix(self._h, _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    # ---- whole path
+    def run(self, text=None, odds_ratio=0.2, device_ptr=None, nbytes=None):
+        res = RunResult()
+        if device_ptr is not None:
+            check(self._lib.cratac_run(self._h, c_vp(int(device_ptr)), int(nbytes), 1, float(odds_ratio), ctypes.byref(res)))
+        elif text is not None:
+            addr, n, keep = _buffer(text)
+            check(self._lib.cratac_run(self._h, addr, n, 0, float(odds_ratio), ctypes.byref(res)))
+        else:
+            check(self._lib.cratac_run_from_fragments(self._h, float(odds_ratio), ctypes.byref(res)))
+        return res
+
+    def encode_text_device(self, n, d_chrom, d_start, d_end, d_seq, d_dup, d_out, cap):
+        nb = c_i64()
+        check(self._lib.cratac_encode_text_device(self._h, int(n), c_vp(int(d_chrom)), c_vp(int(d_start)), c_vp(int(d_end)),
+                                                  c_vp(int(d_seq)), c_vp(int(d_dup)), c_vp(int(d_out)) if d_out else None,
+                                                  int(cap), ctypes.byref(nb)))
+        return nb.value
+
+
+def _fit_result(thr, has, params, it, inner):
+    stats = dict(em_iterations=it, inner_iterations=inner)
+    if has == 0:
+        return thr, None, stats
+    p = tuple(float(x) for x in params)
+    return (None if has == 2 else thr), p, stats
+
+
+def _buffer(text):
+    """-> (c_void_p address, nbytes, keepalive)."""
+    if isinstance(text, tuple):
+        return c_vp(int(text[0])), int(text[1]), None
+    if isinstance(text, np.ndarray):
+        a = np.ascontiguousarray(text).view(np.uint8)
+        return a.ctypes.data_as(c_vp), a.size, a
+    if isinstance(text, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(text, dtype=np.uint8)
+        return a.ctypes.data_as(c_vp), a.size, a
+    raise TypeError("unsupported text buffer type %r" % type(text))
+
+
+def py2_set_order(keys):
+    """CPython-2.7 list(set(keys)) order; keys given in insertion order -> list of indices."""
+    lib = load()
+    n = len(keys)
+    arr = (c_cp * max(n, 1))(*[k.encode("latin-1") if isinstance(k, str) else k for k in keys])
+    out = np.zeros(max(n, 1), dtype=np.int64)
+    check(lib.cratac_py2_set_order(n, arr, _ptr(out)))
+    return out[:n].tolist()
+
+
+def inflate_file(path, threads=None):
+    """Multi-threaded BGZF / gzip inflate -> numpy uint8 array."""
+    lib = load()
+    threads = threads or (os.cpu_count() or 1)
+    n = c_i64()
+    check(lib.cratac_inflate_file(path.encode(), threads, None, 0, ctypes.byref(n)))
+    out = np.empty(max(n.value, 1), dtype=np.uint8)
+    check(lib.cratac_inflate_file(path.encode(), threads, _ptr(out), out.size, ctypes.byref(n)))
+    return out[:n.value]

@@ -1,0 +1,664 @@
+// C ABI of libcratac (include/cratac.h): context management, host<->device plumbing, whole-path driver.
+#include <stdarg.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+
+#include "common.cuh"
+
+namespace cratac {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap && p != nullptr) return CRATAC_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    want = (want + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); p = nullptr; return CRATAC_ERR_CUDA; }
+    cap = want;
+    return CRATAC_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+}
+
+int sync_status(Ctx* c) {
+    CRATAC_CUDA(cudaMemcpyAsync(c->h_status, c->d_status.p, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t err = c->h_status[ST_ERROR];
+    if (err == 0) return CRATAC_OK;
+    int64_t arg = c->h_status[ST_ERROR_ARG];
+    switch ((int)err) {
+        case CRATAC_ERR_UNSORTED: set_error("fragment %lld is out of order: fragments must be sorted by (reference contig order, start)", (long long)arg); break;
+        case CRATAC_ERR_PARSE: set_error("malformed fragments line %lld", (long long)(arg + 1)); break;
+        case CRATAC_ERR_CONTIG: set_error("fragments line %lld: contig is not in the reference", (long long)(arg + 1)); break;
+        case CRATAC_ERR_CAPACITY: set_error("device table overflow (detail %lld)", (long long)arg); break;
+        case CRATAC_ERR_EM_ZERODIV: set_error("threshold fit: a mixture component received no weight (the reference raises ZeroDivisionError here)"); break;
+        case CRATAC_ERR_EM_INDEX: set_error("threshold fit: fewer than two distinct window counts above 15 (the reference raises IndexError here)"); break;
+        default: set_error("device error %lld (detail %lld)", (long long)err, (long long)arg);
+    }
+    cudaMemsetAsync(c->d_status.p, 0, sizeof(int64_t) * 2, c->stream);
+    return (int)err;
+}
+
+int pileup_tile_bases();                                                                 // pileup.cu
+int dump_window_counts(Ctx* c, int contig, int32_t* d_W);                                // pileup.cu
+int compute_max_len(Ctx* c);                                                             // decode.cu
+int fit_threshold_arrays(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n, double odds_ratio);   // em.cu
+void py2_set_order(const std::vector<std::string>& keys, std::vector<int64_t>& order);   // decode.cu
+int encode_text(Ctx* c, int64_t n, const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, const uint32_t* d_seq,
+                const int32_t* d_dup, char* d_out, int64_t cap, int64_t* nbytes);        // decode.cu
+
+static int upload_i64(Ctx* c, DevBuf& b, const std::vector<int64_t>& v) {
+    CRATAC_TRY(b.reserve(sizeof(int64_t) * std::max<size_t>(v.size(), 1)));
+    CRATAC_CUDA(cudaMemcpyAsync(b.p, v.data(), sizeof(int64_t) * v.size(), cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    return CRATAC_OK;
+}
+
+static int fetch_peak_count(Ctx* c) {
+    if (!c->peaks_on_device_count) return CRATAC_OK;
+    CRATAC_TRY(sync_status(c));
+    c->n_peaks = c->h_status[ST_N_PEAKS];
+    c->peaks_on_device_count = false;
+    return CRATAC_OK;
+}
+
+}  // namespace cratac
+
+using namespace cratac;
+
+struct cratac_ctx { Ctx c; };
+
+extern "C" {
+
+const char* cratac_last_error(void) { return g_err; }
+int cratac_abi_version(void) { return 1; }
+
+int cratac_create(int device, int n_contigs, const char* const* contig_names, const int64_t* contig_lens, const int32_t* is_primary,
+                  cratac_ctx** out) {
+    if (!out || n_contigs <= 0 || !contig_names || !contig_lens) { set_error("cratac_create: bad arguments"); return CRATAC_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s); libcratac has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return CRATAC_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return CRATAC_ERR_ARG; }
+    CRATAC_CUDA(cudaSetDevice(device));
+    cratac_ctx* h = new cratac_ctx();
+    Ctx* c = &h->c;
+    c->device = device;
+    c->n_contigs = n_contigs;
+    c->tile_bases = pileup_tile_bases();
+    c->bc_table_cap = 1 << 22;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return CRATAC_ERR_CUDA; }
+    int64_t base = 0, tiles = 0, pidx = 0;
+    for (int i = 0; i < n_contigs; i++) {
+        c->contig_names.push_back(contig_names[i]);
+        c->contig_lens.push_back(contig_lens[i]);
+        c->contig_base.push_back(base);
+        c->contig_tile_off.push_back(tiles);
+        c->contig_pidx_off.push_back(pidx);
+        base += contig_lens[i] + CONTIG_GAP;
+        bool primary = is_primary ? is_primary[i] != 0 : true;
+        if (primary && contig_lens[i] > 0) tiles += (contig_lens[i] + c->tile_bases - 1) / c->tile_bases;
+        pidx += ((contig_lens[i] + HALF_WINDOW + 1) >> POS_INDEX_SHIFT) + 3;
+    }
+    c->contig_base.push_back(base);
+    c->contig_tile_off.push_back(tiles);
+    c->contig_pidx_off.push_back(pidx);
+    int rc = CRATAC_OK;
+    if ((rc = c->d_status.reserve(sizeof(int64_t) * ST_SLOTS)) != CRATAC_OK) { delete h; return rc; }
+    cudaMemsetAsync(c->d_status.p, 0, sizeof(int64_t) * ST_SLOTS, c->stream);
+    if (cudaMallocHost(&c->h_status, sizeof(int64_t) * ST_SLOTS) != cudaSuccess) { set_error("cudaMallocHost failed"); delete h; return CRATAC_ERR_CUDA; }
+    memset(c->h_status, 0, sizeof(int64_t) * ST_SLOTS);
+    if ((rc = upload_i64(c, c->d_contig_lens, c->contig_lens)) || (rc = upload_i64(c, c->d_contig_base, c->contig_base)) ||
+        (rc = upload_i64(c, c->d_contig_tile_off, c->contig_tile_off)) || (rc = upload_i64(c, c->d_contig_pidx_off, c->contig_pidx_off))) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return CRATAC_OK;
+}
+
+void cratac_destroy(cratac_ctx* h) {
+    if (!h) return;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->d_contig_lens, &c->d_contig_base, &c->d_contig_tile_off, &c->d_contig_pidx_off, &c->d_contig_table, &c->d_chrom,
+                      &c->d_start, &c->d_end, &c->d_bc, &c->d_dup, &c->d_contig_frag_off, &c->d_pos_index, &c->d_text_own, &c->d_tile_counts,
+                      &c->d_tile_offsets, &c->d_bc_keys, &c->d_bc_first, &c->d_bc_textoff, &c->d_slot_to_dense, &c->d_dense_key, &c->d_dense_first,
+                      &c->d_dense_textoff, &c->d_dense_to_col, &c->d_col_to_dense, &c->d_hist, &c->d_hist_values, &c->d_hist_weights,
+                      &c->d_em_params, &c->d_em_work, &c->d_chain, &c->d_tile_summary, &c->d_run_start, &c->d_run_end, &c->d_bridge, &c->d_fill,
+                      &c->d_peak_chrom, &c->d_peak_start, &c->d_peak_end, &c->d_peak_row, &c->d_peak_off, &c->d_bc_hits, &c->d_seg_off,
+                      &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
+                      &c->d_status, &c->d_scan_tmp};
+    for (DevBuf* b : bufs) b->release();
+    if (c->h_status) cudaFreeHost(c->h_status);
+    cudaStreamDestroy(c->stream);
+    delete h;
+}
+
+int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
+    if (!h || !key) return CRATAC_ERR_ARG;
+    Ctx* c = &h->c;
+    if (!strcmp(key, "barcode_order")) { c->bc_order = (int)value; c->bc_ready = c->bc_ready && !c->bc_is_slot; return CRATAC_OK; }
+    if (!strcmp(key, "barcode_table_slots")) {
+        int64_t cap = 16;
+        while (cap < value) cap <<= 1;
+        c->bc_table_cap = (int)cap;
+        return CRATAC_OK;
+    }
+    if (!strcmp(key, "run_capacity")) { c->run_cap = value; return CRATAC_OK; }
+    set_error("unknown option '%s'", key);
+    return CRATAC_ERR_ARG;
+}
+
+int64_t cratac_launch_count(cratac_ctx* h, int reset) {
+    int64_t n = h->c.launches;
+    if (reset) h->c.launches = 0;
+    return n;
+}
+
+int cratac_synchronize(cratac_ctx* h) {
+    CRATAC_CUDA(cudaSetDevice(h->c.device));
+    CRATAC_CUDA(cudaStreamSynchronize(h->c.stream));
+    return CRATAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decode
+int cratac_decode_device(cratac_ctx* h, const char* d_text, int64_t nbytes) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (nbytes < 0 || (nbytes > 0 && !d_text)) { set_error("cratac_decode_device: bad buffer"); return CRATAC_ERR_ARG; }
+    c->bc_is_slot = true;
+    CRATAC_TRY(decode_text(c, d_text, nbytes));
+    return CRATAC_OK;
+}
+
+int cratac_decode_host(cratac_ctx* h, const char* text, int64_t nbytes) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (nbytes < 0 || (nbytes > 0 && !text)) { set_error("cratac_decode_host: bad buffer"); return CRATAC_ERR_ARG; }
+    CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
+    if (nbytes > 0) CRATAC_CUDA(cudaMemcpyAsync(c->d_text_own.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
+    c->bc_is_slot = true;
+    return decode_text(c, c->d_text_own.as<char>(), nbytes);
+}
+
+int cratac_set_fragments(cratac_ctx* h, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end, const int32_t* bc,
+                         const int32_t* dup, int64_t n_barcodes, const char* const* barcodes) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (n < 0 || n_barcodes < 0 || (n > 0 && (!chrom || !start || !end || !bc))) { set_error("cratac_set_fragments: bad arguments"); return CRATAC_ERR_ARG; }
+    size_t nn = (size_t)std::max<int64_t>(n, 1);
+    CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));
+    CRATAC_TRY(c->d_bc.reserve(4 * nn)); CRATAC_TRY(c->d_dup.reserve(4 * nn));
+    if (n > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_chrom.p, chrom, 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_start.p, start, 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_end.p, end, 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_bc.p, bc, 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        if (dup) CRATAC_CUDA(cudaMemcpyAsync(c->d_dup.p, dup, 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        else CRATAC_CUDA(cudaMemsetAsync(c->d_dup.p, 0, 4 * nn, c->stream));
+    }
+    c->n_fragments = n;
+    c->n_barcodes = n_barcodes;
+    c->bc_is_slot = false;
+    c->barcodes.clear();
+    for (int64_t j = 0; j < n_barcodes; j++) c->barcodes.push_back(barcodes ? barcodes[j] : "");
+    size_t nb = (size_t)std::max<int64_t>(n_barcodes, 1);
+    std::vector<int32_t> ident(nb);
+    for (size_t j = 0; j < nb; j++) ident[j] = (int32_t)j;
+    CRATAC_TRY(c->d_col_to_dense.reserve(4 * nb)); CRATAC_TRY(c->d_dense_to_col.reserve(4 * nb));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_col_to_dense.p, ident.data(), 4 * nb, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_dense_to_col.p, ident.data(), 4 * nb, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->bc_ready = true;
+    CRATAC_TRY(compute_max_len(c));
+    return finalize_fragments(c);
+}
+
+int cratac_num_fragments(cratac_ctx* h, int64_t* n_fragments, int64_t* n_barcodes) {
+    if (n_fragments) *n_fragments = h->c.n_fragments;
+    if (n_barcodes) *n_barcodes = h->c.n_barcodes;
+    return CRATAC_OK;
+}
+
+int cratac_get_fragments(cratac_ctx* h, int32_t* chrom, int32_t* start, int32_t* end, int32_t* bc, int32_t* dup) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    size_t nn = (size_t)c->n_fragments;
+    if (nn == 0) return CRATAC_OK;
+    if (chrom) CRATAC_CUDA(cudaMemcpyAsync(chrom, c->d_chrom.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream));
+    if (start) CRATAC_CUDA(cudaMemcpyAsync(start, c->d_start.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream));
+    if (end) CRATAC_CUDA(cudaMemcpyAsync(end, c->d_end.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream));
+    if (dup) CRATAC_CUDA(cudaMemcpyAsync(dup, c->d_dup.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream));
+    if (bc) {
+        CRATAC_TRY(build_barcodes(c));
+        CRATAC_CUDA(cudaMemcpyAsync(bc, c->d_bc.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream));
+        if (c->bc_is_slot) {
+            std::vector<int32_t> s2d((size_t)c->bc_table_cap), d2c((size_t)std::max<int64_t>(c->n_barcodes, 1));
+            CRATAC_CUDA(cudaMemcpyAsync(s2d.data(), c->d_slot_to_dense.p, 4 * s2d.size(), cudaMemcpyDeviceToHost, c->stream));
+            CRATAC_CUDA(cudaMemcpyAsync(d2c.data(), c->d_dense_to_col.p, 4 * d2c.size(), cudaMemcpyDeviceToHost, c->stream));
+            CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+            for (size_t i = 0; i < nn; i++) bc[i] = d2c[s2d[bc[i]]];
+        }
+    }
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    return CRATAC_OK;
+}
+
+int cratac_max_barcode_len(cratac_ctx* h, int64_t* len) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(build_barcodes(c));
+    size_t m = 0;
+    for (const std::string& s : c->barcodes) m = std::max(m, s.size());
+    *len = (int64_t)m;
+    return CRATAC_OK;
+}
+
+int cratac_get_barcodes(cratac_ctx* h, char* out, int64_t stride) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(build_barcodes(c));
+    for (size_t j = 0; j < c->barcodes.size(); j++) {
+        if ((int64_t)c->barcodes[j].size() + 1 > stride) { set_error("barcode stride %lld too small", (long long)stride); return CRATAC_ERR_ARG; }
+        memset(out + j * stride, 0, (size_t)stride);
+        memcpy(out + j * stride, c->barcodes[j].data(), c->barcodes[j].size());
+    }
+    return CRATAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ cut sites
+int cratac_count_cut_sites(cratac_ctx* h, int64_t* values, int64_t* weights, int64_t cap, int64_t* n_bins) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(window_histogram(c));
+    CRATAC_TRY(sync_status(c));
+    int64_t nb = c->h_status[ST_N_BINS];
+    if (n_bins) *n_bins = nb;
+    int64_t k = std::min(nb, cap);
+    if (k > 0 && values) CRATAC_CUDA(cudaMemcpyAsync(values, c->d_hist_values.p, 8 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+    if (k > 0 && weights) CRATAC_CUDA(cudaMemcpyAsync(weights, c->d_hist_weights.p, 8 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    return CRATAC_OK;
+}
+
+int cratac_window_counts(cratac_ctx* h, int contig, int32_t* W) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (contig < 0 || contig >= c->n_contigs) { set_error("contig index out of range"); return CRATAC_ERR_ARG; }
+    if (c->contig_tile_off[contig + 1] == c->contig_tile_off[contig]) { set_error("contig %d is not a primary contig", contig); return CRATAC_ERR_ARG; }
+    int64_t L = c->contig_lens[contig];
+    DevBuf d_W;
+    CRATAC_TRY(d_W.reserve(4 * (size_t)std::max<int64_t>(L, 1)));
+    int rc = dump_window_counts(c, contig, d_W.as<int32_t>());
+    if (rc == CRATAC_OK && cudaMemcpyAsync(W, d_W.p, 4 * (size_t)L, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = CRATAC_ERR_CUDA;
+    if (rc == CRATAC_OK) rc = sync_status(c);
+    d_W.release();
+    return rc;
+}
+
+int cratac_bedgraph_rows(cratac_ctx* h, int contig, int64_t* start, int64_t* end, int64_t* count, int64_t cap, int64_t* n_rows) {
+    Ctx* c = &h->c;
+    if (contig < 0 || contig >= c->n_contigs) { set_error("contig index out of range"); return CRATAC_ERR_ARG; }
+    int64_t L = c->contig_lens[contig];
+    std::vector<int32_t> W((size_t)std::max<int64_t>(L, 1));
+    CRATAC_TRY(cratac_window_counts(h, contig, W.data()));
+    // run-length encode the non-zero bases; a zero never closes the open run (count_cut_sites/__init__.py:36-37)
+    int64_t n = 0, rs = 0, last = 0;
+    int32_t cur = 0;
+    for (int64_t p = 0; p < L; p++) {
+        int32_t v = W[p];
+        if (v == 0) continue;
+        if (v == cur) { last = p; continue; }
+        if (cur != 0) { if (n < cap) { start[n] = rs; end[n] = last + 1; count[n] = cur; } n++; }
+        cur = v; rs = p; last = p;
+    }
+    if (cur != 0) { if (n < cap) { start[n] = rs; end[n] = last + 1; count[n] = cur; } n++; }
+    *n_rows = n;
+    return CRATAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ threshold
+static int read_fit(Ctx* c, double params_out[6], int* has_params, int64_t* threshold_out, int64_t* em_it, int64_t* inner_it) {
+    CRATAC_TRY(sync_status(c));
+    double p[6];
+    CRATAC_CUDA(cudaMemcpyAsync(p, c->d_em_params.p, sizeof(p), cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    if (params_out) memcpy(params_out, p, sizeof(p));
+    if (has_params) *has_params = (int)c->h_status[ST_HAS_PARAMS];
+    if (threshold_out) *threshold_out = c->h_status[ST_THRESHOLD];
+    if (em_it) *em_it = c->h_status[ST_EM_ITERS];
+    if (inner_it) *inner_it = c->h_status[ST_EM_INNER];
+    return CRATAC_OK;
+}
+
+int cratac_fit_threshold(cratac_ctx* h, const int64_t* values, const int64_t* weights, int64_t n_bins, double odds_ratio,
+                         double params_out[6], int* has_params, int64_t* threshold_out, int64_t* em_iterations, int64_t* inner_iterations) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (n_bins < 0 || n_bins >= HIST_CAP) { set_error("cratac_fit_threshold: bad bin count"); return CRATAC_ERR_ARG; }
+    CRATAC_TRY(c->d_hist_values.reserve(sizeof(int64_t) * HIST_CAP));
+    CRATAC_TRY(c->d_hist_weights.reserve(sizeof(int64_t) * HIST_CAP));
+    if (n_bins > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_hist_values.p, values, 8 * (size_t)n_bins, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_hist_weights.p, weights, 8 * (size_t)n_bins, cudaMemcpyHostToDevice, c->stream));
+    }
+    CRATAC_TRY(fit_threshold_arrays(c, c->d_hist_values.as<int64_t>(), c->d_hist_weights.as<int64_t>(), n_bins, odds_ratio));
+    return read_fit(c, params_out, has_params, threshold_out, em_iterations, inner_iterations);
+}
+
+int cratac_fit_threshold_device(cratac_ctx* h, double odds_ratio, double params_out[6], int* has_params, int64_t* threshold_out) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(fit_threshold_device(c, odds_ratio));
+    return read_fit(c, params_out, has_params, threshold_out, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------ peaks
+static int call_peaks_with_retry(Ctx* c) {
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CRATAC_TRY(call_peaks_device(c));
+        int rc = sync_status(c);
+        if (rc == CRATAC_ERR_CAPACITY && c->run_cap < ((int64_t)1 << 30)) { c->run_cap <<= 2; continue; }
+        if (rc != CRATAC_OK) return rc;
+        c->n_peaks = c->h_status[ST_N_PEAKS];
+        c->peaks_on_device_count = false;
+        return CRATAC_OK;
+    }
+    set_error("run list overflow");
+    return CRATAC_ERR_CAPACITY;
+}
+
+int cratac_call_peaks(cratac_ctx* h, int64_t threshold, int64_t* n_peaks) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (threshold >= 0) {
+        int64_t* st = c->d_status.as<int64_t>();
+        CRATAC_CUDA(cudaMemcpyAsync(&st[ST_THRESHOLD], &threshold, 8, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    CRATAC_TRY(call_peaks_with_retry(c));
+    if (n_peaks) *n_peaks = c->n_peaks;
+    return CRATAC_OK;
+}
+
+int cratac_get_peaks(cratac_ctx* h, int32_t* chrom, int32_t* start, int32_t* end) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(fetch_peak_count(c));
+    size_t n = (size_t)c->n_peaks;
+    if (n == 0) return CRATAC_OK;
+    // device arrays are sorted by (contig, start); row ids restore the caller's order for user peaks
+    std::vector<int32_t> pc(n), ps(n), pe(n), pr(n);
+    CRATAC_CUDA(cudaMemcpyAsync(pc.data(), c->d_peak_chrom.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(ps.data(), c->d_peak_start.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(pe.data(), c->d_peak_end.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(pr.data(), c->d_peak_row.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) {
+        size_t r = (size_t)pr[i];
+        if (chrom) chrom[r] = pc[i];
+        if (start) start[r] = ps[i];
+        if (end) end[r] = pe[i];
+    }
+    return CRATAC_OK;
+}
+
+int cratac_set_peaks(cratac_ctx* h, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (n < 0 || (n > 0 && (!chrom || !start || !end))) { set_error("cratac_set_peaks: bad arguments"); return CRATAC_ERR_ARG; }
+    std::vector<int32_t> order((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        order[i] = (int32_t)i;
+        if (chrom[i] < 0 || chrom[i] >= c->n_contigs) { set_error("peak %lld: contig index out of range", (long long)i); return CRATAC_ERR_ARG; }
+    }
+    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        if (chrom[x] != chrom[y]) return chrom[x] < chrom[y];
+        if (start[x] != start[y]) return start[x] < start[y];
+        return end[x] < end[y];
+    });
+    std::vector<int32_t> pc((size_t)std::max<int64_t>(n, 1)), ps(pc.size()), pe(pc.size());
+    std::vector<int64_t> off((size_t)c->n_contigs + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        int32_t o = order[i];
+        pc[i] = chrom[o]; ps[i] = start[o]; pe[i] = end[o];
+        off[chrom[o] + 1]++;
+        // tenkit Regions merges overlapping regions on load (tenkit/regions.py:91-110); the merged name then
+        // misses in peaks_dict (generate_peak_matrix/__init__.py:114 -> KeyError).  Touching peaks stay separate.
+        if (i > 0 && pc[i - 1] == pc[i] && ps[i] < pe[i - 1]) {
+            set_error("peaks %d and %d overlap (the reference fails with KeyError on overlapping peaks)", order[i - 1], o);
+            return CRATAC_ERR_PEAKS_OVERLAP;
+        }
+    }
+    for (int k = 0; k < c->n_contigs; k++) off[k + 1] += off[k];
+    size_t nn = pc.size();
+    CRATAC_TRY(c->d_peak_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_peak_start.reserve(4 * nn)); CRATAC_TRY(c->d_peak_end.reserve(4 * nn));
+    CRATAC_TRY(c->d_peak_row.reserve(4 * nn)); CRATAC_TRY(c->d_peak_off.reserve(8 * off.size()));
+    if (n > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_peak_chrom.p, pc.data(), 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_peak_start.p, ps.data(), 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_peak_end.p, pe.data(), 4 * nn, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_peak_row.p, order.data(), 4 * nn, cudaMemcpyHostToDevice, c->stream));
+    }
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_peak_off.p, off.data(), 8 * off.size(), cudaMemcpyHostToDevice, c->stream));
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_CUDA(cudaMemcpyAsync(&st[ST_N_PEAKS], &n, 8, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_peaks = n;
+    c->peaks_on_device_count = false;
+    return CRATAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ matrix
+int cratac_peak_matrix(cratac_ctx* h, int64_t* nnz) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(peak_matrix_device(c));
+    CRATAC_TRY(sync_status(c));
+    if (c->peaks_on_device_count) { c->n_peaks = c->h_status[ST_N_PEAKS]; c->peaks_on_device_count = false; }
+    if (nnz) *nnz = c->nnz;
+    return CRATAC_OK;
+}
+
+int cratac_get_matrix(cratac_ctx* h, int64_t* indptr, int64_t* indices, int32_t* data) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (indptr) CRATAC_CUDA(cudaMemcpyAsync(indptr, c->d_indptr.p, 8 * (size_t)(c->n_barcodes + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (indices && c->nnz > 0) CRATAC_CUDA(cudaMemcpyAsync(indices, c->d_indices.p, 8 * (size_t)c->nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (data && c->nnz > 0) CRATAC_CUDA(cudaMemcpyAsync(data, c->d_data.p, 4 * (size_t)c->nnz, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    return CRATAC_OK;
+}
+
+int cratac_matrix_device(cratac_ctx* h, const int64_t** d_indptr, const int64_t** d_indices, const int32_t** d_data) {
+    Ctx* c = &h->c;
+    if (d_indptr) *d_indptr = c->d_indptr.as<int64_t>();
+    if (d_indices) *d_indices = c->d_indices.as<int64_t>();
+    if (d_data) *d_data = c->d_data.as<int32_t>();
+    return CRATAC_OK;
+}
+
+int cratac_hist_device(cratac_ctx* h, const uint64_t** d_hist, int64_t* cap) {
+    if (d_hist) *d_hist = h->c.d_hist.as<uint64_t>();
+    if (cap) *cap = HIST_CAP;
+    return CRATAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ whole path
+static int run_tail(Ctx* c, double odds_ratio, cratac_run_result* r) {
+    CRATAC_TRY(window_histogram(c));
+    CRATAC_TRY(fit_threshold_device(c, odds_ratio));
+    CRATAC_TRY(call_peaks_device(c));
+    CRATAC_TRY(peak_matrix_device(c));
+    int rc = sync_status(c);
+    if (rc == CRATAC_ERR_CAPACITY && c->run_cap < ((int64_t)1 << 30)) {
+        // the run list overflowed: grow it and redo peaks + matrix (the fitted threshold is still on the device)
+        c->run_cap <<= 2;
+        CRATAC_TRY(call_peaks_with_retry(c));
+        c->peaks_on_device_count = true;
+        CRATAC_TRY(peak_matrix_device(c));
+        rc = sync_status(c);
+    }
+    if (rc != CRATAC_OK) return rc;
+    c->n_peaks = c->h_status[ST_N_PEAKS];
+    c->peaks_on_device_count = false;
+    if (r) {
+        r->n_fragments = c->n_fragments; r->n_barcodes = c->n_barcodes; r->n_bins = c->h_status[ST_N_BINS];
+        r->threshold = c->h_status[ST_THRESHOLD]; r->has_params = c->h_status[ST_HAS_PARAMS]; r->n_peaks = c->n_peaks; r->nnz = c->nnz;
+        r->em_iterations = c->h_status[ST_EM_ITERS]; r->em_inner_iterations = c->h_status[ST_EM_INNER];
+        CRATAC_CUDA(cudaMemcpyAsync(r->params, c->d_em_params.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, c->stream));
+        CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return CRATAC_OK;
+}
+
+int cratac_run(cratac_ctx* h, const char* text, int64_t nbytes, int text_is_device, double odds_ratio, cratac_run_result* result) {
+    if (text_is_device) CRATAC_TRY(cratac_decode_device(h, text, nbytes));
+    else CRATAC_TRY(cratac_decode_host(h, text, nbytes));
+    return run_tail(&h->c, odds_ratio, result);
+}
+
+int cratac_run_from_fragments(cratac_ctx* h, double odds_ratio, cratac_run_result* result) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return run_tail(c, odds_ratio, result);
+}
+
+// ------------------------------------------------------------------------------------------ host helpers
+int cratac_py2_set_order(int64_t n, const char* const* keys, int64_t* order_out) {
+    std::vector<std::string> k((size_t)n);
+    for (int64_t i = 0; i < n; i++) k[i] = keys[i];
+    std::vector<int64_t> order;
+    py2_set_order(k, order);
+    if ((int64_t)order.size() != n) { set_error("cratac_py2_set_order: keys are not distinct"); return CRATAC_ERR_ARG; }
+    for (int64_t i = 0; i < n; i++) order_out[i] = order[i];
+    return CRATAC_OK;
+}
+
+int cratac_encode_text_device(cratac_ctx* h, int64_t n, const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end,
+                              const uint32_t* d_bc_seq, const int32_t* d_dup, char* d_out, int64_t cap, int64_t* nbytes) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return encode_text(c, n, d_chrom, d_start, d_end, d_bc_seq, d_dup, d_out, cap, nbytes);
+}
+
+// BGZF (or plain multi-member gzip) inflate.  BGZF blocks carry their compressed size in the 'BC' extra
+// field and their inflated size in the trailer, so the blocks inflate independently on `threads` threads.
+int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, int64_t* nbytes) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    long fsz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<unsigned char> buf((size_t)fsz);
+    if (fsz > 0 && fread(buf.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); set_error("short read on %s", path); return CRATAC_ERR_IO; }
+    fclose(f);
+    struct Blk { size_t off, csize; int64_t out_off; uint32_t isize; };
+    std::vector<Blk> blocks;
+    size_t p = 0;
+    int64_t total = 0;
+    bool bgzf = true;
+    while (p + 18 <= (size_t)fsz) {
+        const unsigned char* b = &buf[p];
+        if (!(b[0] == 31 && b[1] == 139 && b[2] == 8 && (b[3] & 4))) { bgzf = false; break; }
+        unsigned xlen = b[10] | (b[11] << 8);
+        size_t q = p + 12, xend = q + xlen;
+        long bsize = -1;
+        while (q + 4 <= xend && xend <= (size_t)fsz) {
+            unsigned slen = buf[q + 2] | (buf[q + 3] << 8);
+            if (buf[q] == 'B' && buf[q + 1] == 'C' && slen == 2) bsize = (buf[q + 4] | (buf[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < 0 || p + (size_t)bsize > (size_t)fsz) { bgzf = false; break; }
+        uint32_t isize;
+        memcpy(&isize, &buf[p + bsize - 4], 4);
+        blocks.push_back(Blk{p + 12 + xlen, (size_t)bsize - 12 - xlen - 8, total, isize});
+        total += isize;
+        p += (size_t)bsize;
+    }
+    if (bgzf && p == (size_t)fsz) {
+        *nbytes = total;
+        if (cap == 0 || !out) return CRATAC_OK;
+        if (cap < total) { set_error("inflate buffer too small: need %lld bytes", (long long)total); return CRATAC_ERR_ARG; }
+        if (threads < 1) threads = 1;
+        std::atomic<size_t> next(0);
+        std::atomic<int> failed(0);
+        auto work = [&]() {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= blocks.size()) break;
+                const Blk& k = blocks[i];
+                inflateReset(&zs);
+                zs.next_in = &buf[k.off]; zs.avail_in = (uInt)k.csize;
+                zs.next_out = reinterpret_cast<unsigned char*>(out) + k.out_off; zs.avail_out = k.isize;
+                int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.avail_out != 0) { failed = 1; break; }
+            }
+            inflateEnd(&zs);
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        if (failed) { set_error("corrupt BGZF block in %s", path); return CRATAC_ERR_IO; }
+        return CRATAC_OK;
+    }
+    // plain gzip (possibly multi-member) or uncompressed text: sequential
+    if (fsz >= 2 && buf[0] == 31 && buf[1] == 139) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, 15 + 16) != Z_OK) { set_error("zlib init failed"); return CRATAC_ERR_IO; }
+        std::vector<unsigned char> scratch(1 << 20);
+        zs.next_in = buf.data(); zs.avail_in = (uInt)fsz;
+        int64_t produced = 0;
+        for (;;) {
+            bool counting = (cap == 0 || !out);
+            zs.next_out = counting ? scratch.data() : reinterpret_cast<unsigned char*>(out) + produced;
+            int64_t room = counting ? (int64_t)scratch.size() : cap - produced;
+            zs.avail_out = (uInt)std::min<int64_t>(room, 1 << 30);
+            uInt before = zs.avail_out;
+            int rc = inflate(&zs, Z_NO_FLUSH);
+            produced += before - zs.avail_out;
+            if (rc == Z_STREAM_END) {
+                if (zs.avail_in == 0) break;
+                inflateReset(&zs);
+                continue;
+            }
+            if (rc != Z_OK) { inflateEnd(&zs); set_error("corrupt gzip stream in %s", path); return CRATAC_ERR_IO; }
+            if (!counting && produced >= cap && zs.avail_in > 0) { inflateEnd(&zs); set_error("inflate buffer too small"); return CRATAC_ERR_ARG; }
+        }
+        inflateEnd(&zs);
+        *nbytes = produced;
+        return CRATAC_OK;
+    }
+    *nbytes = fsz;
+    if (cap == 0 || !out) return CRATAC_OK;
+    if (cap < fsz) { set_error("buffer too small"); return CRATAC_ERR_ARG; }
+    memcpy(out, buf.data(), (size_t)fsz);
+    return CRATAC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// Shared declarations for libcratac (sm_100a).  Internal header: the public C ABI is include/cratac.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cratac.h"
+
+namespace cratac {
+
+// ---------------------------------------------------------------- constants of the path
+constexpr int HALF_WINDOW = 200;       // lib/python/constants.py:68  WINDOW_SIZE // 2
+constexpr int MERGE_DIST = 500;        // lib/python/constants.py:70  PEAK_MERGE_DISTANCE
+constexpr int DEFAULT_THRESHOLD = 15;  // lib/python/analysis/peaks.py:17
+constexpr int POS_INDEX_SHIFT = 10;    // one fragment-index entry per 1024 genome bases
+constexpr int64_t CONTIG_GAP = 1024;   // spacing between contigs in the global run coordinate (> MERGE_DIST)
+constexpr int HIST_CAP = 1 << 20;      // largest representable window count
+constexpr int NUM_SMS = 148;
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+#define CRATAC_CUDA(call)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            cratac::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return CRATAC_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+#define CRATAC_TRY(call)                \
+    do {                                \
+        int _rc = (call);               \
+        if (_rc != CRATAC_OK) return _rc; \
+    } while (0)
+
+// device-side status word layout (ctx->d_status, int64[16])
+enum StatusSlot {
+    ST_ERROR = 0,        // first error code raised on device (0 = none)
+    ST_ERROR_ARG = 1,    // detail (line number, tile id ...)
+    ST_N_FRAGMENTS = 2,
+    ST_N_BARCODES = 3,
+    ST_MAX_POS_LEN = 4,  // max(end - start, 0)
+    ST_MAX_NEG_LEN = 5,  // max(start - end, 0)
+    ST_MAX_COUNT = 6,    // largest window count seen
+    ST_N_BINS = 7,
+    ST_N_RUNS = 8,
+    ST_N_FILLS = 9,
+    ST_N_PEAKS = 10,
+    ST_N_HITS = 11,
+    ST_NNZ = 12,
+    ST_THRESHOLD = 13,
+    ST_HAS_PARAMS = 14,
+    ST_EM_ITERS = 15,
+    ST_EM_INNER = 16,
+    ST_TICKET = 17,
+    ST_TICKET2 = 18,
+    ST_SLOTS = 24
+};
+
+// growable device buffer (grow-only; keeps repeated steps free of cudaMalloc)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // reference contigs (genome.fa.fai order)
+    int n_contigs = 0;
+    std::vector<std::string> contig_names;
+    std::vector<int64_t> contig_lens;
+    std::vector<int64_t> contig_base;      // global run coordinate of base 0 of each contig
+    std::vector<int64_t> contig_tile_off;  // first genome tile of each contig (+ total)
+    std::vector<int64_t> contig_pidx_off;  // first pos-index entry of each contig (+ total)
+    DevBuf d_contig_lens, d_contig_base, d_contig_tile_off, d_contig_pidx_off, d_contig_table;
+    int contig_table_cap = 0;
+    int tile_bases = 0;                    // genome bases owned by one pileup tile
+
+    // fragments (SoA, device)
+    int64_t n_fragments = 0;
+    DevBuf d_chrom, d_start, d_end, d_bc, d_dup;
+    DevBuf d_contig_frag_off;              // int64[n_contigs+1]
+    DevBuf d_pos_index;                    // int32 per 1024 bases (fragment index relative to 0)
+    // text
+    const char* d_text = nullptr;          // borrowed or owned device text of the last decode
+    int64_t text_bytes = 0;
+    DevBuf d_text_own;
+    DevBuf d_tile_counts, d_tile_offsets;  // decode line bookkeeping
+    // barcodes
+    int bc_table_cap = 0;                  // slots (power of two)
+    DevBuf d_bc_keys, d_bc_first, d_bc_textoff, d_slot_to_dense;
+    int64_t n_barcodes = 0;
+    DevBuf d_dense_key, d_dense_first, d_dense_textoff, d_dense_to_col, d_col_to_dense;
+    std::vector<std::string> barcodes;     // matrix column order
+    int bc_order = CRATAC_BC_ORDER_PY2SET;
+    bool bc_ready = false;
+    bool bc_is_slot = false;               // d_bc holds hash-table slots (decode) vs dense ids (set_fragments)
+    // histogram / threshold
+    DevBuf d_hist;                         // uint64[HIST_CAP]
+    DevBuf d_hist_values, d_hist_weights;  // compact, ascending
+    DevBuf d_em_params;                    // double[8]
+    DevBuf d_em_work;
+    // peak calling
+    DevBuf d_chain;                        // uint64 per tile
+    DevBuf d_tile_summary;                 // int4-ish per tile
+    DevBuf d_run_start, d_run_end, d_bridge, d_fill;
+    int64_t run_cap = 0;
+    DevBuf d_peak_chrom, d_peak_start, d_peak_end, d_peak_row, d_peak_off;  // sorted by (contig,start)
+    int64_t n_peaks = 0;
+    int64_t peak_cap = 0;
+    bool peaks_on_device_count = false;    // n_peaks lives in d_status[ST_N_PEAKS] until fetched
+    // matrix
+    DevBuf d_bc_hits, d_seg_off, d_cursor, d_hits, d_out_row, d_out_cnt, d_nnz_col;
+    DevBuf d_indptr, d_indices, d_data;
+    int64_t nnz = 0;
+    // misc
+    DevBuf d_status;                       // int64[ST_SLOTS]
+    DevBuf d_scan_tmp;
+    int64_t* h_status = nullptr;           // pinned mirror
+    int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
+};
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ void raise_error(int64_t* status, int code, int64_t arg) {
+    if (atomicCAS(reinterpret_cast<unsigned long long*>(&status[ST_ERROR]), 0ULL, (unsigned long long)code) == 0ULL)
+        status[ST_ERROR_ARG] = arg;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------- scan.cu
+// exclusive prefix sum of n int64 (in -> out, may alias); total written to *d_total if non-null.
+int exclusive_scan_i64(Ctx* c, const int64_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total);
+int exclusive_scan_i32_to_i64(Ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total);
+
+// ---------------------------------------------------------------- stage entry points (host side)
+int decode_text(Ctx* c, const char* d_text, int64_t nbytes);          // decode.cu
+int finalize_fragments(Ctx* c);                                       // decode.cu: contig offsets, pos index, checks
+int build_barcodes(Ctx* c);                                           // decode.cu: dense ids, column order, strings
+int window_histogram(Ctx* c);                                         // pileup.cu: K2+K3 fused
+int call_peaks_device(Ctx* c);                                        // pileup.cu: K5 (threshold from d_status)
+int fit_threshold_device(Ctx* c, double odds_ratio);                  // em.cu: K4 on compact histogram
+int peak_matrix_device(Ctx* c);                                       // matrix.cu: K6-K8
+int sync_status(Ctx* c);                                              // api.cu: D2H of status words + error check
+
+}  // namespace cratac

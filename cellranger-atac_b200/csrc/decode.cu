@@ -1,0 +1,744 @@
+// K1: fragments.tsv text -> SoA int32 (chrom, start, end, barcode slot, dup) + barcode dictionary.
+// Replaces lib/python/tools/io.py:75-79 / :82-92 (one str.split + 3 int() per line on the host).
+//
+// Layout: the text is cut into fixed 16 KiB tiles.  A line belongs to the tile that holds its
+// terminating '\n'.  Pass A counts newlines per tile (128-bit loads), a scan turns the counts into
+// line offsets, pass B stages each tile (+256 B look-back for the line that straddles the tile
+// start) into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier), finds the
+// newlines, and parses one line per thread.  Barcodes of the 10x form [ACGT]{16}-<int> pack
+// losslessly into 64 bits; any other byte string falls back to a 63-bit hash.  Both go through one
+// open-addressing table in HBM/L2 (atomicCAS) that also records the first line of each barcode.
+#include <algorithm>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cratac {
+
+constexpr int DEC_TILE = 16384;
+constexpr int DEC_LOOKBACK = 256;
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_MAX_LINES = DEC_TILE / 8;   // a valid line has >= 10 bytes
+constexpr unsigned long long BC_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
+
+struct ContigEntry { unsigned long long hash; int32_t id; int32_t used; };
+
+__host__ __device__ __forceinline__ unsigned long long fnv1a(const unsigned char* s, int n) {
+    unsigned long long h = 1469598103934665603ULL;
+    for (int i = 0; i < n; i++) { h ^= s[i]; h *= 1099511628211ULL; }
+    return h;
+}
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// ------------------------------------------------------------------ pass A: newline counts
+__global__ void __launch_bounds__(256) k_count_newlines(const char* __restrict__ text, int64_t nbytes, int64_t n_eff,
+                                                         int32_t* __restrict__ tile_counts) {
+    // one CTA per tile; 256 threads x 4 x 16 B
+    int64_t tile_base = (int64_t)blockIdx.x * DEC_TILE;
+    int cnt = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(text) & 15) == 0);
+#pragma unroll
+    for (int k = 0; k < DEC_TILE / (256 * 16); k++) {
+        int64_t off = tile_base + ((int64_t)k * 256 + threadIdx.x) * 16;
+        if (aligned && off + 16 <= nbytes) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(text + off));
+            cnt += __popc(__vcmpeq4(v.x, 0x0a0a0a0au)) + __popc(__vcmpeq4(v.y, 0x0a0a0a0au)) +
+                   __popc(__vcmpeq4(v.z, 0x0a0a0a0au)) + __popc(__vcmpeq4(v.w, 0x0a0a0a0au));
+        } else {
+            int c8 = 0;
+            for (int j = 0; j < 16; j++) {
+                int64_t p = off + j;
+                if (p < nbytes) c8 += (text[p] == '\n');
+                else if (p < n_eff) c8 += 1;   // virtual terminator after an unterminated last line
+            }
+            cnt += c8 * 8;
+        }
+    }
+    cnt >>= 3;  // __vcmpeq4 sets 8 bits per matching byte
+    __shared__ int warp_cnt[8];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; w++) s += warp_cnt[w];
+        tile_counts[blockIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------ TMA bulk copy helpers (sm_90+/sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a mis-programmed copy must surface as an error, never as a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t phase) {
+    for (int spin = 0; spin < (1 << 22); spin++)
+        if (mbar_try_wait(bar, phase)) return true;
+    return false;
+}
+
+// ------------------------------------------------------------------ pass B: parse
+struct DecodeArgs {
+    const char* text;
+    int64_t nbytes, n_eff;
+    const int64_t* tile_offsets;     // exclusive scan of tile_counts
+    const int32_t* tile_counts;
+    const ContigEntry* contig_table;
+    int contig_mask;
+    int32_t *chrom, *start, *end, *bc, *dup;
+    unsigned long long* bc_keys;
+    unsigned long long* bc_first;
+    long long* bc_textoff;
+    int bc_mask;
+    int64_t* status;
+    int use_tma;
+};
+
+__device__ __forceinline__ bool parse_uint(const unsigned char* s, int b, int e, int32_t* out) {
+    if (b >= e || e - b > 10) return false;
+    unsigned long long v = 0;
+    for (int i = b; i < e; i++) {
+        unsigned d = (unsigned)s[i] - (unsigned)'0';
+        if (d > 9u) return false;
+        v = v * 10 + d;
+    }
+    if (v > 2147483647ULL) return false;
+    *out = (int32_t)v;
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long barcode_key(const unsigned char* s, int b, int e) {
+    // fast path: [ACGT]{16}-[0-9]{1,9}
+    int n = e - b;
+    if (n >= 18 && n <= 26 && s[b + 16] == '-') {
+        unsigned seq = 0;
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            unsigned ch = s[b + i];
+            // A=0x41 C=0x43 G=0x47 T=0x54 -> (ch>>1)&3 = 0,1,3,2 ; validate exactly
+            unsigned code = (ch >> 1) & 3u;
+            ok &= (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
+            seq = (seq << 2) | code;
+        }
+        unsigned long long grp = 0;
+        for (int i = b + 17; i < e; i++) {
+            unsigned d = (unsigned)s[i] - (unsigned)'0';
+            ok &= (d <= 9u);
+            grp = grp * 10 + d;
+        }
+        // a leading zero in the group ("-01") would alias "-1": send it to the generic path
+        ok &= !(n > 18 && s[b + 17] == '0');
+        if (ok) return ((unsigned long long)grp << 32) | seq;
+    }
+    unsigned long long h = mix64(fnv1a(s + b, n) ^ ((unsigned long long)n << 56));
+    h = (h >> 1) | 0x8000000000000000ULL;
+    if (h == BC_EMPTY) h ^= 2ULL;
+    return h;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
+    __shared__ __align__(128) unsigned char buf[DEC_LOOKBACK + DEC_TILE];
+    __shared__ uint16_t nlpos[DEC_MAX_LINES];
+    __shared__ int warp_tot[DEC_THREADS / 32];
+    __shared__ int s_first_begin;
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int64_t tile_base = (int64_t)blockIdx.x * DEC_TILE;
+    const int n_lines = a.tile_counts[blockIdx.x];
+    if (n_lines == 0) return;   // uniform per CTA
+    const int64_t src0 = tile_base - DEC_LOOKBACK;
+
+    // ---- stage bytes [src0, tile_base + DEC_TILE) into buf
+    const bool full = a.use_tma && src0 >= 0 && tile_base + DEC_TILE <= a.nbytes;
+    if (full) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, DEC_LOOKBACK + DEC_TILE);
+            tma_load_1d(buf, a.text + src0, DEC_LOOKBACK + DEC_TILE, &bar);
+        }
+        if (!mbar_wait(&bar, 0)) { if (tid == 0) raise_error(a.status, CRATAC_ERR_INTERNAL, -100 - (int64_t)blockIdx.x); return; }
+    } else {
+        for (int i = tid; i < DEC_LOOKBACK + DEC_TILE; i += DEC_THREADS) {
+            int64_t p = src0 + i;
+            unsigned char ch = '\n';
+            if (p >= 0 && p < a.nbytes) ch = (unsigned char)a.text[p];
+            buf[i] = ch;   // p < 0 and p >= nbytes read as '\n' (file start / virtual terminator)
+        }
+        __syncthreads();
+    }
+
+    // ---- newline positions of the tile, in order
+    constexpr int PER_THREAD = DEC_TILE / DEC_THREADS;   // 64 contiguous bytes per thread
+    const unsigned char* mine = buf + DEC_LOOKBACK + tid * PER_THREAD;
+    unsigned long long mask = 0;   // bit j set if mine[j] == '\n'
+#pragma unroll
+    for (int w = 0; w < PER_THREAD / 4; w++) {
+        unsigned v = *reinterpret_cast<const unsigned*>(mine + 4 * w);
+        unsigned m = __vcmpeq4(v, 0x0a0a0a0au);
+        unsigned bits = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+        mask |= (unsigned long long)bits << (4 * w);
+    }
+    // bytes at or beyond n_eff are padding newlines of the last tile: they terminate nothing
+    {
+        int64_t lim = a.n_eff - (tile_base + (int64_t)tid * PER_THREAD);
+        if (lim < PER_THREAD) mask = lim <= 0 ? 0ULL : (mask & ((1ULL << lim) - 1ULL));
+    }
+    int my_cnt = __popcll(mask);
+    int lane = tid & 31, warp = tid >> 5;
+    int incl = my_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += warp_tot[w];
+    int idx = woff + incl - my_cnt;
+    while (mask) {
+        int j = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        if (idx < DEC_MAX_LINES) nlpos[idx] = (uint16_t)(DEC_LOOKBACK + tid * PER_THREAD + j);
+        idx++;
+    }
+    if (tid == 0) {
+        // start of the first line: one past the last '\n' before the tile (or the file start)
+        int p = DEC_LOOKBACK - 1;
+        while (p >= 0 && buf[p] != '\n') p--;
+        s_first_begin = (p < 0 && tile_base > 0) ? -1 : p + 1;
+        if (tile_base == 0) s_first_begin = DEC_LOOKBACK;
+    }
+    __syncthreads();
+    if (n_lines > DEC_MAX_LINES || s_first_begin < 0) {
+        if (tid == 0) raise_error(a.status, CRATAC_ERR_PARSE, a.tile_offsets[blockIdx.x]);
+        return;
+    }
+
+    // ---- one line per thread
+    const int64_t out_base = a.tile_offsets[blockIdx.x];
+    int loc_maxpos = 0, loc_maxneg = 0;
+    for (int li = tid; li < n_lines; li += DEC_THREADS) {
+        int b = li == 0 ? s_first_begin : nlpos[li - 1] + 1;
+        int e = nlpos[li];
+        int64_t line_no = out_base + li;
+        // strip() : leading / trailing blanks, '\r'
+        while (b < e && (buf[b] == ' ' || buf[b] == '\t' || buf[b] == '\r')) b++;
+        while (e > b && (buf[e - 1] == ' ' || buf[e - 1] == '\t' || buf[e - 1] == '\r')) e--;
+        int t[4];
+        int nt = 0;
+        for (int i = b; i < e; i++) {
+            if (buf[i] == '\t') {
+                if (nt < 4) t[nt] = i;
+                nt++;
+            }
+        }
+        int32_t v_start = 0, v_end = 0, v_dup = 0;
+        bool ok = (nt == 4);
+        if (ok) {
+            ok = parse_uint(buf, t[0] + 1, t[1], &v_start) && parse_uint(buf, t[1] + 1, t[2], &v_end) &&
+                 parse_uint(buf, t[3] + 1, e, &v_dup) && (t[0] > b) && (t[3] > t[2] + 1);
+        }
+        if (!ok) { raise_error(a.status, CRATAC_ERR_PARSE, line_no); continue; }
+        // contig id
+        unsigned long long ch = fnv1a(buf + b, t[0] - b);
+        int32_t cid = -1;
+        for (int s = (int)(mix64(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
+            ContigEntry ce = a.contig_table[s];
+            if (!ce.used) break;
+            if (ce.hash == ch) { cid = ce.id; break; }
+        }
+        if (cid < 0) { raise_error(a.status, CRATAC_ERR_CONTIG, line_no); continue; }
+        // barcode slot
+        unsigned long long key = barcode_key(buf, t[2] + 1, t[3]);
+        unsigned slot = (unsigned)(mix64(key)) & (unsigned)a.bc_mask;
+        int probes = 0;
+        bool placed = false;
+        while (probes <= a.bc_mask) {
+            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&a.bc_keys[slot]);
+            if (k == key) { placed = true; break; }
+            if (k == BC_EMPTY) {
+                unsigned long long old = atomicCAS(&a.bc_keys[slot], BC_EMPTY, key);
+                if (old == BC_EMPTY) {
+                    long long off = src0 + (t[2] + 1);
+                    a.bc_textoff[slot] = (off << 8) | (long long)min(t[3] - t[2] - 1, 255);
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_N_BARCODES]), 1ULL);
+                    placed = true;
+                    break;
+                }
+                if (old == key) { placed = true; break; }
+            }
+            slot = (slot + 1) & (unsigned)a.bc_mask;
+            probes++;
+        }
+        if (!placed) { raise_error(a.status, CRATAC_ERR_CAPACITY, line_no); continue; }
+        if (*reinterpret_cast<volatile unsigned long long*>(&a.bc_first[slot]) > (unsigned long long)line_no)
+            atomicMin(&a.bc_first[slot], (unsigned long long)line_no);
+        a.chrom[line_no] = cid;
+        a.start[line_no] = v_start;
+        a.end[line_no] = v_end;
+        a.bc[line_no] = (int32_t)slot;
+        a.dup[line_no] = v_dup;
+        int d = v_end - v_start;
+        loc_maxpos = max(loc_maxpos, d);
+        loc_maxneg = max(loc_maxneg, -d);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        loc_maxpos = max(loc_maxpos, __shfl_xor_sync(0xffffffffu, loc_maxpos, d));
+        loc_maxneg = max(loc_maxneg, __shfl_xor_sync(0xffffffffu, loc_maxneg, d));
+    }
+    if (lane == 0) {
+        if (loc_maxpos > 0) atomicMax(reinterpret_cast<long long*>(&a.status[ST_MAX_POS_LEN]), (long long)loc_maxpos);
+        if (loc_maxneg > 0) atomicMax(reinterpret_cast<long long*>(&a.status[ST_MAX_NEG_LEN]), (long long)loc_maxneg);
+    }
+}
+
+// ------------------------------------------------------------------ fragment bookkeeping
+// chrom[] must be non-decreasing and start[] non-decreasing inside a contig.
+__global__ void k_check_sorted(const int32_t* __restrict__ chrom, const int32_t* __restrict__ start, int64_t n, int64_t* status) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= n) return;
+    int c0 = chrom[i - 1], c1 = chrom[i];
+    if (c1 < c0 || (c1 == c0 && start[i] < start[i - 1])) raise_error(status, CRATAC_ERR_UNSORTED, i);
+}
+
+__global__ void k_contig_frag_offsets(const int32_t* __restrict__ chrom, int64_t n, int n_contigs, int64_t* __restrict__ off) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_contigs) return;
+    int64_t lo = 0, hi = n;   // first i with chrom[i] >= c
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (chrom[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    off[c] = lo;
+}
+
+// pos_index[pidx_off[c] + k] = first fragment i of contig c with start[i] >= k * 1024  (absolute i)
+__global__ void k_pos_index(const int32_t* __restrict__ start, const int64_t* __restrict__ frag_off,
+                            const int64_t* __restrict__ pidx_off, int n_contigs, int64_t total, int64_t* __restrict__ pos_index) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    int lo_c = 0, hi_c = n_contigs;   // contig of entry g: last c with pidx_off[c] <= g
+    while (hi_c - lo_c > 1) {
+        int mid = (lo_c + hi_c) >> 1;
+        if (pidx_off[mid] <= g) lo_c = mid; else hi_c = mid;
+    }
+    int c = lo_c;
+    int64_t target = (g - pidx_off[c]) << POS_INDEX_SHIFT;
+    int64_t lo = frag_off[c], hi = frag_off[c + 1];
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)start[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    pos_index[g] = lo;
+}
+
+__global__ void k_max_len(const int32_t* __restrict__ start, const int32_t* __restrict__ end, int64_t n, int64_t* status) {
+    int mp = 0, mn = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int d = end[i] - start[i];
+        mp = max(mp, d); mn = max(mn, -d);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mp = max(mp, __shfl_xor_sync(0xffffffffu, mp, d));
+        mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mp > 0) atomicMax(reinterpret_cast<long long*>(&status[ST_MAX_POS_LEN]), (long long)mp);
+        if (mn > 0) atomicMax(reinterpret_cast<long long*>(&status[ST_MAX_NEG_LEN]), (long long)mn);
+    }
+}
+
+// ------------------------------------------------------------------ barcode table -> dense ids
+__global__ void k_table_compact(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ first,
+                                const long long* __restrict__ textoff, int cap, int32_t* __restrict__ slot_to_dense,
+                                unsigned long long* __restrict__ dense_first, long long* __restrict__ dense_textoff,
+                                unsigned long long* counter) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cap) return;
+    if (keys[s] == BC_EMPTY) { slot_to_dense[s] = -1; return; }
+    unsigned long long d = atomicAdd(counter, 1ULL);
+    slot_to_dense[s] = (int32_t)d;
+    dense_first[d] = first[s];
+    dense_textoff[d] = textoff[s];
+}
+
+__global__ void k_gather_barcode_text(const char* __restrict__ text, const long long* __restrict__ dense_textoff, int64_t n,
+                                      int stride, char* __restrict__ out) {
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    long long packed = dense_textoff[d];
+    long long off = packed >> 8;
+    int len = (int)(packed & 255);
+    char* o = out + d * stride;
+    for (int i = 0; i < stride; i++) o[i] = (i < len) ? text[off + i] : 0;
+}
+
+// ------------------------------------------------------------------ host side
+static int build_contig_table(Ctx* c) {
+    int cap = 16;
+    while (cap < 4 * c->n_contigs) cap <<= 1;
+    std::vector<ContigEntry> tab(cap);
+    memset(tab.data(), 0, sizeof(ContigEntry) * cap);
+    for (int i = 0; i < c->n_contigs; i++) {
+        const std::string& nm = c->contig_names[i];
+        unsigned long long h = fnv1a(reinterpret_cast<const unsigned char*>(nm.data()), (int)nm.size());
+        int s = (int)(mix64(h) & (unsigned)(cap - 1));
+        while (tab[s].used) {
+            if (tab[s].hash == h) { set_error("contig names '%s' and '%s' collide", nm.c_str(), c->contig_names[tab[s].id].c_str()); return CRATAC_ERR_ARG; }
+            s = (s + 1) & (cap - 1);
+        }
+        tab[s].hash = h; tab[s].id = i; tab[s].used = 1;
+    }
+    CRATAC_TRY(c->d_contig_table.reserve(sizeof(ContigEntry) * cap));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_contig_table.p, tab.data(), sizeof(ContigEntry) * cap, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->contig_table_cap = cap;
+    return CRATAC_OK;
+}
+
+int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
+    if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
+    c->d_text = d_text;
+    c->text_bytes = nbytes;
+    c->bc_ready = false;
+    c->barcodes.clear();
+    int64_t* st = c->d_status.as<int64_t>();
+    // virtual newline after an unterminated last line
+    char last = '\n';
+    if (nbytes > 0) CRATAC_CUDA(cudaMemcpyAsync(&last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t n_eff = nbytes + (last != '\n' ? 1 : 0);
+    int64_t n_tiles = (n_eff + DEC_TILE - 1) / DEC_TILE;
+    if (n_tiles == 0) n_tiles = 1;
+    CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
+    CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
+    k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>());
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>(), c->d_tile_offsets.as<int64_t>(), n_tiles, &st[ST_N_FRAGMENTS]));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_FRAGMENTS], &st[ST_N_FRAGMENTS], sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t n = c->h_status[ST_N_FRAGMENTS];
+    c->n_fragments = n;
+    size_t nn = (size_t)std::max<int64_t>(n, 1);
+    CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));
+    CRATAC_TRY(c->d_bc.reserve(4 * nn)); CRATAC_TRY(c->d_dup.reserve(4 * nn));
+
+    for (int attempt = 0;; attempt++) {
+        size_t cap = (size_t)c->bc_table_cap;
+        CRATAC_TRY(c->d_bc_keys.reserve(8 * cap)); CRATAC_TRY(c->d_bc_first.reserve(8 * cap));
+        CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
+        CRATAC_CUDA(cudaMemsetAsync(c->d_bc_keys.p, 0xFF, 8 * cap, c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(c->d_bc_first.p, 0x7F, 8 * cap, c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_BARCODES], 0, sizeof(int64_t) * 3, c->stream));  // barcodes, maxpos, maxneg
+        DecodeArgs a;
+        a.text = d_text; a.nbytes = nbytes; a.n_eff = n_eff;
+        a.tile_offsets = c->d_tile_offsets.as<int64_t>(); a.tile_counts = c->d_tile_counts.as<int32_t>();
+        a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
+        a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
+        a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
+        a.bc_keys = c->d_bc_keys.as<unsigned long long>(); a.bc_first = c->d_bc_first.as<unsigned long long>();
+        a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
+        a.status = st;
+        a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
+        k_parse_tiles<<<(unsigned)n_tiles, DEC_THREADS, 0, c->stream>>>(a);
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+        CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+        CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+        int64_t err = c->h_status[ST_ERROR];
+        int64_t nb = c->h_status[ST_N_BARCODES];
+        bool crowded = nb * 2 > (int64_t)c->bc_table_cap;
+        if ((err == CRATAC_ERR_CAPACITY || (err == 0 && crowded)) && attempt < 6 && c->bc_table_cap < (1 << 28)) {
+            c->bc_table_cap <<= 2;   // grow and decode again
+            continue;
+        }
+        if (err != 0) {
+            int64_t arg = c->h_status[ST_ERROR_ARG];
+            if (err == CRATAC_ERR_PARSE) set_error("malformed fragments line %lld (expected contig\\tstart\\tstop\\tbarcode\\tdup_count)", (long long)(arg + 1));
+            else if (err == CRATAC_ERR_CONTIG) set_error("fragments line %lld: contig is not in the reference", (long long)(arg + 1));
+            else if (err == CRATAC_ERR_CAPACITY) set_error("barcode table overflow at line %lld", (long long)(arg + 1));
+            else set_error("device error %lld (arg %lld) in decode", (long long)err, (long long)arg);
+            c->n_fragments = 0;
+            return (int)err;
+        }
+        c->n_barcodes = nb;
+        break;
+    }
+    return finalize_fragments(c);
+}
+
+int finalize_fragments(Ctx* c) {
+    int64_t n = c->n_fragments;
+    int64_t* st = c->d_status.as<int64_t>();
+    int nc = c->n_contigs;
+    CRATAC_TRY(c->d_contig_frag_off.reserve(sizeof(int64_t) * (nc + 2)));
+    int64_t total_pidx = c->contig_pidx_off[nc];
+    CRATAC_TRY(c->d_pos_index.reserve(sizeof(int64_t) * (size_t)total_pidx));
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+    if (n > 0) {
+        k_check_sorted<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_chrom.as<int32_t>(), c->d_start.as<int32_t>(), n, st);
+        c->launches++;
+    }
+    k_contig_frag_offsets<<<(nc + 1 + 127) / 128, 128, 0, c->stream>>>(c->d_chrom.as<int32_t>(), n, nc, c->d_contig_frag_off.as<int64_t>());
+    c->launches++;
+    k_pos_index<<<(unsigned)((total_pidx + 255) / 256), 256, 0, c->stream>>>(c->d_start.as<int32_t>(), c->d_contig_frag_off.as<int64_t>(),
+                                                                             c->d_contig_pidx_off.as<int64_t>(), nc, total_pidx,
+                                                                             c->d_pos_index.as<int64_t>());
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    CRATAC_TRY(sync_status(c));
+    return CRATAC_OK;
+}
+
+int compute_max_len(Ctx* c) {
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_MAX_POS_LEN], 0, sizeof(int64_t) * 2, c->stream));
+    if (c->n_fragments > 0) {
+        k_max_len<<<NUM_SMS * 4, 256, 0, c->stream>>>(c->d_start.as<int32_t>(), c->d_end.as<int32_t>(), c->n_fragments, st);
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    return CRATAC_OK;
+}
+
+// ---- CPython 2.7 string hash / set order (see cratac_py2_set_order in api.cu)
+static inline int64_t py2_hash(const std::string& s) {
+    if (s.empty()) return 0;
+    uint64_t x = (uint64_t)(unsigned char)s[0] << 7;
+    for (unsigned char ch : s) x = (1000003ULL * x) ^ ch;
+    x ^= (uint64_t)s.size();
+    int64_t h = (int64_t)x;
+    return h == -1 ? -2 : h;
+}
+
+void py2_set_order(const std::vector<std::string>& keys, std::vector<int64_t>& order) {
+    struct Ent { int64_t idx; int64_t hash; };
+    std::vector<Ent> table(8, Ent{-1, 0});
+    uint64_t mask = 7, used = 0, fill = 0;
+    auto insert_clean = [&](std::vector<Ent>& tab, uint64_t m, Ent e) {
+        uint64_t i = (uint64_t)e.hash & m, perturb = (uint64_t)e.hash;
+        while (tab[i & m].idx >= 0) { i = i * 5 + perturb + 1; perturb >>= 5; }
+        tab[i & m] = e;
+    };
+    for (int64_t k = 0; k < (int64_t)keys.size(); k++) {
+        int64_t h = py2_hash(keys[k]);
+        uint64_t i = (uint64_t)h & mask, perturb = (uint64_t)h;
+        bool found = false;
+        while (true) {
+            Ent& e = table[i & mask];
+            if (e.idx < 0) break;
+            if (e.hash == h && keys[e.idx] == keys[k]) { found = true; break; }
+            i = i * 5 + perturb + 1; perturb >>= 5;
+        }
+        if (found) continue;
+        table[i & mask] = Ent{k, h};
+        used++; fill++;
+        if (fill * 3 >= (mask + 1) * 2) {
+            uint64_t minused = used > 50000 ? used * 2 : used * 4, newsize = 8;
+            while (newsize <= minused) newsize <<= 1;
+            std::vector<Ent> nt(newsize, Ent{-1, 0});
+            for (const Ent& e : table) if (e.idx >= 0) insert_clean(nt, newsize - 1, e);
+            table.swap(nt);
+            mask = newsize - 1;
+            fill = used;
+        }
+    }
+    order.clear();
+    for (const Ent& e : table) if (e.idx >= 0) order.push_back(e.idx);
+}
+
+// dense ids, barcode strings and the matrix column order.  Host work (sort by first line, the
+// py2 set emulation) overlaps whatever the caller queued on the stream before calling this.
+int build_barcodes(Ctx* c) {
+    if (c->bc_ready) return CRATAC_OK;
+    int64_t* st = c->d_status.as<int64_t>();
+    int64_t nb = c->n_barcodes;
+    size_t nn = (size_t)std::max<int64_t>(nb, 1);
+    CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
+    CRATAC_TRY(c->d_dense_to_col.reserve(4 * nn)); CRATAC_TRY(c->d_col_to_dense.reserve(4 * nn));
+    cudaStream_t s = c->stream;
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
+    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<unsigned long long>(), c->d_bc_first.as<unsigned long long>(),
+                                                               c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
+                                                               c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
+                                                               reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    const int stride = 64;
+    DevBuf d_txt;
+    CRATAC_TRY(d_txt.reserve(nn * stride));
+    std::vector<long long> textoff(nn);
+    std::vector<unsigned long long> first(nn);
+    if (nb > 0) {
+        // max barcode length check happens on the packed lengths
+        k_gather_barcode_text<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(c->d_text, c->d_dense_textoff.as<long long>(), nb, stride, d_txt.as<char>());
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    std::vector<char> txt(nn * stride);
+    CRATAC_CUDA(cudaMemcpyAsync(txt.data(), d_txt.p, nn * stride, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaMemcpyAsync(first.data(), c->d_dense_first.p, 8 * nn, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaMemcpyAsync(textoff.data(), c->d_dense_textoff.p, 8 * nn, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    d_txt.release();
+    std::vector<std::string> names((size_t)nb);
+    for (int64_t d = 0; d < nb; d++) {
+        int len = (int)(textoff[d] & 255);
+        if (len >= stride) { set_error("barcode longer than %d bytes", stride - 1); return CRATAC_ERR_PARSE; }
+        names[d].assign(txt.data() + d * stride, (size_t)len);
+    }
+    // first-appearance order
+    std::vector<int64_t> by_first((size_t)nb);
+    for (int64_t d = 0; d < nb; d++) by_first[d] = d;
+    std::sort(by_first.begin(), by_first.end(), [&](int64_t x, int64_t y) { return first[x] < first[y]; });
+    std::vector<int64_t> col_to_dense((size_t)nb);
+    if (c->bc_order == CRATAC_BC_ORDER_FIRST_SEEN) {
+        col_to_dense = by_first;
+    } else if (c->bc_order == CRATAC_BC_ORDER_SORTED) {
+        col_to_dense = by_first;
+        std::sort(col_to_dense.begin(), col_to_dense.end(), [&](int64_t x, int64_t y) { return names[x] < names[y]; });
+    } else {
+        std::vector<std::string> ins((size_t)nb);
+        for (int64_t k = 0; k < nb; k++) ins[k] = names[by_first[k]];
+        std::vector<int64_t> order;
+        py2_set_order(ins, order);
+        if ((int64_t)order.size() != nb) { set_error("duplicate barcode strings in dictionary"); return CRATAC_ERR_INTERNAL; }
+        for (int64_t j = 0; j < nb; j++) col_to_dense[j] = by_first[order[j]];
+    }
+    std::vector<int32_t> c2d((size_t)nn), d2c((size_t)nn);
+    c->barcodes.resize((size_t)nb);
+    for (int64_t j = 0; j < nb; j++) {
+        c2d[j] = (int32_t)col_to_dense[j];
+        d2c[col_to_dense[j]] = (int32_t)j;
+        c->barcodes[j] = names[col_to_dense[j]];
+    }
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_col_to_dense.p, c2d.data(), 4 * nn, cudaMemcpyHostToDevice, s));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_dense_to_col.p, d2c.data(), 4 * nn, cudaMemcpyHostToDevice, s));
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    c->bc_ready = true;
+    return CRATAC_OK;
+}
+
+// ------------------------------------------------------------------ synthetic text encoder (bench / tests)
+__device__ __forceinline__ int dec_digits(uint32_t v) {
+    int n = 1;
+    while (v >= 10) { v /= 10; n++; }
+    return n;
+}
+__device__ __forceinline__ char* put_uint(char* p, uint32_t v) {
+    int n = dec_digits(v);
+    for (int i = n - 1; i >= 0; i--) { p[i] = (char)('0' + v % 10); v /= 10; }
+    return p + n;
+}
+
+struct EncArgs {
+    int64_t n;
+    const int32_t *chrom, *start, *end, *dup;
+    const uint32_t* seq;
+    const char* names;     // 32 bytes per contig, NUL padded
+    const int32_t* name_len;
+    int64_t* line_off;     // in: lengths (pass 0 writes), then exclusive offsets
+    char* out;
+};
+
+__global__ void k_encode_len(EncArgs a) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    a.line_off[i] = a.name_len[a.chrom[i]] + 1 + dec_digits((uint32_t)a.start[i]) + 1 + dec_digits((uint32_t)a.end[i]) + 1 + 18 + 1 +
+                    dec_digits((uint32_t)a.dup[i]) + 1;
+}
+
+__global__ void k_encode_write(EncArgs a) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    char* p = a.out + a.line_off[i];
+    int c = a.chrom[i];
+    for (int k = 0; k < a.name_len[c]; k++) *p++ = a.names[c * 32 + k];
+    *p++ = '\t';
+    p = put_uint(p, (uint32_t)a.start[i]); *p++ = '\t';
+    p = put_uint(p, (uint32_t)a.end[i]); *p++ = '\t';
+    uint32_t s = a.seq[i];
+    const char L[4] = {'A', 'C', 'T', 'G'};   // inverse of (ch >> 1) & 3
+#pragma unroll
+    for (int k = 0; k < 16; k++) *p++ = L[(s >> (30 - 2 * k)) & 3u];
+    *p++ = '-'; *p++ = '1'; *p++ = '\t';
+    p = put_uint(p, (uint32_t)a.dup[i]);
+    *p++ = '\n';
+}
+
+int encode_text(Ctx* c, int64_t n, const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, const uint32_t* d_seq,
+                const int32_t* d_dup, char* d_out, int64_t cap, int64_t* nbytes) {
+    std::vector<char> names((size_t)c->n_contigs * 32, 0);
+    std::vector<int32_t> lens((size_t)c->n_contigs);
+    for (int i = 0; i < c->n_contigs; i++) {
+        if (c->contig_names[i].size() > 31) { set_error("contig name too long for the encoder"); return CRATAC_ERR_ARG; }
+        memcpy(&names[(size_t)i * 32], c->contig_names[i].data(), c->contig_names[i].size());
+        lens[i] = (int32_t)c->contig_names[i].size();
+    }
+    DevBuf d_names, d_lens, d_off;
+    CRATAC_TRY(d_names.reserve(names.size())); CRATAC_TRY(d_lens.reserve(4 * lens.size())); CRATAC_TRY(d_off.reserve(8 * (size_t)(n + 1)));
+    CRATAC_CUDA(cudaMemcpyAsync(d_names.p, names.data(), names.size(), cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(d_lens.p, lens.data(), 4 * lens.size(), cudaMemcpyHostToDevice, c->stream));
+    EncArgs a;
+    a.n = n; a.chrom = d_chrom; a.start = d_start; a.end = d_end; a.dup = d_dup; a.seq = d_seq;
+    a.names = d_names.as<char>(); a.name_len = d_lens.as<int32_t>(); a.line_off = d_off.as<int64_t>(); a.out = d_out;
+    int64_t total = 0;
+    if (n > 0) {
+        k_encode_len<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a);
+        CRATAC_CUDA(cudaGetLastError());
+        CRATAC_TRY(exclusive_scan_i64(c, a.line_off, a.line_off, n, a.line_off + n));
+        CRATAC_CUDA(cudaMemcpyAsync(&total, a.line_off + n, 8, cudaMemcpyDeviceToHost, c->stream));
+        CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *nbytes = total;
+    int rc = CRATAC_OK;
+    if (d_out != nullptr && cap > 0) {
+        if (total > cap) { set_error("encode buffer too small: need %lld", (long long)total); rc = CRATAC_ERR_ARG; }
+        else if (n > 0) {
+            k_encode_write<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a);
+            if (cudaGetLastError() != cudaSuccess) rc = CRATAC_ERR_CUDA;
+            cudaStreamSynchronize(c->stream);
+        }
+    }
+    d_names.release(); d_lens.release(); d_off.release();
+    return rc;
+}
+
+}  // namespace cratac

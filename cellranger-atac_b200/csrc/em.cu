@@ -1,0 +1,342 @@
+// K4: the peak-caller mixture fit in one CTA, fp64.  Replaces lib/python/analysis/peaks.py:28-193
+// (estimate_final_threshold and everything under it) and lib/python/analysis/em_fitting.py:10-87.
+//
+// Model: frac_zero * Geom(p_zero) + frac_bg * NB(mean_bg, alpha_bg) + frac_sig * Geom(p_signal) fitted to
+// the histogram (value v_i, weight w_i).  The operation order follows the reference (SURVEY.md
+// Appendix A); reductions are tree sums instead of numpy pairwise / Python sequential sums, so
+// results agree to rounding, not bit for bit (stated tolerance: threshold identical, parameters
+// 1e-6 relative = the reference's own convergence epsilon).
+//
+// The one algebraic change: the NB dispersion fixed point (em_fitting.py:41-56) evaluates
+//     sum_i w_i * cumsum_j(alpha*j/(1+alpha*j))[v_i - 1]
+// once per inner iteration.  Swapping the sums gives  sum_j alpha*j/(1+alpha*j) * T(j)  with
+// T(j) = sum_{i: v_i > j} w_i, a suffix sum that only changes once per M-step; the inner iteration
+// is then one reduction over max(v) terms and no scan.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cratac {
+
+constexpr int EM_THREADS = 1024;
+constexpr int EM_WARPS = EM_THREADS / 32;
+
+struct EmArgs {
+    const int64_t* values;
+    const int64_t* weights;
+    int64_t n_bins_host;       // < 0: read from status[ST_N_BINS]
+    int64_t* status;
+    double* params_out;        // [6]
+    double odds_ratio;
+    // work arrays
+    double* vd; double* wd; double* R0; double* R1; double* R2; double* Q; double* T;
+    int* first_gt;
+    int64_t work_n, work_v;
+};
+
+template <int K>
+__device__ __forceinline__ void block_sum(double (&x)[K], double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) x[j] += __shfl_xor_sync(0xffffffffu, x[j], d);
+    }
+    __syncthreads();   // previous readers of sm are done
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < K; j++) sm[warp * K + j] = x[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        double s = 0.0;
+        for (int w = 0; w < EM_WARPS; w++) s += sm[w * K + j];
+        x[j] = s;
+    }
+}
+
+__device__ __forceinline__ double block_max(double x, double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, d));
+    __syncthreads();
+    if (lane == 0) sm[warp] = x;
+    __syncthreads();
+    double m = sm[0];
+    for (int w = 1; w < EM_WARPS; w++) m = fmax(m, sm[w]);
+    return m;
+}
+
+struct Theta { double p_zero, mean_bg, alpha_bg, p_signal, f_zero, f_bg; };
+
+__device__ __forceinline__ double nb_pmf(double k, double n, double p) {
+    // legacy scipy nbinom._pmf: exp(gammaln(n+k) - gammaln(k+1) - gammaln(n) + n*log(p) + k*log1p(-p))
+    return exp(lgamma(n + k) - lgamma(k + 1.0) - lgamma(n) + n * log(p) + k * log1p(-p));
+}
+
+// suffix sums Q[i] = sum_{i' >= i} R1[i'] * w[i'] (block-wide, n arbitrary), Q[n] = 0
+__device__ void suffix_sums(const EmArgs& a, int n, double* sm) {
+    // process blocks of EM_THREADS from the top; carry in shared
+    __shared__ double s_carry;
+    __shared__ double s_warp[EM_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry = 0.0; a.Q[n] = 0.0; }
+    __syncthreads();
+    for (int hi = n; hi > 0; hi -= EM_THREADS) {
+        int i = hi - 1 - tid;            // thread 0 takes the top element
+        double x = (i >= 0) ? a.R1[i] * a.wd[i] : 0.0;
+        double incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        double off = s_carry;
+        for (int w = 0; w < warp; w++) off += s_warp[w];
+        if (i >= 0) a.Q[i] = off + incl;
+        __syncthreads();
+        if (tid == EM_THREADS - 1) s_carry = off + incl;
+        __syncthreads();
+    }
+    (void)sm;
+}
+
+// M-step (peaks.py:90-128).  Returns false when the reference would raise ZeroDivisionError.
+__device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, long long& inner_total) {
+    const int tid = threadIdx.x;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // N0 K0 N1 M1 N2 K2 vmax1
+    double vmax1 = 0.0;
+    for (int i = tid; i < n; i += EM_THREADS) {
+        double v = a.vd[i], w = a.wd[i];
+        double r0 = a.R0[i], r1 = a.R1[i], r2 = a.R2[i];
+        double o0 = w * r0, o1 = w * r1, o2 = w * r2;
+        acc[0] += o0; acc[1] += v * o0;
+        acc[2] += o1; acc[3] += v * o1;
+        acc[4] += o2; acc[5] += v * o2;
+        if (r1 > 0.0) vmax1 = fmax(vmax1, v);
+    }
+    double s6[6] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]};
+    block_sum<6>(s6, sm);
+    vmax1 = block_max(vmax1, sm);
+    double N0 = s6[0], K0 = s6[1], N1 = s6[2], M1 = s6[3], N2 = s6[4], K2 = s6[5];
+    if (N0 == 0.0 || N2 == 0.0) return false;   // MLE_geometric_parameter on an empty mask: 0 / (0 + 0)
+    th.p_zero = N0 / (N0 + (K0 - N0));          // em_fitting.py:86-87
+    th.p_signal = N2 / (N2 + (K2 - N2));
+    double mu = M1 / N1;                        // em_fitting.py:14 (NaN when the mask is empty, like numpy)
+    th.mean_bg = mu;
+    double FT = N0 + N1 + N2;
+    th.f_zero = N0 / FT;
+    th.f_bg = N1 / FT;
+    // ---- MLE_dispersion (em_fitting.py:35-74)
+    if (N1 == 0.0) { th.alpha_bg = 1e-6; return true; }      // (counts <= 0).all() on an empty array
+    double sq[1] = {0.0};
+    for (int i = tid; i < n; i += EM_THREADS) {
+        double d = mu - a.vd[i];
+        sq[0] += d * d * (a.wd[i] * a.R1[i]);
+    }
+    block_sum<1>(sq, sm);
+    double var = sq[0] / N1;
+    double alpha = fmax(1e-6, (var - mu) / (mu * mu));        // MOM_dispersion
+    if (vmax1 > 1e8 || !(var > mu)) { th.alpha_bg = alpha; return true; }
+    // tail weights T(j) = sum_{i: v_i > j} w_i R1_i  for j = 0 .. vmax1-1
+    suffix_sums(a, n, sm);
+    const int jmax = (int)vmax1;               // terms j = 0 .. jmax-1  (np.arange(max(counts)))
+    for (int j = tid; j < jmax; j += EM_THREADS) a.T[j] = a.Q[a.first_gt[j]];
+    __syncthreads();
+    double newv = alpha;
+    int it = 0;
+    for (; it < 10000; it++) {
+        double part[1] = {0.0};
+        for (int j = tid + 1; j < jmax; j += EM_THREADS) {    // j = 0 contributes 0
+            double aj = alpha * (double)j;
+            part[0] += aj / (1.0 + aj) * a.T[j];
+        }
+        block_sum<1>(part, sm);
+        newv = log(1.0 + alpha * mu) / (mu - part[0] / N1);
+        if (2.0 * fabs(newv - alpha) / (newv + alpha) < 1e-6) { it++; break; }
+        alpha = newv;
+    }
+    inner_total += it;
+    th.alpha_bg = newv;
+    return true;
+}
+
+// E-step (peaks.py:66-87)
+__device__ void e_step(const EmArgs& a, int n, const Theta& th) {
+    const double f_sig = 1.0 - th.f_zero - th.f_bg;
+    const double nn = 1.0 / th.alpha_bg;
+    const double pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+    for (int i = threadIdx.x; i < n; i += EM_THREADS) {
+        double v = a.vd[i];
+        double z = pow(1.0 - th.p_zero, v - 1.0) * th.p_zero * th.f_zero;
+        double b = nb_pmf(v, nn, pp) * th.f_bg;
+        double s = pow(1.0 - th.p_signal, v - 1.0) * th.p_signal * f_sig;
+        double tot = z + b + s;
+        if (tot == 0.0) { a.R0[i] = 0.0; a.R1[i] = 0.0; a.R2[i] = 0.0; }
+        else { a.R0[i] = z / tot; a.R1[i] = b / tot; a.R2[i] = s / tot; }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void normalize(Theta& t) {   // peaks.py:131-141
+    if (t.p_zero < t.p_signal) {
+        double pz = t.p_signal, ps = t.p_zero, fz = 1.0 - (t.f_zero + t.f_bg);
+        t.p_zero = pz; t.p_signal = ps; t.f_zero = fz;
+    }
+}
+
+__device__ __forceinline__ bool moved(const Theta& last, const Theta& cur, double eps) {
+    // any(abs(last[k] - params[k]) / params[k] > eps)
+    return (fabs(last.p_zero - cur.p_zero) / cur.p_zero > eps) || (fabs(last.mean_bg - cur.mean_bg) / cur.mean_bg > eps) ||
+           (fabs(last.alpha_bg - cur.alpha_bg) / cur.alpha_bg > eps) || (fabs(last.p_signal - cur.p_signal) / cur.p_signal > eps) ||
+           (fabs(last.f_zero - cur.f_zero) / cur.f_zero > eps) || (fabs(last.f_bg - cur.f_bg) / cur.f_bg > eps);
+}
+
+// estimate_parameters (peaks.py:144-170).  ok=false => ZeroDivisionError in the reference.
+__device__ bool estimate_parameters(const EmArgs& a, int n, int t0, bool seeded, Theta& th, double* sm, long long& iters, long long& inner) {
+    const int tid = threadIdx.x;
+    if (!seeded) {
+        for (int i = tid; i < n; i += EM_THREADS) {
+            double v = a.vd[i];
+            a.R0[i] = (v <= (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
+            a.R1[i] = (v <= (double)t0 && v > (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
+            a.R2[i] = (v > (double)t0) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (!m_step(a, n, th, sm, inner)) return false;
+    }
+    Theta last = th;
+    bool have_last = false;
+    int i = 0;
+    while (i < 500 && (!have_last || moved(last, th, 1e-6))) {
+        i++;
+        e_step(a, n, th);
+        last = th;
+        have_last = true;
+        Theta nt = th;
+        if (!m_step(a, n, nt, sm, inner)) return false;
+        normalize(nt);
+        th = nt;
+    }
+    iters += i;
+    return true;
+}
+
+__global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
+    __shared__ double sm[EM_WARPS * 8];
+    __shared__ int s_int;
+    const int tid = threadIdx.x;
+    int64_t n64 = a.n_bins_host >= 0 ? a.n_bins_host : a.status[ST_N_BINS];
+    const int n = (int)n64;
+    long long iters = 0, inner = 0;
+    // ---- gate (peaks.py:176-177)
+    double tot[1] = {0.0};
+    double vmax = 0.0;
+    for (int i = tid; i < n; i += EM_THREADS) {
+        double v = (double)a.values[i], w = (double)a.weights[i];
+        a.vd[i] = v; a.wd[i] = w;
+        tot[0] += w;
+        vmax = fmax(vmax, v);
+    }
+    block_sum<1>(tot, sm);
+    vmax = block_max(vmax, sm);
+    if (n < 30 || tot[0] < 1e5) {
+        if (tid == 0) {
+            a.status[ST_THRESHOLD] = DEFAULT_THRESHOLD; a.status[ST_HAS_PARAMS] = 0;
+            a.status[ST_EM_ITERS] = 0; a.status[ST_EM_INNER] = 0;
+            for (int k = 0; k < 6; k++) a.params_out[k] = 0.0;
+        }
+        return;
+    }
+    if (n > a.work_n || (int64_t)vmax + 2 > a.work_v) { if (tid == 0) raise_error(a.status, CRATAC_ERR_CAPACITY, n); return; }
+    // first_gt[j] = first bin index i with v_i > j   (values ascending)
+    {
+        const int jn = (int)vmax + 1;
+        for (int j = tid; j < jn; j += EM_THREADS) {
+            int lo = 0, hi = n;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (a.vd[mid] > (double)j) hi = mid; else lo = mid + 1; }
+            a.first_gt[j] = lo;
+        }
+    }
+    // ---- simple_threshold_estimate (peaks.py:28-40); thread 0, sequential exact integer cumsum
+    if (tid == 0) {
+        long long total = 0;
+        int first_above = -1, n_above = 0;
+        for (int i = 0; i < n; i++)
+            if (a.values[i] > DEFAULT_THRESHOLD) { if (first_above < 0) first_above = i; n_above++; total += a.values[i] * a.weights[i]; }
+        int t0 = -1;
+        long long cum = 0;
+        bool any = false;
+        for (int i = 0; i < n; i++) {
+            if (a.values[i] <= DEFAULT_THRESHOLD) continue;
+            cum += a.values[i] * a.weights[i];
+            if ((double)cum / (double)total <= 0.25) { t0 = (int)a.values[i]; any = true; }
+        }
+        if (!any) t0 = (n_above >= 2) ? (int)a.values[first_above + 1] : -1;   // count_values[1] (IndexError if missing)
+        s_int = t0;
+    }
+    __syncthreads();
+    const int t0 = s_int;
+    if (t0 < 0) { if (tid == 0) raise_error(a.status, CRATAC_ERR_EM_INDEX, n); return; }
+
+    Theta th;
+    bool ok = estimate_parameters(a, n, t0, false, th, sm, iters, inner);
+    int tries = 0;
+    while (ok && (1.0 / th.p_zero < th.mean_bg) && tries < 3) {   // peaks.py:183-191
+        Theta seed;
+        seed.p_zero = th.p_signal; seed.mean_bg = 1.0 / th.p_zero; seed.alpha_bg = th.alpha_bg; seed.p_signal = 1.0 / th.mean_bg;
+        seed.f_zero = 1.0 - (th.f_zero + th.f_bg); seed.f_bg = th.f_bg;
+        th = seed;
+        ok = estimate_parameters(a, n, t0, true, th, sm, iters, inner);
+        tries++;
+    }
+    if (!ok) { if (tid == 0) raise_error(a.status, CRATAC_ERR_EM_ZERODIV, n); return; }
+
+    // ---- estimate_threshold (peaks.py:43-63): largest x in [0, 1000) with sig/bg < odds
+    const double f_sig = 1.0 - th.f_zero - th.f_bg;
+    const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+    double best = -1.0;
+    for (int x = tid; x < 1000; x += EM_THREADS) {
+        double xv = (double)x;
+        double ysig = f_sig * (pow(1.0 - th.p_signal, xv) * th.p_signal);
+        double ybg = th.f_zero * (pow(1.0 - th.p_zero, xv) * th.p_zero) + th.f_bg * nb_pmf(xv, nn, pp);
+        if (ysig / ybg < a.odds_ratio) best = xv;
+    }
+    best = block_max(best, sm);
+    if (tid == 0) {
+        a.status[ST_THRESHOLD] = best < 0.0 ? 0 : (int64_t)best;   // None in the reference filters nothing == threshold 0
+        a.status[ST_HAS_PARAMS] = best < 0.0 ? 2 : 1;
+        a.status[ST_EM_ITERS] = iters; a.status[ST_EM_INNER] = inner;
+        a.params_out[0] = th.p_zero; a.params_out[1] = th.mean_bg; a.params_out[2] = th.alpha_bg;
+        a.params_out[3] = th.p_signal; a.params_out[4] = th.f_zero; a.params_out[5] = th.f_bg;
+    }
+}
+
+static int em_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio) {
+    const int64_t work_n = 1 << 16, work_v = HIST_CAP + 2;
+    size_t doubles = (size_t)work_n * 6 + 2 + (size_t)work_v;
+    CRATAC_TRY(c->d_em_work.reserve(doubles * 8 + (size_t)work_v * 4));
+    CRATAC_TRY(c->d_em_params.reserve(8 * 8));
+    EmArgs a;
+    a.values = d_values; a.weights = d_weights; a.n_bins_host = n_bins_host; a.status = c->d_status.as<int64_t>();
+    a.params_out = c->d_em_params.as<double>(); a.odds_ratio = odds_ratio;
+    double* w = c->d_em_work.as<double>();
+    a.vd = w; w += work_n; a.wd = w; w += work_n; a.R0 = w; w += work_n; a.R1 = w; w += work_n; a.R2 = w; w += work_n;
+    a.Q = w; w += work_n + 2; a.T = w; w += work_v;
+    a.first_gt = reinterpret_cast<int*>(w);
+    a.work_n = work_n; a.work_v = work_v;
+    k_em_fit<<<1, EM_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+int fit_threshold_device(Ctx* c, double odds_ratio) {
+    return em_launch(c, c->d_hist_values.as<int64_t>(), c->d_hist_weights.as<int64_t>(), -1, odds_ratio);
+}
+
+int fit_threshold_arrays(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n, double odds_ratio) {
+    return em_launch(c, d_values, d_weights, n, odds_ratio);
+}
+
+}  // namespace cratac

@@ -1,0 +1,277 @@
+// K6-K8: fragment ends x peaks, counted per barcode, into canonical CSC.  Replaces
+// generate_peak_matrix/__init__.py:107-119 (per fragment: two bisects in tenkit Regions
+// (tenkit/lib/python/tenkit/regions.py:136-145), Counter[(barcode, peak)] += 1, COO -> CSC) for ALL
+// barcodes in one pass instead of 30 barcode chunks that each re-read the file.
+//
+//   K6a  count   per fragment: upper_bound(peak starts, pos) - 1, half-open containment test, for
+//                pos in (start, stop) -- stop used as is, dup_count ignored; hits per barcode (REDG).
+//   scan         hits per barcode -> segment offsets.
+//   K6b  scatter same search, peak row written into the barcode's segment.
+//   K7   reduce  per barcode segment: sort the rows (bitonic in shared memory for short segments,
+//                range-partitioned counting in shared memory for long ones) and run-length reduce
+//                to (row, count).
+//   K8   build   indptr = scan of distinct counts in column order; copy (row, count) segments to
+//                indices int64 / data int32.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace cratac {
+
+constexpr int MX_THREADS = 256;
+constexpr int SORT_SMALL = 4096;        // bitonic path capacity
+constexpr int SORT_THREADS = 256;
+constexpr int COUNT_RANGE = 24576;      // counters per pass on the dense path (96 KiB)
+constexpr int COUNT_THREADS = 512;
+
+struct OverlapArgs {
+    int64_t n;
+    const int32_t *chrom, *start, *end, *bc;
+    const int32_t* slot_to_dense;          // null: bc already dense
+    const int64_t* peak_off;               // per contig
+    const int32_t *pk_start, *pk_end, *pk_row;
+    int32_t* bc_hits;                      // per dense barcode (count pass)
+    const int64_t* seg_off;                // scatter pass
+    unsigned int* cursor;
+    int32_t* hits;
+};
+
+__device__ __forceinline__ int find_peak(const OverlapArgs& a, int c, int pos) {
+    int64_t lo = a.peak_off[c], hi = a.peak_off[c + 1];
+    const int64_t base = lo;
+    while (lo < hi) {                       // bisect.bisect(starts, pos): first start > pos
+        int64_t mid = (lo + hi) >> 1;
+        if (pos < __ldg(&a.pk_start[mid])) hi = mid; else lo = mid + 1;
+    }
+    int64_t idx = lo - 1;
+    if (idx < base) return -1;
+    if (pos < __ldg(&a.pk_end[idx])) return __ldg(&a.pk_row[idx]);   // pos >= start holds by construction
+    return -1;
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = a.chrom[i];
+        int b = a.bc[i];
+        if (a.slot_to_dense) b = a.slot_to_dense[b];
+        int r0 = find_peak(a, c, a.start[i]);
+        int r1 = find_peak(a, c, a.end[i]);
+        int nh = (r0 >= 0) + (r1 >= 0);
+        if (nh == 0 || b < 0) continue;
+        if (!SCATTER) {
+            atomicAdd(&a.bc_hits[b], nh);
+        } else {
+            unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nh);
+            int64_t o = a.seg_off[b] + p;
+            if (r0 >= 0) a.hits[o++] = r0;
+            if (r1 >= 0) a.hits[o] = r1;
+        }
+    }
+}
+
+// ---- K7: per-barcode sort + run-length reduce -----------------------------------------------------
+// short segments: bitonic sort of <= SORT_SMALL rows in shared memory; one CTA per barcode
+__global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
+                                                                int64_t n_bc, int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
+                                                                int32_t* __restrict__ nnz_col) {
+    __shared__ int s[SORT_SMALL];
+    __shared__ int warp_tot[SORT_THREADS / 32];
+    __shared__ int s_base;
+    for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
+        const int64_t o0 = seg_off[b];
+        const int64_t len64 = seg_off[b + 1] - o0;
+        if (len64 > SORT_SMALL) continue;                 // long path
+        const int len = (int)len64;
+        if (len == 0) { if (threadIdx.x == 0) nnz_col[b] = 0; continue; }
+        int m = 32;
+        while (m < len) m <<= 1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += SORT_THREADS) s[i] = i < len ? hits[o0 + i] : 0x7fffffff;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < m; i += SORT_THREADS) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        int x = s[i], y = s[ixj];
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) { s[i] = y; s[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // run-length reduce, in order
+        if (threadIdx.x == 0) s_base = 0;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int i0 = 0; i0 < len; i0 += SORT_THREADS) {
+            int i = i0 + threadIdx.x;
+            int head = (i < len) && (i == 0 || s[i] != s[i - 1]);
+            int x = head;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+            if (lane == 31) warp_tot[warp] = x;
+            __syncthreads();
+            int off = s_base;
+            for (int w = 0; w < warp; w++) off += warp_tot[w];
+            if (head) {
+                int e = i + 1;
+                while (e < len && s[e] == s[i]) e++;
+                out_row[o0 + off + x - 1] = s[i];
+                out_cnt[o0 + off + x - 1] = e - i;
+            }
+            __syncthreads();
+            if (threadIdx.x == SORT_THREADS - 1) s_base = off + x;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) nnz_col[b] = s_base;
+    }
+}
+
+// long segments: counting over peak-row ranges of COUNT_RANGE rows held in shared memory
+__global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
+                                                                 int64_t n_bc, const int64_t* __restrict__ status, int64_t n_peaks_host,
+                                                                 int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
+                                                                 int32_t* __restrict__ nnz_col) {
+    extern __shared__ int cnt[];           // COUNT_RANGE
+    __shared__ int warp_tot[COUNT_THREADS / 32];
+    __shared__ int s_base;
+    const int64_t n_peaks = n_peaks_host >= 0 ? n_peaks_host : status[ST_N_PEAKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
+        const int64_t o0 = seg_off[b];
+        const int64_t len = seg_off[b + 1] - o0;
+        if (len <= SORT_SMALL) continue;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = 0;
+        for (int64_t r0 = 0; r0 < n_peaks; r0 += COUNT_RANGE) {
+            for (int i = threadIdx.x; i < COUNT_RANGE; i += COUNT_THREADS) cnt[i] = 0;
+            __syncthreads();
+            for (int64_t i = threadIdx.x; i < len; i += COUNT_THREADS) {
+                int64_t r = (int64_t)hits[o0 + i] - r0;
+                if ((uint64_t)r < (uint64_t)COUNT_RANGE) atomicAdd(&cnt[r], 1);
+            }
+            __syncthreads();
+            const int lim = (n_peaks - r0) < (int64_t)COUNT_RANGE ? (int)(n_peaks - r0) : COUNT_RANGE;
+            for (int i0 = 0; i0 < lim; i0 += COUNT_THREADS) {
+                int i = i0 + threadIdx.x;
+                int v = i < lim ? cnt[i] : 0;
+                int flag = v != 0;
+                int x = flag;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+                if (lane == 31) warp_tot[warp] = x;
+                __syncthreads();
+                int off = s_base;
+                for (int w = 0; w < warp; w++) off += warp_tot[w];
+                if (flag) { out_row[o0 + off + x - 1] = (int32_t)(r0 + i); out_cnt[o0 + off + x - 1] = v; }
+                __syncthreads();
+                if (threadIdx.x == COUNT_THREADS - 1) s_base = off + x;
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) nnz_col[b] = s_base;
+    }
+}
+
+// ---- K8 -------------------------------------------------------------------------------------------
+__global__ void k_gather_nnz(const int32_t* __restrict__ nnz_col, const int32_t* __restrict__ col_to_dense, int64_t n_bc, int32_t* __restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_bc) out[j] = nnz_col[col_to_dense ? col_to_dense[j] : j];
+}
+
+// one warp per column
+__global__ void __launch_bounds__(256) k_csc_copy(const int32_t* __restrict__ out_row, const int32_t* __restrict__ out_cnt, const int64_t* __restrict__ seg_off,
+                                                   const int32_t* __restrict__ col_to_dense, const int64_t* __restrict__ indptr, int64_t n_bc,
+                                                   int64_t* __restrict__ indices, int32_t* __restrict__ data) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < n_bc; j += n_warps) {
+        int64_t d = col_to_dense ? col_to_dense[j] : j;
+        int64_t src = seg_off[d], dst = indptr[j], len = indptr[j + 1] - dst;
+        for (int64_t k = lane; k < len; k += 32) {
+            indices[dst + k] = (int64_t)out_row[src + k];
+            data[dst + k] = out_cnt[src + k];
+        }
+    }
+}
+
+int build_barcodes(Ctx* c);   // decode.cu
+
+int peak_matrix_device(Ctx* c) {
+    cudaStream_t s = c->stream;
+    int64_t* st = c->d_status.as<int64_t>();
+    const int64_t n = c->n_fragments, nb = c->n_barcodes;
+    size_t nbb = (size_t)std::max<int64_t>(nb, 1);
+    CRATAC_TRY(c->d_bc_hits.reserve(4 * nbb));
+    CRATAC_TRY(c->d_seg_off.reserve(8 * (nbb + 1)));
+    CRATAC_TRY(c->d_cursor.reserve(4 * nbb));
+    CRATAC_TRY(c->d_nnz_col.reserve(4 * nbb * 2));
+    CRATAC_TRY(c->d_indptr.reserve(8 * (nbb + 1)));
+    CRATAC_CUDA(cudaMemsetAsync(c->d_bc_hits.p, 0, 4 * nbb, s));
+    CRATAC_CUDA(cudaMemsetAsync(c->d_cursor.p, 0, 4 * nbb, s));
+    OverlapArgs a;
+    a.n = n; a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>(); a.bc = c->d_bc.as<int32_t>();
+    a.slot_to_dense = c->bc_is_slot ? c->d_slot_to_dense.as<int32_t>() : nullptr;
+    a.peak_off = c->d_peak_off.as<int64_t>();
+    a.pk_start = c->d_peak_start.as<int32_t>(); a.pk_end = c->d_peak_end.as<int32_t>(); a.pk_row = c->d_peak_row.as<int32_t>();
+    a.bc_hits = c->d_bc_hits.as<int32_t>(); a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = nullptr;
+    int grid = (int)std::min<int64_t>((n + MX_THREADS - 1) / MX_THREADS, (int64_t)NUM_SMS * 16);
+    if (grid < 1) grid = 1;
+    k_overlap<false><<<grid, MX_THREADS, 0, s>>>(a);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, a.bc_hits, c->d_seg_off.as<int64_t>(), nb, c->d_seg_off.as<int64_t>() + nb));
+    // K (total hits) sizes the hit buffers: one host round trip here (8 bytes)
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    const int64_t K = c->h_status[ST_N_HITS];
+    size_t kk = (size_t)std::max<int64_t>(K, 1);
+    CRATAC_TRY(c->d_hits.reserve(4 * kk)); CRATAC_TRY(c->d_out_row.reserve(4 * kk)); CRATAC_TRY(c->d_out_cnt.reserve(4 * kk));
+    a.hits = c->d_hits.as<int32_t>();
+    k_overlap<true><<<grid, MX_THREADS, 0, s>>>(a);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    int32_t* nnz_col = c->d_nnz_col.as<int32_t>();
+    int32_t* nnz_ordered = nnz_col + nbb;
+    if (nb > 0) {
+        static bool configured = false;
+        if (!configured) {
+            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4));
+            configured = true;
+        }
+        int g1 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 32);
+        k_reduce_small<<<g1, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
+        int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
+        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4, s>>>(a.hits, a.seg_off, nb, st, c->peaks_on_device_count ? -1 : c->n_peaks,
+                                                                 c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
+        c->launches += 2;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    // column order (host work of build_barcodes overlaps the kernels queued above)
+    CRATAC_TRY(build_barcodes(c));
+    const int32_t* c2d = c->d_col_to_dense.as<int32_t>();
+    if (nb > 0) {
+        k_gather_nnz<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(nnz_col, c2d, nb, nnz_ordered);
+        c->launches++;
+    }
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, nnz_ordered, c->d_indptr.as<int64_t>(), nb, c->d_indptr.as<int64_t>() + nb));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_NNZ], c->d_indptr.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    c->nnz = c->h_status[ST_NNZ];
+    size_t zz = (size_t)std::max<int64_t>(c->nnz, 1);
+    CRATAC_TRY(c->d_indices.reserve(8 * zz)); CRATAC_TRY(c->d_data.reserve(4 * zz));
+    if (nb > 0) {
+        int g = (int)std::min<int64_t>((nb * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
+        k_csc_copy<<<g, 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d, c->d_indptr.as<int64_t>(), nb,
+                                    c->d_indices.as<int64_t>(), c->d_data.as<int32_t>());
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    return CRATAC_OK;
+}
+
+}  // namespace cratac

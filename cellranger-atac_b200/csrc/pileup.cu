@@ -1,0 +1,542 @@
+// K2+K3 (fused) and K5: cut-site pileup, +-200 bp window sum, window-count histogram, threshold runs,
+// 500 bp merge.  Replaces count_cut_sites/__init__.py:94-104 and utils.py:105-115 +
+// detect_peaks/__init__.py:40-62.
+//
+// The dense per-base count array of the reference (int32[contig_len], 12.4 GB for GRCh38) never
+// exists in HBM.  The genome is cut into tiles of TILE_T bases; a persistent CTA takes tiles from
+// a ticket counter, finds the tile's fragments through a 1024-base position index (fragments are
+// start-sorted), scatters both cut sites of every fragment into a shared-memory count array with
+// shared-memory atomics, turns it into an inclusive prefix sum in place and reads
+//     W[p] = S[p+200] - S[p-201]            (window of count_cut_sites/__init__.py:100-101)
+// for the bases it owns.  Mode HIST bins W>0 (block-local bins, run-length aggregated, flushed once
+// per CTA); mode PEAKS emits the boundaries of the runs W >= threshold in genome order (a chained
+// prefix over tiles gives each tile its output offset) plus what the zero-gap rule of
+// write_chrom_bedgraph (count_cut_sites/__init__.py:36-37) needs; mode DUMP writes W (tests, bedgraph).
+// HBM traffic: 8 B per fragment (start, end) x (1 + halo overhead); everything per-base is on chip.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace cratac {
+
+constexpr int PU_THREADS = 512;
+constexpr int PU_CHUNK = 49;                        // odd -> bank-conflict-free thread-chunked access
+constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entries (25088)
+constexpr int PU_HALO_LO = HALF_WINDOW + 2;         // 202
+constexpr int PU_HALO_HI = HALF_WINDOW + 1;         // 201 (positions up to b + 200)
+constexpr int TILE_T = PU_N - PU_HALO_LO - PU_HALO_HI + 1;   // owned bases per tile (24686)
+constexpr int PU_OWN_CHUNK = (TILE_T + PU_THREADS - 1) / PU_THREADS | 1;   // 49, odd
+constexpr int PU_HB = 2048;                         // block-local histogram bins
+static_assert(PU_OWN_CHUNK * PU_THREADS >= TILE_T, "owned chunking must cover the tile");
+static_assert(TILE_T + 402 <= PU_N, "tile + halos must fit the shared array");
+
+enum { MODE_HIST = 0, MODE_PEAKS = 1, MODE_DUMP = 2 };
+
+int pileup_tile_bases() { return TILE_T; }
+
+struct PileupArgs {
+    const int32_t* start;
+    const int32_t* end;
+    const int64_t* frag_off;        // per contig
+    const int64_t* pos_index;
+    const int64_t* pidx_off;        // per contig
+    const int64_t* contig_lens;
+    const int64_t* contig_base;     // global run coordinate
+    const int64_t* tile_off;        // per contig (+total); non-primary contigs own no tiles
+    int n_contigs;
+    int64_t n_tiles;
+    int64_t* status;
+    unsigned long long* ghist;      // MODE_HIST
+    // MODE_PEAKS
+    unsigned long long* chain;      // per tile: ready bit | n_ends << 31 | n_starts   (inclusive prefix)
+    int64_t* run_start;
+    int64_t* run_end;
+    int64_t run_cap;
+    int4* tile_summary;             // first_nz_pos, first_nz_val, last_nz_pos, last_nz_val
+    int64_t* fills;                 // pairs (g0, g1)
+    int64_t fill_cap;
+    // MODE_DUMP
+    int32_t* dump_W;
+    int dump_contig;
+};
+
+__device__ __forceinline__ int block_excl_scan_i32(int v, int* warp_tot, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (PU_THREADS / 32) ? warp_tot[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += y;
+        }
+        if (lane < (PU_THREADS / 32)) warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int off = warp ? warp_tot[warp - 1] : 0;
+    if (total) *total = warp_tot[PU_THREADS / 32 - 1];
+    int r = off + x - v;
+    __syncthreads();   // warp_tot may be reused by the caller
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
+    extern __shared__ int smem[];
+    int* sc = smem;                       // PU_N
+    int* hist_s = smem + PU_N;            // PU_HB (MODE_HIST)
+    __shared__ int warp_tot[PU_THREADS / 32];
+    __shared__ long long s_tile;
+    __shared__ int s_first_nz, s_last_nz;
+    __shared__ unsigned long long s_chain_prev;
+    __shared__ int s_contig;
+
+    const int tid = threadIdx.x;
+    if (MODE == MODE_HIST)
+        for (int i = tid; i < PU_HB; i += PU_THREADS) hist_s[i] = 0;
+    const int maxpos = (int)a.status[ST_MAX_POS_LEN];
+    const int maxneg = (int)a.status[ST_MAX_NEG_LEN];
+    long long thr_ll = a.status[ST_THRESHOLD];
+    const int thr = thr_ll < 1 ? 1 : (thr_ll > 0x7fffffffLL ? 0x7fffffff : (int)thr_ll);
+    int loc_max = 0;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            long long t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
+            s_tile = t;
+            int c = 0;
+            if (t < a.n_tiles) {
+                int lo = 0, hi = a.n_contigs;   // last c with tile_off[c] <= t
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (a.tile_off[mid] <= t) lo = mid; else hi = mid;
+                }
+                c = lo;
+            }
+            s_contig = c;
+            s_first_nz = 0x7fffffff;
+            s_last_nz = -1;
+        }
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= a.n_tiles) break;
+        const int c = s_contig;
+        const int64_t L = a.contig_lens[c];
+        const int64_t ta = (tile - a.tile_off[c]) * (int64_t)TILE_T;           // first owned base
+        const int64_t tb = ta + TILE_T < L ? ta + TILE_T : L;                  // one past the last owned base
+        const int own = (int)(tb - ta);
+        const int64_t base = ta - PU_HALO_LO;                                  // genome position of sc[0]
+
+        if (MODE == MODE_DUMP && c != a.dump_contig) continue;
+
+        // ---- zero the count array
+#pragma unroll 7
+        for (int r = tid; r < PU_N; r += PU_THREADS) sc[r] = 0;
+        __syncthreads();
+
+        // ---- fragments that can touch [base, base + PU_N)
+        {
+            const int64_t f0 = a.frag_off[c], f1 = a.frag_off[c + 1];
+            const int64_t n_ent = a.pidx_off[c + 1] - a.pidx_off[c];
+            int64_t lo_pos = base - maxpos; if (lo_pos < 0) lo_pos = 0;
+            int64_t hi_pos = base + PU_N + maxneg;                              // exclusive
+            int64_t e_lo = lo_pos >> POS_INDEX_SHIFT;
+            int64_t e_hi = (hi_pos + (1 << POS_INDEX_SHIFT) - 1) >> POS_INDEX_SHIFT;
+            int64_t i_lo = e_lo >= n_ent - 1 ? (e_lo >= n_ent ? f1 : a.pos_index[a.pidx_off[c] + e_lo]) : a.pos_index[a.pidx_off[c] + e_lo];
+            int64_t i_hi = e_hi >= n_ent - 1 ? f1 : a.pos_index[a.pidx_off[c] + e_hi];
+            if (i_lo < f0) i_lo = f0;
+            for (int64_t i = i_lo + tid; i < i_hi; i += PU_THREADS) {
+                int64_t rs = (int64_t)a.start[i] - base;
+                int64_t re = (int64_t)a.end[i] - base;
+                if ((uint64_t)rs < (uint64_t)PU_N) atomicAdd(&sc[rs], 1);
+                if ((uint64_t)re < (uint64_t)PU_N) atomicAdd(&sc[re], 1);
+            }
+        }
+        __syncthreads();
+
+        // ---- in-place inclusive prefix sum (thread-chunked, odd chunk => no bank conflicts)
+        {
+            int* mine = sc + tid * PU_CHUNK;
+            int sum = 0;
+#pragma unroll 7
+            for (int j = 0; j < PU_CHUNK; j++) sum += mine[j];
+            int run = block_excl_scan_i32(sum, warp_tot, nullptr);
+#pragma unroll 7
+            for (int j = 0; j < PU_CHUNK; j++) { run += mine[j]; mine[j] = run; }
+        }
+        __syncthreads();
+
+        // W(k) for owned base ta + k:  S[k + 402] - S[k + 1]
+        const int k0 = tid * PU_OWN_CHUNK;
+        const int k1 = min(k0 + PU_OWN_CHUNK, own);
+
+        if (MODE == MODE_HIST) {
+            int cur = 0, runlen = 0;
+            for (int k = k0; k < k1; k++) {
+                int w = sc[k + 402] - sc[k + 1];
+                if (w == cur) { runlen++; continue; }
+                if (cur > 0) {
+                    if (cur < PU_HB) atomicAdd(&hist_s[cur], runlen);
+                    else if (cur < HIST_CAP) atomicAdd(&a.ghist[cur], (unsigned long long)runlen);
+                    else raise_error(a.status, CRATAC_ERR_CAPACITY, cur);
+                }
+                loc_max = max(loc_max, w);
+                cur = w; runlen = 1;
+            }
+            if (cur > 0) {
+                if (cur < PU_HB) atomicAdd(&hist_s[cur], runlen);
+                else if (cur < HIST_CAP) atomicAdd(&a.ghist[cur], (unsigned long long)runlen);
+                else raise_error(a.status, CRATAC_ERR_CAPACITY, cur);
+            }
+        } else if (MODE == MODE_DUMP) {
+            for (int k = k0; k < k1; k++) a.dump_W[ta + k] = sc[k + 402] - sc[k + 1];
+        } else {
+            // ---- run boundaries of (W >= thr), first/last non-zero W, in-tile zero gaps
+            int n_s = 0, n_e = 0;
+            int first_nz = 0x7fffffff, last_nz = -1;
+            int prev_w = 0;
+            if (k0 < k1 && (k0 > 0 || ta > 0)) prev_w = sc[k0 + 401] - sc[k0];   // W at base ta + k0 - 1
+            {
+                int pw = prev_w;
+                for (int k = k0; k < k1; k++) {
+                    int w = sc[k + 402] - sc[k + 1];
+                    bool sig = w >= thr, psig = pw >= thr;
+                    n_s += (sig && !psig);
+                    n_e += (!sig && psig);
+                    if (w != 0) { if (first_nz == 0x7fffffff) first_nz = k; last_nz = k; }
+                    else if (psig) {
+                        // W drops from pw >= thr to 0 in one step: zero gap of the bedgraph writer.
+                        // Walk to the next non-zero base of this tile; equal value => the row spans the gap.
+                        int k2 = k + 1;
+                        while (k2 < own && sc[k2 + 402] - sc[k2 + 1] == 0) k2++;
+                        if (k2 < own && sc[k2 + 402] - sc[k2 + 1] == pw) {
+                            unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_N_FILLS]), 1ULL);
+                            if ((int64_t)slot < a.fill_cap) {
+                                a.fills[2 * slot] = a.contig_base[c] + ta + k;
+                                a.fills[2 * slot + 1] = a.contig_base[c] + ta + k2;
+                            } else raise_error(a.status, CRATAC_ERR_CAPACITY, -2);
+                        }
+                    }
+                    pw = w;
+                }
+                // the contig's last base closes an open run at L
+                if (k1 == own && k0 < k1 && tb == L && pw >= thr) n_e += 1;
+            }
+            if (last_nz >= 0) { atomicMin(&s_first_nz, first_nz); atomicMax(&s_last_nz, last_nz); }
+            int tot_s = 0, tot_e = 0;
+            int off_s = block_excl_scan_i32(n_s, warp_tot, &tot_s);
+            int off_e = block_excl_scan_i32(n_e, warp_tot, &tot_e);
+            // ---- chained prefix over tiles (tiles are ticketed in genome order => predecessor is running or done)
+            if (tid == 0) {
+                unsigned long long prev = 0;
+                if (tile > 0) {
+                    unsigned long long v;
+                    long long spins = 0;
+                    while (((v = ld_acquire_u64(&a.chain[tile - 1])) >> 63) == 0ULL) {
+                        if (++spins > (1LL << 26)) { raise_error(a.status, CRATAC_ERR_INTERNAL, tile); break; }
+                        __nanosleep(20);
+                    }
+                    prev = v & 0x7FFFFFFFFFFFFFFFULL;
+                }
+                unsigned long long mine = prev + (unsigned long long)tot_s + ((unsigned long long)tot_e << 31);
+                st_release_u64(&a.chain[tile], mine | 0x8000000000000000ULL);
+                s_chain_prev = prev;
+                int4 sm;
+                sm.x = sm.z = -1; sm.y = sm.w = 0;
+                if (s_last_nz >= 0) {
+                    int f = s_first_nz, l = s_last_nz;
+                    sm.x = (int)(ta + f); sm.y = sc[f + 402] - sc[f + 1];
+                    sm.z = (int)(ta + l); sm.w = sc[l + 402] - sc[l + 1];
+                }
+                a.tile_summary[tile] = sm;
+            }
+            __syncthreads();
+            if (n_s + n_e > 0) {
+                const int64_t g0 = a.contig_base[c] + ta;
+                int64_t os = (int64_t)(s_chain_prev & 0x7FFFFFFFULL) + off_s;
+                int64_t oe = (int64_t)((s_chain_prev >> 31) & 0xFFFFFFFFULL) + off_e;
+                int pw = prev_w;
+                for (int k = k0; k < k1; k++) {
+                    int w = sc[k + 402] - sc[k + 1];
+                    bool sig = w >= thr, psig = pw >= thr;
+                    if (sig && !psig) { if (os < a.run_cap) a.run_start[os] = g0 + k; else raise_error(a.status, CRATAC_ERR_CAPACITY, -1); os++; }
+                    if (!sig && psig) { if (oe < a.run_cap) a.run_end[oe] = g0 + k; else raise_error(a.status, CRATAC_ERR_CAPACITY, -1); oe++; }
+                    pw = w;
+                }
+                if (k1 == own && tb == L && pw >= thr) { if (oe < a.run_cap) a.run_end[oe] = g0 + own; else raise_error(a.status, CRATAC_ERR_CAPACITY, -1); }
+            }
+        }
+    }
+
+    if (MODE == MODE_HIST) {
+        __syncthreads();
+        for (int i = tid; i < PU_HB; i += PU_THREADS) {
+            int v = hist_s[i];
+            if (v) atomicAdd(&a.ghist[i], (unsigned long long)v);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) loc_max = max(loc_max, __shfl_xor_sync(0xffffffffu, loc_max, d));
+        if ((tid & 31) == 0 && loc_max > 0) atomicMax(reinterpret_cast<long long*>(&a.status[ST_MAX_COUNT]), (long long)loc_max);
+    }
+    if (MODE == MODE_PEAKS) {
+        // last tile publishes the totals
+        // (done by whoever processed tile n_tiles-1; read back by k_finish_runs)
+    }
+}
+
+// histogram -> compact (value, weight) arrays, ascending.  One CTA.
+__global__ void __launch_bounds__(1024) k_hist_compact(const unsigned long long* __restrict__ ghist, int64_t* status,
+                                                        int64_t* __restrict__ values, int64_t* __restrict__ weights, int64_t cap) {
+    __shared__ int warp_tot[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t maxc = status[ST_MAX_COUNT];
+    if (maxc >= HIST_CAP) maxc = HIST_CAP - 1;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 <= maxc; b0 += 1024) {
+        int64_t v = b0 + tid;
+        unsigned long long w = (v <= maxc && v > 0) ? ghist[v] : 0ULL;
+        int flag = w != 0ULL;
+        int x = flag;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        int pos = s_base + (warp ? warp_tot[warp - 1] : 0) + x - flag;
+        if (flag && pos < cap) { values[pos] = v; weights[pos] = (int64_t)w; }
+        __syncthreads();
+        if (tid == 0) s_base += warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) status[ST_N_BINS] = s_base;
+}
+
+// ---- run list post-processing -----------------------------------------------------------------
+__global__ void k_finish_runs(const unsigned long long* __restrict__ chain, int64_t n_tiles, int64_t* status) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long v = n_tiles > 0 ? chain[n_tiles - 1] : 0ULL;
+        v &= 0x7FFFFFFFFFFFFFFFULL;
+        int64_t ns = (int64_t)(v & 0x7FFFFFFFULL), ne = (int64_t)((v >> 31) & 0xFFFFFFFFULL);
+        if (ns != ne) raise_error(status, CRATAC_ERR_INTERNAL, -3);
+        status[ST_N_RUNS] = ns;
+    }
+}
+
+// zero gaps that span tile boundaries: last non-zero W of tile t vs first non-zero W of the next non-empty tile
+__global__ void k_cross_tile_gaps(const int4* __restrict__ summary, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ contig_base,
+                                  int n_contigs, int64_t n_tiles, int64_t* status, int64_t* fills, int64_t fill_cap) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    int4 me = summary[t];
+    long long thr_ll = status[ST_THRESHOLD];
+    int thr = thr_ll < 1 ? 1 : (thr_ll > 0x7fffffffLL ? 0x7fffffff : (int)thr_ll);
+    if (me.z < 0 || me.w < thr) return;
+    int lo = 0, hi = n_contigs;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tile_off[mid] <= t) lo = mid; else hi = mid; }
+    int c = lo;
+    int64_t t_end = tile_off[c + 1];
+    for (int64_t u = t + 1; u < t_end; u++) {
+        int4 nx = summary[u];
+        if (nx.x < 0) continue;
+        if (nx.x - me.z > 1 && nx.y == me.w) {
+            unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(&status[ST_N_FILLS]), 1ULL);
+            if ((int64_t)slot < fill_cap) { fills[2 * slot] = contig_base[c] + me.z + 1; fills[2 * slot + 1] = contig_base[c] + nx.x; }
+            else raise_error(status, CRATAC_ERR_CAPACITY, -2);
+        }
+        break;
+    }
+}
+
+// bridge[i] = 1 when a filled zero gap joins run i and run i+1
+__global__ void k_mark_bridges(const int64_t* __restrict__ fills, const int64_t* __restrict__ run_end, const int64_t* __restrict__ run_start,
+                               int64_t* status, int32_t* bridge, int64_t fill_cap) {
+    int64_t nf = status[ST_N_FILLS];
+    if (nf > fill_cap) nf = fill_cap;
+    int64_t n = status[ST_N_RUNS];
+    for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+        int64_t g0 = fills[2 * f], g1 = fills[2 * f + 1];
+        int64_t lo = 0, hi = n;   // first run with end >= g0
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (run_end[mid] < g0) lo = mid + 1; else hi = mid; }
+        if (lo + 1 < n && run_end[lo] == g0 && run_start[lo + 1] == g1) bridge[lo] = 1;
+        else raise_error(status, CRATAC_ERR_INTERNAL, -4);
+    }
+}
+
+// head[i] = 1 when run i opens a new peak: detect_peaks/__init__.py:53 (pos - 500 <= window_end keeps merging)
+__global__ void k_run_heads(const int64_t* __restrict__ run_start, const int64_t* __restrict__ run_end, const int32_t* __restrict__ bridge,
+                            const int64_t* __restrict__ status, int64_t cap, int32_t* __restrict__ head) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    int64_t n = status[ST_N_RUNS];
+    int h = 0;
+    if (i < n) h = (i == 0) || (run_start[i] - MERGE_DIST > run_end[i - 1] && !bridge[i - 1]);
+    head[i] = h;
+}
+
+__global__ void k_emit_peaks(const int64_t* __restrict__ run_start, const int64_t* __restrict__ run_end, const int32_t* __restrict__ head,
+                             const int64_t* __restrict__ head_rank, const int64_t* __restrict__ contig_base, int n_contigs, int64_t* status,
+                             int64_t cap, int32_t* __restrict__ pk_chrom, int32_t* __restrict__ pk_start, int32_t* __restrict__ pk_end,
+                             int32_t* __restrict__ pk_row) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = status[ST_N_RUNS];
+    if (i >= n || i >= cap) return;
+    int64_t k = head_rank[i] - (head[i] ? 0 : 1);   // exclusive rank of heads: run i belongs to peak (rank of its head)
+    bool is_last = (i == n - 1) || head[i + 1];
+    if (!head[i] && !is_last) return;
+    int64_t g = head[i] ? run_start[i] : run_end[i];
+    int lo = 0, hi = n_contigs;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (contig_base[mid] <= g - (head[i] ? 0 : 1)) lo = mid; else hi = mid; }
+    if (head[i]) { pk_chrom[k] = lo; pk_start[k] = (int32_t)(run_start[i] - contig_base[lo]); pk_row[k] = (int32_t)k; }
+    if (is_last) {
+        int64_t ge = run_end[i];
+        int lo2 = 0, hi2 = n_contigs;
+        while (hi2 - lo2 > 1) { int mid = (lo2 + hi2) >> 1; if (contig_base[mid] <= ge - 1) lo2 = mid; else hi2 = mid; }
+        pk_end[k] = (int32_t)(ge - contig_base[lo2]);
+    }
+    if (i == n - 1) status[ST_N_PEAKS] = k + 1;
+}
+
+__global__ void k_zero_peaks_if_no_runs(int64_t* status) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && status[ST_N_RUNS] == 0) status[ST_N_PEAKS] = 0;
+}
+
+// peak_off[c] = first peak (sorted by contig,start) of contig c; reads the peak count from the device
+__global__ void k_peak_offsets(const int32_t* __restrict__ pk_chrom, const int64_t* __restrict__ status, int n_contigs, int64_t* __restrict__ peak_off) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_contigs) return;
+    int64_t n = status[ST_N_PEAKS];
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (pk_chrom[mid] < c) lo = mid + 1; else hi = mid; }
+    peak_off[c] = lo;
+}
+
+// ---- host launchers -----------------------------------------------------------------------------
+int compute_max_len(Ctx* c);   // decode.cu
+
+static int fill_args(Ctx* c, PileupArgs& a) {
+    a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
+    a.frag_off = c->d_contig_frag_off.as<int64_t>(); a.pos_index = c->d_pos_index.as<int64_t>();
+    a.pidx_off = c->d_contig_pidx_off.as<int64_t>(); a.contig_lens = c->d_contig_lens.as<int64_t>();
+    a.contig_base = c->d_contig_base.as<int64_t>(); a.tile_off = c->d_contig_tile_off.as<int64_t>();
+    a.n_contigs = c->n_contigs; a.n_tiles = c->contig_tile_off[c->n_contigs];
+    a.status = c->d_status.as<int64_t>();
+    a.ghist = nullptr; a.chain = nullptr; a.run_start = a.run_end = nullptr; a.run_cap = 0; a.tile_summary = nullptr;
+    a.fills = nullptr; a.fill_cap = 0; a.dump_W = nullptr; a.dump_contig = -1;
+    return CRATAC_OK;
+}
+
+static size_t pileup_smem(int mode) { return sizeof(int) * (PU_N + (mode == MODE_HIST ? PU_HB : 0)); }
+
+template <int MODE>
+static int launch_pileup(Ctx* c, PileupArgs& a) {
+    static bool configured = false;
+    if (!configured) {
+        CRATAC_CUDA(cudaFuncSetAttribute(k_pileup<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem(MODE)));
+        configured = true;
+    }
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), c->stream));
+    int64_t grid = std::min<int64_t>(a.n_tiles, 2 * NUM_SMS);
+    if (grid <= 0) return CRATAC_OK;
+    k_pileup<MODE><<<(unsigned)grid, PU_THREADS, pileup_smem(MODE), c->stream>>>(a);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+int window_histogram(Ctx* c) {
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_TRY(c->d_hist.reserve(sizeof(unsigned long long) * HIST_CAP));
+    CRATAC_TRY(c->d_hist_values.reserve(sizeof(int64_t) * HIST_CAP));
+    CRATAC_TRY(c->d_hist_weights.reserve(sizeof(int64_t) * HIST_CAP));
+    // only the part of the histogram that the previous run touched needs clearing, but 8 MB is cheap
+    CRATAC_CUDA(cudaMemsetAsync(c->d_hist.p, 0, sizeof(unsigned long long) * HIST_CAP, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_MAX_COUNT], 0, sizeof(int64_t) * 2, c->stream));   // max count, n_bins
+    PileupArgs a;
+    fill_args(c, a);
+    a.ghist = c->d_hist.as<unsigned long long>();
+    CRATAC_TRY(launch_pileup<MODE_HIST>(c, a));
+    k_hist_compact<<<1, 1024, 0, c->stream>>>(a.ghist, st, c->d_hist_values.as<int64_t>(), c->d_hist_weights.as<int64_t>(), HIST_CAP);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+int dump_window_counts(Ctx* c, int contig, int32_t* d_W) {
+    PileupArgs a;
+    fill_args(c, a);
+    a.dump_W = d_W; a.dump_contig = contig;
+    return launch_pileup<MODE_DUMP>(c, a);
+}
+
+int call_peaks_device(Ctx* c) {
+    int64_t* st = c->d_status.as<int64_t>();
+    int64_t n_tiles = c->contig_tile_off[c->n_contigs];
+    if (c->run_cap == 0) c->run_cap = 1 << 22;
+    for (int attempt = 0;; attempt++) {
+        int64_t cap = c->run_cap;
+        CRATAC_TRY(c->d_chain.reserve(8 * (size_t)std::max<int64_t>(n_tiles, 1)));
+        CRATAC_TRY(c->d_tile_summary.reserve(16 * (size_t)std::max<int64_t>(n_tiles, 1)));
+        CRATAC_TRY(c->d_run_start.reserve(8 * (size_t)cap)); CRATAC_TRY(c->d_run_end.reserve(8 * (size_t)cap));
+        CRATAC_TRY(c->d_bridge.reserve(4 * (size_t)cap * 2));          // bridge flags + head flags
+        CRATAC_TRY(c->d_fill.reserve(16 * (size_t)cap / 16 + 8 * (size_t)cap));   // fills + head ranks
+        CRATAC_TRY(c->d_peak_chrom.reserve(4 * (size_t)cap)); CRATAC_TRY(c->d_peak_start.reserve(4 * (size_t)cap));
+        CRATAC_TRY(c->d_peak_end.reserve(4 * (size_t)cap)); CRATAC_TRY(c->d_peak_row.reserve(4 * (size_t)cap));
+        CRATAC_TRY(c->d_peak_off.reserve(8 * (size_t)(c->n_contigs + 2)));
+        c->peak_cap = cap;
+        int64_t fill_cap = cap / 16;
+        int64_t* fills = c->d_fill.as<int64_t>();
+        int64_t* head_rank = fills + 2 * fill_cap;
+        int32_t* bridge = c->d_bridge.as<int32_t>();
+        int32_t* head = bridge + cap;
+        CRATAC_CUDA(cudaMemsetAsync(c->d_chain.p, 0, 8 * (size_t)std::max<int64_t>(n_tiles, 1), c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(bridge, 0, 4 * (size_t)cap, c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_RUNS], 0, sizeof(int64_t) * 3, c->stream));   // runs, fills, peaks
+        CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+        PileupArgs a;
+        fill_args(c, a);
+        a.chain = c->d_chain.as<unsigned long long>();
+        a.run_start = c->d_run_start.as<int64_t>(); a.run_end = c->d_run_end.as<int64_t>(); a.run_cap = cap;
+        a.tile_summary = c->d_tile_summary.as<int4>(); a.fills = fills; a.fill_cap = fill_cap;
+        CRATAC_TRY(launch_pileup<MODE_PEAKS>(c, a));
+        k_finish_runs<<<1, 32, 0, c->stream>>>(a.chain, n_tiles, st);
+        if (n_tiles > 0)
+            k_cross_tile_gaps<<<(unsigned)((n_tiles + 127) / 128), 128, 0, c->stream>>>(a.tile_summary, a.tile_off, a.contig_base, c->n_contigs, n_tiles, st,
+                                                                                       fills, fill_cap);
+        k_mark_bridges<<<32, 128, 0, c->stream>>>(fills, a.run_end, a.run_start, st, bridge, fill_cap);
+        k_run_heads<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(a.run_start, a.run_end, bridge, st, cap, head);
+        c->launches += 4;
+        CRATAC_CUDA(cudaGetLastError());
+        CRATAC_TRY(exclusive_scan_i32_to_i64(c, head, head_rank, cap, nullptr));
+        k_zero_peaks_if_no_runs<<<1, 32, 0, c->stream>>>(st);
+        k_emit_peaks<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(a.run_start, a.run_end, head, head_rank, a.contig_base, c->n_contigs, st, cap,
+                                                                           c->d_peak_chrom.as<int32_t>(), c->d_peak_start.as<int32_t>(),
+                                                                           c->d_peak_end.as<int32_t>(), c->d_peak_row.as<int32_t>());
+        k_peak_offsets<<<(c->n_contigs + 1 + 127) / 128, 128, 0, c->stream>>>(c->d_peak_chrom.as<int32_t>(), st, c->n_contigs, c->d_peak_off.as<int64_t>());
+        c->launches += 3;
+        CRATAC_CUDA(cudaGetLastError());
+        // capacity overflow is only visible on the host: the caller checks status when it syncs.
+        (void)attempt;
+        break;
+    }
+    c->peaks_on_device_count = true;
+    return CRATAC_OK;
+}
+
+}  // namespace cratac

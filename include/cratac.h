@@ -1,0 +1,155 @@
+/*
+ * libcratac -- C ABI of the B200-native fragment -> peaks -> peak x barcode matrix path.
+ *
+ * The reference (cellranger-atac 1.2.0) has no FFI for this path: the three Martian stages
+ * COUNT_CUT_SITES, DETECT_PEAKS and GENERATE_PEAK_MATRIX are pure Python.  The entry points
+ * below are what a ctypes binding inside those stage modules calls instead of the Python
+ * loops; each one names the reference lines it replaces (paths relative to the reference
+ * checkout).  Style follows the reference's only ctypes precedent,
+ * tenkit/lib/python/striped_smith_waterman/ssw_wrap.py:54-72: explicit argtypes/restype, an
+ * opaque handle, an explicit destroy.
+ *
+ * Conventions
+ *   - every function returns CRATAC_OK (0) or a negative CRATAC_ERR_* code;
+ *     cratac_last_error() returns a human-readable message for the calling thread.
+ *   - host arrays are caller-allocated, plain pointers + element counts; no torch types.
+ *   - pointers named d_* are CUDA device pointers on the context's device.
+ *   - coordinates are 0-based, fragments are (start, stop) exactly as in fragments.tsv.gz.
+ *   - there is NO CPU fallback: without a CUDA device cratac_create fails.
+ */
+#ifndef CRATAC_H
+#define CRATAC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRATAC_OK 0
+#define CRATAC_ERR_CUDA (-1)          /* CUDA runtime failure (message has file:line) */
+#define CRATAC_ERR_ARG (-2)           /* bad argument / call order */
+#define CRATAC_ERR_PARSE (-3)         /* malformed fragments line (message has the line number) */
+#define CRATAC_ERR_UNSORTED (-4)      /* fragments not sorted by (contig order, start) */
+#define CRATAC_ERR_CONTIG (-5)        /* contig name not in the reference */
+#define CRATAC_ERR_CAPACITY (-6)      /* an internal table overflowed after retries */
+#define CRATAC_ERR_EM_ZERODIV (-7)    /* the reference fit raises ZeroDivisionError on this histogram */
+#define CRATAC_ERR_EM_INDEX (-8)      /* the reference fit raises IndexError (fewer than 2 counts > 15) */
+#define CRATAC_ERR_PEAKS_OVERLAP (-9) /* user peaks overlap (reference: KeyError at generate_peak_matrix:114) */
+#define CRATAC_ERR_INTERNAL (-10)
+#define CRATAC_ERR_IO (-11)
+
+/* matrix column (barcode) order */
+#define CRATAC_BC_ORDER_PY2SET 0      /* CPython-2.7 list(set(...)) order: generate_peak_matrix/__init__.py:44 */
+#define CRATAC_BC_ORDER_FIRST_SEEN 1  /* order of first appearance in the file */
+#define CRATAC_BC_ORDER_SORTED 2      /* lexicographic */
+
+typedef struct cratac_ctx cratac_ctx;
+
+const char* cratac_last_error(void);
+int cratac_abi_version(void);
+
+/* One context per GPU.  contig_names/contig_lens: every contig of fasta/genome.fa.fai in file
+ * order (lib/python/tools/ref_manager.py:45-52); is_primary[i] != 0 for the contigs that
+ * ReferenceManager.primary_contigs(allow_sex_chromosomes=True) returns (ref_manager.py:140-146,
+ * the chunking of count_cut_sites/__init__.py:55-62 and detect_peaks/__init__.py:67-81):
+ * peaks are called on primary contigs only; fragments on other contigs still count in the matrix. */
+int cratac_create(int device, int n_contigs, const char* const* contig_names, const int64_t* contig_lens,
+                  const int32_t* is_primary, cratac_ctx** out);
+void cratac_destroy(cratac_ctx* ctx);
+int cratac_set_option(cratac_ctx* ctx, const char* key, int64_t value);
+/* kernels launched by this context since creation / last reset */
+int64_t cratac_launch_count(cratac_ctx* ctx, int reset);
+int cratac_synchronize(cratac_ctx* ctx);
+
+/* ---- (1) fragment decode: replaces lib/python/tools/io.py:75-79 (open_fragment_file) and
+ *      :82-92 (parsed_fragments_from_contig).  `text` is the DECOMPRESSED fragments.tsv
+ *      (contig \t start \t stop \t barcode \t dup_count \n), position sorted.  Produces SoA int32
+ *      (chrom, start, end, barcode index, dup count) in HBM plus the barcode dictionary. */
+int cratac_decode_host(cratac_ctx* ctx, const char* text, int64_t nbytes);
+int cratac_decode_device(cratac_ctx* ctx, const char* d_text, int64_t nbytes);
+/* already-parsed fragments (host SoA, n each); bc = index into `barcodes` (n_barcodes C strings,
+ * which become the matrix columns in that order). */
+int cratac_set_fragments(cratac_ctx* ctx, int64_t n, const int32_t* chrom, const int32_t* start,
+                         const int32_t* end, const int32_t* bc, const int32_t* dup,
+                         int64_t n_barcodes, const char* const* barcodes);
+int cratac_num_fragments(cratac_ctx* ctx, int64_t* n_fragments, int64_t* n_barcodes);
+/* D2H of the SoA; bc[i] is the matrix column of fragment i.  Any pointer may be NULL. */
+int cratac_get_fragments(cratac_ctx* ctx, int32_t* chrom, int32_t* start, int32_t* end, int32_t* bc, int32_t* dup);
+/* barcode strings in matrix column order, NUL-terminated, packed at `stride` bytes each
+ * (replaces the set comprehension of generate_peak_matrix/__init__.py:44). */
+int cratac_get_barcodes(cratac_ctx* ctx, char* out, int64_t stride);
+int cratac_max_barcode_len(cratac_ctx* ctx, int64_t* len);
+
+/* ---- (2) COUNT_CUT_SITES: replaces count_cut_sites/__init__.py:94-104 (pileup of +-200 bp
+ *      windows around both fragment ends, then Counter(v for v in Cuts if v > 0)) for all
+ *      primary contigs, and the Counter merge of :77-81.  The histogram stays on the device for
+ *      cratac_fit_threshold_device; this call also copies it out (values ascending). */
+int cratac_count_cut_sites(cratac_ctx* ctx, int64_t* values, int64_t* weights, int64_t cap, int64_t* n_bins);
+/* windowed counts of one contig, D2H (Cuts of count_cut_sites/__init__.py:96-101); W has contig_len entries */
+int cratac_window_counts(cratac_ctx* ctx, int contig, int32_t* W);
+/* bedgraph rows of one contig (write_chrom_bedgraph, count_cut_sites/__init__.py:27-48, incl. the
+ * zero-gap behaviour of :36-37).  Call with cap = 0 to get the row count. */
+int cratac_bedgraph_rows(cratac_ctx* ctx, int contig, int64_t* start, int64_t* end, int64_t* count,
+                         int64_t cap, int64_t* n_rows);
+
+/* ---- (3) threshold fit: replaces lib/python/analysis/peaks.py:173-193 (estimate_final_threshold)
+ *      with everything it calls (peaks.py:28-170, lib/python/analysis/em_fitting.py:10-87).
+ *      has_params = 0 and threshold = 15 when the gate of peaks.py:176-177 fires. */
+int cratac_fit_threshold(cratac_ctx* ctx, const int64_t* values, const int64_t* weights, int64_t n_bins,
+                         double odds_ratio, double params_out[6], int* has_params, int64_t* threshold_out,
+                         int64_t* em_iterations, int64_t* inner_iterations);
+/* same, on the histogram left on the device by cratac_count_cut_sites; result stays on the
+ * device for cratac_call_peaks(threshold = -1) and is also returned. */
+int cratac_fit_threshold_device(cratac_ctx* ctx, double odds_ratio, double params_out[6], int* has_params,
+                                int64_t* threshold_out);
+
+/* ---- (4) DETECT_PEAKS.main/join: replaces lib/python/utils.py:105-115 + detect_peaks/__init__.py:40-62
+ *      (threshold, 500 bp merge) over all primary contigs and the ordering of
+ *      lib/python/tools/regions.py:392-417 (.fai contig order, then start).  threshold < 0 uses
+ *      the value fitted on the device.  The peaks become the current peak set of the context. */
+int cratac_call_peaks(cratac_ctx* ctx, int64_t threshold, int64_t* n_peaks);
+int cratac_get_peaks(cratac_ctx* ctx, int32_t* chrom, int32_t* start, int32_t* end);
+/* user-supplied peaks in peaks.bed row order (reanalyze / GENERATE_PEAK_MATRIX stage input);
+ * row i of the matrix is peak i.  Touching peaks are fine, overlapping ones are an error. */
+int cratac_set_peaks(cratac_ctx* ctx, int64_t n, const int32_t* chrom, const int32_t* start, const int32_t* end);
+
+/* ---- (5) GENERATE_PEAK_MATRIX: replaces generate_peak_matrix/__init__.py:107-119 (both fragment ends
+ *      tested with tenkit/regions.py:136-145, Counter[(barcode, peak)], COO -> canonical CSC) for all
+ *      barcodes at once and the hstack of :62-72.  Output layout = cellranger/h5_constants.py:25:
+ *      indptr int64[B+1], indices int64[nnz] (row = peak), data int32[nnz]. */
+int cratac_peak_matrix(cratac_ctx* ctx, int64_t* nnz);
+int cratac_get_matrix(cratac_ctx* ctx, int64_t* indptr, int64_t* indices, int32_t* data);
+/* device views of the current results (valid until the next call that recomputes them) */
+int cratac_matrix_device(cratac_ctx* ctx, const int64_t** d_indptr, const int64_t** d_indices, const int32_t** d_data);
+int cratac_hist_device(cratac_ctx* ctx, const uint64_t** d_hist, int64_t* cap);
+
+/* ---- whole path in one call, no host round trip between kernels:
+ *      decode -> pileup/window/histogram -> fit -> peaks -> matrix.  `text_is_device` selects
+ *      whether `text` is a host or a device pointer.  Results are fetched with the getters. */
+typedef struct cratac_run_result {
+    int64_t n_fragments, n_barcodes, n_bins, threshold, has_params, n_peaks, nnz, em_iterations, em_inner_iterations;
+    double params[6];
+} cratac_run_result;
+int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_device, double odds_ratio,
+               cratac_run_result* result);
+/* same, starting from fragments already decoded in this context (SoA resident in HBM) */
+int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_result* result);
+
+/* ---- host helpers */
+/* CPython-2.7 list(set(keys)) order for `n` NUL-terminated strings given in insertion order:
+ * order_out[j] = index of the key at column j (generate_peak_matrix/__init__.py:44). */
+int cratac_py2_set_order(int64_t n, const char* const* keys, int64_t* order_out);
+/* multi-threaded BGZF/gzip inflate of fragments.tsv.gz into a caller buffer (replaces the
+ * `gzip -c -d` pipe of lib/python/tools/io.py:197-217).  cap = 0 returns the inflated size. */
+int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, int64_t* nbytes);
+/* synthetic text encoder (SoA on the device -> fragments.tsv text on the device), used by bench/tests
+ * to build large inputs without a host formatting loop.  bc_seq = 2-bit packed 16-mers. */
+int cratac_encode_text_device(cratac_ctx* ctx, int64_t n, const int32_t* d_chrom, const int32_t* d_start,
+                              const int32_t* d_end, const uint32_t* d_bc_seq, const int32_t* d_dup,
+                              char* d_out, int64_t cap, int64_t* nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRATAC_H */

@@ -1,0 +1,349 @@
+"""GPU parity tests: every comparison goes through the C ABI (cratac._ffi) and is checked against
+the oracle (oracle/) and the golden vectors made by executing the reference's own code.
+Integer / index results must be bit-exact; the threshold fit has its tolerance stated below."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+from cratac import _ffi, synth
+from oracle import cfast, em as oracle_em, stages
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+CUT_CASES = _load("cut_sites.json")
+MATRIX_CASES = _load("matrix.json")
+EM_CASES = _load("em.json")
+
+# Stated tolerance of the threshold fit (K4): threshold identical; parameters within 1e-6 relative,
+# the reference's own convergence epsilon (analysis/peaks.py:144, em_fitting.py:35).  Observed: ~1e-10.
+EM_RTOL = 1e-6
+
+
+def _bed_to_peaks(text):
+    return [(int(s), int(e)) for _, s, e in (l.split("\t") for l in text.strip("\n").split("\n") if l)]
+
+
+# ----------------------------------------------------------------------------- cut sites / peaks
+@pytest.mark.parametrize("case", CUT_CASES, ids=[c["name"] for c in CUT_CASES])
+def test_cut_sites_golden(case):
+    L = case["contig_len"]
+    fr = np.array(case["fragments"], dtype=np.int32).reshape(-1, 2)
+    ctx = _ffi.Context([("chr1", L)])
+    n = fr.shape[0]
+    ctx.set_fragments(np.zeros(n, np.int32), fr[:, 0], fr[:, 1], np.zeros(n, np.int32), None, ["BC"])
+    v, w = ctx.count_cut_sites()
+    assert {str(int(a)): int(b) for a, b in zip(v, w)} == case["count_dict"]
+    assert np.all(np.diff(v) > 0)
+    W = ctx.window_counts("chr1")
+    assert np.array_equal(W, cfast.window_counts(L, fr[:, 0], fr[:, 1]))
+    rs, re_, rc = ctx.bedgraph_rows("chr1")
+    text = "".join("chr1\t%d\t%d\t%d\n" % t for t in zip(rs, re_, rc))
+    assert text == (case["bedgraph"] or "")
+    for thr, want in case["peaks"].items():
+        c, s, e = ctx.call_peaks(int(thr))
+        assert list(zip(s.tolist(), e.tolist())) == _bed_to_peaks(want["bed"]), "threshold %s" % thr
+        assert len(s) == want["total_peaks_detected"]
+    ctx.close()
+
+
+def _random_genome(rng, n_contigs, lmin, lmax, n_frag, piles, pile_max=40):
+    contigs = [("ctg%d" % i, int(rng.integers(lmin, lmax))) for i in range(n_contigs)]
+    chrom, start, end = [], [], []
+    for ci, (_, L) in enumerate(contigs):
+        n = int(rng.integers(n_frag // 2, n_frag))
+        s = rng.integers(0, L, size=n)
+        e = np.minimum(s + np.clip(rng.normal(250, 160, size=n).astype(int), 0, 1200), L)
+        for _ in range(piles):
+            p = int(rng.integers(0, L))
+            q = min(L, p + int(rng.integers(0, 700)))
+            k = int(rng.integers(2, pile_max))
+            s = np.concatenate([s, np.full(k, p)])
+            e = np.concatenate([e, np.full(k, q)])
+        o = np.lexsort((e, s))
+        chrom.append(np.full(s.size, ci))
+        start.append(s[o])
+        end.append(e[o])
+    return contigs, np.concatenate(chrom).astype(np.int32), np.concatenate(start).astype(np.int32), np.concatenate(end).astype(np.int32)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_peaks_random_multi_tile(seed):
+    """Contigs longer than one pileup tile (24 686 bases): runs, merges and zero gaps cross tile boundaries."""
+    rng = np.random.default_rng(seed)
+    contigs, chrom, start, end = _random_genome(rng, 3, 30000, 260000, 1500 if seed % 2 else 150, 12)
+    primary = [c[0] for c in contigs[:2]]          # the third contig is not primary: no peaks there
+    ctx = _ffi.Context(contigs, primary=primary)
+    n = chrom.size
+    ctx.set_fragments(chrom, start, end, np.zeros(n, np.int32), None, ["BC"])
+    v, w = ctx.count_cut_sites()
+    assert {int(a): int(b) for a, b in zip(v, w)} == util.oracle_hist(contigs, primary, chrom, start, end)
+    for ci in (0, 1):
+        m = chrom == ci
+        assert np.array_equal(ctx.window_counts(ci), cfast.window_counts(contigs[ci][1], start[m], end[m]))
+    for thr in (1, 2, 5, 11, 30):
+        c, s, e = ctx.call_peaks(thr)
+        got = list(zip(c.tolist(), s.tolist(), e.tolist()))
+        assert got == util.oracle_peaks(contigs, primary, chrom, start, end, thr), "threshold %d" % thr
+    ctx.close()
+
+
+def test_zero_gap_across_tiles():
+    """Equal-valued piles separated by > 1 tile of cut-free bases: one bedgraph row spans the gap
+    (count_cut_sites/__init__.py:36-37), so one peak does too.  Unequal piles do not join."""
+    L = 400000
+    piles = [(1000, 6), (90000, 6), (91000, 6), (200000, 7), (330000, 7), (399900, 7), (399990, 3)]
+    start = np.concatenate([np.full(k, p) for p, k in piles]).astype(np.int32)
+    end = start.copy()
+    half = start.size
+    # each fragment contributes 2 cut sites at the same base -> multiplicities 12, 12, 12, 14, 14, 14, 6
+    ctx = _ffi.Context([("chrZ", L)])
+    ctx.set_fragments(np.zeros(half, np.int32), start, end, np.zeros(half, np.int32), None, ["BC"])
+    for thr in (1, 6, 7, 12, 13, 14, 15):
+        c, s, e = ctx.call_peaks(thr)
+        ps, pe = cfast.call_peaks_contig(L, start, end, thr)
+        assert list(zip(s.tolist(), e.tolist())) == list(zip(ps.tolist(), pe.tolist())), "threshold %d" % thr
+    rs, re_, rc = ctx.bedgraph_rows(0)
+    W = cfast.window_counts(L, start, end)
+    ors, ore, orc = cfast.bedgraph_rows(W)
+    assert rs.tolist() == ors.tolist() and re_.tolist() == ore.tolist() and rc.tolist() == orc.tolist()
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------- threshold fit
+@pytest.mark.parametrize("case", EM_CASES, ids=[c["name"] for c in EM_CASES])
+def test_em_golden(case):
+    ctx = _ffi.Context([("chr1", 1000)])
+    if case.get("raises"):
+        with pytest.raises(_ffi.CratacError) as e:
+            ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
+        assert e.value.code == _ffi.ERR_EM_ZERODIV
+        ctx.close()
+        return
+    thr, params, stats = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
+    assert thr == case["threshold"]
+    if case["params"] is None:
+        assert params is None
+    else:
+        assert np.allclose(np.array(params), np.array(case["params"]), rtol=EM_RTOL, atol=0), (params, case["params"], stats)
+    ctx.close()
+
+
+def test_em_random_histograms_vs_oracle():
+    ctx = _ffi.Context([("chr1", 1000)])
+    rng = np.random.default_rng(42)
+    for k in range(4):
+        n_bg, n_sig = int(rng.integers(200000, 900000)), int(rng.integers(2000, 20000))
+        vals = np.concatenate([rng.geometric(0.5, size=300000), rng.negative_binomial(6, 0.35, size=n_bg) + 1,
+                               rng.geometric(0.02, size=n_sig) + 10])
+        b = np.bincount(vals)
+        v = np.nonzero(b)[0]
+        v = v[v > 0]
+        w = b[v]
+        cd = {int(a): int(c) for a, c in zip(v, w)}
+        try:
+            othr, oparams = oracle_em.estimate_final_threshold(cd, 1 / 5)
+        except ZeroDivisionError:
+            with pytest.raises(_ffi.CratacError):
+                ctx.fit_threshold(v, w, 1 / 5)
+            continue
+        thr, params, stats = ctx.fit_threshold(v, w, 1 / 5)
+        assert thr == (None if othr is None else int(othr)), (k, stats)
+        assert np.allclose(np.array(params), np.array(oparams, dtype=float), rtol=EM_RTOL, atol=0), (k, params, oparams, stats)
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------- matrix
+@pytest.mark.parametrize("case", MATRIX_CASES, ids=[c["name"] for c in MATRIX_CASES])
+def test_matrix_golden(case):
+    peak_rows = [l.split("\t") for l in case["peaks"].splitlines() if l]
+    contig_names = sorted({r[0] for r in peak_rows} | {f[0] for f in case["fragments"]})
+    contigs = [(c, 100000) for c in contig_names]
+    cid = {c: i for i, c in enumerate(contig_names)}
+    bcid = {b: i for i, b in enumerate(case["barcodes"])}
+    fr = [f for f in case["fragments"] if f[3] in bcid]          # fragments of other barcode chunks are skipped (:108-109)
+    fr.sort(key=lambda f: (cid[f[0]], f[1], f[2]))
+    ctx = _ffi.Context(contigs)
+    ctx.set_fragments([cid[f[0]] for f in fr], [f[1] for f in fr], [f[2] for f in fr], [bcid[f[3]] for f in fr],
+                      [f[4] for f in fr], case["barcodes"])
+    ctx.set_peaks([cid[r[0]] for r in peak_rows], [int(r[1]) for r in peak_rows], [int(r[2]) for r in peak_rows])
+    indptr, indices, data = ctx.peak_matrix()
+    want = case["result"]
+    assert indptr.tolist() == want["indptr"]
+    assert indices.tolist() == want["indices"]
+    assert data.tolist() == want["data"]
+    assert indices.dtype == np.int64 and data.dtype == np.int32 and indptr.dtype == np.int64
+    ctx.close()
+
+
+def test_matrix_overlapping_peaks_rejected():
+    ctx = _ffi.Context([("chr1", 10000)])
+    with pytest.raises(_ffi.CratacError) as e:
+        ctx.set_peaks([0, 0], [100, 150], [200, 300])
+    assert e.value.code == _ffi.ERR_PEAKS_OVERLAP
+    ctx.set_peaks([0, 0], [100, 200], [200, 300])                # touching is fine (tenkit/regions.py:102)
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,n_peaks,n_bc,n_frag", [(5, 300, 40, 20000), (6, 40000, 12, 60000), (7, 5, 3000, 30000)])
+def test_matrix_random_vs_oracle(seed, n_peaks, n_bc, n_frag):
+    """Long segments (> 4096 hits per barcode: counting path), > 24 576 peaks (several counting ranges),
+    many short segments (bitonic path), unsorted user peak order."""
+    rng = np.random.default_rng(seed)
+    contigs = [("a", 3000000), ("b", 2000000)]
+    peaks = []
+    for ci, (_, L) in enumerate(contigs):
+        k = n_peaks // 2 + 1
+        edges = np.sort(rng.choice(L, size=2 * k, replace=False))
+        peaks += [(ci, int(edges[2 * i]), int(edges[2 * i + 1])) for i in range(k)]
+    perm = rng.permutation(len(peaks))
+    peaks = [peaks[i] for i in perm]                              # peaks.bed row order is arbitrary for user peaks
+    chrom = rng.integers(0, 2, size=n_frag).astype(np.int32)
+    L = np.array([c[1] for c in contigs])[chrom]
+    start = (rng.random(n_frag) * L).astype(np.int32)
+    end = np.minimum(start + rng.integers(0, 1200, size=n_frag), L).astype(np.int32)
+    bc = rng.integers(0, n_bc, size=n_frag).astype(np.int32)
+    if n_bc > 4:
+        bc[rng.random(n_frag) < 0.6] = 1                          # one very deep barcode
+    o = np.lexsort((end, start, chrom))
+    chrom, start, end, bc = chrom[o], start[o], end[o], bc[o]
+    ctx = _ffi.Context(contigs)
+    ctx.set_fragments(chrom, start, end, bc, None, ["bc%d" % i for i in range(n_bc)])
+    ctx.set_peaks([p[0] for p in peaks], [p[1] for p in peaks], [p[2] for p in peaks])
+    indptr, indices, data = ctx.peak_matrix()
+    oip, oix, od = util.oracle_matrix(2, peaks, chrom, start, end, bc, n_bc)
+    assert np.array_equal(indptr, oip)
+    assert np.array_equal(indices, oix)
+    assert np.array_equal(data, od)
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------- decode
+def test_decode_parity_and_barcode_order():
+    contigs = synth.GRCH38[:3]
+    frags = synth.generate(contigs, 60000, 30, 200, seed=11)
+    text = synth.to_text(frags)
+    names = [c[0] for c in contigs]
+    ctx = _ffi.Context(contigs)
+    n, nb = ctx.decode_host(text)
+    o = util.oracle_decode(text, names)
+    assert n == o["start"].size and nb == len(o["first_seen"])
+    got = ctx.get_fragments()
+    assert np.array_equal(got["chrom"], o["chrom"])
+    assert np.array_equal(got["start"], o["start"])
+    assert np.array_equal(got["end"], o["end"])
+    assert np.array_equal(got["dup"], o["dup"])
+    bcs = ctx.get_barcodes()
+    assert bcs == util.oracle_columns(o["first_seen"])            # CPython-2.7 list(set(...)) order
+    assert [bcs[j] for j in got["bc"]] == o["barcodes"]
+    for order, want in ((_ffi.BC_ORDER_FIRST_SEEN, o["first_seen"]), (_ffi.BC_ORDER_SORTED, sorted(o["first_seen"]))):
+        ctx.set_option("barcode_order", order)
+        ctx.decode_host(text)
+        assert ctx.get_barcodes() == want
+    ctx.close()
+
+
+def test_decode_edge_cases():
+    contigs = [("chr1", 100000), ("chr2_random", 5000), ("X", 777)]
+    lines = [
+        "chr1\t0\t1\tAAACGAAAGACCATAA-1\t1",
+        "chr1\t5\t900\tAAACGAAAGACCATAA-12\t2",            # multi-digit gem group is a different barcode
+        "chr1\t5\t901\tNNNNGAAAGACCATAA-1\t3",              # not [ACGT]{16}: generic path
+        "chr1\t77\t99999\tsome_generic.barcode\t2147483647",
+        "chr1\t77\t100000\tAAACGAAAGACCATAA-1\t1\r",        # CRLF
+        "chr2_random\t3\t4\tAAACGAAAGACCATAA-01\t9",        # leading zero in the group: generic, distinct from -1
+        "X\t776\t777\tTTTTTTTTTTTTTTTT-1\t1",
+    ]
+    text = ("\n".join(lines)).encode()                         # no trailing newline
+    ctx = _ffi.Context(contigs)
+    for t in (text, text + b"\n"):
+        n, nb = ctx.decode_host(t)
+        o = util.oracle_decode(t, [c[0] for c in contigs])
+        assert (n, nb) == (7, 6)
+        got = ctx.get_fragments()
+        for k in ("chrom", "start", "end", "dup"):
+            assert np.array_equal(got[k], o[k]), k
+        bcs = ctx.get_barcodes()
+        assert [bcs[j] for j in got["bc"]] == o["barcodes"]
+        assert bcs == util.oracle_columns(o["first_seen"])
+    n, nb = ctx.decode_host(b"")
+    assert (n, nb) == (0, 0)
+    for bad, code in ((b"chr1\t1\t2\tAAAA\n", _ffi.ERR_PARSE), (b"chr1\t1\tx\tAAAA\t1\n", _ffi.ERR_PARSE),
+                      (b"chr9\t1\t2\tAAAA\t1\n", _ffi.ERR_CONTIG), (b"chr1\t5\t9\tA\t1\nchr1\t4\t9\tA\t1\n", _ffi.ERR_UNSORTED),
+                      (b"X\t5\t9\tA\t1\nchr1\t4\t9\tA\t1\n", _ffi.ERR_UNSORTED), (b"chr1\t5\t9\tA\t1\n\nchr1\t6\t9\tA\t1\n", _ffi.ERR_PARSE)):
+        with pytest.raises(_ffi.CratacError) as e:
+            ctx.decode_host(bad)
+        assert e.value.code == code, bad
+    ctx.close()
+
+
+def test_decode_many_tiles_and_table_growth():
+    """Text spanning many 16 KiB tiles; barcode table forced to grow from 64 slots."""
+    contigs = synth.GRCH38[:2]
+    frags = synth.generate(contigs, 150000, 400, 100, seed=13, background_factor=3)
+    text = synth.to_text(frags)
+    ctx = _ffi.Context(contigs)
+    ctx.set_option("barcode_table_slots", 64)
+    n, nb = ctx.decode_host(text)
+    o = util.oracle_decode(text, [c[0] for c in contigs])
+    assert n == o["start"].size and nb == len(o["first_seen"])
+    got = ctx.get_fragments()
+    assert np.array_equal(got["start"], o["start"]) and np.array_equal(got["end"], o["end"])
+    bcs = ctx.get_barcodes()
+    assert bcs == util.oracle_columns(o["first_seen"])
+    assert [bcs[j] for j in got["bc"][:5000]] == o["barcodes"][:5000]
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------- whole path
+def _run_and_compare(contigs, primary, text, odds=1 / 5):
+    names = [c[0] for c in contigs]
+    ctx = _ffi.Context(contigs, primary=primary)
+    res = ctx.run(text=text, odds_ratio=odds)
+    o = util.oracle_decode(text, names)
+    hist = util.oracle_hist(contigs, primary, o["chrom"], o["start"], o["end"])
+    othr, oparams = oracle_em.estimate_final_threshold(hist, odds)
+    assert res.threshold == int(othr)
+    if oparams is None:
+        assert res.has_params == 0
+    else:
+        assert np.allclose(np.array(list(res.params)), np.array(oparams, dtype=float), rtol=EM_RTOL, atol=0)
+    peaks = util.oracle_peaks(contigs, primary, o["chrom"], o["start"], o["end"], int(othr))
+    c, s, e = ctx.get_peaks(res.n_peaks)
+    assert list(zip(c.tolist(), s.tolist(), e.tolist())) == peaks
+    cols = util.oracle_columns(o["first_seen"])
+    assert ctx.get_barcodes() == cols
+    col_id = {b: j for j, b in enumerate(cols)}
+    fcol = np.array([col_id[b] for b in o["barcodes"]], dtype=np.int32)
+    oip, oix, od = util.oracle_matrix(len(contigs), peaks, o["chrom"], o["start"], o["end"], fcol, len(cols))
+    indptr, indices, data = ctx.get_matrix(res.nnz)
+    assert np.array_equal(indptr, oip) and np.array_equal(indices, oix) and np.array_equal(data, od)
+    assert res.n_fragments == o["start"].size and res.n_barcodes == len(cols)
+    ctx.close()
+    return res
+
+
+def test_whole_path_small_gated_threshold():
+    """Too few bases for the fit (peaks.py:176-177): threshold 15, no params."""
+    contigs = [("chr1", 60000), ("chr2", 30000)]
+    frags = synth.generate(contigs, 9000, 25, 12, seed=21, background_factor=4)
+    res = _run_and_compare(contigs, ["chr1", "chr2"], synth.to_text(frags))
+    assert res.threshold == 15 and res.has_params == 0 and res.n_peaks > 0 and res.nnz > 0
+
+
+def test_whole_path_fitted_threshold():
+    """Enough signal for the mixture fit to run; chrY left out of the primary list."""
+    contigs = [("chr1", 6000000), ("chr2", 3000000), ("chrY", 500000)]
+    frags = synth.generate(contigs, 350000, 60, 900, seed=22, background_factor=5)
+    res = _run_and_compare(contigs, ["chr1", "chr2"], synth.to_text(frags))
+    assert res.has_params == 1 and res.n_peaks > 100 and res.em_iterations > 0

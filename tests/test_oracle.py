@@ -187,6 +187,10 @@ EM_CASES = _load("em.json") if os.path.exists(_EMP) and os.path.getsize(_EMP) > 
 @pytest.mark.parametrize("case", EM_CASES, ids=[c["name"] for c in EM_CASES])
 def test_em_oracle_vs_reference(case):
     cd = {int(v): int(w) for v, w in zip(case["values"], case["weights"])}
+    if case.get("raises"):
+        with pytest.raises(ZeroDivisionError):
+            em.estimate_final_threshold(cd, 1 / 5)
+        return
     thr, params = em.estimate_final_threshold(cd, 1 / 5)
     if case["params"] is None:
         assert params is None and thr == case["threshold"]
