@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the fragment -> peaks -> peak x barcode matrix path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cratac|reference] [--fragments F]
+
+One "step" = one pass of the whole hot path (decode, pileup/window/histogram, threshold fit, peak
+calling, peak x barcode CSC) over one synthetic GRCh38-shaped input (BASELINE.json configs[1]:
+10k cells, 250M fragments, ~100k latent peaks; `--fragments` scales it down for quick runs and is
+reported in config).  `value` times the step with the decompressed text already resident in HBM;
+`e2e` times the same step through the C ABI from a pinned HOST text buffer to peaks + CSC arrays
+back in pinned host memory (H2D and D2H inside the timed region).  Per-kernel times come from CUDA
+events on the library's own stream (cratac_stage_times).
+
+N > 1 (torchrun, one rank per GPU): the genome is sharded by contig (LPT), each rank runs the path
+on its contigs; the window-count histogram is all-reduced over NCCL before the threshold fit so
+every rank calls peaks with the global threshold; "scaling" is strong (total work fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cellranger-atac_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "fragments/sec (DETECT_PEAKS+peak-bc matrix)"
+UNIT = "fragments/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- workload
+def shard_contigs(contigs, world):
+    """LPT bin-packing of contigs over ranks; rank -> list of contig indices (sorted)."""
+    loads = [0] * world
+    parts = [[] for _ in range(world)]
+    for i in sorted(range(len(contigs)), key=lambda k: -contigs[k][1]):
+        r = loads.index(min(loads))
+        parts[r].append(i)
+        loads[r] += contigs[i][1]
+    return [sorted(p) for p in parts]
+
+
+def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device):
+    """Seeded synthetic fragments generated ON the device (torch is plumbing here), sorted by
+    (contig, start, stop) and rendered to fragments.tsv text by the library's encoder kernel.
+    Same distributions as cratac/synth.py."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lens = torch.tensor([c[1] for c in contigs], dtype=torch.int64, device=device)
+    cum = torch.cat([torch.zeros(1, dtype=torch.int64, device=device), torch.cumsum(lens, 0)])
+    total = int(cum[-1].item())
+    n = int(n_frag)
+    centres = torch.randint(0, total, (max(int(n_peaks), 1),), generator=g, device=device, dtype=torch.int64)
+    in_peak = torch.rand(n, generator=g, device=device) < 0.5
+    pick = torch.randint(0, centres.numel(), (n,), generator=g, device=device, dtype=torch.int64)
+    gpos = centres[pick] + (torch.randn(n, generator=g, device=device) * 150.0).to(torch.int64)
+    del pick
+    bg = torch.randint(0, total, (n,), generator=g, device=device, dtype=torch.int64)
+    gpos = torch.where(in_peak, gpos, bg).clamp_(0, total - 1)
+    del bg, in_peak
+    chrom = torch.searchsorted(cum[1:].contiguous(), gpos, right=True)
+    start = gpos - cum[chrom]
+    del gpos
+    comp = torch.rand(n, generator=g, device=device)
+    z = torch.randn(n, generator=g, device=device)
+    length = torch.where(comp < 0.5, 120.0 + 35.0 * z, torch.where(comp < 0.85, 320.0 + 45.0 * z, 520.0 + 60.0 * z))
+    del comp, z
+    length = length.to(torch.int64).clamp_(20, 1200)
+    L = lens[chrom]
+    start = torch.minimum(start, L - 1)
+    end = torch.minimum(start + length, L)
+    start = torch.minimum(start, end - 1).clamp_(min=0)
+    del length, L
+    # sort by (contig, start, end)
+    key = ((cum[chrom] + start) << 11) | (end - start)
+    order = torch.argsort(key)
+    del key
+    chrom = chrom[order].to(torch.int32)
+    start = start[order].to(torch.int32)
+    end = end[order].to(torch.int32)
+    del order
+    dup = torch.empty(n, device=device).geometric_(0.5, generator=g).to(torch.int32)
+    n_bg = 20 * cells
+    depth = torch.empty(cells, device=device).log_normal_(0.0, 0.5, generator=g)
+    p = torch.cat([0.8 * depth / depth.sum(), torch.full((n_bg,), 0.2 / n_bg, device=device)])
+    cdf = torch.cumsum(p.double(), 0)
+    cdf = cdf / cdf[-1]
+    bc_idx = torch.searchsorted(cdf, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=cells + n_bg - 1)
+    seqs = torch.randint(0, 1 << 32, (cells + n_bg,), generator=g, device=device, dtype=torch.int64)
+    seqs = torch.where(seqs >= (1 << 31), seqs - (1 << 32), seqs).to(torch.int32)
+    seq = seqs[bc_idx].contiguous()
+    del bc_idx
+    torch.cuda.synchronize()   # the encoder runs on the library's stream
+    nbytes = ctx.encode_text_device(n, chrom.data_ptr(), start.data_ptr(), end.data_ptr(), seq.data_ptr(), dup.data_ptr(), 0, 0)
+    text = torch.empty(nbytes + 16, dtype=torch.uint8, device=device)
+    got = ctx.encode_text_device(n, chrom.data_ptr(), start.data_ptr(), end.data_ptr(), seq.data_ptr(), dup.data_ptr(), text.data_ptr(), nbytes)
+    assert got == nbytes
+    torch.cuda.synchronize()
+    return text, nbytes
+
+
+def algorithmic_bytes(T, N, G, P, K, nnz, B):
+    """SURVEY.md section 8d per-kernel algorithmic bytes, summed over the stages each kernel replaces."""
+    return {
+        "decode": T + 20 * N,                         # K1 (newline count + parse)
+        "pileup_window_hist": 16 * N + 4 * G,         # K2 + K3 (fused; the dense count array never reaches HBM)
+        "pileup_call_peaks": 16 * N + 4 * G + 12 * P,  # K2 (recomputed) + K5
+        "overlap": 12 * N + 8 * K,                    # K6 (count pass + scatter pass)
+        "sort_reduce": 8 * K + 12 * nnz,              # K7
+        "csc_build": 12 * nnz + 8 * (B + 1),          # K8
+    }
+
+
+KERNEL_GROUPS = {
+    "decode": ("decode_count_newlines", "decode_parse"),
+    "pileup_window_hist": ("pileup_window_hist",),
+    "pileup_call_peaks": ("pileup_call_peaks",),
+    "overlap": ("overlap_count", "overlap_scatter"),
+    "sort_reduce": ("reduce_small", "reduce_large"),
+    "csc_build": ("csc_build",),
+}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_sample_text(contig_len, n_frag, cells, n_peaks, seed):
+    from cratac import synth
+    contigs = [("chr1", contig_len)]
+    frags = synth.generate(contigs, n_frag, cells, n_peaks, seed=seed, background_factor=20)
+    return contigs, synth.to_text(frags)
+
+
+def run_reference_flow(sample):
+    from oracle import reference_flow
+    contigs, text = sample
+    t0 = time.time()
+    res = reference_flow.run(text, contigs, [c[0] for c in contigs], n_procs=os.cpu_count())
+    dt = time.time() - t0
+    return res["n_fragments"], dt, res["seconds"]
+
+
+def reference_arm(args, world, rank):
+    """--impl reference: the reference-shaped CPU flow (oracle port) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    density = args.config_fragments / float(args.genome_bases)
+    slice_len = 1000000
+    n = int(density * slice_len)
+    sample = cpu_sample_text(slice_len, n, max(args.cells // 250, 10), max(int(args.peaks * slice_len / args.genome_bases), 4), seed=1000)
+    for _ in range(args.warmup):
+        run_reference_flow(sample)
+    t0 = time.time()
+    frs = 0
+    for _ in range(args.steps):
+        nf, dt, secs = run_reference_flow(sample)
+        frs += nf
+    total = time.time() - t0
+    value = frs / total
+    sample_desc = ("%d fragments on a %d-base slice at the config's fragment density (%.4f/base), %d-barcode universe; the whole "
+                   "reference-shaped flow (per-contig pileup, per-base Counter/bedgraph loops, mixture fit, 30 barcode chunks)"
+                   % (n, slice_len, density, 21 * max(args.cells // 250, 10)))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample_desc,
+                             "seconds_by_stage": secs},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "synthetic GRCh38-shape %d-cell run, %d fragments, whole GRCh38, %d latent peak centres"
+                        % (args.cells, args.config_fragments, args.peaks),
+            "fragments": args.config_fragments, "cells": args.cells, "latent_peaks": args.peaks, "genome": "GRCh38 chr1-22,X,Y",
+            "l2": "inputs larger than L2 (text %.1f GB per step)" % (46.0 * args.config_fragments / 1e9),
+            "parallelism": "genome-range sharding by contig, %d GPU(s)" % args.gpus}
+
+
+# --------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cratac", choices=["cratac", "reference"])
+    ap.add_argument("--fragments", type=int, default=250000000, help="total fragments of the workload (configs[1]: 250M)")
+    ap.add_argument("--cells", type=int, default=10000)
+    ap.add_argument("--peaks", type=int, default=100000)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.config_fragments = args.fragments
+
+    from cratac import synth
+    contigs_all = synth.GRCH38
+    args.genome_bases = sum(c[1] for c in contigs_all)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, world, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cratac import _ffi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    # ---- shard the genome by contig
+    parts = shard_contigs(contigs_all, world)
+    mine = parts[rank]
+    contigs = [contigs_all[i] for i in mine]
+    share = sum(c[1] for c in contigs) / float(args.genome_bases)
+    n_local = int(round(args.fragments * share))
+    peaks_local = max(int(round(args.peaks * share)), 1)
+    G = sum(c[1] for c in contigs)
+
+    ctx = _ffi.Context(contigs, device=local_rank)
+    ctx.set_option("profile", 1)
+    text, nbytes = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        if world == 1:
+            return ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
+        return multi_gpu_step(ctx, torch, dist, text.data_ptr(), nbytes, device)
+
+    # ---- device-resident timing
+    res = None
+    for _ in range(args.warmup):
+        res = step_device()
+    stage_ms = {}
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count(reset=True)
+    ev0.record(stream)
+    wall0 = time.time()
+    for _ in range(args.steps):
+        res = step_device()
+        for k, v in ctx.stage_times().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    ev1.record(stream)
+    barrier()
+    wall = time.time() - wall0
+    clocks = sampler.stop()
+    launches = ctx.launch_count(reset=True)
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    total_frags = args.steps * args.fragments
+    value = total_frags / (dev_ms / 1000.0)
+
+    # ---- end to end from pinned host text to pinned host results
+    e2e = None
+    if not args.no_e2e:
+        host_text = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        host_text.copy_(text[:nbytes])
+        torch.cuda.synchronize()
+        nb = res.n_barcodes
+        out_indptr = torch.empty(nb + 1, dtype=torch.int64, pin_memory=True)
+        cap_nnz = int(res.nnz * 1.05) + 1024
+        out_indices = torch.empty(cap_nnz, dtype=torch.int64, pin_memory=True)
+        out_data = torch.empty(cap_nnz, dtype=torch.int32, pin_memory=True)
+        outs = (out_indptr.numpy(), out_indices.numpy(), out_data.numpy())
+
+        def step_e2e():
+            if world == 1:
+                r = ctx.run(text=(host_text.data_ptr(), nbytes), odds_ratio=0.2)
+            else:
+                r = multi_gpu_step(ctx, torch, dist, None, nbytes, device, host_ptr=host_text.data_ptr())
+            ctx.get_peaks(r.n_peaks)
+            ctx.get_matrix(r.nnz, out=outs)
+            return r
+
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            r = step_e2e()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        d2h = 12 * int(r.n_peaks) + 8 * (int(r.n_barcodes) + 1) + 12 * int(r.nnz)
+        e2e = {"value": total_frags / (ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant HBM-bound kernel (rank 0's shard)
+    peak_gbs, peak_src = measured_peaks()
+    K_hits = int(res.n_hits)
+    alg = algorithmic_bytes(nbytes, res.n_fragments, G, res.n_peaks, K_hits, res.nnz, res.n_barcodes)
+    kernels = {}
+    for name, members in KERNEL_GROUPS.items():
+        ms = sum(stage_ms.get(m, 0.0) for m in members) / args.steps
+        if ms > 0:
+            gbs = alg[name] / 1e9 / (ms / 1000.0)
+            kernels[name] = {"ms": ms, "algorithmic_gb": alg[name] / 1e9, "gbs": gbs, "frac": gbs / peak_gbs}
+    em_ms = stage_ms.get("em_fit", 0.0) / args.steps
+    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "note": "achieved = SURVEY section 8d algorithmic bytes of the stages the kernel replaces / CUDA-event time"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        density = args.config_fragments / float(args.genome_bases)
+        slice_len = 1000000
+        n = int(density * slice_len)
+        sample = cpu_sample_text(slice_len, n, max(args.cells // 250, 10), max(int(args.peaks * slice_len / args.genome_bases), 4), seed=1000)
+        nf, dt, secs = run_reference_flow(sample)
+        cpu_baseline = {"value": nf / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": "%d fragments on a %d-base slice at the config's fragment density; reference-shaped flow "
+                                  "(oracle/reference_flow.py: per-contig pileup + per-base loops, mixture fit, 30 barcode chunks) "
+                                  "on a multiprocessing pool" % (n, slice_len),
+                        "seconds_by_stage": secs}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": workload_config(args),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernels": kernels, "em_fit_ms": em_ms, "em_iterations": int(res.em_iterations), "em_inner_iterations": int(res.em_inner_iterations),
+            "result": {"n_fragments_rank0": int(res.n_fragments), "n_barcodes": int(res.n_barcodes), "threshold": int(res.threshold),
+                       "n_peaks_rank0": int(res.n_peaks), "nnz_rank0": int(res.nnz), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},
+            "wall_ms_per_step": 1000.0 * wall / args.steps}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def multi_gpu_step(ctx, torch, dist, dev_ptr, nbytes, device, host_ptr=None):
+    """One step on one rank's genome shard with the cross-rank exchanges of SURVEY.md section 8e."""
+    from cratac import multi
+    return multi.step(ctx, torch, dist, dev_ptr, nbytes, device, host_ptr=host_ptr)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,7 +37,7 @@ BC_ORDER_PY2SET, BC_ORDER_FIRST_SEEN, BC_ORDER_SORTED = 0, 1, 2
 class RunResult(ctypes.Structure):
     _fields_ = [("n_fragments", c_i64), ("n_barcodes", c_i64), ("n_bins", c_i64), ("threshold", c_i64),
                 ("has_params", c_i64), ("n_peaks", c_i64), ("nnz", c_i64), ("em_iterations", c_i64),
-                ("em_inner_iterations", c_i64), ("params", c_dbl * 6)]
+                ("em_inner_iterations", c_i64), ("params", c_dbl * 6), ("n_hits", c_i64)]
 
 
 # symbol -> (restype, argtypes); every entry of include/cratac.h
@@ -49,6 +49,10 @@ SIGNATURES = {
     "cratac_set_option": (c_int, [c_vp, c_cp, c_i64]),
     "cratac_launch_count": (c_i64, [c_vp, c_int]),
     "cratac_synchronize": (c_int, [c_vp]),
+    "cratac_stream": (c_int, [c_vp, P(ctypes.c_uint64)]),
+    "cratac_num_stages": (c_int, []),
+    "cratac_stage_name": (c_cp, [c_int]),
+    "cratac_stage_times": (c_int, [c_vp, P(ctypes.c_float)]),
     "cratac_decode_host": (c_int, [c_vp, c_vp, c_i64]),
     "cratac_decode_device": (c_int, [c_vp, c_vp, c_i64]),
     "cratac_set_fragments": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_cp)]),
@@ -144,6 +148,18 @@ class Context(object):
 
     def synchronize(self):
         check(self._lib.cratac_synchronize(self._h))
+
+    def stream(self):
+        s = ctypes.c_uint64()
+        check(self._lib.cratac_stream(self._h, ctypes.byref(s)))
+        return s.value
+
+    def stage_times(self):
+        """-> {stage name: ms} for the kernels of the last run (needs set_option('profile', 1))."""
+        n = self._lib.cratac_num_stages()
+        ms = (ctypes.c_float * n)()
+        check(self._lib.cratac_stage_times(self._h, ms))
+        return {self._lib.cratac_stage_name(i).decode(): float(ms[i]) for i in range(n) if ms[i] >= 0}
 
     # ---- decode
     def decode_host(self, text):
@@ -251,11 +267,15 @@ class Context(object):
         check(self._lib.cratac_peak_matrix(self._h, ctypes.byref(nnz)))
         return self.get_matrix(nnz.value)
 
-    def get_matrix(self, nnz):
+    def get_matrix(self, nnz, out=None):
+        """out: optional (indptr, indices, data) numpy views of (pinned) host buffers to fill."""
         _, nb = self.num_fragments()
-        indptr = np.zeros(nb + 1, dtype=np.int64)
-        indices = np.zeros(nnz, dtype=np.int64)
-        data = np.zeros(nnz, dtype=np.int32)
+        if out is not None:
+            indptr, indices, data = out[0][:nb + 1], out[1][:nnz], out[2][:nnz]
+        else:
+            indptr = np.zeros(nb + 1, dtype=np.int64)
+            indices = np.zeros(nnz, dtype=np.int64)
+            data = np.zeros(nnz, dtype=np.int32)
         check(self._lib.cratac_get_matrix(self._h, _ptr(indptr), _ptr(indices), _ptr(data)))
         return indptr, indices, data
 

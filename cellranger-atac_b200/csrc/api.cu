@@ -165,6 +165,11 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
         return CRATAC_OK;
     }
     if (!strcmp(key, "run_capacity")) { c->run_cap = value; return CRATAC_OK; }
+    if (!strcmp(key, "profile")) {
+        if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
+        c->profile = value != 0;
+        return CRATAC_OK;
+    }
     set_error("unknown option '%s'", key);
     return CRATAC_ERR_ARG;
 }
@@ -173,6 +178,35 @@ int64_t cratac_launch_count(cratac_ctx* h, int reset) {
     int64_t n = h->c.launches;
     if (reset) h->c.launches = 0;
     return n;
+}
+
+static const char* const kStageNames[SG_COUNT] = {"decode_count_newlines", "decode_parse", "fragment_index", "pileup_window_hist", "hist_compact",
+                                                 "em_fit", "pileup_call_peaks", "merge_runs", "overlap_count", "overlap_scatter",
+                                                 "reduce_small", "reduce_large", "csc_build", "barcode_table"};
+
+int cratac_num_stages(void) { return SG_COUNT; }
+const char* cratac_stage_name(int id) { return (id >= 0 && id < SG_COUNT) ? kStageNames[id] : ""; }
+
+// milliseconds of each stage's kernels in the last run (CUDA events on the context stream); -1 = not run
+int cratac_stage_times(cratac_ctx* h, float* ms_out) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < SG_COUNT; i++) {
+        ms_out[i] = -1.0f;
+        if (c->profile && c->ev_used[i]) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]) == cudaSuccess) ms_out[i] = ms;
+            c->ev_used[i] = false;
+        }
+    }
+    return CRATAC_OK;
+}
+
+// the CUDA stream all kernels of this context are launched on (cudaStream_t as an integer)
+int cratac_stream(cratac_ctx* h, uint64_t* stream_out) {
+    *stream_out = (uint64_t)(uintptr_t)h->c.stream;
+    return CRATAC_OK;
 }
 
 int cratac_synchronize(cratac_ctx* h) {
@@ -526,6 +560,7 @@ static int run_tail(Ctx* c, double odds_ratio, cratac_run_result* r) {
         r->n_fragments = c->n_fragments; r->n_barcodes = c->n_barcodes; r->n_bins = c->h_status[ST_N_BINS];
         r->threshold = c->h_status[ST_THRESHOLD]; r->has_params = c->h_status[ST_HAS_PARAMS]; r->n_peaks = c->n_peaks; r->nnz = c->nnz;
         r->em_iterations = c->h_status[ST_EM_ITERS]; r->em_inner_iterations = c->h_status[ST_EM_INNER];
+        r->n_hits = c->n_hits;
         CRATAC_CUDA(cudaMemcpyAsync(r->params, c->d_em_params.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, c->stream));
         CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     }

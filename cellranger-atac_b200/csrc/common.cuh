@@ -59,6 +59,12 @@ enum StatusSlot {
     ST_SLOTS = 24
 };
 
+// per-kernel timers (cudaEvent pairs on the context stream; only recorded when profiling is on)
+enum StageId {
+    SG_DECODE_COUNT = 0, SG_DECODE_PARSE, SG_FRAG_INDEX, SG_PILEUP_HIST, SG_HIST_COMPACT, SG_EM_FIT, SG_PILEUP_PEAKS, SG_MERGE_RUNS,
+    SG_OVERLAP_COUNT, SG_OVERLAP_SCATTER, SG_REDUCE_SMALL, SG_REDUCE_LARGE, SG_CSC_BUILD, SG_BARCODE_TABLE, SG_COUNT
+};
+
 // growable device buffer (grow-only; keeps repeated steps free of cudaMalloc)
 struct DevBuf {
     void* p = nullptr;
@@ -119,11 +125,17 @@ struct Ctx {
     DevBuf d_bc_hits, d_seg_off, d_cursor, d_hits, d_out_row, d_out_cnt, d_nnz_col;
     DevBuf d_indptr, d_indices, d_data;
     int64_t nnz = 0;
+    int64_t n_hits = 0;
     // misc
     DevBuf d_status;                       // int64[ST_SLOTS]
     DevBuf d_scan_tmp;
     int64_t* h_status = nullptr;           // pinned mirror
     int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
+    bool profile = false;
+    cudaEvent_t ev[2 * SG_COUNT] = {};
+    bool ev_used[SG_COUNT] = {};
+    void stage_begin(int id) { if (profile) { cudaEventRecord(ev[2 * id], stream); } }
+    void stage_end(int id) { if (profile) { cudaEventRecord(ev[2 * id + 1], stream); ev_used[id] = true; } }
 };
 
 // ---------------------------------------------------------------- device helpers

@@ -431,6 +431,25 @@ static int build_contig_table(Ctx* c) {
     return CRATAC_OK;
 }
 
+// device half of the barcode dictionary: hash-table slots -> dense ids (slot_to_dense), needed by the
+// overlap kernels; queued right after the parse kernel.
+static int compact_barcode_table(Ctx* c) {
+    int64_t* st = c->d_status.as<int64_t>();
+    size_t nn = (size_t)std::max<int64_t>(c->n_barcodes, 1);
+    CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
+    cudaStream_t s = c->stream;
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
+    c->stage_begin(SG_BARCODE_TABLE);
+    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<unsigned long long>(), c->d_bc_first.as<unsigned long long>(),
+                                                               c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
+                                                               c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
+                                                               reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
+    c->stage_end(SG_BARCODE_TABLE);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
 int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     c->d_text = d_text;
@@ -447,7 +466,9 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
     if (n_tiles == 0) n_tiles = 1;
     CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
     CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
+    c->stage_begin(SG_DECODE_COUNT);
     k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>());
+    c->stage_end(SG_DECODE_COUNT);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>(), c->d_tile_offsets.as<int64_t>(), n_tiles, &st[ST_N_FRAGMENTS]));
@@ -477,7 +498,9 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
         a.status = st;
         a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
+        c->stage_begin(SG_DECODE_PARSE);
         k_parse_tiles<<<(unsigned)n_tiles, DEC_THREADS, 0, c->stream>>>(a);
+        c->stage_end(SG_DECODE_PARSE);
         c->launches++;
         CRATAC_CUDA(cudaGetLastError());
         CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
@@ -501,6 +524,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         c->n_barcodes = nb;
         break;
     }
+    CRATAC_TRY(compact_barcode_table(c));
     return finalize_fragments(c);
 }
 
@@ -512,6 +536,7 @@ int finalize_fragments(Ctx* c) {
     int64_t total_pidx = c->contig_pidx_off[nc];
     CRATAC_TRY(c->d_pos_index.reserve(sizeof(int64_t) * (size_t)total_pidx));
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+    c->stage_begin(SG_FRAG_INDEX);
     if (n > 0) {
         k_check_sorted<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_chrom.as<int32_t>(), c->d_start.as<int32_t>(), n, st);
         c->launches++;
@@ -521,6 +546,7 @@ int finalize_fragments(Ctx* c) {
     k_pos_index<<<(unsigned)((total_pidx + 255) / 256), 256, 0, c->stream>>>(c->d_start.as<int32_t>(), c->d_contig_frag_off.as<int64_t>(),
                                                                              c->d_contig_pidx_off.as<int64_t>(), nc, total_pidx,
                                                                              c->d_pos_index.as<int64_t>());
+    c->stage_end(SG_FRAG_INDEX);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     CRATAC_TRY(sync_status(c));
@@ -594,13 +620,6 @@ int build_barcodes(Ctx* c) {
     CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
     CRATAC_TRY(c->d_dense_to_col.reserve(4 * nn)); CRATAC_TRY(c->d_col_to_dense.reserve(4 * nn));
     cudaStream_t s = c->stream;
-    CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
-    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<unsigned long long>(), c->d_bc_first.as<unsigned long long>(),
-                                                               c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
-                                                               c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
-                                                               reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
-    c->launches++;
-    CRATAC_CUDA(cudaGetLastError());
     const int stride = 64;
     DevBuf d_txt;
     CRATAC_TRY(d_txt.reserve(nn * stride));

@@ -325,7 +325,9 @@ static int em_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, 
     a.Q = w; w += work_n + 2; a.T = w; w += work_v;
     a.first_gt = reinterpret_cast<int*>(w);
     a.work_n = work_n; a.work_v = work_v;
+    c->stage_begin(SG_EM_FIT);
     k_em_fit<<<1, EM_THREADS, 0, c->stream>>>(a);
+    c->stage_end(SG_EM_FIT);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     return CRATAC_OK;

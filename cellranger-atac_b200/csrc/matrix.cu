@@ -221,7 +221,9 @@ int peak_matrix_device(Ctx* c) {
     a.bc_hits = c->d_bc_hits.as<int32_t>(); a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = nullptr;
     int grid = (int)std::min<int64_t>((n + MX_THREADS - 1) / MX_THREADS, (int64_t)NUM_SMS * 16);
     if (grid < 1) grid = 1;
+    c->stage_begin(SG_OVERLAP_COUNT);
     k_overlap<false><<<grid, MX_THREADS, 0, s>>>(a);
+    c->stage_end(SG_OVERLAP_COUNT);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     CRATAC_TRY(exclusive_scan_i32_to_i64(c, a.bc_hits, c->d_seg_off.as<int64_t>(), nb, c->d_seg_off.as<int64_t>() + nb));
@@ -229,10 +231,13 @@ int peak_matrix_device(Ctx* c) {
     CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
     const int64_t K = c->h_status[ST_N_HITS];
+    c->n_hits = K;
     size_t kk = (size_t)std::max<int64_t>(K, 1);
     CRATAC_TRY(c->d_hits.reserve(4 * kk)); CRATAC_TRY(c->d_out_row.reserve(4 * kk)); CRATAC_TRY(c->d_out_cnt.reserve(4 * kk));
     a.hits = c->d_hits.as<int32_t>();
+    c->stage_begin(SG_OVERLAP_SCATTER);
     k_overlap<true><<<grid, MX_THREADS, 0, s>>>(a);
+    c->stage_end(SG_OVERLAP_SCATTER);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     int32_t* nnz_col = c->d_nnz_col.as<int32_t>();
@@ -244,10 +249,14 @@ int peak_matrix_device(Ctx* c) {
             configured = true;
         }
         int g1 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 32);
+        c->stage_begin(SG_REDUCE_SMALL);
         k_reduce_small<<<g1, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
+        c->stage_end(SG_REDUCE_SMALL);
+        c->stage_begin(SG_REDUCE_LARGE);
         int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
         k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4, s>>>(a.hits, a.seg_off, nb, st, c->peaks_on_device_count ? -1 : c->n_peaks,
                                                                  c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
+        c->stage_end(SG_REDUCE_LARGE);
         c->launches += 2;
         CRATAC_CUDA(cudaGetLastError());
     }
@@ -266,8 +275,10 @@ int peak_matrix_device(Ctx* c) {
     CRATAC_TRY(c->d_indices.reserve(8 * zz)); CRATAC_TRY(c->d_data.reserve(4 * zz));
     if (nb > 0) {
         int g = (int)std::min<int64_t>((nb * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
+        c->stage_begin(SG_CSC_BUILD);
         k_csc_copy<<<g, 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d, c->d_indptr.as<int64_t>(), nb,
                                     c->d_indices.as<int64_t>(), c->d_data.as<int32_t>());
+        c->stage_end(SG_CSC_BUILD);
         c->launches++;
         CRATAC_CUDA(cudaGetLastError());
     }

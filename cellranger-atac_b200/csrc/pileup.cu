@@ -471,8 +471,12 @@ int window_histogram(Ctx* c) {
     PileupArgs a;
     fill_args(c, a);
     a.ghist = c->d_hist.as<unsigned long long>();
+    c->stage_begin(SG_PILEUP_HIST);
     CRATAC_TRY(launch_pileup<MODE_HIST>(c, a));
+    c->stage_end(SG_PILEUP_HIST);
+    c->stage_begin(SG_HIST_COMPACT);
     k_hist_compact<<<1, 1024, 0, c->stream>>>(a.ghist, st, c->d_hist_values.as<int64_t>(), c->d_hist_weights.as<int64_t>(), HIST_CAP);
+    c->stage_end(SG_HIST_COMPACT);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     return CRATAC_OK;
@@ -514,7 +518,10 @@ int call_peaks_device(Ctx* c) {
         a.chain = c->d_chain.as<unsigned long long>();
         a.run_start = c->d_run_start.as<int64_t>(); a.run_end = c->d_run_end.as<int64_t>(); a.run_cap = cap;
         a.tile_summary = c->d_tile_summary.as<int4>(); a.fills = fills; a.fill_cap = fill_cap;
+        c->stage_begin(SG_PILEUP_PEAKS);
         CRATAC_TRY(launch_pileup<MODE_PEAKS>(c, a));
+        c->stage_end(SG_PILEUP_PEAKS);
+        c->stage_begin(SG_MERGE_RUNS);
         k_finish_runs<<<1, 32, 0, c->stream>>>(a.chain, n_tiles, st);
         if (n_tiles > 0)
             k_cross_tile_gaps<<<(unsigned)((n_tiles + 127) / 128), 128, 0, c->stream>>>(a.tile_summary, a.tile_off, a.contig_base, c->n_contigs, n_tiles, st,
@@ -529,6 +536,7 @@ int call_peaks_device(Ctx* c) {
                                                                            c->d_peak_chrom.as<int32_t>(), c->d_peak_start.as<int32_t>(),
                                                                            c->d_peak_end.as<int32_t>(), c->d_peak_row.as<int32_t>());
         k_peak_offsets<<<(c->n_contigs + 1 + 127) / 128, 128, 0, c->stream>>>(c->d_peak_chrom.as<int32_t>(), st, c->n_contigs, c->d_peak_off.as<int64_t>());
+        c->stage_end(SG_MERGE_RUNS);
         c->launches += 3;
         CRATAC_CUDA(cudaGetLastError());
         // capacity overflow is only visible on the host: the caller checks status when it syncs.

@@ -61,6 +61,13 @@ int cratac_set_option(cratac_ctx* ctx, const char* key, int64_t value);
 /* kernels launched by this context since creation / last reset */
 int64_t cratac_launch_count(cratac_ctx* ctx, int reset);
 int cratac_synchronize(cratac_ctx* ctx);
+/* the CUDA stream every kernel of this context is launched on (cudaStream_t as an integer) */
+int cratac_stream(cratac_ctx* ctx, uint64_t* stream_out);
+/* per-kernel device times of the last run, measured with CUDA events on that stream when the
+ * option "profile" is 1: ms_out has cratac_num_stages() entries, -1 for stages that did not run. */
+int cratac_num_stages(void);
+const char* cratac_stage_name(int id);
+int cratac_stage_times(cratac_ctx* ctx, float* ms_out);
 
 /* ---- (1) fragment decode: replaces lib/python/tools/io.py:75-79 (open_fragment_file) and
  *      :82-92 (parsed_fragments_from_contig).  `text` is the DECOMPRESSED fragments.tsv
@@ -130,6 +137,7 @@ int cratac_hist_device(cratac_ctx* ctx, const uint64_t** d_hist, int64_t* cap);
 typedef struct cratac_run_result {
     int64_t n_fragments, n_barcodes, n_bins, threshold, has_params, n_peaks, nnz, em_iterations, em_inner_iterations;
     double params[6];
+    int64_t n_hits;   /* fragment ends that fell inside a peak (sum of the matrix) */
 } cratac_run_result;
 int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_device, double odds_ratio,
                cratac_run_result* result);
