@@ -53,6 +53,8 @@ SIGNATURES = {
     "cratac_num_stages": (c_int, []),
     "cratac_stage_name": (c_cp, [c_int]),
     "cratac_stage_times": (c_int, [c_vp, P(ctypes.c_float)]),
+    "cratac_host_times": (c_int, [c_vp, c_vp, c_i64]),
+    "cratac_em_debug": (c_int, [c_vp, P(c_dbl)]),
     "cratac_decode_host": (c_int, [c_vp, c_vp, c_i64]),
     "cratac_decode_device": (c_int, [c_vp, c_vp, c_i64]),
     "cratac_set_fragments": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_cp)]),
@@ -160,6 +162,22 @@ class Context(object):
         ms = (ctypes.c_float * n)()
         check(self._lib.cratac_stage_times(self._h, ms))
         return {self._lib.cratac_stage_name(i).decode(): float(ms[i]) for i in range(n) if ms[i] >= 0}
+
+    def em_debug(self):
+        out = (c_dbl * 9)()
+        check(self._lib.cratac_em_debug(self._h, out))
+        names = ["e_step", "m_sums", "suffix", "bracket", "nodes", "verify", "doubling", "descent", "direct"]
+        return {k: float(v) for k, v in zip(names, out)}
+
+    def host_times(self):
+        buf = ctypes.create_string_buffer(4096)
+        check(self._lib.cratac_host_times(self._h, buf, 4096))
+        out = []
+        for kv in buf.value.decode().split(";"):
+            if kv:
+                k, v = kv.split("=")
+                out.append((k, float(v)))
+        return out
 
     # ---- decode
     def decode_host(self, text):

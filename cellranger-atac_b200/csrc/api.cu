@@ -165,6 +165,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
         return CRATAC_OK;
     }
     if (!strcmp(key, "run_capacity")) { c->run_cap = value; return CRATAC_OK; }
+    if (!strcmp(key, "em_fast")) { c->em_fast = value != 0; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
         c->profile = value != 0;
@@ -543,8 +544,11 @@ static int run_tail(Ctx* c, double odds_ratio, cratac_run_result* r) {
     CRATAC_TRY(window_histogram(c));
     CRATAC_TRY(fit_threshold_device(c, odds_ratio));
     CRATAC_TRY(call_peaks_device(c));
+    c->host_mark("launch_hist_fit_peaks");
     CRATAC_TRY(peak_matrix_device(c));
+    c->host_mark("peak_matrix_total");
     int rc = sync_status(c);
+    c->host_mark("final_sync");
     if (rc == CRATAC_ERR_CAPACITY && c->run_cap < ((int64_t)1 << 30)) {
         // the run list overflowed: grow it and redo peaks + matrix (the fitted threshold is still on the device)
         c->run_cap <<= 2;
@@ -568,9 +572,30 @@ static int run_tail(Ctx* c, double odds_ratio, cratac_run_result* r) {
 }
 
 int cratac_run(cratac_ctx* h, const char* text, int64_t nbytes, int text_is_device, double odds_ratio, cratac_run_result* result) {
+    h->c.host_reset();
     if (text_is_device) CRATAC_TRY(cratac_decode_device(h, text, nbytes));
     else CRATAC_TRY(cratac_decode_host(h, text, nbytes));
+    h->c.host_mark("decode_total");
     return run_tail(&h->c, odds_ratio, result);
+}
+
+// cycles per phase of the last threshold fit (profiling aid): e_step, m_sums, suffix, bracket, nodes, verify,
+// doubling, descent, direct -- 9 doubles
+int cratac_em_debug(cratac_ctx* h, double* out) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_CUDA(cudaMemcpyAsync(out, c->d_em_params.as<double>() + 8, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    return CRATAC_OK;
+}
+
+// host wall-clock phases of the last cratac_run as "name=ms;name=ms;..." (option "profile" = 1)
+int cratac_host_times(cratac_ctx* h, char* out, int64_t cap) {
+    std::string s;
+    for (auto& kv : h->c.host_ms) { char b[96]; snprintf(b, sizeof(b), "%s=%.3f;", kv.first.c_str(), kv.second); s += b; }
+    if ((int64_t)s.size() + 1 > cap) return CRATAC_ERR_ARG;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return CRATAC_OK;
 }
 
 int cratac_run_from_fragments(cratac_ctx* h, double odds_ratio, cratac_run_result* result) {

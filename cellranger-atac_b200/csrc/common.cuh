@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <chrono>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cratac.h"
@@ -56,6 +58,7 @@ enum StatusSlot {
     ST_EM_INNER = 16,
     ST_TICKET = 17,
     ST_TICKET2 = 18,
+    ST_EM_DIRECT = 19,   // direct evaluations of the dispersion fixed-point map
     ST_SLOTS = 24
 };
 
@@ -131,9 +134,20 @@ struct Ctx {
     DevBuf d_scan_tmp;
     int64_t* h_status = nullptr;           // pinned mirror
     int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
+    bool em_fast = true;                   // accelerated dispersion fixed point (em.cu)
     bool profile = false;
     cudaEvent_t ev[2 * SG_COUNT] = {};
     bool ev_used[SG_COUNT] = {};
+    // host wall-clock marks (profiling only): time since the previous mark is charged to `name`
+    std::vector<std::pair<std::string, double>> host_ms;
+    std::chrono::steady_clock::time_point host_t0;
+    void host_reset() { if (profile) { host_ms.clear(); host_t0 = std::chrono::steady_clock::now(); } }
+    void host_mark(const char* name) {
+        if (!profile) return;
+        auto t = std::chrono::steady_clock::now();
+        host_ms.emplace_back(name, std::chrono::duration<double, std::milli>(t - host_t0).count());
+        host_t0 = t;
+    }
     void stage_begin(int id) { if (profile) { cudaEventRecord(ev[2 * id], stream); } }
     void stage_end(int id) { if (profile) { cudaEventRecord(ev[2 * id + 1], stream); ev_used[id] = true; } }
 };

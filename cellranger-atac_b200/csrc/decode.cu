@@ -476,6 +476,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     int64_t n = c->h_status[ST_N_FRAGMENTS];
     c->n_fragments = n;
+    c->host_mark("decode_count_sync");
     size_t nn = (size_t)std::max<int64_t>(n, 1);
     CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));
     CRATAC_TRY(c->d_bc.reserve(4 * nn)); CRATAC_TRY(c->d_dup.reserve(4 * nn));
@@ -505,6 +506,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         CRATAC_CUDA(cudaGetLastError());
         CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
         CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+        c->host_mark("decode_parse_sync");
         int64_t err = c->h_status[ST_ERROR];
         int64_t nb = c->h_status[ST_N_BARCODES];
         bool crowded = nb * 2 > (int64_t)c->bc_table_cap;

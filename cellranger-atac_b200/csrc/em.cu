@@ -31,6 +31,8 @@ struct EmArgs {
     // work arrays
     double* vd; double* wd; double* R0; double* R1; double* R2; double* Q; double* T;
     int* first_gt;
+    double* costab;            // [64][64] cos(k * theta_i), Chebyshev-Gauss nodes
+    int fast_fixed_point;
     int64_t work_n, work_v;
 };
 
@@ -68,6 +70,12 @@ __device__ __forceinline__ double block_max(double x, double* sm) {
     return m;
 }
 
+// profiling: cycles spent per phase (thread 0's clock), written to params_out[8 + phase]
+enum { PH_ESTEP = 0, PH_MSUMS, PH_SUFFIX, PH_BRACKET, PH_NODES, PH_VERIFY, PH_DOUBLING, PH_DESCENT, PH_DIRECT, PH_COUNT };
+__device__ long long g_em_cycles[PH_COUNT];
+#define PH_BEGIN() long long _ph_t0 = clock64()
+#define PH_END(ph) do { long long _t = clock64(); if (threadIdx.x == 0) g_em_cycles[ph] += _t - _ph_t0; _ph_t0 = _t; } while (0)
+
 struct Theta { double p_zero, mean_bg, alpha_bg, p_signal, f_zero, f_bg; };
 
 __device__ __forceinline__ double nb_pmf(double k, double n, double p) {
@@ -101,9 +109,177 @@ __device__ void suffix_sums(const EmArgs& a, int n, double* sm) {
     (void)sm;
 }
 
-// M-step (peaks.py:90-128).  Returns false when the reference would raise ZeroDivisionError.
-__device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, long long& inner_total) {
+
+// ------------------------------------------------------------------------------------------------
+// Accelerated NB-dispersion fixed point.
+//
+// The reference iterates alpha <- G(alpha) up to 10000 times per M-step (em_fitting.py:69-74) and
+// stops at the first iterate whose relative step is < 1e-6; with linear convergence that is
+// hundreds of strictly sequential evaluations.  Here F(x) = log G(exp x) is interpolated once per
+// M-step by a 64-node Chebyshev series on an interval that brackets every iterate (accuracy
+// checked against direct evaluation, ~1e-14), the maps F^(2), F^(4), ... are built by composing
+// the interpolant with itself, and a binary descent over those powers lands a few iterations
+// short of the stopping index; the last iterations and the stopping test itself are evaluated
+// directly, exactly as the reference does.  Any failed safety check falls back to the plain loop.
+constexpr int CH_M = 64;
+constexpr int CH_LEVELS = 14;
+
+struct FixedPointSmem {
+    double pts[CH_M];
+    double val[CH_M];
+    double coef[CH_LEVELS][CH_M];
+    int ncoef[CH_LEVELS];
+    int flag;
+    int imax;
+};
+
+// G(alpha) of em_fitting.py:41-56 for 64 values of alpha at once: 16 threads per value
+__device__ void eval_G_points(const EmArgs& a, int jmax, double mu, double N1, FixedPointSmem& f) {
+    const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
+    const double alpha = f.pts[grp];
+    double part = 0.0;
+    for (int j = 1 + sub; j < jmax; j += 16) {
+        double aj = alpha * (double)j;
+        part += aj / (1.0 + aj) * a.T[j];
+    }
+#pragma unroll
+    for (int d = 8; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (sub == 0) f.val[grp] = log(1.0 + alpha * mu) / (mu - part / N1);
+    __syncthreads();
+}
+
+__device__ __forceinline__ double clenshaw(const double* c, int nc, double t) {
+    t = fmin(1.0, fmax(-1.0, t));
+    double b1 = 0.0, b2 = 0.0;
+    const double t2 = 2.0 * t;
+    for (int k = nc - 1; k > 0; k--) {
+        double b0 = fma(t2, b1, c[k] - b2);
+        b2 = b1; b1 = b0;
+    }
+    return fma(t, b1, c[0] - b2);
+}
+
+// node values (one per thread < 64, in f.val) -> Chebyshev coefficients of level L
+__device__ void cheb_fit(const EmArgs& a, FixedPointSmem& f, int L) {
+    const int k = threadIdx.x;
+    if (k == 0) f.imax = 0;
+    __syncthreads();
+    double c = 0.0;
+    if (k < CH_M) {
+        for (int i = 0; i < CH_M; i++) c = fma(f.val[i], a.costab[k * CH_M + i], c);
+        c *= (k == 0 ? 1.0 : 2.0) / CH_M;
+        f.coef[L][k] = c;
+        if (fabs(c) > 1e-18) atomicMax(&f.imax, k);
+    }
+    __syncthreads();
+    if (k == 0) f.ncoef[L] = f.imax + 1;
+    __syncthreads();
+}
+
+// Returns true and sets *alpha_k / *k_done when the jump was made; false => caller runs the plain loop.
+__device__ bool fixed_point_jump(const EmArgs& a, int jmax, double mu, double N1, double alpha0, double a1, FixedPointSmem& f,
+                                 double* alpha_k, int* k_done) {
     const int tid = threadIdx.x;
+    const double s = a1 > alpha0 ? 1.0 : -1.0;
+    PH_BEGIN();
+    // ---- bracket the fixed point: geometric candidates, then a linear refinement
+    if (tid < CH_M) f.pts[tid] = alpha0 * pow(1.25, s * (double)(tid + 1));
+    __syncthreads();
+    eval_G_points(a, jmax, mu, N1, f);
+    int hit = -1;
+    for (int i = 0; i < CH_M; i++)
+        if (s * (f.val[i] - f.pts[i]) <= 0.0) { hit = i; break; }
+    if (hit < 0) return false;
+    const double lo_c = hit == 0 ? alpha0 : f.pts[hit - 1], hi_c = f.pts[hit];
+    __syncthreads();
+    if (tid < CH_M) f.pts[tid] = lo_c + (hi_c - lo_c) * (double)(tid + 1) / (double)CH_M;
+    __syncthreads();
+    eval_G_points(a, jmax, mu, N1, f);
+    double b = hi_c;
+    for (int i = 0; i < CH_M; i++)
+        if (s * (f.val[i] - f.pts[i]) <= 0.0) { b = f.pts[i]; break; }
+    const double xa = log(fmin(alpha0, b)), xb = log(fmax(alpha0, b));
+    const double half = 0.5 * (xb - xa), mid = 0.5 * (xb + xa);
+    if (!(half > 0.0) || !isfinite(half)) return false;
+    __syncthreads();
+    PH_END(PH_BRACKET);
+    // ---- interpolate F(x) = log G(exp x) at the Chebyshev-Gauss nodes t_i = cos(theta_i)
+    if (tid < CH_M) f.pts[tid] = exp(mid + half * a.costab[CH_M + tid]);
+    __syncthreads();
+    eval_G_points(a, jmax, mu, N1, f);
+    // slopes between neighbouring nodes must lie in (0, 1): monotone, contracting iteration
+    if (tid == 0) f.flag = 1;
+    __syncthreads();
+    double fx = 0.0;
+    if (tid < CH_M) {
+        fx = log(f.val[tid]);
+        if (!isfinite(fx)) f.flag = 0;
+    }
+    __syncthreads();
+    if (tid < CH_M) f.val[tid] = fx;
+    __syncthreads();
+    if (tid < CH_M - 1) {
+        double dx = half * (a.costab[CH_M + tid] - a.costab[CH_M + tid + 1]);     // > 0 (nodes descend)
+        double df = f.val[tid] - f.val[tid + 1];
+        if (!(df > 0.0) || !(df < dx)) f.flag = 0;
+    }
+    __syncthreads();
+    if (!f.flag) return false;
+    cheb_fit(a, f, 0);
+    PH_END(PH_NODES);
+    // ---- accuracy check at the Chebyshev extrema against direct evaluation
+    if (tid < CH_M) f.pts[tid] = exp(mid + half * cos(3.14159265358979323846 * (double)tid / (double)CH_M));
+    __syncthreads();
+    eval_G_points(a, jmax, mu, N1, f);
+    if (tid < CH_M) {
+        double t = cos(3.14159265358979323846 * (double)tid / (double)CH_M);
+        double err = fabs(clenshaw(f.coef[0], f.ncoef[0], t) - log(f.val[tid]));
+        if (!(err < 2e-12)) f.flag = 0;
+    }
+    __syncthreads();
+    if (!f.flag) return false;
+    PH_END(PH_VERIFY);
+    // ---- powers of two of the map, built until one jump from x0 already overshoots the stopping point
+    const double x0 = log(alpha0);
+    const double epsx = 1e-6 * (1.0 + 1e-3);
+    const double inv_half = 1.0 / half;
+    int n_levels = 1;
+    while (n_levels < CH_LEVELS) {
+        const double* cl = f.coef[n_levels - 1];
+        const int nc = f.ncoef[n_levels - 1];
+        double y0 = clenshaw(cl, nc, (x0 - mid) * inv_half);
+        double step = fabs(clenshaw(f.coef[0], f.ncoef[0], (y0 - mid) * inv_half) - y0);
+        if (step < epsx) break;
+        double v = 0.0;
+        if (tid < CH_M) {
+            double y = clenshaw(cl, nc, a.costab[CH_M + tid]);
+            v = clenshaw(cl, nc, (y - mid) * inv_half);
+        }
+        __syncthreads();
+        if (tid < CH_M) f.val[tid] = v;
+        __syncthreads();
+        cheb_fit(a, f, n_levels);
+        n_levels++;
+    }
+    PH_END(PH_DOUBLING);
+    // ---- binary descent: keep every jump that still lands before the stopping point
+    double x = x0;
+    int k = 0;
+    for (int L = n_levels - 1; L >= 0; L--) {
+        double y = clenshaw(f.coef[L], f.ncoef[L], (x - mid) * inv_half);
+        double step = fabs(clenshaw(f.coef[0], f.ncoef[0], (y - mid) * inv_half) - y);
+        if (step >= epsx && k + (1 << L) <= 9998) { x = y; k += 1 << L; }
+    }
+    PH_END(PH_DESCENT);
+    *alpha_k = exp(x);
+    *k_done = k;
+    return true;
+}
+
+// M-step (peaks.py:90-128).  Returns false when the reference would raise ZeroDivisionError.
+__device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, FixedPointSmem& fps, long long& inner_total, long long& direct_total) {
+    const int tid = threadIdx.x;
+    PH_BEGIN();
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // N0 K0 N1 M1 N2 K2 vmax1
     double vmax1 = 0.0;
     for (int i = tid; i < n; i += EM_THREADS) {
@@ -138,24 +314,51 @@ __device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, long long&
     double var = sq[0] / N1;
     double alpha = fmax(1e-6, (var - mu) / (mu * mu));        // MOM_dispersion
     if (vmax1 > 1e8 || !(var > mu)) { th.alpha_bg = alpha; return true; }
+    PH_END(PH_MSUMS);
     // tail weights T(j) = sum_{i: v_i > j} w_i R1_i  for j = 0 .. vmax1-1
     suffix_sums(a, n, sm);
     const int jmax = (int)vmax1;               // terms j = 0 .. jmax-1  (np.arange(max(counts)))
     for (int j = tid; j < jmax; j += EM_THREADS) a.T[j] = a.Q[a.first_gt[j]];
     __syncthreads();
+    PH_END(PH_SUFFIX);
     double newv = alpha;
     int it = 0;
-    for (; it < 10000; it++) {
+    long long direct = 0;
+    auto G_block = [&](double al) {
         double part[1] = {0.0};
         for (int j = tid + 1; j < jmax; j += EM_THREADS) {    // j = 0 contributes 0
-            double aj = alpha * (double)j;
+            double aj = al * (double)j;
             part[0] += aj / (1.0 + aj) * a.T[j];
         }
         block_sum<1>(part, sm);
-        newv = log(1.0 + alpha * mu) / (mu - part[0] / N1);
-        if (2.0 * fabs(newv - alpha) / (newv + alpha) < 1e-6) { it++; break; }
-        alpha = newv;
+        direct++;
+        return log(1.0 + al * mu) / (mu - part[0] / N1);
+    };
+    bool done = false;
+    if (a.fast_fixed_point) {
+        // first iteration exactly as the reference; it also gives the direction of travel
+        newv = G_block(alpha);
+        PH_END(PH_DIRECT);
+        it = 1;
+        if (2.0 * fabs(newv - alpha) / (newv + alpha) < 1e-6) done = true;
+        else {
+            double ak = alpha;
+            int kd = 0;
+            if (fixed_point_jump(a, jmax, mu, N1, alpha, newv, fps, &ak, &kd) && kd > 0) { alpha = ak; it = kd; }
+            else { alpha = newv; }    // no jump: carry on from iterate 1
+        }
     }
+    if (!done) {
+        _ph_t0 = clock64();
+        for (; it < 10000;) {
+            newv = G_block(alpha);
+            it++;
+            if (2.0 * fabs(newv - alpha) / (newv + alpha) < 1e-6) break;
+            alpha = newv;
+        }
+    }
+    PH_END(PH_DIRECT);
+    direct_total += direct;
     inner_total += it;
     th.alpha_bg = newv;
     return true;
@@ -163,6 +366,7 @@ __device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, long long&
 
 // E-step (peaks.py:66-87)
 __device__ void e_step(const EmArgs& a, int n, const Theta& th) {
+    PH_BEGIN();
     const double f_sig = 1.0 - th.f_zero - th.f_bg;
     const double nn = 1.0 / th.alpha_bg;
     const double pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
@@ -176,6 +380,7 @@ __device__ void e_step(const EmArgs& a, int n, const Theta& th) {
         else { a.R0[i] = z / tot; a.R1[i] = b / tot; a.R2[i] = s / tot; }
     }
     __syncthreads();
+    PH_END(PH_ESTEP);
 }
 
 __device__ __forceinline__ void normalize(Theta& t) {   // peaks.py:131-141
@@ -193,7 +398,7 @@ __device__ __forceinline__ bool moved(const Theta& last, const Theta& cur, doubl
 }
 
 // estimate_parameters (peaks.py:144-170).  ok=false => ZeroDivisionError in the reference.
-__device__ bool estimate_parameters(const EmArgs& a, int n, int t0, bool seeded, Theta& th, double* sm, long long& iters, long long& inner) {
+__device__ bool estimate_parameters(const EmArgs& a, int n, int t0, bool seeded, Theta& th, double* sm, FixedPointSmem& fps, long long& iters, long long& inner, long long& direct) {
     const int tid = threadIdx.x;
     if (!seeded) {
         for (int i = tid; i < n; i += EM_THREADS) {
@@ -203,7 +408,7 @@ __device__ bool estimate_parameters(const EmArgs& a, int n, int t0, bool seeded,
             a.R2[i] = (v > (double)t0) ? 1.0 : 0.0;
         }
         __syncthreads();
-        if (!m_step(a, n, th, sm, inner)) return false;
+        if (!m_step(a, n, th, sm, fps, inner, direct)) return false;
     }
     Theta last = th;
     bool have_last = false;
@@ -214,7 +419,7 @@ __device__ bool estimate_parameters(const EmArgs& a, int n, int t0, bool seeded,
         last = th;
         have_last = true;
         Theta nt = th;
-        if (!m_step(a, n, nt, sm, inner)) return false;
+        if (!m_step(a, n, nt, sm, fps, inner, direct)) return false;
         normalize(nt);
         th = nt;
     }
@@ -225,10 +430,17 @@ __device__ bool estimate_parameters(const EmArgs& a, int n, int t0, bool seeded,
 __global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
     __shared__ double sm[EM_WARPS * 8];
     __shared__ int s_int;
+    __shared__ FixedPointSmem fps;
     const int tid = threadIdx.x;
     int64_t n64 = a.n_bins_host >= 0 ? a.n_bins_host : a.status[ST_N_BINS];
     const int n = (int)n64;
-    long long iters = 0, inner = 0;
+    long long iters = 0, inner = 0, direct = 0;
+    if (tid == 0) for (int q = 0; q < PH_COUNT; q++) g_em_cycles[q] = 0;
+    for (int q = tid; q < CH_M * CH_M; q += EM_THREADS) {
+        int k = q / CH_M, i = q % CH_M;
+        a.costab[q] = cos((double)k * 3.14159265358979323846 * ((double)i + 0.5) / (double)CH_M);
+    }
+    __syncthreads();
     // ---- gate (peaks.py:176-177)
     double tot[1] = {0.0};
     double vmax = 0.0;
@@ -280,14 +492,14 @@ __global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
     if (t0 < 0) { if (tid == 0) raise_error(a.status, CRATAC_ERR_EM_INDEX, n); return; }
 
     Theta th;
-    bool ok = estimate_parameters(a, n, t0, false, th, sm, iters, inner);
+    bool ok = estimate_parameters(a, n, t0, false, th, sm, fps, iters, inner, direct);
     int tries = 0;
     while (ok && (1.0 / th.p_zero < th.mean_bg) && tries < 3) {   // peaks.py:183-191
         Theta seed;
         seed.p_zero = th.p_signal; seed.mean_bg = 1.0 / th.p_zero; seed.alpha_bg = th.alpha_bg; seed.p_signal = 1.0 / th.mean_bg;
         seed.f_zero = 1.0 - (th.f_zero + th.f_bg); seed.f_bg = th.f_bg;
         th = seed;
-        ok = estimate_parameters(a, n, t0, true, th, sm, iters, inner);
+        ok = estimate_parameters(a, n, t0, true, th, sm, fps, iters, inner, direct);
         tries++;
     }
     if (!ok) { if (tid == 0) raise_error(a.status, CRATAC_ERR_EM_ZERODIV, n); return; }
@@ -306,23 +518,26 @@ __global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
     if (tid == 0) {
         a.status[ST_THRESHOLD] = best < 0.0 ? 0 : (int64_t)best;   // None in the reference filters nothing == threshold 0
         a.status[ST_HAS_PARAMS] = best < 0.0 ? 2 : 1;
-        a.status[ST_EM_ITERS] = iters; a.status[ST_EM_INNER] = inner;
+        a.status[ST_EM_ITERS] = iters; a.status[ST_EM_INNER] = inner; a.status[ST_EM_DIRECT] = direct;
         a.params_out[0] = th.p_zero; a.params_out[1] = th.mean_bg; a.params_out[2] = th.alpha_bg;
         a.params_out[3] = th.p_signal; a.params_out[4] = th.f_zero; a.params_out[5] = th.f_bg;
+        for (int q = 0; q < PH_COUNT; q++) a.params_out[8 + q] = (double)g_em_cycles[q];
     }
 }
 
 static int em_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio) {
     const int64_t work_n = 1 << 16, work_v = HIST_CAP + 2;
-    size_t doubles = (size_t)work_n * 6 + 2 + (size_t)work_v;
+    size_t doubles = (size_t)work_n * 6 + 2 + (size_t)work_v + 64 * 64;
     CRATAC_TRY(c->d_em_work.reserve(doubles * 8 + (size_t)work_v * 4));
-    CRATAC_TRY(c->d_em_params.reserve(8 * 8));
+    CRATAC_TRY(c->d_em_params.reserve(8 * 32));
     EmArgs a;
     a.values = d_values; a.weights = d_weights; a.n_bins_host = n_bins_host; a.status = c->d_status.as<int64_t>();
     a.params_out = c->d_em_params.as<double>(); a.odds_ratio = odds_ratio;
     double* w = c->d_em_work.as<double>();
     a.vd = w; w += work_n; a.wd = w; w += work_n; a.R0 = w; w += work_n; a.R1 = w; w += work_n; a.R2 = w; w += work_n;
     a.Q = w; w += work_n + 2; a.T = w; w += work_v;
+    a.costab = w; w += 64 * 64;
+    a.fast_fixed_point = c->em_fast ? 1 : 0;
     a.first_gt = reinterpret_cast<int*>(w);
     a.work_n = work_n; a.work_v = work_v;
     c->stage_begin(SG_EM_FIT);

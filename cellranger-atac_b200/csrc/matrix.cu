@@ -230,6 +230,7 @@ int peak_matrix_device(Ctx* c) {
     // K (total hits) sizes the hit buffers: one host round trip here (8 bytes)
     CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
+    c->host_mark("matrix_wait_hits");
     const int64_t K = c->h_status[ST_N_HITS];
     c->n_hits = K;
     size_t kk = (size_t)std::max<int64_t>(K, 1);
@@ -261,7 +262,9 @@ int peak_matrix_device(Ctx* c) {
         CRATAC_CUDA(cudaGetLastError());
     }
     // column order (host work of build_barcodes overlaps the kernels queued above)
+    c->host_mark("matrix_launch");
     CRATAC_TRY(build_barcodes(c));
+    c->host_mark("build_barcodes");
     const int32_t* c2d = c->d_col_to_dense.as<int32_t>();
     if (nb > 0) {
         k_gather_nnz<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(nnz_col, c2d, nb, nnz_ordered);

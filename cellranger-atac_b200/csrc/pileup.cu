@@ -48,10 +48,13 @@ struct PileupArgs {
     int64_t* status;
     unsigned long long* ghist;      // MODE_HIST
     // MODE_PEAKS
-    unsigned long long* chain;      // per tile: ready bit | n_ends << 31 | n_starts   (inclusive prefix)
-    int64_t* run_start;
-    int64_t* run_end;
-    int64_t run_cap;
+    int64_t* evt_start;             // per-CTA private regions of cta_cap entries: run boundaries in tile order
+    int64_t* evt_end;
+    int64_t cta_cap;
+    int32_t* tile_ns;               // per tile: number of run starts / ends it emitted
+    int32_t* tile_ne;
+    int64_t* tile_src_s;            // per tile: where its events sit in evt_start / evt_end
+    int64_t* tile_src_e;
     int4* tile_summary;             // first_nz_pos, first_nz_val, last_nz_pos, last_nz_val
     int64_t* fills;                 // pairs (g0, g1)
     int64_t fill_cap;
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
     __shared__ int warp_tot[PU_THREADS / 32];
     __shared__ long long s_tile;
     __shared__ int s_first_nz, s_last_nz;
-    __shared__ unsigned long long s_chain_prev;
+    __shared__ long long s_base_s, s_base_e;
+    __shared__ int s_cur_s, s_cur_e;
     __shared__ int s_contig;
 
     const int tid = threadIdx.x;
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
     long long thr_ll = a.status[ST_THRESHOLD];
     const int thr = thr_ll < 1 ? 1 : (thr_ll > 0x7fffffffLL ? 0x7fffffff : (int)thr_ll);
     int loc_max = 0;
+    if (MODE == MODE_PEAKS && tid == 0) { s_cur_s = 0; s_cur_e = 0; }
 
     while (true) {
         __syncthreads();
@@ -234,21 +239,18 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
             int tot_s = 0, tot_e = 0;
             int off_s = block_excl_scan_i32(n_s, warp_tot, &tot_s);
             int off_e = block_excl_scan_i32(n_e, warp_tot, &tot_e);
-            // ---- chained prefix over tiles (tiles are ticketed in genome order => predecessor is running or done)
+            // ---- this CTA appends the tile's boundaries to its private region (tile order is restored by
+            //      k_gather_events from the per-tile counts; no CTA ever waits for another)
             if (tid == 0) {
-                unsigned long long prev = 0;
-                if (tile > 0) {
-                    unsigned long long v;
-                    long long spins = 0;
-                    while (((v = ld_acquire_u64(&a.chain[tile - 1])) >> 63) == 0ULL) {
-                        if (++spins > (1LL << 26)) { raise_error(a.status, CRATAC_ERR_INTERNAL, tile); break; }
-                        __nanosleep(20);
-                    }
-                    prev = v & 0x7FFFFFFFFFFFFFFFULL;
-                }
-                unsigned long long mine = prev + (unsigned long long)tot_s + ((unsigned long long)tot_e << 31);
-                st_release_u64(&a.chain[tile], mine | 0x8000000000000000ULL);
-                s_chain_prev = prev;
+                s_base_s = (long long)blockIdx.x * a.cta_cap + s_cur_s;
+                s_base_e = (long long)blockIdx.x * a.cta_cap + s_cur_e;
+                a.tile_ns[tile] = tot_s; a.tile_ne[tile] = tot_e;
+                a.tile_src_s[tile] = s_base_s; a.tile_src_e[tile] = s_base_e;
+                if ((long long)s_cur_s + tot_s > a.cta_cap || (long long)s_cur_e + tot_e > a.cta_cap) {
+                    raise_error(a.status, CRATAC_ERR_CAPACITY, -1);
+                    a.tile_ns[tile] = 0; a.tile_ne[tile] = 0;
+                    s_base_s = -1;
+                } else { s_cur_s += tot_s; s_cur_e += tot_e; }
                 int4 sm;
                 sm.x = sm.z = -1; sm.y = sm.w = 0;
                 if (s_last_nz >= 0) {
@@ -259,19 +261,19 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
                 a.tile_summary[tile] = sm;
             }
             __syncthreads();
-            if (n_s + n_e > 0) {
+            if (n_s + n_e > 0 && s_base_s >= 0) {
                 const int64_t g0 = a.contig_base[c] + ta;
-                int64_t os = (int64_t)(s_chain_prev & 0x7FFFFFFFULL) + off_s;
-                int64_t oe = (int64_t)((s_chain_prev >> 31) & 0xFFFFFFFFULL) + off_e;
+                int64_t os = s_base_s + off_s;
+                int64_t oe = s_base_e + off_e;
                 int pw = prev_w;
                 for (int k = k0; k < k1; k++) {
                     int w = sc[k + 402] - sc[k + 1];
                     bool sig = w >= thr, psig = pw >= thr;
-                    if (sig && !psig) { if (os < a.run_cap) a.run_start[os] = g0 + k; else raise_error(a.status, CRATAC_ERR_CAPACITY, -1); os++; }
-                    if (!sig && psig) { if (oe < a.run_cap) a.run_end[oe] = g0 + k; else raise_error(a.status, CRATAC_ERR_CAPACITY, -1); oe++; }
+                    if (sig && !psig) a.evt_start[os++] = g0 + k;
+                    if (!sig && psig) a.evt_end[oe++] = g0 + k;
                     pw = w;
                 }
-                if (k1 == own && tb == L && pw >= thr) { if (oe < a.run_cap) a.run_end[oe] = g0 + own; else raise_error(a.status, CRATAC_ERR_CAPACITY, -1); }
+                if (k1 == own && tb == L && pw >= thr) a.evt_end[oe] = g0 + own;
             }
         }
     }
@@ -285,10 +287,6 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
 #pragma unroll
         for (int d = 16; d; d >>= 1) loc_max = max(loc_max, __shfl_xor_sync(0xffffffffu, loc_max, d));
         if ((tid & 31) == 0 && loc_max > 0) atomicMax(reinterpret_cast<long long*>(&a.status[ST_MAX_COUNT]), (long long)loc_max);
-    }
-    if (MODE == MODE_PEAKS) {
-        // last tile publishes the totals
-        // (done by whoever processed tile n_tiles-1; read back by k_finish_runs)
     }
 }
 
@@ -328,13 +326,25 @@ __global__ void __launch_bounds__(1024) k_hist_compact(const unsigned long long*
 }
 
 // ---- run list post-processing -----------------------------------------------------------------
-__global__ void k_finish_runs(const unsigned long long* __restrict__ chain, int64_t n_tiles, int64_t* status) {
+// totals of the two per-tile scans must agree: every run has one start and one end
+__global__ void k_finish_runs(int64_t* status) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long v = n_tiles > 0 ? chain[n_tiles - 1] : 0ULL;
-        v &= 0x7FFFFFFFFFFFFFFFULL;
-        int64_t ns = (int64_t)(v & 0x7FFFFFFFULL), ne = (int64_t)((v >> 31) & 0xFFFFFFFFULL);
-        if (ns != ne) raise_error(status, CRATAC_ERR_INTERNAL, -3);
-        status[ST_N_RUNS] = ns;
+        if (status[ST_N_RUNS] != status[ST_TICKET2]) raise_error(status, CRATAC_ERR_INTERNAL, -3);
+    }
+}
+
+// one warp per tile: copy the tile's boundaries from the CTA-private region to their global rank
+__global__ void __launch_bounds__(256) k_gather_events(const int64_t* __restrict__ evt, const int32_t* __restrict__ tile_n,
+                                                        const int64_t* __restrict__ tile_src, const int64_t* __restrict__ tile_dst,
+                                                        int64_t n_tiles, int64_t cap, int64_t* __restrict__ out, int64_t* status) {
+    const int lane = threadIdx.x & 31;
+    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    int n = tile_n[t];
+    int64_t src = tile_src[t], dst = tile_dst[t];
+    for (int k = lane; k < n; k += 32) {
+        if (dst + k < cap) out[dst + k] = evt[src + k];
+        else raise_error(status, CRATAC_ERR_CAPACITY, -1);
     }
 }
 
@@ -436,7 +446,8 @@ static int fill_args(Ctx* c, PileupArgs& a) {
     a.contig_base = c->d_contig_base.as<int64_t>(); a.tile_off = c->d_contig_tile_off.as<int64_t>();
     a.n_contigs = c->n_contigs; a.n_tiles = c->contig_tile_off[c->n_contigs];
     a.status = c->d_status.as<int64_t>();
-    a.ghist = nullptr; a.chain = nullptr; a.run_start = a.run_end = nullptr; a.run_cap = 0; a.tile_summary = nullptr;
+    a.ghist = nullptr; a.evt_start = a.evt_end = nullptr; a.cta_cap = 0; a.tile_ns = a.tile_ne = nullptr;
+    a.tile_src_s = a.tile_src_e = nullptr; a.tile_summary = nullptr;
     a.fills = nullptr; a.fill_cap = 0; a.dump_W = nullptr; a.dump_contig = -1;
     return CRATAC_OK;
 }
@@ -495,9 +506,14 @@ int call_peaks_device(Ctx* c) {
     if (c->run_cap == 0) c->run_cap = 1 << 22;
     for (int attempt = 0;; attempt++) {
         int64_t cap = c->run_cap;
-        CRATAC_TRY(c->d_chain.reserve(8 * (size_t)std::max<int64_t>(n_tiles, 1)));
-        CRATAC_TRY(c->d_tile_summary.reserve(16 * (size_t)std::max<int64_t>(n_tiles, 1)));
-        CRATAC_TRY(c->d_run_start.reserve(8 * (size_t)cap)); CRATAC_TRY(c->d_run_end.reserve(8 * (size_t)cap));
+        const size_t nt = (size_t)std::max<int64_t>(n_tiles, 1);
+        const int64_t n_cta = std::max<int64_t>(std::min<int64_t>(n_tiles, 2 * NUM_SMS), 1);
+        const int64_t cta_cap = std::max<int64_t>(cap / n_cta, 64);
+        // chain buffer layout: tile_ns | tile_ne (int32) then tile_src_s | tile_src_e | tile_dst_s | tile_dst_e (int64)
+        CRATAC_TRY(c->d_chain.reserve(nt * (2 * 4 + 4 * 8)));
+        CRATAC_TRY(c->d_tile_summary.reserve(16 * nt));
+        CRATAC_TRY(c->d_run_start.reserve(8 * (size_t)cap + 8 * (size_t)(n_cta * cta_cap)));
+        CRATAC_TRY(c->d_run_end.reserve(8 * (size_t)cap + 8 * (size_t)(n_cta * cta_cap)));
         CRATAC_TRY(c->d_bridge.reserve(4 * (size_t)cap * 2));          // bridge flags + head flags
         CRATAC_TRY(c->d_fill.reserve(16 * (size_t)cap / 16 + 8 * (size_t)cap));   // fills + head ranks
         CRATAC_TRY(c->d_peak_chrom.reserve(4 * (size_t)cap)); CRATAC_TRY(c->d_peak_start.reserve(4 * (size_t)cap));
@@ -509,30 +525,45 @@ int call_peaks_device(Ctx* c) {
         int64_t* head_rank = fills + 2 * fill_cap;
         int32_t* bridge = c->d_bridge.as<int32_t>();
         int32_t* head = bridge + cap;
-        CRATAC_CUDA(cudaMemsetAsync(c->d_chain.p, 0, 8 * (size_t)std::max<int64_t>(n_tiles, 1), c->stream));
+        int32_t* tile_ns = c->d_chain.as<int32_t>();
+        int32_t* tile_ne = tile_ns + nt;
+        int64_t* tile_src_s = reinterpret_cast<int64_t*>(tile_ne + nt);
+        int64_t* tile_src_e = tile_src_s + nt;
+        int64_t* tile_dst_s = tile_src_e + nt;
+        int64_t* tile_dst_e = tile_dst_s + nt;
+        CRATAC_CUDA(cudaMemsetAsync(c->d_chain.p, 0, nt * 8, c->stream));   // tile_ns, tile_ne
         CRATAC_CUDA(cudaMemsetAsync(bridge, 0, 4 * (size_t)cap, c->stream));
         CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_RUNS], 0, sizeof(int64_t) * 3, c->stream));   // runs, fills, peaks
         CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
         PileupArgs a;
         fill_args(c, a);
-        a.chain = c->d_chain.as<unsigned long long>();
-        a.run_start = c->d_run_start.as<int64_t>(); a.run_end = c->d_run_end.as<int64_t>(); a.run_cap = cap;
+        int64_t* run_start = c->d_run_start.as<int64_t>();
+        int64_t* run_end = c->d_run_end.as<int64_t>();
+        a.evt_start = run_start + cap; a.evt_end = run_end + cap; a.cta_cap = cta_cap;
+        a.tile_ns = tile_ns; a.tile_ne = tile_ne; a.tile_src_s = tile_src_s; a.tile_src_e = tile_src_e;
         a.tile_summary = c->d_tile_summary.as<int4>(); a.fills = fills; a.fill_cap = fill_cap;
         c->stage_begin(SG_PILEUP_PEAKS);
         CRATAC_TRY(launch_pileup<MODE_PEAKS>(c, a));
         c->stage_end(SG_PILEUP_PEAKS);
         c->stage_begin(SG_MERGE_RUNS);
-        k_finish_runs<<<1, 32, 0, c->stream>>>(a.chain, n_tiles, st);
-        if (n_tiles > 0)
+        CRATAC_TRY(exclusive_scan_i32_to_i64(c, tile_ns, tile_dst_s, n_tiles, &st[ST_N_RUNS]));
+        CRATAC_TRY(exclusive_scan_i32_to_i64(c, tile_ne, tile_dst_e, n_tiles, &st[ST_TICKET2]));
+        k_finish_runs<<<1, 32, 0, c->stream>>>(st);
+        if (n_tiles > 0) {
+            unsigned gg = (unsigned)((n_tiles * 32 + 255) / 256);
+            k_gather_events<<<gg, 256, 0, c->stream>>>(a.evt_start, tile_ns, tile_src_s, tile_dst_s, n_tiles, cap, run_start, st);
+            k_gather_events<<<gg, 256, 0, c->stream>>>(a.evt_end, tile_ne, tile_src_e, tile_dst_e, n_tiles, cap, run_end, st);
             k_cross_tile_gaps<<<(unsigned)((n_tiles + 127) / 128), 128, 0, c->stream>>>(a.tile_summary, a.tile_off, a.contig_base, c->n_contigs, n_tiles, st,
                                                                                        fills, fill_cap);
-        k_mark_bridges<<<32, 128, 0, c->stream>>>(fills, a.run_end, a.run_start, st, bridge, fill_cap);
-        k_run_heads<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(a.run_start, a.run_end, bridge, st, cap, head);
-        c->launches += 4;
+            c->launches += 3;
+        }
+        k_mark_bridges<<<32, 128, 0, c->stream>>>(fills, run_end, run_start, st, bridge, fill_cap);
+        k_run_heads<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(run_start, run_end, bridge, st, cap, head);
+        c->launches += 3;
         CRATAC_CUDA(cudaGetLastError());
         CRATAC_TRY(exclusive_scan_i32_to_i64(c, head, head_rank, cap, nullptr));
         k_zero_peaks_if_no_runs<<<1, 32, 0, c->stream>>>(st);
-        k_emit_peaks<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(a.run_start, a.run_end, head, head_rank, a.contig_base, c->n_contigs, st, cap,
+        k_emit_peaks<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(run_start, run_end, head, head_rank, a.contig_base, c->n_contigs, st, cap,
                                                                            c->d_peak_chrom.as<int32_t>(), c->d_peak_start.as<int32_t>(),
                                                                            c->d_peak_end.as<int32_t>(), c->d_peak_row.as<int32_t>());
         k_peak_offsets<<<(c->n_contigs + 1 + 127) / 128, 128, 0, c->stream>>>(c->d_peak_chrom.as<int32_t>(), st, c->n_contigs, c->d_peak_off.as<int64_t>());

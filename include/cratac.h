@@ -68,6 +68,10 @@ int cratac_stream(cratac_ctx* ctx, uint64_t* stream_out);
 int cratac_num_stages(void);
 const char* cratac_stage_name(int id);
 int cratac_stage_times(cratac_ctx* ctx, float* ms_out);
+/* host wall-clock phases of the last cratac_run as "name=ms;..." (profiling aid) */
+int cratac_host_times(cratac_ctx* ctx, char* out, int64_t cap);
+/* SM cycles per phase of the last threshold fit, 9 doubles (profiling aid) */
+int cratac_em_debug(cratac_ctx* ctx, double* out);
 
 /* ---- (1) fragment decode: replaces lib/python/tools/io.py:75-79 (open_fragment_file) and
  *      :82-92 (parsed_fragments_from_contig).  `text` is the DECOMPRESSED fragments.tsv

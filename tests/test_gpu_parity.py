@@ -139,6 +139,22 @@ def test_em_golden(case):
     ctx.close()
 
 
+def test_em_accelerated_fixed_point_matches_plain_iteration():
+    """The interpolated / doubled dispersion fixed point must stop at the same iterate as the plain loop."""
+    ctx = _ffi.Context([("chr1", 1000)])
+    for case in EM_CASES:
+        if case.get("raises") or case["params"] is None:
+            continue
+        ctx.set_option("em_fast", 0)
+        thr0, p0, st0 = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
+        ctx.set_option("em_fast", 1)
+        thr1, p1, st1 = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
+        assert thr0 == thr1 == case["threshold"]
+        assert st0 == st1, (case["name"], st0, st1)
+        assert np.allclose(np.array(p0), np.array(p1), rtol=1e-9, atol=0), (case["name"], p0, p1)
+    ctx.close()
+
+
 def test_em_random_histograms_vs_oracle():
     ctx = _ffi.Context([("chr1", 1000)])
     rng = np.random.default_rng(42)
