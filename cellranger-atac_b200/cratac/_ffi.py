@@ -164,9 +164,9 @@ class Context(object):
         return {self._lib.cratac_stage_name(i).decode(): float(ms[i]) for i in range(n) if ms[i] >= 0}
 
     def em_debug(self):
-        out = (c_dbl * 9)()
+        out = (c_dbl * 11)()
         check(self._lib.cratac_em_debug(self._h, out))
-        names = ["e_step", "m_sums", "suffix", "bracket", "nodes", "verify", "doubling", "descent", "direct"]
+        names = ["e_step", "m_sums", "suffix", "bracket", "nodes", "verify_or_xc", "doubling", "descent", "direct", "ncoef0_sum", "levels_sum"]
         return {k: float(v) for k, v in zip(names, out)}
 
     def host_times(self):

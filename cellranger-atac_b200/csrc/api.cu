@@ -143,13 +143,17 @@ void cratac_destroy(cratac_ctx* h) {
     DevBuf* bufs[] = {&c->d_contig_lens, &c->d_contig_base, &c->d_contig_tile_off, &c->d_contig_pidx_off, &c->d_contig_table, &c->d_chrom,
                       &c->d_start, &c->d_end, &c->d_bc, &c->d_dup, &c->d_contig_frag_off, &c->d_pos_index, &c->d_text_own, &c->d_tile_counts,
                       &c->d_tile_offsets, &c->d_bc_keys, &c->d_bc_first, &c->d_bc_textoff, &c->d_slot_to_dense, &c->d_dense_key, &c->d_dense_first,
-                      &c->d_dense_textoff, &c->d_dense_to_col, &c->d_col_to_dense, &c->d_hist, &c->d_hist_values, &c->d_hist_weights,
+                      &c->d_dense_textoff, &c->d_dense_to_col, &c->d_col_to_dense, &c->d_bc_bitmap, &c->d_hist, &c->d_hist_values, &c->d_hist_weights,
                       &c->d_em_params, &c->d_em_work, &c->d_chain, &c->d_tile_summary, &c->d_run_start, &c->d_run_end, &c->d_bridge, &c->d_fill,
                       &c->d_peak_chrom, &c->d_peak_start, &c->d_peak_end, &c->d_peak_row, &c->d_peak_off, &c->d_bc_hits, &c->d_seg_off,
                       &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
                       &c->d_status, &c->d_scan_tmp};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_bc_hash) cudaFreeHost(c->h_bc_hash);
+    if (c->h_bc_order) cudaFreeHost(c->h_bc_order);
+    if (c->h_c2d_pin) cudaFreeHost(c->h_c2d_pin);
+    if (c->bc_event) cudaEventDestroy(c->bc_event);
     cudaStreamDestroy(c->stream);
     delete h;
 }
@@ -157,7 +161,11 @@ void cratac_destroy(cratac_ctx* h) {
 int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!h || !key) return CRATAC_ERR_ARG;
     Ctx* c = &h->c;
-    if (!strcmp(key, "barcode_order")) { c->bc_order = (int)value; c->bc_ready = c->bc_ready && !c->bc_is_slot; return CRATAC_OK; }
+    if (!strcmp(key, "barcode_order")) {
+        c->bc_order = (int)value;
+        if (c->bc_is_slot) { c->bc_ready = false; c->bc_strings_ready = false; }
+        return CRATAC_OK;
+    }
     if (!strcmp(key, "barcode_table_slots")) {
         int64_t cap = 16;
         while (cap < value) cap <<= 1;
@@ -165,7 +173,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
         return CRATAC_OK;
     }
     if (!strcmp(key, "run_capacity")) { c->run_cap = value; return CRATAC_OK; }
-    if (!strcmp(key, "em_fast")) { c->em_fast = value != 0; return CRATAC_OK; }
+    if (!strcmp(key, "em_fast")) { c->em_fast = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
         c->profile = value != 0;
@@ -265,6 +273,8 @@ int cratac_set_fragments(cratac_ctx* h, int64_t n, const int32_t* chrom, const i
     CRATAC_CUDA(cudaMemcpyAsync(c->d_dense_to_col.p, ident.data(), 4 * nb, cudaMemcpyHostToDevice, c->stream));
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     c->bc_ready = true;
+    c->bc_strings_ready = true;
+    c->h_c2d.assign(ident.begin(), ident.begin() + n_barcodes);
     CRATAC_TRY(compute_max_len(c));
     return finalize_fragments(c);
 }
@@ -302,7 +312,7 @@ int cratac_get_fragments(cratac_ctx* h, int32_t* chrom, int32_t* start, int32_t*
 int cratac_max_barcode_len(cratac_ctx* h, int64_t* len) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
-    CRATAC_TRY(build_barcodes(c));
+    CRATAC_TRY(build_barcode_strings(c));
     size_t m = 0;
     for (const std::string& s : c->barcodes) m = std::max(m, s.size());
     *len = (int64_t)m;
@@ -312,7 +322,7 @@ int cratac_max_barcode_len(cratac_ctx* h, int64_t* len) {
 int cratac_get_barcodes(cratac_ctx* h, char* out, int64_t stride) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
-    CRATAC_TRY(build_barcodes(c));
+    CRATAC_TRY(build_barcode_strings(c));
     for (size_t j = 0; j < c->barcodes.size(); j++) {
         if ((int64_t)c->barcodes[j].size() + 1 > stride) { set_error("barcode stride %lld too small", (long long)stride); return CRATAC_ERR_ARG; }
         memset(out + j * stride, 0, (size_t)stride);
@@ -584,7 +594,7 @@ int cratac_run(cratac_ctx* h, const char* text, int64_t nbytes, int text_is_devi
 int cratac_em_debug(cratac_ctx* h, double* out) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
-    CRATAC_CUDA(cudaMemcpyAsync(out, c->d_em_params.as<double>() + 8, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(out, c->d_em_params.as<double>() + 8, 11 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     return CRATAC_OK;
 }

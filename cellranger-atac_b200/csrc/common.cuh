@@ -59,6 +59,7 @@ enum StatusSlot {
     ST_TICKET = 17,
     ST_TICKET2 = 18,
     ST_EM_DIRECT = 19,   // direct evaluations of the dispersion fixed-point map
+    ST_EM_MODE = 20,     // 0 = fit pending, 1 = left to the generic kernel, 2 = done by the register-resident kernel
     ST_SLOTS = 24
 };
 
@@ -105,7 +106,14 @@ struct Ctx {
     int bc_table_cap = 0;                  // slots (power of two)
     DevBuf d_bc_keys, d_bc_first, d_bc_textoff, d_slot_to_dense;
     int64_t n_barcodes = 0;
-    DevBuf d_dense_key, d_dense_first, d_dense_textoff, d_dense_to_col, d_col_to_dense;
+    DevBuf d_dense_key, d_dense_first, d_dense_textoff, d_dense_to_col, d_col_to_dense, d_bc_bitmap;
+    long long* h_bc_hash = nullptr;        // pinned: py2 hashes in first-appearance order
+    int32_t* h_bc_order = nullptr;         // pinned: dense id of the k-th barcode to appear
+    int32_t* h_c2d_pin = nullptr;          // pinned: column -> dense id
+    size_t h_bc_cap = 0;
+    cudaEvent_t bc_event = nullptr;
+    std::vector<int32_t> h_c2d;
+    bool bc_strings_ready = false;
     std::vector<std::string> barcodes;     // matrix column order
     int bc_order = CRATAC_BC_ORDER_PY2SET;
     bool bc_ready = false;
@@ -134,7 +142,7 @@ struct Ctx {
     DevBuf d_scan_tmp;
     int64_t* h_status = nullptr;           // pinned mirror
     int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
-    bool em_fast = true;                   // accelerated dispersion fixed point (em.cu)
+    int em_fast = 2;                       // 0 plain fixed point, 1 accelerated (em.cu), 2 register-resident kernel first (em_fast.cu)
     bool profile = false;
     cudaEvent_t ev[2 * SG_COUNT] = {};
     bool ev_used[SG_COUNT] = {};
@@ -175,7 +183,8 @@ int exclusive_scan_i32_to_i64(Ctx* c, const int32_t* d_in, int64_t* d_out, int64
 // ---------------------------------------------------------------- stage entry points (host side)
 int decode_text(Ctx* c, const char* d_text, int64_t nbytes);          // decode.cu
 int finalize_fragments(Ctx* c);                                       // decode.cu: contig offsets, pos index, checks
-int build_barcodes(Ctx* c);                                           // decode.cu: dense ids, column order, strings
+int build_barcodes(Ctx* c);                                           // decode.cu: matrix column order (host half)
+int build_barcode_strings(Ctx* c);                                    // decode.cu: barcode strings in column order (lazy)
 int window_histogram(Ctx* c);                                         // pileup.cu: K2+K3 fused
 int call_peaks_device(Ctx* c);                                        // pileup.cu: K5 (threshold from d_status)
 int fit_threshold_device(Ctx* c, double odds_ratio);                  // em.cu: K4 on compact histogram

@@ -408,6 +408,50 @@ __global__ void k_gather_barcode_text(const char* __restrict__ text, const long 
     for (int i = 0; i < stride; i++) o[i] = (i < len) ? text[off + i] : 0;
 }
 
+// CPython-2.7 string_hash of every barcode (Objects/stringobject.c), straight from the text
+__global__ void k_barcode_py2hash(const char* __restrict__ text, const long long* __restrict__ dense_textoff, int64_t n, long long* __restrict__ out) {
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    long long packed = dense_textoff[d];
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(text) + (packed >> 8);
+    int len = (int)(packed & 255);
+    unsigned long long x = 0;
+    if (len > 0) {
+        x = (unsigned long long)p[0] << 7;
+        for (int i = 0; i < len; i++) x = (1000003ULL * x) ^ (unsigned long long)p[i];
+        x ^= (unsigned long long)len;
+        if (x == 0xFFFFFFFFFFFFFFFFULL) x = 0xFFFFFFFFFFFFFFFEULL;
+    }
+    out[d] = (long long)x;
+}
+
+// first-appearance rank without a sort: the first lines of the barcodes are distinct fragment indices, so a
+// bitmap over the fragments + a prefix popcount ranks them.
+__global__ void k_mark_first(const unsigned long long* __restrict__ dense_first, int64_t n, unsigned int* __restrict__ bitmap) {
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    unsigned long long f = dense_first[d];
+    atomicOr(&bitmap[f >> 5], 1u << (f & 31));
+}
+__global__ void k_popc_words(const unsigned int* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ cnt) {
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n_words) cnt[w] = __popc(bitmap[w]);
+}
+__global__ void k_rank_first(const unsigned long long* __restrict__ dense_first, const long long* __restrict__ dense_hash, int64_t n,
+                             const unsigned int* __restrict__ bitmap, const int64_t* __restrict__ word_prefix,
+                             int32_t* __restrict__ order_f, long long* __restrict__ hash_f) {
+    int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    unsigned long long f = dense_first[d];
+    int64_t r = word_prefix[f >> 5] + __popc(bitmap[f >> 5] & ((1u << (f & 31)) - 1u));
+    order_f[r] = (int32_t)d;           // the r-th barcode to appear in the file is dense id d
+    hash_f[r] = dense_hash[d];
+}
+__global__ void k_invert_order(const int32_t* __restrict__ col_to_dense, int64_t n, int32_t* __restrict__ dense_to_col) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dense_to_col[col_to_dense[j]] = (int32_t)j;
+}
+
 // ------------------------------------------------------------------ host side
 static int build_contig_table(Ctx* c) {
     int cap = 16;
@@ -431,12 +475,23 @@ static int build_contig_table(Ctx* c) {
     return CRATAC_OK;
 }
 
-// device half of the barcode dictionary: hash-table slots -> dense ids (slot_to_dense), needed by the
-// overlap kernels; queued right after the parse kernel.
-static int compact_barcode_table(Ctx* c) {
+// device half of the barcode dictionary, queued right after the parse kernel: hash-table slots -> dense ids
+// (slot_to_dense, needed by the overlap kernels), CPython-2.7 hashes, first-appearance order; the small
+// results travel to pinned host memory asynchronously and an event marks their arrival.
+static int barcode_prepare_device(Ctx* c) {
     int64_t* st = c->d_status.as<int64_t>();
-    size_t nn = (size_t)std::max<int64_t>(c->n_barcodes, 1);
+    const int64_t nb = c->n_barcodes, n = c->n_fragments;
+    size_t nn = (size_t)std::max<int64_t>(nb, 1);
     CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
+    CRATAC_TRY(c->d_dense_key.reserve(8 * nn));                 // py2 hashes by dense id
+    CRATAC_TRY(c->d_dense_to_col.reserve(4 * nn)); CRATAC_TRY(c->d_col_to_dense.reserve(4 * nn));
+    const int64_t n_words = (n + 31) / 32 + 1;
+    CRATAC_TRY(c->d_bc_bitmap.reserve(16 * (size_t)n_words + 12 * nn + 64));
+    unsigned int* bitmap = c->d_bc_bitmap.as<unsigned int>();
+    int32_t* word_cnt = reinterpret_cast<int32_t*>(bitmap + n_words);
+    int64_t* word_prefix = reinterpret_cast<int64_t*>(word_cnt + n_words);   // 2 * n_words int32 => 8-byte aligned
+    long long* hash_f = reinterpret_cast<long long*>(word_prefix + n_words);
+    int32_t* order_f = reinterpret_cast<int32_t*>(hash_f + nn);
     cudaStream_t s = c->stream;
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
     c->stage_begin(SG_BARCODE_TABLE);
@@ -444,9 +499,42 @@ static int compact_barcode_table(Ctx* c) {
                                                                c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
                                                                c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
                                                                reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
-    c->stage_end(SG_BARCODE_TABLE);
     c->launches++;
+    if (nb > 0) {
+        unsigned g = (unsigned)((nb + 255) / 256);
+        k_barcode_py2hash<<<g, 256, 0, s>>>(c->d_text, c->d_dense_textoff.as<long long>(), nb, c->d_dense_key.as<long long>());
+        CRATAC_CUDA(cudaMemsetAsync(bitmap, 0, 4 * (size_t)n_words, s));
+        k_mark_first<<<g, 256, 0, s>>>(c->d_dense_first.as<unsigned long long>(), nb, bitmap);
+        k_popc_words<<<(unsigned)((n_words + 255) / 256), 256, 0, s>>>(bitmap, n_words, word_cnt);
+        c->launches += 3;
+        CRATAC_CUDA(cudaGetLastError());
+        CRATAC_TRY(exclusive_scan_i32_to_i64(c, word_cnt, word_prefix, n_words, nullptr));
+        k_rank_first<<<g, 256, 0, s>>>(c->d_dense_first.as<unsigned long long>(), c->d_dense_key.as<long long>(), nb, bitmap, word_prefix, order_f, hash_f);
+        c->launches++;
+    }
+    c->stage_end(SG_BARCODE_TABLE);
     CRATAC_CUDA(cudaGetLastError());
+    // pinned host mirrors
+    if (c->h_bc_cap < nn) {
+        if (c->h_bc_hash) cudaFreeHost(c->h_bc_hash);
+        if (c->h_bc_order) cudaFreeHost(c->h_bc_order);
+        if (c->h_c2d_pin) cudaFreeHost(c->h_c2d_pin);
+        size_t cap = nn + nn / 2 + 1024;
+        if (cudaMallocHost(&c->h_bc_hash, 8 * cap) != cudaSuccess || cudaMallocHost(&c->h_bc_order, 4 * cap) != cudaSuccess ||
+            cudaMallocHost(&c->h_c2d_pin, 4 * cap) != cudaSuccess) {
+            set_error("cudaMallocHost failed for the barcode mirrors");
+            return CRATAC_ERR_CUDA;
+        }
+        c->h_bc_cap = cap;
+    }
+    if (nb > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(c->h_bc_hash, hash_f, 8 * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        CRATAC_CUDA(cudaMemcpyAsync(c->h_bc_order, order_f, 4 * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    }
+    if (!c->bc_event) CRATAC_CUDA(cudaEventCreateWithFlags(&c->bc_event, cudaEventDisableTiming));
+    CRATAC_CUDA(cudaEventRecord(c->bc_event, s));
+    c->bc_ready = false;
+    c->bc_strings_ready = false;
     return CRATAC_OK;
 }
 
@@ -526,8 +614,8 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         c->n_barcodes = nb;
         break;
     }
-    CRATAC_TRY(compact_barcode_table(c));
-    return finalize_fragments(c);
+    CRATAC_TRY(finalize_fragments(c));
+    return barcode_prepare_device(c);
 }
 
 int finalize_fragments(Ctx* c) {
@@ -567,113 +655,125 @@ int compute_max_len(Ctx* c) {
 }
 
 // ---- CPython 2.7 string hash / set order (see cratac_py2_set_order in api.cu)
-static inline int64_t py2_hash(const std::string& s) {
-    if (s.empty()) return 0;
-    uint64_t x = (uint64_t)(unsigned char)s[0] << 7;
-    for (unsigned char ch : s) x = (1000003ULL * x) ^ ch;
-    x ^= (uint64_t)s.size();
-    int64_t h = (int64_t)x;
-    return h == -1 ? -2 : h;
-}
-
-void py2_set_order(const std::vector<std::string>& keys, std::vector<int64_t>& order) {
-    struct Ent { int64_t idx; int64_t hash; };
-    std::vector<Ent> table(8, Ent{-1, 0});
+// CPython 2.7 set of distinct str keys given by their hashes in insertion order; returns the insertion index
+// of the key in every occupied slot, in slot order = list(set) order.  Distinct keys never compare equal, so the
+// probe sequence depends on the hashes only (Objects/setobject.c: set_lookkey_string, set_insert_clean,
+// set_add_key, set_table_resize; PySet_MINSIZE 8, PERTURB_SHIFT 5).
+void py2_set_order_hashes(const long long* hashes, int64_t n, std::vector<int32_t>& order) {
+    std::vector<int32_t> table(8, -1);
     uint64_t mask = 7, used = 0, fill = 0;
-    auto insert_clean = [&](std::vector<Ent>& tab, uint64_t m, Ent e) {
-        uint64_t i = (uint64_t)e.hash & m, perturb = (uint64_t)e.hash;
-        while (tab[i & m].idx >= 0) { i = i * 5 + perturb + 1; perturb >>= 5; }
-        tab[i & m] = e;
-    };
-    for (int64_t k = 0; k < (int64_t)keys.size(); k++) {
-        int64_t h = py2_hash(keys[k]);
-        uint64_t i = (uint64_t)h & mask, perturb = (uint64_t)h;
-        bool found = false;
-        while (true) {
-            Ent& e = table[i & mask];
-            if (e.idx < 0) break;
-            if (e.hash == h && keys[e.idx] == keys[k]) { found = true; break; }
-            i = i * 5 + perturb + 1; perturb >>= 5;
-        }
-        if (found) continue;
-        table[i & mask] = Ent{k, h};
+    for (int64_t k = 0; k < n; k++) {
+        uint64_t h = (uint64_t)hashes[k];
+        uint64_t i = h & mask, perturb = h;
+        while (table[i & mask] >= 0) { i = i * 5 + perturb + 1; perturb >>= 5; }
+        table[i & mask] = (int32_t)k;
         used++; fill++;
         if (fill * 3 >= (mask + 1) * 2) {
             uint64_t minused = used > 50000 ? used * 2 : used * 4, newsize = 8;
             while (newsize <= minused) newsize <<= 1;
-            std::vector<Ent> nt(newsize, Ent{-1, 0});
-            for (const Ent& e : table) if (e.idx >= 0) insert_clean(nt, newsize - 1, e);
+            std::vector<int32_t> nt(newsize, -1);
+            const uint64_t m2 = newsize - 1;
+            for (int32_t e : table) {
+                if (e < 0) continue;
+                uint64_t hh = (uint64_t)hashes[e], q = hh & m2, pp = hh;
+                while (nt[q & m2] >= 0) { q = q * 5 + pp + 1; pp >>= 5; }
+                nt[q & m2] = e;
+            }
             table.swap(nt);
-            mask = newsize - 1;
+            mask = m2;
             fill = used;
         }
     }
     order.clear();
-    for (const Ent& e : table) if (e.idx >= 0) order.push_back(e.idx);
+    order.reserve((size_t)n);
+    for (int32_t e : table) if (e >= 0) order.push_back(e);
 }
 
-// dense ids, barcode strings and the matrix column order.  Host work (sort by first line, the
-// py2 set emulation) overlaps whatever the caller queued on the stream before calling this.
-int build_barcodes(Ctx* c) {
-    if (c->bc_ready) return CRATAC_OK;
-    int64_t* st = c->d_status.as<int64_t>();
-    int64_t nb = c->n_barcodes;
+static inline long long py2_hash(const std::string& s) {
+    if (s.empty()) return 0;
+    uint64_t x = (uint64_t)(unsigned char)s[0] << 7;
+    for (unsigned char ch : s) x = (1000003ULL * x) ^ ch;
+    x ^= (uint64_t)s.size();
+    long long h = (long long)x;
+    return h == -1 ? -2 : h;
+}
+
+// string front end (cratac_py2_set_order): equal strings collapse first, then the hash-only simulation applies
+void py2_set_order(const std::vector<std::string>& keys, std::vector<int64_t>& order) {
+    std::vector<long long> h(keys.size());
+    for (size_t k = 0; k < keys.size(); k++) h[k] = py2_hash(keys[k]);
+    std::vector<int32_t> o;
+    py2_set_order_hashes(h.data(), (int64_t)keys.size(), o);
+    order.assign(o.begin(), o.end());
+}
+
+static int fetch_barcode_strings(Ctx* c, std::vector<std::string>& names) {
+    const int64_t nb = c->n_barcodes;
     size_t nn = (size_t)std::max<int64_t>(nb, 1);
-    CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
-    CRATAC_TRY(c->d_dense_to_col.reserve(4 * nn)); CRATAC_TRY(c->d_col_to_dense.reserve(4 * nn));
-    cudaStream_t s = c->stream;
     const int stride = 64;
     DevBuf d_txt;
     CRATAC_TRY(d_txt.reserve(nn * stride));
     std::vector<long long> textoff(nn);
-    std::vector<unsigned long long> first(nn);
+    std::vector<char> txt(nn * stride);
+    cudaStream_t s = c->stream;
     if (nb > 0) {
-        // max barcode length check happens on the packed lengths
         k_gather_barcode_text<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(c->d_text, c->d_dense_textoff.as<long long>(), nb, stride, d_txt.as<char>());
         c->launches++;
         CRATAC_CUDA(cudaGetLastError());
     }
-    std::vector<char> txt(nn * stride);
     CRATAC_CUDA(cudaMemcpyAsync(txt.data(), d_txt.p, nn * stride, cudaMemcpyDeviceToHost, s));
-    CRATAC_CUDA(cudaMemcpyAsync(first.data(), c->d_dense_first.p, 8 * nn, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaMemcpyAsync(textoff.data(), c->d_dense_textoff.p, 8 * nn, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
     d_txt.release();
-    std::vector<std::string> names((size_t)nb);
+    names.resize((size_t)nb);
     for (int64_t d = 0; d < nb; d++) {
         int len = (int)(textoff[d] & 255);
         if (len >= stride) { set_error("barcode longer than %d bytes", stride - 1); return CRATAC_ERR_PARSE; }
         names[d].assign(txt.data() + d * stride, (size_t)len);
     }
-    // first-appearance order
-    std::vector<int64_t> by_first((size_t)nb);
-    for (int64_t d = 0; d < nb; d++) by_first[d] = d;
-    std::sort(by_first.begin(), by_first.end(), [&](int64_t x, int64_t y) { return first[x] < first[y]; });
-    std::vector<int64_t> col_to_dense((size_t)nb);
+    return CRATAC_OK;
+}
+
+// host half: matrix column order.  Only the hashes (PY2SET) or nothing (FIRST_SEEN) cross to the host; the
+// caller queues GPU work first so that this overlaps it.
+int build_barcodes(Ctx* c) {
+    if (c->bc_ready) return CRATAC_OK;
+    const int64_t nb = c->n_barcodes;
+    cudaStream_t s = c->stream;
+    CRATAC_CUDA(cudaEventSynchronize(c->bc_event));
+    int32_t* c2d = c->h_c2d_pin;    // pinned: the upload below does not wait for the stream
     if (c->bc_order == CRATAC_BC_ORDER_FIRST_SEEN) {
-        col_to_dense = by_first;
+        for (int64_t j = 0; j < nb; j++) c2d[j] = c->h_bc_order[j];
     } else if (c->bc_order == CRATAC_BC_ORDER_SORTED) {
-        col_to_dense = by_first;
-        std::sort(col_to_dense.begin(), col_to_dense.end(), [&](int64_t x, int64_t y) { return names[x] < names[y]; });
+        std::vector<std::string> names;
+        CRATAC_TRY(fetch_barcode_strings(c, names));
+        for (int64_t j = 0; j < nb; j++) c2d[j] = (int32_t)j;
+        std::sort(c2d, c2d + nb, [&](int32_t x, int32_t y) { return names[x] < names[y]; });
     } else {
-        std::vector<std::string> ins((size_t)nb);
-        for (int64_t k = 0; k < nb; k++) ins[k] = names[by_first[k]];
-        std::vector<int64_t> order;
-        py2_set_order(ins, order);
-        if ((int64_t)order.size() != nb) { set_error("duplicate barcode strings in dictionary"); return CRATAC_ERR_INTERNAL; }
-        for (int64_t j = 0; j < nb; j++) col_to_dense[j] = by_first[order[j]];
+        std::vector<int32_t> order;
+        py2_set_order_hashes(c->h_bc_hash, nb, order);
+        for (int64_t j = 0; j < nb; j++) c2d[j] = c->h_bc_order[order[j]];
     }
-    std::vector<int32_t> c2d((size_t)nn), d2c((size_t)nn);
-    c->barcodes.resize((size_t)nb);
-    for (int64_t j = 0; j < nb; j++) {
-        c2d[j] = (int32_t)col_to_dense[j];
-        d2c[col_to_dense[j]] = (int32_t)j;
-        c->barcodes[j] = names[col_to_dense[j]];
+    c->h_c2d.assign(c2d, c2d + nb);
+    if (nb > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_col_to_dense.p, c2d, 4 * (size_t)nb, cudaMemcpyHostToDevice, s));
+        k_invert_order<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(c->d_col_to_dense.as<int32_t>(), nb, c->d_dense_to_col.as<int32_t>());
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
     }
-    CRATAC_CUDA(cudaMemcpyAsync(c->d_col_to_dense.p, c2d.data(), 4 * nn, cudaMemcpyHostToDevice, s));
-    CRATAC_CUDA(cudaMemcpyAsync(c->d_dense_to_col.p, d2c.data(), 4 * nn, cudaMemcpyHostToDevice, s));
-    CRATAC_CUDA(cudaStreamSynchronize(s));
     c->bc_ready = true;
+    return CRATAC_OK;
+}
+
+// barcode strings in column order (lazy: only the getters need them)
+int build_barcode_strings(Ctx* c) {
+    CRATAC_TRY(build_barcodes(c));
+    if (c->bc_strings_ready) return CRATAC_OK;
+    std::vector<std::string> names;
+    CRATAC_TRY(fetch_barcode_strings(c, names));
+    c->barcodes.resize((size_t)c->n_barcodes);
+    for (int64_t j = 0; j < c->n_barcodes; j++) c->barcodes[j] = names[c->h_c2d[j]];
+    c->bc_strings_ready = true;
     return CRATAC_OK;
 }
 

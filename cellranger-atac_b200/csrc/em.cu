@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
     __shared__ int s_int;
     __shared__ FixedPointSmem fps;
     const int tid = threadIdx.x;
+    if (a.status[ST_EM_MODE] == 2) return;   // the register-resident kernel (em_fast.cu) already did the fit
     int64_t n64 = a.n_bins_host >= 0 ? a.n_bins_host : a.status[ST_N_BINS];
     const int n = (int)n64;
     long long iters = 0, inner = 0, direct = 0;
@@ -525,6 +526,8 @@ __global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
     }
 }
 
+int em_fast_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio);   // em_fast.cu
+
 static int em_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio) {
     const int64_t work_n = 1 << 16, work_v = HIST_CAP + 2;
     size_t doubles = (size_t)work_n * 6 + 2 + (size_t)work_v + 64 * 64;
@@ -538,9 +541,12 @@ static int em_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, 
     a.Q = w; w += work_n + 2; a.T = w; w += work_v;
     a.costab = w; w += 64 * 64;
     a.fast_fixed_point = c->em_fast ? 1 : 0;
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_EM_MODE], 0, sizeof(int64_t), c->stream));
     a.first_gt = reinterpret_cast<int*>(w);
     a.work_n = work_n; a.work_v = work_v;
     c->stage_begin(SG_EM_FIT);
+    if (c->em_fast >= 2) CRATAC_TRY(em_fast_launch(c, d_values, d_weights, n_bins_host, odds_ratio));
     k_em_fit<<<1, EM_THREADS, 0, c->stream>>>(a);
     c->stage_end(SG_EM_FIT);
     c->launches++;

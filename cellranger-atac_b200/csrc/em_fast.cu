@@ -1,0 +1,675 @@
+// K4, register-resident variant: the same fit as em.cu (peaks.py:28-193, em_fitting.py:10-87) for the
+// common case of <= 2048 histogram bins and window counts <= 8192.  One CTA of 512 threads (128 registers
+// each); every thread owns up to 4 bins (value, weight, responsibilities) in registers for the whole fit, the tail-weight
+// table T(j), the Chebyshev cosine table and the series coefficients live in shared memory, so an EM
+// iteration touches HBM not at all.  The dispersion fixed point uses the interpolate / compose / descend
+// scheme described in em.cu, restructured so that every step uses the whole CTA:
+//   * G at 64 candidates (bracket) or 128 points (64 nodes + 64 check points) per pass
+//   * Chebyshev fits and the first half of each composition as 1024-thread mat-vecs with the cosine table
+//   * the stopping point x_c (where the step size crosses 1e-6) located once by 3 rounds of 1024-way
+//     sectioning on the level-0 series; the descent then needs one series evaluation per level
+//   * the last iterations and the stopping test evaluated directly, exactly as the reference does.
+// Histograms outside the limits, or any failed safety check, are left to k_em_fit (em.cu).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cratac {
+
+constexpr int EF_THREADS = 512;
+constexpr int EF_WARPS = EF_THREADS / 32;
+constexpr int EF_BPT = 4;
+constexpr int EF_MAXN = EF_THREADS * EF_BPT;
+constexpr int EF_MAXV = 8192;
+constexpr int CM = 64;          // Chebyshev nodes
+constexpr int CS = 65;          // row stride of the cosine table (odd => both access patterns are bank-conflict free)
+constexpr int CL = 14;          // composition levels (2^13 = 8192 < 10000 iterations)
+constexpr double EF_PI = 3.14159265358979323846;
+
+struct EfArgs {
+    const int64_t* values;
+    const int64_t* weights;
+    int64_t n_bins_host;
+    int64_t* status;
+    double* params_out;
+    double odds_ratio;
+};
+
+struct EfSmem {
+    double costab[CM * CS];     // cos(k * theta_i) at [k * CS + i]
+    double T[EF_MAXV];
+    double red[EF_WARPS * 8];
+    double pts[2 * CM];
+    double val[2 * CM];
+    double coef[CL][CM];
+    double wtot[EF_WARPS];
+    double bcast[4];
+    int ncoef[CL];
+    int flag;
+    int ibc;
+    long long cyc[12];
+};
+
+enum { EP_ESTEP = 0, EP_MSUMS, EP_TFILL, EP_BRACKET, EP_NODES, EP_XC, EP_DOUBLING, EP_DESCENT, EP_DIRECT, EP_NCOEF, EP_LEVELS, EP_COUNT };
+#define EP_BEGIN() long long _ep_t0 = clock64()
+#define EP_END(s, ph) do { long long _t = clock64(); if (threadIdx.x == 0) (s).cyc[ph] += _t - _ep_t0; _ep_t0 = _t; } while (0)
+
+struct Th { double p_zero, mean_bg, alpha_bg, p_signal, f_zero, f_bg; };
+
+template <int K>
+__device__ __forceinline__ void ef_block_sum(double (&x)[K], double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) x[j] += __shfl_xor_sync(0xffffffffu, x[j], d);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < K; j++) red[warp * K + j] = x[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        double v = lane < EF_WARPS ? red[lane * K + j] : 0.0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        x[j] = v;
+    }
+}
+
+__device__ __forceinline__ double ef_block_max(double x, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, d));
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    double v = red[lane < EF_WARPS ? lane : 0];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+__device__ __forceinline__ double ef_clenshaw(const double* c, int nc, double t) {
+    t = fmin(1.0, fmax(-1.0, t));
+    double b1 = 0.0, b2 = 0.0;
+    const double t2 = 2.0 * t;
+#pragma unroll 4
+    for (int k = nc - 1; k > 0; k--) {
+        double b0 = fma(t2, b1, c[k] - b2);
+        b2 = b1; b1 = b0;
+    }
+    return fma(t, b1, c[0] - b2);
+}
+
+// aj / (1 + aj) = 1 - 1 / (1 + aj) with the reciprocal from a single-precision seed and two Newton steps
+// (full double accuracy to ~1 ulp at a third of the cost of an IEEE division; 1 + aj >= 1 so no range issues)
+__device__ __forceinline__ double ef_frac(double aj) {
+    const double y = 1.0 + aj;
+    double r = (double)__frcp_rn((float)y);
+    r = r * fma(-y, r, 2.0);
+    r = r * fma(-y, r, 2.0);
+    r = fma(r, fma(-y, r, 1.0), r);     // final correction step
+    return 1.0 - r;
+}
+
+// G(alpha) (em_fitting.py:41-56 with the sums swapped) at NP points held in s.pts, EF_THREADS / NP threads per point
+template <int NP>
+__device__ __forceinline__ void ef_eval_points(EfSmem& s, int jmax, double mu, double N1, int n_active = NP) {
+    constexpr int TPP = EF_THREADS / NP;
+    const int grp = threadIdx.x / TPP, sub = threadIdx.x % TPP;
+    const double alpha = s.pts[grp < n_active ? grp : 0];
+    double p0 = 0.0, p1 = 0.0;
+    int j = grp < n_active ? 1 + sub : jmax;
+    for (; j + TPP < jmax; j += 2 * TPP) {
+        double a0 = alpha * (double)j, a1 = alpha * (double)(j + TPP);
+        p0 = fma(ef_frac(a0), s.T[j], p0);
+        p1 = fma(ef_frac(a1), s.T[j + TPP], p1);
+    }
+    if (j < jmax) { double a0 = alpha * (double)j; p0 = fma(ef_frac(a0), s.T[j], p0); }
+    double part = p0 + p1;
+#pragma unroll
+    for (int d = TPP / 2; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (sub == 0 && grp < n_active) s.val[grp] = log(1.0 + alpha * mu) / (mu - part / N1);
+    __syncthreads();
+}
+
+// sum_k c[k] T_k(t) evaluated by a group of G lanes (G = 8, 16 or 32): lane s owns the terms s, s+G, s+2G, ...
+// T_0..T_G come from the forward recurrence (each lane keeps T_s and T_{G-s} as they pass); the terms further
+// up follow from T_{k+G} = 2 T_G T_k - T_{|k-G|}.  No trigonometric functions; every lane returns the sum.
+template <int G>
+__device__ __forceinline__ double ef_cheb_group(const double* c, int nc, double t) {
+    const int sub = threadIdx.x & (G - 1);
+    t = fmin(1.0, fmax(-1.0, t));
+    const double t2 = 2.0 * t;
+    double a = 1.0, b = t;
+    double ts = sub == 0 ? 1.0 : t;        // T_sub
+    double tm = 1.0;                       // T_{G - sub}
+#pragma unroll 4
+    for (int k = 2; k <= G; k++) {
+        double n = fma(t2, b, -a);
+        a = b; b = n;
+        if (k == sub) ts = n;
+        if (k == G - sub) tm = n;
+    }
+    if (sub == G - 1) tm = t;
+    const double tg2 = 2.0 * b;            // 2 T_G
+    double um = tm, u = ts;                // T_{|sub - G|}, T_sub
+    double acc = sub < nc ? c[sub] * u : 0.0;
+#pragma unroll
+    for (int m = 1; m < CM / G; m++) {
+        double un = fma(tg2, u, -um);
+        um = u; u = un;
+        if (sub + G * m < nc) acc = fma(c[sub + G * m], u, acc);
+    }
+#pragma unroll
+    for (int d = G / 2; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    return acc;
+}
+
+// Chebyshev coefficients of level L from the 64 node values in s.val[0..64): 16 threads per coefficient.
+// The caller zeroes s.ncoef[L] before the preceding barrier.
+__device__ __forceinline__ void ef_cheb_fit(EfSmem& s, int L) {
+    constexpr int TPC = EF_THREADS / CM;   // threads per coefficient
+    const int k = threadIdx.x / TPC, sub = threadIdx.x % TPC;
+    double c = 0.0;
+#pragma unroll
+    for (int q = 0; q < CM / TPC; q++) { int i = sub + TPC * q; c = fma(s.val[i], s.costab[k * CS + i], c); }
+#pragma unroll
+    for (int d = TPC / 2; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (sub == 0) {
+        c *= (k == 0 ? 1.0 : 2.0) / CM;
+        s.coef[L][k] = c;
+        if (k == 0 || fabs(c) > 1e-18) atomicMax(&s.ncoef[L], k + 1);
+    }
+    __syncthreads();
+}
+
+// Jump along the fixed-point iteration.  On success *alpha_k is iterate number *k_done (k_done >= 1) counted
+// from alpha0.  `guess` (> 0) is the previous M-step's result: the bracket end is first looked for right next to it.
+__device__ bool ef_jump(EfSmem& s, int jmax, double mu, double N1, double alpha0, double a1, int k_offset, double guess,
+                        double* alpha_k, int* k_done) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double sg = a1 > alpha0 ? 1.0 : -1.0;
+    EP_BEGIN();
+    // ---- bracket end b: a point just beyond the fixed point (G(b) - b has the opposite sign of the travel)
+    double b = 0.0;
+    if (guess > 0.0 && sg * (guess - alpha0) > 0.0) {
+        if (tid < 2) s.pts[tid] = guess * (tid == 0 ? (1.0 + 0.02 * sg) : (1.0 + 0.15 * sg));
+        __syncthreads();
+        ef_eval_points<CM>(s, jmax, mu, N1, 2);
+        if (sg * (s.val[0] - s.pts[0]) <= 0.0) b = s.pts[0];
+        else if (sg * (s.val[1] - s.pts[1]) <= 0.0) b = s.pts[1];
+        __syncthreads();
+    }
+    if (!(b > 0.0)) {
+        if (tid < CM) s.pts[tid] = alpha0 * pow(1.1, sg * (double)(tid + 1));
+        __syncthreads();
+        ef_eval_points<CM>(s, jmax, mu, N1);
+        int hit = -1;
+        for (int i = 0; i < CM; i++)
+            if (sg * (s.val[i] - s.pts[i]) <= 0.0) { hit = i; break; }
+        if (hit < 0) return false;
+        b = s.pts[hit];
+        __syncthreads();
+    }
+    const double xa = log(fmin(alpha0, b)), xb = log(fmax(alpha0, b));
+    const double half = 0.5 * (xb - xa), mid = 0.5 * (xb + xa);
+    if (!(half > 0.0) || !isfinite(half)) return false;
+    const double inv_half = 1.0 / half;
+    EP_END(s, EP_BRACKET);
+    // ---- F(x) = log G(exp x) at the 64 Chebyshev-Gauss nodes + 16 check points (extrema of T_64)
+    constexpr int NCHK = 16;
+    if (tid < CM) s.pts[tid] = exp(mid + half * s.costab[CS + tid]);
+    else if (tid < CM + NCHK) s.pts[tid] = exp(mid + half * cos(EF_PI * (double)(tid - CM) / (double)NCHK));
+    if (tid == 0) { s.flag = 1; for (int q = 0; q < CL; q++) s.ncoef[q] = 0; }
+    __syncthreads();
+    ef_eval_points<2 * CM>(s, jmax, mu, N1, CM + NCHK);
+    double fx = 0.0;
+    if (tid < CM + NCHK) { fx = log(s.val[tid]); if (!isfinite(fx)) s.flag = 0; }
+    __syncthreads();
+    if (tid < CM + NCHK) s.val[tid] = fx;
+    __syncthreads();
+    if (tid < CM - 1) {   // secant slopes in (0, 1): monotone, contracting
+        double dx = half * (s.costab[CS + tid] - s.costab[CS + tid + 1]);
+        double df = s.val[tid] - s.val[tid + 1];
+        if (!(df > 0.0) || !(df < dx)) s.flag = 0;
+    }
+    __syncthreads();
+    if (!s.flag) return false;
+    ef_cheb_fit(s, 0);
+    const double* c0 = s.coef[0];
+    const int nc0 = s.ncoef[0];
+    if (warp < NCHK) {   // one warp per check point
+        double t = cos(EF_PI * (double)warp / (double)NCHK);
+        double err = fabs(ef_cheb_group<32>(c0, nc0, t) - s.val[CM + warp]);
+        if (lane == 0 && !(err < 2e-12)) s.flag = 0;
+    }
+    __syncthreads();
+    if (!s.flag) return false;
+    EP_END(s, EP_NODES);
+    if (tid == 0) s.cyc[EP_NCOEF] += nc0;
+    // ---- x_c: last point on the path (from x0 towards the bracket end) whose step is still >= eps * (1 + 1e-3);
+    //      rounds of EF_WARPS-way sectioning, one warp per trial point (16^8 > 4e9 subdivisions)
+    const double x0 = log(alpha0), xe = sg > 0.0 ? xb : xa;
+    const double epsx = 1e-6 * (1.0 + 1e-3);
+    double lo = 0.0, hi = 1.0;
+    for (int round = 0; round < 8; round++) {
+        double u = lo + (hi - lo) * (double)(warp + 1) / (double)EF_WARPS;
+        double x = x0 + u * (xe - x0);
+        double g = sg * (ef_cheb_group<32>(c0, nc0, (x - mid) * inv_half) - x);
+        int cnt = __syncthreads_count(lane == 0 && g >= epsx);
+        double nlo = lo + (hi - lo) * (double)cnt / (double)EF_WARPS;
+        double nhi = lo + (hi - lo) * (double)min(cnt + 1, EF_WARPS) / (double)EF_WARPS;
+        lo = nlo; hi = nhi;
+    }
+    const double xc = x0 + lo * (xe - x0);
+    if (!(sg * (xc - x0) > 0.0)) return false;   // the stopping point is (almost) at x0: nothing to jump over
+    EP_END(s, EP_XC);
+    // ---- number of composition levels from a contraction estimate (step at x0, slope at the far end);
+    //      the descent below is exact whatever the estimate
+    int want_levels;
+    if (warp == 0) {
+        const double d0 = fabs(ef_cheb_group<32>(c0, nc0, (x0 - mid) * inv_half) - x0);
+        const double h = 1e-3 * half;
+        const double slope = fabs(ef_cheb_group<32>(c0, nc0, (xe - mid) * inv_half) - ef_cheb_group<32>(c0, nc0, (xe - sg * h - mid) * inv_half)) / h;
+        double kest = 16.0;
+        if (slope > 0.0 && slope < 1.0 && d0 > epsx) kest = log(d0 / epsx) / -log(slope);
+        if (!(kest >= 1.0)) kest = 1.0;
+        if (kest > 16384.0) kest = 16384.0;
+        int wl = (int)ceil(log2(kest)) + 2;
+        if (wl < 2) wl = 2;
+        if (wl > CL) wl = CL;
+        if (lane == 0) s.ibc = wl;
+    }
+    __syncthreads();
+    want_levels = s.ibc;
+    // ---- F^(2^L) at the nodes: inner evaluation = mat-vec with the cosine table, outer = 16-lane series evaluation
+    int n_levels = 1;
+    while (n_levels < want_levels) {
+        const double* cl = s.coef[n_levels - 1];
+        const int nc = s.ncoef[n_levels - 1];
+        constexpr int TPN = EF_THREADS / CM;   // threads per node
+        const int i = tid / TPN, sub = tid % TPN;
+        double y = 0.0;
+#pragma unroll
+        for (int q = 0; q < CM / TPN; q++) { int k = sub + TPN * q; if (k < nc) y = fma(cl[k], s.costab[k * CS + i], y); }
+#pragma unroll
+        for (int d = TPN / 2; d; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
+        double v = ef_cheb_group<TPN>(cl, nc, (y - mid) * inv_half);
+        if (sub == 0) s.val[i] = v;
+        __syncthreads();
+        ef_cheb_fit(s, n_levels);
+        n_levels++;
+    }
+    EP_END(s, EP_DOUBLING);
+    if (tid == 0) s.cyc[EP_LEVELS] += n_levels;
+    // ---- descent: keep every jump that still lands at or before x_c
+    double x = x0;
+    int k = 0;
+    if (warp == 0) {
+        for (int L = n_levels - 1; L >= 0; L--) {
+            double y = ef_cheb_group<32>(s.coef[L], s.ncoef[L], (x - mid) * inv_half);
+            if (sg * (xc - y) >= 0.0 && k_offset + k + (1 << L) <= 9998) { x = y; k += 1 << L; }
+        }
+        if (lane == 0) { s.bcast[0] = x; s.ibc = k; }
+    }
+    __syncthreads();
+    x = s.bcast[0]; k = s.ibc;
+    __syncthreads();
+    EP_END(s, EP_DESCENT);
+    if (k == 0) return false;
+    *alpha_k = exp(x);
+    *k_done = k;
+    return true;
+}
+
+__global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
+    extern __shared__ __align__(16) unsigned char ef_raw[];
+    EfSmem& s = *reinterpret_cast<EfSmem*>(ef_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n64 = a.n_bins_host >= 0 ? a.n_bins_host : a.status[ST_N_BINS];
+    if (n64 > EF_MAXN) { if (tid == 0) a.status[ST_EM_MODE] = 1; return; }
+    const int n = (int)n64;
+    // ---- bins into registers
+    double v[EF_BPT], w[EF_BPT], lgk1[EF_BPT], r0[EF_BPT], r1[EF_BPT], r2[EF_BPT];
+    double tot[1] = {0.0};
+    double vmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < EF_BPT; k++) {
+        int i = tid + k * EF_THREADS;
+        v[k] = 0.0; w[k] = 0.0; lgk1[k] = 0.0; r0[k] = r1[k] = r2[k] = 0.0;
+        if (i < n) {
+            v[k] = (double)a.values[i]; w[k] = (double)a.weights[i];
+            lgk1[k] = lgamma(v[k] + 1.0);
+            tot[0] += w[k];
+            vmax = fmax(vmax, v[k]);
+        }
+    }
+    if (tid < 12) s.cyc[tid] = 0;
+    for (int q = tid; q < CM * CM; q += EF_THREADS) {
+        int k = q / CM, i = q % CM;
+        s.costab[k * CS + i] = cos((double)k * EF_PI * ((double)i + 0.5) / (double)CM);
+    }
+    ef_block_sum<1>(tot, s.red);
+    vmax = ef_block_max(vmax, s.red);
+    if (n < 30 || tot[0] < 1e5) {   // peaks.py:176-177
+        if (tid == 0) {
+            a.status[ST_THRESHOLD] = DEFAULT_THRESHOLD; a.status[ST_HAS_PARAMS] = 0; a.status[ST_EM_ITERS] = 0; a.status[ST_EM_INNER] = 0;
+            a.status[ST_EM_DIRECT] = 0; a.status[ST_EM_MODE] = 2;
+            for (int k = 0; k < 6; k++) a.params_out[k] = 0.0;
+        }
+        return;
+    }
+    if (vmax + 2.0 > (double)EF_MAXV) { if (tid == 0) a.status[ST_EM_MODE] = 1; return; }
+
+    // ---- inclusive scans over the bins in bin order (slab k = bins [1024k, 1024k+1024))
+    auto scan_forward = [&](const double (&x)[EF_BPT], double (&out)[EF_BPT]) {
+        double carry = 0.0;
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++) {
+            if (k * EF_THREADS >= n) { out[k] = carry; continue; }   // uniform
+            double inc = x[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+            __syncthreads();
+            if (lane == 31) s.wtot[warp] = inc;
+            __syncthreads();
+            double off = carry, slab = 0.0;
+            for (int q = 0; q < EF_WARPS; q++) { double t = s.wtot[q]; if (q < warp) off += t; slab += t; }
+            out[k] = off + inc;
+            carry += slab;
+        }
+    };
+    auto scan_backward = [&](const double (&x)[EF_BPT], double (&out)[EF_BPT]) {   // out = sum of x over bins >= this one
+        double carry = 0.0;
+#pragma unroll
+        for (int k = EF_BPT - 1; k >= 0; k--) {
+            if (k * EF_THREADS >= n) { out[k] = 0.0; continue; }
+            double inc = x[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_down_sync(0xffffffffu, inc, d); if (lane + d < 32) inc += y; }
+            __syncthreads();
+            if (lane == 0) s.wtot[warp] = inc;
+            __syncthreads();
+            double off = carry, slab = 0.0;
+            for (int q = EF_WARPS - 1; q >= 0; q--) { double t = s.wtot[q]; if (q > warp) off += t; slab += t; }
+            out[k] = off + inc;
+            carry += slab;
+        }
+    };
+
+    // ---- simple_threshold_estimate (peaks.py:28-40)
+    int t0;
+    {
+        double r[EF_BPT], cum[EF_BPT];
+        double cnt[2] = {0.0, 0.0};   // bins <= 15, bins > 15
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++) {
+            bool in = tid + k * EF_THREADS < n;
+            bool above = in && v[k] > (double)DEFAULT_THRESHOLD;
+            r[k] = above ? v[k] * w[k] : 0.0;
+            cnt[0] += (in && !above) ? 1.0 : 0.0;
+            cnt[1] += above ? 1.0 : 0.0;
+        }
+        scan_forward(r, cum);
+        ef_block_sum<2>(cnt, s.red);
+        double total[1] = {0.0};
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++) total[0] += r[k];
+        ef_block_sum<1>(total, s.red);
+        double best = -1.0;
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++)
+            if (r[k] > 0.0 && cum[k] / total[0] <= 0.25) best = fmax(best, v[k]);
+        best = ef_block_max(best, s.red);
+        if (best > 0.0) t0 = (int)best;
+        else if (cnt[1] >= 2.0) t0 = (int)a.values[(int)cnt[0] + 1];   // count_values[1]
+        else { if (tid == 0) raise_error(a.status, CRATAC_ERR_EM_INDEX, n); return; }
+    }
+
+    long long iters = 0, inner = 0, direct = 0;
+    int prev_inner = 1 << 20;     // iterations of the previous dispersion fixed point (first one: assume long)
+    double prev_alpha = 0.0;      // its result: where the next bracket is looked for first
+    bool bail = false;        // a safety check failed inside the fast path: let k_em_fit redo the fit
+    bool zerodiv = false;
+
+    // ---- M-step (peaks.py:90-128) on the register-resident responsibilities
+    auto m_step = [&](Th& th) -> bool {
+        EP_BEGIN();
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        double vmax1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++) {
+            double o0 = w[k] * r0[k], o1 = w[k] * r1[k], o2 = w[k] * r2[k];
+            acc[0] += o0; acc[1] += v[k] * o0; acc[2] += o1; acc[3] += v[k] * o1; acc[4] += o2; acc[5] += v[k] * o2;
+            if (r1[k] > 0.0) vmax1 = fmax(vmax1, v[k]);
+        }
+        ef_block_sum<6>(acc, s.red);
+        vmax1 = ef_block_max(vmax1, s.red);
+        const double N0 = acc[0], K0 = acc[1], N1 = acc[2], M1 = acc[3], N2 = acc[4], K2 = acc[5];
+        if (N0 == 0.0 || N2 == 0.0) { zerodiv = true; return false; }
+        th.p_zero = N0 / (N0 + (K0 - N0));
+        th.p_signal = N2 / (N2 + (K2 - N2));
+        const double mu = M1 / N1;
+        th.mean_bg = mu;
+        const double FT = N0 + N1 + N2;
+        th.f_zero = N0 / FT;
+        th.f_bg = N1 / FT;
+        if (N1 == 0.0) { th.alpha_bg = 1e-6; return true; }
+        double sq[1] = {0.0};
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++) { double d = mu - v[k]; sq[0] += d * d * (w[k] * r1[k]); }
+        ef_block_sum<1>(sq, s.red);
+        const double var = sq[0] / N1;
+        double alpha = fmax(1e-6, (var - mu) / (mu * mu));
+        if (vmax1 > 1e8 || !(var > mu)) { th.alpha_bg = alpha; return true; }
+        EP_END(s, EP_MSUMS);
+        // tail weights T(j) = sum_{i: v_i > j} w_i r1_i : bin i covers j in [v_{i-1}, v_i)
+        {
+            double o1[EF_BPT], suf[EF_BPT];
+#pragma unroll
+            for (int k = 0; k < EF_BPT; k++) o1[k] = w[k] * r1[k];
+            scan_backward(o1, suf);
+#pragma unroll
+            for (int k = 0; k < EF_BPT; k++)
+                if (tid + k * EF_THREADS < n) {
+                    const int i = tid + k * EF_THREADS;
+                    const int jlo = i > 0 ? (int)a.values[i - 1] : 0;
+                    for (int j = jlo; j < (int)v[k]; j++) s.T[j] = suf[k];
+                }
+            __syncthreads();
+        }
+        EP_END(s, EP_TFILL);
+        const int jmax = (int)vmax1;
+        auto G_block = [&](double al) {
+            double part[1] = {0.0};
+            for (int j = tid + 1; j < jmax; j += EF_THREADS) { double aj = al * (double)j; part[0] = fma(ef_frac(aj), s.T[j], part[0]); }
+            ef_block_sum<1>(part, s.red);
+            direct++;
+            return log(1.0 + al * mu) / (mu - part[0] / N1);
+        };
+        // Direct iterations alpha <- G(alpha) from evaluation `it` up to `limit` evaluations; true when the
+        // reference's stopping test fired.  For short tables one warp runs the whole loop on its own (no block
+        // barrier per iteration) and publishes the outcome; longer tables use the block-wide reduction.
+        auto plain = [&](double& al, double& nv, int& itc, int limit) -> bool {
+            bool stop = false;
+            if (jmax <= 2048) {
+                if (warp == 0) {
+                    long long nd = 0;
+                    while (itc < limit) {
+                        double part = 0.0;
+                        double part2 = 0.0;
+                        int j = lane + 1;
+                        for (; j + 32 < jmax; j += 64) {
+                            part = fma(ef_frac(al * (double)j), s.T[j], part);
+                            part2 = fma(ef_frac(al * (double)(j + 32)), s.T[j + 32], part2);
+                        }
+                        if (j < jmax) part = fma(ef_frac(al * (double)j), s.T[j], part);
+                        part += part2;
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                        nv = log(1.0 + al * mu) / (mu - part / N1);
+                        itc++; nd++;
+                        if (2.0 * fabs(nv - al) / (nv + al) < 1e-6) { stop = true; break; }
+                        al = nv;
+                    }
+                    if (lane == 0) { s.bcast[0] = al; s.bcast[1] = nv; s.bcast[2] = (double)itc; s.bcast[3] = stop ? 1.0 : 0.0; s.ibc = (int)nd; }
+                }
+                __syncthreads();
+                al = s.bcast[0]; nv = s.bcast[1]; itc = (int)s.bcast[2]; stop = s.bcast[3] != 0.0;
+                direct += s.ibc;
+                __syncthreads();
+            } else {
+                while (itc < limit) {
+                    nv = G_block(al);
+                    itc++;
+                    if (2.0 * fabs(nv - al) / (nv + al) < 1e-6) { stop = true; break; }
+                    al = nv;
+                }
+            }
+            return stop;
+        };
+        // Plain iterations first when the previous M-step was short; otherwise go to the jump almost at once.
+        // A failed jump (safety check) is retried after 64 more plain iterations, closer to the fixed point.
+        const int k_plain = prev_inner <= 64 ? 96 : 3;
+        double newv = alpha;
+        int it = 0;
+        bool stopped = plain(alpha, newv, it, k_plain);
+        for (int attempt = 0; !stopped && attempt < 8 && it < 9000; attempt++) {
+            double a_prev = alpha;                       // iterate number `it`
+            stopped = plain(alpha, newv, it, it + 1);    // one more evaluation: direction of travel
+            if (stopped) break;
+            double ak = a_prev;
+            int kd = 0;
+            EP_END(s, EP_DIRECT);
+            bool jumped = ef_jump(s, jmax, mu, N1, a_prev, newv, it - 1, prev_alpha, &ak, &kd);
+            _ep_t0 = clock64();
+            if (jumped) { alpha = ak; it = it - 1 + kd; break; }
+            stopped = plain(alpha, newv, it, it + 64);
+        }
+        if (!stopped) plain(alpha, newv, it, 10000);
+        prev_inner = it;
+        prev_alpha = newv;
+        EP_END(s, EP_DIRECT);
+        inner += it;
+        th.alpha_bg = newv;
+        return true;
+    };
+
+    auto e_step = [&](const Th& th) {   // peaks.py:66-87
+        EP_BEGIN();
+        const double f_sig = 1.0 - th.f_zero - th.f_bg;
+        const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+        const double lgn = lgamma(nn), nlogp = nn * log(pp), l1p = log1p(-pp);
+        const double lz = log(1.0 - th.p_zero), ls = log(1.0 - th.p_signal);
+#pragma unroll
+        for (int k = 0; k < EF_BPT; k++) {
+            if (tid + k * EF_THREADS >= n) { r0[k] = r1[k] = r2[k] = 0.0; continue; }
+            double z = exp((v[k] - 1.0) * lz) * th.p_zero * th.f_zero;
+            double b = exp(lgamma(nn + v[k]) - lgk1[k] - lgn + nlogp + v[k] * l1p) * th.f_bg;
+            double g = exp((v[k] - 1.0) * ls) * th.p_signal * f_sig;
+            double t = z + b + g;
+            if (t == 0.0) { r0[k] = r1[k] = r2[k] = 0.0; }
+            else { r0[k] = z / t; r1[k] = b / t; r2[k] = g / t; }
+        }
+        EP_END(s, EP_ESTEP);
+    };
+
+    auto moved = [](const Th& l, const Th& c) {
+        const double eps = 1e-6;
+        return (fabs(l.p_zero - c.p_zero) / c.p_zero > eps) || (fabs(l.mean_bg - c.mean_bg) / c.mean_bg > eps) ||
+               (fabs(l.alpha_bg - c.alpha_bg) / c.alpha_bg > eps) || (fabs(l.p_signal - c.p_signal) / c.p_signal > eps) ||
+               (fabs(l.f_zero - c.f_zero) / c.f_zero > eps) || (fabs(l.f_bg - c.f_bg) / c.f_bg > eps);
+    };
+
+    auto estimate_parameters = [&](bool seeded, Th& th) -> bool {   // peaks.py:144-170
+        if (!seeded) {
+#pragma unroll
+            for (int k = 0; k < EF_BPT; k++) {
+                bool in = tid + k * EF_THREADS < n;
+                r0[k] = (in && v[k] <= (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
+                r1[k] = (in && v[k] <= (double)t0 && v[k] > (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
+                r2[k] = (in && v[k] > (double)t0) ? 1.0 : 0.0;
+            }
+            if (!m_step(th)) return false;
+        }
+        Th last = th;
+        bool have_last = false;
+        int i = 0;
+        while (i < 500 && (!have_last || moved(last, th))) {
+            i++;
+            e_step(th);
+            last = th;
+            have_last = true;
+            Th nt = th;
+            if (!m_step(nt)) return false;
+            if (nt.p_zero < nt.p_signal) {   // normalize_params (peaks.py:131-141)
+                double pz = nt.p_signal, ps = nt.p_zero, fz = 1.0 - (nt.f_zero + nt.f_bg);
+                nt.p_zero = pz; nt.p_signal = ps; nt.f_zero = fz;
+            }
+            th = nt;
+        }
+        iters += i;
+        return true;
+    };
+
+    Th th;
+    bool ok = estimate_parameters(false, th);
+    int tries = 0;
+    while (ok && (1.0 / th.p_zero < th.mean_bg) && tries < 3) {   // peaks.py:183-191
+        Th seed;
+        seed.p_zero = th.p_signal; seed.mean_bg = 1.0 / th.p_zero; seed.alpha_bg = th.alpha_bg; seed.p_signal = 1.0 / th.mean_bg;
+        seed.f_zero = 1.0 - (th.f_zero + th.f_bg); seed.f_bg = th.f_bg;
+        th = seed;
+        ok = estimate_parameters(true, th);
+        tries++;
+    }
+    (void)bail;
+    if (!ok) {
+        if (tid == 0) { if (zerodiv) raise_error(a.status, CRATAC_ERR_EM_ZERODIV, n); a.status[ST_EM_MODE] = 2; }
+        return;
+    }
+    // ---- estimate_threshold (peaks.py:43-63)
+    const double f_sig = 1.0 - th.f_zero - th.f_bg;
+    const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+    double best = -1.0;
+    for (int xi = tid; xi < 1000; xi += EF_THREADS) {
+        double xv = (double)xi;
+        double ysig = f_sig * (pow(1.0 - th.p_signal, xv) * th.p_signal);
+        double nb = exp(lgamma(nn + xv) - lgamma(xv + 1.0) - lgamma(nn) + nn * log(pp) + xv * log1p(-pp));
+        double ybg = th.f_zero * (pow(1.0 - th.p_zero, xv) * th.p_zero) + th.f_bg * nb;
+        if (ysig / ybg < a.odds_ratio) best = fmax(best, xv);
+    }
+    best = ef_block_max(best, s.red);
+    if (tid == 0) {
+        a.status[ST_THRESHOLD] = best < 0.0 ? 0 : (int64_t)best;
+        a.status[ST_HAS_PARAMS] = best < 0.0 ? 2 : 1;
+        a.status[ST_EM_ITERS] = iters; a.status[ST_EM_INNER] = inner; a.status[ST_EM_DIRECT] = direct; a.status[ST_EM_MODE] = 2;
+        a.params_out[0] = th.p_zero; a.params_out[1] = th.mean_bg; a.params_out[2] = th.alpha_bg;
+        a.params_out[3] = th.p_signal; a.params_out[4] = th.f_zero; a.params_out[5] = th.f_bg;
+        for (int q = 0; q < EP_COUNT; q++) a.params_out[8 + q] = (double)s.cyc[q];
+    }
+}
+
+// returns the dynamic shared memory the fast kernel needs
+size_t em_fast_smem() { return sizeof(EfSmem); }
+
+int em_fast_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio) {
+    static bool configured = false;
+    if (!configured) {
+        CRATAC_CUDA(cudaFuncSetAttribute(k_em_fit_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EfSmem)));
+        configured = true;
+    }
+    EfArgs a;
+    a.values = d_values; a.weights = d_weights; a.n_bins_host = n_bins_host; a.status = c->d_status.as<int64_t>();
+    a.params_out = c->d_em_params.as<double>(); a.odds_ratio = odds_ratio;
+    k_em_fit_fast<<<1, EF_THREADS, sizeof(EfSmem), c->stream>>>(a);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+}  // namespace cratac

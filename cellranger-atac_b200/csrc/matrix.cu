@@ -227,6 +227,11 @@ int peak_matrix_device(Ctx* c) {
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     CRATAC_TRY(exclusive_scan_i32_to_i64(c, a.bc_hits, c->d_seg_off.as<int64_t>(), nb, c->d_seg_off.as<int64_t>() + nb));
+    // matrix column order: host work (CPython-2.7 set emulation over the barcode hashes) overlaps the kernels
+    // queued so far (pileup, fit, peaks, overlap count)
+    c->host_mark("matrix_launch");
+    CRATAC_TRY(build_barcodes(c));
+    c->host_mark("build_barcodes");
     // K (total hits) sizes the hit buffers: one host round trip here (8 bytes)
     CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
@@ -261,10 +266,6 @@ int peak_matrix_device(Ctx* c) {
         c->launches += 2;
         CRATAC_CUDA(cudaGetLastError());
     }
-    // column order (host work of build_barcodes overlaps the kernels queued above)
-    c->host_mark("matrix_launch");
-    CRATAC_TRY(build_barcodes(c));
-    c->host_mark("build_barcodes");
     const int32_t* c2d = c->d_col_to_dense.as<int32_t>();
     if (nb > 0) {
         k_gather_nnz<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(nnz_col, c2d, nb, nnz_ordered);

@@ -145,13 +145,14 @@ def test_em_accelerated_fixed_point_matches_plain_iteration():
     for case in EM_CASES:
         if case.get("raises") or case["params"] is None:
             continue
-        ctx.set_option("em_fast", 0)
+        ctx.set_option("em_fast", 0)                    # plain fixed point, generic kernel
         thr0, p0, st0 = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
-        ctx.set_option("em_fast", 1)
-        thr1, p1, st1 = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
-        assert thr0 == thr1 == case["threshold"]
-        assert st0 == st1, (case["name"], st0, st1)
-        assert np.allclose(np.array(p0), np.array(p1), rtol=1e-9, atol=0), (case["name"], p0, p1)
+        for mode in (1, 2):                             # accelerated generic kernel, register-resident kernel
+            ctx.set_option("em_fast", mode)
+            thr1, p1, st1 = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
+            assert thr0 == thr1 == case["threshold"]
+            assert st0 == st1, (case["name"], mode, st0, st1)
+            assert np.allclose(np.array(p0), np.array(p1), rtol=1e-9, atol=0), (case["name"], mode, p0, p1)
     ctx.close()
 
 

@@ -5,7 +5,7 @@ cases=json.load(open('tests/golden/em.json'))
 ctx=_ffi.Context([("chr1",1000)])
 for c in cases:
     if c.get('raises') or c['params'] is None: continue
-    for fast in (1,):
+    for fast in (2,):
         ctx.set_option('em_fast', fast)
         ctx.fit_threshold(c['values'], c['weights'], 0.2)
         t=time.time(); thr,p,st=ctx.fit_threshold(c['values'], c['weights'], 0.2); dt=time.time()-t
