@@ -92,7 +92,8 @@ class ClockSampler(object):
 
 # --------------------------------------------------------------------------------------------- workload
 def shard_contigs(contigs, world):
-    """LPT bin-packing of contigs over ranks; rank -> list of contig indices (sorted)."""
+    """LPT bin-packing of contigs over ranks (kept for reference; the benchmark uses contiguous ranges,
+    cratac.multi.partition_contigs, so that matrix rows of different ranks never interleave)."""
     loads = [0] * world
     parts = [[] for _ in range(world)]
     for i in sorted(range(len(contigs)), key=lambda k: -contigs[k][1]):
@@ -102,7 +103,7 @@ def shard_contigs(contigs, world):
     return [sorted(p) for p in parts]
 
 
-def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device):
+def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chrom_offset=0):
     """Seeded synthetic fragments generated ON the device (torch is plumbing here), sorted by
     (contig, start, stop) and rendered to fragments.tsv text by the library's encoder kernel.
     Same distributions as cratac/synth.py."""
@@ -137,18 +138,20 @@ def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device):
     key = ((cum[chrom] + start) << 11) | (end - start)
     order = torch.argsort(key)
     del key
-    chrom = chrom[order].to(torch.int32)
+    chrom = (chrom[order] + chrom_offset).to(torch.int32)   # index into the context's (global) contig list
     start = start[order].to(torch.int32)
     end = end[order].to(torch.int32)
     del order
     dup = torch.empty(n, device=device).geometric_(0.5, generator=g).to(torch.int32)
     n_bg = 20 * cells
-    depth = torch.empty(cells, device=device).log_normal_(0.0, 0.5, generator=g)
+    gb = torch.Generator(device=device)
+    gb.manual_seed(977)                      # the barcode universe is the same on every rank
+    depth = torch.empty(cells, device=device).log_normal_(0.0, 0.5, generator=gb)
     p = torch.cat([0.8 * depth / depth.sum(), torch.full((n_bg,), 0.2 / n_bg, device=device)])
     cdf = torch.cumsum(p.double(), 0)
     cdf = cdf / cdf[-1]
     bc_idx = torch.searchsorted(cdf, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=cells + n_bg - 1)
-    seqs = torch.randint(0, 1 << 32, (cells + n_bg,), generator=g, device=device, dtype=torch.int64)
+    seqs = torch.randint(0, 1 << 32, (cells + n_bg,), generator=gb, device=device, dtype=torch.int64)
     seqs = torch.where(seqs >= (1 << 31), seqs - (1 << 32), seqs).to(torch.int32)
     seq = seqs[bc_idx].contiguous()
     del bc_idx
@@ -278,18 +281,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    # ---- shard the genome by contig
-    parts = shard_contigs(contigs_all, world)
-    mine = parts[rank]
-    contigs = [contigs_all[i] for i in mine]
+    # ---- shard the genome into contiguous contig ranges (rank order = genome order)
+    from cratac import multi
+    parts = multi.partition_contigs([c[1] for c in contigs_all], world)
+    first_c, last_c = parts[rank]
+    contigs = contigs_all[first_c:last_c]
     share = sum(c[1] for c in contigs) / float(args.genome_bases)
     n_local = int(round(args.fragments * share))
     peaks_local = max(int(round(args.peaks * share)), 1)
     G = sum(c[1] for c in contigs)
 
-    ctx = _ffi.Context(contigs, device=local_rank)
+    # every rank knows all contigs (global ids); it piles up / calls peaks on its own range only
+    ctx = _ffi.Context(contigs_all, primary=[c[0] for c in contigs], device=local_rank)
     ctx.set_option("profile", 1)
-    text, nbytes = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device)
+    text, nbytes = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device, chrom_offset=first_c)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
     def barrier():
@@ -301,7 +306,9 @@ def main():
     def step_device():
         if world == 1:
             return ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
-        return multi_gpu_step(ctx, torch, dist, text.data_ptr(), nbytes, device)
+        with torch.cuda.stream(stream):
+            shard = multi.CudaShard(ctx, torch, device, text_dev_ptr=text.data_ptr(), nbytes=nbytes)
+            return multi.step(shard, torch, dist, device)
 
     # ---- device-resident timing
     res = None
@@ -340,7 +347,7 @@ def main():
         torch.cuda.synchronize()
         nb = res.n_barcodes
         out_indptr = torch.empty(nb + 1, dtype=torch.int64, pin_memory=True)
-        cap_nnz = int(res.nnz * 1.05) + 1024
+        cap_nnz = int(res.nnz * 1.05) + 1024 if (world == 1 or rank == 0) else 16
         out_indices = torch.empty(cap_nnz, dtype=torch.int64, pin_memory=True)
         out_data = torch.empty(cap_nnz, dtype=torch.int32, pin_memory=True)
         outs = (out_indptr.numpy(), out_indices.numpy(), out_data.numpy())
@@ -348,10 +355,14 @@ def main():
         def step_e2e():
             if world == 1:
                 r = ctx.run(text=(host_text.data_ptr(), nbytes), odds_ratio=0.2)
-            else:
-                r = multi_gpu_step(ctx, torch, dist, None, nbytes, device, host_ptr=host_text.data_ptr())
-            ctx.get_peaks(r.n_peaks)
-            ctx.get_matrix(r.nnz, out=outs)
+                ctx.get_peaks(r.n_peaks)
+                ctx.get_matrix(r.nnz, out=outs)
+                return r
+            with torch.cuda.stream(stream):
+                shard = multi.CudaShard(ctx, torch, device, text_host=(host_text.data_ptr(), nbytes), nbytes=nbytes)
+                r = multi.step(shard, torch, dist, device)
+            if rank == 0:
+                ctx.get_matrix_cols(r.n_barcodes, r.nnz, out=outs)       # merged matrix -> pinned host memory
             return r
 
         for _ in range(min(args.warmup, 2)):
@@ -369,7 +380,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         d2h = 12 * int(r.n_peaks) + 8 * (int(r.n_barcodes) + 1) + 12 * int(r.nnz)
-        e2e = {"value": total_frags / (ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(d2h),
+        nbytes_all = torch.tensor([nbytes], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(nbytes_all)
+        h2d_total = int(nbytes_all.item())
+        e2e = {"value": total_frags / (ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms / args.steps}
 
     if rank != 0:
@@ -380,7 +395,10 @@ def main():
     # ---- roofline of the dominant HBM-bound kernel (rank 0's shard)
     peak_gbs, peak_src = measured_peaks()
     K_hits = int(res.n_hits)
-    alg = algorithmic_bytes(nbytes, res.n_fragments, G, res.n_peaks, K_hits, res.nnz, res.n_barcodes)
+    n_frag_r0 = getattr(res, "n_fragments_local", res.n_fragments)
+    n_peaks_r0 = getattr(res, "n_peaks_local", res.n_peaks)
+    nnz_r0 = getattr(res, "nnz_local", res.nnz)
+    alg = algorithmic_bytes(nbytes, n_frag_r0, G, n_peaks_r0, K_hits, nnz_r0, res.n_barcodes)
     kernels = {}
     for name, members in KERNEL_GROUPS.items():
         ms = sum(stage_ms.get(m, 0.0) for m in members) / args.steps
@@ -413,21 +431,15 @@ def main():
             "dtype": "int32", "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": kernels, "em_fit_ms": em_ms, "em_iterations": int(res.em_iterations), "em_inner_iterations": int(res.em_inner_iterations),
-            "result": {"n_fragments_rank0": int(res.n_fragments), "n_barcodes": int(res.n_barcodes), "threshold": int(res.threshold),
-                       "n_peaks_rank0": int(res.n_peaks), "nnz_rank0": int(res.nnz), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},
+            "result": {"n_fragments": int(res.n_fragments), "n_fragments_rank0": int(n_frag_r0), "n_barcodes": int(res.n_barcodes),
+                       "threshold": int(res.threshold), "n_peaks": int(res.n_peaks), "n_peaks_rank0": int(n_peaks_r0), "nnz": int(res.nnz),
+                       "nnz_rank0": int(nnz_r0), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},
             "wall_ms_per_step": 1000.0 * wall / args.steps, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "host_phases_last_step_ms": ctx.host_times(),
-            "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},
-            "n_bins": int(res.n_bins)}
+            "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def multi_gpu_step(ctx, torch, dist, dev_ptr, nbytes, device, host_ptr=None):
-    """One step on one rank's genome shard with the cross-rank exchanges of SURVEY.md section 8e."""
-    from cratac import multi
-    return multi.step(ctx, torch, dist, dev_ptr, nbytes, device, host_ptr=host_ptr)
 
 
 if __name__ == "__main__":

@@ -77,6 +77,14 @@ SIGNATURES = {
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_py2_set_order": (c_int, [c_i64, P(c_cp), c_vp]),
+    "cratac_status_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
+    "cratac_window_histogram": (c_int, [c_vp]),
+    "cratac_compact_histogram": (c_int, [c_vp]),
+    "cratac_barcode_table_device": (c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_i64)]),
+    "cratac_set_column_map": (c_int, [c_vp, c_i64, c_vp]),
+    "cratac_set_row_offset": (c_int, [c_vp, c_i64, c_i64]),
+    "cratac_merge_rank_csc": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64]),
+    "cratac_py2_set_order_hashes": (c_int, [c_i64, c_vp, c_vp]),
     "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
     "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
 }
@@ -309,6 +317,57 @@ class Context(object):
             check(self._lib.cratac_run_from_fragments(self._h, float(odds_ratio), ctypes.byref(res)))
         return res
 
+    # ---- multi-GPU building blocks (device pointers; the host code wraps them as torch tensors)
+    def status_device(self):
+        p, n = c_vp(), c_i64()
+        check(self._lib.cratac_status_device(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def hist_device(self):
+        p, n = c_vp(), c_i64()
+        check(self._lib.cratac_hist_device(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def window_histogram(self):
+        check(self._lib.cratac_window_histogram(self._h))
+
+    def compact_histogram(self):
+        check(self._lib.cratac_compact_histogram(self._h))
+
+    def barcode_table_device(self):
+        k, f, hsh, n = c_vp(), c_vp(), c_vp(), c_i64()
+        check(self._lib.cratac_barcode_table_device(self._h, ctypes.byref(k), ctypes.byref(f), ctypes.byref(hsh), ctypes.byref(n)))
+        return k.value, f.value, hsh.value, n.value
+
+    def set_column_map(self, n_cols, d_col_to_dense):
+        check(self._lib.cratac_set_column_map(self._h, int(n_cols), c_vp(int(d_col_to_dense)) if d_col_to_dense else None))
+
+    def set_row_offset(self, row_base, total_rows):
+        check(self._lib.cratac_set_row_offset(self._h, int(row_base), int(total_rows)))
+
+    def peak_matrix_device(self):
+        """Build the CSC on the device only -> (nnz, d_indptr, d_indices, d_data)."""
+        nnz = c_i64()
+        check(self._lib.cratac_peak_matrix(self._h, ctypes.byref(nnz)))
+        a, b, c = c_vp(), c_vp(), c_vp()
+        check(self._lib.cratac_matrix_device(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return nnz.value, a.value, b.value, c.value
+
+    def merge_rank_csc(self, world, n_cols, d_indptr_all, d_rank_off, d_indices_all, d_data_all, total_nnz):
+        check(self._lib.cratac_merge_rank_csc(self._h, int(world), int(n_cols), c_vp(int(d_indptr_all)), c_vp(int(d_rank_off)),
+                                              c_vp(int(d_indices_all)), c_vp(int(d_data_all)), int(total_nnz)))
+
+    def get_matrix_cols(self, n_cols, nnz, out=None):
+        """D2H of the current CSC when its column count is not the shard's own barcode count."""
+        if out is not None:
+            indptr, indices, data = out[0][:n_cols + 1], out[1][:nnz], out[2][:nnz]
+        else:
+            indptr = np.zeros(n_cols + 1, dtype=np.int64)
+            indices = np.zeros(nnz, dtype=np.int64)
+            data = np.zeros(nnz, dtype=np.int32)
+        check(self._lib.cratac_get_matrix(self._h, _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
     def encode_text_device(self, n, d_chrom, d_start, d_end, d_seq, d_dup, d_out, cap):
         nb = c_i64()
         check(self._lib.cratac_encode_text_device(self._h, int(n), c_vp(int(d_chrom)), c_vp(int(d_start)), c_vp(int(d_end)),
@@ -346,6 +405,15 @@ def py2_set_order(keys):
     out = np.zeros(max(n, 1), dtype=np.int64)
     check(lib.cratac_py2_set_order(n, arr, _ptr(out)))
     return out[:n].tolist()
+
+
+def py2_set_order_hashes(hashes):
+    """CPython-2.7 list(set) order of distinct str keys from their hashes (insertion order) -> int32 index array."""
+    lib = load()
+    h = np.ascontiguousarray(hashes, dtype=np.int64)
+    out = np.zeros(max(h.size, 1), dtype=np.int32)
+    check(lib.cratac_py2_set_order_hashes(h.size, _ptr(h), _ptr(out)))
+    return out[:h.size]
 
 
 def inflate_file(path, threads=None):

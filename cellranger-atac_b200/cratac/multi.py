@@ -1,0 +1,232 @@
+"""Genome-range sharding of the path over the GPUs of one node.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo on CPU for the tests).  The genome is cut into
+`world` CONTIGUOUS contig ranges (rank order = genome order), so no halo and no peak stitching is needed and
+matrix rows of different ranks never interleave.  Exchanges, all small except the last:
+
+  1. window-count histogram: all-reduce(max) of the largest count, all-reduce(sum) of the bins  -- replaces the
+     `Counter +=` of count_cut_sites/__init__.py:77-81; the mixture fit then runs redundantly on every rank.
+  2. peak counts and fragment counts: all-gather -> matrix row base and global line base of every rank.
+  3. barcode dictionary: all-gather of (64-bit key, first global line, CPython-2.7 hash); union -> the global
+     column order of generate_peak_matrix/__init__.py:44 and each rank's column -> local barcode map.
+  4. CSC column blocks: gathered to rank 0 and interleaved per column (rank order keeps rows ascending) --
+     replaces the hstack of generate_peak_matrix/__init__.py:62-72.
+
+`step()` is written against a small backend interface so that the exchange logic runs unchanged on CPU tensors
+with gloo (tests/test_multi_cpu.py, where the per-shard compute is played by the oracle) and on the GPU with the
+CUDA library (`CudaShard`).
+"""
+import numpy as np
+
+
+# --------------------------------------------------------------------------------------------- partition
+def partition_contigs(contig_lens, world):
+    """Contiguous partition of the contigs into `world` ranges minimising the largest range (DP).
+    -> list of (first, last_exclusive) index pairs, one per rank (ranges may be empty when world > n)."""
+    n = len(contig_lens)
+    pre = [0]
+    for L in contig_lens:
+        pre.append(pre[-1] + int(L))
+    INF = float("inf")
+    best = [[INF] * (n + 1) for _ in range(world + 1)]
+    cut = [[0] * (n + 1) for _ in range(world + 1)]
+    best[0][0] = 0
+    for k in range(1, world + 1):
+        for j in range(0, n + 1):
+            for i in range(0, j + 1):
+                if best[k - 1][i] == INF:
+                    continue
+                cost = max(best[k - 1][i], pre[j] - pre[i])
+                if cost < best[k][j]:
+                    best[k][j] = cost
+                    cut[k][j] = i
+    bounds = []
+    j = n
+    for k in range(world, 0, -1):
+        i = cut[k][j]
+        bounds.append((i, j))
+        j = i
+    return bounds[::-1]
+
+
+# --------------------------------------------------------------------------------------------- barcode union
+def global_columns(torch, keys_all, first_all, hash_all, valid_all, py2_order_fn, order="py2set"):
+    """keys/first/hash: int64 tensors [world, maxB] (padded), valid_all: bool [world, maxB].
+    -> (n_cols, col_of[world, maxB] int64 with -1 on padding, uniq_keys in column order)."""
+    flat_valid = valid_all.reshape(-1)
+    keys = keys_all.reshape(-1)[flat_valid]
+    first = first_all.reshape(-1)[flat_valid]
+    hsh = hash_all.reshape(-1)[flat_valid]
+    uniq, inv = torch.unique(keys, return_inverse=True)
+    n = uniq.numel()
+    first_min = torch.full((n,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=keys.device)
+    first_min = first_min.scatter_reduce(0, inv, first, reduce="amin", include_self=True)
+    hash_u = torch.zeros(n, dtype=torch.int64, device=keys.device).scatter(0, inv, hsh)
+    by_first = torch.argsort(first_min)                      # insertion order of the reference's set
+    if order == "py2set":
+        perm = py2_order_fn(hash_u[by_first].cpu().numpy())  # slot order of the CPython-2.7 set
+        col_to_uniq = by_first[torch.as_tensor(np.asarray(perm, dtype=np.int64), device=keys.device)]
+    else:
+        col_to_uniq = by_first
+    col_of_uniq = torch.empty(n, dtype=torch.int64, device=keys.device)
+    col_of_uniq[col_to_uniq] = torch.arange(n, dtype=torch.int64, device=keys.device)
+    col_flat = torch.full(flat_valid.shape, -1, dtype=torch.int64, device=keys.device)
+    col_flat[flat_valid] = col_of_uniq[inv]
+    return n, col_flat.reshape(valid_all.shape), uniq[col_to_uniq]
+
+
+# --------------------------------------------------------------------------------------------- the step
+class StepResult(object):
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _all_gather_i64(torch, dist, values, device):
+    t = torch.tensor(values, dtype=torch.int64, device=device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return torch.stack(out).cpu().numpy()
+
+
+def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set"):
+    """One pass of the path on this rank's shard + the cross-rank exchanges.  `shard` implements the backend
+    interface (see CudaShard).  Returns a StepResult; the merged matrix lives on rank 0 (shard.merged)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_frag, n_bc = shard.decode()
+    # 1. histogram
+    hist, maxc = shard.window_histogram()                    # int64 tensor view [cap], local largest count
+    mx = torch.tensor([maxc], dtype=torch.int64, device=device)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    gmax = int(mx.item())
+    bins = hist[: gmax + 1]
+    dist.all_reduce(bins, op=dist.ReduceOp.SUM)
+    threshold, params = shard.fit(gmax, odds_ratio)
+    # 2. peaks, row / line bases
+    n_peaks = shard.call_peaks()
+    counts = _all_gather_i64(torch, dist, [n_peaks, n_frag, n_bc], device)
+    row_base = int(counts[:rank, 0].sum())
+    total_rows = int(counts[:, 0].sum())
+    line_base = int(counts[:rank, 1].sum())
+    shard.set_row_offset(row_base, total_rows)
+    # 3. barcode dictionary
+    keys, first, hsh = shard.barcode_table()                 # int64 tensors [n_bc]
+    max_b = int(counts[:, 2].max())
+    pad = torch.zeros((3, max(max_b, 1)), dtype=torch.int64, device=device)
+    pad[0, :n_bc] = keys
+    pad[1, :n_bc] = first + line_base
+    pad[2, :n_bc] = hsh
+    gathered = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad)
+    g = torch.stack(gathered)                                # [world, 3, maxB]
+    valid = torch.arange(max(max_b, 1), device=device)[None, :] < torch.as_tensor(counts[:, 2], device=device)[:, None]
+    n_cols, col_of, col_keys = global_columns(torch, g[:, 0], g[:, 1], g[:, 2], valid, shard.py2_order, order)
+    c2d = torch.full((max(n_cols, 1),), -1, dtype=torch.int32, device=device)
+    mine = col_of[rank, :n_bc]
+    c2d[mine] = torch.arange(n_bc, dtype=torch.int32, device=device)
+    shard.set_column_map(n_cols, c2d)
+    # 4. local CSC over the global columns, gathered to rank 0
+    indptr, indices, data = shard.peak_matrix(n_cols)        # tensors (views) on `device`
+    nnz = int(indices.numel())
+    nnz_all = _all_gather_i64(torch, dist, [nnz], device)[:, 0]
+    total_nnz = int(nnz_all.sum())
+    if rank == 0:
+        indptr_all = torch.empty(world * (n_cols + 1), dtype=torch.int64, device=device)
+        indices_all = torch.empty(max(total_nnz, 1), dtype=torch.int64, device=device)
+        data_all = torch.empty(max(total_nnz, 1), dtype=torch.int32, device=device)
+        offs = np.concatenate(([0], np.cumsum(nnz_all)))
+        indptr_all[: n_cols + 1] = indptr
+        indices_all[: nnz] = indices
+        data_all[: nnz] = data
+        for r in range(1, world):
+            dist.recv(indptr_all[r * (n_cols + 1):(r + 1) * (n_cols + 1)], src=r)
+            if nnz_all[r] > 0:
+                dist.recv(indices_all[offs[r]:offs[r + 1]], src=r)
+                dist.recv(data_all[offs[r]:offs[r + 1]], src=r)
+        rank_off = torch.as_tensor(offs[:-1].astype(np.int64), device=device)
+        shard.merge(world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz)
+    else:
+        dist.send(indptr.contiguous(), dst=0)
+        if nnz > 0:
+            dist.send(indices.contiguous(), dst=0)
+            dist.send(data.contiguous(), dst=0)
+    return StepResult(n_fragments=int(counts[:, 1].sum()), n_fragments_local=n_frag, n_barcodes=n_cols, threshold=threshold,
+                      params=params, n_peaks=total_rows, n_peaks_local=n_peaks, row_base=row_base, nnz=total_nnz, nnz_local=nnz,
+                      col_keys=col_keys, em_iterations=getattr(shard, "em_iterations", 0),
+                      em_inner_iterations=getattr(shard, "em_inner_iterations", 0), n_hits=getattr(shard, "n_hits", 0))
+
+
+# --------------------------------------------------------------------------------------------- CUDA backend
+class _DevArray(object):
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def dev_tensor(torch, ptr, n, typestr, device):
+    if n == 0:
+        dt = {"<i8": torch.int64, "<i4": torch.int32}[typestr]
+        return torch.empty(0, dtype=dt, device=device)
+    return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+
+
+class CudaShard(object):
+    """Backend of step() on one GPU: every compute call goes through libcratac (cratac._ffi.Context)."""
+
+    def __init__(self, ctx, torch, device, text_dev_ptr=None, text_host=None, nbytes=0):
+        self.ctx, self.torch, self.device = ctx, torch, device
+        self.text_dev_ptr, self.text_host, self.nbytes = text_dev_ptr, text_host, nbytes
+        self.merged = None
+
+    def decode(self):
+        if self.text_dev_ptr is not None:
+            return self.ctx.decode_device(self.text_dev_ptr, self.nbytes)
+        return self.ctx.decode_host(self.text_host)
+
+    def window_histogram(self):
+        self.ctx.window_histogram()
+        sp, ns = self.ctx.status_device()
+        self.status = dev_tensor(self.torch, sp, ns, "<i8", self.device)
+        hp, cap = self.ctx.hist_device()
+        return dev_tensor(self.torch, hp, cap, "<i8", self.device), int(self.status[6].item())
+
+    def fit(self, global_max, odds_ratio):
+        self.status[6] = global_max
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.compact_histogram()
+        thr, params, _ = self.ctx.fit_threshold_device(odds_ratio)
+        self.em_iterations = int(self.status[15].item())
+        self.em_inner_iterations = int(self.status[16].item())
+        return thr, params
+
+    def call_peaks(self):
+        c, s, e = self.ctx.call_peaks(None)
+        self.peaks = (c, s, e)
+        return len(s)
+
+    def set_row_offset(self, base, total):
+        self.ctx.set_row_offset(base, total)
+
+    def barcode_table(self):
+        k, f, h, n = self.ctx.barcode_table_device()
+        t = self.torch
+        return (dev_tensor(t, k, n, "<i8", self.device).clone(), dev_tensor(t, f, n, "<i8", self.device).clone(),
+                dev_tensor(t, h, n, "<i8", self.device).clone())
+
+    def py2_order(self, hashes):
+        from . import _ffi
+        return _ffi.py2_set_order_hashes(hashes)
+
+    def set_column_map(self, n_cols, c2d):
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.set_column_map(n_cols, c2d.data_ptr())
+
+    def peak_matrix(self, n_cols):
+        nnz, ip, ix, dt = self.ctx.peak_matrix_device()
+        t = self.torch
+        data = dev_tensor(t, dt, nnz, "<i4", self.device)
+        self.n_hits = int(data.sum(dtype=t.int64).item()) if nnz else 0
+        return dev_tensor(t, ip, n_cols + 1, "<i8", self.device), dev_tensor(t, ix, nnz, "<i8", self.device), data
+
+    def merge(self, world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz):
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.merge_rank_csc(world, n_cols, indptr_all.data_ptr(), rank_off.data_ptr(), indices_all.data_ptr(), data_all.data_ptr(), total_nnz)
+        self.merged = (n_cols, total_nnz)

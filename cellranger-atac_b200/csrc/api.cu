@@ -55,6 +55,11 @@ int sync_status(Ctx* c) {
 }
 
 int pileup_tile_bases();                                                                 // pileup.cu
+int compact_histogram(Ctx* c);                                                           // pileup.cu
+int offset_peak_rows(Ctx* c, int64_t base);                                              // pileup.cu
+void py2_set_order_hashes(const long long* hashes, int64_t n, std::vector<int32_t>& order);   // decode.cu
+int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off, const int64_t* d_indices_all,
+                   const int32_t* d_data_all, int64_t total_nnz);                         // matrix.cu
 int dump_window_counts(Ctx* c, int contig, int32_t* d_W);                                // pileup.cu
 int compute_max_len(Ctx* c);                                                             // decode.cu
 int fit_threshold_arrays(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n, double odds_ratio);   // em.cu
@@ -147,7 +152,7 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_em_params, &c->d_em_work, &c->d_chain, &c->d_tile_summary, &c->d_run_start, &c->d_run_end, &c->d_bridge, &c->d_fill,
                       &c->d_peak_chrom, &c->d_peak_start, &c->d_peak_end, &c->d_peak_row, &c->d_peak_off, &c->d_bc_hits, &c->d_seg_off,
                       &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
-                      &c->d_status, &c->d_scan_tmp};
+                      &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_bc_hash) cudaFreeHost(c->h_bc_hash);
@@ -528,7 +533,7 @@ int cratac_peak_matrix(cratac_ctx* h, int64_t* nnz) {
 int cratac_get_matrix(cratac_ctx* h, int64_t* indptr, int64_t* indices, int32_t* data) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
-    if (indptr) CRATAC_CUDA(cudaMemcpyAsync(indptr, c->d_indptr.p, 8 * (size_t)(c->n_barcodes + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (indptr) CRATAC_CUDA(cudaMemcpyAsync(indptr, c->d_indptr.p, 8 * (size_t)(c->n_cols + 1), cudaMemcpyDeviceToHost, c->stream));
     if (indices && c->nnz > 0) CRATAC_CUDA(cudaMemcpyAsync(indices, c->d_indices.p, 8 * (size_t)c->nnz, cudaMemcpyDeviceToHost, c->stream));
     if (data && c->nnz > 0) CRATAC_CUDA(cudaMemcpyAsync(data, c->d_data.p, 4 * (size_t)c->nnz, cudaMemcpyDeviceToHost, c->stream));
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
@@ -612,6 +617,81 @@ int cratac_run_from_fragments(cratac_ctx* h, double odds_ratio, cratac_run_resul
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
     return run_tail(c, odds_ratio, result);
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU building blocks
+// (one process per GPU; the exchanges themselves are NCCL calls made by the host code on these device buffers)
+int cratac_status_device(cratac_ctx* h, int64_t** d_status, int64_t* n_slots) {
+    if (d_status) *d_status = h->c.d_status.as<int64_t>();
+    if (n_slots) *n_slots = ST_SLOTS;
+    return CRATAC_OK;
+}
+
+// pileup + window + histogram for this shard's contigs; the histogram (cratac_hist_device) and the largest
+// count (status slot 6) stay on the device for the all-reduce
+int cratac_window_histogram(cratac_ctx* h) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(window_histogram(c));
+    return sync_status(c);
+}
+
+// re-derive the compact (value, weight) arrays from the (all-reduced) device histogram
+int cratac_compact_histogram(cratac_ctx* h) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(compact_histogram(c));
+    return sync_status(c);
+}
+
+// barcode dictionary of this shard by dense id: 64-bit keys, first line (shard-local), CPython-2.7 hash
+int cratac_barcode_table_device(cratac_ctx* h, const uint64_t** d_keys, const uint64_t** d_first, const int64_t** d_py2hash, int64_t* n) {
+    Ctx* c = &h->c;
+    if (!c->bc_is_slot) { set_error("barcode table is only available after a decode"); return CRATAC_ERR_ARG; }
+    if (d_keys) *d_keys = c->d_dense_bckey.as<uint64_t>();
+    if (d_first) *d_first = c->d_dense_first.as<uint64_t>();
+    if (d_py2hash) *d_py2hash = c->d_dense_key.as<int64_t>();
+    if (n) *n = c->n_barcodes;
+    return CRATAC_OK;
+}
+
+// matrix columns = a global barcode list: d_col_to_dense[j] = this shard's dense barcode id of column j, or -1
+int cratac_set_column_map(cratac_ctx* h, int64_t n_cols, const int32_t* d_col_to_dense) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (n_cols < 0) { c->global_cols = false; c->n_global_cols = 0; return CRATAC_OK; }
+    CRATAC_TRY(c->d_global_c2d.reserve(4 * (size_t)std::max<int64_t>(n_cols, 1)));
+    if (n_cols > 0) CRATAC_CUDA(cudaMemcpyAsync(c->d_global_c2d.p, d_col_to_dense, 4 * (size_t)n_cols, cudaMemcpyDeviceToDevice, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->global_cols = true;
+    c->n_global_cols = n_cols;
+    return CRATAC_OK;
+}
+
+// this shard's peaks are rows [row_base, row_base + n_peaks) of a matrix with total_rows rows
+int cratac_set_row_offset(cratac_ctx* h, int64_t row_base, int64_t total_rows) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(fetch_peak_count(c));
+    c->row_range = total_rows;
+    return offset_peak_rows(c, row_base);
+}
+
+// rank 0: column blocks of all shards (gathered into contiguous device buffers) -> the final CSC of this context
+int cratac_merge_rank_csc(cratac_ctx* h, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off,
+                          const int64_t* d_indices_all, const int32_t* d_data_all, int64_t total_nnz) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return merge_rank_csc(c, world, n_cols, d_indptr_all, d_rank_off, d_indices_all, d_data_all, total_nnz);
+}
+
+// CPython-2.7 list(set) order from the string hashes alone (distinct keys, insertion order)
+int cratac_py2_set_order_hashes(int64_t n, const int64_t* hashes, int32_t* order_out) {
+    std::vector<int32_t> order;
+    py2_set_order_hashes(reinterpret_cast<const long long*>(hashes), n, order);
+    if ((int64_t)order.size() != n) { set_error("cratac_py2_set_order_hashes: internal error"); return CRATAC_ERR_INTERNAL; }
+    for (int64_t i = 0; i < n; i++) order_out[i] = order[i];
+    return CRATAC_OK;
 }
 
 // ------------------------------------------------------------------------------------------ host helpers

@@ -137,6 +137,12 @@ struct Ctx {
     DevBuf d_indptr, d_indices, d_data;
     int64_t nnz = 0;
     int64_t n_hits = 0;
+    int64_t n_cols = 0;                    // columns of the current matrix (= n_barcodes unless a global column map is set)
+    // multi-GPU: global column map / row range
+    bool global_cols = false;
+    int64_t n_global_cols = 0;
+    int64_t row_range = 0;                 // rows of the global matrix (0 = the local peak count)
+    DevBuf d_global_c2d, d_nnz_ordered, d_dense_bckey;
     // misc
     DevBuf d_status;                       // int64[ST_SLOTS]
     DevBuf d_scan_tmp;

@@ -387,7 +387,7 @@ __global__ void k_max_len(const int32_t* __restrict__ start, const int32_t* __re
 __global__ void k_table_compact(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ first,
                                 const long long* __restrict__ textoff, int cap, int32_t* __restrict__ slot_to_dense,
                                 unsigned long long* __restrict__ dense_first, long long* __restrict__ dense_textoff,
-                                unsigned long long* counter) {
+                                unsigned long long* __restrict__ dense_bckey, unsigned long long* counter) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= cap) return;
     if (keys[s] == BC_EMPTY) { slot_to_dense[s] = -1; return; }
@@ -395,6 +395,7 @@ __global__ void k_table_compact(const unsigned long long* __restrict__ keys, con
     slot_to_dense[s] = (int32_t)d;
     dense_first[d] = first[s];
     dense_textoff[d] = textoff[s];
+    dense_bckey[d] = keys[s];
 }
 
 __global__ void k_gather_barcode_text(const char* __restrict__ text, const long long* __restrict__ dense_textoff, int64_t n,
@@ -484,6 +485,7 @@ static int barcode_prepare_device(Ctx* c) {
     size_t nn = (size_t)std::max<int64_t>(nb, 1);
     CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
     CRATAC_TRY(c->d_dense_key.reserve(8 * nn));                 // py2 hashes by dense id
+    CRATAC_TRY(c->d_dense_bckey.reserve(8 * nn));               // 64-bit barcode keys by dense id
     CRATAC_TRY(c->d_dense_to_col.reserve(4 * nn)); CRATAC_TRY(c->d_col_to_dense.reserve(4 * nn));
     const int64_t n_words = (n + 31) / 32 + 1;
     CRATAC_TRY(c->d_bc_bitmap.reserve(16 * (size_t)n_words + 12 * nn + 64));
@@ -498,7 +500,7 @@ static int barcode_prepare_device(Ctx* c) {
     k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<unsigned long long>(), c->d_bc_first.as<unsigned long long>(),
                                                                c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
                                                                c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
-                                                               reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
+                                                               c->d_dense_bckey.as<unsigned long long>(), reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
     c->launches++;
     if (nb > 0) {
         unsigned g = (unsigned)((nb + 255) / 256);

@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
 }
 
 // ---- K8 -------------------------------------------------------------------------------------------
-__global__ void k_gather_nnz(const int32_t* __restrict__ nnz_col, const int32_t* __restrict__ col_to_dense, int64_t n_bc, int32_t* __restrict__ out) {
+__global__ void k_gather_nnz(const int32_t* __restrict__ nnz_col, const int32_t* __restrict__ col_to_dense, int64_t n_cols, int32_t* __restrict__ out) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_bc) out[j] = nnz_col[col_to_dense ? col_to_dense[j] : j];
+    if (j >= n_cols) return;
+    int64_t d = col_to_dense ? col_to_dense[j] : j;
+    out[j] = d >= 0 ? nnz_col[d] : 0;       // d < 0: the barcode of this (global) column does not occur in this shard
 }
 
 // one warp per column
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(256) k_csc_copy(const int32_t* __restrict__ ou
     int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t j = warp; j < n_bc; j += n_warps) {
         int64_t d = col_to_dense ? col_to_dense[j] : j;
+        if (d < 0) continue;
         int64_t src = seg_off[d], dst = indptr[j], len = indptr[j + 1] - dst;
         for (int64_t k = lane; k < len; k += 32) {
             indices[dst + k] = (int64_t)out_row[src + k];
@@ -200,6 +203,57 @@ __global__ void __launch_bounds__(256) k_csc_copy(const int32_t* __restrict__ ou
 }
 
 int build_barcodes(Ctx* c);   // decode.cu
+
+// ---- multi-GPU: column blocks of the shards (same global columns, disjoint ascending row ranges) -> one CSC
+__global__ void k_merge_counts(const int64_t* __restrict__ indptr_all, int world, int64_t n_cols, int32_t* __restrict__ cnt) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    int64_t t = 0;
+    for (int r = 0; r < world; r++) { const int64_t* ip = indptr_all + (int64_t)r * (n_cols + 1); t += ip[j + 1] - ip[j]; }
+    cnt[j] = (int32_t)t;
+}
+__global__ void __launch_bounds__(256) k_merge_copy(const int64_t* __restrict__ indptr_all, const int64_t* __restrict__ rank_off, int world, int64_t n_cols,
+                                                    const int64_t* __restrict__ indices_all, const int32_t* __restrict__ data_all,
+                                                    const int64_t* __restrict__ indptr, int64_t* __restrict__ indices, int32_t* __restrict__ data) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < n_cols; j += n_warps) {
+        int64_t dst = indptr[j];
+        for (int r = 0; r < world; r++) {       // rank order = genome order = ascending rows
+            const int64_t* ip = indptr_all + (int64_t)r * (n_cols + 1);
+            int64_t src = rank_off[r] + ip[j], len = ip[j + 1] - ip[j];
+            for (int64_t k = lane; k < len; k += 32) { indices[dst + k] = indices_all[src + k]; data[dst + k] = data_all[src + k]; }
+            dst += len;
+        }
+    }
+}
+
+int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off, const int64_t* d_indices_all,
+                   const int32_t* d_data_all, int64_t total_nnz) {
+    cudaStream_t s = c->stream;
+    size_t ncc = (size_t)std::max<int64_t>(n_cols, 1);
+    CRATAC_TRY(c->d_indptr.reserve(8 * (ncc + 1)));
+    CRATAC_TRY(c->d_nnz_ordered.reserve(4 * ncc));
+    size_t zz = (size_t)std::max<int64_t>(total_nnz, 1);
+    CRATAC_TRY(c->d_indices.reserve(8 * zz)); CRATAC_TRY(c->d_data.reserve(4 * zz));
+    if (n_cols > 0) {
+        k_merge_counts<<<(unsigned)((n_cols + 255) / 256), 256, 0, s>>>(d_indptr_all, world, n_cols, c->d_nnz_ordered.as<int32_t>());
+        c->launches++;
+    }
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_nnz_ordered.as<int32_t>(), c->d_indptr.as<int64_t>(), n_cols, c->d_indptr.as<int64_t>() + n_cols));
+    if (n_cols > 0) {
+        int g = (int)std::min<int64_t>((n_cols * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
+        k_merge_copy<<<g, 256, 0, s>>>(d_indptr_all, d_rank_off, world, n_cols, d_indices_all, d_data_all, c->d_indptr.as<int64_t>(),
+                                      c->d_indices.as<int64_t>(), c->d_data.as<int32_t>());
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    c->nnz = total_nnz;
+    c->n_cols = n_cols;
+    return CRATAC_OK;
+}
 
 int peak_matrix_device(Ctx* c) {
     cudaStream_t s = c->stream;
@@ -230,7 +284,7 @@ int peak_matrix_device(Ctx* c) {
     // matrix column order: host work (CPython-2.7 set emulation over the barcode hashes) overlaps the kernels
     // queued so far (pileup, fit, peaks, overlap count)
     c->host_mark("matrix_launch");
-    CRATAC_TRY(build_barcodes(c));
+    if (!c->global_cols) CRATAC_TRY(build_barcodes(c));
     c->host_mark("build_barcodes");
     // K (total hits) sizes the hit buffers: one host round trip here (8 bytes)
     CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
@@ -247,7 +301,6 @@ int peak_matrix_device(Ctx* c) {
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     int32_t* nnz_col = c->d_nnz_col.as<int32_t>();
-    int32_t* nnz_ordered = nnz_col + nbb;
     if (nb > 0) {
         static bool configured = false;
         if (!configured) {
@@ -260,27 +313,35 @@ int peak_matrix_device(Ctx* c) {
         c->stage_end(SG_REDUCE_SMALL);
         c->stage_begin(SG_REDUCE_LARGE);
         int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
-        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4, s>>>(a.hits, a.seg_off, nb, st, c->peaks_on_device_count ? -1 : c->n_peaks,
+        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4, s>>>(a.hits, a.seg_off, nb, st,
+                                                                 c->row_range > 0 ? c->row_range : (c->peaks_on_device_count ? -1 : c->n_peaks),
                                                                  c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_LARGE);
         c->launches += 2;
         CRATAC_CUDA(cudaGetLastError());
     }
-    const int32_t* c2d = c->d_col_to_dense.as<int32_t>();
-    if (nb > 0) {
-        k_gather_nnz<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(nnz_col, c2d, nb, nnz_ordered);
+    // columns: the shard's own barcodes in matrix order, or the global column map of a multi-GPU run
+    const int32_t* c2d = c->global_cols ? c->d_global_c2d.as<int32_t>() : c->d_col_to_dense.as<int32_t>();
+    const int64_t n_cols = c->global_cols ? c->n_global_cols : nb;
+    c->n_cols = n_cols;
+    size_t ncc = (size_t)std::max<int64_t>(n_cols, 1);
+    CRATAC_TRY(c->d_indptr.reserve(8 * (ncc + 1)));
+    CRATAC_TRY(c->d_nnz_ordered.reserve(4 * ncc));
+    int32_t* nnz_ordered = c->d_nnz_ordered.as<int32_t>();
+    if (n_cols > 0) {
+        k_gather_nnz<<<(unsigned)((n_cols + 255) / 256), 256, 0, s>>>(nnz_col, c2d, n_cols, nnz_ordered);
         c->launches++;
     }
-    CRATAC_TRY(exclusive_scan_i32_to_i64(c, nnz_ordered, c->d_indptr.as<int64_t>(), nb, c->d_indptr.as<int64_t>() + nb));
-    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_NNZ], c->d_indptr.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, nnz_ordered, c->d_indptr.as<int64_t>(), n_cols, c->d_indptr.as<int64_t>() + n_cols));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_NNZ], c->d_indptr.as<int64_t>() + n_cols, 8, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
     c->nnz = c->h_status[ST_NNZ];
     size_t zz = (size_t)std::max<int64_t>(c->nnz, 1);
     CRATAC_TRY(c->d_indices.reserve(8 * zz)); CRATAC_TRY(c->d_data.reserve(4 * zz));
-    if (nb > 0) {
-        int g = (int)std::min<int64_t>((nb * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
+    if (n_cols > 0) {
+        int g = (int)std::min<int64_t>((n_cols * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
         c->stage_begin(SG_CSC_BUILD);
-        k_csc_copy<<<g, 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d, c->d_indptr.as<int64_t>(), nb,
+        k_csc_copy<<<g, 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d, c->d_indptr.as<int64_t>(), n_cols,
                                     c->d_indices.as<int64_t>(), c->d_data.as<int32_t>());
         c->stage_end(SG_CSC_BUILD);
         c->launches++;

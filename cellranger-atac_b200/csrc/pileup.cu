@@ -493,6 +493,31 @@ int window_histogram(Ctx* c) {
     return CRATAC_OK;
 }
 
+// re-run the histogram compaction (after a cross-rank all-reduce of d_hist / ST_MAX_COUNT)
+int compact_histogram(Ctx* c) {
+    int64_t* st = c->d_status.as<int64_t>();
+    c->stage_begin(SG_HIST_COMPACT);
+    k_hist_compact<<<1, 1024, 0, c->stream>>>(c->d_hist.as<unsigned long long>(), st, c->d_hist_values.as<int64_t>(), c->d_hist_weights.as<int64_t>(), HIST_CAP);
+    c->stage_end(SG_HIST_COMPACT);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+__global__ void k_offset_rows(int32_t* __restrict__ pk_row, int64_t n, int32_t base) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pk_row[i] = (int32_t)i + base;
+}
+// matrix rows of this shard's peaks start at `base` in the global matrix
+int offset_peak_rows(Ctx* c, int64_t base) {
+    if (c->n_peaks > 0) {
+        k_offset_rows<<<(unsigned)((c->n_peaks + 255) / 256), 256, 0, c->stream>>>(c->d_peak_row.as<int32_t>(), c->n_peaks, (int32_t)base);
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    return CRATAC_OK;
+}
+
 int dump_window_counts(Ctx* c, int contig, int32_t* d_W) {
     PileupArgs a;
     fill_args(c, a);
@@ -575,6 +600,7 @@ int call_peaks_device(Ctx* c) {
         break;
     }
     c->peaks_on_device_count = true;
+    c->row_range = 0;
     return CRATAC_OK;
 }
 

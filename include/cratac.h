@@ -148,6 +148,20 @@ int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_de
 /* same, starting from fragments already decoded in this context (SoA resident in HBM) */
 int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_result* result);
 
+/* ---- multi-GPU building blocks (one process per GPU, genome sharded by contiguous contig ranges; the
+ *      exchanges are NCCL calls made by the host on these device buffers).  They replace the file-based
+ *      merges of the reference: `Counter +=` (count_cut_sites/__init__.py:77-81) and `hstack`
+ *      (generate_peak_matrix/__init__.py:62-72). */
+int cratac_status_device(cratac_ctx* ctx, int64_t** d_status, int64_t* n_slots);   /* slot 6 = max window count, 10 = n_peaks */
+int cratac_window_histogram(cratac_ctx* ctx);
+int cratac_compact_histogram(cratac_ctx* ctx);
+int cratac_barcode_table_device(cratac_ctx* ctx, const uint64_t** d_keys, const uint64_t** d_first, const int64_t** d_py2hash, int64_t* n);
+int cratac_set_column_map(cratac_ctx* ctx, int64_t n_cols, const int32_t* d_col_to_dense);   /* n_cols < 0 resets */
+int cratac_set_row_offset(cratac_ctx* ctx, int64_t row_base, int64_t total_rows);
+int cratac_merge_rank_csc(cratac_ctx* ctx, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off,
+                          const int64_t* d_indices_all, const int32_t* d_data_all, int64_t total_nnz);
+int cratac_py2_set_order_hashes(int64_t n, const int64_t* hashes, int32_t* order_out);
+
 /* ---- host helpers */
 /* CPython-2.7 list(set(keys)) order for `n` NUL-terminated strings given in insertion order:
  * order_out[j] = index of the key at column j (generate_peak_matrix/__init__.py:44). */

@@ -364,3 +364,26 @@ def test_whole_path_fitted_threshold():
     frags = synth.generate(contigs, 350000, 60, 900, seed=22, background_factor=5)
     res = _run_and_compare(contigs, ["chr1", "chr2"], synth.to_text(frags))
     assert res.has_params == 1 and res.n_peaks > 100 and res.em_iterations > 0
+
+
+# ----------------------------------------------------------------------------- multi-GPU path
+def _run_multi_check(nproc):
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(__file__), "multi_gpu_check.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", script]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_GPU_CHECK" in out.stdout and " OK " in out.stdout, out.stdout[-3000:]
+
+
+def test_multi_step_one_rank_equals_single_context():
+    """The sharded path with world_size 1 (NCCL): exchanges degenerate, merge kernels still run."""
+    _run_multi_check(1)
+
+
+def test_multi_step_two_ranks_equals_single_context():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_multi_check(2)

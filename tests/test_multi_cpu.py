@@ -1,0 +1,162 @@
+"""The N>1 exchange logic (cratac/multi.py) on CPU with gloo, world_size 2: the per-shard compute is played by
+the oracle, the exchanges (histogram all-reduce, row/line bases, barcode union, CSC gather + merge) are the
+product code.  The merged result must equal the single-process oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util
+from cratac import _ffi, multi, synth
+from oracle import cfast, em as oracle_em, py2set
+
+
+def test_partition_contigs():
+    lens = [c[1] for c in synth.GRCH38]
+    for world in (1, 2, 4, 8):
+        parts = multi.partition_contigs(lens, world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(lens)
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        loads = [sum(lens[a:b]) for a, b in parts]
+        assert max(loads) <= 1.25 * sum(lens) / world        # contiguous ranges stay within 25 % of perfect balance
+    assert multi.partition_contigs([5, 5], 4)[-1][1] == 2
+
+
+class OracleShard(object):
+    """multi.step backend whose compute is the CPU oracle (tests only)."""
+
+    def __init__(self, contigs, primary, text, first_contig):
+        self.contigs, self.primary, self.text, self.first_contig = contigs, primary, text, first_contig
+        self.names = [c[0] for c in contigs]
+
+    def decode(self):
+        o = util.oracle_decode(self.text, self.names)
+        self.o = o
+        self.bc_list = o["first_seen"]
+        self.bc_id = {b: i for i, b in enumerate(self.bc_list)}
+        self.frag_bc = np.array([self.bc_id[b] for b in o["barcodes"]], dtype=np.int64)
+        first = {}
+        for i, b in enumerate(o["barcodes"]):
+            first.setdefault(b, i)
+        self.first = np.array([first[b] for b in self.bc_list], dtype=np.int64)
+        return o["start"].size, len(self.bc_list)
+
+    def window_histogram(self):
+        h = util.oracle_hist(self.contigs, self.primary, self.o["chrom"], self.o["start"], self.o["end"])
+        cap = 1 << 14
+        self.hist = torch.zeros(cap, dtype=torch.int64)
+        for v, w in h.items():
+            self.hist[v] = w
+        return self.hist, max(h) if h else 0
+
+    def fit(self, gmax, odds):
+        cd = {int(v): int(self.hist[v]) for v in range(1, gmax + 1) if int(self.hist[v]) > 0}
+        thr, params = oracle_em.estimate_final_threshold(cd, odds)
+        self.thr = int(thr)
+        return self.thr, params
+
+    def call_peaks(self):
+        self.peaks = util.oracle_peaks(self.contigs, self.primary, self.o["chrom"], self.o["start"], self.o["end"], self.thr)
+        return len(self.peaks)
+
+    def set_row_offset(self, base, total):
+        self.row_base, self.total_rows = base, total
+
+    def barcode_table(self):
+        # any injective 64-bit key works for the union; use the low 63 bits of the CPython-2.7 hash pair
+        keys = np.array([(py2set.py2_str_hash(b) ^ (len(b) << 50)) & ((1 << 62) - 1) for b in self.bc_list], dtype=np.int64)
+        assert len(set(keys.tolist())) == len(keys)
+        hashes = np.array([py2set.py2_str_hash(b) for b in self.bc_list], dtype=np.int64)
+        return torch.from_numpy(keys), torch.from_numpy(self.first.copy()), torch.from_numpy(hashes)
+
+    def py2_order(self, hashes):
+        return _ffi.py2_set_order_hashes(hashes)             # host-only entry point of libcratac
+
+    def set_column_map(self, n_cols, c2d):
+        self.n_cols, self.c2d = n_cols, c2d.numpy().copy()
+
+    def peak_matrix(self, n_cols):
+        d2c = np.full(len(self.bc_list), -1, dtype=np.int64)
+        for j, d in enumerate(self.c2d[:n_cols]):
+            if d >= 0:
+                d2c[d] = j
+        indptr, indices, data = util.oracle_matrix(len(self.contigs), self.peaks, self.o["chrom"], self.o["start"], self.o["end"],
+                                                   d2c[self.frag_bc].astype(np.int32), n_cols)
+        return torch.from_numpy(indptr), torch.from_numpy(indices + self.row_base), torch.from_numpy(data.astype(np.int32))
+
+    def merge(self, world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz):
+        ip = indptr_all.numpy().reshape(world, n_cols + 1)
+        cnt = (ip[:, 1:] - ip[:, :-1]).sum(axis=0)
+        indptr = np.concatenate(([0], np.cumsum(cnt)))
+        indices = np.zeros(total_nnz, dtype=np.int64)
+        data = np.zeros(total_nnz, dtype=np.int32)
+        for j in range(n_cols):
+            dst = indptr[j]
+            for r in range(world):
+                s, e = int(rank_off[r]) + ip[r, j], int(rank_off[r]) + ip[r, j + 1]
+                indices[dst:dst + e - s] = indices_all.numpy()[s:e]
+                data[dst:dst + e - s] = data_all.numpy()[s:e]
+                dst += e - s
+        self.merged = (indptr, indices, data)
+
+
+def _dataset():
+    contigs = [("chr1", 400000), ("chr2", 250000), ("chr3", 300000), ("chr4", 120000)]
+    frags = synth.generate(contigs, 60000, 30, 120, seed=31, background_factor=4)
+    return contigs, frags
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    contigs, frags = _dataset()
+    parts = multi.partition_contigs([c[1] for c in contigs], world)
+    a, b = parts[rank]
+    m = (frags["chrom"] >= a) & (frags["chrom"] < b)
+    sub = {k: (v[m] if isinstance(v, np.ndarray) else v) for k, v in frags.items()}
+    text = synth.to_text(sub)
+    shard = OracleShard(contigs, [c[0] for c in contigs[a:b]], text, a)
+    res = multi.step(shard, torch, dist, torch.device("cpu"))
+    if rank == 0:
+        indptr, indices, data = shard.merged
+        np.savez(os.path.join(out_dir, "merged.npz"), indptr=indptr, indices=indices, data=data, threshold=res.threshold,
+                 n_peaks=res.n_peaks, n_cols=res.n_barcodes, col_keys=res.col_keys.numpy())
+    # every rank reports its peaks for the global peak list
+    np.save(os.path.join(out_dir, "peaks_%d.npy" % rank), np.array(shard.peaks, dtype=np.int64).reshape(-1, 3))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_matches_single_process_oracle(tmp_path):
+    world = 2
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(str(tmp_path / "merged.npz"))
+    # single-process oracle on the whole dataset
+    contigs, frags = _dataset()
+    names = [c[0] for c in contigs]
+    text = synth.to_text(frags)
+    o = util.oracle_decode(text, names)
+    hist = util.oracle_hist(contigs, names, o["chrom"], o["start"], o["end"])
+    thr, _ = oracle_em.estimate_final_threshold(hist, 0.2)
+    assert int(got["threshold"]) == int(thr)
+    peaks = util.oracle_peaks(contigs, names, o["chrom"], o["start"], o["end"], int(thr))
+    shard_peaks = np.concatenate([np.load(str(tmp_path / ("peaks_%d.npy" % r))) for r in range(world)])
+    assert [tuple(p) for p in shard_peaks.tolist()] == peaks and int(got["n_peaks"]) == len(peaks)
+    cols = util.oracle_columns(o["first_seen"])              # CPython-2.7 order over the WHOLE file
+    assert int(got["n_cols"]) == len(cols)
+    want_keys = [(py2set.py2_str_hash(b) ^ (len(b) << 50)) & ((1 << 62) - 1) for b in cols]
+    assert got["col_keys"].tolist() == want_keys
+    col_id = {b: j for j, b in enumerate(cols)}
+    fcol = np.array([col_id[b] for b in o["barcodes"]], dtype=np.int32)
+    oip, oix, od = util.oracle_matrix(len(contigs), peaks, o["chrom"], o["start"], o["end"], fcol, len(cols))
+    assert np.array_equal(got["indptr"], oip) and np.array_equal(got["indices"], oix) and np.array_equal(got["data"], od)
