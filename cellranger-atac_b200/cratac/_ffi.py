@@ -68,6 +68,7 @@ SIGNATURES = {
     "cratac_fit_threshold": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, P(c_dbl), P(c_int), P(c_i64), P(c_i64), P(c_i64)]),
     "cratac_fit_threshold_device": (c_int, [c_vp, c_dbl, P(c_dbl), P(c_int), P(c_i64)]),
     "cratac_call_peaks": (c_int, [c_vp, c_i64, P(c_i64)]),
+    "cratac_peaks_from_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, P(c_i64)]),
     "cratac_get_peaks": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cratac_set_peaks": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cratac_peak_matrix": (c_int, [c_vp, P(c_i64)]),
@@ -274,6 +275,15 @@ class Context(object):
     def call_peaks(self, threshold=None):
         n = c_i64()
         check(self._lib.cratac_call_peaks(self._h, -1 if threshold is None else int(threshold), ctypes.byref(n)))
+        return self.get_peaks(n.value)
+
+    def peaks_from_rows(self, chrom, start, end):
+        """Signal intervals (bedgraph rows with count >= threshold, sorted by contig, start) -> merged peaks."""
+        chrom = _i32(chrom)
+        start = np.ascontiguousarray(start, dtype=np.int64)
+        end = np.ascontiguousarray(end, dtype=np.int64)
+        n = c_i64()
+        check(self._lib.cratac_peaks_from_rows(self._h, chrom.size, _ptr(chrom), _ptr(start), _ptr(end), ctypes.byref(n)))
         return self.get_peaks(n.value)
 
     def get_peaks(self, n):

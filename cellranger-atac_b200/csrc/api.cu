@@ -57,6 +57,7 @@ int sync_status(Ctx* c) {
 int pileup_tile_bases();                                                                 // pileup.cu
 int compact_histogram(Ctx* c);                                                           // pileup.cu
 int offset_peak_rows(Ctx* c, int64_t base);                                              // pileup.cu
+int merge_runs_from_host(Ctx* c, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end);   // pileup.cu
 void py2_set_order_hashes(const long long* hashes, int64_t n, std::vector<int32_t>& order);   // decode.cu
 int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off, const int64_t* d_indices_all,
                    const int32_t* d_data_all, int64_t total_nnz);                         // matrix.cu
@@ -447,6 +448,16 @@ int cratac_call_peaks(cratac_ctx* h, int64_t threshold, int64_t* n_peaks) {
         CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     }
     CRATAC_TRY(call_peaks_with_retry(c));
+    if (n_peaks) *n_peaks = c->n_peaks;
+    return CRATAC_OK;
+}
+
+// DETECT_PEAKS.main on bedgraph rows: `n` signal intervals (count >= threshold) sorted by (contig, start)
+int cratac_peaks_from_rows(cratac_ctx* h, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end, int64_t* n_peaks) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(merge_runs_from_host(c, n, chrom, start, end));
+    CRATAC_TRY(fetch_peak_count(c));
     if (n_peaks) *n_peaks = c->n_peaks;
     return CRATAC_OK;
 }

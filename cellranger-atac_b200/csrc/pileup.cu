@@ -604,4 +604,47 @@ int call_peaks_device(Ctx* c) {
     return CRATAC_OK;
 }
 
+// Peaks from already-thresholded signal intervals (the DETECT_PEAKS stage receives bedgraph rows, not fragments):
+// rows sorted by (contig, start), merged while next.start - 500 <= cur.end (detect_peaks/__init__.py:53).
+int merge_runs_from_host(Ctx* c, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end) {
+    int64_t* st = c->d_status.as<int64_t>();
+    int64_t cap = std::max<int64_t>(n, 1);
+    CRATAC_TRY(c->d_run_start.reserve(8 * (size_t)cap)); CRATAC_TRY(c->d_run_end.reserve(8 * (size_t)cap));
+    CRATAC_TRY(c->d_bridge.reserve(4 * (size_t)cap * 2));
+    CRATAC_TRY(c->d_fill.reserve(8 * (size_t)cap));
+    CRATAC_TRY(c->d_peak_chrom.reserve(4 * (size_t)cap)); CRATAC_TRY(c->d_peak_start.reserve(4 * (size_t)cap));
+    CRATAC_TRY(c->d_peak_end.reserve(4 * (size_t)cap)); CRATAC_TRY(c->d_peak_row.reserve(4 * (size_t)cap));
+    CRATAC_TRY(c->d_peak_off.reserve(8 * (size_t)(c->n_contigs + 2)));
+    c->peak_cap = cap;
+    std::vector<int64_t> gs((size_t)cap), ge((size_t)cap);
+    for (int64_t i = 0; i < n; i++) {
+        if (chrom[i] < 0 || chrom[i] >= c->n_contigs) { set_error("row %lld: contig index out of range", (long long)i); return CRATAC_ERR_ARG; }
+        gs[i] = c->contig_base[chrom[i]] + start[i];
+        ge[i] = c->contig_base[chrom[i]] + end[i];
+        if (i > 0 && gs[i] < ge[i - 1]) { set_error("rows must be sorted by (contig, start) and disjoint (row %lld)", (long long)i); return CRATAC_ERR_UNSORTED; }
+    }
+    int32_t* bridge = c->d_bridge.as<int32_t>();
+    int32_t* head = bridge + cap;
+    int64_t* head_rank = c->d_fill.as<int64_t>();
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_run_start.p, gs.data(), 8 * (size_t)cap, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_run_end.p, ge.data(), 8 * (size_t)cap, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(bridge, 0, 4 * (size_t)cap, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_RUNS], 0, sizeof(int64_t) * 3, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(&st[ST_N_RUNS], &n, 8, cudaMemcpyHostToDevice, c->stream));
+    k_run_heads<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_run_start.as<int64_t>(), c->d_run_end.as<int64_t>(), bridge, st, cap, head);
+    c->launches++;
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, head, head_rank, cap, nullptr));
+    k_emit_peaks<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_run_start.as<int64_t>(), c->d_run_end.as<int64_t>(), head, head_rank,
+                                                                       c->d_contig_base.as<int64_t>(), c->n_contigs, st, cap,
+                                                                       c->d_peak_chrom.as<int32_t>(), c->d_peak_start.as<int32_t>(),
+                                                                       c->d_peak_end.as<int32_t>(), c->d_peak_row.as<int32_t>());
+    k_peak_offsets<<<(c->n_contigs + 1 + 127) / 128, 128, 0, c->stream>>>(c->d_peak_chrom.as<int32_t>(), st, c->n_contigs, c->d_peak_off.as<int64_t>());
+    c->launches += 2;
+    CRATAC_CUDA(cudaGetLastError());
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));   // gs / ge live on this stack frame
+    c->peaks_on_device_count = true;
+    c->row_range = 0;
+    return CRATAC_OK;
+}
+
 }  // namespace cratac

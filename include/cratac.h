@@ -120,6 +120,9 @@ int cratac_fit_threshold_device(cratac_ctx* ctx, double odds_ratio, double param
  *      lib/python/tools/regions.py:392-417 (.fai contig order, then start).  threshold < 0 uses
  *      the value fitted on the device.  The peaks become the current peak set of the context. */
 int cratac_call_peaks(cratac_ctx* ctx, int64_t threshold, int64_t* n_peaks);
+/* the same merge for the DETECT_PEAKS stage proper, whose input is the bedgraph (cut_sites) and not the fragments:
+ * `n` signal intervals = bedgraph rows with count >= threshold (lib/python/utils.py:105-115), sorted by (contig, start) */
+int cratac_peaks_from_rows(cratac_ctx* ctx, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end, int64_t* n_peaks);
 int cratac_get_peaks(cratac_ctx* ctx, int32_t* chrom, int32_t* start, int32_t* end);
 /* user-supplied peaks in peaks.bed row order (reanalyze / GENERATE_PEAK_MATRIX stage input);
  * row i of the matrix is peak i.  Touching peaks are fine, overlapping ones are an error. */

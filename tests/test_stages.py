@@ -1,0 +1,170 @@
+"""The three Martian stage modules (cellranger-atac_b200/mro/atac/stages/processing/*) driven the way Martian
+drives them (split / main / join with Record objects), plus the hand-written HDF5 / MEX writers."""
+import importlib.util
+import json
+import os
+import pickle
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import util
+from cratac import bgzf, h5, mex, refmgr, synth
+from oracle import reference_flow
+
+STAGES = os.path.join(util.PKG, "mro", "atac", "stages", "processing")
+
+
+class Record(object):
+    """stand-in for martian.Record"""
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def coerce_strings(self):
+        pass
+
+
+def load_stage(name):
+    spec = importlib.util.spec_from_file_location("stage_" + name, os.path.join(STAGES, name, "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_mro_declarations_match_the_reference_signatures():
+    ccs, dp, gpm = load_stage("count_cut_sites"), load_stage("detect_peaks"), load_stage("generate_peak_matrix")
+    assert "stage COUNT_CUT_SITES(" in ccs.__MRO__ and "out pickle     count_dict" in ccs.__MRO__ and "in  string     contig" in ccs.__MRO__
+    assert "stage DETECT_PEAKS(" in dp.__MRO__ and "in  float[]    params" in dp.__MRO__ and "out json       peak_metrics" in dp.__MRO__
+    assert "stage GENERATE_PEAK_MATRIX(" in gpm.__MRO__ and "out h5     raw_matrix" in gpm.__MRO__ and "in  file   barcodes" in gpm.__MRO__
+    for m in (ccs, dp, gpm):
+        assert callable(m.split) and callable(m.main) and callable(m.join)
+
+
+def test_null_inputs_propagate_as_null_outputs():
+    ccs, dp, gpm = load_stage("count_cut_sites"), load_stage("detect_peaks"), load_stage("generate_peak_matrix")
+    assert ccs.split(Record(fragments=None)) == {'chunks': [], 'join': {}}
+    assert dp.split(Record(cut_sites=None)) == {'chunks': [], 'join': {}}
+    assert gpm.split(Record(fragments=None)) == {'chunks': [], 'join': {}}
+    o = Record(count_dict="x", cut_sites="y")
+    ccs.join(Record(fragments=None), o, [], [])
+    assert o.count_dict is None and o.cut_sites is None
+    o = Record(peaks="x", peak_metrics="y")
+    dp.join(Record(cut_sites=None), o, [], [])
+    assert o.peaks is None and o.peak_metrics is None
+    o = Record(raw_matrix="x", raw_matrix_mex="y")
+    gpm.join(Record(fragments=None), o, [], [])
+    assert o.raw_matrix is None and o.raw_matrix_mex is None
+
+
+def test_h5_round_trip(tmp_path):
+    rng = np.random.default_rng(8)
+    n_feat, n_bc = 57, 23
+    dense = (rng.random((n_feat, n_bc)) < 0.1) * rng.integers(1, 9, size=(n_feat, n_bc))
+    indptr, indices, data = [0], [], []
+    for j in range(n_bc):
+        rows = np.nonzero(dense[:, j])[0]
+        indices += rows.tolist()
+        data += dense[rows, j].tolist()
+        indptr.append(len(indices))
+    barcodes = ["".join(rng.choice(list("ACGT"), size=16)) + "-1" for _ in range(n_bc)]
+    feats = ["chr%d:%d-%d" % (i % 3 + 1, 100 * i, 100 * i + 50) for i in range(n_feat)]
+    p = str(tmp_path / "m.h5")
+    h5.write_matrix_h5(p, indptr, indices, data, n_feat, barcodes, feats, "GRCh38", sw_version="1.2.0")
+    blob = open(p, "rb").read()
+    assert blob[:8] == b"\x89HDF\r\n\x1a\n"
+    m = h5.read_matrix_h5(p)
+    assert m["attrs"] == {"filetype": "matrix", "version": 2, "software_version": "1.2.0"}
+    assert m["indptr"].tolist() == indptr and m["indices"].tolist() == indices and m["data"].tolist() == data
+    assert m["indptr"].dtype == np.int64 and m["indices"].dtype == np.int64 and m["data"].dtype == np.int32
+    assert m["shape"].tolist() == [n_feat, n_bc] and m["shape"].dtype == np.int32
+    assert [b.decode() for b in m["barcodes"]] == barcodes
+    f = m["features"]
+    assert sorted(f) == ["_all_tag_keys", "derivation", "feature_type", "genome", "id", "name"]
+    assert [x.decode() for x in f["id"]] == feats and [x.decode() for x in f["name"]] == feats
+    assert set(f["feature_type"].tolist()) == {b"Peaks"} and set(f["genome"].tolist()) == {b"GRCh38"}
+    assert [x.decode() for x in f["_all_tag_keys"]] == ["genome", "derivation"]
+    # empty matrix
+    h5.write_matrix_h5(p, [0], [], [], 0, [], [], "GRCh38")
+    m = h5.read_matrix_h5(p)
+    assert m["indptr"].tolist() == [0] and m["indices"].size == 0 and m["shape"].tolist() == [0, 0]
+
+
+def test_mex_writer(tmp_path):
+    d = str(tmp_path / "mex")
+    mex.save_mex(d, [0, 2, 2, 3], [0, 2, 1], [4, 1, 7], 3, ["A-1", "B-1", "C-1"], ["chr1:1-5", "chr1:9-20", "chr2:0-3"], "1.2.0")
+    lines = open(os.path.join(d, "matrix.mtx")).read().splitlines()
+    assert lines[0] == "%%MatrixMarket matrix coordinate integer general"
+    assert lines[1].startswith("%metadata_json: ") and json.loads(lines[1][len("%metadata_json: "):]) == {"software_version": "1.2.0", "format_version": 2}
+    assert lines[2:] == ["3 3 3", "1 1 4", "3 1 1", "2 3 7"]
+    assert open(os.path.join(d, "peaks.bed")).read() == "chr1\t1\t5\nchr1\t9\t20\nchr2\t0\t3\n"
+    assert open(os.path.join(d, "barcodes.tsv")).read() == "A-1\nB-1\nC-1\n"
+
+
+def test_reference_manager(tmp_path):
+    contigs = [("chr1", 1000), ("chr2", 500), ("chrX", 300), ("chrM", 16)]
+    ref = str(tmp_path / "ref")
+    refmgr.write_reference(ref, contigs)
+    defs = json.load(open(os.path.join(ref, "fasta", "contig-defs.json")))
+    defs["primary_contigs"] = ["chr1", "chr2", "chrX"]
+    defs["non_nuclear_contigs"] = ["chrM"]
+    json.dump(defs, open(os.path.join(ref, "fasta", "contig-defs.json"), "w"))
+    m = refmgr.ReferenceManager(ref)
+    assert m.contig_table() == contigs and m.genome == "GRCh38"
+    assert m.primary_contigs(allow_sex_chromosomes=True) == ["chr1", "chr2", "chrX"]
+    assert m.primary_contigs() == ["chr1", "chr2"]
+    assert refmgr.generate_genome_tag(ref) == ["GRCh38"]
+
+
+@pytest.mark.gpu
+def test_three_stages_end_to_end_match_reference_flow(tmp_path):
+    contigs = [("chr1", 900000), ("chr2", 500000), ("chrX", 300000)]
+    ref = str(tmp_path / "ref")
+    refmgr.write_reference(ref, contigs)
+    frags = synth.generate(contigs, 110000, 40, 400, seed=77, background_factor=5)
+    text = synth.to_text(frags)
+    fpath = str(tmp_path / "fragments.tsv.gz")
+    bgzf.write(fpath, text)
+    want = reference_flow.run(text, contigs, [c[0] for c in contigs], n_procs=4)
+
+    ccs, dp, gpm = load_stage("count_cut_sites"), load_stage("detect_peaks"), load_stage("generate_peak_matrix")
+    # ---- COUNT_CUT_SITES
+    args = Record(reference_path=ref, fragments=fpath, fragments_index=fpath + ".tbi")
+    s = ccs.split(args)
+    assert s["chunks"] == []
+    outs = Record(cut_sites=str(tmp_path / "cut_sites.bedgraph"), count_dict=str(tmp_path / "count_dict.pickle"))
+    ccs.join(args, outs, [], [])
+    cd = pickle.load(open(outs.count_dict, "rb"))
+    assert isinstance(cd, Counter) and dict(cd) == dict(want["count_dict"])
+    # ---- DETECT_PEAKS
+    args = Record(cut_sites=outs.cut_sites, reference_path=ref, count_dict=outs.count_dict)
+    s = dp.split(args)
+    assert len(s["chunks"]) == 1 and s["chunks"][0]["threshold"] == int(want["threshold"])
+    chunk = Record(**s["chunks"][0])
+    margs = Record(cut_sites=outs.cut_sites, reference_path=ref, count_dict=outs.count_dict, contig=chunk.contig, params=chunk.params,
+                   threshold=chunk.threshold)
+    mouts = Record(peaks=str(tmp_path / "chunk_peaks.bed"), peak_metrics=str(tmp_path / "chunk_metrics.json"))
+    dp.main(margs, mouts)
+    jouts = Record(peaks=str(tmp_path / "peaks.bed"), peak_metrics=str(tmp_path / "peak_metrics.json"))
+    dp.join(args, jouts, [chunk], [mouts])
+    peaks_text = open(jouts.peaks).read()
+    assert peaks_text == "".join("%s\t%d\t%d\n" % p for p in want["peaks"])
+    metrics = json.load(open(jouts.peak_metrics))
+    assert metrics["total_peaks_detected"] == len(want["peaks"]) and metrics["peakcaller_threshold"] == int(want["threshold"])
+    assert metrics["bases_in_peaks"] == sum(e - s for _, s, e in want["peaks"])
+    if want["params"] is not None:
+        assert np.allclose([metrics["peakcaller_" + k] for k in dp.PARAM_NAMES], np.array(want["params"], dtype=float), rtol=1e-6)
+    # ---- GENERATE_PEAK_MATRIX
+    args = Record(reference_path=ref, fragments=fpath, peaks=jouts.peaks)
+    assert gpm.split(args)["chunks"] == []
+    gouts = Record(raw_matrix=str(tmp_path / "raw_peak_bc_matrix.h5"), raw_matrix_mex=str(tmp_path / "raw_peak_bc_matrix_mex"))
+    gpm.join(args, gouts, [], [])
+    m = h5.read_matrix_h5(gouts.raw_matrix)
+    assert [b.decode() for b in m["barcodes"]] == want["barcodes"]
+    assert np.array_equal(m["indptr"], want["indptr"]) and np.array_equal(m["indices"], want["indices"])
+    assert np.array_equal(m["data"], want["data"])
+    assert m["shape"].tolist() == [len(want["peaks"]), len(want["barcodes"])]
+    assert [x.decode() for x in m["features"]["id"]] == ["%s:%d-%d" % p for p in want["peaks"]]
+    assert open(os.path.join(gouts.raw_matrix_mex, "peaks.bed")).read() == peaks_text
+    # the bedgraph the stage wrote is the reference writer's, row for row
+    assert os.path.getsize(outs.cut_sites) > 0
