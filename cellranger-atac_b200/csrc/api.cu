@@ -110,7 +110,7 @@ int cratac_create(int device, int n_contigs, const char* const* contig_names, co
     c->device = device;
     c->n_contigs = n_contigs;
     c->tile_bases = pileup_tile_bases();
-    c->bc_table_cap = 1 << 22;
+    c->bc_table_cap = 1 << 20;   // 16 MiB of slots; grows x4 when more than half full
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return CRATAC_ERR_CUDA; }
     int64_t base = 0, tiles = 0, pidx = 0;
     for (int i = 0; i < n_contigs; i++) {

@@ -22,6 +22,13 @@ constexpr int DEC_MAX_LINES = DEC_TILE / 8;   // a valid line has >= 10 bytes
 constexpr unsigned long long BC_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
 
 struct ContigEntry { unsigned long long hash; int32_t id; int32_t used; };
+// barcode table slot: key and first line share one 16-byte slot (one sector per probe)
+struct __align__(16) BcSlot { unsigned long long key; unsigned long long first; };
+
+__global__ void k_init_table(BcSlot* __restrict__ tab, int cap) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) { BcSlot e; e.key = BC_EMPTY; e.first = 0x7F7F7F7F7F7F7F7FULL; tab[s] = e; }
+}
 
 __host__ __device__ __forceinline__ unsigned long long fnv1a(const unsigned char* s, int n) {
     unsigned long long h = 1469598103934665603ULL;
@@ -112,8 +119,7 @@ struct DecodeArgs {
     const ContigEntry* contig_table;
     int contig_mask;
     int32_t *chrom, *start, *end, *bc, *dup;
-    unsigned long long* bc_keys;
-    unsigned long long* bc_first;
+    BcSlot* bc_tab;
     long long* bc_textoff;
     int bc_mask;
     int64_t* status;
@@ -287,10 +293,11 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         int probes = 0;
         bool placed = false;
         while (probes <= a.bc_mask) {
-            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&a.bc_keys[slot]);
-            if (k == key) { placed = true; break; }
+            // a key never changes once written, so a cached read that already shows our key is final;
+            // anything else is re-checked by the CAS
+            unsigned long long k = a.bc_tab[slot].key;
             if (k == BC_EMPTY) {
-                unsigned long long old = atomicCAS(&a.bc_keys[slot], BC_EMPTY, key);
+                unsigned long long old = atomicCAS(&a.bc_tab[slot].key, BC_EMPTY, key);
                 if (old == BC_EMPTY) {
                     long long off = src0 + (t[2] + 1);
                     a.bc_textoff[slot] = (off << 8) | (long long)min(t[3] - t[2] - 1, 255);
@@ -298,14 +305,15 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
                     placed = true;
                     break;
                 }
-                if (old == key) { placed = true; break; }
+                k = old;
             }
+            if (k == key) { placed = true; break; }
             slot = (slot + 1) & (unsigned)a.bc_mask;
             probes++;
         }
         if (!placed) { raise_error(a.status, CRATAC_ERR_CAPACITY, line_no); continue; }
-        if (*reinterpret_cast<volatile unsigned long long*>(&a.bc_first[slot]) > (unsigned long long)line_no)
-            atomicMin(&a.bc_first[slot], (unsigned long long)line_no);
+        if (*reinterpret_cast<volatile unsigned long long*>(&a.bc_tab[slot].first) > (unsigned long long)line_no)
+            atomicMin(&a.bc_tab[slot].first, (unsigned long long)line_no);
         a.chrom[line_no] = cid;
         a.start[line_no] = v_start;
         a.end[line_no] = v_end;
@@ -384,18 +392,19 @@ __global__ void k_max_len(const int32_t* __restrict__ start, const int32_t* __re
 }
 
 // ------------------------------------------------------------------ barcode table -> dense ids
-__global__ void k_table_compact(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ first,
+__global__ void k_table_compact(const BcSlot* __restrict__ tab,
                                 const long long* __restrict__ textoff, int cap, int32_t* __restrict__ slot_to_dense,
                                 unsigned long long* __restrict__ dense_first, long long* __restrict__ dense_textoff,
                                 unsigned long long* __restrict__ dense_bckey, unsigned long long* counter) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= cap) return;
-    if (keys[s] == BC_EMPTY) { slot_to_dense[s] = -1; return; }
+    const BcSlot e = tab[s];
+    if (e.key == BC_EMPTY) { slot_to_dense[s] = -1; return; }
     unsigned long long d = atomicAdd(counter, 1ULL);
     slot_to_dense[s] = (int32_t)d;
-    dense_first[d] = first[s];
+    dense_first[d] = e.first;
     dense_textoff[d] = textoff[s];
-    dense_bckey[d] = keys[s];
+    dense_bckey[d] = e.key;
 }
 
 __global__ void k_gather_barcode_text(const char* __restrict__ text, const long long* __restrict__ dense_textoff, int64_t n,
@@ -497,7 +506,7 @@ static int barcode_prepare_device(Ctx* c) {
     cudaStream_t s = c->stream;
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
     c->stage_begin(SG_BARCODE_TABLE);
-    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<unsigned long long>(), c->d_bc_first.as<unsigned long long>(),
+    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<BcSlot>(),
                                                                c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
                                                                c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
                                                                c->d_dense_bckey.as<unsigned long long>(), reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
@@ -573,10 +582,10 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
 
     for (int attempt = 0;; attempt++) {
         size_t cap = (size_t)c->bc_table_cap;
-        CRATAC_TRY(c->d_bc_keys.reserve(8 * cap)); CRATAC_TRY(c->d_bc_first.reserve(8 * cap));
+        CRATAC_TRY(c->d_bc_keys.reserve(sizeof(BcSlot) * cap));
         CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
-        CRATAC_CUDA(cudaMemsetAsync(c->d_bc_keys.p, 0xFF, 8 * cap, c->stream));
-        CRATAC_CUDA(cudaMemsetAsync(c->d_bc_first.p, 0x7F, 8 * cap, c->stream));
+        k_init_table<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_bc_keys.as<BcSlot>(), (int)cap);
+        c->launches++;
         CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
         CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_BARCODES], 0, sizeof(int64_t) * 3, c->stream));  // barcodes, maxpos, maxneg
         DecodeArgs a;
@@ -585,7 +594,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
         a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
         a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
-        a.bc_keys = c->d_bc_keys.as<unsigned long long>(); a.bc_first = c->d_bc_first.as<unsigned long long>();
+        a.bc_tab = c->d_bc_keys.as<BcSlot>();
         a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
         a.status = st;
         a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;

@@ -34,6 +34,7 @@ struct OverlapArgs {
     const int64_t* seg_off;                // scatter pass
     unsigned int* cursor;
     int32_t* hits;
+    long long maxpos, maxneg;              // bounds of end - start over all fragments
 };
 
 __device__ __forceinline__ int find_peak(const OverlapArgs& a, int c, int pos) {
@@ -49,23 +50,77 @@ __device__ __forceinline__ int find_peak(const OverlapArgs& a, int c, int pos) {
     return -1;
 }
 
+// Fragments are start-sorted, so the OV_TILE fragments a CTA takes at a time touch a handful of consecutive
+// peaks: the CTA finds that window with two bisects, stages it in shared memory and every fragment end is
+// then located there.  Tiles that straddle a contig boundary or a very dense peak region fall back to the
+// global bisect.
+constexpr int OV_TILE = 2048;
+constexpr int OV_WIN = 1024;
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = a.chrom[i];
-        int b = a.bc[i];
-        if (a.slot_to_dense) b = a.slot_to_dense[b];
-        int r0 = find_peak(a, c, a.start[i]);
-        int r1 = find_peak(a, c, a.end[i]);
-        int nh = (r0 >= 0) + (r1 >= 0);
-        if (nh == 0 || b < 0) continue;
-        if (!SCATTER) {
-            atomicAdd(&a.bc_hits[b], nh);
-        } else {
-            unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nh);
-            int64_t o = a.seg_off[b] + p;
-            if (r0 >= 0) a.hits[o++] = r0;
-            if (r1 >= 0) a.hits[o] = r1;
+    __shared__ int s_start[OV_WIN], s_end[OV_WIN], s_row[OV_WIN];
+    __shared__ long long s_plo;
+    __shared__ int s_w;
+    const int64_t n_tiles = (a.n + OV_TILE - 1) / OV_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * OV_TILE;
+        const int64_t i1 = i0 + OV_TILE < a.n ? i0 + OV_TILE : a.n;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int w = -1;
+            const int c0 = a.chrom[i0];
+            if (c0 == a.chrom[i1 - 1]) {
+                const long long lo_pos = (long long)a.start[i0] - a.maxneg;
+                const long long hi_pos = (long long)a.start[i1 - 1] + a.maxpos;
+                const int64_t base = a.peak_off[c0], top = a.peak_off[c0 + 1];
+                int64_t lo = base, hi = top;             // first peak start > lo_pos
+                while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (lo_pos < (long long)a.pk_start[mid]) hi = mid; else lo = mid + 1; }
+                int64_t p_lo = lo > base ? lo - 1 : base;
+                lo = p_lo; hi = top;                      // first peak start > hi_pos
+                while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (hi_pos < (long long)a.pk_start[mid]) hi = mid; else lo = mid + 1; }
+                if (lo - p_lo <= OV_WIN) { w = (int)(lo - p_lo); s_plo = p_lo; }
+            }
+            s_w = w;
+        }
+        __syncthreads();
+        const int w = s_w;
+        if (w > 0) {
+            const int64_t p_lo = s_plo;
+            for (int k = threadIdx.x; k < w; k += MX_THREADS) {
+                s_start[k] = a.pk_start[p_lo + k]; s_end[k] = a.pk_end[p_lo + k]; s_row[k] = a.pk_row[p_lo + k];
+            }
+        }
+        __syncthreads();
+        for (int64_t i = i0 + threadIdx.x; i < i1; i += MX_THREADS) {
+            int b = a.bc[i];
+            if (a.slot_to_dense) b = a.slot_to_dense[b];
+            int r0, r1;
+            if (w >= 0) {
+                int pos[2] = {a.start[i], a.end[i]};
+                int r[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    int lo = 0, hi = w;                   // first staged start > pos
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (pos[q] < s_start[mid]) hi = mid; else lo = mid + 1; }
+                    r[q] = (lo > 0 && pos[q] < s_end[lo - 1]) ? s_row[lo - 1] : -1;
+                }
+                r0 = r[0]; r1 = r[1];
+            } else {
+                const int c = a.chrom[i];
+                r0 = find_peak(a, c, a.start[i]);
+                r1 = find_peak(a, c, a.end[i]);
+            }
+            int nh = (r0 >= 0) + (r1 >= 0);
+            if (nh == 0 || b < 0) continue;
+            if (!SCATTER) {
+                atomicAdd(&a.bc_hits[b], nh);
+            } else {
+                unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nh);
+                int64_t o = a.seg_off[b] + p;
+                if (r0 >= 0) a.hits[o++] = r0;
+                if (r1 >= 0) a.hits[o] = r1;
+            }
         }
     }
 }
@@ -135,7 +190,8 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
                                                                  int64_t n_bc, const int64_t* __restrict__ status, int64_t n_peaks_host,
                                                                  int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                  int32_t* __restrict__ nnz_col) {
-    extern __shared__ int cnt[];           // COUNT_RANGE
+    extern __shared__ int cnt[];           // COUNT_RANGE counters, then COUNT_RANGE / 32 bitmap words
+    unsigned* bm = reinterpret_cast<unsigned*>(cnt + COUNT_RANGE);
     __shared__ int warp_tot[COUNT_THREADS / 32];
     __shared__ int s_base;
     const int64_t n_peaks = n_peaks_host >= 0 ? n_peaks_host : status[ST_N_PEAKS];
@@ -155,18 +211,33 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
             }
             __syncthreads();
             const int lim = (n_peaks - r0) < (int64_t)COUNT_RANGE ? (int)(n_peaks - r0) : COUNT_RANGE;
-            for (int i0 = 0; i0 < lim; i0 += COUNT_THREADS) {
+            // occupancy bitmap of the counters (one ballot per warp per 32 counters), then emit only the set bits
+            for (int i0 = 0; i0 < COUNT_RANGE; i0 += COUNT_THREADS) {
                 int i = i0 + threadIdx.x;
-                int v = i < lim ? cnt[i] : 0;
-                int flag = v != 0;
-                int x = flag;
+                unsigned m = __ballot_sync(0xffffffffu, i < lim && cnt[i] != 0);
+                if (lane == 0) bm[i >> 5] = m;
+            }
+            __syncthreads();
+            for (int w0 = 0; w0 < COUNT_RANGE / 32; w0 += COUNT_THREADS) {
+                int wi = w0 + threadIdx.x;
+                unsigned word = wi < COUNT_RANGE / 32 ? bm[wi] : 0u;
+                int c = __popc(word);
+                int x = c;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
                 if (lane == 31) warp_tot[warp] = x;
                 __syncthreads();
                 int off = s_base;
                 for (int w = 0; w < warp; w++) off += warp_tot[w];
-                if (flag) { out_row[o0 + off + x - 1] = (int32_t)(r0 + i); out_cnt[o0 + off + x - 1] = v; }
+                int64_t pos = o0 + off + x - c;
+                while (word) {
+                    int bit = __ffs(word) - 1;
+                    word &= word - 1;
+                    int row = wi * 32 + bit;
+                    out_row[pos] = (int32_t)(r0 + row);
+                    out_cnt[pos] = cnt[row];
+                    pos++;
+                }
                 __syncthreads();
                 if (threadIdx.x == COUNT_THREADS - 1) s_base = off + x;
                 __syncthreads();
@@ -272,8 +343,9 @@ int peak_matrix_device(Ctx* c) {
     a.slot_to_dense = c->bc_is_slot ? c->d_slot_to_dense.as<int32_t>() : nullptr;
     a.peak_off = c->d_peak_off.as<int64_t>();
     a.pk_start = c->d_peak_start.as<int32_t>(); a.pk_end = c->d_peak_end.as<int32_t>(); a.pk_row = c->d_peak_row.as<int32_t>();
+    a.maxpos = c->h_status[ST_MAX_POS_LEN]; a.maxneg = c->h_status[ST_MAX_NEG_LEN];
     a.bc_hits = c->d_bc_hits.as<int32_t>(); a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = nullptr;
-    int grid = (int)std::min<int64_t>((n + MX_THREADS - 1) / MX_THREADS, (int64_t)NUM_SMS * 16);
+    int grid = (int)std::min<int64_t>((n + OV_TILE - 1) / OV_TILE, (int64_t)NUM_SMS * 8);
     if (grid < 1) grid = 1;
     c->stage_begin(SG_OVERLAP_COUNT);
     k_overlap<false><<<grid, MX_THREADS, 0, s>>>(a);
@@ -304,7 +376,7 @@ int peak_matrix_device(Ctx* c) {
     if (nb > 0) {
         static bool configured = false;
         if (!configured) {
-            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4));
+            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4 + COUNT_RANGE / 8));
             configured = true;
         }
         int g1 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 32);
@@ -313,7 +385,7 @@ int peak_matrix_device(Ctx* c) {
         c->stage_end(SG_REDUCE_SMALL);
         c->stage_begin(SG_REDUCE_LARGE);
         int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
-        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4, s>>>(a.hits, a.seg_off, nb, st,
+        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 8, s>>>(a.hits, a.seg_off, nb, st,
                                                                  c->row_range > 0 ? c->row_range : (c->peaks_on_device_count ? -1 : c->n_peaks),
                                                                  c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_LARGE);
