@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "parse_swar.cuh"
 
 namespace cratac {
 
@@ -169,12 +170,33 @@ __device__ __forceinline__ unsigned long long barcode_key(const unsigned char* s
     return h;
 }
 
+__device__ __forceinline__ unsigned byte_at(const uint32_t* words, int p) { return (words[p >> 2] >> ((p & 3) * 8)) & 0xFFu; }
+
+__device__ __forceinline__ unsigned long long barcode_key_words(const uint32_t* words, int p, int n) {
+    // fast path: [ACGT]{16}-[0-9]{1,9} without a leading zero in the group (so that "-01" cannot alias "-1")
+    if (n >= 18 && n <= 26 && byte_at(words, p + 16) == '-' && !(n > 18 && byte_at(words, p + 17) == '0')) {
+        bool ok = true;
+        unsigned seq = (swar_pack4(swar_get4(words, p), &ok) << 24) | (swar_pack4(swar_get4(words, p + 4), &ok) << 16) |
+                       (swar_pack4(swar_get4(words, p + 8), &ok) << 8) | swar_pack4(swar_get4(words, p + 12), &ok);
+        int32_t grp = 0;
+        ok = ok && swar_parse_uint(words, p + 17, n - 17, &grp);
+        if (ok) return ((unsigned long long)(unsigned)grp << 32) | seq;
+    }
+    unsigned long long h = mix64(swar_fnv1a(words, p, n) ^ ((unsigned long long)n << 56));
+    h = (h >> 1) | 0x8000000000000000ULL;
+    if (h == BC_EMPTY) h ^= 2ULL;
+    return h;
+}
+
 __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
-    __shared__ __align__(128) unsigned char buf[DEC_LOOKBACK + DEC_TILE];
+    constexpr int N_CHUNKS = (DEC_LOOKBACK + DEC_TILE) / 16;
+    __shared__ __align__(128) uint32_t words[(DEC_LOOKBACK + DEC_TILE) / 4 + 4];   // text tile (+16 B slack for word over-reads)
+    __shared__ uint32_t masks[N_CHUNKS];            // per 16-byte chunk: newline bits (low half), tab bits (high half)
     __shared__ uint16_t nlpos[DEC_MAX_LINES];
     __shared__ int warp_tot[DEC_THREADS / 32];
     __shared__ int s_first_begin;
     __shared__ __align__(8) uint64_t bar;
+    unsigned char* buf = reinterpret_cast<unsigned char*>(words);
 
     const int tid = threadIdx.x;
     const int64_t tile_base = (int64_t)blockIdx.x * DEC_TILE;
@@ -182,7 +204,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     if (n_lines == 0) return;   // uniform per CTA
     const int64_t src0 = tile_base - DEC_LOOKBACK;
 
-    // ---- stage bytes [src0, tile_base + DEC_TILE) into buf
+    // ---- stage bytes [src0, tile_base + DEC_TILE) into shared memory: one TMA bulk copy when the tile is interior
     const bool full = a.use_tma && src0 >= 0 && tile_base + DEC_TILE <= a.nbytes;
     if (full) {
         if (tid == 0) {
@@ -205,16 +227,24 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         __syncthreads();
     }
 
-    // ---- newline positions of the tile, in order
+    // ---- newline / tab bitmasks per 16-byte chunk (thread t owns the 4 chunks of its 64 tile bytes;
+    //      the first 16 threads also take one look-back chunk each)
     constexpr int PER_THREAD = DEC_TILE / DEC_THREADS;   // 64 contiguous bytes per thread
-    const unsigned char* mine = buf + DEC_LOOKBACK + tid * PER_THREAD;
-    unsigned long long mask = 0;   // bit j set if mine[j] == '\n'
+    unsigned long long mask = 0;                         // newline bits of my 64 bytes
+    {
+        const int c0 = DEC_LOOKBACK / 16 + tid * (PER_THREAD / 16);
 #pragma unroll
-    for (int w = 0; w < PER_THREAD / 4; w++) {
-        unsigned v = *reinterpret_cast<const unsigned*>(mine + 4 * w);
-        unsigned m = __vcmpeq4(v, 0x0a0a0a0au);
-        unsigned bits = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
-        mask |= (unsigned long long)bits << (4 * w);
+        for (int k = 0; k < PER_THREAD / 16; k++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * (c0 + k));
+            const uint32_t nl = swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au);
+            const uint32_t tb = swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u);
+            masks[c0 + k] = nl | (tb << 16);
+            mask |= (unsigned long long)nl << (16 * k);
+        }
+        if (tid < DEC_LOOKBACK / 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * tid);
+            masks[tid] = swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) | (swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << 16);
+        }
     }
     // bytes at or beyond n_eff are padding newlines of the last tile: they terminate nothing
     {
@@ -242,10 +272,13 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     }
     if (tid == 0) {
         // start of the first line: one past the last '\n' before the tile (or the file start)
-        int p = DEC_LOOKBACK - 1;
-        while (p >= 0 && buf[p] != '\n') p--;
-        s_first_begin = (p < 0 && tile_base > 0) ? -1 : p + 1;
-        if (tile_base == 0) s_first_begin = DEC_LOOKBACK;
+        int begin = -1;
+        for (int c = DEC_LOOKBACK / 16 - 1; c >= 0; c--) {
+            unsigned nl = masks[c] & 0xFFFFu;
+            if (nl) { begin = c * 16 + (31 - __clz(nl)) + 1; break; }
+        }
+        if (tile_base == 0) begin = DEC_LOOKBACK;
+        s_first_begin = begin;
     }
     __syncthreads();
     if (n_lines > DEC_MAX_LINES || s_first_begin < 0) {
@@ -253,33 +286,41 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         return;
     }
 
-    // ---- one line per thread
+    // ---- one line per thread: tabs from the chunk masks, numbers and barcode a word at a time
     const int64_t out_base = a.tile_offsets[blockIdx.x];
     int loc_maxpos = 0, loc_maxneg = 0;
     for (int li = tid; li < n_lines; li += DEC_THREADS) {
         int b = li == 0 ? s_first_begin : nlpos[li - 1] + 1;
         int e = nlpos[li];
         int64_t line_no = out_base + li;
-        // strip() : leading / trailing blanks, '\r'
-        while (b < e && (buf[b] == ' ' || buf[b] == '\t' || buf[b] == '\r')) b++;
-        while (e > b && (buf[e - 1] == ' ' || buf[e - 1] == '\t' || buf[e - 1] == '\r')) e--;
-        int t[4];
+        // strip(): leading / trailing blanks, '\r'
+        while (b < e) { unsigned ch = byte_at(words, b); if (ch == ' ' || ch == '\t' || ch == '\r') b++; else break; }
+        while (e > b) { unsigned ch = byte_at(words, e - 1); if (ch == ' ' || ch == '\t' || ch == '\r') e--; else break; }
+        int t[4] = {0, 0, 0, 0};
         int nt = 0;
-        for (int i = b; i < e; i++) {
-            if (buf[i] == '\t') {
-                if (nt < 4) t[nt] = i;
-                nt++;
+        if (b < e) {
+            const int cb = b >> 4, ce = (e - 1) >> 4;
+            for (int c = cb; c <= ce; c++) {
+                unsigned tm = masks[c] >> 16;
+                if (c == cb) tm &= 0xFFFFu << (b & 15);
+                if (c == ce) tm &= 0xFFFFu >> (15 - ((e - 1) & 15));
+                while (tm) {
+                    int bit = __ffs(tm) - 1;
+                    tm &= tm - 1;
+                    if (nt < 4) t[nt] = c * 16 + bit;
+                    nt++;
+                }
             }
         }
         int32_t v_start = 0, v_end = 0, v_dup = 0;
         bool ok = (nt == 4);
         if (ok) {
-            ok = parse_uint(buf, t[0] + 1, t[1], &v_start) && parse_uint(buf, t[1] + 1, t[2], &v_end) &&
-                 parse_uint(buf, t[3] + 1, e, &v_dup) && (t[0] > b) && (t[3] > t[2] + 1);
+            ok = swar_parse_uint(words, t[0] + 1, t[1] - t[0] - 1, &v_start) && swar_parse_uint(words, t[1] + 1, t[2] - t[1] - 1, &v_end) &&
+                 swar_parse_uint(words, t[3] + 1, e - t[3] - 1, &v_dup) && (t[0] > b) && (t[3] > t[2] + 1);
         }
         if (!ok) { raise_error(a.status, CRATAC_ERR_PARSE, line_no); continue; }
         // contig id
-        unsigned long long ch = fnv1a(buf + b, t[0] - b);
+        unsigned long long ch = swar_fnv1a(words, b, t[0] - b);
         int32_t cid = -1;
         for (int s = (int)(mix64(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
             ContigEntry ce = a.contig_table[s];
@@ -288,7 +329,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         }
         if (cid < 0) { raise_error(a.status, CRATAC_ERR_CONTIG, line_no); continue; }
         // barcode slot
-        unsigned long long key = barcode_key(buf, t[2] + 1, t[3]);
+        unsigned long long key = barcode_key_words(words, t[2] + 1, t[3] - t[2] - 1);
         unsigned slot = (unsigned)(mix64(key)) & (unsigned)a.bc_mask;
         int probes = 0;
         bool placed = false;
