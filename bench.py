@@ -436,7 +436,8 @@ def main():
                        "nnz_rank0": int(nnz_r0), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},
             "wall_ms_per_step": 1000.0 * wall / args.steps, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "host_phases_last_step_ms": ctx.host_times(),
-            "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()}}
+            "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},
+            "n_bins": int(getattr(res, "n_bins", 0))}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

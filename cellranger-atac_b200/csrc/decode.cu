@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         // strip(): leading / trailing blanks, '\r'
         while (b < e) { unsigned ch = byte_at(words, b); if (ch == ' ' || ch == '\t' || ch == '\r') b++; else break; }
         while (e > b) { unsigned ch = byte_at(words, e - 1); if (ch == ' ' || ch == '\t' || ch == '\r') e--; else break; }
-        int t[4] = {0, 0, 0, 0};
+        int t0 = 0, t1 = 0, t2 = 0, t3 = 0;   // scalars, not an indexed array: keeps them out of local memory
         int nt = 0;
         if (b < e) {
             const int cb = b >> 4, ce = (e - 1) >> 4;
@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
                 if (c == cb) tm &= 0xFFFFu << (b & 15);
                 if (c == ce) tm &= 0xFFFFu >> (15 - ((e - 1) & 15));
                 while (tm) {
-                    int bit = __ffs(tm) - 1;
+                    const int pos = c * 16 + __ffs(tm) - 1;
                     tm &= tm - 1;
-                    if (nt < 4) t[nt] = c * 16 + bit;
+                    if (nt == 0) t0 = pos; else if (nt == 1) t1 = pos; else if (nt == 2) t2 = pos; else if (nt == 3) t3 = pos;
                     nt++;
                 }
             }
@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         int32_t v_start = 0, v_end = 0, v_dup = 0;
         bool ok = (nt == 4);
         if (ok) {
-            ok = swar_parse_uint(words, t[0] + 1, t[1] - t[0] - 1, &v_start) && swar_parse_uint(words, t[1] + 1, t[2] - t[1] - 1, &v_end) &&
-                 swar_parse_uint(words, t[3] + 1, e - t[3] - 1, &v_dup) && (t[0] > b) && (t[3] > t[2] + 1);
+            ok = swar_parse_uint(words, t0 + 1, t1 - t0 - 1, &v_start) && swar_parse_uint(words, t1 + 1, t2 - t1 - 1, &v_end) &&
+                 swar_parse_uint(words, t3 + 1, e - t3 - 1, &v_dup) && (t0 > b) && (t3 > t2 + 1);
         }
         if (!ok) { raise_error(a.status, CRATAC_ERR_PARSE, line_no); continue; }
         // contig id
-        unsigned long long ch = swar_fnv1a(words, b, t[0] - b);
+        unsigned long long ch = swar_fnv1a(words, b, t0 - b);
         int32_t cid = -1;
         for (int s = (int)(mix64(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
             ContigEntry ce = a.contig_table[s];
@@ -329,19 +329,22 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         }
         if (cid < 0) { raise_error(a.status, CRATAC_ERR_CONTIG, line_no); continue; }
         // barcode slot
-        unsigned long long key = barcode_key_words(words, t[2] + 1, t[3] - t[2] - 1);
+        unsigned long long key = barcode_key_words(words, t2 + 1, t3 - t2 - 1);
         unsigned slot = (unsigned)(mix64(key)) & (unsigned)a.bc_mask;
         int probes = 0;
         bool placed = false;
+        unsigned long long seen_first = 0xFFFFFFFFFFFFFFFFULL;
         while (probes <= a.bc_mask) {
             // a key never changes once written, so a cached read that already shows our key is final;
             // anything else is re-checked by the CAS
-            unsigned long long k = a.bc_tab[slot].key;
+            const ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&a.bc_tab[slot]);   // key and first line in one 16-byte load
+            unsigned long long k = sl.x;
+            seen_first = sl.y;
             if (k == BC_EMPTY) {
                 unsigned long long old = atomicCAS(&a.bc_tab[slot].key, BC_EMPTY, key);
                 if (old == BC_EMPTY) {
-                    long long off = src0 + (t[2] + 1);
-                    a.bc_textoff[slot] = (off << 8) | (long long)min(t[3] - t[2] - 1, 255);
+                    long long off = src0 + (t2 + 1);
+                    a.bc_textoff[slot] = (off << 8) | (long long)min(t3 - t2 - 1, 255);
                     atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_N_BARCODES]), 1ULL);
                     placed = true;
                     break;
@@ -353,8 +356,8 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
             probes++;
         }
         if (!placed) { raise_error(a.status, CRATAC_ERR_CAPACITY, line_no); continue; }
-        if (*reinterpret_cast<volatile unsigned long long*>(&a.bc_tab[slot].first) > (unsigned long long)line_no)
-            atomicMin(&a.bc_tab[slot].first, (unsigned long long)line_no);
+        // `seen_first` may be stale (cached) but only ever too large: the atomicMin decides
+        if (seen_first > (unsigned long long)line_no) atomicMin(&a.bc_tab[slot].first, (unsigned long long)line_no);
         a.chrom[line_no] = cid;
         a.start[line_no] = v_start;
         a.end[line_no] = v_end;

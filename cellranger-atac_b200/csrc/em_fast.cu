@@ -1,8 +1,8 @@
-// K4, register-resident variant: the same fit as em.cu (peaks.py:28-193, em_fitting.py:10-87) for the
-// common case of <= 2048 histogram bins and window counts <= 8192.  One CTA of 512 threads (128 registers
-// each); every thread owns up to 4 bins (value, weight, responsibilities) in registers for the whole fit, the tail-weight
-// table T(j), the Chebyshev cosine table and the series coefficients live in shared memory, so an EM
-// iteration touches HBM not at all.  The dispersion fixed point uses the interpolate / compose / descend
+// K4, on-chip variant: the same fit as em.cu (peaks.py:28-193, em_fitting.py:10-87).  One CTA of 512 threads;
+// the histogram (value, weight, log-factorial, background weight per bin) lives in shared memory for up to
+// 4608 bins (global scratch beyond), as do the tail-weight table T(j), the Chebyshev cosine table and the
+// series coefficients, so an EM iteration of a typical histogram touches HBM not at all.  The E-step and the
+// sums of the M-step are fused: responsibilities are never stored, only the background weight w*r1.  The dispersion fixed point uses the interpolate / compose / descend
 // scheme described in em.cu, restructured so that every step uses the whole CTA:
 //   * G at 64 candidates (bracket) or 128 points (64 nodes + 64 check points) per pass
 //   * Chebyshev fits and the first half of each composition as 1024-thread mat-vecs with the cosine table
@@ -18,9 +18,10 @@ namespace cratac {
 
 constexpr int EF_THREADS = 512;
 constexpr int EF_WARPS = EF_THREADS / 32;
-constexpr int EF_BPT = 4;
-constexpr int EF_MAXN = EF_THREADS * EF_BPT;
-constexpr int EF_MAXV = 8192;
+constexpr int EF_NS = 4608;          // bins kept in shared memory (more: global scratch)
+constexpr int EF_MAXN = 65536;       // bins this kernel handles at all
+constexpr int EF_TS = 6144;          // tail-weight table entries in shared memory (more: global scratch)
+constexpr int EF_MAXV = 1 << 20;
 constexpr int CM = 64;          // Chebyshev nodes
 constexpr int CS = 65;          // row stride of the cosine table (odd => both access patterns are bank-conflict free)
 constexpr int CL = 14;          // composition levels (2^13 = 8192 < 10000 iterations)
@@ -33,11 +34,15 @@ struct EfArgs {
     int64_t* status;
     double* params_out;
     double odds_ratio;
+    // global scratch for histograms that do not fit shared memory
+    double* g_w; double* g_lg; double* g_o1; double* g_T;
+    int* g_v;
 };
 
 struct EfSmem {
     double costab[CM * CS];     // cos(k * theta_i) at [k * CS + i]
-    double T[EF_MAXV];
+    double T[EF_TS];
+    const double* Tp;           // tail-weight table in use (shared or global)
     double red[EF_WARPS * 8];
     double pts[2 * CM];
     double val[2 * CM];
@@ -125,10 +130,10 @@ __device__ __forceinline__ void ef_eval_points(EfSmem& s, int jmax, double mu, d
     int j = grp < n_active ? 1 + sub : jmax;
     for (; j + TPP < jmax; j += 2 * TPP) {
         double a0 = alpha * (double)j, a1 = alpha * (double)(j + TPP);
-        p0 = fma(ef_frac(a0), s.T[j], p0);
-        p1 = fma(ef_frac(a1), s.T[j + TPP], p1);
+        p0 = fma(ef_frac(a0), s.Tp[j], p0);
+        p1 = fma(ef_frac(a1), s.Tp[j + TPP], p1);
     }
-    if (j < jmax) { double a0 = alpha * (double)j; p0 = fma(ef_frac(a0), s.T[j], p0); }
+    if (j < jmax) { double a0 = alpha * (double)j; p0 = fma(ef_frac(a0), s.Tp[j], p0); }
     double part = p0 + p1;
 #pragma unroll
     for (int d = TPP / 2; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -333,22 +338,21 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
     const int64_t n64 = a.n_bins_host >= 0 ? a.n_bins_host : a.status[ST_N_BINS];
     if (n64 > EF_MAXN) { if (tid == 0) a.status[ST_EM_MODE] = 1; return; }
     const int n = (int)n64;
-    // ---- bins into registers
-    double v[EF_BPT], w[EF_BPT], lgk1[EF_BPT], r0[EF_BPT], r1[EF_BPT], r2[EF_BPT];
+    // ---- per-bin arrays: shared memory when they fit, global scratch otherwise
+    double* wS; double* lgS; double* o1S; int* vS;
+    if (n <= EF_NS) {
+        double* base = reinterpret_cast<double*>(ef_raw + ((sizeof(EfSmem) + 15) & ~(size_t)15));
+        wS = base; lgS = base + EF_NS; o1S = base + 2 * EF_NS; vS = reinterpret_cast<int*>(base + 3 * EF_NS);
+    } else { wS = a.g_w; lgS = a.g_lg; o1S = a.g_o1; vS = a.g_v; }
+    if (tid < 12) s.cyc[tid] = 0;
     double tot[1] = {0.0};
     double vmax = 0.0;
-#pragma unroll
-    for (int k = 0; k < EF_BPT; k++) {
-        int i = tid + k * EF_THREADS;
-        v[k] = 0.0; w[k] = 0.0; lgk1[k] = 0.0; r0[k] = r1[k] = r2[k] = 0.0;
-        if (i < n) {
-            v[k] = (double)a.values[i]; w[k] = (double)a.weights[i];
-            lgk1[k] = lgamma(v[k] + 1.0);
-            tot[0] += w[k];
-            vmax = fmax(vmax, v[k]);
-        }
+    for (int i = tid; i < n; i += EF_THREADS) {
+        const double v = (double)a.values[i], w = (double)a.weights[i];
+        vS[i] = (int)a.values[i]; wS[i] = w; lgS[i] = lgamma(v + 1.0);
+        tot[0] += w;
+        vmax = fmax(vmax, v);
     }
-    if (tid < 12) s.cyc[tid] = 0;
     for (int q = tid; q < CM * CM; q += EF_THREADS) {
         int k = q / CM, i = q % CM;
         s.costab[k * CS + i] = cos((double)k * EF_PI * ((double)i + 0.5) / (double)CM);
@@ -364,66 +368,54 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         return;
     }
     if (vmax + 2.0 > (double)EF_MAXV) { if (tid == 0) a.status[ST_EM_MODE] = 1; return; }
+    double* Tw = (vmax + 2.0 <= (double)EF_TS) ? s.T : a.g_T;   // writable view of the tail-weight table
+    if (tid == 0) s.Tp = Tw;
+    __syncthreads();
+    const int n_slabs = (n + EF_THREADS - 1) / EF_THREADS;
 
-    // ---- inclusive scans over the bins in bin order (slab k = bins [1024k, 1024k+1024))
-    auto scan_forward = [&](const double (&x)[EF_BPT], double (&out)[EF_BPT]) {
+    // inclusive scan over the bins of f(i), forward (prefix) or backward (suffix), result handed to g(i, value)
+    auto scan_bins = [&](bool backward, auto f, auto g) {
         double carry = 0.0;
+        for (int sl = 0; sl < n_slabs; sl++) {
+            const int slab = backward ? n_slabs - 1 - sl : sl;
+            const int i = slab * EF_THREADS + tid;
+            double inc = i < n ? f(i) : 0.0;
+            if (!backward) {
 #pragma unroll
-        for (int k = 0; k < EF_BPT; k++) {
-            if (k * EF_THREADS >= n) { out[k] = carry; continue; }   // uniform
-            double inc = x[k];
+                for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+            } else {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+                for (int d = 1; d < 32; d <<= 1) { double y = __shfl_down_sync(0xffffffffu, inc, d); if (lane + d < 32) inc += y; }
+            }
             __syncthreads();
-            if (lane == 31) s.wtot[warp] = inc;
+            if (lane == (backward ? 0 : 31)) s.wtot[warp] = inc;
             __syncthreads();
-            double off = carry, slab = 0.0;
-            for (int q = 0; q < EF_WARPS; q++) { double t = s.wtot[q]; if (q < warp) off += t; slab += t; }
-            out[k] = off + inc;
-            carry += slab;
-        }
-    };
-    auto scan_backward = [&](const double (&x)[EF_BPT], double (&out)[EF_BPT]) {   // out = sum of x over bins >= this one
-        double carry = 0.0;
-#pragma unroll
-        for (int k = EF_BPT - 1; k >= 0; k--) {
-            if (k * EF_THREADS >= n) { out[k] = 0.0; continue; }
-            double inc = x[k];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_down_sync(0xffffffffu, inc, d); if (lane + d < 32) inc += y; }
-            __syncthreads();
-            if (lane == 0) s.wtot[warp] = inc;
-            __syncthreads();
-            double off = carry, slab = 0.0;
-            for (int q = EF_WARPS - 1; q >= 0; q--) { double t = s.wtot[q]; if (q > warp) off += t; slab += t; }
-            out[k] = off + inc;
-            carry += slab;
+            double off = carry, slab_sum = 0.0;
+            for (int q = 0; q < EF_WARPS; q++) {
+                double t = s.wtot[q];
+                if (backward ? q > warp : q < warp) off += t;
+                slab_sum += t;
+            }
+            if (i < n) g(i, off + inc);
+            carry += slab_sum;
         }
     };
 
     // ---- simple_threshold_estimate (peaks.py:28-40)
     int t0;
     {
-        double r[EF_BPT], cum[EF_BPT];
-        double cnt[2] = {0.0, 0.0};   // bins <= 15, bins > 15
-#pragma unroll
-        for (int k = 0; k < EF_BPT; k++) {
-            bool in = tid + k * EF_THREADS < n;
-            bool above = in && v[k] > (double)DEFAULT_THRESHOLD;
-            r[k] = above ? v[k] * w[k] : 0.0;
-            cnt[0] += (in && !above) ? 1.0 : 0.0;
+        double cnt[3] = {0.0, 0.0, 0.0};   // bins <= 15, bins > 15, sum of v*w over bins > 15
+        for (int i = tid; i < n; i += EF_THREADS) {
+            const bool above = vS[i] > DEFAULT_THRESHOLD;
+            cnt[0] += above ? 0.0 : 1.0;
             cnt[1] += above ? 1.0 : 0.0;
+            cnt[2] += above ? (double)vS[i] * wS[i] : 0.0;
         }
-        scan_forward(r, cum);
-        ef_block_sum<2>(cnt, s.red);
-        double total[1] = {0.0};
-#pragma unroll
-        for (int k = 0; k < EF_BPT; k++) total[0] += r[k];
-        ef_block_sum<1>(total, s.red);
+        ef_block_sum<3>(cnt, s.red);
+        const double total = cnt[2];
         double best = -1.0;
-#pragma unroll
-        for (int k = 0; k < EF_BPT; k++)
-            if (r[k] > 0.0 && cum[k] / total[0] <= 0.25) best = fmax(best, v[k]);
+        scan_bins(false, [&](int i) { return vS[i] > DEFAULT_THRESHOLD ? (double)vS[i] * wS[i] : 0.0; },
+                  [&](int i, double cum) { if (vS[i] > DEFAULT_THRESHOLD && cum / total <= 0.25) best = fmax(best, (double)vS[i]); });
         best = ef_block_max(best, s.red);
         if (best > 0.0) t0 = (int)best;
         else if (cnt[1] >= 2.0) t0 = (int)a.values[(int)cnt[0] + 1];   // count_values[1]
@@ -433,20 +425,42 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
     long long iters = 0, inner = 0, direct = 0;
     int prev_inner = 1 << 20;     // iterations of the previous dispersion fixed point (first one: assume long)
     double prev_alpha = 0.0;      // its result: where the next bracket is looked for first
-    bool bail = false;        // a safety check failed inside the fast path: let k_em_fit redo the fit
     bool zerodiv = false;
 
-    // ---- M-step (peaks.py:90-128) on the register-resident responsibilities
-    auto m_step = [&](Th& th) -> bool {
+    // ---- fused E-step (peaks.py:66-87) + sums of the M-step (peaks.py:90-128).  hard = the initial assignment
+    //      of estimate_parameters (peaks.py:152-155).  Only the background weight o1 = w * r1 is stored.
+    auto em_update = [&](bool hard, Th& th) -> bool {
         EP_BEGIN();
         double acc[6] = {0, 0, 0, 0, 0, 0};
         double vmax1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < EF_BPT; k++) {
-            double o0 = w[k] * r0[k], o1 = w[k] * r1[k], o2 = w[k] * r2[k];
-            acc[0] += o0; acc[1] += v[k] * o0; acc[2] += o1; acc[3] += v[k] * o1; acc[4] += o2; acc[5] += v[k] * o2;
-            if (r1[k] > 0.0) vmax1 = fmax(vmax1, v[k]);
+        const double f_sig = 1.0 - th.f_zero - th.f_bg;
+        double nn = 0.0, lgn = 0.0, nlogp = 0.0, l1p = 0.0, lz = 0.0, ls = 0.0;
+        if (!hard) {
+            nn = 1.0 / th.alpha_bg;
+            const double pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+            lgn = lgamma(nn); nlogp = nn * log(pp); l1p = log1p(-pp);
+            lz = log(1.0 - th.p_zero); ls = log(1.0 - th.p_signal);
         }
+        for (int i = tid; i < n; i += EF_THREADS) {
+            const double v = (double)vS[i], w = wS[i];
+            double r0, r1, r2;
+            if (hard) {
+                r0 = v <= (double)DEFAULT_THRESHOLD ? 1.0 : 0.0;
+                r1 = (v <= (double)t0 && v > (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
+                r2 = v > (double)t0 ? 1.0 : 0.0;
+            } else {
+                const double z = exp((v - 1.0) * lz) * th.p_zero * th.f_zero;
+                const double b = exp(lgamma(nn + v) - lgS[i] - lgn + nlogp + v * l1p) * th.f_bg;
+                const double g = exp((v - 1.0) * ls) * th.p_signal * f_sig;
+                const double t = z + b + g;
+                if (t == 0.0) { r0 = r1 = r2 = 0.0; } else { r0 = z / t; r1 = b / t; r2 = g / t; }
+            }
+            const double o0 = w * r0, o1 = w * r1, o2 = w * r2;
+            acc[0] += o0; acc[1] += v * o0; acc[2] += o1; acc[3] += v * o1; acc[4] += o2; acc[5] += v * o2;
+            if (r1 > 0.0) vmax1 = fmax(vmax1, v);
+            o1S[i] = o1;
+        }
+        EP_END(s, EP_ESTEP);
         ef_block_sum<6>(acc, s.red);
         vmax1 = ef_block_max(vmax1, s.red);
         const double N0 = acc[0], K0 = acc[1], N1 = acc[2], M1 = acc[3], N2 = acc[4], K2 = acc[5];
@@ -460,38 +474,27 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         th.f_bg = N1 / FT;
         if (N1 == 0.0) { th.alpha_bg = 1e-6; return true; }
         double sq[1] = {0.0};
-#pragma unroll
-        for (int k = 0; k < EF_BPT; k++) { double d = mu - v[k]; sq[0] += d * d * (w[k] * r1[k]); }
+        for (int i = tid; i < n; i += EF_THREADS) { double d = mu - (double)vS[i]; sq[0] += d * d * o1S[i]; }
         ef_block_sum<1>(sq, s.red);
         const double var = sq[0] / N1;
         double alpha = fmax(1e-6, (var - mu) / (mu * mu));
         if (vmax1 > 1e8 || !(var > mu)) { th.alpha_bg = alpha; return true; }
         EP_END(s, EP_MSUMS);
         // tail weights T(j) = sum_{i: v_i > j} w_i r1_i : bin i covers j in [v_{i-1}, v_i)
-        {
-            double o1[EF_BPT], suf[EF_BPT];
-#pragma unroll
-            for (int k = 0; k < EF_BPT; k++) o1[k] = w[k] * r1[k];
-            scan_backward(o1, suf);
-#pragma unroll
-            for (int k = 0; k < EF_BPT; k++)
-                if (tid + k * EF_THREADS < n) {
-                    const int i = tid + k * EF_THREADS;
-                    const int jlo = i > 0 ? (int)a.values[i - 1] : 0;
-                    for (int j = jlo; j < (int)v[k]; j++) s.T[j] = suf[k];
-                }
-            __syncthreads();
-        }
+        scan_bins(true, [&](int i) { return o1S[i]; },
+                  [&](int i, double suf) { const int jlo = i > 0 ? vS[i - 1] : 0; for (int j = jlo; j < vS[i]; j++) Tw[j] = suf; });
+        __syncthreads();
         EP_END(s, EP_TFILL);
         const int jmax = (int)vmax1;
+        const double* T = s.Tp;
         auto G_block = [&](double al) {
             double part[1] = {0.0};
-            for (int j = tid + 1; j < jmax; j += EF_THREADS) { double aj = al * (double)j; part[0] = fma(ef_frac(aj), s.T[j], part[0]); }
+            for (int j = tid + 1; j < jmax; j += EF_THREADS) { double aj = al * (double)j; part[0] = fma(ef_frac(aj), T[j], part[0]); }
             ef_block_sum<1>(part, s.red);
             direct++;
             return log(1.0 + al * mu) / (mu - part[0] / N1);
         };
-        // Direct iterations alpha <- G(alpha) from evaluation `it` up to `limit` evaluations; true when the
+        // Direct iterations alpha <- G(alpha) from evaluation `itc` up to `limit` evaluations; true when the
         // reference's stopping test fired.  For short tables one warp runs the whole loop on its own (no block
         // barrier per iteration) and publishes the outcome; longer tables use the block-wide reduction.
         auto plain = [&](double& al, double& nv, int& itc, int limit) -> bool {
@@ -500,14 +503,13 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
                 if (warp == 0) {
                     long long nd = 0;
                     while (itc < limit) {
-                        double part = 0.0;
-                        double part2 = 0.0;
+                        double part = 0.0, part2 = 0.0;
                         int j = lane + 1;
                         for (; j + 32 < jmax; j += 64) {
-                            part = fma(ef_frac(al * (double)j), s.T[j], part);
-                            part2 = fma(ef_frac(al * (double)(j + 32)), s.T[j + 32], part2);
+                            part = fma(ef_frac(al * (double)j), T[j], part);
+                            part2 = fma(ef_frac(al * (double)(j + 32)), T[j + 32], part2);
                         }
-                        if (j < jmax) part = fma(ef_frac(al * (double)j), s.T[j], part);
+                        if (j < jmax) part = fma(ef_frac(al * (double)j), T[j], part);
                         part += part2;
 #pragma unroll
                         for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -559,25 +561,6 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         return true;
     };
 
-    auto e_step = [&](const Th& th) {   // peaks.py:66-87
-        EP_BEGIN();
-        const double f_sig = 1.0 - th.f_zero - th.f_bg;
-        const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
-        const double lgn = lgamma(nn), nlogp = nn * log(pp), l1p = log1p(-pp);
-        const double lz = log(1.0 - th.p_zero), ls = log(1.0 - th.p_signal);
-#pragma unroll
-        for (int k = 0; k < EF_BPT; k++) {
-            if (tid + k * EF_THREADS >= n) { r0[k] = r1[k] = r2[k] = 0.0; continue; }
-            double z = exp((v[k] - 1.0) * lz) * th.p_zero * th.f_zero;
-            double b = exp(lgamma(nn + v[k]) - lgk1[k] - lgn + nlogp + v[k] * l1p) * th.f_bg;
-            double g = exp((v[k] - 1.0) * ls) * th.p_signal * f_sig;
-            double t = z + b + g;
-            if (t == 0.0) { r0[k] = r1[k] = r2[k] = 0.0; }
-            else { r0[k] = z / t; r1[k] = b / t; r2[k] = g / t; }
-        }
-        EP_END(s, EP_ESTEP);
-    };
-
     auto moved = [](const Th& l, const Th& c) {
         const double eps = 1e-6;
         return (fabs(l.p_zero - c.p_zero) / c.p_zero > eps) || (fabs(l.mean_bg - c.mean_bg) / c.mean_bg > eps) ||
@@ -587,25 +570,18 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
 
     auto estimate_parameters = [&](bool seeded, Th& th) -> bool {   // peaks.py:144-170
         if (!seeded) {
-#pragma unroll
-            for (int k = 0; k < EF_BPT; k++) {
-                bool in = tid + k * EF_THREADS < n;
-                r0[k] = (in && v[k] <= (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
-                r1[k] = (in && v[k] <= (double)t0 && v[k] > (double)DEFAULT_THRESHOLD) ? 1.0 : 0.0;
-                r2[k] = (in && v[k] > (double)t0) ? 1.0 : 0.0;
-            }
-            if (!m_step(th)) return false;
+            th.p_zero = th.mean_bg = th.alpha_bg = th.p_signal = th.f_zero = th.f_bg = 0.0;
+            if (!em_update(true, th)) return false;
         }
         Th last = th;
         bool have_last = false;
         int i = 0;
         while (i < 500 && (!have_last || moved(last, th))) {
             i++;
-            e_step(th);
             last = th;
             have_last = true;
             Th nt = th;
-            if (!m_step(nt)) return false;
+            if (!em_update(false, nt)) return false;   // E-step with th, M-step into nt
             if (nt.p_zero < nt.p_signal) {   // normalize_params (peaks.py:131-141)
                 double pz = nt.p_signal, ps = nt.p_zero, fz = 1.0 - (nt.f_zero + nt.f_bg);
                 nt.p_zero = pz; nt.p_signal = ps; nt.f_zero = fz;
@@ -627,7 +603,6 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         ok = estimate_parameters(true, th);
         tries++;
     }
-    (void)bail;
     if (!ok) {
         if (tid == 0) { if (zerodiv) raise_error(a.status, CRATAC_ERR_EM_ZERODIV, n); a.status[ST_EM_MODE] = 2; }
         return;
@@ -654,19 +629,22 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
     }
 }
 
-// returns the dynamic shared memory the fast kernel needs
-size_t em_fast_smem() { return sizeof(EfSmem); }
+static size_t ef_smem_bytes() { return ((sizeof(EfSmem) + 15) & ~(size_t)15) + (size_t)EF_NS * (3 * 8 + 4); }
 
 int em_fast_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio) {
     static bool configured = false;
     if (!configured) {
-        CRATAC_CUDA(cudaFuncSetAttribute(k_em_fit_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EfSmem)));
+        CRATAC_CUDA(cudaFuncSetAttribute(k_em_fit_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ef_smem_bytes()));
         configured = true;
     }
+    // global scratch shared with the generic kernel's work buffer (em.cu sizes it: >= 6 * 65536 + 2^20 doubles)
     EfArgs a;
     a.values = d_values; a.weights = d_weights; a.n_bins_host = n_bins_host; a.status = c->d_status.as<int64_t>();
     a.params_out = c->d_em_params.as<double>(); a.odds_ratio = odds_ratio;
-    k_em_fit_fast<<<1, EF_THREADS, sizeof(EfSmem), c->stream>>>(a);
+    double* w = c->d_em_work.as<double>();
+    a.g_w = w; a.g_lg = w + EF_MAXN; a.g_o1 = w + 2 * EF_MAXN; a.g_v = reinterpret_cast<int*>(w + 3 * EF_MAXN);
+    a.g_T = w + 6 * (size_t)EF_MAXN + 2;      // the generic kernel's T region
+    k_em_fit_fast<<<1, EF_THREADS, ef_smem_bytes(), c->stream>>>(a);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     return CRATAC_OK;
