@@ -153,7 +153,7 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_em_params, &c->d_em_work, &c->d_chain, &c->d_tile_summary, &c->d_run_start, &c->d_run_end, &c->d_bridge, &c->d_fill,
                       &c->d_peak_chrom, &c->d_peak_start, &c->d_peak_end, &c->d_peak_row, &c->d_peak_off, &c->d_bc_hits, &c->d_seg_off,
                       &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
-                      &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey};
+                      &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_bc_hash) cudaFreeHost(c->h_bc_hash);

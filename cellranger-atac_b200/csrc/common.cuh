@@ -96,7 +96,9 @@ struct Ctx {
     int64_t n_fragments = 0;
     DevBuf d_chrom, d_start, d_end, d_bc, d_dup;
     DevBuf d_contig_frag_off;              // int64[n_contigs+1]
-    DevBuf d_pos_index;                    // int32 per 1024 bases (fragment index relative to 0)
+    DevBuf d_pos_index;                    // int64 per 1024 bases: first fragment with start >= k * 1024
+    DevBuf d_tile_desc;                    // per pileup tile: contig, extent, fragment range
+    bool tile_desc_valid = false;
     // text
     const char* d_text = nullptr;          // borrowed or owned device text of the last decode
     int64_t text_bytes = 0;

@@ -20,12 +20,13 @@
 namespace cratac {
 
 constexpr int PU_THREADS = 512;
-constexpr int PU_CHUNK = 49;                        // odd -> bank-conflict-free thread-chunked access
-constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entries (25088)
+constexpr int PU_CHUNK = 44;                        // 4 x odd: thread-chunked 128-bit shared accesses are bank-conflict free
+constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entries (22528)
+constexpr int PU_PAD = 64;                          // slack for vector over-reads past the last window
 constexpr int PU_HALO_LO = HALF_WINDOW + 2;         // 202
 constexpr int PU_HALO_HI = HALF_WINDOW + 1;         // 201 (positions up to b + 200)
 constexpr int TILE_T = PU_N - PU_HALO_LO - PU_HALO_HI + 1;   // owned bases per tile (24686)
-constexpr int PU_OWN_CHUNK = (TILE_T + PU_THREADS - 1) / PU_THREADS | 1;   // 49, odd
+constexpr int PU_OWN_CHUNK = PU_CHUNK;              // owned bases per thread (multiple of 4)
 constexpr int PU_HB = 2048;                         // block-local histogram bins
 static_assert(PU_OWN_CHUNK * PU_THREADS >= TILE_T, "owned chunking must cover the tile");
 static_assert(TILE_T + 402 <= PU_N, "tile + halos must fit the shared array");
@@ -34,7 +35,15 @@ enum { MODE_HIST = 0, MODE_PEAKS = 1, MODE_DUMP = 2 };
 
 int pileup_tile_bases() { return TILE_T; }
 
+// everything a CTA needs to start on a tile, precomputed once per fragment set (k_tile_desc)
+struct __align__(16) TileDesc {
+    int32_t contig, own;        // contig id, owned bases
+    int64_t ta;                 // first owned base (contig coordinate)
+    int64_t i_lo, i_hi;         // fragment index range whose cut sites can fall into the tile's window
+};
+
 struct PileupArgs {
+    const TileDesc* desc;
     const int32_t* start;
     const int32_t* end;
     const int64_t* frag_off;        // per contig
@@ -90,17 +99,59 @@ __device__ __forceinline__ int block_excl_scan_i32(int v, int* warp_tot, int* to
     return r;
 }
 
+// W(k) = S[k + 402] - S[k + 1] for the bases k0 <= k < k1 of one thread (k0 a multiple of 4), four at a time
+// from 128-bit shared loads: the two prefix streams are offset by 2 and 1 words from 16-byte alignment, so each
+// group of four windows combines two consecutive vectors of each stream.
+__global__ void k_tile_desc(PileupArgs a, TileDesc* __restrict__ out) {
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= a.n_tiles) return;
+    int lo = 0, hi = a.n_contigs;   // last c with tile_off[c] <= tile
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.tile_off[mid] <= tile) lo = mid; else hi = mid; }
+    const int c = lo;
+    const int64_t L = a.contig_lens[c];
+    const int64_t ta = (tile - a.tile_off[c]) * (int64_t)TILE_T;
+    const int64_t tb = ta + TILE_T < L ? ta + TILE_T : L;
+    const int64_t base = ta - PU_HALO_LO;
+    const int maxpos = (int)a.status[ST_MAX_POS_LEN], maxneg = (int)a.status[ST_MAX_NEG_LEN];
+    const int64_t f0 = a.frag_off[c], f1 = a.frag_off[c + 1];
+    const int64_t n_ent = a.pidx_off[c + 1] - a.pidx_off[c];
+    int64_t lo_pos = base - maxpos; if (lo_pos < 0) lo_pos = 0;
+    const int64_t hi_pos = base + PU_N + maxneg;                              // exclusive
+    const int64_t e_lo = lo_pos >> POS_INDEX_SHIFT;
+    const int64_t e_hi = (hi_pos + (1 << POS_INDEX_SHIFT) - 1) >> POS_INDEX_SHIFT;
+    int64_t i_lo = e_lo >= n_ent ? f1 : a.pos_index[a.pidx_off[c] + e_lo];
+    const int64_t i_hi = e_hi >= n_ent - 1 ? f1 : a.pos_index[a.pidx_off[c] + e_hi];
+    if (i_lo < f0) i_lo = f0;
+    TileDesc d;
+    d.contig = c; d.own = (int)(tb - ta); d.ta = ta; d.i_lo = i_lo; d.i_hi = i_hi;
+    out[tile] = d;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_each_window(const int* sc, int k0, int k1, F&& body) {
+    if (k0 >= k1) return;
+    const int4* U4 = reinterpret_cast<const int4*>(sc + k0 + 400);
+    const int4* V4 = reinterpret_cast<const int4*>(sc + k0);
+    int4 u = U4[0], v = V4[0];
+    for (int k = k0, j = 1; k < k1; k += 4, j++) {
+        const int4 un = U4[j], vn = V4[j];
+        body(k, u.z - v.y);
+        if (k + 1 < k1) body(k + 1, u.w - v.z);
+        if (k + 2 < k1) body(k + 2, un.x - v.w);
+        if (k + 3 < k1) body(k + 3, un.y - vn.x);
+        u = un; v = vn;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
-    extern __shared__ int smem[];
-    int* sc = smem;                       // PU_N
-    int* hist_s = smem + PU_N;            // PU_HB (MODE_HIST)
+    extern __shared__ __align__(16) int smem[];
+    int* sc = smem;                       // PU_N (+ PU_PAD)
+    int* hist_s = smem + PU_N + PU_PAD;   // PU_HB (MODE_HIST)
     __shared__ int warp_tot[PU_THREADS / 32];
-    __shared__ long long s_tile;
     __shared__ int s_first_nz, s_last_nz;
     __shared__ long long s_base_s, s_base_e;
     __shared__ int s_cur_s, s_cur_e;
-    __shared__ int s_contig;
 
     const int tid = threadIdx.x;
     if (MODE == MODE_HIST)
@@ -112,53 +163,52 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
     int loc_max = 0;
     if (MODE == MODE_PEAKS && tid == 0) { s_cur_s = 0; s_cur_e = 0; }
 
+    // tiles come from a ticket counter; the ticket of the NEXT tile is taken while the current one is processed
+    __shared__ long long s_next;
+    if (tid == 0) s_next = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
     while (true) {
         __syncthreads();
+        const long long tile = s_next;
+        __syncthreads();
+        if (tile >= a.n_tiles) break;
         if (tid == 0) {
-            long long t = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
-            s_tile = t;
-            int c = 0;
-            if (t < a.n_tiles) {
-                int lo = 0, hi = a.n_contigs;   // last c with tile_off[c] <= t
-                while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
-                    if (a.tile_off[mid] <= t) lo = mid; else hi = mid;
-                }
-                c = lo;
-            }
-            s_contig = c;
+            s_next = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
             s_first_nz = 0x7fffffff;
             s_last_nz = -1;
         }
-        __syncthreads();
-        const long long tile = s_tile;
-        if (tile >= a.n_tiles) break;
-        const int c = s_contig;
+        const TileDesc td = a.desc[tile];
+        const int c = td.contig;
         const int64_t L = a.contig_lens[c];
-        const int64_t ta = (tile - a.tile_off[c]) * (int64_t)TILE_T;           // first owned base
-        const int64_t tb = ta + TILE_T < L ? ta + TILE_T : L;                  // one past the last owned base
-        const int own = (int)(tb - ta);
+        const int64_t ta = td.ta;
+        const int64_t tb = ta + td.own;
+        const int own = td.own;
         const int64_t base = ta - PU_HALO_LO;                                  // genome position of sc[0]
 
         if (MODE == MODE_DUMP && c != a.dump_contig) continue;
 
         // ---- zero the count array
-#pragma unroll 7
-        for (int r = tid; r < PU_N; r += PU_THREADS) sc[r] = 0;
-        __syncthreads();
-
-        // ---- fragments that can touch [base, base + PU_N)
+        // ---- issue the first fragment loads, zero the count array while they fly, then scatter
         {
-            const int64_t f0 = a.frag_off[c], f1 = a.frag_off[c + 1];
-            const int64_t n_ent = a.pidx_off[c + 1] - a.pidx_off[c];
-            int64_t lo_pos = base - maxpos; if (lo_pos < 0) lo_pos = 0;
-            int64_t hi_pos = base + PU_N + maxneg;                              // exclusive
-            int64_t e_lo = lo_pos >> POS_INDEX_SHIFT;
-            int64_t e_hi = (hi_pos + (1 << POS_INDEX_SHIFT) - 1) >> POS_INDEX_SHIFT;
-            int64_t i_lo = e_lo >= n_ent - 1 ? (e_lo >= n_ent ? f1 : a.pos_index[a.pidx_off[c] + e_lo]) : a.pos_index[a.pidx_off[c] + e_lo];
-            int64_t i_hi = e_hi >= n_ent - 1 ? f1 : a.pos_index[a.pidx_off[c] + e_hi];
-            if (i_lo < f0) i_lo = f0;
-            for (int64_t i = i_lo + tid; i < i_hi; i += PU_THREADS) {
+            constexpr int PRE = 4;
+            const int64_t i_lo = td.i_lo, i_hi = td.i_hi;
+            int fs[PRE], fe[PRE];
+#pragma unroll
+            for (int q = 0; q < PRE; q++) {
+                const int64_t i = i_lo + tid + (int64_t)q * PU_THREADS;
+                fs[q] = i < i_hi ? a.start[i] : -0x40000000;
+                fe[q] = i < i_hi ? a.end[i] : -0x40000000;
+            }
+            int4* z = reinterpret_cast<int4*>(sc);
+#pragma unroll
+            for (int r = tid; r < PU_N / 4; r += PU_THREADS) z[r] = make_int4(0, 0, 0, 0);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < PRE; q++) {
+                int64_t rs = (int64_t)fs[q] - base, re = (int64_t)fe[q] - base;
+                if ((uint64_t)rs < (uint64_t)PU_N) atomicAdd(&sc[rs], 1);
+                if ((uint64_t)re < (uint64_t)PU_N) atomicAdd(&sc[re], 1);
+            }
+            for (int64_t i = i_lo + tid + (int64_t)PRE * PU_THREADS; i < i_hi; i += PU_THREADS) {
                 int64_t rs = (int64_t)a.start[i] - base;
                 int64_t re = (int64_t)a.end[i] - base;
                 if ((uint64_t)rs < (uint64_t)PU_N) atomicAdd(&sc[rs], 1);
@@ -167,15 +217,20 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
         }
         __syncthreads();
 
-        // ---- in-place inclusive prefix sum (thread-chunked, odd chunk => no bank conflicts)
+        // ---- in-place inclusive prefix sum (thread-chunked, 128-bit accesses)
         {
-            int* mine = sc + tid * PU_CHUNK;
+            int4* mine = reinterpret_cast<int4*>(sc + tid * PU_CHUNK);
             int sum = 0;
-#pragma unroll 7
-            for (int j = 0; j < PU_CHUNK; j++) sum += mine[j];
+#pragma unroll
+            for (int j = 0; j < PU_CHUNK / 4; j++) { const int4 q = mine[j]; sum += (q.x + q.y) + (q.z + q.w); }
             int run = block_excl_scan_i32(sum, warp_tot, nullptr);
-#pragma unroll 7
-            for (int j = 0; j < PU_CHUNK; j++) { run += mine[j]; mine[j] = run; }
+#pragma unroll
+            for (int j = 0; j < PU_CHUNK / 4; j++) {
+                int4 q = mine[j];
+                q.x += run; q.y += q.x; q.z += q.y; q.w += q.z;
+                run = q.w;
+                mine[j] = q;
+            }
         }
         __syncthreads();
 
@@ -185,24 +240,22 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
 
         if (MODE == MODE_HIST) {
             int cur = 0, runlen = 0;
-            for (int k = k0; k < k1; k++) {
-                int w = sc[k + 402] - sc[k + 1];
-                if (w == cur) { runlen++; continue; }
+            auto flush = [&]() {
                 if (cur > 0) {
                     if (cur < PU_HB) atomicAdd(&hist_s[cur], runlen);
                     else if (cur < HIST_CAP) atomicAdd(&a.ghist[cur], (unsigned long long)runlen);
                     else raise_error(a.status, CRATAC_ERR_CAPACITY, cur);
                 }
+            };
+            for_each_window(sc, k0, k1, [&](int, int w) {
+                if (w == cur) { runlen++; return; }
+                flush();
                 loc_max = max(loc_max, w);
                 cur = w; runlen = 1;
-            }
-            if (cur > 0) {
-                if (cur < PU_HB) atomicAdd(&hist_s[cur], runlen);
-                else if (cur < HIST_CAP) atomicAdd(&a.ghist[cur], (unsigned long long)runlen);
-                else raise_error(a.status, CRATAC_ERR_CAPACITY, cur);
-            }
+            });
+            flush();
         } else if (MODE == MODE_DUMP) {
-            for (int k = k0; k < k1; k++) a.dump_W[ta + k] = sc[k + 402] - sc[k + 1];
+            for_each_window(sc, k0, k1, [&](int k, int w) { a.dump_W[ta + k] = w; });
         } else {
             // ---- run boundaries of (W >= thr), first/last non-zero W, in-tile zero gaps
             int n_s = 0, n_e = 0;
@@ -211,8 +264,7 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
             if (k0 < k1 && (k0 > 0 || ta > 0)) prev_w = sc[k0 + 401] - sc[k0];   // W at base ta + k0 - 1
             {
                 int pw = prev_w;
-                for (int k = k0; k < k1; k++) {
-                    int w = sc[k + 402] - sc[k + 1];
+                for_each_window(sc, k0, k1, [&](int k, int w) {
                     bool sig = w >= thr, psig = pw >= thr;
                     n_s += (sig && !psig);
                     n_e += (!sig && psig);
@@ -231,7 +283,9 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
                         }
                     }
                     pw = w;
-                }
+                });
+                const int pw_last = pw;
+                pw = pw_last;
                 // the contig's last base closes an open run at L
                 if (k1 == own && k0 < k1 && tb == L && pw >= thr) n_e += 1;
             }
@@ -440,6 +494,7 @@ __global__ void k_peak_offsets(const int32_t* __restrict__ pk_chrom, const int64
 int compute_max_len(Ctx* c);   // decode.cu
 
 static int fill_args(Ctx* c, PileupArgs& a) {
+    a.desc = c->d_tile_desc.as<TileDesc>();
     a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
     a.frag_off = c->d_contig_frag_off.as<int64_t>(); a.pos_index = c->d_pos_index.as<int64_t>();
     a.pidx_off = c->d_contig_pidx_off.as<int64_t>(); a.contig_lens = c->d_contig_lens.as<int64_t>();
@@ -452,7 +507,21 @@ static int fill_args(Ctx* c, PileupArgs& a) {
     return CRATAC_OK;
 }
 
-static size_t pileup_smem(int mode) { return sizeof(int) * (PU_N + (mode == MODE_HIST ? PU_HB : 0)); }
+static size_t pileup_smem(int mode) { return sizeof(int) * (PU_N + PU_PAD + (mode == MODE_HIST ? PU_HB : 0)); }
+
+// per-tile descriptors: valid for the current fragment set (recomputed whenever the fragments changed)
+static int ensure_tile_desc(Ctx* c, PileupArgs& a) {
+    if (c->tile_desc_valid) return CRATAC_OK;
+    if (a.n_tiles > 0) {
+        CRATAC_TRY(c->d_tile_desc.reserve(sizeof(TileDesc) * (size_t)a.n_tiles));
+        a.desc = c->d_tile_desc.as<TileDesc>();
+        k_tile_desc<<<(unsigned)((a.n_tiles + 255) / 256), 256, 0, c->stream>>>(a, c->d_tile_desc.as<TileDesc>());
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    c->tile_desc_valid = true;
+    return CRATAC_OK;
+}
 
 template <int MODE>
 static int launch_pileup(Ctx* c, PileupArgs& a) {
@@ -461,6 +530,7 @@ static int launch_pileup(Ctx* c, PileupArgs& a) {
         CRATAC_CUDA(cudaFuncSetAttribute(k_pileup<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pileup_smem(MODE)));
         configured = true;
     }
+    CRATAC_TRY(ensure_tile_desc(c, a));
     int64_t* st = c->d_status.as<int64_t>();
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), c->stream));
     int64_t grid = std::min<int64_t>(a.n_tiles, 2 * NUM_SMS);
