@@ -239,21 +239,28 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
         const int k1 = min(k0 + PU_OWN_CHUNK, own);
 
         if (MODE == MODE_HIST) {
+            // run-length aggregated histogram update, branch-free on the common path: one predicated shared-memory
+            // reduction per change of W (counts >= PU_HB go to the global histogram on a rare slow path)
             int cur = 0, runlen = 0;
-            auto flush = [&]() {
-                if (cur > 0) {
-                    if (cur < PU_HB) atomicAdd(&hist_s[cur], runlen);
-                    else if (cur < HIST_CAP) atomicAdd(&a.ghist[cur], (unsigned long long)runlen);
-                    else raise_error(a.status, CRATAC_ERR_CAPACITY, cur);
-                }
+            const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(hist_s);
+            auto flush_slow = [&](int v, int len) {
+                if (v < HIST_CAP) atomicAdd(&a.ghist[v], (unsigned long long)len);
+                else raise_error(a.status, CRATAC_ERR_CAPACITY, v);
             };
             for_each_window(sc, k0, k1, [&](int, int w) {
-                if (w == cur) { runlen++; return; }
-                flush();
+                const bool changed = w != cur;
+                if (changed && cur > 0) {
+                    if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
+                    else flush_slow(cur, runlen);
+                }
                 loc_max = max(loc_max, w);
-                cur = w; runlen = 1;
+                runlen = changed ? 1 : runlen + 1;
+                cur = w;
             });
-            flush();
+            if (cur > 0) {
+                if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
+                else flush_slow(cur, runlen);
+            }
         } else if (MODE == MODE_DUMP) {
             for_each_window(sc, k0, k1, [&](int k, int w) { a.dump_W[ta + k] = w; });
         } else {
