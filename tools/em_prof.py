@@ -10,4 +10,4 @@ for c in cases:
         ctx.fit_threshold(c['values'], c['weights'], 0.2)
         t=time.time(); thr,p,st=ctx.fit_threshold(c['values'], c['weights'], 0.2); dt=time.time()-t
         dbg=ctx.em_debug(); tot=sum(dbg.values())
-        print(c['name'], 'fast',fast, 'ms %.2f'%(dt*1e3), st, {k: round(v/max(st['em_iterations'],1)) for k,v in dbg.items()}, 'cyc/iter total', round(tot/max(st['em_iterations'],1)))
+        print(c["name"], "fast", fast, "ms %.2f" % (dt*1e3), st, {k: round(v/max(st['em_iterations'],1)) for k,v in dbg.items()}, 'cyc/iter total', round(tot/max(st['em_iterations'],1)))
