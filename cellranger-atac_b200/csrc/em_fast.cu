@@ -138,11 +138,12 @@ __device__ __forceinline__ void ef_eval_points(EfSmem& s, int jmax, double mu, d
     const double alpha = s.pts[grp < n_active ? grp : 0];
     double p0 = 0.0, p1 = 0.0;
     int j = grp < n_active ? 1 + sub : jmax;
-    for (; j + TPP < jmax; j += 2 * TPP) {
-        p0 = fma(ef_frac(alpha, (double)j), s.Tp[j], p0);
-        p1 = fma(ef_frac(alpha, (double)(j + TPP)), s.Tp[j + TPP], p1);
+    double jd = (double)j;                  // carried as a double: no int -> double conversion per term
+    for (; j + TPP < jmax; j += 2 * TPP, jd += (double)(2 * TPP)) {
+        p0 = fma(ef_frac(alpha, jd), s.Tp[j], p0);
+        p1 = fma(ef_frac(alpha, jd + (double)TPP), s.Tp[j + TPP], p1);
     }
-    if (j < jmax) p0 = fma(ef_frac(alpha, (double)j), s.Tp[j], p0);
+    if (j < jmax) p0 = fma(ef_frac(alpha, jd), s.Tp[j], p0);
     double part = p0 + p1;
 #pragma unroll
     for (int d = TPP / 2; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -180,7 +181,8 @@ __device__ __forceinline__ double ef_bary_group(const EfSmem& s, const double* f
 __device__ __forceinline__ double ef_G_block(EfSmem& s, int jmax, double mu, double N1, double al) {
     const double* T = s.Tp;
     double part[1] = {0.0};
-    for (int j = threadIdx.x + 1; j < jmax; j += EF_THREADS) part[0] = fma(ef_frac(al, (double)j), T[j], part[0]);
+    double jd = (double)(threadIdx.x + 1);
+    for (int j = threadIdx.x + 1; j < jmax; j += EF_THREADS, jd += (double)EF_THREADS) part[0] = fma(ef_frac(al, jd), T[j], part[0]);
     ef_block_sum<1>(part, s.red);
     return log(1.0 + al * mu) / (mu - part[0] / N1);
 }
@@ -249,7 +251,6 @@ __device__ __noinline__ bool ef_jump(int jmax, double mu, double N1, double alph
     __syncthreads();
     if (!s.flag) return false;
     EP_END(s, EP_NODES);
-    if (tid == 0) s.cyc[EP_NCOEF] += 1;   // jumps taken this far
     // ---- x_c: last point on the path (from x0 towards the bracket end) whose step is still >= eps * (1 + 1e-3);
     //      7 rounds of 16-way sectioning, one warp per trial point.  x_c only has to be on the early side of the
     //      crossing: a resolution of 16^-7 of the path costs at most a fraction of one extra direct iteration.
@@ -471,15 +472,35 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         if (vmax1 > 1e8 || !(var > mu)) { th.alpha_bg = alpha; return true; }
         EP_END(s, EP_MSUMS);
         // tail weights T(j) = sum_{i: v_i > j} w_i r1_i : bin i covers j in [v_{i-1}, v_i)
-        scan_bins(true, [&](int i) { return o1S[i]; },
-                  [&](int i, double suf) { const int jlo = i > 0 ? vS[i - 1] : 0; for (int j = jlo; j < vS[i]; j++) Tw[j] = suf; });
+        // (thread t owns the contiguous bins [t * per, (t + 1) * per): one block-wide suffix scan of the thread sums,
+        // then a serial walk down the thread's own bins)
+        {
+            const int per = (n + EF_THREADS - 1) / EF_THREADS;
+            const int b0 = min(n, tid * per), b1 = min(n, b0 + per);
+            double loc = 0.0;
+            for (int i = b0; i < b1; i++) loc += o1S[i];
+            double inc = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_down_sync(0xffffffffu, inc, d); if (lane + d < 32) inc += y; }
+            __syncthreads();
+            if (lane == 0) s.wtot[warp] = inc;
+            __syncthreads();
+            double run = inc - loc;
+            for (int q = warp + 1; q < EF_WARPS; q++) run += s.wtot[q];
+            for (int i = b1 - 1; i >= b0; i--) {
+                run += o1S[i];
+                const int jlo = i > 0 ? vS[i - 1] : 0;
+                for (int j = jlo; j < vS[i]; j++) Tw[j] = run;
+            }
+        }
         __syncthreads();
         EP_END(s, EP_TFILL);
         const int jmax = (int)vmax1;
         const double* T = s.Tp;
         auto G_block = [&](double al) {
             double part[1] = {0.0};
-            for (int j = tid + 1; j < jmax; j += EF_THREADS) part[0] = fma(ef_frac(al, (double)j), T[j], part[0]);
+            double jd = (double)(tid + 1);
+            for (int j = tid + 1; j < jmax; j += EF_THREADS, jd += (double)EF_THREADS) part[0] = fma(ef_frac(al, jd), T[j], part[0]);
             ef_block_sum<1>(part, s.red);
             direct++;
             return log(1.0 + al * mu) / (mu - part[0] / N1);
@@ -489,7 +510,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         // barrier per iteration) and publishes the outcome; longer tables use the block-wide reduction.
         auto plain = [&](double& al, double& nv, int& itc, int limit) -> bool {
             bool stop = false;
-            if (jmax <= 2048) {
+            if (jmax <= 512) {
                 if (warp == 0) {
                     long long nd = 0;
                     while (itc < limit) {
@@ -622,6 +643,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         a.params_out[0] = th.p_zero; a.params_out[1] = th.mean_bg; a.params_out[2] = th.alpha_bg;
         a.params_out[3] = th.p_signal; a.params_out[4] = th.f_zero; a.params_out[5] = th.f_bg;
         for (int q = 0; q < EP_COUNT; q++) a.params_out[8 + q] = (double)s.cyc[q];
+        a.params_out[8 + EP_NCOEF] = (double)direct;   // reported as direct evaluations of G
     }
 }
 
