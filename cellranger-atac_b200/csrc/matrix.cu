@@ -21,6 +21,7 @@ namespace cratac {
 constexpr int MX_THREADS = 256;
 constexpr int SORT_SMALL = 4096;        // bitonic path capacity
 constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARP = 1024;         // segments up to this length are sorted by a single warp
 constexpr int COUNT_RANGE = 24576;      // counters per pass on the dense path (96 KiB)
 constexpr int COUNT_THREADS = 512;
 
@@ -136,9 +137,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __
     for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
         const int64_t o0 = seg_off[b];
         const int64_t len64 = seg_off[b + 1] - o0;
-        if (len64 > SORT_SMALL) continue;                 // long path
+        if (len64 > SORT_SMALL || len64 <= SORT_WARP) continue;   // long path / warp path
         const int len = (int)len64;
-        if (len == 0) { if (threadIdx.x == 0) nnz_col[b] = 0; continue; }
         int m = 32;
         while (m < len) m <<= 1;
         __syncthreads();
@@ -185,42 +185,115 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __
     }
 }
 
+// very short segments (most barcodes of a library are background with a few dozen hits): one warp per barcode,
+// bitonic sort in the warp's own slice of shared memory, no block barriers
+__global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
+                                                               int64_t n_bc, int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
+                                                               int32_t* __restrict__ nnz_col) {
+    __shared__ int s_all[(SORT_THREADS / 32) * SORT_WARP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* s = s_all + warp * SORT_WARP;
+    const int64_t n_warps = (int64_t)gridDim.x * (SORT_THREADS / 32);
+    for (int64_t b = (int64_t)blockIdx.x * (SORT_THREADS / 32) + warp; b < n_bc; b += n_warps) {
+        const int64_t o0 = seg_off[b];
+        const int64_t len64 = seg_off[b + 1] - o0;
+        if (len64 > SORT_WARP) continue;
+        const int len = (int)len64;
+        if (len == 0) { if (lane == 0) nnz_col[b] = 0; continue; }
+        int m = 32;
+        while (m < len) m <<= 1;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) s[i] = i < len ? hits[o0 + i] : 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                // m / 2 compare-exchanges: pair index q -> element i with bit j clear
+                for (int q = lane; q < (m >> 1); q += 32) {
+                    const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+                    const int x = s[i], y = s[i | j];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s[i] = y; s[i | j] = x; }
+                }
+                __syncwarp();
+            }
+        }
+        int base = 0;
+        for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            const int head = (i < len) && (i == 0 || s[i] != s[i - 1]);
+            const unsigned hm = __ballot_sync(0xffffffffu, head);
+            if (head) {
+                int e = i + 1;
+                while (e < len && s[e] == s[i]) e++;
+                const int pos = base + __popc(hm & ((1u << lane) - 1u));
+                out_row[o0 + pos] = s[i];
+                out_cnt[o0 + pos] = e - i;
+            }
+            base += __popc(hm);
+        }
+        if (lane == 0) nnz_col[b] = base;
+    }
+}
+
 // long segments: counting over peak-row ranges of COUNT_RANGE rows held in shared memory
 __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
                                                                  int64_t n_bc, const int64_t* __restrict__ status, int64_t n_peaks_host,
                                                                  int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                  int32_t* __restrict__ nnz_col) {
-    extern __shared__ int cnt[];           // COUNT_RANGE counters, then COUNT_RANGE / 32 bitmap words
+    extern __shared__ int cnt[];           // COUNT_RANGE counter words, then 2 * COUNT_RANGE / 32 bitmap words
     unsigned* bm = reinterpret_cast<unsigned*>(cnt + COUNT_RANGE);
     __shared__ int warp_tot[COUNT_THREADS / 32];
     __shared__ int s_base;
     const int64_t n_peaks = n_peaks_host >= 0 ? n_peaks_host : status[ST_N_PEAKS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // counters and bitmap start clean and are cleaned again as they are emitted: no clearing pass per range
+    for (int i = threadIdx.x; i < COUNT_RANGE + 2 * COUNT_RANGE / 32; i += COUNT_THREADS) cnt[i] = 0;
     for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
         const int64_t o0 = seg_off[b];
         const int64_t len = seg_off[b + 1] - o0;
         if (len <= SORT_SMALL) continue;
+        if (len > 0x7fffffffLL) { if (threadIdx.x == 0) raise_error(const_cast<int64_t*>(status), CRATAC_ERR_CAPACITY, b); continue; }
         __syncthreads();
         if (threadIdx.x == 0) s_base = 0;
-        for (int64_t r0 = 0; r0 < n_peaks; r0 += COUNT_RANGE) {
-            for (int i = threadIdx.x; i < COUNT_RANGE; i += COUNT_THREADS) cnt[i] = 0;
-            __syncthreads();
-            for (int64_t i = threadIdx.x; i < len; i += COUNT_THREADS) {
-                int64_t r = (int64_t)hits[o0 + i] - r0;
-                if ((uint64_t)r < (uint64_t)COUNT_RANGE) atomicAdd(&cnt[r], 1);
+        // a segment shorter than 65536 cannot overflow 16-bit counters: two per word, twice the rows per pass
+        const bool half = len < 65536;
+        const int range = half ? 2 * COUNT_RANGE : COUNT_RANGE;
+        for (int64_t r0 = 0; r0 < n_peaks; r0 += range) {
+            // count; the first hit of a row also sets its bit in the occupancy bitmap.  Eight loads in flight per
+            // thread: the loop is bound by the latency of the global loads otherwise.
+            constexpr int UN = 8;
+            const int32_t* __restrict__ seg = hits + o0;
+            const int len32 = (int)len, r0_32 = (int)r0;
+            for (int i0 = threadIdx.x; i0 < len32; i0 += UN * COUNT_THREADS) {
+                unsigned r[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int i = i0 + u * COUNT_THREADS;
+                    r[u] = i < len32 ? (unsigned)(seg[i] - r0_32) : 0xFFFFFFFFu;
+                }
+                unsigned old[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    old[u] = 1u;
+                    if (r[u] < (unsigned)range) {
+                        if (half) {
+                            const int sh = 16 * (r[u] & 1u);
+                            old[u] = ((unsigned)atomicAdd(&cnt[r[u] >> 1], 1 << sh) >> sh) & 0xFFFFu;
+                        } else {
+                            old[u] = (unsigned)atomicAdd(&cnt[r[u]], 1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++)
+                    if (old[u] == 0u) atomicOr(&bm[r[u] >> 5], 1u << (r[u] & 31u));
             }
             __syncthreads();
-            const int lim = (n_peaks - r0) < (int64_t)COUNT_RANGE ? (int)(n_peaks - r0) : COUNT_RANGE;
-            // occupancy bitmap of the counters (one ballot per warp per 32 counters), then emit only the set bits
-            for (int i0 = 0; i0 < COUNT_RANGE; i0 += COUNT_THREADS) {
-                int i = i0 + threadIdx.x;
-                unsigned m = __ballot_sync(0xffffffffu, i < lim && cnt[i] != 0);
-                if (lane == 0) bm[i >> 5] = m;
-            }
-            __syncthreads();
-            for (int w0 = 0; w0 < COUNT_RANGE / 32; w0 += COUNT_THREADS) {
-                int wi = w0 + threadIdx.x;
-                unsigned word = wi < COUNT_RANGE / 32 ? bm[wi] : 0u;
+            // emit the set bits in row order
+            for (int w0 = 0; w0 < range / 32; w0 += COUNT_THREADS) {
+                const int wi = w0 + threadIdx.x;
+                unsigned word = wi < range / 32 ? bm[wi] : 0u;
+                const unsigned word0 = word;
                 int c = __popc(word);
                 int x = c;
 #pragma unroll
@@ -231,12 +304,21 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
                 for (int w = 0; w < warp; w++) off += warp_tot[w];
                 int64_t pos = o0 + off + x - c;
                 while (word) {
-                    int bit = __ffs(word) - 1;
+                    const int bit = __ffs(word) - 1;
                     word &= word - 1;
-                    int row = wi * 32 + bit;
+                    const int row = wi * 32 + bit;
                     out_row[pos] = (int32_t)(r0 + row);
-                    out_cnt[pos] = cnt[row];
+                    out_cnt[pos] = half ? (int)(((unsigned)cnt[row >> 1] >> (16 * (row & 1))) & 0xFFFFu) : cnt[row];
                     pos++;
+                }
+                if (word0) {   // this thread owns the 32 rows of its bitmap word: clean up behind it
+                    bm[wi] = 0u;
+                    word = word0;
+                    while (word) {
+                        const int row = wi * 32 + __ffs(word) - 1;
+                        word &= word - 1;
+                        cnt[half ? row >> 1 : row] = 0;
+                    }
                 }
                 __syncthreads();
                 if (threadIdx.x == COUNT_THREADS - 1) s_base = off + x;
@@ -255,20 +337,40 @@ __global__ void k_gather_nnz(const int32_t* __restrict__ nnz_col, const int32_t*
     out[j] = d >= 0 ? nnz_col[d] : 0;       // d < 0: the barcode of this (global) column does not occur in this shard
 }
 
-// one warp per column
+// One CTA per CSC_CHUNK consecutive output entries (not per column: a cell's column is 100x a background
+// barcode's).  The columns a chunk touches are found by two binary searches in indptr; a chunk inside few
+// columns is copied by the whole CTA column after column, a chunk over many short columns one warp per column.
+constexpr int CSC_CHUNK = 4096;
 __global__ void __launch_bounds__(256) k_csc_copy(const int32_t* __restrict__ out_row, const int32_t* __restrict__ out_cnt, const int64_t* __restrict__ seg_off,
-                                                   const int32_t* __restrict__ col_to_dense, const int64_t* __restrict__ indptr, int64_t n_bc,
+                                                   const int32_t* __restrict__ col_to_dense, const int64_t* __restrict__ indptr, int64_t n_cols, int64_t nnz,
                                                    int64_t* __restrict__ indices, int32_t* __restrict__ data) {
-    const int lane = threadIdx.x & 31;
-    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t j = warp; j < n_bc; j += n_warps) {
-        int64_t d = col_to_dense ? col_to_dense[j] : j;
-        if (d < 0) continue;
-        int64_t src = seg_off[d], dst = indptr[j], len = indptr[j + 1] - dst;
-        for (int64_t k = lane; k < len; k += 32) {
-            indices[dst + k] = (int64_t)out_row[src + k];
-            data[dst + k] = out_cnt[src + k];
+    __shared__ int64_t s_j[2];
+    const int64_t p0 = (int64_t)blockIdx.x * CSC_CHUNK;
+    const int64_t p1 = p0 + CSC_CHUNK < nnz ? p0 + CSC_CHUNK : nnz;
+    if (threadIdx.x < 2) {       // largest j < n_cols with indptr[j] <= target
+        const int64_t target = threadIdx.x == 0 ? p0 : p1 - 1;
+        int64_t lo = 0, hi = n_cols - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (indptr[mid] <= target) lo = mid; else hi = mid - 1;
+        }
+        s_j[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int64_t j0 = s_j[0], j1 = s_j[1];
+    const bool by_warp = j1 - j0 >= 8;
+    const int step = by_warp ? 8 : 1, width = by_warp ? 32 : 256;
+    const int me = by_warp ? (threadIdx.x & 31) : threadIdx.x;
+    for (int64_t j = j0 + (by_warp ? (threadIdx.x >> 5) : 0); j <= j1; j += step) {
+        const int64_t c0 = indptr[j], c1 = indptr[j + 1];
+        const int64_t a = c0 > p0 ? c0 : p0, b = c1 < p1 ? c1 : p1;
+        if (b <= a) continue;
+        const int64_t d = col_to_dense ? col_to_dense[j] : j;
+        const int64_t src = seg_off[d] + (a - c0);
+        const int len = (int)(b - a);
+        for (int k = me; k < len; k += width) {
+            indices[a + k] = (int64_t)out_row[src + k];
+            data[a + k] = out_cnt[src + k];
         }
     }
 }
@@ -376,20 +478,21 @@ int peak_matrix_device(Ctx* c) {
     if (nb > 0) {
         static bool configured = false;
         if (!configured) {
-            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4 + COUNT_RANGE / 8));
+            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4 + COUNT_RANGE / 4));
             configured = true;
         }
         int g1 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 32);
         c->stage_begin(SG_REDUCE_SMALL);
+        k_reduce_warp<<<NUM_SMS * 8, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         k_reduce_small<<<g1, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_SMALL);
         c->stage_begin(SG_REDUCE_LARGE);
         int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
-        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 8, s>>>(a.hits, a.seg_off, nb, st,
+        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 4, s>>>(a.hits, a.seg_off, nb, st,
                                                                  c->row_range > 0 ? c->row_range : (c->peaks_on_device_count ? -1 : c->n_peaks),
                                                                  c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_LARGE);
-        c->launches += 2;
+        c->launches += 3;
         CRATAC_CUDA(cudaGetLastError());
     }
     // columns: the shard's own barcodes in matrix order, or the global column map of a multi-GPU run
@@ -411,10 +514,11 @@ int peak_matrix_device(Ctx* c) {
     size_t zz = (size_t)std::max<int64_t>(c->nnz, 1);
     CRATAC_TRY(c->d_indices.reserve(8 * zz)); CRATAC_TRY(c->d_data.reserve(4 * zz));
     if (n_cols > 0) {
-        int g = (int)std::min<int64_t>((n_cols * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
         c->stage_begin(SG_CSC_BUILD);
-        k_csc_copy<<<g, 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d, c->d_indptr.as<int64_t>(), n_cols,
-                                    c->d_indices.as<int64_t>(), c->d_data.as<int32_t>());
+        if (c->nnz > 0)
+            k_csc_copy<<<(unsigned)((c->nnz + CSC_CHUNK - 1) / CSC_CHUNK), 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d,
+                                                                                       c->d_indptr.as<int64_t>(), n_cols, c->nnz, c->d_indices.as<int64_t>(),
+                                                                                       c->d_data.as<int32_t>());
         c->stage_end(SG_CSC_BUILD);
         c->launches++;
         CRATAC_CUDA(cudaGetLastError());
