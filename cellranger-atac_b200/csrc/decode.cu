@@ -20,6 +20,7 @@ constexpr int DEC_TILE = 16384;
 constexpr int DEC_LOOKBACK = 256;
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_MAX_LINES = DEC_TILE / 8;   // a valid line has >= 10 bytes
+constexpr int DEC_MAX_TABS = 3072;               // tab list capacity (lines beyond it take the general path)
 constexpr unsigned long long BC_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
 
 struct ContigEntry { unsigned long long hash; int32_t id; int32_t used; };
@@ -189,18 +190,21 @@ __device__ __forceinline__ unsigned long long barcode_key_words(const uint32_t* 
 }
 
 __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
-    constexpr int N_CHUNKS = (DEC_LOOKBACK + DEC_TILE) / 16;
     __shared__ __align__(128) uint32_t words[(DEC_LOOKBACK + DEC_TILE) / 4 + 4];   // text tile (+16 B slack for word over-reads)
-    __shared__ uint32_t masks[N_CHUNKS];            // per 16-byte chunk: newline bits (low half), tab bits (high half)
-    __shared__ uint16_t nlpos[DEC_MAX_LINES];
+    __shared__ uint32_t lb_masks[DEC_LOOKBACK / 16];   // look-back chunks: newline bits (low half), tab bits (high half)
+    __shared__ uint16_t nlpos[DEC_MAX_LINES];          // newline positions of the tile region, in order
+    __shared__ uint16_t nltabs[DEC_MAX_LINES];         // tabs of the tile region before each of them
+    __shared__ uint16_t tabpos[DEC_MAX_TABS];          // tab positions of the tile region, in order
     __shared__ int warp_tot[DEC_THREADS / 32];
     __shared__ int s_first_begin;
     __shared__ __align__(8) uint64_t bar;
     unsigned char* buf = reinterpret_cast<unsigned char*>(words);
 
     const int tid = threadIdx.x;
-    const int64_t tile_base = (int64_t)blockIdx.x * DEC_TILE;
-    const int n_lines = a.tile_counts[blockIdx.x];
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_base = tile * DEC_TILE;
+    const int n_lines = a.tile_counts[tile];
     if (n_lines == 0) return;   // uniform per CTA
     const int64_t src0 = tile_base - DEC_LOOKBACK;
 
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
             mbar_expect_tx(&bar, DEC_LOOKBACK + DEC_TILE);
             tma_load_1d(buf, a.text + src0, DEC_LOOKBACK + DEC_TILE, &bar);
         }
-        if (!mbar_wait(&bar, 0)) { if (tid == 0) raise_error(a.status, CRATAC_ERR_INTERNAL, -100 - (int64_t)blockIdx.x); return; }
+        if (!mbar_wait(&bar, 0)) { if (tid == 0) raise_error(a.status, CRATAC_ERR_INTERNAL, -100 - tile); return; }
     } else {
         for (int i = tid; i < DEC_LOOKBACK + DEC_TILE; i += DEC_THREADS) {
             int64_t p = src0 + i;
@@ -227,32 +231,32 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         __syncthreads();
     }
 
-    // ---- newline / tab bitmasks per 16-byte chunk (thread t owns the 4 chunks of its 64 tile bytes;
-    //      the first 16 threads also take one look-back chunk each)
+    // ---- newline / tab bits of my 64 tile bytes (thread t owns 4 chunks of 16; the first 16 threads also take
+    //      one look-back chunk each), then ordered position lists of both through one packed block scan
     constexpr int PER_THREAD = DEC_TILE / DEC_THREADS;   // 64 contiguous bytes per thread
-    unsigned long long mask = 0;                         // newline bits of my 64 bytes
+    unsigned long long mask = 0, tmask = 0;
     {
         const int c0 = DEC_LOOKBACK / 16 + tid * (PER_THREAD / 16);
 #pragma unroll
         for (int k = 0; k < PER_THREAD / 16; k++) {
             const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * (c0 + k));
-            const uint32_t nl = swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au);
-            const uint32_t tb = swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u);
-            masks[c0 + k] = nl | (tb << 16);
-            mask |= (unsigned long long)nl << (16 * k);
+            mask |= (unsigned long long)swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) << (16 * k);
+            tmask |= (unsigned long long)swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << (16 * k);
         }
         if (tid < DEC_LOOKBACK / 16) {
             const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * tid);
-            masks[tid] = swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) | (swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << 16);
+            lb_masks[tid] = swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) | (swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << 16);
         }
     }
     // bytes at or beyond n_eff are padding newlines of the last tile: they terminate nothing
     {
         int64_t lim = a.n_eff - (tile_base + (int64_t)tid * PER_THREAD);
-        if (lim < PER_THREAD) mask = lim <= 0 ? 0ULL : (mask & ((1ULL << lim) - 1ULL));
+        if (lim < PER_THREAD) {
+            const unsigned long long keep = lim <= 0 ? 0ULL : ((1ULL << lim) - 1ULL);
+            mask &= keep; tmask &= keep;
+        }
     }
-    int my_cnt = __popcll(mask);
-    int lane = tid & 31, warp = tid >> 5;
+    const int my_cnt = __popcll(mask) | (__popcll(tmask) << 16);   // both counts stay below 2^15
     int incl = my_cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -263,18 +267,33 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     __syncthreads();
     int woff = 0;
     for (int w = 0; w < warp; w++) woff += warp_tot[w];
-    int idx = woff + incl - my_cnt;
-    while (mask) {
-        int j = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        if (idx < DEC_MAX_LINES) nlpos[idx] = (uint16_t)(DEC_LOOKBACK + tid * PER_THREAD + j);
-        idx++;
+    {
+        const int excl = woff + incl - my_cnt;
+        int idx = excl & 0xFFFF, tidx = excl >> 16;
+        const int pos0 = DEC_LOOKBACK + tid * PER_THREAD;
+        unsigned long long m = mask;
+        while (m) {
+            const int j = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (idx < DEC_MAX_LINES) {
+                nlpos[idx] = (uint16_t)(pos0 + j);
+                nltabs[idx] = (uint16_t)(tidx + __popcll(tmask & ((1ULL << j) - 1ULL)));
+            }
+            idx++;
+        }
+        m = tmask;
+        while (m) {
+            const int j = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (tidx < DEC_MAX_TABS) tabpos[tidx] = (uint16_t)(pos0 + j);
+            tidx++;
+        }
     }
     if (tid == 0) {
         // start of the first line: one past the last '\n' before the tile (or the file start)
         int begin = -1;
         for (int c = DEC_LOOKBACK / 16 - 1; c >= 0; c--) {
-            unsigned nl = masks[c] & 0xFFFFu;
+            unsigned nl = lb_masks[c] & 0xFFFFu;
             if (nl) { begin = c * 16 + (31 - __clz(nl)) + 1; break; }
         }
         if (tile_base == 0) begin = DEC_LOOKBACK;
@@ -282,62 +301,68 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     }
     __syncthreads();
     if (n_lines > DEC_MAX_LINES || s_first_begin < 0) {
-        if (tid == 0) raise_error(a.status, CRATAC_ERR_PARSE, a.tile_offsets[blockIdx.x]);
+        if (tid == 0) raise_error(a.status, CRATAC_ERR_PARSE, a.tile_offsets[tile]);
         return;
     }
 
     // ---- one line per thread: tabs from the chunk masks, numbers and barcode a word at a time
-    const int64_t out_base = a.tile_offsets[blockIdx.x];
+    const int64_t out_base = a.tile_offsets[tile];
     int loc_maxpos = 0, loc_maxneg = 0;
     for (int li = tid; li < n_lines; li += DEC_THREADS) {
         int b = li == 0 ? s_first_begin : nlpos[li - 1] + 1;
         int e = nlpos[li];
         int64_t line_no = out_base + li;
-        // strip(): leading / trailing blanks, '\r'
-        while (b < e) { unsigned ch = byte_at(words, b); if (ch == ' ' || ch == '\t' || ch == '\r') b++; else break; }
-        while (e > b) { unsigned ch = byte_at(words, e - 1); if (ch == ' ' || ch == '\t' || ch == '\r') e--; else break; }
         int t0 = 0, t1 = 0, t2 = 0, t3 = 0;   // scalars, not an indexed array: keeps them out of local memory
         int nt = 0;
-        if (b < e) {
-            const int cb = b >> 4, ce = (e - 1) >> 4;
-            for (int c = cb; c <= ce; c++) {
-                unsigned tm = masks[c] >> 16;
-                if (c == cb) tm &= 0xFFFFu << (b & 15);
-                if (c == ce) tm &= 0xFFFFu >> (15 - ((e - 1) & 15));
-                while (tm) {
-                    const int pos = c * 16 + __ffs(tm) - 1;
-                    tm &= tm - 1;
-                    if (nt == 0) t0 = pos; else if (nt == 1) t1 = pos; else if (nt == 2) t2 = pos; else if (nt == 3) t3 = pos;
+        // Common case: the line lies in the tile region, has exactly 4 tabs and nothing for strip() to remove:
+        // its tab positions are 4 consecutive entries of the tile's tab list.
+        if (li > 0) {
+            const int kt = nltabs[li - 1];
+            if (nltabs[li] - kt == 4 && kt + 4 <= DEC_MAX_TABS && e - b >= 9 && byte_at(words, b) > ' ' && byte_at(words, e - 1) > ' ') {
+                t0 = tabpos[kt]; t1 = tabpos[kt + 1]; t2 = tabpos[kt + 2]; t3 = tabpos[kt + 3];
+                nt = 4;
+            }
+        }
+        if (nt == 0) {
+            // general path (first line of the tile, blanks to strip, wrong number of fields): byte by byte
+            // strip(): leading / trailing blanks, '\r'
+            while (b < e) { unsigned ch = byte_at(words, b); if (ch == ' ' || ch == '\t' || ch == '\r') b++; else break; }
+            while (e > b) { unsigned ch = byte_at(words, e - 1); if (ch == ' ' || ch == '\t' || ch == '\r') e--; else break; }
+            for (int p = b; p < e; p++) {
+                if (byte_at(words, p) == '\t') {
+                    if (nt == 0) t0 = p; else if (nt == 1) t1 = p; else if (nt == 2) t2 = p; else if (nt == 3) t3 = p;
                     nt++;
                 }
             }
         }
+        if (nt != 4) { raise_error(a.status, CRATAC_ERR_PARSE, line_no); continue; }
+        // barcode key first: the load of its table slot (a random 16-byte access, usually the longest latency of
+        // the line) is in flight while the numbers and the contig name are parsed
+        const unsigned long long key = barcode_key_words(words, t2 + 1, t3 - t2 - 1);
+        unsigned slot = (unsigned)(mix64(key)) & (unsigned)a.bc_mask;
+        ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&a.bc_tab[slot]);   // key and first line in one 16-byte load
         int32_t v_start = 0, v_end = 0, v_dup = 0;
-        bool ok = (nt == 4);
-        if (ok) {
-            ok = swar_parse_uint(words, t0 + 1, t1 - t0 - 1, &v_start) && swar_parse_uint(words, t1 + 1, t2 - t1 - 1, &v_end) &&
-                 swar_parse_uint(words, t3 + 1, e - t3 - 1, &v_dup) && (t0 > b) && (t3 > t2 + 1);
-        }
+        const bool ok = swar_parse_uint(words, t0 + 1, t1 - t0 - 1, &v_start) && swar_parse_uint(words, t1 + 1, t2 - t1 - 1, &v_end) &&
+                        swar_parse_uint(words, t3 + 1, e - t3 - 1, &v_dup) && (t0 > b) && (t3 > t2 + 1);
         if (!ok) { raise_error(a.status, CRATAC_ERR_PARSE, line_no); continue; }
         // contig id
-        unsigned long long ch = swar_fnv1a(words, b, t0 - b);
+        unsigned long long ch = swar_contig_key(words, b, t0 - b);
         int32_t cid = -1;
-        for (int s = (int)(mix64(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
-            ContigEntry ce = a.contig_table[s];
-            if (!ce.used) break;
-            if (ce.hash == ch) { cid = ce.id; break; }
+        for (int s = (int)(swar_key_slot(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(&a.contig_table[s]));   // small read-only table: L1
+            const unsigned long long eh = (unsigned long long)(unsigned)raw.x | ((unsigned long long)(unsigned)raw.y << 32);
+            if (!raw.w) break;
+            if (eh == ch) { cid = raw.z; break; }
         }
         if (cid < 0) { raise_error(a.status, CRATAC_ERR_CONTIG, line_no); continue; }
         // barcode slot
-        unsigned long long key = barcode_key_words(words, t2 + 1, t3 - t2 - 1);
-        unsigned slot = (unsigned)(mix64(key)) & (unsigned)a.bc_mask;
         int probes = 0;
         bool placed = false;
         unsigned long long seen_first = 0xFFFFFFFFFFFFFFFFULL;
         while (probes <= a.bc_mask) {
             // a key never changes once written, so a cached read that already shows our key is final;
             // anything else is re-checked by the CAS
-            const ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&a.bc_tab[slot]);   // key and first line in one 16-byte load
+            if (probes > 0) sl = *reinterpret_cast<const ulonglong2*>(&a.bc_tab[slot]);
             unsigned long long k = sl.x;
             seen_first = sl.y;
             if (k == BC_EMPTY) {
@@ -514,8 +539,10 @@ static int build_contig_table(Ctx* c) {
     memset(tab.data(), 0, sizeof(ContigEntry) * cap);
     for (int i = 0; i < c->n_contigs; i++) {
         const std::string& nm = c->contig_names[i];
-        unsigned long long h = fnv1a(reinterpret_cast<const unsigned char*>(nm.data()), (int)nm.size());
-        int s = (int)(mix64(h) & (unsigned)(cap - 1));
+        std::vector<uint32_t> padded(nm.size() / 4 + 4, 0u);
+        memcpy(padded.data(), nm.data(), nm.size());
+        unsigned long long h = swar_contig_key(padded.data(), 0, (int)nm.size());
+        int s = (int)(swar_key_slot(h) & (unsigned)(cap - 1));
         while (tab[s].used) {
             if (tab[s].hash == h) { set_error("contig names '%s' and '%s' collide", nm.c_str(), c->contig_names[tab[s].id].c_str()); return CRATAC_ERR_ARG; }
             s = (s + 1) & (cap - 1);

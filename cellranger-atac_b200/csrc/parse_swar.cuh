@@ -24,6 +24,11 @@ SWAR_HD uint32_t swar_get4(const uint32_t* words, int p) {
 // parse the decimal field [p, p + len), 1 <= len <= 10; false on a non-digit or a value above INT32_MAX
 SWAR_HD bool swar_parse_uint(const uint32_t* words, int p, int len, int32_t* out) {
     if (len < 1 || len > 10) return false;
+    if (len == 1) {                      // the duplicate count is a single digit nearly always
+        const uint32_t d = (swar_get4(words, p) & 0xFFu) - 0x30u;
+        *out = (int32_t)d;
+        return d <= 9u;
+    }
     uint64_t head = 0;
     if (len > 8) {                       // leading 1-2 digits one by one, the last 8 digits word-wise
         const uint32_t w = swar_get4(words, p);
@@ -71,6 +76,22 @@ SWAR_HD uint64_t swar_fnv1a(const uint32_t* words, int p, int len) {
         for (int k = 0; k < n; k++) { h ^= (w >> (8 * k)) & 0xFFu; h *= 1099511628211ULL; }
     }
     return h;
+}
+
+// Key of a contig name: the bytes themselves (little endian, zero padded) for names of up to 8 bytes, FNV-1a
+// with the top bit set for longer ones; and the slot hash of the contig table.
+SWAR_HD uint64_t swar_contig_key(const uint32_t* words, int p, int len) {
+    if (len <= 8) {
+        uint32_t lo = swar_get4(words, p), hi = len > 4 ? swar_get4(words, p + 4) : 0u;
+        if (len < 4) lo &= (1u << (8 * len)) - 1u;
+        else if (len < 8) hi &= (1u << (8 * (len - 4))) - 1u;
+        return (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+    return swar_fnv1a(words, p, len) | 0x8000000000000000ULL;
+}
+SWAR_HD uint32_t swar_key_slot(uint64_t key) {
+    const uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
+    return h ^ (h >> 15);
 }
 
 // bit i of the result = (byte i of the 16 bytes v0..v3 equals the replicated pattern byte)

@@ -19,7 +19,8 @@
 
 namespace cratac {
 
-constexpr int PU_THREADS = 512;
+constexpr int PU_THREADS = 256;
+constexpr int PU_CTAS_PER_SM = 4;
 constexpr int PU_CHUNK = 44;                        // 4 x odd: thread-chunked 128-bit shared accesses are bank-conflict free
 constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entries (22528)
 constexpr int PU_PAD = 64;                          // slack for vector over-reads past the last window
@@ -82,18 +83,14 @@ __device__ __forceinline__ int block_excl_scan_i32(int v, int* warp_tot, int* to
     }
     if (lane == 31) warp_tot[warp] = x;
     __syncthreads();
-    if (warp == 0) {
-        int w = lane < (PU_THREADS / 32) ? warp_tot[lane] : 0;
+    int off = 0, tot = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += y;
-        }
-        if (lane < (PU_THREADS / 32)) warp_tot[lane] = w;
+    for (int w = 0; w < PU_THREADS / 32; w++) {   // 8 warps: every thread adds up the warp totals itself
+        const int t = warp_tot[w];
+        off += w < warp ? t : 0;
+        tot += t;
     }
-    __syncthreads();
-    int off = warp ? warp_tot[warp - 1] : 0;
-    if (total) *total = warp_tot[PU_THREADS / 32 - 1];
+    if (total) *total = tot;
     int r = off + x - v;
     __syncthreads();   // warp_tot may be reused by the caller
     return r;
@@ -143,8 +140,26 @@ __device__ __forceinline__ void for_each_window(const int* sc, int k0, int k1, F
     }
 }
 
+// the same for a chunk of exactly 4 * N4 bases: no bounds checks
+template <int N4, typename F>
+__device__ __forceinline__ void for_each_window_full(const int* sc, int k0, F&& body) {
+    const int4* U4 = reinterpret_cast<const int4*>(sc + k0 + 400);
+    const int4* V4 = reinterpret_cast<const int4*>(sc + k0);
+    int4 u = U4[0], v = V4[0];
+#pragma unroll
+    for (int j = 1; j <= N4; j++) {
+        const int4 un = U4[j], vn = V4[j];
+        const int k = k0 + 4 * (j - 1);
+        body(k, u.z - v.y);
+        body(k + 1, u.w - v.z);
+        body(k + 2, un.x - v.w);
+        body(k + 3, un.y - vn.x);
+        u = un; v = vn;
+    }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
+__global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArgs a) {
     extern __shared__ __align__(16) int smem[];
     int* sc = smem;                       // PU_N (+ PU_PAD)
     int* hist_s = smem + PU_N + PU_PAD;   // PU_HB (MODE_HIST)
@@ -164,18 +179,19 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
     if (MODE == MODE_PEAKS && tid == 0) { s_cur_s = 0; s_cur_e = 0; }
 
     // tiles come from a ticket counter; the ticket of the NEXT tile is taken while the current one is processed
-    __shared__ long long s_next;
-    if (tid == 0) s_next = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
+    __shared__ long long s_next[2];   // double-buffered: one barrier per tile hand-over
+    int par = 0;
+    if (tid == 0) s_next[0] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
     while (true) {
         __syncthreads();
-        const long long tile = s_next;
-        __syncthreads();
+        const long long tile = s_next[par];
         if (tile >= a.n_tiles) break;
         if (tid == 0) {
-            s_next = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
+            s_next[par ^ 1] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
             s_first_nz = 0x7fffffff;
             s_last_nz = -1;
         }
+        par ^= 1;
         const TileDesc td = a.desc[tile];
         const int c = td.contig;
         const int64_t L = a.contig_lens[c];
@@ -247,19 +263,37 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
                 if (v < HIST_CAP) atomicAdd(&a.ghist[v], (unsigned long long)len);
                 else raise_error(a.status, CRATAC_ERR_CAPACITY, v);
             };
-            for_each_window(sc, k0, k1, [&](int, int w) {
-                const bool changed = w != cur;
-                if (changed && cur > 0) {
+            // Common case: no window count of the tile can reach PU_HB (bounded from the prefix sums: every W of my
+            // chunk is at most S[k0 + chunk + 401] - S[k0]) -> no range check, no max tracking, and bin 0 may
+            // collect garbage (it is never read); the checked path handles the few tiles over the bound.
+            const int hi = min(k0 + PU_OWN_CHUNK + 401, PU_N - 1);
+            const int bound = k0 < own ? sc[hi] - sc[k0] : 0;
+            const bool fast = !__syncthreads_or(bound >= PU_HB);
+            if (fast) {
+                auto body = [&](int, int w) {
+                    const bool changed = w != cur;
+                    if (changed) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
+                    runlen = changed ? 1 : runlen + 1;
+                    cur = w;
+                };
+                if (k1 - k0 == PU_OWN_CHUNK) for_each_window_full<PU_OWN_CHUNK / 4>(sc, k0, body);
+                else for_each_window(sc, k0, k1, body);
+                asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
+            } else {
+                for_each_window(sc, k0, k1, [&](int, int w) {
+                    const bool changed = w != cur;
+                    if (changed && cur > 0) {
+                        if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
+                        else flush_slow(cur, runlen);
+                    }
+                    loc_max = max(loc_max, w);
+                    runlen = changed ? 1 : runlen + 1;
+                    cur = w;
+                });
+                if (cur > 0) {
                     if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
                     else flush_slow(cur, runlen);
                 }
-                loc_max = max(loc_max, w);
-                runlen = changed ? 1 : runlen + 1;
-                cur = w;
-            });
-            if (cur > 0) {
-                if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
-                else flush_slow(cur, runlen);
             }
         } else if (MODE == MODE_DUMP) {
             for_each_window(sc, k0, k1, [&](int k, int w) { a.dump_W[ta + k] = w; });
@@ -271,35 +305,59 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
             if (k0 < k1 && (k0 > 0 || ta > 0)) prev_w = sc[k0 + 401] - sc[k0];   // W at base ta + k0 - 1
             {
                 int pw = prev_w;
-                for_each_window(sc, k0, k1, [&](int k, int w) {
-                    bool sig = w >= thr, psig = pw >= thr;
+                bool psig = pw >= thr, zero_drop = false;
+                auto body = [&](int, int w) {
+                    const bool sig = w >= thr;
+                    const bool down = !sig && psig;
                     n_s += (sig && !psig);
-                    n_e += (!sig && psig);
-                    if (w != 0) { if (first_nz == 0x7fffffff) first_nz = k; last_nz = k; }
-                    else if (psig) {
-                        // W drops from pw >= thr to 0 in one step: zero gap of the bedgraph writer.
-                        // Walk to the next non-zero base of this tile; equal value => the row spans the gap.
-                        int k2 = k + 1;
-                        while (k2 < own && sc[k2 + 402] - sc[k2 + 1] == 0) k2++;
-                        if (k2 < own && sc[k2 + 402] - sc[k2 + 1] == pw) {
-                            unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_N_FILLS]), 1ULL);
-                            if ((int64_t)slot < a.fill_cap) {
-                                a.fills[2 * slot] = a.contig_base[c] + ta + k;
-                                a.fills[2 * slot + 1] = a.contig_base[c] + ta + k2;
-                            } else raise_error(a.status, CRATAC_ERR_CAPACITY, -2);
-                        }
-                    }
+                    n_e += down;
+                    zero_drop |= down && w == 0;
+                    psig = sig;
                     pw = w;
-                });
+                };
+                if (k1 - k0 == PU_OWN_CHUNK) for_each_window_full<PU_OWN_CHUNK / 4>(sc, k0, body);
+                else for_each_window(sc, k0, k1, body);
+                if (zero_drop) {
+                    // W dropped from >= thr to 0 in one step somewhere in my chunk: zero gap of the bedgraph writer
+                    // (rare; kept out of the unrolled loop).  Walk to the next non-zero base of this tile; equal
+                    // value => the row spans the gap.
+                    int pv = prev_w;
+                    for (int k = k0; k < k1; k++) {
+                        const int w = sc[k + 402] - sc[k + 1];
+                        if (w == 0 && pv >= thr) {
+                            int k2 = k + 1;
+                            while (k2 < own && sc[k2 + 402] - sc[k2 + 1] == 0) k2++;
+                            if (k2 < own && sc[k2 + 402] - sc[k2 + 1] == pv) {
+                                unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_N_FILLS]), 1ULL);
+                                if ((int64_t)slot < a.fill_cap) {
+                                    a.fills[2 * slot] = a.contig_base[c] + ta + k;
+                                    a.fills[2 * slot + 1] = a.contig_base[c] + ta + k2;
+                                } else raise_error(a.status, CRATAC_ERR_CAPACITY, -2);
+                            }
+                        }
+                        pv = w;
+                    }
+                }
+                // first / last base of my chunk with a non-zero window count (almost always the chunk's ends)
+                if (k0 < k1) {
+                    int f = k0, l = k1 - 1;
+                    while (f < k1 && sc[f + 402] - sc[f + 1] == 0) f++;
+                    if (f < k1) {
+                        while (sc[l + 402] - sc[l + 1] == 0) l--;
+                        first_nz = f; last_nz = l;
+                    }
+                }
                 const int pw_last = pw;
                 pw = pw_last;
                 // the contig's last base closes an open run at L
                 if (k1 == own && k0 < k1 && tb == L && pw >= thr) n_e += 1;
             }
             if (last_nz >= 0) { atomicMin(&s_first_nz, first_nz); atomicMax(&s_last_nz, last_nz); }
-            int tot_s = 0, tot_e = 0;
-            int off_s = block_excl_scan_i32(n_s, warp_tot, &tot_s);
-            int off_e = block_excl_scan_i32(n_e, warp_tot, &tot_e);
+            // one block scan for both counters (a tile has fewer than 2^15 boundaries of either kind)
+            static_assert(PU_N < (1 << 15), "packed boundary counters");
+            int tot_p = 0;
+            const int off_p = block_excl_scan_i32(n_s | (n_e << 16), warp_tot, &tot_p);
+            const int off_s = off_p & 0xFFFF, off_e = off_p >> 16, tot_s = tot_p & 0xFFFF, tot_e = tot_p >> 16;
             // ---- this CTA appends the tile's boundaries to its private region (tile order is restored by
             //      k_gather_events from the per-tile counts; no CTA ever waits for another)
             if (tid == 0) {
@@ -341,9 +399,9 @@ __global__ void __launch_bounds__(PU_THREADS, 2) k_pileup(PileupArgs a) {
 
     if (MODE == MODE_HIST) {
         __syncthreads();
-        for (int i = tid; i < PU_HB; i += PU_THREADS) {
+        for (int i = tid; i < PU_HB; i += PU_THREADS) {     // bin 0 is scratch of the unchecked path
             int v = hist_s[i];
-            if (v) atomicAdd(&a.ghist[i], (unsigned long long)v);
+            if (v && i > 0) { atomicAdd(&a.ghist[i], (unsigned long long)v); loc_max = max(loc_max, i); }
         }
 #pragma unroll
         for (int d = 16; d; d >>= 1) loc_max = max(loc_max, __shfl_xor_sync(0xffffffffu, loc_max, d));
@@ -540,7 +598,7 @@ static int launch_pileup(Ctx* c, PileupArgs& a) {
     CRATAC_TRY(ensure_tile_desc(c, a));
     int64_t* st = c->d_status.as<int64_t>();
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), c->stream));
-    int64_t grid = std::min<int64_t>(a.n_tiles, 2 * NUM_SMS);
+    int64_t grid = std::min<int64_t>(a.n_tiles, PU_CTAS_PER_SM * NUM_SMS);
     if (grid <= 0) return CRATAC_OK;
     k_pileup<MODE><<<(unsigned)grid, PU_THREADS, pileup_smem(MODE), c->stream>>>(a);
     c->launches++;
@@ -609,7 +667,7 @@ int call_peaks_device(Ctx* c) {
     for (int attempt = 0;; attempt++) {
         int64_t cap = c->run_cap;
         const size_t nt = (size_t)std::max<int64_t>(n_tiles, 1);
-        const int64_t n_cta = std::max<int64_t>(std::min<int64_t>(n_tiles, 2 * NUM_SMS), 1);
+        const int64_t n_cta = std::max<int64_t>(std::min<int64_t>(n_tiles, PU_CTAS_PER_SM * NUM_SMS), 1);
         const int64_t cta_cap = std::max<int64_t>(cap / n_cta, 64);
         // chain buffer layout: tile_ns | tile_ne (int32) then tile_src_s | tile_src_e | tile_dst_s | tile_dst_e (int64)
         CRATAC_TRY(c->d_chain.reserve(nt * (2 * 4 + 4 * 8)));

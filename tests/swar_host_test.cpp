@@ -33,5 +33,21 @@ int main(){
     unsigned wt=0,wn=0; for(int i=0;i<16;i++){ if(buf[i]=='\t') wt|=1u<<i; if(buf[i]=='\n') wn|=1u<<i; }
     if(t!=wt||n!=wn){ fails++; if(fails<40) printf("mask fail %x %x %x %x\n",t,wt,n,wn); }
   }
+  // contig keys: equal names <=> equal keys for short names; the bytes after the name must not leak in
+  for(int it=0;it<500000;it++){
+    for(int i=0;i<64;i++) buf[i]=(unsigned char)(33+rand()%90);
+    int off=rand()%20,len=rand()%13;
+    uint64_t k1=swar_contig_key(w,off,len);
+    unsigned char save[64]; memcpy(save,buf,64);
+    for(int i=off+len;i<64;i++) buf[i]=(unsigned char)rand();           // different context after the name
+    for(int i=0;i<off;i++) buf[i]=(unsigned char)rand();
+    uint64_t k2=swar_contig_key(w,off,len);
+    if(k1!=k2){ fails++; if(fails<50) printf("contig key context leak off=%d len=%d\n",off,len); }
+    if(len>=1&&len<=8){
+      uint64_t want=0; for(int i=0;i<len;i++) want|=(uint64_t)buf[off+i]<<(8*i);
+      if(k1!=want){ fails++; if(fails<50) printf("contig key value off=%d len=%d\n",off,len); }
+      buf[off+rand()%len]^=1; if(swar_contig_key(w,off,len)==k1){ fails++; if(fails<50) printf("contig key collision\n"); }
+    }
+  }
   printf("fails=%d\n",fails); return fails!=0;
 }
