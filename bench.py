@@ -43,51 +43,51 @@ def measured_peaks():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (one light query
+    every 50 ms; spawning nvidia-smi per rank stalls the driver for the first timed steps of an 8-GPU run)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples, self.reasons = [], set()
+        self.smax = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                # noqa: BLE001 - reported in the JSON line
+            self.nv = None
+            self.err = "NVML unavailable: %s" % (e,)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:                                 # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.05)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err], "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------------- workload
@@ -303,12 +303,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    trace = []
+
     def step_device():
         if world == 1:
             return ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
         with torch.cuda.stream(stream):
             shard = multi.CudaShard(ctx, torch, device, text_dev_ptr=text.data_ptr(), nbytes=nbytes)
-            return multi.step(shard, torch, dist, device)
+            trace.clear()
+            return multi.step(shard, torch, dist, device, trace=trace)
 
     # ---- device-resident timing
     res = None
@@ -322,10 +325,14 @@ def main():
     launches0 = ctx.launch_count(reset=True)
     ev0.record(stream)
     wall0 = time.time()
+    loop_ms = []
     for _ in range(args.steps):
+        t_a = time.time()
         res = step_device()
+        t_b = time.time()
         for k, v in ctx.stage_times().items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
+        loop_ms.append((round(1e3 * (t_b - t_a), 2), round(1e3 * (time.time() - t_b), 2)))
     ev1.record(stream)
     barrier()
     wall = time.time() - wall0
@@ -336,6 +343,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
+    traces_by_rank = None
+    if world > 1:
+        traces_by_rank = [None] * world
+        dist.all_gather_object(traces_by_rank, {"rank": rank, "dev_ms_per_step": ev0.elapsed_time(ev1) / args.steps, "phases": [(k, round(v, 2)) for k, v in trace], "loop_ms": loop_ms})
     total_frags = args.steps * args.fragments
     value = total_frags / (dev_ms / 1000.0)
 
@@ -435,7 +446,7 @@ def main():
                        "threshold": int(res.threshold), "n_peaks": int(res.n_peaks), "n_peaks_rank0": int(n_peaks_r0), "nnz": int(res.nnz),
                        "nnz_rank0": int(nnz_r0), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},
             "wall_ms_per_step": 1000.0 * wall / args.steps, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-            "host_phases_last_step_ms": ctx.host_times(),
+            "host_phases_last_step_ms": ctx.host_times()[-12:], "multi_phases_last_step_ms": traces_by_rank,
             "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},
             "n_bins": int(getattr(res, "n_bins", 0))}
     print(json.dumps(line))

@@ -67,6 +67,7 @@ SIGNATURES = {
     "cratac_bedgraph_rows": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
     "cratac_fit_threshold": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, P(c_dbl), P(c_int), P(c_i64), P(c_i64), P(c_i64)]),
     "cratac_fit_threshold_device": (c_int, [c_vp, c_dbl, P(c_dbl), P(c_int), P(c_i64)]),
+    "cratac_fit_threshold_result": (c_int, [c_vp, P(c_dbl), P(c_int), P(c_i64)]),
     "cratac_call_peaks": (c_int, [c_vp, c_i64, P(c_i64)]),
     "cratac_peaks_from_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, P(c_i64)]),
     "cratac_get_peaks": (c_int, [c_vp, c_vp, c_vp, c_vp]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "cratac_set_row_offset": (c_int, [c_vp, c_i64, c_i64]),
     "cratac_merge_rank_csc": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "cratac_py2_set_order_hashes": (c_int, [c_i64, c_vp, c_vp]),
+    "cratac_py2_set_order_hashes_device": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_uint64]),
     "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
     "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
 }
@@ -269,6 +271,18 @@ class Context(object):
         has = c_int()
         thr = c_i64()
         check(self._lib.cratac_fit_threshold_device(self._h, float(odds_ratio), params, ctypes.byref(has), ctypes.byref(thr)))
+        return _fit_result(thr.value, has.value, params, None, None)
+
+    def py2_set_order_hashes_device(self, n, d_hashes, d_order_out, stream=0):
+        """CPython-2.7 list(set) order from the hashes of n distinct keys, device pointers in and out."""
+        check(self._lib.cratac_py2_set_order_hashes_device(self._h, int(n), c_vp(int(d_hashes)), c_vp(int(d_order_out)), int(stream)))
+
+    def fit_threshold_result(self):
+        """Numbers of a fit queued under option defer_sync = 1."""
+        params = (c_dbl * 6)()
+        has = c_int()
+        thr = c_i64()
+        check(self._lib.cratac_fit_threshold_result(self._h, params, ctypes.byref(has), ctypes.byref(thr)))
         return _fit_result(thr.value, has.value, params, None, None)
 
     # ---- peaks

@@ -64,8 +64,8 @@ def global_columns(torch, keys_all, first_all, hash_all, valid_all, py2_order_fn
     hash_u = torch.zeros(n, dtype=torch.int64, device=keys.device).scatter(0, inv, hsh)
     by_first = torch.argsort(first_min)                      # insertion order of the reference's set
     if order == "py2set":
-        perm = py2_order_fn(hash_u[by_first].cpu().numpy())  # slot order of the CPython-2.7 set
-        col_to_uniq = by_first[torch.as_tensor(np.asarray(perm, dtype=np.int64), device=keys.device)]
+        perm = py2_order_fn(hash_u[by_first].contiguous())   # slot order of the CPython-2.7 set (tensor in, tensor out)
+        col_to_uniq = by_first[perm.to(torch.int64)]
     else:
         col_to_uniq = by_first
     col_of_uniq = torch.empty(n, dtype=torch.int64, device=keys.device)
@@ -88,44 +88,64 @@ def _all_gather_i64(torch, dist, values, device):
     return torch.stack(out).cpu().numpy()
 
 
-def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set"):
+def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set", trace=None):
     """One pass of the path on this rank's shard + the cross-rank exchanges.  `shard` implements the backend
     interface (see CudaShard).  Returns a StepResult; the merged matrix lives on rank 0 (shard.merged)."""
+    import time
+    t_last = [time.time()]
+
+    def mark(name):      # host wall clock between phase boundaries (no extra synchronisation)
+        if trace is not None:
+            now = time.time()
+            trace.append((name, 1e3 * (now - t_last[0])))
+            t_last[0] = now
+
     world, rank = dist.get_world_size(), dist.get_rank()
     n_frag, n_bc = shard.decode()
-    # 1. histogram
-    hist, maxc = shard.window_histogram()                    # int64 tensor view [cap], local largest count
-    mx = torch.tensor([maxc], dtype=torch.int64, device=device)
+    mark("decode")
+    # 1. histogram: queued, all-reduced in place (largest count and bins), fit queued behind it -- no host wait
+    hist, mx = shard.window_histogram()                      # int64 tensors: bins [cap], largest count [1]
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    gmax = int(mx.item())
-    bins = hist[: gmax + 1]
-    dist.all_reduce(bins, op=dist.ReduceOp.SUM)
-    threshold, params = shard.fit(gmax, odds_ratio)
-    # 2. peaks, row / line bases
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    shard.fit_launch(odds_ratio)
+    mark("hist_fit_launch")
+    # 2. barcode dictionary, exchanged while the fit runs (side stream on a GPU: the fit occupies one SM)
+    with shard.side_stream():
+        counts = _all_gather_i64(torch, dist, [n_frag, n_bc], device)
+        mark("d_gather_counts")
+        line_base = int(counts[:rank, 0].sum())
+        keys, first, hsh = shard.barcode_table()             # int64 tensors [n_bc]
+        max_b = int(counts[:, 1].max())
+        pad = torch.zeros((3, max(max_b, 1)), dtype=torch.int64, device=device)
+        pad[0, :n_bc] = keys
+        pad[1, :n_bc] = first + line_base
+        pad[2, :n_bc] = hsh
+        gathered = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(gathered, pad)
+        if trace is not None: torch.cuda.current_stream().synchronize()
+        mark("d_all_gather")
+        g = torch.stack(gathered)                            # [world, 3, maxB]
+        valid = torch.arange(max(max_b, 1), device=device)[None, :] < torch.as_tensor(counts[:, 1], device=device)[:, None]
+        n_cols, col_of, col_keys = global_columns(torch, g[:, 0], g[:, 1], g[:, 2], valid, shard.py2_order, order)
+        mark("d_global_columns")
+        c2d = torch.full((max(n_cols, 1),), -1, dtype=torch.int32, device=device)
+        mine = col_of[rank, :n_bc]
+        c2d[mine] = torch.arange(n_bc, dtype=torch.int32, device=device)
+    mark("dictionary")
+    # 3. threshold, peaks, row bases
+    threshold, params = shard.fit_result()
+    mark("fit_wait")
     n_peaks = shard.call_peaks()
-    counts = _all_gather_i64(torch, dist, [n_peaks, n_frag, n_bc], device)
-    row_base = int(counts[:rank, 0].sum())
-    total_rows = int(counts[:, 0].sum())
-    line_base = int(counts[:rank, 1].sum())
+    mark("call_peaks")
+    pk = _all_gather_i64(torch, dist, [n_peaks], device)[:, 0]
+    row_base = int(pk[:rank].sum())
+    total_rows = int(pk.sum())
     shard.set_row_offset(row_base, total_rows)
-    # 3. barcode dictionary
-    keys, first, hsh = shard.barcode_table()                 # int64 tensors [n_bc]
-    max_b = int(counts[:, 2].max())
-    pad = torch.zeros((3, max(max_b, 1)), dtype=torch.int64, device=device)
-    pad[0, :n_bc] = keys
-    pad[1, :n_bc] = first + line_base
-    pad[2, :n_bc] = hsh
-    gathered = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(gathered, pad)
-    g = torch.stack(gathered)                                # [world, 3, maxB]
-    valid = torch.arange(max(max_b, 1), device=device)[None, :] < torch.as_tensor(counts[:, 2], device=device)[:, None]
-    n_cols, col_of, col_keys = global_columns(torch, g[:, 0], g[:, 1], g[:, 2], valid, shard.py2_order, order)
-    c2d = torch.full((max(n_cols, 1),), -1, dtype=torch.int32, device=device)
-    mine = col_of[rank, :n_bc]
-    c2d[mine] = torch.arange(n_bc, dtype=torch.int32, device=device)
     shard.set_column_map(n_cols, c2d)
     # 4. local CSC over the global columns, gathered to rank 0
+    mark("row_col_maps")
     indptr, indices, data = shard.peak_matrix(n_cols)        # tensors (views) on `device`
+    mark("peak_matrix")
     nnz = int(indices.numel())
     nnz_all = _all_gather_i64(torch, dist, [nnz], device)[:, 0]
     total_nnz = int(nnz_all.sum())
@@ -137,19 +157,25 @@ def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set"):
         indptr_all[: n_cols + 1] = indptr
         indices_all[: nnz] = indices
         data_all[: nnz] = data
-        for r in range(1, world):
-            dist.recv(indptr_all[r * (n_cols + 1):(r + 1) * (n_cols + 1)], src=r)
+        ops = []
+        for r in range(1, world):                             # all receives posted at once: the transfers of the
+            ops.append(dist.P2POp(dist.irecv, indptr_all[r * (n_cols + 1):(r + 1) * (n_cols + 1)], r))   # ranks overlap
             if nnz_all[r] > 0:
-                dist.recv(indices_all[offs[r]:offs[r + 1]], src=r)
-                dist.recv(data_all[offs[r]:offs[r + 1]], src=r)
+                ops.append(dist.P2POp(dist.irecv, indices_all[offs[r]:offs[r + 1]], r))
+                ops.append(dist.P2POp(dist.irecv, data_all[offs[r]:offs[r + 1]], r))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
         rank_off = torch.as_tensor(offs[:-1].astype(np.int64), device=device)
         shard.merge(world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz)
     else:
-        dist.send(indptr.contiguous(), dst=0)
+        ops = [dist.P2POp(dist.isend, indptr.contiguous(), 0)]
         if nnz > 0:
-            dist.send(indices.contiguous(), dst=0)
-            dist.send(data.contiguous(), dst=0)
-    return StepResult(n_fragments=int(counts[:, 1].sum()), n_fragments_local=n_frag, n_barcodes=n_cols, threshold=threshold,
+            ops.append(dist.P2POp(dist.isend, indices.contiguous(), 0))
+            ops.append(dist.P2POp(dist.isend, data.contiguous(), 0))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    mark("gather_merge")
+    return StepResult(n_fragments=int(counts[:, 0].sum()), n_fragments_local=n_frag, n_barcodes=n_cols, threshold=threshold,
                       params=params, n_peaks=total_rows, n_peaks_local=n_peaks, row_base=row_base, nnz=total_nnz, nnz_local=nnz,
                       col_keys=col_keys, em_iterations=getattr(shard, "em_iterations", 0),
                       em_inner_iterations=getattr(shard, "em_inner_iterations", 0), n_hits=getattr(shard, "n_hits", 0))
@@ -175,6 +201,7 @@ class CudaShard(object):
         self.ctx, self.torch, self.device = ctx, torch, device
         self.text_dev_ptr, self.text_host, self.nbytes = text_dev_ptr, text_host, nbytes
         self.merged = None
+        self._side = None
 
     def decode(self):
         if self.text_dev_ptr is not None:
@@ -182,17 +209,27 @@ class CudaShard(object):
         return self.ctx.decode_host(self.text_host)
 
     def window_histogram(self):
+        self.ctx.set_option("defer_sync", 1)
         self.ctx.window_histogram()
         sp, ns = self.ctx.status_device()
         self.status = dev_tensor(self.torch, sp, ns, "<i8", self.device)
         hp, cap = self.ctx.hist_device()
-        return dev_tensor(self.torch, hp, cap, "<i8", self.device), int(self.status[6].item())
+        return dev_tensor(self.torch, hp, cap, "<i8", self.device), self.status[6:7]
 
-    def fit(self, global_max, odds_ratio):
-        self.status[6] = global_max
-        self.torch.cuda.current_stream(self.device).synchronize()
+    def fit_launch(self, odds_ratio):
+        # the all-reduces were queued by torch on the current stream; the library's stream must be that stream
         self.ctx.compact_histogram()
-        thr, params, _ = self.ctx.fit_threshold_device(odds_ratio)
+        self.ctx.fit_threshold_device(odds_ratio)
+        self.ctx.set_option("defer_sync", 0)
+
+    def side_stream(self):
+        if self._side is None:
+            self._side = self.torch.cuda.Stream(device=self.device)
+        # no wait on the main stream: the dictionary inputs were final when decode() returned (it synchronises)
+        return self.torch.cuda.stream(self._side)
+
+    def fit_result(self):
+        thr, params, _ = self.ctx.fit_threshold_result()
         self.em_iterations = int(self.status[15].item())
         self.em_inner_iterations = int(self.status[16].item())
         return thr, params
@@ -212,10 +249,16 @@ class CudaShard(object):
                 dev_tensor(t, h, n, "<i8", self.device).clone())
 
     def py2_order(self, hashes):
-        from . import _ffi
-        return _ffi.py2_set_order_hashes(hashes)
+        t = self.torch
+        out = t.empty(hashes.numel(), dtype=t.int32, device=self.device)
+        cur = t.cuda.current_stream(self.device)             # the side stream of step(): the fit has the context's own
+        cur.synchronize()                                    # `hashes` is complete before the library reads it
+        self.ctx.py2_set_order_hashes_device(hashes.numel(), hashes.data_ptr(), out.data_ptr(), stream=cur.cuda_stream)
+        return out
 
     def set_column_map(self, n_cols, c2d):
+        if self._side is not None:
+            self._side.synchronize()                          # c2d was computed there
         self.torch.cuda.current_stream(self.device).synchronize()
         self.ctx.set_column_map(n_cols, c2d.data_ptr())
 

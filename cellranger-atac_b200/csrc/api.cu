@@ -59,6 +59,7 @@ int compact_histogram(Ctx* c);                                                  
 int offset_peak_rows(Ctx* c, int64_t base);                                              // pileup.cu
 int merge_runs_from_host(Ctx* c, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end);   // pileup.cu
 void py2_set_order_hashes(const long long* hashes, int64_t n, std::vector<int32_t>& order);   // decode.cu
+int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_order_out);   // py2order.cu
 int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off, const int64_t* d_indices_all,
                    const int32_t* d_data_all, int64_t total_nnz);                         // matrix.cu
 int dump_window_counts(Ctx* c, int contig, int32_t* d_W);                                // pileup.cu
@@ -180,6 +181,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "run_capacity")) { c->run_cap = value; return CRATAC_OK; }
     if (!strcmp(key, "em_fast")) { c->em_fast = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "defer_sync")) { c->defer_sync = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
         c->profile = value != 0;
@@ -421,6 +423,13 @@ int cratac_fit_threshold_device(cratac_ctx* h, double odds_ratio, double params_
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
     CRATAC_TRY(fit_threshold_device(c, odds_ratio));
+    if (c->defer_sync) return CRATAC_OK;     // queued only: cratac_fit_threshold_result picks the numbers up
+    return read_fit(c, params_out, has_params, threshold_out, nullptr, nullptr);
+}
+
+int cratac_fit_threshold_result(cratac_ctx* h, double params_out[6], int* has_params, int64_t* threshold_out) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
     return read_fit(c, params_out, has_params, threshold_out, nullptr, nullptr);
 }
 
@@ -644,7 +653,7 @@ int cratac_window_histogram(cratac_ctx* h) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
     CRATAC_TRY(window_histogram(c));
-    return sync_status(c);
+    return c->defer_sync ? CRATAC_OK : sync_status(c);
 }
 
 // re-derive the compact (value, weight) arrays from the (all-reduced) device histogram
@@ -652,7 +661,7 @@ int cratac_compact_histogram(cratac_ctx* h) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
     CRATAC_TRY(compact_histogram(c));
-    return sync_status(c);
+    return c->defer_sync ? CRATAC_OK : sync_status(c);
 }
 
 // barcode dictionary of this shard by dense id: 64-bit keys, first line (shard-local), CPython-2.7 hash
@@ -703,6 +712,17 @@ int cratac_py2_set_order_hashes(int64_t n, const int64_t* hashes, int32_t* order
     if ((int64_t)order.size() != n) { set_error("cratac_py2_set_order_hashes: internal error"); return CRATAC_ERR_INTERNAL; }
     for (int64_t i = 0; i < n; i++) order_out[i] = order[i];
     return CRATAC_OK;
+}
+
+// the same order computed on the device (device pointers; returns when the order is complete)
+int cratac_py2_set_order_hashes_device(cratac_ctx* h, int64_t n, const int64_t* d_hashes, int32_t* d_order_out, uint64_t stream) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t saved = c->stream;
+    if (stream) c->stream = (cudaStream_t)(uintptr_t)stream;   // e.g. a side stream while the fit occupies the context's own
+    const int rc = py2_set_order_device(c, n, d_hashes, d_order_out);
+    c->stream = saved;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------ host helpers

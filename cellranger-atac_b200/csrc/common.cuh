@@ -122,6 +122,7 @@ struct Ctx {
     bool bc_is_slot = false;               // d_bc holds hash-table slots (decode) vs dense ids (set_fragments)
     // histogram / threshold
     DevBuf d_hist;                         // uint64[HIST_CAP]
+    DevBuf d_p2_scratch;                   // tables and probe state of py2_set_order_device (py2order.cu)
     DevBuf d_hist_values, d_hist_weights;  // compact, ascending
     DevBuf d_em_params;                    // double[8]
     DevBuf d_em_work;
@@ -150,6 +151,7 @@ struct Ctx {
     DevBuf d_scan_tmp;
     int64_t* h_status = nullptr;           // pinned mirror
     int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
+    int defer_sync = 0;                    // 1: window_histogram / compact_histogram / fit_threshold_device only queue their work
     int em_fast = 2;                       // 0 plain fixed point, 1 accelerated (em.cu), 2 register-resident kernel first (em_fast.cu)
     bool profile = false;
     cudaEvent_t ev[2 * SG_COUNT] = {};

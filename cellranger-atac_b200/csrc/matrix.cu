@@ -385,18 +385,40 @@ __global__ void k_merge_counts(const int64_t* __restrict__ indptr_all, int world
     for (int r = 0; r < world; r++) { const int64_t* ip = indptr_all + (int64_t)r * (n_cols + 1); t += ip[j + 1] - ip[j]; }
     cnt[j] = (int32_t)t;
 }
+// chunked over the merged output like k_csc_copy; inside a column the rank segments follow each other in rank
+// order (= genome order = ascending rows)
 __global__ void __launch_bounds__(256) k_merge_copy(const int64_t* __restrict__ indptr_all, const int64_t* __restrict__ rank_off, int world, int64_t n_cols,
                                                     const int64_t* __restrict__ indices_all, const int32_t* __restrict__ data_all,
-                                                    const int64_t* __restrict__ indptr, int64_t* __restrict__ indices, int32_t* __restrict__ data) {
-    const int lane = threadIdx.x & 31;
-    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t j = warp; j < n_cols; j += n_warps) {
+                                                    const int64_t* __restrict__ indptr, int64_t nnz, int64_t* __restrict__ indices, int32_t* __restrict__ data) {
+    __shared__ int64_t s_j[2];
+    const int64_t p0 = (int64_t)blockIdx.x * CSC_CHUNK;
+    const int64_t p1 = p0 + CSC_CHUNK < nnz ? p0 + CSC_CHUNK : nnz;
+    if (threadIdx.x < 2) {       // largest j < n_cols with indptr[j] <= target
+        const int64_t target = threadIdx.x == 0 ? p0 : p1 - 1;
+        int64_t lo = 0, hi = n_cols - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (indptr[mid] <= target) lo = mid; else hi = mid - 1;
+        }
+        s_j[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int64_t j0 = s_j[0], j1 = s_j[1];
+    const bool by_warp = j1 - j0 >= 8;
+    const int step = by_warp ? 8 : 1, width = by_warp ? 32 : 256;
+    const int me = by_warp ? (threadIdx.x & 31) : threadIdx.x;
+    for (int64_t j = j0 + (by_warp ? (threadIdx.x >> 5) : 0); j <= j1; j += step) {
         int64_t dst = indptr[j];
-        for (int r = 0; r < world; r++) {       // rank order = genome order = ascending rows
+        if (indptr[j + 1] <= p0 || dst >= p1) continue;
+        for (int r = 0; r < world; r++) {
             const int64_t* ip = indptr_all + (int64_t)r * (n_cols + 1);
-            int64_t src = rank_off[r] + ip[j], len = ip[j + 1] - ip[j];
-            for (int64_t k = lane; k < len; k += 32) { indices[dst + k] = indices_all[src + k]; data[dst + k] = data_all[src + k]; }
+            const int64_t s0 = ip[j], len = ip[j + 1] - s0;
+            const int64_t a = dst > p0 ? dst : p0, b = dst + len < p1 ? dst + len : p1;
+            if (b > a) {
+                const int64_t src = rank_off[r] + s0 + (a - dst);
+                const int n = (int)(b - a);
+                for (int k = me; k < n; k += width) { indices[a + k] = indices_all[src + k]; data[a + k] = data_all[src + k]; }
+            }
             dst += len;
         }
     }
@@ -416,9 +438,10 @@ int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_al
     }
     CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_nnz_ordered.as<int32_t>(), c->d_indptr.as<int64_t>(), n_cols, c->d_indptr.as<int64_t>() + n_cols));
     if (n_cols > 0) {
-        int g = (int)std::min<int64_t>((n_cols * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
-        k_merge_copy<<<g, 256, 0, s>>>(d_indptr_all, d_rank_off, world, n_cols, d_indices_all, d_data_all, c->d_indptr.as<int64_t>(),
-                                      c->d_indices.as<int64_t>(), c->d_data.as<int32_t>());
+        if (total_nnz > 0)
+            k_merge_copy<<<(unsigned)((total_nnz + CSC_CHUNK - 1) / CSC_CHUNK), 256, 0, s>>>(d_indptr_all, d_rank_off, world, n_cols, d_indices_all, d_data_all,
+                                                                                            c->d_indptr.as<int64_t>(), total_nnz, c->d_indices.as<int64_t>(),
+                                                                                            c->d_data.as<int32_t>());
         c->launches++;
         CRATAC_CUDA(cudaGetLastError());
     }

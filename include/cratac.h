@@ -114,6 +114,11 @@ int cratac_fit_threshold(cratac_ctx* ctx, const int64_t* values, const int64_t* 
  * device for cratac_call_peaks(threshold = -1) and is also returned. */
 int cratac_fit_threshold_device(cratac_ctx* ctx, double odds_ratio, double params_out[6], int* has_params,
                                 int64_t* threshold_out);
+/* With option "defer_sync" = 1, cratac_window_histogram, cratac_compact_histogram and
+ * cratac_fit_threshold_device only queue their kernels on the context's stream (outputs untouched), so
+ * that a multi-GPU host can exchange the barcode dictionary while the fit runs; this call waits for the
+ * fit and returns its numbers (the Counter merge + estimate_final_threshold of detect_peaks/__init__.py:36-58). */
+int cratac_fit_threshold_result(cratac_ctx* ctx, double params_out[6], int* has_params, int64_t* threshold_out);
 
 /* ---- (4) DETECT_PEAKS.main/join: replaces lib/python/utils.py:105-115 + detect_peaks/__init__.py:40-62
  *      (threshold, 500 bp merge) over all primary contigs and the ordering of
@@ -164,6 +169,13 @@ int cratac_set_row_offset(cratac_ctx* ctx, int64_t row_base, int64_t total_rows)
 int cratac_merge_rank_csc(cratac_ctx* ctx, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off,
                           const int64_t* d_indices_all, const int32_t* d_data_all, int64_t total_nnz);
 int cratac_py2_set_order_hashes(int64_t n, const int64_t* hashes, int32_t* order_out);
+/* the same on the device: d_hashes int64[n] in insertion order, d_order_out int32[n]; the tables of
+ * every growth step are rebuilt in parallel (fixed point of "a slot keeps the earliest key that asks for
+ * it"), which gives exactly the layout of the one-by-one insertion.  Used by the multi-GPU step, where
+ * the host simulation of every rank would sit on the critical path.  stream = 0: the context's stream,
+ * otherwise the cudaStream_t to run on (the fit may be occupying the context's own). */
+int cratac_py2_set_order_hashes_device(cratac_ctx* ctx, int64_t n, const int64_t* d_hashes, int32_t* d_order_out,
+                                       uint64_t stream);
 
 /* ---- host helpers */
 /* CPython-2.7 list(set(keys)) order for `n` NUL-terminated strings given in insertion order:

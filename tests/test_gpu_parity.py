@@ -390,3 +390,23 @@ def test_multi_step_two_ranks_equals_single_context():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run_multi_check(2)
+
+
+def test_py2_set_order_on_device_matches_host_simulation():
+    """The parallel rebuild of the CPython-2.7 set tables (py2order.cu) against the sequential simulation."""
+    import torch
+    ctx = _ffi.Context([("chr1", 1000)])
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (1, 5, 6, 7, 21, 22, 100, 1365, 1366, 21845, 21846, 50001, 87381, 87382, 174762, 174763, 210000, 600000):
+        cases.append(rng.integers(-2 ** 62, 2 ** 62, size=n, dtype=np.int64))
+    cases.append((rng.integers(0, 64, size=30000, dtype=np.int64) << 24) + np.arange(30000, dtype=np.int64) * (1 << 30))   # equal low bits: long probe chains
+    cases.append(np.arange(100000, dtype=np.int64) * 8)                                                             # clustered home slots
+    cases.append(rng.integers(0, 1 << 16, size=40000, dtype=np.int64))                                             # duplicates of the hash, distinct keys
+    for h in cases:
+        want = _ffi.py2_set_order_hashes(h)
+        d_h = torch.from_numpy(h).cuda()
+        d_o = torch.empty(h.size, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.py2_set_order_hashes_device(h.size, d_h.data_ptr(), d_o.data_ptr())
+        assert np.array_equal(d_o.cpu().numpy(), want), h.size

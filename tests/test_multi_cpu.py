@@ -52,11 +52,20 @@ class OracleShard(object):
         self.hist = torch.zeros(cap, dtype=torch.int64)
         for v, w in h.items():
             self.hist[v] = w
-        return self.hist, max(h) if h else 0
+        self.mx = torch.tensor([max(h) if h else 0], dtype=torch.int64)
+        return self.hist, self.mx
 
-    def fit(self, gmax, odds):
+    def fit_launch(self, odds):
+        self.odds = odds
+
+    def side_stream(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def fit_result(self):
+        gmax = int(self.mx.item())
         cd = {int(v): int(self.hist[v]) for v in range(1, gmax + 1) if int(self.hist[v]) > 0}
-        thr, params = oracle_em.estimate_final_threshold(cd, odds)
+        thr, params = oracle_em.estimate_final_threshold(cd, self.odds)
         self.thr = int(thr)
         return self.thr, params
 
@@ -75,7 +84,7 @@ class OracleShard(object):
         return torch.from_numpy(keys), torch.from_numpy(self.first.copy()), torch.from_numpy(hashes)
 
     def py2_order(self, hashes):
-        return _ffi.py2_set_order_hashes(hashes)             # host-only entry point of libcratac
+        return torch.from_numpy(_ffi.py2_set_order_hashes(hashes.numpy()).astype(np.int64))   # host-only entry point of libcratac
 
     def set_column_map(self, n_cols, c2d):
         self.n_cols, self.c2d = n_cols, c2d.numpy().copy()
