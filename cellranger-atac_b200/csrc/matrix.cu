@@ -36,6 +36,7 @@ struct OverlapArgs {
     unsigned int* cursor;
     int32_t* hits;
     long long maxpos, maxneg;              // bounds of end - start over all fragments
+    int64_t* n_hits;                       // device counter of fragment ends inside peaks
 };
 
 __device__ __forceinline__ int find_peak(const OverlapArgs& a, int c, int pos) {
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
     __shared__ long long s_plo;
     __shared__ int s_w;
     const int64_t n_tiles = (a.n + OV_TILE - 1) / OV_TILE;
+    long long my_hits = 0;                                  // count pass: fragment ends inside peaks (K of the size accounting)
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i0 = tile * OV_TILE;
         const int64_t i1 = i0 + OV_TILE < a.n ? i0 + OV_TILE : a.n;
@@ -112,17 +114,26 @@ __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
                 r0 = find_peak(a, c, a.start[i]);
                 r1 = find_peak(a, c, a.end[i]);
             }
-            int nh = (r0 >= 0) + (r1 >= 0);
-            if (nh == 0 || b < 0) continue;
+            // one record per (fragment, peak): value = row << 1 | (both ends in that peak).  Most fragments that hit
+            // a peak lie inside it, so this nearly halves the scattered 4-byte stores that bound the scatter pass.
+            const bool same = r0 >= 0 && r1 == r0;
+            const int nrec = (r0 >= 0) + (r1 >= 0 && !same);
+            if (nrec == 0 || b < 0) continue;
             if (!SCATTER) {
-                atomicAdd(&a.bc_hits[b], nh);
+                atomicAdd(&a.bc_hits[b], nrec);
+                my_hits += (r0 >= 0) + (r1 >= 0);
             } else {
-                unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nh);
+                unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nrec);
                 int64_t o = a.seg_off[b] + p;
-                if (r0 >= 0) a.hits[o++] = r0;
-                if (r1 >= 0) a.hits[o] = r1;
+                if (r0 >= 0) a.hits[o++] = (r0 << 1) | (int)same;
+                if (r1 >= 0 && !same) a.hits[o] = r1 << 1;
             }
         }
+    }
+    if (!SCATTER) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
+        if ((threadIdx.x & 31) == 0 && my_hits) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_hits), (unsigned long long)my_hits);
     }
 }
 
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int i0 = 0; i0 < len; i0 += SORT_THREADS) {
             int i = i0 + threadIdx.x;
-            int head = (i < len) && (i == 0 || s[i] != s[i - 1]);
+            int head = (i < len) && (i == 0 || (s[i] >> 1) != (s[i - 1] >> 1));
             int x = head;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
@@ -172,10 +183,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __
             int off = s_base;
             for (int w = 0; w < warp; w++) off += warp_tot[w];
             if (head) {
-                int e = i + 1;
-                while (e < len && s[e] == s[i]) e++;
-                out_row[o0 + off + x - 1] = s[i];
-                out_cnt[o0 + off + x - 1] = e - i;
+                const int row = s[i] >> 1;
+                int e = i, cnt = 0;
+                while (e < len && (s[e] >> 1) == row) { cnt += 1 + (s[e] & 1); e++; }
+                out_row[o0 + off + x - 1] = row;
+                out_cnt[o0 + off + x - 1] = cnt;
             }
             __syncthreads();
             if (threadIdx.x == SORT_THREADS - 1) s_base = off + x;
@@ -220,14 +232,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __r
         int base = 0;
         for (int i0 = 0; i0 < len; i0 += 32) {
             const int i = i0 + lane;
-            const int head = (i < len) && (i == 0 || s[i] != s[i - 1]);
+            const int head = (i < len) && (i == 0 || (s[i] >> 1) != (s[i - 1] >> 1));
             const unsigned hm = __ballot_sync(0xffffffffu, head);
             if (head) {
-                int e = i + 1;
-                while (e < len && s[e] == s[i]) e++;
+                const int row = s[i] >> 1;
+                int e = i, cnt = 0;
+                while (e < len && (s[e] >> 1) == row) { cnt += 1 + (s[e] & 1); e++; }
                 const int pos = base + __popc(hm & ((1u << lane) - 1u));
-                out_row[o0 + pos] = s[i];
-                out_cnt[o0 + pos] = e - i;
+                out_row[o0 + pos] = row;
+                out_cnt[o0 + pos] = cnt;
             }
             base += __popc(hm);
         }
@@ -255,8 +268,9 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
         if (len > 0x7fffffffLL) { if (threadIdx.x == 0) raise_error(const_cast<int64_t*>(status), CRATAC_ERR_CAPACITY, b); continue; }
         __syncthreads();
         if (threadIdx.x == 0) s_base = 0;
-        // a segment shorter than 65536 cannot overflow 16-bit counters: two per word, twice the rows per pass
-        const bool half = len < 65536;
+        // a segment of fewer than 32768 records (each worth 1 or 2) cannot overflow 16-bit counters: two per word,
+        // twice the rows per pass
+        const bool half = len < 32768;
         const int range = half ? 2 * COUNT_RANGE : COUNT_RANGE;
         for (int64_t r0 = 0; r0 < n_peaks; r0 += range) {
             // count; the first hit of a row also sets its bit in the occupancy bitmap.  Eight loads in flight per
@@ -266,10 +280,13 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
             const int len32 = (int)len, r0_32 = (int)r0;
             for (int i0 = threadIdx.x; i0 < len32; i0 += UN * COUNT_THREADS) {
                 unsigned r[UN];
+                int inc[UN];
 #pragma unroll
                 for (int u = 0; u < UN; u++) {
                     const int i = i0 + u * COUNT_THREADS;
-                    r[u] = i < len32 ? (unsigned)(seg[i] - r0_32) : 0xFFFFFFFFu;
+                    const int v = i < len32 ? seg[i] : -1;
+                    r[u] = v >= 0 ? (unsigned)((v >> 1) - r0_32) : 0xFFFFFFFFu;
+                    inc[u] = 1 + (v & 1);
                 }
                 unsigned old[UN];
 #pragma unroll
@@ -278,9 +295,9 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
                     if (r[u] < (unsigned)range) {
                         if (half) {
                             const int sh = 16 * (r[u] & 1u);
-                            old[u] = ((unsigned)atomicAdd(&cnt[r[u] >> 1], 1 << sh) >> sh) & 0xFFFFu;
+                            old[u] = ((unsigned)atomicAdd(&cnt[r[u] >> 1], inc[u] << sh) >> sh) & 0xFFFFu;
                         } else {
-                            old[u] = (unsigned)atomicAdd(&cnt[r[u]], 1);
+                            old[u] = (unsigned)atomicAdd(&cnt[r[u]], inc[u]);
                         }
                     }
                 }
@@ -470,6 +487,8 @@ int peak_matrix_device(Ctx* c) {
     a.pk_start = c->d_peak_start.as<int32_t>(); a.pk_end = c->d_peak_end.as<int32_t>(); a.pk_row = c->d_peak_row.as<int32_t>();
     a.maxpos = c->h_status[ST_MAX_POS_LEN]; a.maxneg = c->h_status[ST_MAX_NEG_LEN];
     a.bc_hits = c->d_bc_hits.as<int32_t>(); a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = nullptr;
+    a.n_hits = &st[ST_N_HITS];
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_HITS], 0, sizeof(int64_t), s));
     int grid = (int)std::min<int64_t>((n + OV_TILE - 1) / OV_TILE, (int64_t)NUM_SMS * 8);
     if (grid < 1) grid = 1;
     c->stage_begin(SG_OVERLAP_COUNT);
@@ -484,11 +503,12 @@ int peak_matrix_device(Ctx* c) {
     if (!c->global_cols) CRATAC_TRY(build_barcodes(c));
     c->host_mark("build_barcodes");
     // K (total hits) sizes the hit buffers: one host round trip here (8 bytes)
-    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_NNZ], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));   // records (slot reused below)
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], &st[ST_N_HITS], 8, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
     c->host_mark("matrix_wait_hits");
-    const int64_t K = c->h_status[ST_N_HITS];
-    c->n_hits = K;
+    const int64_t K = c->h_status[ST_NNZ];                  // hit records: one per (fragment, peak)
+    c->n_hits = c->h_status[ST_N_HITS];                     // fragment ends inside peaks
     size_t kk = (size_t)std::max<int64_t>(K, 1);
     CRATAC_TRY(c->d_hits.reserve(4 * kk)); CRATAC_TRY(c->d_out_row.reserve(4 * kk)); CRATAC_TRY(c->d_out_cnt.reserve(4 * kk));
     a.hits = c->d_hits.as<int32_t>();
