@@ -405,11 +405,26 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
 
 // ------------------------------------------------------------------ fragment bookkeeping
 // chrom[] must be non-decreasing and start[] non-decreasing inside a contig.
-__global__ void k_check_sorted(const int32_t* __restrict__ chrom, const int32_t* __restrict__ start, int64_t n, int64_t* status) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 || i >= n) return;
-    int c0 = chrom[i - 1], c1 = chrom[i];
-    if (c1 < c0 || (c1 == c0 && start[i] < start[i - 1])) raise_error(status, CRATAC_ERR_UNSORTED, i);
+__global__ void __launch_bounds__(256) k_check_sorted(const int32_t* __restrict__ chrom, const int32_t* __restrict__ start, int64_t n, int64_t* status) {
+    // grid-stride over groups of 4 fragments (128-bit loads; the arrays come from cudaMalloc, so group starts are aligned)
+    const int64_t n4 = (n + 3) >> 2;
+    int64_t bad = -1;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        int c[5], s[5];
+        if (i0 + 4 <= n) {
+            const int4 cv = *reinterpret_cast<const int4*>(chrom + i0), sv = *reinterpret_cast<const int4*>(start + i0);
+            c[1] = cv.x; c[2] = cv.y; c[3] = cv.z; c[4] = cv.w; s[1] = sv.x; s[2] = sv.y; s[3] = sv.z; s[4] = sv.w;
+        } else {
+            for (int k = 0; k < 4; k++) { const int64_t i = i0 + k < n ? i0 + k : n - 1; c[k + 1] = chrom[i]; s[k + 1] = start[i]; }
+        }
+        c[0] = i0 > 0 ? chrom[i0 - 1] : c[1];
+        s[0] = i0 > 0 ? start[i0 - 1] : s[1];
+#pragma unroll
+        for (int k = 1; k <= 4; k++)
+            if (i0 + k - 1 < n && (c[k] < c[k - 1] || (c[k] == c[k - 1] && s[k] < s[k - 1])) && bad < 0) bad = i0 + k - 1;
+    }
+    if (bad >= 0) raise_error(status, CRATAC_ERR_UNSORTED, bad);
 }
 
 __global__ void k_contig_frag_offsets(const int32_t* __restrict__ chrom, int64_t n, int n_contigs, int64_t* __restrict__ off) {
@@ -711,7 +726,7 @@ int finalize_fragments(Ctx* c) {
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
     c->stage_begin(SG_FRAG_INDEX);
     if (n > 0) {
-        k_check_sorted<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_chrom.as<int32_t>(), c->d_start.as<int32_t>(), n, st);
+        k_check_sorted<<<(unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)NUM_SMS * 16), 256, 0, c->stream>>>(c->d_chrom.as<int32_t>(), c->d_start.as<int32_t>(), n, st);
         c->launches++;
     }
     k_contig_frag_offsets<<<(nc + 1 + 127) / 128, 128, 0, c->stream>>>(c->d_chrom.as<int32_t>(), n, nc, c->d_contig_frag_off.as<int64_t>());
