@@ -215,10 +215,13 @@ def test_matrix_overlapping_peaks_rejected():
     ctx.close()
 
 
-@pytest.mark.parametrize("seed,n_peaks,n_bc,n_frag", [(5, 300, 40, 20000), (6, 40000, 12, 60000), (7, 5, 3000, 30000)])
+@pytest.mark.parametrize("seed,n_peaks,n_bc,n_frag", [(5, 300, 40, 20000), (6, 40000, 12, 60000), (7, 5, 3000, 30000),
+                                                        (8, 2000, 6, 400000), (9, 60000, 200, 300000), (10, 50, 400, 200000)])
 def test_matrix_random_vs_oracle(seed, n_peaks, n_bc, n_frag):
-    """Long segments (> 4096 hits per barcode: counting path), > 24 576 peaks (several counting ranges),
-    many short segments (bitonic path), unsorted user peak order."""
+    """Every reduce path: segments of a few records (one warp each), 1025..4096 records (bitonic sort by a CTA),
+    longer ones (range counting: 16-bit counters below 32768 records -- seeds 6, 8 -- and 32-bit ones above -- seed 8's
+    deep barcode), > 49 152 peaks (several counting ranges, seed 9), few wide peaks (large counts, most fragments with
+    both ends in one peak, seed 10), unsorted user peak order."""
     rng = np.random.default_rng(seed)
     contigs = [("a", 3000000), ("b", 2000000)]
     peaks = []
@@ -245,6 +248,24 @@ def test_matrix_random_vs_oracle(seed, n_peaks, n_bc, n_frag):
     assert np.array_equal(indptr, oip)
     assert np.array_equal(indices, oix)
     assert np.array_equal(data, od)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_frag", [30000, 70000])
+def test_matrix_one_cell_count_beyond_16_bits(n_frag):
+    """All fragments of one barcode inside one peak: 2 * n_frag in a single matrix entry.  30 000 records still use the
+    16-bit counters (count 60 000 fits), 70 000 must take the 32-bit ones."""
+    contigs = [("a", 100000)]
+    rng = np.random.default_rng(n_frag)
+    start = np.sort(rng.integers(1000, 5000, size=n_frag)).astype(np.int32)
+    end = (start + rng.integers(1, 300, size=n_frag)).astype(np.int32)
+    chrom = np.zeros(n_frag, dtype=np.int32)
+    bc = np.zeros(n_frag, dtype=np.int32)
+    ctx = _ffi.Context(contigs)
+    ctx.set_fragments(chrom, start, end, bc, None, ["only"])
+    ctx.set_peaks([0, 0], [500, 20000], [6000, 30000])
+    indptr, indices, data = ctx.peak_matrix()
+    assert indptr.tolist() == [0, 1] and indices.tolist() == [0] and data.tolist() == [2 * n_frag]
     ctx.close()
 
 
