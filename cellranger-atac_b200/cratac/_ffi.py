@@ -177,7 +177,7 @@ class Context(object):
     def em_debug(self):
         out = (c_dbl * 11)()
         check(self._lib.cratac_em_debug(self._h, out))
-        names = ["e_step", "m_sums", "suffix", "bracket", "nodes", "verify_or_xc", "doubling", "descent", "direct", "direct_evals", "levels_sum"]
+        names = ["e_step", "m_sums", "suffix", "bracket", "nodes", "verify_or_xc", "doubling", "descent", "direct", "retries_with_64_nodes", "levels_sum"]
         return {k: float(v) for k, v in zip(names, out)}
 
     def host_times(self):

@@ -42,8 +42,8 @@ struct EfArgs {
 };
 
 struct EfSmem {
-    double xn[CM];              // Chebyshev-Gauss nodes cos((i + 1/2) pi / 64), descending
-    double wn[CM];              // their barycentric weights (-1)^i sin((i + 1/2) pi / 64)
+    double xn[CM + CM / 2];     // Chebyshev-Gauss nodes cos((i + 1/2) pi / N), descending: N = 64 at [0, 64), N = 32 at [64, 96)
+    double wn[CM + CM / 2];     // their barycentric weights (-1)^i sin((i + 1/2) pi / N)
     double T[EF_TS];
     const double* Tp;           // tail-weight table in use (shared or global)
     double red[EF_WARPS * 8];
@@ -155,17 +155,20 @@ __device__ __forceinline__ void ef_eval_points(EfSmem& s, int jmax, double mu, d
 // of G lanes (G = 8, 16 or 32) with the barycentric formula of the second kind: lane s owns the nodes s, s+G, ...
 // The terms are independent (no recurrence), so a group finishes in a few hundred cycles; no coefficient fit is
 // needed, which makes composing two interpolants one evaluation per node.  Every lane returns the value.
-template <int G>
+template <int G, int N = CM>
 __device__ __forceinline__ double ef_bary_group(const EfSmem& s, const double* f, double t) {
+    constexpr int TAB = N == CM ? 0 : CM;
+    const double* xn = s.xn + TAB;
+    const double* wn = s.wn + TAB;
     const int sub = threadIdx.x & (G - 1);
     t = fmin(1.0, fmax(-1.0, t));
     double num = 0.0, den = 0.0;
 #pragma unroll
-    for (int m = 0; m < CM / G; m++) {
+    for (int m = 0; m < N / G; m++) {
         const int i = sub + G * m;
-        double d = t - s.xn[i];
+        double d = t - xn[i];
         d = d == 0.0 ? 1e-300 : d;                   // t is a node: its term swamps the others and f[i] comes out
-        const double q = s.wn[i] * ef_rcp(d);
+        const double q = wn[i] * ef_rcp(d);
         num = fma(q, f[i], num);
         den += q;
     }
@@ -186,6 +189,119 @@ __device__ __forceinline__ double ef_G_block(EfSmem& s, int jmax, double mu, dou
     ef_block_sum<1>(part, s.red);
     return log(1.0 + al * mu) / (mu - part[0] / N1);
 }
+
+// The part of the jump that works on the interpolant of F = log G(exp x) over [xa, xb] with N nodes.
+// Returns 1 on success, 2 when the interpolation error check failed (more nodes may do), 0 otherwise.
+template <int N>
+__device__ __noinline__ int ef_jump_nodes(int jmax, double mu, double N1, double alpha0, double sg, double xa, double xb, int k_offset,
+                                          double* alpha_k, int* k_done) {
+    EfSmem& s = ef_smem();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double half = 0.5 * (xb - xa), mid = 0.5 * (xb + xa);
+    const double inv_half = 1.0 / half;
+    EP_BEGIN();
+    // ---- F(x) = log G(exp x) at the N Chebyshev-Gauss nodes + N / 4 check points (extrema of T_N)
+    constexpr int NCHK = N / 4;
+    constexpr int WG = 32;                  // lanes of a single-warp evaluation
+    const double* xn = s.xn + (N == CM ? 0 : CM);
+    if (tid < N) s.pts[tid] = exp(mid + half * xn[tid]);
+    else if (tid < N + NCHK) s.pts[tid] = exp(mid + half * cos(EF_PI * (double)(tid - N) / (double)NCHK));
+    if (tid == 0) s.flag = 1;
+    __syncthreads();
+    ef_eval_points<2 * N>(s, jmax, mu, N1, N + NCHK);
+    double fx = 0.0;
+    if (tid < N + NCHK) { fx = log(s.val[tid]); if (!isfinite(fx)) s.flag = 0; }
+    __syncthreads();
+    if (tid < N) s.lv[0][tid] = fx;
+    else if (tid < N + NCHK) s.val[tid] = fx;
+    __syncthreads();
+    const double* f0 = s.lv[0];
+    if (tid < N - 1) {   // secant slopes in (0, 1): monotone, contracting
+        double dx = half * (xn[tid] - xn[tid + 1]);
+        double df = f0[tid] - f0[tid + 1];
+        if (!(df > 0.0) || !(df < dx)) s.flag = 0;
+    }
+    constexpr int BG = EF_THREADS / N;      // lanes per interpolant evaluation in the node-parallel passes (8 or 16)
+    const int grp = tid / BG, sub = tid % BG;
+    if (grp < NCHK) {     // interpolant against the true F half-way between the nodes
+        double t = cos(EF_PI * (double)grp / (double)NCHK);
+        double err = fabs(ef_bary_group<BG, N>(s, f0, t) - s.val[N + grp]);
+        if (sub == 0 && !(err < 2e-12)) s.flag = 2;      // interpolation error: worth another try with more nodes
+    }
+    __syncthreads();
+    if (s.flag != 1) return s.flag == 2 ? 2 : 0;
+    EP_END(s, EP_NODES);
+    // ---- x_c: last point on the path (from x0 towards the bracket end) whose step is still >= eps * (1 + 1e-3);
+    //      7 rounds of 16-way sectioning, one warp per trial point.  x_c only has to be on the early side of the
+    //      crossing: a resolution of 16^-7 of the path costs at most a fraction of one extra direct iteration.
+    const double x0 = log(alpha0), xe = sg > 0.0 ? xb : xa;
+    const double epsx = 1e-6 * (1.0 + 1e-3);
+    double lo = 0.0, hi = 1.0;
+    for (int round = 0; round < 7; round++) {
+        double u = lo + (hi - lo) * (double)(warp + 1) / (double)EF_WARPS;
+        double x = x0 + u * (xe - x0);
+        double g = sg * (ef_bary_group<WG, N>(s, f0, (x - mid) * inv_half) - x);
+        int cnt = __syncthreads_count(lane == 0 && g >= epsx);
+        double nlo = lo + (hi - lo) * (double)cnt / (double)EF_WARPS;
+        double nhi = lo + (hi - lo) * (double)min(cnt + 1, EF_WARPS) / (double)EF_WARPS;
+        lo = nlo; hi = nhi;
+    }
+    const double xc = x0 + lo * (xe - x0);
+    if (!(sg * (xc - x0) > 0.0)) return 0;   // the stopping point is (almost) at x0: nothing to jump over
+    EP_END(s, EP_XC);
+    // ---- number of composition levels from a contraction estimate (step at x0, slope at the far end);
+    //      the descent below is exact whatever the estimate
+    int want_levels;
+    if (warp == 0) {
+        const double h = 1e-3 * half;
+        const int g3 = lane / 8;             // 8-lane groups 0..2 evaluate at x0, xe, xe - h towards x0
+        const double xq = g3 == 0 ? x0 : (g3 == 1 ? xe : xe - sg * h);
+        const double fq = ef_bary_group<8, N>(s, f0, (xq - mid) * inv_half);
+        const double fx0 = __shfl_sync(0xffffffffu, fq, 0), fe = __shfl_sync(0xffffffffu, fq, 8), fh = __shfl_sync(0xffffffffu, fq, 16);
+        const double d0 = fabs(fx0 - x0);
+        const double slope = fabs(fe - fh) / h;
+        double kest = 16.0;
+        if (slope > 0.0 && slope < 1.0 && d0 > epsx) kest = log(d0 / epsx) / -log(slope);
+        if (!(kest >= 1.0)) kest = 1.0;
+        if (kest > 16384.0) kest = 16384.0;
+        int wl = (int)ceil(log2(kest * 1.25)) + 1;
+        if (wl < 2) wl = 2;
+        if (wl > CL) wl = CL;
+        if (lane == 0) s.ibc = wl;
+    }
+    __syncthreads();
+    want_levels = s.ibc;
+    // ---- F^(2^L) at the nodes: one interpolant evaluation per node and level
+    int n_levels = 1;
+    while (n_levels < want_levels) {
+        const double* fl = s.lv[n_levels - 1];
+        double v = ef_bary_group<BG, N>(s, fl, (fl[grp] - mid) * inv_half);
+        if (sub == 0) s.lv[n_levels][grp] = v;
+        __syncthreads();
+        n_levels++;
+    }
+    EP_END(s, EP_DOUBLING);
+    if (tid == 0) s.cyc[EP_LEVELS] += n_levels;
+    // ---- descent: keep every jump that still lands at or before x_c
+    double x = x0;
+    int k = 0;
+    if (warp == 0) {
+        for (int L = n_levels - 1; L >= 0; L--) {
+            double y = ef_bary_group<WG, N>(s, s.lv[L], (x - mid) * inv_half);
+            if (sg * (xc - y) >= 0.0 && k_offset + k + (1 << L) <= 9998) { x = y; k += 1 << L; }
+        }
+        if (lane == 0) { s.bcast[0] = x; s.ibc = k; }
+    }
+    __syncthreads();
+    x = s.bcast[0]; k = s.ibc;
+    __syncthreads();
+    EP_END(s, EP_DESCENT);
+    if (k == 0) return 0;
+    *alpha_k = exp(x);
+    *k_done = k;
+    return 1;
+}
+
 
 // Jump along the fixed-point iteration.  On success *alpha_k is iterate number *k_done (k_done >= 1) counted
 // from alpha0.  `guess` (> 0) is the previous M-step's result: the bracket end is first looked for right next to it.
@@ -217,109 +333,14 @@ __device__ __noinline__ bool ef_jump(int jmax, double mu, double N1, double alph
         __syncthreads();
     }
     const double xa = log(fmin(alpha0, b)), xb = log(fmax(alpha0, b));
-    const double half = 0.5 * (xb - xa), mid = 0.5 * (xb + xa);
+    const double half = 0.5 * (xb - xa);
     if (!(half > 0.0) || !isfinite(half)) return false;
-    const double inv_half = 1.0 / half;
     EP_END(s, EP_BRACKET);
-    // ---- F(x) = log G(exp x) at the 64 Chebyshev-Gauss nodes + 16 check points (extrema of T_64)
-    constexpr int NCHK = 16;
-    if (tid < CM) s.pts[tid] = exp(mid + half * s.xn[tid]);
-    else if (tid < CM + NCHK) s.pts[tid] = exp(mid + half * cos(EF_PI * (double)(tid - CM) / (double)NCHK));
-    if (tid == 0) s.flag = 1;
-    __syncthreads();
-    ef_eval_points<2 * CM>(s, jmax, mu, N1, CM + NCHK);
-    double fx = 0.0;
-    if (tid < CM + NCHK) { fx = log(s.val[tid]); if (!isfinite(fx)) s.flag = 0; }
-    __syncthreads();
-    if (tid < CM) s.lv[0][tid] = fx;
-    else if (tid < CM + NCHK) s.val[tid] = fx;
-    __syncthreads();
-    const double* f0 = s.lv[0];
-    if (tid < CM - 1) {   // secant slopes in (0, 1): monotone, contracting
-        double dx = half * (s.xn[tid] - s.xn[tid + 1]);
-        double df = f0[tid] - f0[tid + 1];
-        if (!(df > 0.0) || !(df < dx)) s.flag = 0;
-    }
-    constexpr int BG = 8;                   // lanes per interpolant evaluation
-    constexpr int NGRP = EF_THREADS / BG;   // evaluations per pass (64)
-    const int grp = tid / BG, sub = tid % BG;
-    if (grp < NCHK) {     // interpolant against the true F half-way between the nodes
-        double t = cos(EF_PI * (double)grp / (double)NCHK);
-        double err = fabs(ef_bary_group<BG>(s, f0, t) - s.val[CM + grp]);
-        if (sub == 0 && !(err < 2e-12)) s.flag = 0;
-    }
-    __syncthreads();
-    if (!s.flag) return false;
-    EP_END(s, EP_NODES);
-    // ---- x_c: last point on the path (from x0 towards the bracket end) whose step is still >= eps * (1 + 1e-3);
-    //      7 rounds of 16-way sectioning, one warp per trial point.  x_c only has to be on the early side of the
-    //      crossing: a resolution of 16^-7 of the path costs at most a fraction of one extra direct iteration.
-    const double x0 = log(alpha0), xe = sg > 0.0 ? xb : xa;
-    const double epsx = 1e-6 * (1.0 + 1e-3);
-    double lo = 0.0, hi = 1.0;
-    for (int round = 0; round < 7; round++) {
-        double u = lo + (hi - lo) * (double)(warp + 1) / (double)EF_WARPS;
-        double x = x0 + u * (xe - x0);
-        double g = sg * (ef_bary_group<32>(s, f0, (x - mid) * inv_half) - x);
-        int cnt = __syncthreads_count(lane == 0 && g >= epsx);
-        double nlo = lo + (hi - lo) * (double)cnt / (double)EF_WARPS;
-        double nhi = lo + (hi - lo) * (double)min(cnt + 1, EF_WARPS) / (double)EF_WARPS;
-        lo = nlo; hi = nhi;
-    }
-    const double xc = x0 + lo * (xe - x0);
-    if (!(sg * (xc - x0) > 0.0)) return false;   // the stopping point is (almost) at x0: nothing to jump over
-    EP_END(s, EP_XC);
-    // ---- number of composition levels from a contraction estimate (step at x0, slope at the far end);
-    //      the descent below is exact whatever the estimate
-    int want_levels;
-    if (warp == 0) {
-        const double h = 1e-3 * half;
-        const int g3 = lane / BG;            // groups 0..2 evaluate at x0, xe, xe - h towards x0
-        const double xq = g3 == 0 ? x0 : (g3 == 1 ? xe : xe - sg * h);
-        const double fq = ef_bary_group<BG>(s, f0, (xq - mid) * inv_half);
-        const double fx0 = __shfl_sync(0xffffffffu, fq, 0), fe = __shfl_sync(0xffffffffu, fq, BG), fh = __shfl_sync(0xffffffffu, fq, 2 * BG);
-        const double d0 = fabs(fx0 - x0);
-        const double slope = fabs(fe - fh) / h;
-        double kest = 16.0;
-        if (slope > 0.0 && slope < 1.0 && d0 > epsx) kest = log(d0 / epsx) / -log(slope);
-        if (!(kest >= 1.0)) kest = 1.0;
-        if (kest > 16384.0) kest = 16384.0;
-        int wl = (int)ceil(log2(kest * 1.25)) + 1;
-        if (wl < 2) wl = 2;
-        if (wl > CL) wl = CL;
-        if (lane == 0) s.ibc = wl;
-    }
-    __syncthreads();
-    want_levels = s.ibc;
-    // ---- F^(2^L) at the nodes: one interpolant evaluation per node and level
-    int n_levels = 1;
-    while (n_levels < want_levels) {
-        const double* fl = s.lv[n_levels - 1];
-        double v = ef_bary_group<BG>(s, fl, (fl[grp] - mid) * inv_half);
-        if (sub == 0) s.lv[n_levels][grp] = v;
-        __syncthreads();
-        n_levels++;
-    }
-    EP_END(s, EP_DOUBLING);
-    if (tid == 0) s.cyc[EP_LEVELS] += n_levels;
-    // ---- descent: keep every jump that still lands at or before x_c
-    double x = x0;
-    int k = 0;
-    if (warp == 0) {
-        for (int L = n_levels - 1; L >= 0; L--) {
-            double y = ef_bary_group<32>(s, s.lv[L], (x - mid) * inv_half);
-            if (sg * (xc - y) >= 0.0 && k_offset + k + (1 << L) <= 9998) { x = y; k += 1 << L; }
-        }
-        if (lane == 0) { s.bcast[0] = x; s.ibc = k; }
-    }
-    __syncthreads();
-    x = s.bcast[0]; k = s.ibc;
-    __syncthreads();
-    EP_END(s, EP_DESCENT);
-    if (k == 0) return false;
-    *alpha_k = exp(x);
-    *k_done = k;
-    return true;
+    // 32 nodes first (half the evaluations of G and half the interpolation work); 64 when its error check says so
+    // (16 nodes were tried: the error check fails on every M-step of the 250 M-fragment histogram)
+    int rc = ef_jump_nodes<CM / 2>(jmax, mu, N1, alpha0, sg, xa, xb, k_offset, alpha_k, k_done);
+    if (rc == 2) { if (tid == 0) s.cyc[EP_NCOEF] += 1; rc = ef_jump_nodes<CM>(jmax, mu, N1, alpha0, sg, xa, xb, k_offset, alpha_k, k_done); }
+    return rc == 1;
 }
 
 __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
@@ -343,10 +364,11 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         tot[0] += w;
         vmax = fmax(vmax, v);
     }
-    if (tid < CM) {
-        const double th = EF_PI * ((double)tid + 0.5) / (double)CM;
+    if (tid < CM + CM / 2) {
+        const int nn = tid < CM ? CM : CM / 2, i = tid < CM ? tid : tid - CM;
+        const double th = EF_PI * ((double)i + 0.5) / (double)nn;
         s.xn[tid] = cos(th);
-        s.wn[tid] = (tid & 1) ? -sin(th) : sin(th);
+        s.wn[tid] = (i & 1) ? -sin(th) : sin(th);
     }
     ef_block_sum<1>(tot, s.red);
     vmax = ef_block_max(vmax, s.red);
@@ -643,7 +665,6 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         a.params_out[0] = th.p_zero; a.params_out[1] = th.mean_bg; a.params_out[2] = th.alpha_bg;
         a.params_out[3] = th.p_signal; a.params_out[4] = th.f_zero; a.params_out[5] = th.f_bg;
         for (int q = 0; q < EP_COUNT; q++) a.params_out[8 + q] = (double)s.cyc[q];
-        a.params_out[8 + EP_NCOEF] = (double)direct;   // reported as direct evaluations of G
     }
 }
 
