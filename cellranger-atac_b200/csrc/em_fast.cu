@@ -104,20 +104,6 @@ __device__ __forceinline__ double ef_block_max(double x, double* red) {
     return v;
 }
 
-// log Gamma(x): Stirling series for x >= 24 (truncation error < 1e-18 there), library lgamma below.  The E-step
-// evaluates lgamma(1/alpha + v) for every bin and iteration; the series is ~4x cheaper than the library routine.
-__device__ __forceinline__ double ef_lgamma(double x) {
-    if (x < 24.0) return lgamma(x);
-    const double r = 1.0 / x, r2 = r * r;
-    // 1/12 - r2/360 + r2^2/1260 - r2^3/1680 + r2^4/1188 - r2^5 * 691/360360
-    double p = fma(r2, -691.0 / 360360.0, 1.0 / 1188.0);
-    p = fma(r2, p, -1.0 / 1680.0);
-    p = fma(r2, p, 1.0 / 1260.0);
-    p = fma(r2, p, -1.0 / 360.0);
-    p = fma(r2, p, 1.0 / 12.0);
-    return fma(x - 0.5, log(x), -x) + 0.91893853320467274178 + p * r;
-}
-
 // 1 / y to ~1 ulp: hardware seed (rcp.approx.ftz.f64, relative error 2^-23), one Newton step and a final
 // residual correction.  A quarter of the FP64-pipe work of an IEEE division; y = 0 gives inf / NaN.
 __device__ __forceinline__ double ef_rcp(double y) {
@@ -125,6 +111,20 @@ __device__ __forceinline__ double ef_rcp(double y) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
     r = r * fma(-y, r, 2.0);
     return fma(r, fma(-y, r, 1.0), r);
+}
+
+// log Gamma(x): Stirling series for x >= 24 (truncation error < 1e-18 there), library lgamma below.  The E-step
+// evaluates lgamma(1/alpha + v) for every bin and iteration; the series is ~4x cheaper than the library routine.
+__device__ __forceinline__ double ef_lgamma(double x) {
+    if (x < 24.0) return lgamma(x);
+    const double r = ef_rcp(x), r2 = r * r;
+    // 1/12 - r2/360 + r2^2/1260 - r2^3/1680 + r2^4/1188 - r2^5 * 691/360360
+    double p = fma(r2, -691.0 / 360360.0, 1.0 / 1188.0);
+    p = fma(r2, p, -1.0 / 1680.0);
+    p = fma(r2, p, 1.0 / 1260.0);
+    p = fma(r2, p, -1.0 / 360.0);
+    p = fma(r2, p, 1.0 / 12.0);
+    return fma(x - 0.5, log(x), -x) + 0.91893853320467274178 + p * r;
 }
 
 // alpha j / (1 + alpha j) = 1 - 1 / (1 + alpha j)
@@ -232,19 +232,23 @@ __device__ __noinline__ int ef_jump_nodes(int jmax, double mu, double N1, double
     if (s.flag != 1) return s.flag == 2 ? 2 : 0;
     EP_END(s, EP_NODES);
     // ---- x_c: last point on the path (from x0 towards the bracket end) whose step is still >= eps * (1 + 1e-3);
-    //      7 rounds of 16-way sectioning, one warp per trial point.  x_c only has to be on the early side of the
-    //      crossing: a resolution of 16^-7 of the path costs at most a fraction of one extra direct iteration.
+    //      4 rounds of 64-way sectioning, 8 lanes per trial point.  x_c only has to be on the early side of the
+    //      crossing: a resolution of 64^-4 of the path costs at most a fraction of one extra direct iteration.
     const double x0 = log(alpha0), xe = sg > 0.0 ? xb : xa;
     const double epsx = 1e-6 * (1.0 + 1e-3);
     double lo = 0.0, hi = 1.0;
-    for (int round = 0; round < 7; round++) {
-        double u = lo + (hi - lo) * (double)(warp + 1) / (double)EF_WARPS;
-        double x = x0 + u * (xe - x0);
-        double g = sg * (ef_bary_group<WG, N>(s, f0, (x - mid) * inv_half) - x);
-        int cnt = __syncthreads_count(lane == 0 && g >= epsx);
-        double nlo = lo + (hi - lo) * (double)cnt / (double)EF_WARPS;
-        double nhi = lo + (hi - lo) * (double)min(cnt + 1, EF_WARPS) / (double)EF_WARPS;
-        lo = nlo; hi = nhi;
+    {
+        constexpr int SG = 8, NS = EF_THREADS / SG;
+        const int sgrp = tid / SG, ssub = tid % SG;
+        for (int round = 0; round < 4; round++) {
+            double u = lo + (hi - lo) * (double)(sgrp + 1) / (double)NS;
+            double x = x0 + u * (xe - x0);
+            double g = sg * (ef_bary_group<SG, N>(s, f0, (x - mid) * inv_half) - x);
+            int cnt = __syncthreads_count(ssub == 0 && g >= epsx);
+            double nlo = lo + (hi - lo) * (double)cnt / (double)NS;
+            double nhi = lo + (hi - lo) * (double)min(cnt + 1, NS) / (double)NS;
+            lo = nlo; hi = nhi;
+        }
     }
     const double xc = x0 + lo * (xe - x0);
     if (!(sg * (xc - x0) > 0.0)) return 0;   // the stopping point is (almost) at x0: nothing to jump over
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
                 const double b = exp(ef_lgamma(nn + v) - lgS[i] - lgn + nlogp + v * l1p) * th.f_bg;
                 const double g = exp((v - 1.0) * ls) * th.p_signal * f_sig;
                 const double t = z + b + g;
-                if (t == 0.0) { r0 = r1 = r2 = 0.0; } else { const double it = 1.0 / t; r0 = z * it; r1 = b * it; r2 = g * it; }
+                if (t == 0.0) { r0 = r1 = r2 = 0.0; } else { const double it = ef_rcp(t); r0 = z * it; r1 = b * it; r2 = g * it; }
             }
             const double o0 = w * r0, o1 = w * r1, o2 = w * r2;
             acc[0] += o0; acc[1] += v * o0; acc[2] += o1; acc[3] += v * o1; acc[4] += o2; acc[5] += v * o2;
