@@ -125,11 +125,15 @@ int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_
         const unsigned g = (unsigned)((m + 255) / 256);
         k_p2_begin<<<g, 256, 0, s>>>(d_hashes, seq, (int)m, mask, st_i, st_p, cand);
         c->launches++;
-        for (int round = 0;; round++) {
-            if (round > 4096) { set_error("py2_set_order_device: no fixed point"); return CRATAC_ERR_INTERNAL; }
-            CRATAC_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), s));
-            k_p2_round<<<g, 256, 0, s>>>((int)m, mask, st_i, st_p, cand, table, changed);
-            c->launches++;
+        // rounds are idempotent once the fixed point is reached: queue four at a time, then look at the flag of the
+        // last one (one host round trip per batch instead of per round)
+        for (int batch = 0;; batch++) {
+            if (batch > 1024) { set_error("py2_set_order_device: no fixed point"); return CRATAC_ERR_INTERNAL; }
+            for (int r = 0; r < 4; r++) {
+                if (r == 3) CRATAC_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), s));
+                k_p2_round<<<g, 256, 0, s>>>((int)m, mask, st_i, st_p, cand, table, changed);
+            }
+            c->launches += 4;
             int h_changed = 0;
             CRATAC_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, s));
             CRATAC_CUDA(cudaStreamSynchronize(s));
