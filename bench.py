@@ -473,6 +473,26 @@ def main():
                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
                     "note": "achieved = SURVEY section 8d algorithmic bytes of the stages the kernel replaces / CUDA-event time"}
 
+    # ---- the stage right after the path (FILTER_PEAK_MATRIX) on the matrix just built: the 10 000
+    #      columns with most entries stand in for the cell barcodes; outside the timed region, reported on its own
+    filter_info = None
+    if world == 1 and int(res.nnz) > 0:
+        ip = ctx.get_matrix_indptr(int(res.n_barcodes))
+        per_col = np.diff(ip)
+        cols = np.sort(np.argsort(-per_col, kind="stable")[: min(args.cells, per_col.size)]).astype(np.int64)
+        ctx.select_columns_device(cols)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        reps = 3
+        for _ in range(reps):
+            n_sel, nnz_sel = ctx.select_columns_device(cols)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.time() - t0) / reps
+        gb = 2 * 12 * nnz_sel / 1e9
+        filter_info = {"ms_host_wall": ms, "columns_in": int(cols.size), "columns_out": int(n_sel), "nnz_out": int(nnz_sel),
+                       "algorithmic_gb": gb, "gbs": gb / (ms / 1e3), "frac": gb / (ms / 1e3) / peak_gbs,
+                       "note": "cratac_select_columns incl. its host round trips; 12 B read + 12 B written per kept entry"}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         sample, desc = cpu_sample(args)
@@ -483,7 +503,7 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels, "em_fit_ms": em_ms, "em_iterations": int(res.em_iterations), "em_inner_iterations": int(res.em_inner_iterations),
+            "kernels": kernels, "filter_peak_matrix": filter_info, "em_fit_ms": em_ms, "em_iterations": int(res.em_iterations), "em_inner_iterations": int(res.em_inner_iterations),
             "result": {"n_fragments": int(res.n_fragments), "n_fragments_rank0": int(n_frag_r0), "n_barcodes": int(res.n_barcodes),
                        "threshold": int(res.threshold), "n_peaks": int(res.n_peaks), "n_peaks_rank0": int(n_peaks_r0), "nnz": int(res.nnz),
                        "nnz_rank0": int(nnz_r0), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},

@@ -75,6 +75,9 @@ SIGNATURES = {
     "cratac_peak_matrix": (c_int, [c_vp, P(c_i64)]),
     "cratac_get_matrix": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cratac_matrix_device": (c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp)]),
+    "cratac_set_matrix": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cratac_select_columns": (c_int, [c_vp, c_i64, c_vp, c_int, P(c_i64), P(c_i64)]),
+    "cratac_get_selected": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cratac_hist_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
@@ -273,6 +276,35 @@ class Context(object):
         check(self._lib.cratac_fit_threshold_device(self._h, float(odds_ratio), params, ctypes.byref(has), ctypes.byref(thr)))
         return _fit_result(thr.value, has.value, params, None, None)
 
+    # ---- FILTER_PEAK_MATRIX
+    def set_matrix(self, indptr, indices, data):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        data = np.ascontiguousarray(data, dtype=np.int32)
+        check(self._lib.cratac_set_matrix(self._h, indptr.size - 1, _ptr(indptr), _ptr(indices), _ptr(data)))
+
+    def select_columns_device(self, cols, drop_empty=True):
+        """Same, result left in HBM -> (n_cols, nnz)."""
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        nc, nz = c_i64(), c_i64()
+        check(self._lib.cratac_select_columns(self._h, cols.size, _ptr(cols) if cols.size else None, int(bool(drop_empty)),
+                                              ctypes.byref(nc), ctypes.byref(nz)))
+        return nc.value, nz.value
+
+    def select_columns(self, cols, drop_empty=True):
+        """m[:, cols] of the current matrix, without the columns left empty -> (indptr, indices, data, kept)."""
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        nc, nz = c_i64(), c_i64()
+        check(self._lib.cratac_select_columns(self._h, cols.size, _ptr(cols) if cols.size else None, int(bool(drop_empty)),
+                                              ctypes.byref(nc), ctypes.byref(nz)))
+        indptr = np.zeros(nc.value + 1, dtype=np.int64)
+        indices = np.zeros(nz.value, dtype=np.int64)
+        data = np.zeros(nz.value, dtype=np.int32)
+        kept = np.zeros(nc.value, dtype=np.int64)
+        check(self._lib.cratac_get_selected(self._h, _ptr(indptr), _ptr(indices) if nz.value else None, _ptr(data) if nz.value else None,
+                                            _ptr(kept) if nc.value else None))
+        return indptr, indices, data, kept
+
     def py2_set_order_hashes_device(self, n, d_hashes, d_order_out, stream=0):
         """CPython-2.7 list(set) order from the hashes of n distinct keys, device pointers in and out."""
         check(self._lib.cratac_py2_set_order_hashes_device(self._h, int(n), c_vp(int(d_hashes)), c_vp(int(d_order_out)), int(stream)))
@@ -380,6 +412,12 @@ class Context(object):
     def merge_rank_csc(self, world, n_cols, d_indptr_all, d_rank_off, d_indices_all, d_data_all, total_nnz):
         check(self._lib.cratac_merge_rank_csc(self._h, int(world), int(n_cols), c_vp(int(d_indptr_all)), c_vp(int(d_rank_off)),
                                               c_vp(int(d_indices_all)), c_vp(int(d_data_all)), int(total_nnz)))
+
+    def get_matrix_indptr(self, n_cols):
+        """indptr of the current CSC only (8 * (n_cols + 1) bytes)."""
+        indptr = np.zeros(n_cols + 1, dtype=np.int64)
+        check(self._lib.cratac_get_matrix(self._h, _ptr(indptr), None, None))
+        return indptr
 
     def get_matrix_cols(self, n_cols, nnz, out=None):
         """D2H of the current CSC when its column count is not the shard's own barcode count."""

@@ -60,6 +60,7 @@ int offset_peak_rows(Ctx* c, int64_t base);                                     
 int merge_runs_from_host(Ctx* c, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end);   // pileup.cu
 void py2_set_order_hashes(const long long* hashes, int64_t n, std::vector<int32_t>& order);   // decode.cu
 int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_order_out);   // py2order.cu
+int select_columns(Ctx* c, int64_t n_sel, const int64_t* h_cols, int drop_empty);   // matrix.cu
 int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off, const int64_t* d_indices_all,
                    const int32_t* d_data_all, int64_t total_nnz);                         // matrix.cu
 int dump_window_counts(Ctx* c, int contig, int32_t* d_W);                                // pileup.cu
@@ -565,6 +566,49 @@ int cratac_matrix_device(cratac_ctx* h, const int64_t** d_indptr, const int64_t*
     if (d_indptr) *d_indptr = c->d_indptr.as<int64_t>();
     if (d_indices) *d_indices = c->d_indices.as<int64_t>();
     if (d_data) *d_data = c->d_data.as<int32_t>();
+    return CRATAC_OK;
+}
+
+// ---- FILTER_PEAK_MATRIX -------------------------------------------------------------------------------------------
+// the current matrix from host CSC arrays (the stage starts from raw_peak_bc_matrix.h5)
+int cratac_set_matrix(cratac_ctx* h, int64_t n_cols, const int64_t* indptr, const int64_t* indices, const int32_t* data) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (n_cols < 0 || !indptr) { set_error("cratac_set_matrix: bad arguments"); return CRATAC_ERR_ARG; }
+    const int64_t nnz = indptr[n_cols];
+    if (indptr[0] != 0 || nnz < 0 || (nnz > 0 && (!indices || !data))) { set_error("cratac_set_matrix: bad indptr"); return CRATAC_ERR_ARG; }
+    for (int64_t j = 0; j < n_cols; j++)
+        if (indptr[j + 1] < indptr[j]) { set_error("cratac_set_matrix: indptr decreases at column %lld", (long long)j); return CRATAC_ERR_ARG; }
+    CRATAC_TRY(c->d_indptr.reserve(8 * (size_t)(n_cols + 1)));
+    CRATAC_TRY(c->d_indices.reserve(8 * (size_t)std::max<int64_t>(nnz, 1))); CRATAC_TRY(c->d_data.reserve(4 * (size_t)std::max<int64_t>(nnz, 1)));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_indptr.p, indptr, 8 * (size_t)(n_cols + 1), cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_indices.p, indices, 8 * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->d_data.p, data, 4 * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    }
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_cols = n_cols; c->nnz = nnz;
+    return CRATAC_OK;
+}
+
+int cratac_select_columns(cratac_ctx* h, int64_t n_sel, const int64_t* cols, int drop_empty, int64_t* n_cols_out, int64_t* nnz_out) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (n_sel < 0 || (n_sel > 0 && !cols)) { set_error("cratac_select_columns: bad arguments"); return CRATAC_ERR_ARG; }
+    CRATAC_TRY(select_columns(c, n_sel, cols, drop_empty));
+    if (n_cols_out) *n_cols_out = c->n_sel_cols;
+    if (nnz_out) *nnz_out = c->sel_nnz;
+    return CRATAC_OK;
+}
+
+int cratac_get_selected(cratac_ctx* h, int64_t* indptr, int64_t* indices, int32_t* data, int64_t* kept) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (indptr) CRATAC_CUDA(cudaMemcpyAsync(indptr, c->d_sel_indptr.p, 8 * (size_t)(c->n_sel_cols + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (indices && c->sel_nnz > 0) CRATAC_CUDA(cudaMemcpyAsync(indices, c->d_sel_indices.p, 8 * (size_t)c->sel_nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (data && c->sel_nnz > 0) CRATAC_CUDA(cudaMemcpyAsync(data, c->d_sel_data.p, 4 * (size_t)c->sel_nnz, cudaMemcpyDeviceToHost, c->stream));
+    if (kept && c->n_sel_cols > 0) CRATAC_CUDA(cudaMemcpyAsync(kept, c->d_sel_kept.p, 8 * (size_t)c->n_sel_cols, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     return CRATAC_OK;
 }
 

@@ -138,6 +138,8 @@ struct Ctx {
     // matrix
     DevBuf d_bc_hits, d_seg_off, d_cursor, d_hits, d_out_row, d_out_cnt, d_nnz_col;
     DevBuf d_indptr, d_indices, d_data;
+    DevBuf d_sel_indptr, d_sel_indices, d_sel_data, d_sel_kept, d_sel_scratch;   // result of select_columns (FILTER_PEAK_MATRIX)
+    int64_t n_sel_cols = 0, sel_nnz = 0;
     int64_t nnz = 0;
     int64_t n_hits = 0;
     int64_t n_cols = 0;                    // columns of the current matrix (= n_barcodes unless a global column map is set)

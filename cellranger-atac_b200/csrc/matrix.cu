@@ -569,4 +569,113 @@ int peak_matrix_device(Ctx* c) {
     return CRATAC_OK;
 }
 
+// ---- FILTER_PEAK_MATRIX: m[:, cols] (+ drop the columns left without a positive entry) -----------------------------
+// filter_peak_matrix/__init__.py:46-70 (prune) and :93 (filter_barcodes -> cellranger/matrix.py:658-662 m[:, indices]).
+// one warp per selected column: entries and whether any is > 0
+__global__ void __launch_bounds__(256) k_sel_count(const int64_t* __restrict__ cols, int64_t n_sel, int64_t n_cols_old, const int64_t* __restrict__ indptr,
+                                                    const int32_t* __restrict__ data, int drop_empty, int32_t* __restrict__ cnt,
+                                                    int32_t* __restrict__ keep, int64_t* status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_sel; j += n_warps) {
+        const int64_t c = cols[j];
+        if (c < 0 || c >= n_cols_old) { if (lane == 0) { raise_error(status, CRATAC_ERR_ARG, j); cnt[j] = 0; keep[j] = 0; } continue; }
+        const int64_t s = indptr[c], e = indptr[c + 1];
+        bool pos = false;
+        for (int64_t k = s + lane; k < e && !pos; k += 32) pos = data[k] > 0;
+        pos = __any_sync(0xffffffffu, pos);
+        const bool kp = !drop_empty || pos;
+        if (lane == 0) { cnt[j] = kp ? (int32_t)(e - s) : 0; keep[j] = kp; }
+    }
+}
+__global__ void k_sel_compact(const int64_t* __restrict__ cols, int64_t n_sel, const int64_t* __restrict__ indptr, const int32_t* __restrict__ cnt,
+                              const int32_t* __restrict__ keep, const int64_t* __restrict__ kpos, int64_t* __restrict__ kept, int32_t* __restrict__ out_cnt,
+                              int64_t* __restrict__ src_start) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sel || !keep[j]) return;
+    const int64_t o = kpos[j];
+    kept[o] = j;
+    out_cnt[o] = cnt[j];
+    src_start[o] = indptr[cols[j]];
+}
+// chunked over the output entries like k_csc_copy
+__global__ void __launch_bounds__(256) k_sel_copy(const int64_t* __restrict__ src_start, const int64_t* __restrict__ indptr_out, int64_t n_out, int64_t nnz,
+                                                   const int64_t* __restrict__ indices_in, const int32_t* __restrict__ data_in,
+                                                   int64_t* __restrict__ indices, int32_t* __restrict__ data) {
+    __shared__ int64_t s_j[2];
+    const int64_t p0 = (int64_t)blockIdx.x * CSC_CHUNK;
+    const int64_t p1 = p0 + CSC_CHUNK < nnz ? p0 + CSC_CHUNK : nnz;
+    if (threadIdx.x < 2) {
+        const int64_t target = threadIdx.x == 0 ? p0 : p1 - 1;
+        int64_t lo = 0, hi = n_out - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (indptr_out[mid] <= target) lo = mid; else hi = mid - 1;
+        }
+        s_j[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int64_t j0 = s_j[0], j1 = s_j[1];
+    const bool by_warp = j1 - j0 >= 8;
+    const int step = by_warp ? 8 : 1, width = by_warp ? 32 : 256;
+    const int me = by_warp ? (threadIdx.x & 31) : threadIdx.x;
+    for (int64_t j = j0 + (by_warp ? (threadIdx.x >> 5) : 0); j <= j1; j += step) {
+        const int64_t c0 = indptr_out[j], c1 = indptr_out[j + 1];
+        const int64_t a = c0 > p0 ? c0 : p0, b = c1 < p1 ? c1 : p1;
+        if (b <= a) continue;
+        const int64_t src = src_start[j] + (a - c0);
+        const int len = (int)(b - a);
+        for (int k = me; k < len; k += width) { indices[a + k] = indices_in[src + k]; data[a + k] = data_in[src + k]; }
+    }
+}
+
+int select_columns(Ctx* c, int64_t n_sel, const int64_t* h_cols, int drop_empty) {
+    cudaStream_t s = c->stream;
+    int64_t* st = c->d_status.as<int64_t>();
+    const size_t ns = (size_t)std::max<int64_t>(n_sel, 1);
+    // scratch: cols i64 | kpos i64 | src_start i64 | cnt i32 | keep i32 | out_cnt i32
+    CRATAC_TRY(c->d_sel_scratch.reserve(ns * (8 * 3 + 4 * 3) + 64));
+    int64_t* cols = c->d_sel_scratch.as<int64_t>();
+    int64_t* kpos = cols + ns;
+    int64_t* src_start = kpos + ns;
+    int32_t* cnt = reinterpret_cast<int32_t*>(src_start + ns);
+    int32_t* keep = cnt + ns;
+    int32_t* out_cnt = keep + ns;
+    CRATAC_TRY(c->d_sel_kept.reserve(8 * ns));
+    CRATAC_TRY(c->d_sel_indptr.reserve(8 * (ns + 1)));
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, s));
+    c->n_sel_cols = 0; c->sel_nnz = 0;
+    if (n_sel > 0) {
+        CRATAC_CUDA(cudaMemcpyAsync(cols, h_cols, 8 * (size_t)n_sel, cudaMemcpyHostToDevice, s));
+        const int g = (int)std::min<int64_t>((n_sel * 32 + 255) / 256, (int64_t)NUM_SMS * 16);
+        k_sel_count<<<g, 256, 0, s>>>(cols, n_sel, c->n_cols, c->d_indptr.as<int64_t>(), c->d_data.as<int32_t>(), drop_empty, cnt, keep, st);
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, keep, kpos, n_sel, &st[ST_TICKET2]));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_TICKET2], &st[ST_TICKET2], 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_TRY(sync_status(c));
+    const int64_t n_out = c->h_status[ST_TICKET2];
+    if (n_sel > 0) {
+        k_sel_compact<<<(unsigned)((n_sel + 255) / 256), 256, 0, s>>>(cols, n_sel, c->d_indptr.as<int64_t>(), cnt, keep, kpos, c->d_sel_kept.as<int64_t>(), out_cnt,
+                                                                     src_start);
+        c->launches++;
+    }
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, out_cnt, c->d_sel_indptr.as<int64_t>(), n_out, c->d_sel_indptr.as<int64_t>() + n_out));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_TICKET2], c->d_sel_indptr.as<int64_t>() + n_out, 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    const int64_t nnz = c->h_status[ST_TICKET2];
+    const size_t zz = (size_t)std::max<int64_t>(nnz, 1);
+    CRATAC_TRY(c->d_sel_indices.reserve(8 * zz)); CRATAC_TRY(c->d_sel_data.reserve(4 * zz));
+    if (nnz > 0) {
+        k_sel_copy<<<(unsigned)((nnz + CSC_CHUNK - 1) / CSC_CHUNK), 256, 0, s>>>(src_start, c->d_sel_indptr.as<int64_t>(), n_out, nnz, c->d_indices.as<int64_t>(),
+                                                                                c->d_data.as<int32_t>(), c->d_sel_indices.as<int64_t>(), c->d_sel_data.as<int32_t>());
+        c->launches++;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    CRATAC_CUDA(cudaStreamSynchronize(s));
+    c->n_sel_cols = n_out; c->sel_nnz = nnz;
+    return CRATAC_OK;
+}
+
 }  // namespace cratac

@@ -141,6 +141,20 @@ int cratac_peak_matrix(cratac_ctx* ctx, int64_t* nnz);
 int cratac_get_matrix(cratac_ctx* ctx, int64_t* indptr, int64_t* indices, int32_t* data);
 /* device views of the current results (valid until the next call that recomputes them) */
 int cratac_matrix_device(cratac_ctx* ctx, const int64_t** d_indptr, const int64_t** d_indices, const int32_t** d_data);
+
+/* ---- (6) FILTER_PEAK_MATRIX (the stage right after the path): replaces
+ *      filter_peak_matrix/__init__.py:84-96 -> cellranger/matrix.py:874-883 (filter_barcodes: the columns of
+ *      the sorted cell barcodes, m[:, indices] of matrix.py:658-662) and prune (:46-70: optional random
+ *      subset of barcodes, then the columns with at least one positive entry).  The caller passes the
+ *      column indices in output order (the random subset is drawn on the host with numpy's legacy
+ *      generator, as the reference does); with drop_empty the columns without a positive entry are
+ *      removed.  cratac_set_matrix loads a raw matrix from host CSC arrays (raw_peak_bc_matrix.h5);
+ *      after cratac_peak_matrix / cratac_run the matrix in HBM is used as it is.  kept[j] = position in
+ *      `cols` of output column j. */
+int cratac_set_matrix(cratac_ctx* ctx, int64_t n_cols, const int64_t* indptr, const int64_t* indices, const int32_t* data);
+int cratac_select_columns(cratac_ctx* ctx, int64_t n_sel, const int64_t* cols, int drop_empty, int64_t* n_cols_out,
+                          int64_t* nnz_out);
+int cratac_get_selected(cratac_ctx* ctx, int64_t* indptr, int64_t* indices, int32_t* data, int64_t* kept);
 int cratac_hist_device(cratac_ctx* ctx, const uint64_t** d_hist, int64_t* cap);
 
 /* ---- whole path in one call, no host round trip between kernels:

@@ -294,3 +294,38 @@ def hstack_csc(chunks):
 def feature_names(peak_lines):
     """cellranger/atac/feature_ref.py:58-68: id = name = 'chr:start-end'."""
     return ["{}:{}-{}".format(*line.strip("\n").split("\t")) for line in peak_lines]
+
+
+# ---------------------------------------------------------------------------------------------- FILTER_PEAK_MATRIX
+def filter_peak_matrix(n_features, bcs, indptr, indices, data, cell_barcodes, num_analysis_bcs=None, random_seed=None):
+    """filter_peak_matrix/__init__.py:84-96 (cell barcodes present in the matrix, over all species) ->
+    cellranger/matrix.py:874-883 (sorted union, m[:, indices] :658-662) -> prune (:46-70: optional random subset with
+    numpy's legacy generator, then the columns with at least one positive entry).
+    -> (bcs, indptr, indices, data) of the filtered CSC.  Plain loops; test infrastructure only."""
+    import numpy as np
+    index = {}
+    for j, b in enumerate(bcs):
+        index.setdefault(b, j)
+    present = set()
+    for species in cell_barcodes:
+        for bc in cell_barcodes[species]:
+            if bc in index:
+                present.add(bc)
+    sel = sorted(present)
+    cols = [index[b] for b in sel]
+    if num_analysis_bcs:
+        np.random.seed(0 if random_seed is None else random_seed)
+        n = len(cols)
+        pick = np.sort(np.random.choice(np.arange(n), size=min(num_analysis_bcs, n), replace=False))
+        cols = [cols[i] for i in pick]
+        sel = [sel[i] for i in pick]
+    out_bcs, out_indptr, out_indices, out_data = [], [0], [], []
+    for b, c in zip(sel, cols):
+        lo, hi = indptr[c], indptr[c + 1]
+        if not any(v > 0 for v in data[lo:hi]):
+            continue
+        out_bcs.append(b)
+        out_indices.extend(indices[lo:hi])
+        out_data.extend(data[lo:hi])
+        out_indptr.append(len(out_indices))
+    return out_bcs, out_indptr, out_indices, out_data

@@ -375,6 +375,107 @@ def make_matrix_cases(tmpdir):
     return out
 
 
+# --------------------------------------------------------------------------- FILTER_PEAK_MATRIX
+def _bisect_left(a, x, keys):
+    """cellranger/bisect.pyx:6-18 is Cython (not importable here): its 12 lines restated -- index into `keys` of x
+    given the argsort `a` of keys."""
+    lo, hi = 0, a.shape[0]
+    while hi - lo > 1:
+        i = (lo + hi) // 2
+        y = keys[a[i]]
+        if keys[a[i - 1]] < x and x <= y:
+            return a[i]
+        elif y < x:
+            lo = i
+        elif hi == i + 1:
+            hi = i
+        else:
+            hi = i + 1
+    return a[lo]
+
+
+class _NumpyProxy(object):
+    """numpy with the py2-era ``np.array(list, copy=False)`` meaning 'copy only if needed' (numpy 2 raises)."""
+    def __getattr__(self, k):
+        return getattr(np, k)
+
+    @staticmethod
+    def array(a, dtype=None, copy=True, **kw):
+        return np.asarray(a, dtype=dtype) if not copy else np.array(a, dtype=dtype, **kw)
+
+
+def run_filter_peak_matrix(n_features, bcs, indptr, indices, data, cell_barcodes, num_analysis_bcs, random_seed):
+    """filter_peak_matrix/__init__.py join (:84-96) + prune (:46-70) on the reference's CountMatrix
+    (cellranger/matrix.py: __init__ :187-202, bc_to_int :379-383, select_barcodes :658-662,
+    filter_barcodes :874-883), scipy doing the column slicing as it does there."""
+    import functools
+    import scipy.sparse as sp_sparse
+    ns = {"np": _NumpyProxy(), "sp_sparse": sp_sparse, "reduce": functools.reduce, "DEFAULT_DATA_DTYPE": "int32",
+          "cr_bisect": types.SimpleNamespace(bisect_left=_bisect_left)}
+    load_reference_module("lib/cellranger/lib/python/cellranger/matrix.py", ns, keep_funcs={"CountMatrix"})
+    src = open(os.path.join(REF, "lib/cellranger/lib/python/cellranger/matrix.py")).read()
+    assert ".itervalues()" in src                       # filter_barcodes: shimmed below like .iteritems()
+    ns2 = {"np": np, "martian": types.SimpleNamespace(log_info=lambda *a: None)}
+    load_reference_module("mro/atac/stages/processing/filter_peak_matrix/__init__.py", ns2, keep_funcs={"prune"})
+    CountMatrix = ns["CountMatrix"]
+    fdefs = [types.SimpleNamespace(id="f%d" % i, index=i) for i in range(n_features)]
+    m = sp_sparse.csc_matrix((np.array(data, dtype=np.int32), np.array(indices, dtype=np.int64), np.array(indptr, dtype=np.int64)),
+                             shape=(n_features, len(bcs)))
+    matrix = CountMatrix(types.SimpleNamespace(feature_defs=fdefs, all_tag_keys=[]), [b.encode() for b in bcs], m)
+    peak_matrix_bcs = set(matrix.bcs)
+    present = {}
+    for species in cell_barcodes:                        # the loop of filter_peak_matrix/__init__.py:84-91
+        present[species] = set()
+        for bc in cell_barcodes[species]:
+            if bc.encode() in peak_matrix_bcs:
+                present[species].add(bc.encode())
+
+    class _Dict(dict):                                   # py2 dict.itervalues for matrix.py:882
+        def itervalues(self):
+            return self.values()
+    matrix = matrix.filter_barcodes(_Dict(present))
+    matrix = ns2["prune"](matrix, num_analysis_bcs=num_analysis_bcs, random_state=random_seed)
+    out = matrix.m.tocsc()
+    return {"bcs": [b.decode() for b in matrix.bcs.tolist()], "indptr": out.indptr.astype(np.int64).tolist(),
+            "indices": out.indices.astype(np.int64).tolist(), "data": out.data.astype(np.int64).tolist()}
+
+
+def make_filter_cases():
+    cases = []
+    rng = np.random.default_rng(77)
+    specs = [("plain", 40, 60, 0.15, None, None, 0.0), ("subsample", 30, 80, 0.2, 25, 7, 0.0), ("subsample_more_than_present", 30, 50, 0.2, 500, 3, 0.0),
+             ("explicit_zeros", 25, 70, 0.1, None, None, 0.5), ("seed_none_means_zero", 20, 90, 0.3, 10, None, 0.0),
+             ("nothing_left", 10, 30, 0.0, None, None, 0.0), ("wide", 300, 400, 0.05, 120, 11, 0.1)]
+    for name, n_feat, n_bc, dens, nab, seed, zero_frac in specs:
+        cols = []
+        indptr = [0]
+        indices, data = [], []
+        for j in range(n_bc):
+            k = rng.binomial(n_feat, dens) if rng.random() > 0.2 else 0          # a fifth of the columns empty
+            rows = np.sort(rng.choice(n_feat, size=k, replace=False))
+            vals = rng.integers(1, 9, size=k)
+            if zero_frac and k:
+                vals[rng.random(k) < zero_frac] = 0                               # stored zeros: (m > 0) must ignore them
+            indices += rows.tolist()
+            data += vals.tolist()
+            indptr.append(len(indices))
+        letters = "ACGT"
+        bcs = []
+        seen = set()
+        while len(bcs) < n_bc:
+            b = "".join(letters[i] for i in rng.integers(0, 4, size=16)) + "-1"
+            if b not in seen:
+                seen.add(b)
+                bcs.append(b)
+        perm = rng.permutation(n_bc)
+        half = [bcs[i] for i in perm[: n_bc * 2 // 3]]
+        cell = {"GRCh38": half[: len(half) * 2 // 3] + ["TTTTTTTTTTTTTTTT-9"], "mm10": half[len(half) // 2:]}   # overlap + one absent barcode
+        res = run_filter_peak_matrix(n_feat, bcs, indptr, indices, data, cell, nab, seed)
+        cases.append({"name": name, "n_features": n_feat, "bcs": bcs, "indptr": indptr, "indices": indices, "data": data,
+                      "cell_barcodes": cell, "num_analysis_bcs": nab, "random_seed": seed, "result": res})
+    return cases
+
+
 def main():
     only = set(sys.argv[1:])
     with tempfile.TemporaryDirectory() as tmpdir:
@@ -384,6 +485,9 @@ def main():
         if not only or "matrix" in only:
             with open(os.path.join(HERE, "matrix.json"), "w") as f:
                 json.dump(make_matrix_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "filter" in only:
+            with open(os.path.join(HERE, "filter.json"), "w") as f:
+                json.dump(make_filter_cases(), f, separators=(",", ":"))
         if not only or "em" in only:
             with open(os.path.join(HERE, "em.json"), "w") as f:
                 json.dump(make_em_cases(), f, separators=(",", ":"))

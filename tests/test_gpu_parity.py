@@ -431,3 +431,42 @@ def test_py2_set_order_on_device_matches_host_simulation():
         torch.cuda.synchronize()
         ctx.py2_set_order_hashes_device(h.size, d_h.data_ptr(), d_o.data_ptr())
         assert np.array_equal(d_o.cpu().numpy(), want), h.size
+
+
+# ----------------------------------------------------------------------------- FILTER_PEAK_MATRIX
+FILTER_CASES = json.load(open(os.path.join(GOLDEN, "filter.json")))
+
+
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c["name"] for c in FILTER_CASES])
+def test_filter_peak_matrix_golden(case):
+    from cratac import stage_util
+    ctx = _ffi.Context([("matrix", 1)])
+    ctx.set_matrix(case["indptr"], case["indices"], case["data"])
+    bcs, indptr, indices, data = stage_util.filter_peak_matrix(ctx, case["bcs"], case["cell_barcodes"], case["num_analysis_bcs"], case["random_seed"])
+    want = case["result"]
+    assert bcs == want["bcs"]
+    assert indptr.tolist() == want["indptr"] and indices.tolist() == want["indices"] and data.tolist() == want["data"]
+    assert indptr.dtype == np.int64 and indices.dtype == np.int64 and data.dtype == np.int32
+    ctx.close()
+
+
+def test_filter_peak_matrix_large_random_vs_oracle():
+    """Columns of 0 .. 50 000 entries (chunked copy, columns spanning chunks), selection in arbitrary order with repeats excluded."""
+    from cratac import stage_util
+    from oracle import stages as ostages
+    rng = np.random.default_rng(3)
+    n_feat, n_bc = 60000, 700
+    sizes = np.where(rng.random(n_bc) < 0.1, rng.integers(20000, 50000, size=n_bc), rng.integers(0, 300, size=n_bc))
+    indptr = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    indices = np.concatenate([np.sort(rng.choice(n_feat, size=k, replace=False)) for k in sizes]).astype(np.int64)
+    data = rng.integers(0, 5, size=indices.size).astype(np.int32)
+    bcs = ["BC%05d-1" % i for i in rng.permutation(n_bc)]
+    cell = {"a": set(rng.choice(bcs, size=400, replace=False).tolist()), "b": set(rng.choice(bcs, size=100, replace=False).tolist()) | {"missing-1"}}
+    ctx = _ffi.Context([("matrix", 1)])
+    ctx.set_matrix(indptr, indices, data)
+    for nab, seed in ((None, None), (150, 5)):
+        got = stage_util.filter_peak_matrix(ctx, bcs, cell, nab, seed)
+        want = ostages.filter_peak_matrix(n_feat, bcs, indptr.tolist(), indices.tolist(), data.tolist(), cell, nab, seed)
+        assert got[0] == want[0]
+        assert got[1].tolist() == want[1] and got[2].tolist() == want[2] and got[3].tolist() == want[3]
+    ctx.close()

@@ -197,3 +197,15 @@ def test_em_oracle_vs_reference(case):
         return
     assert int(thr) == case["threshold"]
     assert np.allclose(np.array(params, dtype=float), np.array(case["params"]), rtol=1e-12, atol=0)
+
+
+FILTER_CASES = json.load(open(os.path.join(GOLDEN, "filter.json")))
+
+
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c["name"] for c in FILTER_CASES])
+def test_filter_peak_matrix_restatement_matches_reference(case):
+    """oracle.stages.filter_peak_matrix against vectors produced by the reference's own prune / CountMatrix code."""
+    bcs, indptr, indices, data = stages.filter_peak_matrix(case["n_features"], case["bcs"], case["indptr"], case["indices"], case["data"],
+                                                           case["cell_barcodes"], case["num_analysis_bcs"], case["random_seed"])
+    want = case["result"]
+    assert bcs == want["bcs"] and list(indptr) == want["indptr"] and list(indices) == want["indices"] and list(data) == want["data"]

@@ -168,3 +168,42 @@ def test_three_stages_end_to_end_match_reference_flow(tmp_path):
     assert open(os.path.join(gouts.raw_matrix_mex, "peaks.bed")).read() == peaks_text
     # the bedgraph the stage wrote is the reference writer's, row for row
     assert os.path.getsize(outs.cut_sites) > 0
+
+
+def test_filter_peak_matrix_stage_null_and_declaration():
+    fpm = load_stage("filter_peak_matrix")
+    assert "stage FILTER_PEAK_MATRIX(" in fpm.__MRO__ and "in  csv    cell_barcodes" in fpm.__MRO__ and "out path   filtered_matrix_mex" in fpm.__MRO__
+    assert fpm.split(Record(raw_matrix=None)) == {'chunks': []}
+    o = Record(filtered_matrix="x", filtered_matrix_mex="y")
+    fpm.join(Record(raw_matrix=None), o, [], [])
+    assert o.filtered_matrix is None
+
+
+@pytest.mark.gpu
+def test_filter_peak_matrix_stage_end_to_end(tmp_path):
+    """raw_peak_bc_matrix.h5 + cell_barcodes.csv -> filtered matrix h5 / MEX, against the oracle restatement of the stage."""
+    from oracle import stages as ostages
+    fpm = load_stage("filter_peak_matrix")
+    rng = np.random.default_rng(12)
+    n_feat, n_bc = 500, 300
+    sizes = np.where(rng.random(n_bc) < 0.25, 0, rng.integers(1, 60, size=n_bc))
+    indptr = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    indices = np.concatenate([np.sort(rng.choice(n_feat, size=k, replace=False)) for k in sizes] + [np.zeros(0, dtype=np.int64)]).astype(np.int64)
+    data = rng.integers(1, 7, size=indices.size).astype(np.int32)
+    bcs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=16)) + "-1" for _ in range(n_bc)]
+    feats = ["chr1:%d-%d" % (1000 * i, 1000 * i + 500) for i in range(n_feat)]
+    raw = str(tmp_path / "raw.h5")
+    h5.write_matrix_h5(raw, indptr, indices, data, n_feat, bcs, feats, "GRCh38", sw_version="t")
+    cells = {"GRCh38": [bcs[i] for i in rng.choice(n_bc, size=120, replace=False)], "mm10": [bcs[i] for i in rng.choice(n_bc, size=30, replace=False)] + ["AAAA-7"]}
+    csv = str(tmp_path / "cell_barcodes.csv")
+    with open(csv, "w") as f:
+        for sp, v in cells.items():
+            f.write(",".join([sp] + v) + "\n")
+    outs = Record(filtered_matrix=str(tmp_path / "f.h5"), filtered_matrix_mex=str(tmp_path / "mex"))
+    fpm.join(Record(raw_matrix=raw, num_analysis_bcs=80, random_seed=4, cell_barcodes=csv), outs, [], [])
+    want = ostages.filter_peak_matrix(n_feat, bcs, indptr.tolist(), indices.tolist(), data.tolist(), {k: set(v) for k, v in cells.items()}, 80, 4)
+    got = h5.read_matrix_h5(outs.filtered_matrix)
+    assert [b.decode() for b in got["barcodes"].tolist()] == want[0]
+    assert got["indptr"].tolist() == want[1] and got["indices"].tolist() == want[2] and got["data"].tolist() == want[3]
+    assert got["shape"].tolist() == [n_feat, len(want[0])]
+    assert os.path.exists(os.path.join(outs.filtered_matrix_mex, "matrix.mtx.gz")) or os.listdir(outs.filtered_matrix_mex)
