@@ -207,3 +207,56 @@ def test_filter_peak_matrix_stage_end_to_end(tmp_path):
     assert got["indptr"].tolist() == want[1] and got["indices"].tolist() == want[2] and got["data"].tolist() == want[3]
     assert got["shape"].tolist() == [n_feat, len(want[0])]
     assert os.path.exists(os.path.join(outs.filtered_matrix_mex, "matrix.mtx.gz")) or os.listdir(outs.filtered_matrix_mex)
+
+
+@pytest.mark.gpu
+def test_setup_aggr_samples_signal_normalization(tmp_path):
+    """SETUP_AGGR_SAMPLES (another caller of the same pileup + fit): per-library threshold and signal
+    mean over ALL contigs of the reference, rates in join -- against the oracle's histogram + fit."""
+    from oracle import em as oracle_em
+    spec = importlib.util.spec_from_file_location("stage_setup_aggr", os.path.join(util.PKG, "mro", "atac", "stages", "aggr", "setup_aggr_samples", "__init__.py"))
+    sas = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sas)
+    assert "stage SETUP_AGGR_SAMPLES(" in sas.__MRO__ and "out pickle     library_info" in sas.__MRO__
+    contigs = [("chr1", 700000), ("chr2", 500000), ("chrX", 250000)]
+    ref = str(tmp_path / "ref")
+    refmgr.write_reference(ref, contigs)
+    rows = []
+    want = {}
+    for lib, (n_frag, seed) in enumerate(((25000, 5), (40000, 6))):
+        frags = synth.generate(contigs, n_frag, 30, 300, seed=seed, background_factor=5)
+        text = synth.to_text(frags)
+        fpath = str(tmp_path / ("fragments_%d.tsv.gz" % lib))
+        bgzf.write(fpath, text)
+        cells = str(tmp_path / ("singlecell_%d.csv" % lib))
+        with open(cells, "w") as f:
+            f.write("barcode,total,duplicate,passed_filters,is__cell_barcode\n")
+            for k in range(50):
+                f.write("BC%d-1,%d,%d,%d,%d\n" % (k, 1000 + 10 * k + lib, 100, 700 + 5 * k, 1 if k % 2 == 0 else 0))
+        rows.append("lib%d,%s,%s" % (lib, fpath, cells))
+        o = util.oracle_decode(text, [c[0] for c in contigs])
+        hist = util.oracle_hist(contigs, [c[0] for c in contigs], o["chrom"], o["start"], o["end"])
+        thr, params = oracle_em.estimate_final_threshold(hist, 1 / 5.0)
+        want[lib + 1] = (int(thr), 1.0 / params[3])
+    csv = str(tmp_path / "aggr.csv")
+    with open(csv, "w") as f:
+        f.write("library_id,fragments,cells\n" + "\n".join(rows) + "\n")
+    s = sas.split(Record(aggr_csv=csv, normalization="signal_mean", reference_path=ref))
+    assert [c['n'] for c in s['chunks']] == [0, 1]
+    chunk_outs = []
+    for c in s['chunks']:
+        outs = Record(library_info=str(tmp_path / ("lib_%d.pickle" % c['n'])))
+        sas.main(Record(aggr_csv=csv, normalization="signal_mean", reference_path=ref, n=c['n']), outs)
+        chunk_outs.append(outs)
+    outs = Record(library_info=str(tmp_path / "library_info.pickle"), gem_group_index=None, gem_group_index_json=str(tmp_path / "ggi.json"))
+    sas.join(Record(aggr_csv=csv, normalization="signal_mean", reference_path=ref), outs, s['chunks'], chunk_outs)
+    info = pickle.load(open(outs.library_info, "rb"))
+    for lib_id, (thr, sm) in want.items():
+        assert info[lib_id]['original_threshold'] == thr
+        assert abs(info[lib_id]['signal_mean'] - sm) <= 1e-6 * sm
+        assert info[lib_id]['kind'] == "unique"
+    lowest = min(v[1] for v in want.values())
+    for lib_id, (thr, sm) in want.items():
+        assert abs(info[lib_id]['rate'] - lowest / sm) < 1e-6
+    assert info[1]['total_fragments_per_cell'] == float(np.median([1000 + 10 * k for k in range(0, 50, 2)]))
+    assert outs.gem_group_index == {"gem_group_index": {1: ("lib0", 1), 2: ("lib1", 1)}}
