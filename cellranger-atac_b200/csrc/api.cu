@@ -183,6 +183,8 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "run_capacity")) { c->run_cap = value; return CRATAC_OK; }
     if (!strcmp(key, "em_fast")) { c->em_fast = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "defer_sync")) { c->defer_sync = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "stream_decode")) { c->stream_decode = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
         c->profile = value != 0;
@@ -247,9 +249,16 @@ int cratac_decode_host(cratac_ctx* h, const char* text, int64_t nbytes) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
     if (nbytes < 0 || (nbytes > 0 && !text)) { set_error("cratac_decode_host: bad buffer"); return CRATAC_ERR_ARG; }
+    c->bc_is_slot = true;
+    if (nbytes > 0 && (c->stream_decode == 2 || (c->stream_decode == 1 && nbytes >= ((int64_t)64 << 20)))) {
+        // large text: chunked copy overlapped with the decode of the chunks already on the device
+        const int rc = decode_text_streamed(c, text, nbytes);
+        if (rc != CRATAC_ERR_CAPACITY) return rc;
+        // estimate or table too small: the text is on the device by now, decode it the exact way
+        return decode_text(c, c->d_text_own.as<char>(), nbytes);
+    }
     CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
     if (nbytes > 0) CRATAC_CUDA(cudaMemcpyAsync(c->d_text_own.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
-    c->bc_is_slot = true;
     return decode_text(c, c->d_text_own.as<char>(), nbytes);
 }
 

@@ -153,6 +153,11 @@ struct Ctx {
     DevBuf d_scan_tmp;
     int64_t* h_status = nullptr;           // pinned mirror
     int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
+    cudaStream_t copy_stream = nullptr;    // chunked H2D of a host text (decode_text_streamed)
+    cudaEvent_t copy_event = nullptr;
+    DevBuf d_stream_scalars;               // running line base + chunk total of the streamed decode
+    int stream_decode = 1;                 // option "stream_decode": 0 off, 1 overlap the H2D copy of a host text >= 64 MiB with its decode, 2 always
+    int64_t stream_chunk_tiles = 0;        // option "stream_chunk_tiles": text tiles per chunk (0: 128 MiB worth)
     int defer_sync = 0;                    // 1: window_histogram / compact_histogram / fit_threshold_device only queue their work
     int em_fast = 2;                       // 0 plain fixed point, 1 accelerated (em.cu), 2 register-resident kernel first (em_fast.cu)
     bool profile = false;
@@ -194,6 +199,7 @@ int exclusive_scan_i32_to_i64(Ctx* c, const int32_t* d_in, int64_t* d_out, int64
 
 // ---------------------------------------------------------------- stage entry points (host side)
 int decode_text(Ctx* c, const char* d_text, int64_t nbytes);          // decode.cu
+int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes); // decode.cu: host text, H2D overlapped with the decode
 int finalize_fragments(Ctx* c);                                       // decode.cu: contig offsets, pos index, checks
 int build_barcodes(Ctx* c);                                           // decode.cu: matrix column order (host half)
 int build_barcode_strings(Ctx* c);                                    // decode.cu: barcode strings in column order (lazy)

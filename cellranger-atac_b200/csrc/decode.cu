@@ -44,9 +44,9 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
 
 // ------------------------------------------------------------------ pass A: newline counts
 __global__ void __launch_bounds__(256) k_count_newlines(const char* __restrict__ text, int64_t nbytes, int64_t n_eff,
-                                                         int32_t* __restrict__ tile_counts) {
+                                                         int32_t* __restrict__ tile_counts, int64_t tile0) {
     // one CTA per tile; 256 threads x 4 x 16 B
-    int64_t tile_base = (int64_t)blockIdx.x * DEC_TILE;
+    int64_t tile_base = ((int64_t)blockIdx.x + tile0) * DEC_TILE;
     int cnt = 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(text) & 15) == 0);
 #pragma unroll
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_count_newlines(const char* __restrict__
     if (threadIdx.x == 0) {
         int s = 0;
         for (int w = 0; w < 8; w++) s += warp_cnt[w];
-        tile_counts[blockIdx.x] = s;
+        tile_counts[blockIdx.x + tile0] = s;
     }
 }
 
@@ -126,6 +126,10 @@ struct DecodeArgs {
     int bc_mask;
     int64_t* status;
     int use_tma;
+    // streamed decode (host text copied in chunks): tiles of this launch start at tile0, line numbers at *line_base
+    int64_t tile0;
+    const int64_t* line_base;
+    int64_t line_cap;                 // capacity of the output arrays when the total is not known in advance (0: exact)
 };
 
 __device__ __forceinline__ bool parse_uint(const unsigned char* s, int b, int e, int32_t* out) {
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = (int64_t)blockIdx.x + a.tile0;
     const int64_t tile_base = tile * DEC_TILE;
     const int n_lines = a.tile_counts[tile];
     if (n_lines == 0) return;   // uniform per CTA
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     }
 
     // ---- one line per thread: tabs from the chunk masks, numbers and barcode a word at a time
-    const int64_t out_base = a.tile_offsets[tile];
+    const int64_t out_base = a.tile_offsets[tile] + (a.line_base ? *a.line_base : 0);
     int loc_maxpos = 0, loc_maxneg = 0;
     for (int li = tid; li < n_lines; li += DEC_THREADS) {
         int b = li == 0 ? s_first_begin : nlpos[li - 1] + 1;
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
             probes++;
         }
         if (!placed) { raise_error(a.status, CRATAC_ERR_CAPACITY, line_no); continue; }
+        if (a.line_cap > 0 && line_no >= a.line_cap) { raise_error(a.status, CRATAC_ERR_CAPACITY, -7); continue; }   // more lines than estimated
         // `seen_first` may be stale (cached) but only ever too large: the atomicMin decides
         if (seen_first > (unsigned long long)line_no) atomicMin(&a.bc_tab[slot].first, (unsigned long long)line_no);
         a.chrom[line_no] = cid;
@@ -652,7 +657,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
     CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
     CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
     c->stage_begin(SG_DECODE_COUNT);
-    k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>());
+    k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), 0);
     c->stage_end(SG_DECODE_COUNT);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
@@ -684,6 +689,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
         a.status = st;
         a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
+        a.tile0 = 0; a.line_base = nullptr; a.line_cap = 0;
         c->stage_begin(SG_DECODE_PARSE);
         k_parse_tiles<<<(unsigned)n_tiles, DEC_THREADS, 0, c->stream>>>(a);
         c->stage_end(SG_DECODE_PARSE);
@@ -711,6 +717,101 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         c->n_barcodes = nb;
         break;
     }
+    CRATAC_TRY(finalize_fragments(c));
+    return barcode_prepare_device(c);
+}
+
+__global__ void k_add_i64(int64_t* __restrict__ acc, const int64_t* __restrict__ x) { *acc += *x; }
+
+// Host text -> fragments with the PCIe copy overlapped: the text is copied in chunks on a copy stream and every chunk is
+// counted, scanned (line offsets relative to the chunk, plus a running base kept on the device) and parsed as soon as it
+// has arrived, while the next chunk is in flight.  The number of lines is not known before the last chunk, so the output
+// arrays are sized from an estimate; returns CRATAC_ERR_CAPACITY when anything did not fit (table or estimate) -- the
+// caller then falls back to copy-all-then-decode.
+int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
+    if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
+    CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
+    char* d_text = c->d_text_own.as<char>();
+    c->d_text = d_text;
+    c->text_bytes = nbytes;
+    c->bc_ready = false;
+    c->barcodes.clear();
+    int64_t* st = c->d_status.as<int64_t>();
+    if (!c->copy_stream) {
+        CRATAC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CRATAC_CUDA(cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming));
+    }
+    const int64_t n_eff = nbytes + ((nbytes > 0 && h_text[nbytes - 1] != '\n') ? 1 : 0);
+    int64_t n_tiles = (n_eff + DEC_TILE - 1) / DEC_TILE;
+    if (n_tiles == 0) n_tiles = 1;
+    CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
+    CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
+    const size_t held = std::min({c->d_chrom.cap, c->d_start.cap, c->d_end.cap, c->d_bc.cap, c->d_dup.cap}) / 4;
+    const int64_t line_cap = std::max<int64_t>(nbytes / 16 + 4096, (int64_t)held);
+    {
+        const size_t nn = (size_t)line_cap;
+        CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));
+        CRATAC_TRY(c->d_bc.reserve(4 * nn)); CRATAC_TRY(c->d_dup.reserve(4 * nn));
+    }
+    const size_t cap = (size_t)c->bc_table_cap;
+    CRATAC_TRY(c->d_bc_keys.reserve(sizeof(BcSlot) * cap));
+    CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
+    CRATAC_TRY(c->d_stream_scalars.reserve(64));
+    int64_t* line_base = c->d_stream_scalars.as<int64_t>();
+    int64_t* chunk_total = line_base + 1;
+    k_init_table<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_bc_keys.as<BcSlot>(), (int)cap);
+    c->launches++;
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_BARCODES], 0, sizeof(int64_t) * 3, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(line_base, 0, 16, c->stream));
+    DecodeArgs a;
+    a.text = d_text; a.nbytes = nbytes; a.n_eff = n_eff;
+    a.tile_offsets = c->d_tile_offsets.as<int64_t>(); a.tile_counts = c->d_tile_counts.as<int32_t>();
+    a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
+    a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
+    a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
+    a.bc_tab = c->d_bc_keys.as<BcSlot>();
+    a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
+    a.status = st;
+    a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
+    a.line_base = line_base; a.line_cap = line_cap;
+    const int64_t CHUNK_TILES = c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles : (int64_t)(128 << 20) / DEC_TILE;   // default: 128 MiB of text per chunk
+    c->stage_begin(SG_DECODE_PARSE);
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES) {
+        const int64_t t1 = std::min(n_tiles, t0 + CHUNK_TILES);
+        const int64_t b0 = t0 * DEC_TILE, b1 = std::min(nbytes, t1 * DEC_TILE);
+        if (b1 > b0) CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, h_text + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+        CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
+        CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->copy_event, 0));
+        const unsigned nt = (unsigned)(t1 - t0);
+        k_count_newlines<<<nt, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), t0);
+        CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>() + t0, c->d_tile_offsets.as<int64_t>() + t0, t1 - t0, chunk_total));
+        a.tile0 = t0;
+        k_parse_tiles<<<nt, DEC_THREADS, 0, c->stream>>>(a);
+        k_add_i64<<<1, 1, 0, c->stream>>>(line_base, chunk_total);
+        c->launches += 3;
+        CRATAC_CUDA(cudaGetLastError());
+    }
+    c->stage_end(SG_DECODE_PARSE);
+    CRATAC_CUDA(cudaMemcpyAsync(&st[ST_N_FRAGMENTS], line_base, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_FRAGMENTS], line_base, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, c->stream));   // error, arg
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_BARCODES], &st[ST_N_BARCODES], sizeof(int64_t) * 3, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_mark("decode_streamed_sync");
+    const int64_t err = c->h_status[ST_ERROR];
+    const int64_t nb = c->h_status[ST_N_BARCODES];
+    if (err == CRATAC_ERR_CAPACITY || (err == 0 && nb * 2 > (int64_t)c->bc_table_cap)) return CRATAC_ERR_CAPACITY;   // caller: exact two-pass path
+    if (err != 0) {
+        int64_t arg = c->h_status[ST_ERROR_ARG];
+        if (err == CRATAC_ERR_PARSE) set_error("malformed fragments line %lld (expected contig\\tstart\\tstop\\tbarcode\\tdup_count)", (long long)(arg + 1));
+        else if (err == CRATAC_ERR_CONTIG) set_error("fragments line %lld: contig is not in the reference", (long long)(arg + 1));
+        else set_error("device error %lld (arg %lld) in decode", (long long)err, (long long)arg);
+        c->n_fragments = 0;
+        return (int)err;
+    }
+    c->n_fragments = c->h_status[ST_N_FRAGMENTS];
+    c->n_barcodes = nb;
     CRATAC_TRY(finalize_fragments(c));
     return barcode_prepare_device(c);
 }

@@ -57,6 +57,11 @@ int cratac_abi_version(void);
 int cratac_create(int device, int n_contigs, const char* const* contig_names, const int64_t* contig_lens,
                   const int32_t* is_primary, cratac_ctx** out);
 void cratac_destroy(cratac_ctx* ctx);
+/* options: "barcode_order" (CRATAC_BC_ORDER_*), "barcode_table_slots", "run_capacity", "em_fast" (0 plain fixed
+ * point, 1 accelerated, 2 on-chip kernel first), "profile" (per-kernel CUDA events), "defer_sync" (see
+ * cratac_fit_threshold_result), "stream_decode" (0 off / 1 host texts of 64 MiB and more / 2 always: the host text is
+ * copied in chunks and each chunk is decoded while the next one is on the PCIe bus), "stream_chunk_tiles" (16 KiB
+ * text tiles per chunk, 0 = 128 MiB worth) */
 int cratac_set_option(cratac_ctx* ctx, const char* key, int64_t value);
 /* kernels launched by this context since creation / last reset */
 int64_t cratac_launch_count(cratac_ctx* ctx, int reset);

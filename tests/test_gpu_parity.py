@@ -470,3 +470,44 @@ def test_filter_peak_matrix_large_random_vs_oracle():
         assert got[0] == want[0]
         assert got[1].tolist() == want[1] and got[2].tolist() == want[2] and got[3].tolist() == want[3]
     ctx.close()
+
+
+def test_streamed_host_decode_equals_plain_decode():
+    """cratac_decode_host with the chunked, overlapped H2D path (option stream_decode = 2, tiny chunks so that lines,
+    look-back windows and the running line base cross many chunk borders) against the copy-all-then-decode path."""
+    contigs = synth.GRCH38[:4]
+    frags = synth.generate(contigs, 150000, 50, 300, seed=21)
+    text = synth.to_text(frags)
+    for tail in (text, text.rstrip(b"\n")):                       # with and without a final newline
+        plain = _ffi.Context(contigs)
+        plain.set_option("stream_decode", 0)
+        n0, nb0 = plain.decode_host(tail)
+        want = plain.get_fragments()
+        want_bcs = plain.get_barcodes()
+        for chunk_tiles in (1, 3, 64):
+            ctx = _ffi.Context(contigs)
+            ctx.set_option("stream_decode", 2)
+            ctx.set_option("stream_chunk_tiles", chunk_tiles)
+            n1, nb1 = ctx.decode_host(tail)
+            assert (n1, nb1) == (n0, nb0)
+            got = ctx.get_fragments()
+            for k in ("chrom", "start", "end", "bc", "dup"):
+                assert np.array_equal(got[k], want[k]), k
+            assert ctx.get_barcodes() == want_bcs
+            ctx.close()
+        plain.close()
+
+
+def test_streamed_host_decode_falls_back_when_the_estimate_is_too_small():
+    """Lines of ~12 bytes: more lines than the nbytes / 16 estimate -> the exact two-pass path takes over."""
+    contigs = [("c", 100000)]
+    lines = ["c\t%d\t%d\tB%d\t1" % (i // 3000, i // 3000 + 1, i % 7) for i in range(1, 90000)]
+    text = ("\n".join(lines) + "\n").encode()
+    ctx = _ffi.Context(contigs)
+    ctx.set_option("stream_decode", 2)
+    n, nb = ctx.decode_host(text)
+    assert n == len(lines) and nb == 7
+    fr = ctx.get_fragments()
+    assert fr["start"].tolist() == [i // 3000 for i in range(1, 90000)] and fr["end"].tolist() == [i // 3000 + 1 for i in range(1, 90000)]
+    assert len(text) // 16 + 4096 < len(lines)                   # i.e. the streamed attempt did run out of room
+    ctx.close()
