@@ -4,8 +4,10 @@
 // Layout: the text is cut into fixed 16 KiB tiles.  A line belongs to the tile that holds its
 // terminating '\n'.  Pass A counts newlines per tile (128-bit loads), a scan turns the counts into
 // line offsets, pass B stages each tile (+256 B look-back for the line that straddles the tile
-// start) into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier), finds the
-// newlines, and parses one line per thread.  Barcodes of the 10x form [ACGT]{16}-<int> pack
+// start) into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier), turns the newline and tab
+// bits of the tile into ordered position lists, and parses one line per thread (its 4 tabs are 4
+// consecutive list entries).  A host text is copied in chunks and decoded chunk by chunk under the copy
+// (decode_text_streamed).  Barcodes of the 10x form [ACGT]{16}-<int> pack
 // losslessly into 64 bits; any other byte string falls back to a 63-bit hash.  Both go through one
 // open-addressing table in HBM/L2 (atomicCAS) that also records the first line of each barcode.
 #include <algorithm>

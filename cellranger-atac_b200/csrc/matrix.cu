@@ -4,14 +4,16 @@
 // barcodes in one pass instead of 30 barcode chunks that each re-read the file.
 //
 //   K6a  count   per fragment: upper_bound(peak starts, pos) - 1, half-open containment test, for
-//                pos in (start, stop) -- stop used as is, dup_count ignored; hits per barcode (REDG).
-//   scan         hits per barcode -> segment offsets.
-//   K6b  scatter same search, peak row written into the barcode's segment.
-//   K7   reduce  per barcode segment: sort the rows (bitonic in shared memory for short segments,
-//                range-partitioned counting in shared memory for long ones) and run-length reduce
-//                to (row, count).
+//                pos in (start, stop) -- stop used as is, dup_count ignored; ONE record per (fragment, peak)
+//                (a fragment with both ends in the same peak is one record worth 2); records per barcode (REDG).
+//   scan         records per barcode -> segment offsets.
+//   K6b  scatter same search, record = row << 1 | both-ends written into the barcode's segment.
+//   K7   reduce  per barcode segment: sort the records (one warp for <= 1024, a CTA for <= 4096: bitonic in
+//                shared memory; range-partitioned counting in shared memory for longer ones) and run-length
+//                reduce to (row, count).
 //   K8   build   indptr = scan of distinct counts in column order; copy (row, count) segments to
-//                indices int64 / data int32.
+//                indices int64 / data int32, chunked over the output entries.
+//   select_columns (FILTER_PEAK_MATRIX) and merge_rank_csc (multi-GPU) reuse the chunked copy.
 #include <algorithm>
 
 #include "common.cuh"
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
 }
 
 // ---- K7: per-barcode sort + run-length reduce -----------------------------------------------------
-// short segments: bitonic sort of <= SORT_SMALL rows in shared memory; one CTA per barcode
+// medium segments (SORT_WARP < records <= SORT_SMALL): bitonic sort in shared memory; one CTA per barcode
 __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
                                                                 int64_t n_bc, int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                 int32_t* __restrict__ nnz_col) {

@@ -9,8 +9,8 @@
 // shared-memory atomics, turns it into an inclusive prefix sum in place and reads
 //     W[p] = S[p+200] - S[p-201]            (window of count_cut_sites/__init__.py:100-101)
 // for the bases it owns.  Mode HIST bins W>0 (block-local bins, run-length aggregated, flushed once
-// per CTA); mode PEAKS emits the boundaries of the runs W >= threshold in genome order (a chained
-// prefix over tiles gives each tile its output offset) plus what the zero-gap rule of
+// per CTA); mode PEAKS emits the boundaries of the runs W >= threshold into CTA-private regions, tile by tile
+// (k_gather_events restores genome order from the per-tile counts: no CTA waits for another) plus what the zero-gap rule of
 // write_chrom_bedgraph (count_cut_sites/__init__.py:36-37) needs; mode DUMP writes W (tests, bedgraph).
 // HBM traffic: 8 B per fragment (start, end) x (1 + halo overhead); everything per-base is on chip.
 #include <algorithm>
@@ -26,7 +26,7 @@ constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entrie
 constexpr int PU_PAD = 64;                          // slack for vector over-reads past the last window
 constexpr int PU_HALO_LO = HALF_WINDOW + 2;         // 202
 constexpr int PU_HALO_HI = HALF_WINDOW + 1;         // 201 (positions up to b + 200)
-constexpr int TILE_T = PU_N - PU_HALO_LO - PU_HALO_HI + 1;   // owned bases per tile (24686)
+constexpr int TILE_T = PU_N - PU_HALO_LO - PU_HALO_HI + 1;   // owned bases per tile (10862)
 constexpr int PU_OWN_CHUNK = PU_CHUNK;              // owned bases per thread (multiple of 4)
 constexpr int PU_HB = 2048;                         // block-local histogram bins
 static_assert(PU_OWN_CHUNK * PU_THREADS >= TILE_T, "owned chunking must cover the tile");
