@@ -99,6 +99,8 @@ struct Ctx {
     DevBuf d_pos_index;                    // int64 per 1024 bases: first fragment with start >= k * 1024
     DevBuf d_tile_desc;                    // per pileup tile: contig, extent, fragment range
     bool tile_desc_valid = false;
+    bool tile_bound_valid = false;         // d_tile_bound / d_tile_summary hold the histogram pass's per-tile results for these fragments
+    DevBuf d_tile_bound;
     // text
     const char* d_text = nullptr;          // borrowed or owned device text of the last decode
     int64_t text_bytes = 0;

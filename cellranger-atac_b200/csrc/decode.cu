@@ -821,6 +821,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
 int finalize_fragments(Ctx* c) {
     int64_t n = c->n_fragments;
     c->tile_desc_valid = false;
+    c->tile_bound_valid = false;
     int64_t* st = c->d_status.as<int64_t>();
     int nc = c->n_contigs;
     CRATAC_TRY(c->d_contig_frag_off.reserve(sizeof(int64_t) * (nc + 2)));

@@ -66,6 +66,8 @@ struct PileupArgs {
     int64_t* tile_src_s;            // per tile: where its events sit in evt_start / evt_end
     int64_t* tile_src_e;
     int4* tile_summary;             // first_nz_pos, first_nz_val, last_nz_pos, last_nz_val
+    int32_t* tile_bound;            // per tile: an upper bound of its window counts.  MODE_HIST writes it (and the summary);
+                                    // MODE_PEAKS skips the tiles whose bound is below the threshold (null: no skipping)
     int64_t* fills;                 // pairs (g0, g1)
     int64_t fill_cap;
     // MODE_DUMP
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
     int* sc = smem;                       // PU_N (+ PU_PAD)
     int* hist_s = smem + PU_N + PU_PAD;   // PU_HB (MODE_HIST)
     __shared__ int warp_tot[PU_THREADS / 32];
-    __shared__ int s_first_nz, s_last_nz;
+    __shared__ int s_first_nz, s_last_nz, s_bound;
     __shared__ long long s_base_s, s_base_e;
     __shared__ int s_cur_s, s_cur_e;
 
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
             s_next[par ^ 1] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
             s_first_nz = 0x7fffffff;
             s_last_nz = -1;
+            s_bound = 0;
         }
         par ^= 1;
         const TileDesc td = a.desc[tile];
@@ -201,6 +204,9 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
         const int64_t base = ta - PU_HALO_LO;                                  // genome position of sc[0]
 
         if (MODE == MODE_DUMP && c != a.dump_contig) continue;
+        // no window count of this tile can reach the threshold (bound from the histogram pass): nothing to emit, and the
+        // tile's non-zero summary is already in place
+        if (MODE == MODE_PEAKS && a.tile_bound && a.tile_bound[tile] < thr) continue;
 
         // ---- zero the count array
         // ---- issue the first fragment loads, zero the count array while they fly, then scatter
@@ -268,7 +274,37 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
             // collect garbage (it is never read); the checked path handles the few tiles over the bound.
             const int hi = min(k0 + PU_OWN_CHUNK + 401, PU_N - 1);
             const int bound = k0 < own ? sc[hi] - sc[k0] : 0;
+            if (a.tile_bound) {
+                // for the peak pass: the tile's bound and its first / last base with a non-zero window count
+                // (reduced in the warp first: one shared-memory atomic per warp, not per thread)
+                int f = 0x7fffffff, l = -1;
+                if (k0 < k1) {
+                    int ff = k0, ll = k1 - 1;
+                    while (ff < k1 && sc[ff + 402] - sc[ff + 1] == 0) ff++;
+                    if (ff < k1) {
+                        while (sc[ll + 402] - sc[ll + 1] == 0) ll--;
+                        f = ff; l = ll;
+                    }
+                }
+                const int wb = __reduce_max_sync(0xffffffffu, bound);
+                const int wf = __reduce_min_sync(0xffffffffu, f), wl = __reduce_max_sync(0xffffffffu, l);
+                if ((tid & 31) == 0) {
+                    if (wb > 0) atomicMax(&s_bound, wb);
+                    if (wl >= 0) { atomicMin(&s_first_nz, wf); atomicMax(&s_last_nz, wl); }
+                }
+            }
             const bool fast = !__syncthreads_or(bound >= PU_HB);
+            if (a.tile_bound && tid == 0) {
+                int4 sm;
+                sm.x = sm.z = -1; sm.y = sm.w = 0;
+                if (s_last_nz >= 0) {
+                    const int f = s_first_nz, l = s_last_nz;
+                    sm.x = (int)(ta + f); sm.y = sc[f + 402] - sc[f + 1];
+                    sm.z = (int)(ta + l); sm.w = sc[l + 402] - sc[l + 1];
+                }
+                a.tile_summary[tile] = sm;
+                a.tile_bound[tile] = s_bound;
+            }
             if (fast) {
                 auto body = [&](int, int w) {
                     const bool changed = w != cur;
@@ -567,7 +603,7 @@ static int fill_args(Ctx* c, PileupArgs& a) {
     a.n_contigs = c->n_contigs; a.n_tiles = c->contig_tile_off[c->n_contigs];
     a.status = c->d_status.as<int64_t>();
     a.ghist = nullptr; a.evt_start = a.evt_end = nullptr; a.cta_cap = 0; a.tile_ns = a.tile_ne = nullptr;
-    a.tile_src_s = a.tile_src_e = nullptr; a.tile_summary = nullptr;
+    a.tile_src_s = a.tile_src_e = nullptr; a.tile_summary = nullptr; a.tile_bound = nullptr;
     a.fills = nullptr; a.fill_cap = 0; a.dump_W = nullptr; a.dump_contig = -1;
     return CRATAC_OK;
 }
@@ -617,6 +653,14 @@ int window_histogram(Ctx* c) {
     PileupArgs a;
     fill_args(c, a);
     a.ghist = c->d_hist.as<unsigned long long>();
+    {
+        const size_t nt = (size_t)std::max<int64_t>(c->contig_tile_off[c->n_contigs], 1);
+        CRATAC_TRY(c->d_tile_summary.reserve(16 * nt));
+        CRATAC_TRY(c->d_tile_bound.reserve(4 * nt));
+        a.tile_summary = c->d_tile_summary.as<int4>();
+        a.tile_bound = c->d_tile_bound.as<int32_t>();
+        c->tile_bound_valid = true;           // (cleared when the fragments change)
+    }
     c->stage_begin(SG_PILEUP_HIST);
     CRATAC_TRY(launch_pileup<MODE_HIST>(c, a));
     c->stage_end(SG_PILEUP_HIST);
@@ -702,6 +746,7 @@ int call_peaks_device(Ctx* c) {
         a.evt_start = run_start + cap; a.evt_end = run_end + cap; a.cta_cap = cta_cap;
         a.tile_ns = tile_ns; a.tile_ne = tile_ne; a.tile_src_s = tile_src_s; a.tile_src_e = tile_src_e;
         a.tile_summary = c->d_tile_summary.as<int4>(); a.fills = fills; a.fill_cap = fill_cap;
+        a.tile_bound = c->tile_bound_valid ? c->d_tile_bound.as<int32_t>() : nullptr;
         c->stage_begin(SG_PILEUP_PEAKS);
         CRATAC_TRY(launch_pileup<MODE_PEAKS>(c, a));
         c->stage_end(SG_PILEUP_PEAKS);
