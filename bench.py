@@ -468,9 +468,29 @@ def main():
     em_ms = stage_ms.get("em_fit", 0.0) / args.steps
     dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roofline = None
+    traffic = None
+    ncu_csv = os.path.join(ROOT, "profiles", "r01g_kernels_full_250m.csv")
+    if dom and world == 1 and args.fragments == 250000000 and os.path.exists(ncu_csv):
+        # DRAM bytes of the dominant group's kernels from the committed `ncu --set full` capture of this same workload
+        import csv
+        name_of = {"decode": ("k_count_newlines", "k_parse_tiles"), "pileup_window_hist": ("k_pileup<0>",), "pileup_call_peaks": ("k_pileup<1>",),
+                   "overlap": ("k_overlap<0>", "k_overlap<1>"), "sort_reduce": ("k_reduce_warp", "k_reduce_small", "k_reduce_large"),
+                   "csc_build": ("k_csc_copy",)}[dom]
+        rows = list(csv.reader(open(ncu_csv)))
+        hdr = rows[0]
+        seen, total = set(), 0.0
+        for r in rows[2:]:
+            for nm in name_of:
+                if nm in r[0] and nm not in seen:               # one launch of each kernel
+                    seen.add(nm)
+                    total += float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")])
+        if len(seen) == len(name_of):
+            traffic = total * 1e9                               # the capture reports Gbyte
     if dom:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": kernels[dom]["frac"], "traffic": traffic,
+                    "traffic_note": "bytes per step: ncu dram__bytes_read.sum + dram__bytes_write.sum of the group's kernels, profiles/r01g_kernels_full_250m.csv" if traffic else None,
+                    "peak_source": peak_src,
                     "note": "achieved = SURVEY section 8d algorithmic bytes of the stages the kernel replaces / CUDA-event time"}
 
     # ---- the stage right after the path (FILTER_PEAK_MATRIX) on the matrix just built: the 10 000
