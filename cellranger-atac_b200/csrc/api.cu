@@ -280,6 +280,7 @@ int cratac_set_fragments(cratac_ctx* h, int64_t n, const int32_t* chrom, const i
     }
     c->n_fragments = n;
     c->n_barcodes = n_barcodes;
+    c->dense_nfrag_valid = false;          // counted on demand by peak_matrix_device
     c->bc_is_slot = false;
     c->barcodes.clear();
     for (int64_t j = 0; j < n_barcodes; j++) c->barcodes.push_back(barcodes ? barcodes[j] : "");

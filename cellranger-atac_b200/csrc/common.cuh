@@ -121,6 +121,8 @@ struct Ctx {
     std::vector<std::string> barcodes;     // matrix column order
     int bc_order = CRATAC_BC_ORDER_PY2SET;
     bool bc_ready = false;
+    DevBuf d_bc_nfrag, d_dense_nfrag;      // fragments per table slot / per dense barcode (int32)
+    bool dense_nfrag_valid = false;        // d_dense_nfrag matches the current fragments (decode fills it; set_fragments counts on demand)
     bool bc_is_slot = false;               // d_bc holds hash-table slots (decode) vs dense ids (set_fragments)
     // histogram / threshold
     DevBuf d_hist;                         // uint64[HIST_CAP]

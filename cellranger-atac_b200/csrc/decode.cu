@@ -124,6 +124,7 @@ struct DecodeArgs {
     int contig_mask;
     int32_t *chrom, *start, *end, *bc, *dup;
     BcSlot* bc_tab;
+    int32_t* bc_nfrag;                // fragments per table slot (sizes the matrix's per-barcode hit segments: no count pass)
     long long* bc_textoff;
     int bc_mask;
     int64_t* status;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         if (a.line_cap > 0 && line_no >= a.line_cap) { raise_error(a.status, CRATAC_ERR_CAPACITY, -7); continue; }   // more lines than estimated
         // `seen_first` may be stale (cached) but only ever too large: the atomicMin decides
         if (seen_first > (unsigned long long)line_no) atomicMin(&a.bc_tab[slot].first, (unsigned long long)line_no);
+        atomicAdd(&a.bc_nfrag[slot], 1);
         a.chrom[line_no] = cid;
         a.start[line_no] = v_start;
         a.end[line_no] = v_end;
@@ -483,7 +485,7 @@ __global__ void k_max_len(const int32_t* __restrict__ start, const int32_t* __re
 }
 
 // ------------------------------------------------------------------ barcode table -> dense ids
-__global__ void k_table_compact(const BcSlot* __restrict__ tab,
+__global__ void k_table_compact(const BcSlot* __restrict__ tab, const int32_t* __restrict__ nfrag, int32_t* __restrict__ dense_nfrag,
                                 const long long* __restrict__ textoff, int cap, int32_t* __restrict__ slot_to_dense,
                                 unsigned long long* __restrict__ dense_first, long long* __restrict__ dense_textoff,
                                 unsigned long long* __restrict__ dense_bckey, unsigned long long* counter) {
@@ -496,6 +498,7 @@ __global__ void k_table_compact(const BcSlot* __restrict__ tab,
     dense_first[d] = e.first;
     dense_textoff[d] = textoff[s];
     dense_bckey[d] = e.key;
+    dense_nfrag[d] = nfrag[s];
 }
 
 __global__ void k_gather_barcode_text(const char* __restrict__ text, const long long* __restrict__ dense_textoff, int64_t n,
@@ -588,6 +591,8 @@ static int barcode_prepare_device(Ctx* c) {
     CRATAC_TRY(c->d_dense_first.reserve(8 * nn)); CRATAC_TRY(c->d_dense_textoff.reserve(8 * nn));
     CRATAC_TRY(c->d_dense_key.reserve(8 * nn));                 // py2 hashes by dense id
     CRATAC_TRY(c->d_dense_bckey.reserve(8 * nn));               // 64-bit barcode keys by dense id
+    CRATAC_TRY(c->d_dense_nfrag.reserve(4 * nn));               // fragments per dense barcode
+    c->dense_nfrag_valid = true;
     CRATAC_TRY(c->d_dense_to_col.reserve(4 * nn)); CRATAC_TRY(c->d_col_to_dense.reserve(4 * nn));
     const int64_t n_words = (n + 31) / 32 + 1;
     CRATAC_TRY(c->d_bc_bitmap.reserve(16 * (size_t)n_words + 12 * nn + 64));
@@ -599,7 +604,7 @@ static int barcode_prepare_device(Ctx* c) {
     cudaStream_t s = c->stream;
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
     c->stage_begin(SG_BARCODE_TABLE);
-    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<BcSlot>(),
+    k_table_compact<<<(c->bc_table_cap + 255) / 256, 256, 0, s>>>(c->d_bc_keys.as<BcSlot>(), c->d_bc_nfrag.as<int32_t>(), c->d_dense_nfrag.as<int32_t>(),
                                                                c->d_bc_textoff.as<long long>(), c->bc_table_cap, c->d_slot_to_dense.as<int32_t>(),
                                                                c->d_dense_first.as<unsigned long long>(), c->d_dense_textoff.as<long long>(),
                                                                c->d_dense_bckey.as<unsigned long long>(), reinterpret_cast<unsigned long long*>(&st[ST_TICKET]));
@@ -677,6 +682,8 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         size_t cap = (size_t)c->bc_table_cap;
         CRATAC_TRY(c->d_bc_keys.reserve(sizeof(BcSlot) * cap));
         CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
+        CRATAC_TRY(c->d_bc_nfrag.reserve(4 * cap));
+        CRATAC_CUDA(cudaMemsetAsync(c->d_bc_nfrag.p, 0, 4 * cap, c->stream));
         k_init_table<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_bc_keys.as<BcSlot>(), (int)cap);
         c->launches++;
         CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
@@ -687,7 +694,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
         a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
         a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
-        a.bc_tab = c->d_bc_keys.as<BcSlot>();
+        a.bc_tab = c->d_bc_keys.as<BcSlot>(); a.bc_nfrag = c->d_bc_nfrag.as<int32_t>();
         a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
         a.status = st;
         a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
@@ -758,6 +765,8 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
     const size_t cap = (size_t)c->bc_table_cap;
     CRATAC_TRY(c->d_bc_keys.reserve(sizeof(BcSlot) * cap));
     CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
+    CRATAC_TRY(c->d_bc_nfrag.reserve(4 * cap));
+    CRATAC_CUDA(cudaMemsetAsync(c->d_bc_nfrag.p, 0, 4 * cap, c->stream));
     CRATAC_TRY(c->d_stream_scalars.reserve(64));
     int64_t* line_base = c->d_stream_scalars.as<int64_t>();
     int64_t* chunk_total = line_base + 1;
@@ -772,7 +781,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
     a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
     a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
     a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
-    a.bc_tab = c->d_bc_keys.as<BcSlot>();
+    a.bc_tab = c->d_bc_keys.as<BcSlot>(); a.bc_nfrag = c->d_bc_nfrag.as<int32_t>();
     a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
     a.status = st;
     a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;

@@ -33,8 +33,7 @@ struct OverlapArgs {
     const int32_t* slot_to_dense;          // null: bc already dense
     const int64_t* peak_off;               // per contig
     const int32_t *pk_start, *pk_end, *pk_row;
-    int32_t* bc_hits;                      // per dense barcode (count pass)
-    const int64_t* seg_off;                // scatter pass
+    const int64_t* seg_off;                // per dense barcode: start of its segment (capacity 2 x its fragments)
     unsigned int* cursor;
     int32_t* hits;
     long long maxpos, maxneg;              // bounds of end - start over all fragments
@@ -61,13 +60,12 @@ __device__ __forceinline__ int find_peak(const OverlapArgs& a, int c, int pos) {
 constexpr int OV_TILE = 2048;
 constexpr int OV_WIN = 1024;
 
-template <bool SCATTER>
 __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
     __shared__ int s_start[OV_WIN], s_end[OV_WIN], s_row[OV_WIN];
     __shared__ long long s_plo;
     __shared__ int s_w;
     const int64_t n_tiles = (a.n + OV_TILE - 1) / OV_TILE;
-    long long my_hits = 0;                                  // count pass: fragment ends inside peaks (K of the size accounting)
+    long long my_hits = 0;                                  // fragment ends inside peaks (K of the size accounting)
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i0 = tile * OV_TILE;
         const int64_t i1 = i0 + OV_TILE < a.n ? i0 + OV_TILE : a.n;
@@ -121,27 +119,34 @@ __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
             const bool same = r0 >= 0 && r1 == r0;
             const int nrec = (r0 >= 0) + (r1 >= 0 && !same);
             if (nrec == 0 || b < 0) continue;
-            if (!SCATTER) {
-                atomicAdd(&a.bc_hits[b], nrec);
-                my_hits += (r0 >= 0) + (r1 >= 0);
-            } else {
-                unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nrec);
-                int64_t o = a.seg_off[b] + p;
-                if (r0 >= 0) a.hits[o++] = (r0 << 1) | (int)same;
-                if (r1 >= 0 && !same) a.hits[o] = r1 << 1;
-            }
+            my_hits += (r0 >= 0) + (r1 >= 0);
+            unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nrec);
+            int64_t o = a.seg_off[b] + p;
+            if (r0 >= 0) a.hits[o++] = (r0 << 1) | (int)same;
+            if (r1 >= 0 && !same) a.hits[o] = r1 << 1;
         }
     }
-    if (!SCATTER) {
 #pragma unroll
-        for (int d = 16; d; d >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
-        if ((threadIdx.x & 31) == 0 && my_hits) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_hits), (unsigned long long)my_hits);
+    for (int d = 16; d; d >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
+    if ((threadIdx.x & 31) == 0 && my_hits) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_hits), (unsigned long long)my_hits);
+}
+
+// segment capacities: a barcode with f fragments has at most 2 f hit records
+__global__ void k_seg_caps(const int32_t* __restrict__ nfrag, int64_t nb, int32_t* __restrict__ caps) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) caps[b] = 2 * nfrag[b];
+}
+// fragments per dense barcode for fragments that did not come through the decoder (cratac_set_fragments)
+__global__ void k_count_frags(const int32_t* __restrict__ bc, int64_t n, int64_t nb, int32_t* __restrict__ nfrag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = bc[i];
+        if (b >= 0 && b < nb) atomicAdd(&nfrag[b], 1);
     }
 }
 
 // ---- K7: per-barcode sort + run-length reduce -----------------------------------------------------
 // medium segments (SORT_WARP < records <= SORT_SMALL): bitonic sort in shared memory; one CTA per barcode
-__global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
+__global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off, const unsigned int* __restrict__ seg_len,
                                                                 int64_t n_bc, int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                 int32_t* __restrict__ nnz_col) {
     __shared__ int s[SORT_SMALL];
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __
     __shared__ int s_base;
     for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
         const int64_t o0 = seg_off[b];
-        const int64_t len64 = seg_off[b + 1] - o0;
+        const int64_t len64 = seg_len[b];
         if (len64 > SORT_SMALL || len64 <= SORT_WARP) continue;   // long path / warp path
         const int len = (int)len64;
         int m = 32;
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_small(const int32_t* __
 
 // very short segments (most barcodes of a library are background with a few dozen hits): one warp per barcode,
 // bitonic sort in the warp's own slice of shared memory, no block barriers
-__global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
+__global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off, const unsigned int* __restrict__ seg_len,
                                                                int64_t n_bc, int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                int32_t* __restrict__ nnz_col) {
     __shared__ int s_all[(SORT_THREADS / 32) * SORT_WARP];
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __r
     const int64_t n_warps = (int64_t)gridDim.x * (SORT_THREADS / 32);
     for (int64_t b = (int64_t)blockIdx.x * (SORT_THREADS / 32) + warp; b < n_bc; b += n_warps) {
         const int64_t o0 = seg_off[b];
-        const int64_t len64 = seg_off[b + 1] - o0;
+        const int64_t len64 = seg_len[b];
         if (len64 > SORT_WARP) continue;
         const int len = (int)len64;
         if (len == 0) { if (lane == 0) nnz_col[b] = 0; continue; }
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __r
 }
 
 // long segments: counting over peak-row ranges of COUNT_RANGE rows held in shared memory
-__global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off,
+__global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off, const unsigned int* __restrict__ seg_len,
                                                                  int64_t n_bc, const int64_t* __restrict__ status, int64_t n_peaks_host,
                                                                  int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                  int32_t* __restrict__ nnz_col) {
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* _
     for (int i = threadIdx.x; i < COUNT_RANGE + 2 * COUNT_RANGE / 32; i += COUNT_THREADS) cnt[i] = 0;
     for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
         const int64_t o0 = seg_off[b];
-        const int64_t len = seg_off[b + 1] - o0;
+        const int64_t len = seg_len[b];
         if (len <= SORT_SMALL) continue;
         if (len > 0x7fffffffLL) { if (threadIdx.x == 0) raise_error(const_cast<int64_t*>(status), CRATAC_ERR_CAPACITY, b); continue; }
         __syncthreads();
@@ -475,50 +480,53 @@ int peak_matrix_device(Ctx* c) {
     int64_t* st = c->d_status.as<int64_t>();
     const int64_t n = c->n_fragments, nb = c->n_barcodes;
     size_t nbb = (size_t)std::max<int64_t>(nb, 1);
-    CRATAC_TRY(c->d_bc_hits.reserve(4 * nbb));
+    CRATAC_TRY(c->d_bc_hits.reserve(4 * nbb));                  // segment capacities
     CRATAC_TRY(c->d_seg_off.reserve(8 * (nbb + 1)));
     CRATAC_TRY(c->d_cursor.reserve(4 * nbb));
     CRATAC_TRY(c->d_nnz_col.reserve(4 * nbb * 2));
     CRATAC_TRY(c->d_indptr.reserve(8 * (nbb + 1)));
-    CRATAC_CUDA(cudaMemsetAsync(c->d_bc_hits.p, 0, 4 * nbb, s));
     CRATAC_CUDA(cudaMemsetAsync(c->d_cursor.p, 0, 4 * nbb, s));
+    // Per-barcode segments are sized from the barcode's fragment count (at most 2 records per fragment; the decoder
+    // counts fragments per barcode as it inserts them), so the hits are placed in ONE pass over the fragments: no count pass
+    // and no host round trip for the number of hits.
+    if (!c->dense_nfrag_valid) {
+        CRATAC_TRY(c->d_dense_nfrag.reserve(4 * nbb));
+        CRATAC_CUDA(cudaMemsetAsync(c->d_dense_nfrag.p, 0, 4 * nbb, s));
+        if (n > 0) {
+            k_count_frags<<<NUM_SMS * 8, 256, 0, s>>>(c->d_bc.as<int32_t>(), n, nb, c->d_dense_nfrag.as<int32_t>());
+            c->launches++;
+        }
+        c->dense_nfrag_valid = true;
+    }
+    int32_t* caps = c->d_bc_hits.as<int32_t>();
+    if (nb > 0) {
+        k_seg_caps<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(c->d_dense_nfrag.as<int32_t>(), nb, caps);
+        c->launches++;
+    }
+    CRATAC_TRY(exclusive_scan_i32_to_i64(c, caps, c->d_seg_off.as<int64_t>(), nb, c->d_seg_off.as<int64_t>() + nb));
+    const size_t kk = (size_t)std::max<int64_t>(2 * n, 1);      // total capacity = 2 N
+    CRATAC_TRY(c->d_hits.reserve(4 * kk)); CRATAC_TRY(c->d_out_row.reserve(4 * kk)); CRATAC_TRY(c->d_out_cnt.reserve(4 * kk));
     OverlapArgs a;
     a.n = n; a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>(); a.bc = c->d_bc.as<int32_t>();
     a.slot_to_dense = c->bc_is_slot ? c->d_slot_to_dense.as<int32_t>() : nullptr;
     a.peak_off = c->d_peak_off.as<int64_t>();
     a.pk_start = c->d_peak_start.as<int32_t>(); a.pk_end = c->d_peak_end.as<int32_t>(); a.pk_row = c->d_peak_row.as<int32_t>();
     a.maxpos = c->h_status[ST_MAX_POS_LEN]; a.maxneg = c->h_status[ST_MAX_NEG_LEN];
-    a.bc_hits = c->d_bc_hits.as<int32_t>(); a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = nullptr;
+    a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = c->d_hits.as<int32_t>();
     a.n_hits = &st[ST_N_HITS];
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_HITS], 0, sizeof(int64_t), s));
     int grid = (int)std::min<int64_t>((n + OV_TILE - 1) / OV_TILE, (int64_t)NUM_SMS * 8);
     if (grid < 1) grid = 1;
-    c->stage_begin(SG_OVERLAP_COUNT);
-    k_overlap<false><<<grid, MX_THREADS, 0, s>>>(a);
-    c->stage_end(SG_OVERLAP_COUNT);
-    c->launches++;
-    CRATAC_CUDA(cudaGetLastError());
-    CRATAC_TRY(exclusive_scan_i32_to_i64(c, a.bc_hits, c->d_seg_off.as<int64_t>(), nb, c->d_seg_off.as<int64_t>() + nb));
-    // matrix column order: host work (CPython-2.7 set emulation over the barcode hashes) overlaps the kernels
-    // queued so far (pileup, fit, peaks, overlap count)
-    c->host_mark("matrix_launch");
-    if (!c->global_cols) CRATAC_TRY(build_barcodes(c));
-    c->host_mark("build_barcodes");
-    // K (total hits) sizes the hit buffers: one host round trip here (8 bytes)
-    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_NNZ], c->d_seg_off.as<int64_t>() + nb, 8, cudaMemcpyDeviceToHost, s));   // records (slot reused below)
-    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], &st[ST_N_HITS], 8, cudaMemcpyDeviceToHost, s));
-    CRATAC_CUDA(cudaStreamSynchronize(s));
-    c->host_mark("matrix_wait_hits");
-    const int64_t K = c->h_status[ST_NNZ];                  // hit records: one per (fragment, peak)
-    c->n_hits = c->h_status[ST_N_HITS];                     // fragment ends inside peaks
-    size_t kk = (size_t)std::max<int64_t>(K, 1);
-    CRATAC_TRY(c->d_hits.reserve(4 * kk)); CRATAC_TRY(c->d_out_row.reserve(4 * kk)); CRATAC_TRY(c->d_out_cnt.reserve(4 * kk));
-    a.hits = c->d_hits.as<int32_t>();
     c->stage_begin(SG_OVERLAP_SCATTER);
-    k_overlap<true><<<grid, MX_THREADS, 0, s>>>(a);
+    k_overlap<<<grid, MX_THREADS, 0, s>>>(a);
     c->stage_end(SG_OVERLAP_SCATTER);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
+    // matrix column order: host work (CPython-2.7 set emulation over the barcode hashes) overlaps the kernels
+    // queued so far (pileup, fit, peaks, overlap)
+    c->host_mark("matrix_launch");
+    if (!c->global_cols) CRATAC_TRY(build_barcodes(c));
+    c->host_mark("build_barcodes");
     int32_t* nnz_col = c->d_nnz_col.as<int32_t>();
     if (nb > 0) {
         static bool configured = false;
@@ -528,12 +536,12 @@ int peak_matrix_device(Ctx* c) {
         }
         int g1 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 32);
         c->stage_begin(SG_REDUCE_SMALL);
-        k_reduce_warp<<<NUM_SMS * 8, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
-        k_reduce_small<<<g1, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
+        k_reduce_warp<<<NUM_SMS * 8, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, a.cursor, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
+        k_reduce_small<<<g1, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, a.cursor, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_SMALL);
         c->stage_begin(SG_REDUCE_LARGE);
         int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
-        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 4, s>>>(a.hits, a.seg_off, nb, st,
+        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 4, s>>>(a.hits, a.seg_off, a.cursor, nb, st,
                                                                  c->row_range > 0 ? c->row_range : (c->peaks_on_device_count ? -1 : c->n_peaks),
                                                                  c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_LARGE);
@@ -554,8 +562,10 @@ int peak_matrix_device(Ctx* c) {
     }
     CRATAC_TRY(exclusive_scan_i32_to_i64(c, nnz_ordered, c->d_indptr.as<int64_t>(), n_cols, c->d_indptr.as<int64_t>() + n_cols));
     CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_NNZ], c->d_indptr.as<int64_t>() + n_cols, 8, cudaMemcpyDeviceToHost, s));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_N_HITS], &st[ST_N_HITS], 8, cudaMemcpyDeviceToHost, s));
     CRATAC_CUDA(cudaStreamSynchronize(s));
     c->nnz = c->h_status[ST_NNZ];
+    c->n_hits = c->h_status[ST_N_HITS];                     // fragment ends inside peaks
     size_t zz = (size_t)std::max<int64_t>(c->nnz, 1);
     CRATAC_TRY(c->d_indices.reserve(8 * zz)); CRATAC_TRY(c->d_data.reserve(4 * zz));
     if (n_cols > 0) {
