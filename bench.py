@@ -474,7 +474,7 @@ def main():
         # DRAM bytes of the dominant group's kernels from the committed `ncu --set full` capture of this same workload
         import csv
         name_of = {"decode": ("k_count_newlines", "k_parse_tiles"), "pileup_window_hist": ("k_pileup<0>",), "pileup_call_peaks": ("k_pileup<1>",),
-                   "overlap": ("k_overlap<0>", "k_overlap<1>"), "sort_reduce": ("k_reduce_warp", "k_reduce_small", "k_reduce_large"),
+                   "overlap": ("k_overlap(",), "sort_reduce": ("k_reduce_warp", "k_reduce_small", "k_reduce_large"),
                    "csc_build": ("k_csc_copy",)}[dom]
         rows = list(csv.reader(open(ncu_csv)))
         hdr = rows[0]
