@@ -375,10 +375,13 @@ def main():
     ev0.record(stream)
     wall0 = time.time()
     loop_ms = []
+    slow_trace = None
     for _ in range(args.steps):
         t_a = time.time()
         res = step_device()
         t_b = time.time()
+        if world > 1 and (slow_trace is None or t_b - t_a > slow_trace[0]):
+            slow_trace = (t_b - t_a, [(k, round(v, 2)) for k, v in trace])
         for k, v in ctx.stage_times().items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
         loop_ms.append((round(1e3 * (t_b - t_a), 2), round(1e3 * (time.time() - t_b), 2)))
@@ -395,7 +398,8 @@ def main():
     traces_by_rank = None
     if world > 1:
         traces_by_rank = [None] * world
-        dist.all_gather_object(traces_by_rank, {"rank": rank, "dev_ms_per_step": ev0.elapsed_time(ev1) / args.steps, "phases": [(k, round(v, 2)) for k, v in trace], "loop_ms": loop_ms})
+        dist.all_gather_object(traces_by_rank, {"rank": rank, "dev_ms_per_step": ev0.elapsed_time(ev1) / args.steps, "phases": [(k, round(v, 2)) for k, v in trace], "loop_ms": loop_ms,
+                                                "slowest_step_phases": slow_trace[1] if slow_trace else None})
     total_frags = args.steps * args.fragments
     value = total_frags / (dev_ms / 1000.0)
 

@@ -106,7 +106,8 @@ def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set", trace=None)
     # 1. histogram: queued, all-reduced in place (largest count and bins), fit queued behind it -- no host wait
     hist, mx = shard.window_histogram()                      # int64 tensors: bins [cap], largest count [1]
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    gmax = int(mx.item())                                    # (waits for the histogram pass; only the used bins are exchanged:
+    dist.all_reduce(hist[: gmax + 1], op=dist.ReduceOp.SUM)  #  an 8 MB all-reduce of the whole table stalled NCCL for 50-150 ms now and then)
     shard.fit_launch(odds_ratio)
     mark("hist_fit_launch")
     # 2. barcode dictionary, exchanged while the fit runs (side stream on a GPU: the fit occupies one SM)
