@@ -34,11 +34,6 @@ __global__ void k_init_table(BcSlot* __restrict__ tab, int cap) {
     if (s < cap) { BcSlot e; e.key = BC_EMPTY; e.first = 0x7F7F7F7F7F7F7F7FULL; tab[s] = e; }
 }
 
-__host__ __device__ __forceinline__ unsigned long long fnv1a(const unsigned char* s, int n) {
-    unsigned long long h = 1469598103934665603ULL;
-    for (int i = 0; i < n; i++) { h ^= s[i]; h *= 1099511628211ULL; }
-    return h;
-}
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
@@ -134,49 +129,6 @@ struct DecodeArgs {
     const int64_t* line_base;
     int64_t line_cap;                 // capacity of the output arrays when the total is not known in advance (0: exact)
 };
-
-__device__ __forceinline__ bool parse_uint(const unsigned char* s, int b, int e, int32_t* out) {
-    if (b >= e || e - b > 10) return false;
-    unsigned long long v = 0;
-    for (int i = b; i < e; i++) {
-        unsigned d = (unsigned)s[i] - (unsigned)'0';
-        if (d > 9u) return false;
-        v = v * 10 + d;
-    }
-    if (v > 2147483647ULL) return false;
-    *out = (int32_t)v;
-    return true;
-}
-
-__device__ __forceinline__ unsigned long long barcode_key(const unsigned char* s, int b, int e) {
-    // fast path: [ACGT]{16}-[0-9]{1,9}
-    int n = e - b;
-    if (n >= 18 && n <= 26 && s[b + 16] == '-') {
-        unsigned seq = 0;
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            unsigned ch = s[b + i];
-            // A=0x41 C=0x43 G=0x47 T=0x54 -> (ch>>1)&3 = 0,1,3,2 ; validate exactly
-            unsigned code = (ch >> 1) & 3u;
-            ok &= (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
-            seq = (seq << 2) | code;
-        }
-        unsigned long long grp = 0;
-        for (int i = b + 17; i < e; i++) {
-            unsigned d = (unsigned)s[i] - (unsigned)'0';
-            ok &= (d <= 9u);
-            grp = grp * 10 + d;
-        }
-        // a leading zero in the group ("-01") would alias "-1": send it to the generic path
-        ok &= !(n > 18 && s[b + 17] == '0');
-        if (ok) return ((unsigned long long)grp << 32) | seq;
-    }
-    unsigned long long h = mix64(fnv1a(s + b, n) ^ ((unsigned long long)n << 56));
-    h = (h >> 1) | 0x8000000000000000ULL;
-    if (h == BC_EMPTY) h ^= 2ULL;
-    return h;
-}
 
 __device__ __forceinline__ unsigned byte_at(const uint32_t* words, int p) { return (words[p >> 2] >> ((p & 3) * 8)) & 0xFFu; }
 
