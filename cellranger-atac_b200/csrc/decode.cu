@@ -708,7 +708,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
     CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
     CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
     const size_t held = std::min({c->d_chrom.cap, c->d_start.cap, c->d_end.cap, c->d_bc.cap, c->d_dup.cap}) / 4;
-    const int64_t line_cap = std::max<int64_t>(nbytes / 16 + 4096, (int64_t)held);
+    const int64_t line_cap = std::max<int64_t>(nbytes / 24 + 4096, (int64_t)held);   // a fragments.tsv line is rarely under 24 bytes
     {
         const size_t nn = (size_t)line_cap;
         CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));

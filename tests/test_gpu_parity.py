@@ -499,7 +499,7 @@ def test_streamed_host_decode_equals_plain_decode():
 
 
 def test_streamed_host_decode_falls_back_when_the_estimate_is_too_small():
-    """Lines of ~12 bytes: more lines than the nbytes / 16 estimate -> the exact two-pass path takes over."""
+    """Lines of ~12 bytes: more lines than the nbytes / 24 estimate -> the exact two-pass path takes over."""
     contigs = [("c", 100000)]
     lines = ["c\t%d\t%d\tB%d\t1" % (i // 3000, i // 3000 + 1, i % 7) for i in range(1, 90000)]
     text = ("\n".join(lines) + "\n").encode()
@@ -509,5 +509,5 @@ def test_streamed_host_decode_falls_back_when_the_estimate_is_too_small():
     assert n == len(lines) and nb == 7
     fr = ctx.get_fragments()
     assert fr["start"].tolist() == [i // 3000 for i in range(1, 90000)] and fr["end"].tolist() == [i // 3000 + 1 for i in range(1, 90000)]
-    assert len(text) // 16 + 4096 < len(lines)                   # i.e. the streamed attempt did run out of room
+    assert len(text) // 24 + 4096 < len(lines)                   # i.e. the streamed attempt did run out of room
     ctx.close()
