@@ -18,7 +18,13 @@ Python-2 comparison semantics are supplied by value wrappers, not code edits:
   * ``None >= min_counts``   -> False   (count_cut_sites/__init__.py:42,47)
   * ``"12" < threshold``     -> False   (lib/python/utils.py:112, str vs float)
 
-Usage: python tests/golden/make_golden.py            (writes next to this file)
+filter.json (FILTER_PEAK_MATRIX) is produced the same way: the reference's `prune`
+(filter_peak_matrix/__init__.py:46-70) and its `CountMatrix` class (cellranger/matrix.py:
+__init__, bc_to_int, select_barcodes, filter_barcodes) are exec'd unmodified on scipy
+matrices; only cellranger/bisect.pyx (Cython, 12 lines) is restated, and numpy's
+``np.array(list, copy=False)`` is given its pre-2.0 meaning.
+
+Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter ...]   (writes next to this file)
 """
 import ast
 import io
