@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
     int* hist_s = smem + PU_N + PU_PAD;   // PU_HB (MODE_HIST)
     __shared__ int warp_tot[PU_THREADS / 32];
     __shared__ int s_first_nz, s_last_nz, s_bound;
+    __shared__ unsigned long long s_firstp, s_lastp;   // MODE_HIST: (absolute position << 32 | W) of the tile's first / last non-zero base
     __shared__ long long s_base_s, s_base_e;
     __shared__ int s_cur_s, s_cur_e;
 
@@ -184,16 +185,30 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
     __shared__ long long s_next[2];   // double-buffered: one barrier per tile hand-over
     int par = 0;
     if (tid == 0) s_next[0] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
+    long long prev_tile = -1;         // MODE_HIST: tile whose non-zero summary is still in s_firstp / s_lastp
+    auto flush_summary = [&]() {      // thread 0, right after a barrier that follows the tile's window walk
+        int4 sm;
+        sm.x = sm.z = -1; sm.y = sm.w = 0;
+        if (s_lastp != 0ULL) {
+            sm.x = (int)(s_firstp >> 32); sm.y = (int)(s_firstp & 0xFFFFFFFFULL);
+            sm.z = (int)(s_lastp >> 32); sm.w = (int)(s_lastp & 0xFFFFFFFFULL);
+        }
+        a.tile_summary[prev_tile] = sm;
+    };
     while (true) {
         __syncthreads();
         const long long tile = s_next[par];
+        if (MODE == MODE_HIST && a.tile_bound && tid == 0 && prev_tile >= 0) flush_summary();
         if (tile >= a.n_tiles) break;
         if (tid == 0) {
             s_next[par ^ 1] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(&a.status[ST_TICKET]), 1ULL);
             s_first_nz = 0x7fffffff;
             s_last_nz = -1;
             s_bound = 0;
+            s_firstp = 0xFFFFFFFFFFFFFFFFULL;
+            s_lastp = 0ULL;
         }
+        prev_tile = tile;
         par ^= 1;
         const TileDesc td = a.desc[tile];
         const int c = td.contig;
@@ -274,39 +289,16 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
             // collect garbage (it is never read); the checked path handles the few tiles over the bound.
             const int hi = min(k0 + PU_OWN_CHUNK + 401, PU_N - 1);
             const int bound = k0 < own ? sc[hi] - sc[k0] : 0;
-            if (a.tile_bound) {
-                // for the peak pass: the tile's bound and its first / last base with a non-zero window count
-                // (reduced in the warp first: one shared-memory atomic per warp, not per thread)
-                int f = 0x7fffffff, l = -1;
-                if (k0 < k1) {
-                    int ff = k0, ll = k1 - 1;
-                    while (ff < k1 && sc[ff + 402] - sc[ff + 1] == 0) ff++;
-                    if (ff < k1) {
-                        while (sc[ll + 402] - sc[ll + 1] == 0) ll--;
-                        f = ff; l = ll;
-                    }
-                }
+            if (a.tile_bound) {   // for the peak pass: an upper bound of the tile's window counts
                 const int wb = __reduce_max_sync(0xffffffffu, bound);
-                const int wf = __reduce_min_sync(0xffffffffu, f), wl = __reduce_max_sync(0xffffffffu, l);
-                if ((tid & 31) == 0) {
-                    if (wb > 0) atomicMax(&s_bound, wb);
-                    if (wl >= 0) { atomicMin(&s_first_nz, wf); atomicMax(&s_last_nz, wl); }
-                }
+                if ((tid & 31) == 0 && wb > 0) atomicMax(&s_bound, wb);
             }
             const bool fast = !__syncthreads_or(bound >= PU_HB);
-            if (a.tile_bound && tid == 0) {
-                int4 sm;
-                sm.x = sm.z = -1; sm.y = sm.w = 0;
-                if (s_last_nz >= 0) {
-                    const int f = s_first_nz, l = s_last_nz;
-                    sm.x = (int)(ta + f); sm.y = sc[f + 402] - sc[f + 1];
-                    sm.z = (int)(ta + l); sm.w = sc[l + 402] - sc[l + 1];
-                }
-                a.tile_summary[tile] = sm;
-                a.tile_bound[tile] = s_bound;
-            }
+            if (a.tile_bound && tid == 0) a.tile_bound[tile] = s_bound;
+            int w_first = 0;          // W of my first base (captured by the walkers below at no cost)
             if (fast) {
-                auto body = [&](int, int w) {
+                auto body = [&](int k, int w) {
+                    if (k == k0) w_first = w;
                     const bool changed = w != cur;
                     if (changed) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
                     runlen = changed ? 1 : runlen + 1;
@@ -316,7 +308,8 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
                 else for_each_window(sc, k0, k1, body);
                 asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
             } else {
-                for_each_window(sc, k0, k1, [&](int, int w) {
+                for_each_window(sc, k0, k1, [&](int k, int w) {
+                    if (k == k0) w_first = w;
                     const bool changed = w != cur;
                     if (changed && cur > 0) {
                         if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
@@ -329,6 +322,37 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
                 if (cur > 0) {
                     if (cur < PU_HB) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
                     else flush_slow(cur, runlen);
+                }
+            }
+            if (a.tile_bound) {
+                // first / last base of the tile with a non-zero window count and their counts, for the peak pass's
+                // zero-gap logic.  Almost always my chunk's own ends, whose counts the walk has just produced (w_first,
+                // cur); thread 0 writes the tile's summary after the next barrier (loop top).
+                int f = 0x7fffffff, l = -1, wf = 0, wl = 0;
+                if (k0 < k1) {
+                    if (w_first != 0) { f = k0; wf = w_first; }
+                    else {
+                        int ff = k0;
+                        while (ff < k1 && sc[ff + 402] - sc[ff + 1] == 0) ff++;
+                        if (ff < k1) { f = ff; wf = sc[ff + 402] - sc[ff + 1]; }
+                    }
+                    if (f != 0x7fffffff) {
+                        if (cur != 0) { l = k1 - 1; wl = cur; }
+                        else {
+                            int ll = k1 - 1;
+                            while (sc[ll + 402] - sc[ll + 1] == 0) ll--;
+                            l = ll; wl = sc[ll + 402] - sc[ll + 1];
+                        }
+                    }
+                }
+                const int mf = __reduce_min_sync(0xffffffffu, f), ml = __reduce_max_sync(0xffffffffu, l);
+                if (ml >= 0) {
+                    const int src_f = __ffs(__ballot_sync(0xffffffffu, f == mf)) - 1, src_l = __ffs(__ballot_sync(0xffffffffu, l == ml)) - 1;
+                    const int vf = __shfl_sync(0xffffffffu, wf, src_f), vl = __shfl_sync(0xffffffffu, wl, src_l);
+                    if ((tid & 31) == 0) {
+                        atomicMin(&s_firstp, ((unsigned long long)(unsigned)(ta + mf) << 32) | (unsigned)vf);
+                        atomicMax(&s_lastp, ((unsigned long long)(unsigned)(ta + ml) << 32) | (unsigned)vl);
+                    }
                 }
             }
         } else if (MODE == MODE_DUMP) {
