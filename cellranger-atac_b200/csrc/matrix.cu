@@ -53,6 +53,27 @@ __device__ __forceinline__ int find_peak(const OverlapArgs& a, int c, int pos) {
     return -1;
 }
 
+// first index in [lo, hi) whose value exceeds key (hi if none), searched by a whole warp: 32 split points per round
+__device__ __forceinline__ int64_t warp_upper_bound(const int32_t* __restrict__ arr, int64_t lo, int64_t hi, long long key) {
+    const int lane = threadIdx.x & 31;
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo) / 33 + 1;
+        const int64_t p = lo + step * (lane + 1) - 1;                     // probes ascend with the lane
+        const bool gt = p < hi ? key < (long long)__ldg(&arr[p]) : true;
+        const unsigned m = __ballot_sync(0xffffffffu, gt);
+        if (m == 0u) { lo = lo + step * 32; continue; }                  // every probe <= key: the answer lies beyond the last one
+        const int j = __ffs(m) - 1;                                      // first probe with a larger value
+        const int64_t pj = lo + step * (j + 1) - 1;
+        const int64_t nlo = j > 0 ? lo + step * j : lo;                  // one past the previous probe
+        hi = pj < hi ? pj : hi;                                          // arr[pj] > key (or pj is past the end): answer <= pj
+        lo = nlo;
+    }
+    const int64_t p = lo + lane;
+    const bool gt = p < hi ? key < (long long)__ldg(&arr[p]) : true;
+    const unsigned m = __ballot_sync(0xffffffffu, gt);
+    return m ? lo + (__ffs(m) - 1) : hi;
+}
+
 // Fragments are start-sorted, so the OV_TILE fragments a CTA takes at a time touch a handful of consecutive
 // peaks: the CTA finds that window with two bisects, stages it in shared memory and every fragment end is
 // then located there.  Tiles that straddle a contig boundary or a very dense peak region fall back to the
@@ -70,21 +91,21 @@ __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
         const int64_t i0 = tile * OV_TILE;
         const int64_t i1 = i0 + OV_TILE < a.n ? i0 + OV_TILE : a.n;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            // warp 0 finds the tile's peak window with two 33-ary searches (every lane probes one split point per
+            // round: 3 rounds of dependent loads for a contig's few thousand peaks instead of 13 for a bisect)
             int w = -1;
             const int c0 = a.chrom[i0];
             if (c0 == a.chrom[i1 - 1]) {
                 const long long lo_pos = (long long)a.start[i0] - a.maxneg;
                 const long long hi_pos = (long long)a.start[i1 - 1] + a.maxpos;
                 const int64_t base = a.peak_off[c0], top = a.peak_off[c0 + 1];
-                int64_t lo = base, hi = top;             // first peak start > lo_pos
-                while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (lo_pos < (long long)a.pk_start[mid]) hi = mid; else lo = mid + 1; }
-                int64_t p_lo = lo > base ? lo - 1 : base;
-                lo = p_lo; hi = top;                      // first peak start > hi_pos
-                while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (hi_pos < (long long)a.pk_start[mid]) hi = mid; else lo = mid + 1; }
-                if (lo - p_lo <= OV_WIN) { w = (int)(lo - p_lo); s_plo = p_lo; }
+                const int64_t lo = warp_upper_bound(a.pk_start, base, top, lo_pos);      // first peak start > lo_pos
+                const int64_t p_lo = lo > base ? lo - 1 : base;
+                const int64_t hi = warp_upper_bound(a.pk_start, p_lo, top, hi_pos);      // first peak start > hi_pos
+                if (hi - p_lo <= OV_WIN) { w = (int)(hi - p_lo); if (threadIdx.x == 0) s_plo = p_lo; }
             }
-            s_w = w;
+            if (threadIdx.x == 0) s_w = w;
         }
         __syncthreads();
         const int w = s_w;
