@@ -390,6 +390,19 @@ def test_whole_path_fitted_threshold():
     assert res.has_params == 1 and res.n_peaks > 100 and res.em_iterations > 0
 
 
+MM10_SCALED = [(name, length // 400) for name, length in synth.MM10]   # BASELINE.json configs[4] shape: 21 contigs, chrY not primary
+
+
+@pytest.mark.parametrize("n_peaks,cells", [(300, 4), (300, 150), (1500, 4), (1500, 150)])
+def test_whole_path_mm10_sweep(n_peaks, cells):
+    """The mm10 sweep of BASELINE.json (peak density x barcode count) at 1/400 of the genome: threshold, peaks,
+    column order and CSC against the oracle at the four corners."""
+    primary = [c[0] for c in MM10_SCALED if c[0] != "chrY"]
+    frags = synth.generate(MM10_SCALED, 150000, cells, n_peaks, seed=300 + n_peaks + cells, background_factor=6)
+    res = _run_and_compare(MM10_SCALED, primary, synth.to_text(frags))
+    assert res.n_peaks > 0 and res.nnz > 0
+
+
 # ----------------------------------------------------------------------------- multi-GPU path
 def _run_multi_check(nproc):
     import subprocess
