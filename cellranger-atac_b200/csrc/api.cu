@@ -185,6 +185,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "defer_sync")) { c->defer_sync = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "stream_decode")) { c->stream_decode = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
+    if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
         c->profile = value != 0;

@@ -116,11 +116,15 @@ struct Ctx {
     int32_t* h_c2d_pin = nullptr;          // pinned: column -> dense id
     size_t h_bc_cap = 0;
     cudaEvent_t bc_event = nullptr;
+    const long long* d_hash_first = nullptr;   // device copies of the two mirrors above (inside d_bc_bitmap)
+    const int32_t* d_order_first = nullptr;
+    int64_t py2_device_min = 300000;       // option "py2_device_min": from this many barcodes on, the column order is worked out on the device
     std::vector<int32_t> h_c2d;
     bool bc_strings_ready = false;
     std::vector<std::string> barcodes;     // matrix column order
     int bc_order = CRATAC_BC_ORDER_PY2SET;
     bool bc_ready = false;
+    DevBuf d_py2_rank;                     // first-appearance rank of every matrix column (device column order)
     DevBuf d_bc_nfrag, d_dense_nfrag;      // fragments per table slot / per dense barcode (int32)
     bool dense_nfrag_valid = false;        // d_dense_nfrag matches the current fragments (decode fills it; set_fragments counts on demand)
     bool bc_is_slot = false;               // d_bc holds hash-table slots (decode) vs dense ids (set_fragments)

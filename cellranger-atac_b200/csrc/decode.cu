@@ -503,6 +503,12 @@ __global__ void k_rank_first(const unsigned long long* __restrict__ dense_first,
     order_f[r] = (int32_t)d;           // the r-th barcode to appear in the file is dense id d
     hash_f[r] = dense_hash[d];
 }
+// col_to_dense[j] = dense id of the barcode whose first-appearance rank is rank_of_col[j]
+__global__ void k_compose_order(const int32_t* __restrict__ rank_of_col, const int32_t* __restrict__ order_first, int64_t n, int32_t* __restrict__ col_to_dense) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) col_to_dense[j] = order_first[rank_of_col[j]];
+}
+
 __global__ void k_invert_order(const int32_t* __restrict__ col_to_dense, int64_t n, int32_t* __restrict__ dense_to_col) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) dense_to_col[col_to_dense[j]] = (int32_t)j;
@@ -553,6 +559,8 @@ static int barcode_prepare_device(Ctx* c) {
     int64_t* word_prefix = reinterpret_cast<int64_t*>(word_cnt + n_words);   // 2 * n_words int32 => 8-byte aligned
     long long* hash_f = reinterpret_cast<long long*>(word_prefix + n_words);
     int32_t* order_f = reinterpret_cast<int32_t*>(hash_f + nn);
+    c->d_hash_first = hash_f;
+    c->d_order_first = order_f;
     cudaStream_t s = c->stream;
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_TICKET], 0, sizeof(int64_t), s));
     c->stage_begin(SG_BARCODE_TABLE);
@@ -908,6 +916,8 @@ static int fetch_barcode_strings(Ctx* c, std::vector<std::string>& names) {
 
 // host half: matrix column order.  Only the hashes (PY2SET) or nothing (FIRST_SEEN) cross to the host; the
 // caller queues GPU work first so that this overlaps it.
+int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_order_out);   // py2order.cu
+
 int build_barcodes(Ctx* c) {
     if (c->bc_ready) return CRATAC_OK;
     const int64_t nb = c->n_barcodes;
@@ -921,6 +931,21 @@ int build_barcodes(Ctx* c) {
         CRATAC_TRY(fetch_barcode_strings(c, names));
         for (int64_t j = 0; j < nb; j++) c2d[j] = (int32_t)j;
         std::sort(c2d, c2d + nb, [&](int32_t x, int32_t y) { return names[x] < names[y]; });
+    } else if (nb >= c->py2_device_min && nb > 0 && c->d_hash_first) {
+        // many barcodes: the sequential host simulation (~50 ns per key) would outlast the GPU work it hides behind,
+        // so the set is rebuilt on the device (py2order.cu), behind whatever the stream already holds
+        CRATAC_TRY(c->d_py2_rank.reserve(4 * (size_t)nb));
+        CRATAC_TRY(py2_set_order_device(c, nb, reinterpret_cast<const int64_t*>(c->d_hash_first), c->d_py2_rank.as<int32_t>()));
+        const unsigned g = (unsigned)((nb + 255) / 256);
+        k_compose_order<<<g, 256, 0, s>>>(c->d_py2_rank.as<int32_t>(), c->d_order_first, nb, c->d_col_to_dense.as<int32_t>());
+        k_invert_order<<<g, 256, 0, s>>>(c->d_col_to_dense.as<int32_t>(), nb, c->d_dense_to_col.as<int32_t>());
+        c->launches += 2;
+        CRATAC_CUDA(cudaGetLastError());
+        CRATAC_CUDA(cudaMemcpyAsync(c2d, c->d_col_to_dense.p, 4 * (size_t)nb, cudaMemcpyDeviceToHost, s));
+        CRATAC_CUDA(cudaStreamSynchronize(s));
+        c->h_c2d.assign(c2d, c2d + nb);
+        c->bc_ready = true;
+        return CRATAC_OK;
     } else {
         std::vector<int32_t> order;
         py2_set_order_hashes(c->h_bc_hash, nb, order);

@@ -61,7 +61,8 @@ void cratac_destroy(cratac_ctx* ctx);
  * point, 1 accelerated, 2 on-chip kernel first), "profile" (per-kernel CUDA events), "defer_sync" (see
  * cratac_fit_threshold_result), "stream_decode" (0 off / 1 host texts of 64 MiB and more / 2 always: the host text is
  * copied in chunks and each chunk is decoded while the next one is on the PCIe bus), "stream_chunk_tiles" (16 KiB
- * text tiles per chunk, 0 = 128 MiB worth) */
+ * text tiles per chunk, 0 = 128 MiB worth), "py2_device_min" (from this many distinct barcodes on the PY2SET column
+ * order is worked out on the device instead of by the host simulation; default 300000) */
 int cratac_set_option(cratac_ctx* ctx, const char* key, int64_t value);
 /* kernels launched by this context since creation / last reset */
 int64_t cratac_launch_count(cratac_ctx* ctx, int reset);

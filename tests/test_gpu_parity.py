@@ -294,6 +294,28 @@ def test_decode_parity_and_barcode_order():
     ctx.close()
 
 
+def test_column_order_worked_out_on_the_device_for_many_barcodes():
+    """From `py2_device_min` barcodes on, the list(set(...)) column order comes from the device rebuild of the set
+    (py2order.cu) instead of the host simulation: same columns, same per-fragment column ids, same matrix."""
+    contigs = [("chr1", 400000), ("chr2", 250000)]
+    frags = synth.generate(contigs, 90000, 2500, 60, seed=41, background_factor=8)   # ~20k distinct barcodes
+    text = synth.to_text(frags)
+    results = []
+    for device_min in (1 << 40, 0):
+        ctx = _ffi.Context(contigs)
+        ctx.set_option("py2_device_min", device_min)
+        res = ctx.run(text=text, odds_ratio=0.2)
+        results.append((ctx.get_barcodes(), ctx.get_fragments()["bc"], ctx.get_matrix(res.nnz), res.n_barcodes))
+        ctx.close()
+    (b0, f0, m0, n0), (b1, f1, m1, n1) = results
+    assert n0 == n1 and n0 > 10000
+    assert b0 == b1 and np.array_equal(f0, f1)
+    for x, y in zip(m0, m1):
+        assert np.array_equal(x, y)
+    o = util.oracle_decode(text, [c[0] for c in contigs])
+    assert b1 == util.oracle_columns(o["first_seen"])
+
+
 def test_decode_edge_cases():
     contigs = [("chr1", 100000), ("chr2_random", 5000), ("X", 777)]
     lines = [

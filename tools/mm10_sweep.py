@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--peaks", default="20000,100000,300000")
     ap.add_argument("--cells", default="1000,10000,100000")
+    ap.add_argument("--py2-device-min", default="", help="comma list of values of the library option of that name: every point is timed "
+                                                         "once per value on the same text (empty: library default only)")
     args = ap.parse_args()
 
     import torch
@@ -48,28 +50,36 @@ def main():
                 ctx.set_option("profile", 1)
                 text, nbytes = bench.make_workload(torch, ctx, contigs, args.fragments, cells, n_peaks, 5, device)
                 stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
-                for _ in range(args.warmup):
-                    res = ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
-                torch.cuda.synchronize()
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                stage_ms = {}
-                ev0.record(stream)
-                for _ in range(args.steps):
-                    res = ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
-                    for k, v in ctx.stage_times().items():
-                        stage_ms[k] = stage_ms.get(k, 0.0) + v
-                ev1.record(stream)
-                torch.cuda.synchronize()
-                ms = ev0.elapsed_time(ev1) / args.steps
-                alg = bench.algorithmic_bytes(nbytes, res.n_fragments, G, res.n_peaks, int(res.n_hits), res.nnz, res.n_barcodes)
-                groups = {}
-                for name, members in bench.KERNEL_GROUPS.items():
-                    gms = sum(stage_ms.get(m, 0.0) for m in members) / args.steps
-                    if gms > 0:
-                        groups[name] = {"ms": round(gms, 3), "frac": round(alg[name] / 1e9 / (gms / 1e3) / peak_gbs, 3)}
-                point.update({"ms_per_step": round(ms, 3), "fragments_per_s": args.fragments / (ms / 1e3), "threshold": int(res.threshold),
-                              "n_peaks": int(res.n_peaks), "n_barcodes": int(res.n_barcodes), "nnz": int(res.nnz),
-                              "em_fit_ms": round(stage_ms.get("em_fit", 0.0) / args.steps, 3), "kernels": groups})
+                settings = [int(x) for x in args.py2_device_min.split(",") if x] or [None]
+                for si, setting in enumerate(settings):
+                    if setting is not None:
+                        ctx.set_option("py2_device_min", setting)
+                        point["py2_device_min"] = setting
+                    for _ in range(args.warmup):
+                        res = ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
+                    torch.cuda.synchronize()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    stage_ms = {}
+                    ev0.record(stream)
+                    for _ in range(args.steps):
+                        res = ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
+                        for k, v in ctx.stage_times().items():
+                            stage_ms[k] = stage_ms.get(k, 0.0) + v
+                    ev1.record(stream)
+                    torch.cuda.synchronize()
+                    ms = ev0.elapsed_time(ev1) / args.steps
+                    alg = bench.algorithmic_bytes(nbytes, res.n_fragments, G, res.n_peaks, int(res.n_hits), res.nnz, res.n_barcodes)
+                    groups = {}
+                    for name, members in bench.KERNEL_GROUPS.items():
+                        gms = sum(stage_ms.get(m, 0.0) for m in members) / args.steps
+                        if gms > 0:
+                            groups[name] = {"ms": round(gms, 3), "frac": round(alg[name] / 1e9 / (gms / 1e3) / peak_gbs, 3)}
+                    point.update({"ms_per_step": round(ms, 3), "fragments_per_s": args.fragments / (ms / 1e3), "threshold": int(res.threshold),
+                                  "n_peaks": int(res.n_peaks), "n_barcodes": int(res.n_barcodes), "nnz": int(res.nnz),
+                                  "em_fit_ms": round(stage_ms.get("em_fit", 0.0) / args.steps, 3), "kernels": groups})
+                    if si + 1 < len(settings):
+                        print(json.dumps(point))
+                        sys.stdout.flush()
                 del text
                 ctx.close()
                 torch.cuda.empty_cache()
