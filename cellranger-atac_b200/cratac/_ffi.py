@@ -92,6 +92,7 @@ SIGNATURES = {
     "cratac_py2_set_order_hashes": (c_int, [c_i64, c_vp, c_vp]),
     "cratac_py2_set_order_hashes_device": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_uint64]),
     "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
+    "cratac_inflate_range": (c_int, [c_cp, c_int, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_i64, P(c_i64)]),
     "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
 }
 
@@ -487,3 +488,35 @@ def inflate_file(path, threads=None):
     out = np.empty(max(n.value, 1), dtype=np.uint8)
     check(lib.cratac_inflate_file(path.encode(), threads, _ptr(out), out.size, ctypes.byref(n)))
     return out[:n.value]
+
+
+def inflate_range(path, voff_begin, voff_end, threads=None):
+    """Inflate the BGZF virtual-offset range [voff_begin, voff_end) of a file -> numpy uint8 array."""
+    lib = load()
+    threads = threads or (os.cpu_count() or 1)
+    n = c_i64()
+    check(lib.cratac_inflate_range(path.encode(), threads, int(voff_begin), int(voff_end), None, 0, ctypes.byref(n)))
+    out = np.empty(max(n.value, 1), dtype=np.uint8)
+    check(lib.cratac_inflate_range(path.encode(), threads, int(voff_begin), int(voff_end), _ptr(out), out.size, ctypes.byref(n)))
+    return out[:n.value]
+
+
+def inflate_contigs(path, contigs, index=None, threads=None):
+    """Text of the records of `contigs`, in the order given, from fragments.tsv.gz + its .tbi: what a rank that owns this
+    contig range reads (the reference fetches one contig at a time, lib/python/tools/io.py:82-93).  Contigs that follow
+    one another in the file are inflated as one span."""
+    from . import tabix
+    idx = tabix.read_index(index or path + ".tbi") if not isinstance(index, dict) else index
+    spans = tabix.contig_spans(idx)
+    runs = []
+    for c in contigs:
+        if c not in spans:
+            continue
+        if runs and runs[-1][1] == spans[c][0]:
+            runs[-1][1] = spans[c][1]
+        else:
+            runs.append(list(spans[c]))
+    parts = [inflate_range(path, b, e, threads) for b, e in runs]
+    if not parts:
+        return np.empty(0, dtype=np.uint8)
+    return parts[0] if len(parts) == 1 else np.concatenate(parts)

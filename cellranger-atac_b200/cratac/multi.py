@@ -49,6 +49,16 @@ def partition_contigs(contig_lens, world):
     return bounds[::-1]
 
 
+def rank_text(fragments_path, contigs, rank, world, index=None, threads=None):
+    """Host text of rank `rank`'s contig range of fragments.tsv.gz: only the BGZF blocks the tabix index assigns to
+    those contigs are read and inflated (the reference's per-contig chunks go through
+    pysam.TabixFile.fetch, lib/python/tools/io.py:82-93).  contigs = [(name, length), ...] in reference order.
+    -> (numpy uint8 text, (first, last_exclusive) contig range)."""
+    from . import _ffi
+    first, last = partition_contigs([c[1] for c in contigs], world)[rank]
+    return _ffi.inflate_contigs(fragments_path, [c[0] for c in contigs[first:last]], index=index, threads=threads), (first, last)
+
+
 # --------------------------------------------------------------------------------------------- barcode union
 def global_columns(torch, keys_all, first_all, hash_all, valid_all, py2_order_fn, order="py2set"):
     """keys/first/hash: int64 tensors [world, maxB] (padded), valid_all: bool [world, maxB].

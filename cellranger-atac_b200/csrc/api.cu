@@ -897,4 +897,86 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
     return CRATAC_OK;
 }
 
+// Inflate the BGZF virtual-offset range [voff_begin, voff_end) of a file (voff = compressed offset of a block << 16 |
+// offset inside the inflated block: the unit of a tabix index, lib/python/tools/io.py:86 reads contigs through
+// pysam.TabixFile the same way).  Only the bytes of the blocks involved are read; they inflate on `threads` threads.
+int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uint64_t voff_end, char* out, int64_t cap, int64_t* nbytes) {
+    if (!path || !nbytes) { set_error("cratac_inflate_range: null argument"); return CRATAC_ERR_ARG; }
+    *nbytes = 0;
+    if (voff_end <= voff_begin) return CRATAC_OK;
+    const uint64_t c_begin = voff_begin >> 16, c_end = voff_end >> 16;
+    const uint32_t u_begin = (uint32_t)(voff_begin & 0xFFFF), u_end = (uint32_t)(voff_end & 0xFFFF);
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    const uint64_t fsz = (uint64_t)ftell(f);
+    if (c_begin >= fsz) { fclose(f); set_error("virtual offset beyond the end of %s", path); return CRATAC_ERR_ARG; }
+    // the last block is needed only when some of its bytes are inside the range
+    const uint64_t read_end = std::min<uint64_t>(fsz, u_end > 0 ? c_end + 65536 : c_end);
+    std::vector<unsigned char> buf((size_t)(read_end - c_begin));
+    fseek(f, (long)c_begin, SEEK_SET);
+    if (!buf.empty() && fread(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); set_error("short read on %s", path); return CRATAC_ERR_IO; }
+    fclose(f);
+    struct Blk { size_t off, csize; int64_t out_off; uint32_t isize, lo, hi; };   // [lo, hi) of the inflated block is kept
+    std::vector<Blk> blocks;
+    size_t p = 0;
+    int64_t total = 0;
+    while (c_begin + p < c_end || (c_begin + p == c_end && u_end > 0)) {
+        if (p + 18 > buf.size()) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
+        const unsigned char* b = &buf[p];
+        if (!(b[0] == 31 && b[1] == 139 && b[2] == 8 && (b[3] & 4))) { set_error("no BGZF block at offset %llu of %s", (unsigned long long)(c_begin + p), path); return CRATAC_ERR_IO; }
+        const unsigned xlen = b[10] | (b[11] << 8);
+        size_t q = p + 12;
+        const size_t xend = q + xlen;
+        long bsize = -1;
+        while (q + 4 <= xend && xend <= buf.size()) {
+            const unsigned slen = buf[q + 2] | (buf[q + 3] << 8);
+            if (buf[q] == 'B' && buf[q + 1] == 'C' && slen == 2) bsize = (buf[q + 4] | (buf[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < 0 || p + (size_t)bsize > buf.size()) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
+        uint32_t isize;
+        memcpy(&isize, &buf[p + bsize - 4], 4);
+        const uint64_t at = c_begin + p;
+        uint32_t lo = at == c_begin ? u_begin : 0u, hi = at == c_end ? u_end : isize;
+        if (hi > isize || lo > hi) { set_error("virtual offset beyond its block in %s", path); return CRATAC_ERR_ARG; }
+        blocks.push_back(Blk{p + 12 + xlen, (size_t)bsize - 12 - xlen - 8, total, isize, lo, hi});
+        total += hi - lo;
+        p += (size_t)bsize;
+    }
+    *nbytes = total;
+    if (cap == 0 || !out) return CRATAC_OK;
+    if (cap < total) { set_error("inflate buffer too small: need %lld bytes", (long long)total); return CRATAC_ERR_ARG; }
+    if (threads < 1) threads = 1;
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
+        std::vector<unsigned char> part;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= blocks.size()) break;
+            const Blk& k = blocks[i];
+            const bool whole = k.lo == 0 && k.hi == k.isize;
+            if (!whole) part.resize(k.isize);
+            inflateReset(&zs);
+            zs.next_in = &buf[k.off]; zs.avail_in = (uInt)k.csize;
+            zs.next_out = whole ? reinterpret_cast<unsigned char*>(out) + k.out_off : part.data(); zs.avail_out = k.isize;
+            const int rc = k.isize == 0 && k.csize == 0 ? Z_STREAM_END : inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) { failed = 1; break; }
+            if (!whole && k.hi > k.lo) memcpy(out + k.out_off, part.data() + k.lo, k.hi - k.lo);
+        }
+        inflateEnd(&zs);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (failed) { set_error("corrupt BGZF block in %s", path); return CRATAC_ERR_IO; }
+    return CRATAC_OK;
+}
+
+
 }  // extern "C"

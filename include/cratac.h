@@ -204,6 +204,11 @@ int cratac_py2_set_order(int64_t n, const char* const* keys, int64_t* order_out)
 /* multi-threaded BGZF/gzip inflate of fragments.tsv.gz into a caller buffer (replaces the
  * `gzip -c -d` pipe of lib/python/tools/io.py:197-217).  cap = 0 returns the inflated size. */
 int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, int64_t* nbytes);
+/* the same for one BGZF virtual-offset range [voff_begin, voff_end) of the file (virtual offset = compressed offset of
+ * a block << 16 | offset in the inflated block, the unit of a tabix index): what a rank that owns a range of contigs
+ * reads instead of the whole file (replaces pysam.TabixFile(...).fetch(contig), lib/python/tools/io.py:86-99).
+ * cap = 0 returns the inflated size. */
+int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uint64_t voff_end, char* out, int64_t cap, int64_t* nbytes);
 /* synthetic text encoder (SoA on the device -> fragments.tsv text on the device), used by bench/tests
  * to build large inputs without a host formatting loop.  bc_seq = 2-bit packed 16-mers. */
 int cratac_encode_text_device(cratac_ctx* ctx, int64_t n, const int32_t* d_chrom, const int32_t* d_start,

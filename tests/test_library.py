@@ -68,6 +68,73 @@ def test_inflate_bgzf_and_gzip(tmp_path):
     assert _ffi.inflate_file(p3).tobytes() == text
 
 
+def test_tabix_index_and_contig_range_inflate(tmp_path):
+    """Host ingest: a rank reads only the BGZF blocks of its contig range, located through the
+    tabix index (the reference fetches contig by contig through pysam.TabixFile, lib/python/tools/io.py:82-93)."""
+    from cratac import tabix
+    contigs = [("chr1", 3000000), ("chr2", 2000000), ("chr3", 500000), ("chr4", 900000), ("chrM", 16000)]
+    frags = synth.generate(contigs[:4], 40000, 20, 80, seed=9)        # chrM has no record
+    text = synth.to_text(frags)
+    p = str(tmp_path / "fragments.tsv.gz")
+    bgzf.write(p, text)
+    tbi = tabix.build_index(p)
+    idx = tabix.read_index(tbi)
+    assert idx["names"] == ["chr1", "chr2", "chr3", "chr4"] and idx["format"] == tabix.TBX_UCSC
+    assert (idx["col_seq"], idx["col_beg"], idx["col_end"]) == (1, 2, 3)
+    lines = text.split(b"\n")[:-1]
+    by_contig = {}
+    for ln in lines:
+        by_contig.setdefault(ln.split(b"\t")[0].decode(), []).append(ln)
+    spans = tabix.contig_spans(idx)
+    assert set(spans) == set(by_contig)
+    for name, (v0, v1) in spans.items():                                # every contig on its own
+        got = _ffi.inflate_range(p, v0, v1, threads=3).tobytes()
+        assert got == b"\n".join(by_contig[name]) + b"\n"
+    # contiguous contig ranges, as the multi-GPU step partitions them; a range without records is empty
+    for first, last in ((0, 2), (2, 5), (1, 4), (4, 5), (0, 5)):
+        names = [c[0] for c in contigs[first:last]]
+        want = b"".join(b"\n".join(by_contig[n]) + b"\n" for n in names if n in by_contig)
+        assert _ffi.inflate_contigs(p, names, threads=2).tobytes() == want
+    assert _ffi.inflate_contigs(p, ["chr3", "chr1"]).tobytes() == b"".join(b"\n".join(by_contig[n]) + b"\n" for n in ("chr3", "chr1"))
+    # every rank of a 1..4-GPU step reads its own range; together they read the file once
+    from cratac import multi
+    for world in (1, 2, 3, 4):
+        texts = [multi.rank_text(p, contigs, r, world, threads=2) for r in range(world)]
+        assert b"".join(t.tobytes() for t, _ in texts) == text
+        assert [rng for _, rng in texts] == multi.partition_contigs([c[1] for c in contigs], world)
+    # the spans tile the file: consecutive contigs meet, and the union is the whole text
+    order = [spans[n] for n in idx["names"]]
+    assert all(order[k][1] == order[k + 1][0] for k in range(len(order) - 1))
+    assert _ffi.inflate_range(p, order[0][0], order[-1][1]).tobytes() == text
+    # a range inside one block, and ranges that end exactly on a block boundary
+    v0 = spans["chr1"][0]
+    assert _ffi.inflate_range(p, v0 + 10, v0 + 110).tobytes() == text[10:110]
+    assert _ffi.inflate_range(p, v0, v0).size == 0
+    assert _ffi.inflate_range(p, v0, v0 + bgzf.BLOCK_IN).tobytes() == text[:bgzf.BLOCK_IN]      # end = isize of the block
+    with pytest.raises(_ffi.CratacError):
+        _ffi.inflate_range(p, v0 + 7, (v0 + 7) + (1 << 40))                                  # beyond the file
+
+
+def test_tabix_bins_and_linear_index(tmp_path):
+    """reg2bin is the UCSC scheme of the tabix paper (16 kb leaves, 5 levels); the linear index holds, per 16 kb
+    window, the offset of the first record that overlaps it."""
+    from cratac import tabix
+    assert tabix.reg2bin(0, 1) == 4681 and tabix.reg2bin(16384, 16385) == 4682
+    assert tabix.reg2bin(0, 16385) == 585 and tabix.reg2bin(0, 1 << 29) == 0
+    assert tabix.reg2bin((1 << 17) - 1, (1 << 17) + 1) == 73 and tabix.reg2bin(1 << 26, (1 << 26) + 5) == 4681 + 4096
+    rows = [("chrA", 5, 300), ("chrA", 20000, 20100), ("chrA", 20050, 40000), ("chrB", 1, 2)]
+    text = "".join("%s\t%d\t%d\tACGTACGTACGTACGT-1\t1\n" % r for r in rows).encode()
+    p = str(tmp_path / "f.tsv.gz")
+    bgzf.write(p, text)
+    idx = tabix.read_index(tabix.build_index(p))
+    a, b = idx["refs"]
+    first = tabix.contig_spans(idx)["chrA"][0]
+    line_len = [len(("%s\t%d\t%d\tACGTACGTACGTACGT-1\t1\n" % r)) for r in rows]
+    assert sorted(a["bins"]) == sorted({tabix.reg2bin(5, 300), tabix.reg2bin(20000, 20100), tabix.reg2bin(20050, 40000)})
+    assert a["linear"] == [first, first + line_len[0], first + line_len[0] + line_len[1]]
+    assert list(b["bins"]) == [4681] and len(b["linear"]) == 1
+
+
 def test_synth_is_sorted_and_valid():
     contigs = synth.GRCH38[:3]
     f = synth.generate(contigs, 5000, 10, 30, seed=1)
