@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import util
-from cratac import _ffi, multi, synth
+from cratac import _ffi, bgzf, multi, synth, tabix
 from oracle import cfast, em as oracle_em, py2set
 
 
@@ -125,11 +125,12 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     contigs, frags = _dataset()
-    parts = multi.partition_contigs([c[1] for c in contigs], world)
-    a, b = parts[rank]
+    # every rank reads its own contig range of fragments.tsv.gz through the tabix index (host ingest of the product)
+    text, (a, b) = multi.rank_text(os.path.join(out_dir, "fragments.tsv.gz"), contigs, rank, world, threads=2)
     m = (frags["chrom"] >= a) & (frags["chrom"] < b)
     sub = {k: (v[m] if isinstance(v, np.ndarray) else v) for k, v in frags.items()}
-    text = synth.to_text(sub)
+    text = text.tobytes()
+    assert text == synth.to_text(sub)
     shard = OracleShard(contigs, [c[0] for c in contigs[a:b]], text, a)
     res = multi.step(shard, torch, dist, torch.device("cpu"))
     if rank == 0:
@@ -148,6 +149,9 @@ def test_two_rank_step_matches_single_process_oracle(tmp_path):
     sock.bind(("127.0.0.1", 0))
     port = sock.getsockname()[1]
     sock.close()
+    contigs, frags = _dataset()
+    bgzf.write(str(tmp_path / "fragments.tsv.gz"), synth.to_text(frags))
+    tabix.build_index(str(tmp_path / "fragments.tsv.gz"))
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     got = np.load(str(tmp_path / "merged.npz"))
     # single-process oracle on the whole dataset
