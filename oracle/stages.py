@@ -329,3 +329,81 @@ def filter_peak_matrix(n_features, bcs, indptr, indices, data, cell_barcodes, nu
         out_data.extend(data[lo:hi])
         out_indptr.append(len(out_indices))
     return out_bcs, out_indptr, out_indices, out_data
+
+
+# --------------------------------------------------------------------------- #
+# REMOVE_LOW_TARGETING_BARCODES (oracle ahead of the kernel) #
+# --------------------------------------------------------------------------- #
+LOW_TARGETING_DISTANCE = 2000              # cell_calling/remove_low_targeting_barcodes/__init__.py:40
+LOW_TARGETING_PADDINGS = (0, 50000)        # :41
+
+
+def tools_regions(rows):
+    """lib/python/tools/regions.py:39-53 (NOT tenkit's Regions: no merging of overlapping rows).  rows = (start, end)
+    pairs of one contig -> (starts, ends) in the order of the sorted (start, end) pairs.  `ends` is NOT sorted when rows
+    nest, and overlaps_region bisects it all the same -- kept."""
+    srt = sorted(rows)
+    return [r[0] for r in srt], [r[1] for r in srt]
+
+
+def overlaps_region(starts, ends, start, end):
+    """lib/python/tools/regions.py:83-93: the first row whose end is >= start (bisect_left: a row that ENDS where the
+    fragment starts is taken) overlaps iff the fragment ends beyond that row's start."""
+    k = bisect.bisect_left(ends, start)
+    if k == len(starts):
+        return False
+    return end > starts[k]
+
+
+def count_covered_bases(starts, stops, contig_len, padding):
+    """cell_calling/remove_low_targeting_barcodes/__init__.py:44-73: bases covered by the union of the padded intervals,
+    taken in the order given (a later interval joins the running one iff it starts before the running stop)."""
+    occupancy = 0
+    run_start = run_stop = None
+    for start, stop in zip(starts, stops):
+        start = max(0, start - padding)
+        stop = min(contig_len, stop + padding)
+        if run_start is None:
+            run_start, run_stop = start, stop
+        elif start < run_stop:
+            run_stop = max(stop, run_stop)
+        else:
+            occupancy += run_stop - run_start
+            run_start, run_stop = start, stop
+    if run_start is not None:
+        occupancy += run_stop - run_start
+    return occupancy
+
+
+def remove_low_targeting_contig(contig, contig_len, peak_rows, fragments):
+    """REMOVE_LOW_TARGETING_BARCODES.main for one contig (cell_calling/remove_low_targeting_barcodes/__init__.py:178-243).
+    peak_rows = (contig, start, end) of the whole peaks file; fragments = (contig, start, stop, barcode, dup) rows of the
+    file in file order (only those of `contig` are used, as tabix fetch would return them).
+    -> dict(fragment_counts, targeted_counts, fragment_lengths{padding}, covered_bases{padding}, peak_coverage)."""
+    mine = [(s, e) for c, s, e in peak_rows if c == contig]
+    starts, ends = tools_regions(mine) if mine else ([], [])
+    fragment_counts, targeted_counts = Counter(), Counter()
+    lengths = {p: Counter() for p in LOW_TARGETING_PADDINGS}
+    running = {p: {} for p in LOW_TARGETING_PADDINGS}          # barcode -> [covered so far, run start, run stop]
+    for c, start, stop, barcode, _dup in fragments:
+        if c != contig:
+            continue
+        fragment_counts[barcode] += 1
+        if mine and overlaps_region(starts, ends, start, stop):
+            targeted_counts[barcode] += 1
+        for p in LOW_TARGETING_PADDINGS:
+            a, b = max(0, start - p), min(contig_len, stop + p)
+            lengths[p][barcode] += b - a
+            st = running[p].setdefault(barcode, [0, None, None])
+            if st[1] is None:
+                st[1], st[2] = a, b
+            elif a < st[2]:
+                st[2] = max(b, st[2])
+            else:
+                st[0] += st[2] - st[1]
+                st[1], st[2] = a, b
+    covered = {p: Counter({bc: st[0] + (st[2] - st[1] if st[1] is not None else 0) for bc, st in running[p].items()})
+               for p in LOW_TARGETING_PADDINGS}
+    peak_coverage = count_covered_bases(starts, ends, contig_len, LOW_TARGETING_DISTANCE) if mine else 0
+    return dict(fragment_counts=fragment_counts, targeted_counts=targeted_counts, fragment_lengths=lengths,
+                covered_bases=covered, peak_coverage=peak_coverage)

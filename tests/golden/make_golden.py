@@ -24,7 +24,7 @@ __init__, bc_to_int, select_barcodes, filter_barcodes) are exec'd unmodified on 
 matrices; only cellranger/bisect.pyx (Cython, 12 lines) is restated, and numpy's
 ``np.array(list, copy=False)`` is given its pre-2.0 meaning.
 
-Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter ...]   (writes next to this file)
+Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting ...]   (writes next to this file)
 """
 import ast
 import io
@@ -482,6 +482,88 @@ def make_filter_cases():
     return cases
 
 
+# --------------------------------------------------------------------------- REMOVE_LOW_TARGETING_BARCODES
+def run_remove_low_targeting_main(contig, contig_len, peaks_text, frag_rows, tmpdir):
+    """reference REMOVE_LOW_TARGETING_BARCODES.main for one contig chunk (cell_calling/remove_low_targeting_barcodes/
+    __init__.py:178-243) with the reference's own Regions / fragment_overlaps_target (lib/python/tools/regions.py)."""
+    import bisect as _bisect
+    from collections import namedtuple
+    fp = FakePickle()
+    FakeRefMgr.contig_lengths = {contig: contig_len}
+    reg_ns = {"bisect": _bisect, "namedtuple": namedtuple}
+    load_reference_module("lib/python/tools/regions.py", reg_ns,
+                          keep_funcs={"Region", "Regions", "get_target_regions_dict", "get_target_regions", "fragment_overlaps_target"})
+
+    def parsed_fragments_from_contig(c, filename, index=None):
+        for r in frag_rows:
+            if r[0] == c:
+                yield r
+
+    ns = {"json": json, "pickle": fp, "Counter": Counter, "ReferenceManager": FakeRefMgr,
+          "parsed_fragments_from_contig": parsed_fragments_from_contig,
+          "get_target_regions": reg_ns["get_target_regions"], "fragment_overlaps_target": reg_ns["fragment_overlaps_target"]}
+    load_reference_module("mro/atac/stages/processing/cell_calling/remove_low_targeting_barcodes/__init__.py", ns)
+    pk = os.path.join(tmpdir, "peaks_rlt.bed")
+    with open(pk, "w") as f:
+        f.write(peaks_text)
+    outs = Record(fragment_counts=os.path.join(tmpdir, "fc.pickle"), targeted_counts=os.path.join(tmpdir, "tc.pickle"),
+                  fragment_lengths=os.path.join(tmpdir, "fl.pickle"), covered_bases=os.path.join(tmpdir, "cb.pickle"),
+                  peak_coverage=None)
+    args = Record(peaks=pk, fragments="frag.tsv.gz", fragments_index="frag.tsv.gz.tbi", reference_path="ref", contig=contig)
+    ns["main"](args, outs)
+    as_dict = lambda c: {k: int(v) for k, v in sorted(c.items())}
+    return dict(fragment_counts=as_dict(fp.store[outs.fragment_counts]), targeted_counts=as_dict(fp.store[outs.targeted_counts]),
+                fragment_lengths={str(p): as_dict(c) for p, c in fp.store[outs.fragment_lengths].items()},
+                covered_bases={str(p): as_dict(c) for p, c in fp.store[outs.covered_bases].items()},
+                peak_coverage=int(outs.peak_coverage))
+
+
+def make_low_targeting_cases(tmpdir):
+    cases = []
+
+    def add(name, contig_len, peaks, frags):
+        peaks_text = "".join("%s\t%d\t%d\n" % p for p in peaks)
+        got = run_remove_low_targeting_main("chr1", contig_len, peaks_text, frags, tmpdir)
+        cases.append(dict(name=name, contig="chr1", contig_len=contig_len, peaks=[list(p) for p in peaks],
+                          fragments=[list(r) for r in frags], expect=got))
+
+    # touching is overlap on the left only: Regions.overlaps_region bisects the ENDS with bisect_left
+    add("touching_edges", 100000, [("chr1", 1000, 2000), ("chr1", 5000, 6000)],
+        [("chr1", 500, 1000, "A-1", 1), ("chr1", 2000, 2100, "A-1", 1), ("chr1", 1999, 2001, "B-1", 1), ("chr1", 2001, 2100, "B-1", 2),
+         ("chr1", 4000, 5000, "C-1", 1), ("chr1", 4000, 5001, "C-1", 1), ("chr1", 6000, 6001, "D-1", 1), ("chr1", 6001, 6002, "D-1", 1)])
+    add("no_peaks_on_contig", 50000, [("chr2", 10, 20)], [("chr1", 10, 200, "A-1", 1), ("chr1", 40000, 49999, "B-1", 1)])
+    add("no_fragments", 50000, [("chr1", 100, 200), ("chr1", 3000, 3100)], [])
+    add("padding_clipped_at_contig_ends", 60000, [("chr1", 100, 900), ("chr1", 59000, 59900)],
+        [("chr1", 0, 120, "A-1", 1), ("chr1", 30, 400, "A-1", 1), ("chr1", 59950, 60000, "A-1", 1), ("chr1", 20000, 20300, "B-1", 1)])
+    add("overlapping_and_nested_peaks", 300000, [("chr1", 1000, 9000), ("chr1", 2000, 3000), ("chr1", 8500, 12000), ("chr1", 100000, 100500),
+                                                   ("chr1", 103000, 104000)],
+        [("chr1", 3100, 3200, "A-1", 1), ("chr1", 9500, 9600, "A-1", 1), ("chr1", 12000, 12100, "B-1", 1), ("chr1", 50000, 50400, "B-1", 1),
+         ("chr1", 101000, 101200, "B-1", 1), ("chr1", 160000, 160100, "A-1", 1)])
+    rng = np.random.default_rng(77)
+    for k, (L, n_peaks, n_frag, n_bc) in enumerate([(400000, 40, 600, 12), (3000000, 300, 4000, 60), (150000, 3, 900, 5)]):
+        ps = np.sort(rng.integers(0, L - 3000, size=n_peaks))
+        peaks, last = [], -1
+        for s in ps.tolist():
+            s = max(s, last + 1)
+            e = min(L, s + int(rng.integers(150, 2500)))
+            if e <= s:
+                continue
+            peaks.append(("chr1", s, e))
+            last = e + int(rng.integers(0, 3)) - 1          # touching and 1-base gaps do occur
+        st = np.sort(rng.integers(0, L - 1300, size=n_frag))
+        ln = rng.integers(20, 1200, size=n_frag)
+        bcs = ["".join(rng.choice(list("ACGT"), size=16)) + "-1" for _ in range(n_bc)]
+        frags = [("chr1", int(a), int(min(L, a + b)), bcs[int(rng.integers(0, n_bc))], int(rng.integers(1, 4))) for a, b in zip(st, ln)]
+        # a few fragments pinned to peak boundaries
+        for j in range(0, len(peaks), max(1, len(peaks) // 6)):
+            _, s, e = peaks[j]
+            frags.append(("chr1", e, min(L, e + 50), bcs[0], 1))
+            frags.append(("chr1", max(0, s - 50), s, bcs[1 % n_bc], 1))
+        frags.sort(key=lambda r: (r[1], r[2]))
+        add("random_%d" % k, L, peaks, frags)
+    return cases
+
+
 def main():
     only = set(sys.argv[1:])
     with tempfile.TemporaryDirectory() as tmpdir:
@@ -494,6 +576,9 @@ def main():
         if not only or "filter" in only:
             with open(os.path.join(HERE, "filter.json"), "w") as f:
                 json.dump(make_filter_cases(), f, separators=(",", ":"))
+        if not only or "low_targeting" in only:
+            with open(os.path.join(HERE, "low_targeting.json"), "w") as f:
+                json.dump(make_low_targeting_cases(tmpdir), f, separators=(",", ":"))
         if not only or "em" in only:
             with open(os.path.join(HERE, "em.json"), "w") as f:
                 json.dump(make_em_cases(), f, separators=(",", ":"))

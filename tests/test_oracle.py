@@ -209,3 +209,23 @@ def test_filter_peak_matrix_restatement_matches_reference(case):
                                                            case["cell_barcodes"], case["num_analysis_bcs"], case["random_seed"])
     want = case["result"]
     assert bcs == want["bcs"] and list(indptr) == want["indptr"] and list(indices) == want["indices"] and list(data) == want["data"]
+
+
+LOW_TARGETING_CASES = json.load(open(os.path.join(GOLDEN, "low_targeting.json")))
+
+
+@pytest.mark.parametrize("case", LOW_TARGETING_CASES, ids=[c["name"] for c in LOW_TARGETING_CASES])
+def test_remove_low_targeting_restatement_matches_reference(case):
+    """oracle.stages.remove_low_targeting_contig (the next sibling stage) against vectors produced by
+    the reference's own REMOVE_LOW_TARGETING_BARCODES.main + tools/regions.py: fragment-INTERVAL overlap with the
+    bisect-on-ends rule (touching on the left counts; nested rows leave `ends` unsorted), per-barcode padded lengths and
+    covered bases, peak coverage within 2 kb."""
+    got = stages.remove_low_targeting_contig(case["contig"], case["contig_len"], [tuple(p) for p in case["peaks"]],
+                                             [tuple(r) for r in case["fragments"]])
+    want = case["expect"]
+    assert dict(got["fragment_counts"]) == want["fragment_counts"]
+    assert {k: v for k, v in got["targeted_counts"].items() if v} == want["targeted_counts"]
+    for p in (0, 50000):
+        assert dict(got["fragment_lengths"][p]) == want["fragment_lengths"][str(p)]
+        assert dict(got["covered_bases"][p]) == want["covered_bases"][str(p)]
+    assert got["peak_coverage"] == want["peak_coverage"]
