@@ -407,3 +407,137 @@ def remove_low_targeting_contig(contig, contig_len, peak_rows, fragments):
     peak_coverage = count_covered_bases(starts, ends, contig_len, LOW_TARGETING_DISTANCE) if mine else 0
     return dict(fragment_counts=fragment_counts, targeted_counts=targeted_counts, fragment_lengths=lengths,
                 covered_bases=covered, peak_coverage=peak_coverage)
+
+
+# --------------------------------------------------------------------------- #
+# get_counts_by_barcode (oracle ahead of the kernel)         #
+# --------------------------------------------------------------------------- #
+def tools_target_regions(lines, padding=0):
+    """lib/python/tools/regions.py:96-128: BED lines -> {contig: sorted [(start - padding, end + padding, name, strand)]}.
+    Rows are ordered as tuples; None sorts before any string as it does in Python 2."""
+    targets = {}
+    for line in lines:
+        info = line.strip().split("\t")
+        if any(line.startswith(c) for c in ("browser", "track", "-browser", "-track", "#")):
+            continue
+        if len(line.strip()) == 0:
+            continue
+        name = info[3] if len(info) >= 4 else None
+        strand = info[5] if len(info) >= 6 else None
+        if strand not in ("+", "-"):
+            strand = None
+        targets.setdefault(info[0], []).append((int(info[1]) - padding, int(info[2]) + padding, name, strand))
+    py2_key = lambda r: (r[0], r[1], r[2] is not None, r[2] or "", r[3] is not None, r[3] or "")
+    return {chrom: sorted(rows, key=py2_key) for chrom, rows in targets.items()}
+
+
+def region_containing_point(rows, starts, point):
+    """lib/python/tools/regions.py:66-81 (contains_point / get_region_containing_point)."""
+    k = bisect.bisect(starts, point) - 1
+    if k >= 0 and starts[k] <= point < rows[k][1]:
+        return rows[k]
+    return None
+
+
+def relative_position(region, point):
+    """Region.get_relative_position, lib/python/tools/regions.py:24-36 (width = end - start - 1)."""
+    start, end, _name, strand = region
+    width = end - start - 1
+    if strand != "-":
+        return (point - start) - width // 2
+    return (end - point) - width // 2
+
+
+def get_counts_by_barcode(tracks, peaks_text, fragments, species_list, species_of_contig, known_cells_text=None, contig=None):
+    """lib/python/tools/io.py:429-555.  tracks = {"tss" | "ctcf" | "dnase" | "enhancer" | "promoter" | "blacklist": BED text
+    or None}; fragments = (contig, start, stop, barcode, dups) rows in file order.
+    -> (read_count, {barcode: Counter}, tss_relpos, ctcf_relpos).  The "cell_id" label (io.py:482-488) numbers cells in
+    CPython-2.7 dict order, emulated with the same table walk as the matrix columns (oracle/py2set.py)."""
+    from . import py2set
+
+    def load(text, padding=0):
+        if text is None:
+            return None
+        rows = tools_target_regions(text.splitlines(True), padding)
+        return {c: (r, [x[0] for x in r], [x[1] for x in r]) for c, r in rows.items()}
+
+    tss, ctcf = load(tracks.get("tss"), 2000), load(tracks.get("ctcf"), 250)
+    dnase, enhancer = load(tracks.get("dnase")), load(tracks.get("enhancer"))
+    promoter, blacklist = load(tracks.get("promoter")), load(tracks.get("blacklist"))
+    peaks = load(peaks_text)
+
+    def point_region(c, position, regions):
+        if regions is None or c not in regions:
+            return None
+        rows, starts, _ends = regions[c]
+        return region_containing_point(rows, starts, position)
+
+    def overlaps(c, start, stop, regions):
+        if regions is None or c not in regions:
+            return False
+        _rows, starts, ends = regions[c]
+        return overlaps_region(starts, ends, start, stop)
+
+    cell_barcodes, inserted = {}, []
+    if known_cells_text is not None:
+        for line in known_cells_text.splitlines(True):
+            items = line.strip("\n").split(",")
+            for barcode in items[1:]:
+                if barcode != "null":
+                    if barcode not in cell_barcodes:
+                        cell_barcodes[barcode] = []
+                        inserted.append(barcode)
+                    cell_barcodes[barcode] += [items[0]]
+    cell_index = {}
+    spnum = {species: 0 for species in species_list}
+    py2_order = list(py2set.py2_set_order(inserted)) if inserted else []     # returns the keys in table order
+    for species in species_list:
+        for barcode in py2_order:
+            if species in cell_barcodes[barcode]:
+                label = "{}_cell_{}".format(species, spnum[species])
+                spnum[species] += 1
+                cell_index[barcode] = label if barcode not in cell_index else "_".join([cell_index[barcode], label])
+
+    counts, tss_relpos, ctcf_relpos = {}, Counter(), Counter()
+    read_count = 0
+    for c, start, stop, barcode, dups in fragments:
+        if contig is not None and c != contig:
+            continue
+        read_count += 2
+        if barcode not in counts:
+            counts[barcode] = Counter()
+            if known_cells_text is not None:
+                counts[barcode]["cell_id"] = cell_index.get(barcode, "None")
+                for species in species_list:
+                    counts[barcode]["is_{}_cell_barcode".format(species)] = 1 if species in cell_barcodes.get(barcode, []) else 0
+        cb = counts[barcode]
+        if known_cells_text is not None and len(species_list) > 1:
+            sp = species_of_contig[c]
+            cb["passed_filters_{}".format(sp)] += 1
+            if overlaps(c, start, stop, peaks):
+                cb["peak_region_fragments_{}".format(sp)] += 1
+        cb["passed_filters"] += 1
+        cb["total"] += dups
+        cb["duplicate"] += dups - 1
+        for position in (start, stop):
+            r = point_region(c, position, tss)
+            if r is not None:
+                tss_relpos[relative_position(r, position)] += 1
+            r = point_region(c, position, ctcf)
+            if r is not None:
+                ctcf_relpos[relative_position(r, position)] += 1
+            if point_region(c, position, peaks) is not None:
+                cb["peak_region_cutsites"] += 1
+        targeted = False
+        for regions, key in ((tss, "TSS_fragments"), (dnase, "DNase_sensitive_region_fragments"),
+                             (enhancer, "enhancer_region_fragments"), (promoter, "promoter_region_fragments")):
+            if overlaps(c, start, stop, regions):
+                cb[key] += 1
+                targeted = True
+        if targeted:
+            cb["on_target_fragments"] += 1
+        if overlaps(c, start, stop, blacklist):
+            cb["blacklist_region_fragments"] += 1
+        if overlaps(c, start, stop, peaks):
+            cb["peak_region_fragments"] += 1
+    return read_count, counts, tss_relpos, ctcf_relpos

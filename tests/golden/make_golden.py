@@ -24,7 +24,7 @@ __init__, bc_to_int, select_barcodes, filter_barcodes) are exec'd unmodified on 
 matrices; only cellranger/bisect.pyx (Cython, 12 lines) is restated, and numpy's
 ``np.array(list, copy=False)`` is given its pre-2.0 meaning.
 
-Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting ...]   (writes next to this file)
+Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting|counts_by_barcode ...]   (writes next to this file)
 """
 import ast
 import io
@@ -564,6 +564,132 @@ def make_low_targeting_cases(tmpdir):
     return cases
 
 
+# --------------------------------------------------------------------------- get_counts_by_barcode
+TRACKS = ("tss", "ctcf", "dnase", "enhancer", "promoter", "blacklist")
+
+
+def run_get_counts_by_barcode(tracks, peaks_text, frag_rows, species_list, species_of_contig, known_cells_text, contig, tmpdir):
+    """reference tools/io.py:429-555 with the reference's own Region / Regions (lib/python/tools/regions.py)."""
+    import bisect as _bisect
+    from collections import namedtuple
+    reg_ns = {"bisect": _bisect, "namedtuple": namedtuple}
+    load_reference_module("lib/python/tools/regions.py", reg_ns,
+                          keep_funcs={"Region", "Regions", "get_target_regions_dict", "get_target_regions"})
+    paths = {}
+    for name in TRACKS:
+        paths[name] = None
+        if tracks.get(name) is not None:
+            paths[name] = os.path.join(tmpdir, "track_%s.bed" % name)
+            with open(paths[name], "w") as f:
+                f.write(tracks[name])
+    pk = None
+    if peaks_text is not None:
+        pk = os.path.join(tmpdir, "peaks_gcb.bed")
+        with open(pk, "w") as f:
+            f.write(peaks_text)
+    kc = None
+    if known_cells_text is not None:
+        kc = os.path.join(tmpdir, "cells.csv")
+        with open(kc, "w") as f:
+            f.write(known_cells_text)
+
+    class RefMgr(object):
+        def __init__(self, path):
+            self.tss_track, self.ctcf_track, self.dnase_track = paths["tss"], paths["ctcf"], paths["dnase"]
+            self.enhancer_track, self.promoter_track, self.blacklist_track = paths["enhancer"], paths["promoter"], paths["blacklist"]
+
+        def list_species(self):
+            return list(species_list)
+
+        def species_from_contig(self, c):
+            return species_of_contig[c]
+
+    def open_fragment_file(filename):
+        for r in frag_rows:
+            yield r
+
+    def parsed_fragments_from_contig(c, filename, index=None):
+        for r in frag_rows:
+            if r[0] == c:
+                yield r
+
+    ns = {"Counter": Counter, "ReferenceManager": RefMgr, "regtools": types.SimpleNamespace(get_target_regions=reg_ns["get_target_regions"]),
+          "open_fragment_file": open_fragment_file, "parsed_fragments_from_contig": parsed_fragments_from_contig}
+    load_reference_module("lib/python/tools/io.py", ns, keep_funcs={"get_counts_by_barcode"})
+    read_count, counts, tss_relpos, ctcf_relpos = ns["get_counts_by_barcode"]("ref", pk, "frag.tsv.gz", fragments_index="x.tbi",
+                                                                              contig=contig, known_cells=kc)
+    # "cell_id" numbers the cells in the iteration order of a CPython-2.7 dict (io.py:482-488); a Python-3 run cannot
+    # reproduce that order, so the label is left out of the vectors (everything else does not depend on it)
+    return dict(read_count=int(read_count),
+                counts_by_barcode={bc: {k: int(v) for k, v in sorted(c.items()) if k != "cell_id"} for bc, c in sorted(counts.items())},
+                tss_relpos={str(k): int(v) for k, v in sorted(tss_relpos.items())},
+                ctcf_relpos={str(k): int(v) for k, v in sorted(ctcf_relpos.items())})
+
+
+def make_counts_by_barcode_cases(tmpdir):
+    cases = []
+
+    def bed(rows):
+        return "".join("\t".join(str(x) for x in r) + "\n" for r in rows)
+
+    def add(name, tracks, peaks, frags, species_list=("GRCh38",), species_of_contig=None, known_cells=None, contig=None):
+        species_of_contig = species_of_contig or {"chr1": "GRCh38", "chr2": "GRCh38"}
+        tr = {k: (bed(v) if v is not None else None) for k, v in tracks.items()}
+        pk = bed(peaks) if peaks is not None else None
+        got = run_get_counts_by_barcode(tr, pk, frags, species_list, species_of_contig, known_cells, contig, tmpdir)
+        cases.append(dict(name=name, tracks=tr, peaks=pk, fragments=[list(r) for r in frags], species_list=list(species_list),
+                          species_of_contig=species_of_contig, known_cells=known_cells, contig=contig, expect=got))
+
+    tss = [("chr1", 10000, 10001, "GENE1", ".", "+"), ("chr1", 30000, 30001, "GENE2", ".", "-"), ("chr2", 5000, 5001, "GENE3", ".", "+")]
+    ctcf = [("chr1", 12000, 12020, "CTCF1", ".", "+"), ("chr1", 40000, 40019, "CTCF2", ".", "-")]
+    small = dict(tss=tss, ctcf=ctcf, dnase=[("chr1", 100, 500), ("chr1", 20000, 21000)], enhancer=[("chr1", 400, 450)],
+                 promoter=[("chr1", 9000, 10500), ("chr2", 4000, 5200)], blacklist=[("chr1", 50000, 60000)])
+    frags = [("chr1", 90, 100, "A-1", 1), ("chr1", 100, 130, "A-1", 3), ("chr1", 500, 700, "A-1", 1), ("chr1", 8001, 8100, "B-1", 2),
+             ("chr1", 9999, 10001, "B-1", 1), ("chr1", 11749, 11751, "B-1", 1), ("chr1", 12269, 12271, "C-1", 5), ("chr1", 28000, 32001, "C-1", 1),
+             ("chr1", 39750, 40269, "A-1", 1), ("chr1", 55000, 55100, "C-1", 1), ("chr2", 3000, 3001, "A-1", 1), ("chr2", 6999, 7001, "D-1", 2)]
+    peaks = [("chr1", 95, 120), ("chr1", 9990, 10010), ("chr1", 39000, 41000), ("chr2", 2990, 3001)]
+    add("all_tracks_single_species", small, peaks, frags)
+    add("one_contig_only", small, peaks, frags, contig="chr1")
+    add("no_tracks_no_peaks", {k: None for k in TRACKS}, None, frags)
+    add("known_cells", small, peaks, frags, known_cells="GRCh38,A-1,C-1,null\n")
+    two = {"chr1": "hg19", "chr2": "mm10"}
+    add("two_species_known_cells", small, peaks, frags, species_list=("hg19", "mm10"), species_of_contig=two,
+        known_cells="hg19,A-1,B-1\nmm10,A-1,D-1,null\n")
+    rng = np.random.default_rng(91)
+    L = {"chr1": 600000, "chr2": 300000}
+
+    def rand_rows(n, wmin, wmax, named):
+        rows = set()
+        out = []
+        for _ in range(n):
+            c = "chr1" if rng.random() < 0.66 else "chr2"
+            s0 = int(rng.integers(3000, L[c] - wmax - 3000))
+            e0 = s0 + int(rng.integers(wmin, wmax + 1))
+            if (c, s0, e0) in rows:
+                continue
+            rows.add((c, s0, e0))
+            out.append((c, s0, e0, "n%d" % len(out), ".", "+-"[int(rng.integers(0, 2))]) if named else (c, s0, e0))
+        return out
+
+    tracks = dict(tss=rand_rows(60, 1, 1, True), ctcf=rand_rows(80, 19, 20, True), dnase=rand_rows(150, 150, 2000, False),
+                  enhancer=rand_rows(100, 200, 3000, False), promoter=rand_rows(60, 500, 2500, False), blacklist=rand_rows(6, 1000, 20000, False))
+    peaks, last = [], {"chr1": -1, "chr2": -1}
+    for c, s0, e0 in sorted(rand_rows(250, 150, 2500, False)):
+        s0 = max(s0, last[c] + 1)
+        if e0 > s0:
+            peaks.append((c, s0, e0))
+            last[c] = e0 - 1 + int(rng.integers(0, 2))
+    bcs = ["".join(rng.choice(list("ACGT"), size=16)) + "-1" for _ in range(40)]
+    fr = []
+    for _ in range(5000):
+        c = "chr1" if rng.random() < 0.66 else "chr2"
+        a = int(rng.integers(0, L[c] - 1300))
+        fr.append((c, a, a + int(rng.integers(20, 1200)), bcs[int(rng.integers(0, len(bcs)))], int(rng.integers(1, 5))))
+    fr.sort(key=lambda r: (r[0], r[1], r[2]))
+    add("random_tracks", tracks, peaks, fr, known_cells="GRCh38," + ",".join(bcs[:15]) + "\n")
+    return cases
+
+
 def main():
     only = set(sys.argv[1:])
     with tempfile.TemporaryDirectory() as tmpdir:
@@ -579,6 +705,9 @@ def main():
         if not only or "low_targeting" in only:
             with open(os.path.join(HERE, "low_targeting.json"), "w") as f:
                 json.dump(make_low_targeting_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "counts_by_barcode" in only:
+            with open(os.path.join(HERE, "counts_by_barcode.json"), "w") as f:
+                json.dump(make_counts_by_barcode_cases(tmpdir), f, separators=(",", ":"))
         if not only or "em" in only:
             with open(os.path.join(HERE, "em.json"), "w") as f:
                 json.dump(make_em_cases(), f, separators=(",", ":"))

@@ -229,3 +229,27 @@ def test_remove_low_targeting_restatement_matches_reference(case):
         assert dict(got["fragment_lengths"][p]) == want["fragment_lengths"][str(p)]
         assert dict(got["covered_bases"][p]) == want["covered_bases"][str(p)]
     assert got["peak_coverage"] == want["peak_coverage"]
+
+
+COUNTS_CASES = json.load(open(os.path.join(GOLDEN, "counts_by_barcode.json")))
+
+
+@pytest.mark.parametrize("case", COUNTS_CASES, ids=[c["name"] for c in COUNTS_CASES])
+def test_get_counts_by_barcode_restatement_matches_reference(case):
+    """oracle.stages.get_counts_by_barcode against vectors produced by the reference's own tools/io.py:429-555 and
+    tools/regions.py: per-barcode fragment / cut-site counts against seven region tracks, TSS and CTCF relative-position
+    profiles (padded, strand-aware).  `cell_id` is not in the vectors (CPython-2.7 dict order, see make_golden.py)."""
+    read_count, counts, tss_relpos, ctcf_relpos = stages.get_counts_by_barcode(
+        case["tracks"], case["peaks"], [tuple(r) for r in case["fragments"]], case["species_list"], case["species_of_contig"],
+        case["known_cells"], case["contig"])
+    want = case["expect"]
+    assert read_count == want["read_count"]
+    got = {bc: {k: int(v) for k, v in c.items() if k != "cell_id"} for bc, c in counts.items()}
+    # a Counter keeps keys that were written as 0 (is_<species>_cell_barcode) and those that `duplicate += 0` created
+    assert got == want["counts_by_barcode"]
+    assert {str(k): v for k, v in tss_relpos.items()} == want["tss_relpos"]
+    assert {str(k): v for k, v in ctcf_relpos.items()} == want["ctcf_relpos"]
+    if case["known_cells"] is not None:
+        ids = {bc: c["cell_id"] for bc, c in counts.items()}
+        cells = [b for line in case["known_cells"].splitlines() for b in line.split(",")[1:] if b != "null"]
+        assert all((ids[bc] == "None") == (bc not in cells) for bc in ids)
