@@ -24,6 +24,11 @@ __init__, bc_to_int, select_barcodes, filter_barcodes) are exec'd unmodified on 
 matrices; only cellranger/bisect.pyx (Cython, 12 lines) is restated, and numpy's
 ``np.array(list, copy=False)`` is given its pre-2.0 meaning.
 
+low_targeting.json and counts_by_barcode.json (the sibling stages of SURVEY 8f rank 3, oracle only so far) come from
+REMOVE_LOW_TARGETING_BARCODES.main (cell_calling/remove_low_targeting_barcodes/__init__.py:178-243) and
+get_counts_by_barcode (lib/python/tools/io.py:429-555), exec'd with the reference's own Region / Regions
+(lib/python/tools/regions.py).
+
 Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting|counts_by_barcode ...]   (writes next to this file)
 """
 import ast
