@@ -29,7 +29,7 @@ REMOVE_LOW_TARGETING_BARCODES.main (cell_calling/remove_low_targeting_barcodes/_
 get_counts_by_barcode (lib/python/tools/io.py:429-555), exec'd with the reference's own Region / Regions
 (lib/python/tools/regions.py).
 
-Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting|counts_by_barcode ...]   (writes next to this file)
+Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting|counts_by_barcode|cell_em ...]   (writes next to this file)
 """
 import ast
 import io
@@ -695,6 +695,47 @@ def make_counts_by_barcode_cases(tmpdir):
     return cases
 
 
+# --------------------------------------------------------------------------- cell-caller mixture fit
+def reference_cell_caller():
+    """The two-negative-binomial fit of DETECT_CELL_BARCODES (cell_calling/detect_cell_barcodes/__init__.py:84-201),
+    exec'd with the reference's own analysis.em_fitting and scipy.stats."""
+    from collections import namedtuple
+    from scipy import stats
+    sys.path.insert(0, os.path.join(REF, "lib/python"))
+    from analysis.em_fitting import weighted_mean, MLE_dispersion
+    ns = {"np": np, "stats": stats, "weighted_mean": weighted_mean, "MLE_dispersion": MLE_dispersion,
+          "MixedModelParams": namedtuple("MixedModelParams", ["mu_noise", "alpha_noise", "mu_signal", "alpha_signal", "frac_noise"]),
+          "print": lambda *a, **k: None}
+    load_reference_module("mro/atac/stages/processing/cell_calling/detect_cell_barcodes/__init__.py", ns,
+                          keep_funcs={"calculate_probability_distribution", "weighted_parameter_estimates", "estimate_threshold",
+                                      "simple_threshold_estimate", "normalize_parameters", "estimate_parameters"})
+    return ns
+
+
+def make_cell_em_cases():
+    ns = reference_cell_caller()
+    cases = []
+    rng = np.random.default_rng(123)
+
+    def nb(mu, alpha, n):
+        r = 1.0 / alpha
+        return rng.negative_binomial(r, r / (r + mu), size=n)
+
+    shapes = [("pbmc_like", (40, 2.0, 60000), (9000, 0.25, 1200)), ("low_depth", (8, 1.5, 30000), (700, 0.4, 400)),
+              ("few_cells", (25, 3.0, 80000), (15000, 0.15, 60)), ("overlapping", (120, 1.0, 20000), (900, 0.8, 3000))]
+    for name, noise, signal in shapes:
+        counts = np.concatenate((nb(*noise), nb(*signal)))
+        counts = counts[counts > 0]
+        cd = Counter(int(c) for c in counts)
+        t0 = time.time()
+        simple = ns["simple_threshold_estimate"](cd)
+        params = ns["estimate_parameters"](cd)
+        thr = ns["estimate_threshold"](params, 20)
+        cases.append(dict(name=name, values=sorted(cd), weights=[cd[k] for k in sorted(cd)], simple_threshold=int(simple),
+                          params=[float(x) for x in params], threshold=int(thr), seconds=round(time.time() - t0, 2)))
+    return cases
+
+
 def main():
     only = set(sys.argv[1:])
     with tempfile.TemporaryDirectory() as tmpdir:
@@ -713,6 +754,9 @@ def main():
         if not only or "counts_by_barcode" in only:
             with open(os.path.join(HERE, "counts_by_barcode.json"), "w") as f:
                 json.dump(make_counts_by_barcode_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "cell_em" in only:
+            with open(os.path.join(HERE, "cell_em.json"), "w") as f:
+                json.dump(make_cell_em_cases(), f, separators=(",", ":"))
         if not only or "em" in only:
             with open(os.path.join(HERE, "em.json"), "w") as f:
                 json.dump(make_em_cases(), f, separators=(",", ":"))

@@ -253,3 +253,19 @@ def test_get_counts_by_barcode_restatement_matches_reference(case):
         ids = {bc: c["cell_id"] for bc, c in counts.items()}
         cells = [b for line in case["known_cells"].splitlines() for b in line.split(",")[1:] if b != "null"]
         assert all((ids[bc] == "None") == (bc not in cells) for bc in ids)
+
+
+CELL_EM_CASES = json.load(open(os.path.join(GOLDEN, "cell_em.json")))
+
+
+@pytest.mark.parametrize("case", CELL_EM_CASES, ids=[c["name"] for c in CELL_EM_CASES])
+def test_cell_caller_fit_restatement_matches_reference(case):
+    """oracle.cell_em (two negative binomials over fragments per barcode, DETECT_CELL_BARCODES :84-201) against the
+    reference's own functions run on the same histograms: initial threshold and final threshold equal, parameters
+    to 1e-9 relative (same arithmetic, same scipy)."""
+    from oracle import cell_em
+    cd = dict(zip(case["values"], case["weights"]))
+    assert int(cell_em.simple_threshold_estimate(cd)) == case["simple_threshold"]
+    params = cell_em.estimate_parameters(cd)
+    assert np.allclose(np.array(params), np.array(case["params"]), rtol=1e-9, atol=0)
+    assert int(cell_em.estimate_threshold(params, 20)) == case["threshold"]
