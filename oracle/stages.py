@@ -541,3 +541,30 @@ def get_counts_by_barcode(tracks, peaks_text, fragments, species_list, species_o
         if overlaps(c, start, stop, peaks):
             cb["peak_region_fragments"] += 1
     return read_count, counts, tss_relpos, ctcf_relpos
+
+
+# --------------------------------------------------------------------------- #
+# REPORT_INSERT_SIZES (one more scan of the fragments; oracle ahead of the kernel)
+# --------------------------------------------------------------------------- #
+MAX_INSERT_SIZE = 1000                      # stages/metrics/report_insert_sizes/__init__.py:32
+
+
+def insert_size_table(barcodes, fragments, primary, exclude_non_nuclear):
+    """REPORT_INSERT_SIZES.main for one barcode chunk (stages/metrics/report_insert_sizes/__init__.py:74-113).
+    -> (rows in the order of `barcodes`: {barcode: int64[1001]} with column n - 1 = fragments of size n for n = 1..1000
+    and column 1000 = fragments longer than 1000, and total int64[1000]).  Fragments of size 0 are counted under "0" by the
+    reference and never written: they appear nowhere."""
+    index = OrderedDict((bc, k) for k, bc in enumerate(barcodes))
+    table = np.zeros((len(index), MAX_INSERT_SIZE + 1), dtype=np.int64)
+    primary = set(primary)
+    for contig, start, stop, barcode, _dup in fragments:
+        if barcode not in index:
+            continue
+        if exclude_non_nuclear and contig not in primary:
+            continue
+        size = stop - start
+        if size > MAX_INSERT_SIZE:
+            table[index[barcode], MAX_INSERT_SIZE] += 1
+        elif size >= 1:
+            table[index[barcode], size - 1] += 1
+    return OrderedDict((bc, table[k]) for bc, k in index.items()), table[:, :MAX_INSERT_SIZE].sum(axis=0)

@@ -29,7 +29,7 @@ REMOVE_LOW_TARGETING_BARCODES.main (cell_calling/remove_low_targeting_barcodes/_
 get_counts_by_barcode (lib/python/tools/io.py:429-555), exec'd with the reference's own Region / Regions
 (lib/python/tools/regions.py).
 
-Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting|counts_by_barcode|cell_em ...]   (writes next to this file)
+Usage: python tests/golden/make_golden.py [cut_sites|matrix|em|filter|low_targeting|counts_by_barcode|cell_em|insert_sizes ...]   (writes next to this file)
 """
 import ast
 import io
@@ -736,6 +736,63 @@ def make_cell_em_cases():
     return cases
 
 
+# --------------------------------------------------------------------------- REPORT_INSERT_SIZES.main (another scan of the fragments)
+def run_report_insert_sizes_main(barcodes, frag_rows, primary, exclude_non_nuclear, tmpdir):
+    """reference REPORT_INSERT_SIZES.main for one barcode chunk (stages/metrics/report_insert_sizes/__init__.py:74-113)."""
+    FakeRefMgr.primary = list(primary)
+
+    def open_fragment_file(filename):
+        for r in frag_rows:
+            yield r
+
+    ns = {"np": np, "Counter": Counter, "OrderedDict": OrderedDict, "ReferenceManager": FakeRefMgr, "open_fragment_file": open_fragment_file,
+          "json": json, "martian": None, "utils": None, "combine_csv": None, "signal": None, "stats": None}
+    src_path = "mro/atac/stages/metrics/report_insert_sizes/__init__.py"
+    load_reference_module(src_path, ns, keep_funcs={"main"})
+    ns["MAX_INSERT_SIZE"] = 1000
+    ns["GT_MAX_INSERT_SIZE"] = ">1000"
+    bcf = os.path.join(tmpdir, "barcodes_ris.txt")
+    with open(bcf, "w") as f:
+        f.write("\n".join(barcodes))
+    args = Record(barcodes=bcf, fragments="frag.tsv.gz", exclude_non_nuclear=exclude_non_nuclear, reference_path="ref")
+    outs = Record(insert_sizes=os.path.join(tmpdir, "is.csv"), insert_summary=None, total=os.path.join(tmpdir, "total.csv"))
+    src = open(os.path.join(REF, src_path)).read()
+    assert ".iterkeys()" in src           # one more py2 token on this path, mapped below
+    ns["OrderedDict"] = type("OrderedDictPy2", (OrderedDict,), {"iterkeys": lambda self: iter(self.keys())})
+    ns["main"](args, outs)
+    if outs.insert_sizes is None:
+        return None
+    rows = open(outs.insert_sizes).read().split("\n")
+    table = {}
+    for line in rows[1:]:
+        if line:
+            f = line.split(",")
+            nz = {str(i + 1): int(v) for i, v in enumerate(f[1:1001]) if int(v)}
+            if int(f[1001]):
+                nz[">1000"] = int(f[1001])
+            table[f[0]] = nz
+    return dict(header_ok=rows[0] == ",".join(["Barcode"] + [str(n) for n in range(1, 1001)] + [">1000"]),
+                row_order=[line.split(",")[0] for line in rows[1:] if line], table=table,
+                total=[int(x) for x in np.genfromtxt(outs.total, "float64").tolist()])
+
+
+def make_insert_size_cases(tmpdir):
+    rng = np.random.default_rng(55)
+    cases = []
+    bcs = ["".join(rng.choice(list("ACGT"), size=16)) + "-1" for _ in range(25)]
+    frags = []
+    for _ in range(4000):
+        c = ["chr1", "chr2", "chrM"][int(rng.integers(0, 3))]
+        a = int(rng.integers(0, 100000))
+        ln = int(rng.choice([0, 1, 37, 147, 999, 1000, 1001, 1500])) if rng.random() < 0.1 else int(rng.integers(1, 1200))
+        frags.append((c, a, a + ln, bcs[int(rng.integers(0, len(bcs)))], 1))
+    frags.sort()
+    for name, chunk, excl in (("all_contigs", bcs[:18], False), ("nuclear_only", bcs[:18], True), ("absent_barcodes", bcs[20:] + ["TTTTTTTTTTTTTTTT-1"], True)):
+        got = run_report_insert_sizes_main(chunk, frags, ["chr1", "chr2"], excl, tmpdir)
+        cases.append(dict(name=name, barcodes=chunk, primary=["chr1", "chr2"], exclude_non_nuclear=excl, expect=got))
+    return dict(fragments=[list(r) for r in frags], cases=cases)       # the three cases share the fragments
+
+
 def main():
     only = set(sys.argv[1:])
     with tempfile.TemporaryDirectory() as tmpdir:
@@ -757,6 +814,9 @@ def main():
         if not only or "cell_em" in only:
             with open(os.path.join(HERE, "cell_em.json"), "w") as f:
                 json.dump(make_cell_em_cases(), f, separators=(",", ":"))
+        if not only or "insert_sizes" in only:
+            with open(os.path.join(HERE, "insert_sizes.json"), "w") as f:
+                json.dump(make_insert_size_cases(tmpdir), f, separators=(",", ":"))
         if not only or "em" in only:
             with open(os.path.join(HERE, "em.json"), "w") as f:
                 json.dump(make_em_cases(), f, separators=(",", ":"))

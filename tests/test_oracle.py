@@ -269,3 +269,22 @@ def test_cell_caller_fit_restatement_matches_reference(case):
     params = cell_em.estimate_parameters(cd)
     assert np.allclose(np.array(params), np.array(case["params"]), rtol=1e-9, atol=0)
     assert int(cell_em.estimate_threshold(params, 20)) == case["threshold"]
+
+
+INSERT_SIZES = json.load(open(os.path.join(GOLDEN, "insert_sizes.json")))
+
+
+@pytest.mark.parametrize("case", INSERT_SIZES["cases"], ids=[c["name"] for c in INSERT_SIZES["cases"]])
+def test_insert_size_table_restatement_matches_reference(case):
+    """oracle.stages.insert_size_table against REPORT_INSERT_SIZES.main run by make_golden.py: per-barcode size histogram
+    (1..1000, >1000; size 0 dropped), row order = barcode chunk order, totals."""
+    rows, total = stages.insert_size_table(case["barcodes"], [tuple(r) for r in INSERT_SIZES["fragments"]], case["primary"],
+                                           case["exclude_non_nuclear"])
+    want = case["expect"]
+    assert want["header_ok"] and list(rows) == want["row_order"]
+    for bc, hist in rows.items():
+        got = {str(n + 1): int(v) for n, v in enumerate(hist[:1000]) if v}
+        if hist[1000]:
+            got[">1000"] = int(hist[1000])
+        assert got == want["table"][bc]
+    assert total.tolist() == want["total"]
