@@ -50,6 +50,65 @@ def test_py2_set_order_matches_oracle():
     assert [small[i] for i in _ffi.py2_set_order(small)] == ["a", "c", "b", "d"]
 
 
+def _parallel_set_rebuild(hashes):
+    """numpy model of csrc/py2order.cu: every table of the CPython-2.7 set's life is the result of inserting a known
+    sequence of keys one after the other, and that result is the fixed point of `slot <- min(sequence position asking for
+    it)` with losers moving on along their probe sequence -- reached here in synchronous rounds, as the kernel does with
+    atomicMin."""
+    n = len(hashes)
+    M64 = (1 << 64) - 1
+    h = [int(x) & M64 for x in hashes]
+    seq = []                                 # keys in slot order of the previous table
+    size, fill, used = 8, 0, 0
+    while True:
+        room = (2 * size + 2) // 3
+        fresh = min(n - used, room - fill if room > fill else (1 if n > used else 0))
+        keys = seq + list(range(used, used + fresh))
+        m = len(keys)
+        mask = size - 1
+        i = [h[k] & mask for k in keys]
+        pert = [h[k] for k in keys]
+        cand = [x & mask for x in i]
+        table = [m] * size                   # m = empty
+        changed = True
+        while changed:
+            changed = False
+            for t in range(m):               # "parallel": every position asks for its candidate slot
+                if table[cand[t]] > t:
+                    table[cand[t]] = t
+            for t in range(m):               # losers move one probe further
+                if table[cand[t]] != t:
+                    i[t] = (i[t] * 5 + pert[t] + 1) & M64
+                    pert[t] >>= 5
+                    cand[t] = i[t] & mask
+                    changed = True
+        seq = [keys[t] for t in table if t < m]
+        fill += fresh
+        used += fresh
+        grow = fill * 3 >= size * 2
+        if used == n and not grow:
+            return seq
+        if grow:
+            minused = used * 2 if used > 50000 else used * 4
+            size = 8
+            while size <= minused:
+                size <<= 1
+            fill = used
+
+
+def test_parallel_set_rebuild_is_the_sequential_insertion():
+    """The algorithm behind cratac_py2_set_order_hashes_device, modelled on the host (the CUDA kernels themselves are
+    checked on the GPU): the fixed point of the parallel rounds equals one-by-one insertion for random hashes, long
+    probe chains and clustered home slots, through several table growths."""
+    rng = np.random.default_rng(12)
+    cases = [rng.integers(-2 ** 62, 2 ** 62, size=n, dtype=np.int64) for n in (1, 5, 6, 21, 22, 90, 1500)]
+    cases.append((rng.integers(0, 8, size=600, dtype=np.int64) << 20) + np.arange(600, dtype=np.int64) * (1 << 40))
+    cases.append(np.arange(900, dtype=np.int64) * 8)
+    for hs in cases:
+        want = _ffi.py2_set_order_hashes(hs).tolist()
+        assert _parallel_set_rebuild(hs.tolist()) == want, hs.size
+
+
 def test_inflate_bgzf_and_gzip(tmp_path):
     import gzip
     frags = synth.generate(synth.GRCH38[:2], 30000, 20, 50, seed=7)
