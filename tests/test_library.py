@@ -109,6 +109,33 @@ def test_parallel_set_rebuild_is_the_sequential_insertion():
         assert _parallel_set_rebuild(hs.tolist()) == want, hs.size
 
 
+def _warp_upper_bound(arr, lo, hi, key):
+    """Lane-by-lane model of warp_upper_bound (csrc/matrix.cu): 32 probes per round, ballot, narrow."""
+    while hi - lo > 32:
+        step = (hi - lo) // 33 + 1
+        probes = [lo + step * (lane + 1) - 1 for lane in range(32)]
+        gt = [(key < arr[p]) if p < hi else True for p in probes]
+        if not any(gt):
+            lo = lo + step * 32
+            continue
+        j = gt.index(True)
+        lo, hi = (lo + step * j if j > 0 else lo), (probes[j] if probes[j] < hi else hi)
+    gt = [(key < arr[lo + lane]) if lo + lane < hi else True for lane in range(32)]
+    return lo + gt.index(True) if any(gt) else hi
+
+
+def test_warp_wide_search_model_equals_bisect():
+    import bisect
+    rng = np.random.default_rng(4)
+    for _ in range(4000):
+        n = int(rng.choice([0, 1, 5, 31, 32, 33, 34, 64, 65, 100, 1000, 1089, 1090, 5000, 40000]))
+        arr = np.sort(rng.integers(0, max(1, n * int(rng.choice([1, 3, 50]))), size=n)).tolist()
+        lo = int(rng.integers(0, n + 1))
+        hi = int(rng.integers(lo, n + 1))
+        key = int(rng.integers(-2, (arr[-1] if n else 0) + 3))
+        assert _warp_upper_bound(arr, lo, hi, key) == bisect.bisect_right(arr, key, lo, hi)
+
+
 def test_inflate_bgzf_and_gzip(tmp_path):
     import gzip
     frags = synth.generate(synth.GRCH38[:2], 30000, 20, 50, seed=7)
