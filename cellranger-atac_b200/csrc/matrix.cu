@@ -3,12 +3,14 @@
 // (tenkit/lib/python/tenkit/regions.py:136-145), Counter[(barcode, peak)] += 1, COO -> CSC) for ALL
 // barcodes in one pass instead of 30 barcode chunks that each re-read the file.
 //
-//   K6a  count   per fragment: upper_bound(peak starts, pos) - 1, half-open containment test, for
-//                pos in (start, stop) -- stop used as is, dup_count ignored; ONE record per (fragment, peak)
-//                (a fragment with both ends in the same peak is one record worth 2); records per barcode (REDG).
-//   scan         records per barcode -> segment offsets.
-//   K6b  scatter same search, record = row << 1 | both-ends written into the barcode's segment.
-//   K7   reduce  per barcode segment: sort the records (one warp for <= 1024, a CTA for <= 4096: bitonic in
+//   sizes        per-barcode segment capacity = 2 x the barcode's fragments (counted by the decoder, or by
+//                k_count_frags for fragments handed over as arrays); scan -> segment offsets.  No count pass.
+//   K6   overlap per fragment: upper_bound(peak starts, pos) - 1, half-open containment test, for pos in
+//                (start, stop) -- stop used as is, dup_count ignored; ONE record per (fragment, peak)
+//                (row << 1 | both-ends: a fragment with both ends in the same peak is one record worth 2),
+//                appended to the barcode's segment through a per-barcode cursor.  Tiles of 2048 start-sorted
+//                fragments search a peak window staged in shared memory (found by a warp-wide 33-ary search).
+//   K7   reduce  per barcode segment [0, cursor): sort the records (one warp for <= 1024, a CTA for <= 4096: bitonic in
 //                shared memory; range-partitioned counting in shared memory for longer ones) and run-length
 //                reduce to (row, count).
 //   K8   build   indptr = scan of distinct counts in column order; copy (row, count) segments to

@@ -12,6 +12,8 @@
 // per CTA); mode PEAKS emits the boundaries of the runs W >= threshold into CTA-private regions, tile by tile
 // (k_gather_events restores genome order from the per-tile counts: no CTA waits for another) plus what the zero-gap rule of
 // write_chrom_bedgraph (count_cut_sites/__init__.py:36-37) needs; mode DUMP writes W (tests, bedgraph).
+// Mode HIST also leaves, per tile, an upper bound of W and the first / last non-zero window: mode PEAKS skips the
+// tiles whose bound is below the threshold (most of the genome) without staging them.
 // HBM traffic: 8 B per fragment (start, end) x (1 + halo overhead); everything per-base is on chip.
 #include <algorithm>
 
@@ -22,7 +24,7 @@ namespace cratac {
 constexpr int PU_THREADS = 256;
 constexpr int PU_CTAS_PER_SM = 4;
 constexpr int PU_CHUNK = 44;                        // 4 x odd: thread-chunked 128-bit shared accesses are bank-conflict free
-constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entries (22528)
+constexpr int PU_N = PU_THREADS * PU_CHUNK;         // shared count array entries (11264)
 constexpr int PU_PAD = 64;                          // slack for vector over-reads past the last window
 constexpr int PU_HALO_LO = HALF_WINDOW + 2;         // 202
 constexpr int PU_HALO_HI = HALF_WINDOW + 1;         // 201 (positions up to b + 200)
