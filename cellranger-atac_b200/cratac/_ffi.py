@@ -93,6 +93,8 @@ SIGNATURES = {
     "cratac_py2_set_order_hashes_device": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_uint64]),
     "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
     "cratac_inflate_range": (c_int, [c_cp, c_int, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_i64, P(c_i64)]),
+    "cratac_inflate_stats": (c_int, [P(c_i64), P(c_i64), c_int]),
+    "cratac_inflate_mode": (c_int, [c_int]),
     "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
 }
 
@@ -488,6 +490,18 @@ def inflate_file(path, threads=None):
     out = np.empty(max(n.value, 1), dtype=np.uint8)
     check(lib.cratac_inflate_file(path.encode(), threads, _ptr(out), out.size, ctypes.byref(n)))
     return out[:n.value]
+
+
+def inflate_stats(reset=False):
+    """-> (BGZF blocks decoded by the library's own DEFLATE decoder, blocks handed to zlib) since the last reset."""
+    a, b = c_i64(), c_i64()
+    check(load().cratac_inflate_stats(ctypes.byref(a), ctypes.byref(b), 1 if reset else 0))
+    return a.value, b.value
+
+
+def inflate_mode(mode):
+    """0: zlib only; 1 (default): own decoder first."""
+    check(load().cratac_inflate_mode(int(mode)))
 
 
 def inflate_range(path, voff_begin, voff_end, threads=None):

@@ -12,8 +12,8 @@ BLOCK_IN = 0xff00
 EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
-def _block(data, level):
-    comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+def _block(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
     body = comp.compress(data) + comp.flush()
     bsize = len(body) + 25
     assert bsize < 65536
@@ -22,10 +22,10 @@ def _block(data, level):
     return head + body + tail
 
 
-def compress(data, level=1):
+def compress(data, level=1, strategy=zlib.Z_DEFAULT_STRATEGY, block_in=BLOCK_IN):
     """bytes -> BGZF bytes."""
     mv = memoryview(data)
-    out = [_block(bytes(mv[i:i + BLOCK_IN]), level) for i in range(0, len(mv), BLOCK_IN)]
+    out = [_block(bytes(mv[i:i + block_in]), level, strategy) for i in range(0, len(mv), block_in)]
     out.append(EOF_BLOCK)
     return b"".join(out)
 

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 #include <zlib.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -60,6 +64,8 @@ int offset_peak_rows(Ctx* c, int64_t base);                                     
 int merge_runs_from_host(Ctx* c, int64_t n, const int32_t* chrom, const int64_t* start, const int64_t* end);   // pileup.cu
 void py2_set_order_hashes(const long long* hashes, int64_t n, std::vector<int32_t>& order);   // decode.cu
 int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_order_out);   // py2order.cu
+bool inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len, uint32_t* scratch);   // inflate.cpp
+size_t inflate_scratch_words();
 int select_columns(Ctx* c, int64_t n_sel, const int64_t* h_cols, int drop_empty);   // matrix.cu
 int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off, const int64_t* d_indices_all,
                    const int32_t* d_data_all, int64_t total_nnz);                         // matrix.cu
@@ -798,17 +804,68 @@ int cratac_encode_text_device(cratac_ctx* h, int64_t n, const int32_t* d_chrom, 
     return encode_text(c, n, d_chrom, d_start, d_end, d_bc_seq, d_dup, d_out, cap, nbytes);
 }
 
+// read-only mapping of an input file: no copy, no zero-filled staging buffer, pages come in as the worker threads touch them
+struct MappedFile {
+    const unsigned char* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    bool open_path(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return false;
+        n = (size_t)st.st_size;
+        if (n == 0) return true;
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        p = static_cast<const unsigned char*>(m);
+        madvise(m, n, MADV_WILLNEED);
+        return true;
+    }
+    ~MappedFile() {
+        if (p) munmap(const_cast<unsigned char*>(p), n);
+        if (fd >= 0) ::close(fd);
+    }
+};
+
+// block decoder statistics / selection (process-wide): blocks decoded by inflate.cpp, blocks handed to zlib
+static std::atomic<long long> g_inflate_fast(0), g_inflate_zlib(0);
+static std::atomic<int> g_inflate_mode(1);          // 1: own decoder first, zlib when it declines; 0: zlib only
+
+// one BGZF block: raw DEFLATE `in` -> exactly `isize` bytes at `dst`
+static bool inflate_block(z_stream* zs, uint32_t* scratch, const unsigned char* in, size_t csize, unsigned char* dst, uint32_t isize) {
+    if (g_inflate_mode.load(std::memory_order_relaxed) && inflate_raw(in, csize, dst, isize, scratch)) {
+        g_inflate_fast.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
+    g_inflate_zlib.fetch_add(1, std::memory_order_relaxed);
+    if (isize == 0 && csize == 0) return true;
+    inflateReset(zs);
+    zs->next_in = const_cast<unsigned char*>(in); zs->avail_in = (uInt)csize;
+    zs->next_out = dst; zs->avail_out = isize;
+    const int rc = inflate(zs, Z_FINISH);
+    return rc == Z_STREAM_END && zs->avail_out == 0;
+}
+
+int cratac_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks, int reset) {
+    if (fast_blocks) *fast_blocks = g_inflate_fast.load();
+    if (zlib_blocks) *zlib_blocks = g_inflate_zlib.load();
+    if (reset) { g_inflate_fast = 0; g_inflate_zlib = 0; }
+    return CRATAC_OK;
+}
+
+int cratac_inflate_mode(int mode) {
+    g_inflate_mode = mode ? 1 : 0;
+    return CRATAC_OK;
+}
+
 // BGZF (or plain multi-member gzip) inflate.  BGZF blocks carry their compressed size in the 'BC' extra
 // field and their inflated size in the trailer, so the blocks inflate independently on `threads` threads.
 int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, int64_t* nbytes) {
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
-    fseek(f, 0, SEEK_END);
-    long fsz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<unsigned char> buf((size_t)fsz);
-    if (fsz > 0 && fread(buf.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); set_error("short read on %s", path); return CRATAC_ERR_IO; }
-    fclose(f);
+    MappedFile mf;
+    if (!mf.open_path(path)) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
+    const long fsz = (long)mf.n;
+    const unsigned char* buf = mf.p;
     struct Blk { size_t off, csize; int64_t out_off; uint32_t isize; };
     std::vector<Blk> blocks;
     size_t p = 0;
@@ -843,15 +900,12 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
             z_stream zs;
             memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
+            std::vector<uint32_t> scratch(inflate_scratch_words());
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= blocks.size()) break;
                 const Blk& k = blocks[i];
-                inflateReset(&zs);
-                zs.next_in = &buf[k.off]; zs.avail_in = (uInt)k.csize;
-                zs.next_out = reinterpret_cast<unsigned char*>(out) + k.out_off; zs.avail_out = k.isize;
-                int rc = inflate(&zs, Z_FINISH);
-                if (rc != Z_STREAM_END || zs.avail_out != 0) { failed = 1; break; }
+                if (!inflate_block(&zs, scratch.data(), &buf[k.off], k.csize, reinterpret_cast<unsigned char*>(out) + k.out_off, k.isize)) { failed = 1; break; }
             }
             inflateEnd(&zs);
         };
@@ -868,7 +922,7 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, 15 + 16) != Z_OK) { set_error("zlib init failed"); return CRATAC_ERR_IO; }
         std::vector<unsigned char> scratch(1 << 20);
-        zs.next_in = buf.data(); zs.avail_in = (uInt)fsz;
+        zs.next_in = const_cast<unsigned char*>(buf); zs.avail_in = (uInt)fsz;
         int64_t produced = 0;
         for (;;) {
             bool counting = (cap == 0 || !out);
@@ -893,7 +947,7 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
     *nbytes = fsz;
     if (cap == 0 || !out) return CRATAC_OK;
     if (cap < fsz) { set_error("buffer too small"); return CRATAC_ERR_ARG; }
-    memcpy(out, buf.data(), (size_t)fsz);
+    memcpy(out, buf, (size_t)fsz);
     return CRATAC_OK;
 }
 
@@ -906,35 +960,32 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
     if (voff_end <= voff_begin) return CRATAC_OK;
     const uint64_t c_begin = voff_begin >> 16, c_end = voff_end >> 16;
     const uint32_t u_begin = (uint32_t)(voff_begin & 0xFFFF), u_end = (uint32_t)(voff_end & 0xFFFF);
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
-    fseek(f, 0, SEEK_END);
-    const uint64_t fsz = (uint64_t)ftell(f);
-    if (c_begin >= fsz) { fclose(f); set_error("virtual offset beyond the end of %s", path); return CRATAC_ERR_ARG; }
+    MappedFile mf;
+    if (!mf.open_path(path)) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
+    const uint64_t fsz = (uint64_t)mf.n;
+    if (c_begin >= fsz) { set_error("virtual offset beyond the end of %s", path); return CRATAC_ERR_ARG; }
     // the last block is needed only when some of its bytes are inside the range
     const uint64_t read_end = std::min<uint64_t>(fsz, u_end > 0 ? c_end + 65536 : c_end);
-    std::vector<unsigned char> buf((size_t)(read_end - c_begin));
-    fseek(f, (long)c_begin, SEEK_SET);
-    if (!buf.empty() && fread(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); set_error("short read on %s", path); return CRATAC_ERR_IO; }
-    fclose(f);
+    const unsigned char* buf = mf.p + c_begin;                    // the blocks of the range, read through the mapping
+    const size_t buf_size = (size_t)(read_end - c_begin);
     struct Blk { size_t off, csize; int64_t out_off; uint32_t isize, lo, hi; };   // [lo, hi) of the inflated block is kept
     std::vector<Blk> blocks;
     size_t p = 0;
     int64_t total = 0;
     while (c_begin + p < c_end || (c_begin + p == c_end && u_end > 0)) {
-        if (p + 18 > buf.size()) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
+        if (p + 18 > buf_size) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
         const unsigned char* b = &buf[p];
         if (!(b[0] == 31 && b[1] == 139 && b[2] == 8 && (b[3] & 4))) { set_error("no BGZF block at offset %llu of %s", (unsigned long long)(c_begin + p), path); return CRATAC_ERR_IO; }
         const unsigned xlen = b[10] | (b[11] << 8);
         size_t q = p + 12;
         const size_t xend = q + xlen;
         long bsize = -1;
-        while (q + 4 <= xend && xend <= buf.size()) {
+        while (q + 4 <= xend && xend <= buf_size) {
             const unsigned slen = buf[q + 2] | (buf[q + 3] << 8);
             if (buf[q] == 'B' && buf[q + 1] == 'C' && slen == 2) bsize = (buf[q + 4] | (buf[q + 5] << 8)) + 1;
             q += 4 + slen;
         }
-        if (bsize < 0 || p + (size_t)bsize > buf.size()) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
+        if (bsize < 0 || p + (size_t)bsize > buf_size) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
         uint32_t isize;
         memcpy(&isize, &buf[p + bsize - 4], 4);
         const uint64_t at = c_begin + p;
@@ -955,17 +1006,15 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
         std::vector<unsigned char> part;
+        std::vector<uint32_t> scratch(inflate_scratch_words());
         for (;;) {
             const size_t i = next.fetch_add(1);
             if (i >= blocks.size()) break;
             const Blk& k = blocks[i];
             const bool whole = k.lo == 0 && k.hi == k.isize;
             if (!whole) part.resize(k.isize);
-            inflateReset(&zs);
-            zs.next_in = &buf[k.off]; zs.avail_in = (uInt)k.csize;
-            zs.next_out = whole ? reinterpret_cast<unsigned char*>(out) + k.out_off : part.data(); zs.avail_out = k.isize;
-            const int rc = k.isize == 0 && k.csize == 0 ? Z_STREAM_END : inflate(&zs, Z_FINISH);
-            if (rc != Z_STREAM_END || zs.avail_out != 0) { failed = 1; break; }
+            unsigned char* dst = whole ? reinterpret_cast<unsigned char*>(out) + k.out_off : part.data();
+            if (!inflate_block(&zs, scratch.data(), &buf[k.off], k.csize, dst, k.isize)) { failed = 1; break; }
             if (!whole && k.hi > k.lo) memcpy(out + k.out_off, part.data() + k.lo, k.hi - k.lo);
         }
         inflateEnd(&zs);

@@ -209,6 +209,10 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
  * reads instead of the whole file (replaces pysam.TabixFile(...).fetch(contig), lib/python/tools/io.py:86-99).
  * cap = 0 returns the inflated size. */
 int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uint64_t voff_end, char* out, int64_t cap, int64_t* nbytes);
+/* BGZF blocks are decoded by the library's own DEFLATE decoder (csrc/inflate.cpp); a block it declines goes to zlib.
+ * Process-wide counters of both, and a switch for measurements (mode 0: zlib only, 1: own decoder first, the default). */
+int cratac_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks, int reset);
+int cratac_inflate_mode(int mode);
 /* synthetic text encoder (SoA on the device -> fragments.tsv text on the device), used by bench/tests
  * to build large inputs without a host formatting loop.  bc_seq = 2-bit packed 16-mers. */
 int cratac_encode_text_device(cratac_ctx* ctx, int64_t n, const int32_t* d_chrom, const int32_t* d_start,

@@ -154,6 +154,91 @@ def test_inflate_bgzf_and_gzip(tmp_path):
     assert _ffi.inflate_file(p3).tobytes() == text
 
 
+def test_own_deflate_decoder_against_zlib(tmp_path):
+    """csrc/inflate.cpp decodes every valid BGZF block itself (no block handed to zlib) and reproduces zlib's output:
+    stored, fixed-Huffman and dynamic blocks, long codes (second-level tables), matches at every small distance, runs,
+    incompressible data, block sizes from 0 to the BGZF maximum."""
+    import zlib
+    rng = np.random.default_rng(8)
+    text = synth.to_text(synth.generate(synth.GRCH38[:2], 20000, 20, 50, seed=17))
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(2, 12)), dtype=np.uint8)) for _ in range(400)]
+    datas = {
+        "empty": b"", "one_byte": b"x", "fragments_text": text,
+        "random_bytes": rng.integers(0, 256, size=300000, dtype=np.uint8).tobytes(),
+        "zeros": bytes(200000), "run_then_noise": b"A" * 70000 + rng.integers(0, 256, size=5000, dtype=np.uint8).tobytes(),
+        "small_periods": b"".join((bytes(range(65, 65 + k)) * 3000)[:9000] for k in range(1, 12)),
+        "skewed_alphabet": bytes(rng.choice(np.arange(256, dtype=np.uint8), size=250000,
+                                             p=(lambda w: w / w.sum())(1.0 / np.arange(1, 257) ** 2.2)).tolist()),
+        "dictionary_words": b" ".join(words[int(i)] for i in rng.integers(0, len(words), size=60000)),
+        "exact_block": text[:bgzf.BLOCK_IN], "block_plus_one": text[:bgzf.BLOCK_IN + 1],
+    }
+    settings = [(0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (9, zlib.Z_FILTERED)]
+    _ffi.inflate_mode(1)
+    p = str(tmp_path / "x.gz")
+    for name, data in datas.items():
+        for level, strategy in settings:
+            for block_in in (bgzf.BLOCK_IN, 700):
+                if block_in == 700 and len(data) > 40000:
+                    continue
+                with open(p, "wb") as f:
+                    f.write(bgzf.compress(data, level, strategy, block_in))
+                _ffi.inflate_stats(reset=True)
+                got = _ffi.inflate_file(p, threads=3).tobytes()
+                fast, slow = _ffi.inflate_stats()
+                assert got == data, (name, level, strategy, block_in)
+                assert slow == 0 and fast > 0, (name, level, strategy, block_in, fast, slow)
+    # the zlib route gives the same bytes (measurement switch)
+    with open(p, "wb") as f:
+        f.write(bgzf.compress(text, 6))
+    _ffi.inflate_mode(0)
+    _ffi.inflate_stats(reset=True)
+    assert _ffi.inflate_file(p, threads=2).tobytes() == text and _ffi.inflate_stats()[0] == 0
+    _ffi.inflate_mode(1)
+
+
+def test_corrupt_bgzf_blocks_fail_cleanly(tmp_path):
+    """Damaged payloads: the own decoder declines, zlib confirms -> an error (or, when the damage still decodes to the
+    right size, some output: BGZF's CRC is not checked here, as `gzip -dc | ...` consumers of a truncated pipe would not
+    see it either) -- never a crash or an out-of-bounds write."""
+    rng = np.random.default_rng(21)
+    text = synth.to_text(synth.generate(synth.GRCH38[:1], 6000, 10, 20, seed=3))
+    blob = bytearray(bgzf.compress(text, 6))
+    p = str(tmp_path / "bad.gz")
+    outcomes = {"error": 0, "decoded": 0}
+    for _ in range(300):
+        bad = bytearray(blob)
+        for _k in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(18, len(bad) - 40))            # keep the first header and the EOF block intact
+            bad[pos] ^= int(rng.integers(1, 256))
+        with open(p, "wb") as f:
+            f.write(bad)
+        try:
+            _ffi.inflate_file(p, threads=2)
+            outcomes["decoded"] += 1
+        except _ffi.CratacError:
+            outcomes["error"] += 1
+    assert outcomes["error"] > 100
+
+
+def test_own_deflate_decoder_under_sanitizers(tmp_path):
+    """The decoder on damaged / truncated / mis-sized blocks, compiled with -fsanitize=address,undefined."""
+    exe = str(tmp_path / "inflate_fuzz")
+    src = [os.path.join(ROOT, "tests", "inflate_fuzz.cpp"), os.path.join(ROOT, "cellranger-atac_b200", "csrc", "inflate.cpp")]
+    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe] + src + ["-lpthread"],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("no sanitizer runtime in this toolchain")
+    assert build.returncode == 0, build.stderr
+    text = synth.to_text(synth.generate(synth.GRCH38[:2], 30000, 20, 50, seed=23))
+    p = str(tmp_path / "f.gz")
+    bgzf.write(p, text, level=6)
+    run = subprocess.run([exe, p, "6000"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-2000:]
+    ok, declined = [int(x.split("=")[1]) for x in run.stdout.split()]
+    assert ok > 1000 and declined > 1000
+
+
 def test_tabix_index_and_contig_range_inflate(tmp_path):
     """Host ingest: a rank reads only the BGZF blocks of its contig range, located through the
     tabix index (the reference fetches contig by contig through pysam.TabixFile, lib/python/tools/io.py:82-93)."""
