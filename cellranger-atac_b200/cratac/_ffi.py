@@ -93,6 +93,7 @@ SIGNATURES = {
     "cratac_py2_set_order_hashes_device": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_uint64]),
     "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
     "cratac_inflate_range": (c_int, [c_cp, c_int, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_i64, P(c_i64)]),
+    "cratac_write_mtx": (c_int, [c_cp, c_cp, c_i64, c_vp, c_vp, c_vp, c_int]),
     "cratac_inflate_stats": (c_int, [P(c_i64), P(c_i64), c_int]),
     "cratac_inflate_mode": (c_int, [c_int]),
     "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
@@ -490,6 +491,16 @@ def inflate_file(path, threads=None):
     out = np.empty(max(n.value, 1), dtype=np.uint8)
     check(lib.cratac_inflate_file(path.encode(), threads, _ptr(out), out.size, ctypes.byref(n)))
     return out[:n.value]
+
+
+def write_mtx(path, header, indptr, indices, data, threads=None):
+    """Matrix Market file: `header` text, then one "row col value" line (1-based) per stored entry, column by column."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    nnz = int(indptr[-1]) if indptr.size else 0
+    indices = np.ascontiguousarray(indices[:nnz], dtype=np.int64)
+    data = np.ascontiguousarray(data[:nnz], dtype=np.int32)
+    threads = threads or (os.cpu_count() or 1)
+    check(load().cratac_write_mtx(path.encode(), header.encode("ascii"), max(indptr.size - 1, 0), _ptr(indptr), _ptr(indices), _ptr(data), threads))
 
 
 def inflate_stats(reset=False):

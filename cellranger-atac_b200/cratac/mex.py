@@ -6,6 +6,8 @@ import os
 
 import numpy as np
 
+from . import _ffi
+
 
 def save_mex(base_dir, indptr, indices, data, n_features, barcodes, feature_ids, sw_version):
     if not os.path.isdir(base_dir):
@@ -13,13 +15,10 @@ def save_mex(base_dir, indptr, indices, data, n_features, barcodes, feature_ids,
     n_bc = len(barcodes)
     nnz = int(indptr[-1]) if len(indptr) else 0
     meta = json.dumps({"software_version": sw_version, "format_version": 2})
-    cols = np.repeat(np.arange(1, n_bc + 1, dtype=np.int64), np.diff(indptr))       # CSC -> COO order
-    with open(os.path.join(base_dir, "matrix.mtx"), "wb") as f:
-        f.write(b"%%MatrixMarket matrix coordinate integer general\n")
-        f.write(("%%metadata_json: %s\n" % meta).encode("ascii"))
-        f.write(("%i %i %i\n" % (n_features, n_bc, nnz)).encode("ascii"))
-        if nnz:
-            np.savetxt(f, np.stack([np.asarray(indices[:nnz]) + 1, cols, np.asarray(data[:nnz], dtype=np.int64)], axis=1), fmt="%i %i %i")
+    header = ("%%MatrixMarket matrix coordinate integer general\n" + "%%metadata_json: %s\n" % meta + "%i %i %i\n" % (n_features, n_bc, nnz))
+    # the entries ("row col value", 1-based, CSC -> COO order) are formatted natively on all cores (cratac_write_mtx)
+    _ffi.write_mtx(os.path.join(base_dir, "matrix.mtx"), header, np.asarray(indptr, dtype=np.int64) if len(indptr) else np.zeros(1, dtype=np.int64),
+                   indices, data)
     with open(os.path.join(base_dir, "peaks.bed"), "w") as f:
         for name in feature_ids:
             contig, span = name.split(":")

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <thread>
 
 #include "common.cuh"
@@ -1027,5 +1028,70 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
     return CRATAC_OK;
 }
 
+
+// Matrix Market body: "row col value\n" (1-based) for every stored entry, column by column -- the per-entry Python loop
+// of CountMatrix.save_mex (cellranger/matrix.py:812-814).  `header` (the three header lines, already formatted) is written
+// first.  Columns are cut into chunks of about 1 M entries; `threads` chunks are formatted at a time and written in order.
+int cratac_write_mtx(const char* path, const char* header, int64_t n_cols, const int64_t* indptr, const int64_t* indices,
+                     const int32_t* data, int threads) {
+    if (!path || !indptr || n_cols < 0) { set_error("cratac_write_mtx: bad argument"); return CRATAC_ERR_ARG; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("cannot open %s for writing", path); return CRATAC_ERR_IO; }
+    if (header && fputs(header, f) < 0) { fclose(f); set_error("write failed on %s", path); return CRATAC_ERR_IO; }
+    if (threads < 1) threads = 1;
+    // chunk boundaries in columns
+    const int64_t target = 1 << 20;
+    std::vector<int64_t> cuts(1, 0);
+    for (int64_t j = 0; j < n_cols;) {
+        const int64_t want = indptr[j] + target;
+        int64_t k = std::upper_bound(indptr + j + 1, indptr + n_cols + 1, want) - indptr;   // first column whose END exceeds want
+        if (k > n_cols) k = n_cols;
+        if (k <= j) k = j + 1;
+        cuts.push_back(k);
+        j = k;
+    }
+    const size_t n_chunks = cuts.size() - 1;
+    auto put_uint = [](char* p, uint64_t v) -> char* {
+        char tmp[24];
+        int n = 0;
+        do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (n) *p++ = tmp[--n];
+        return p;
+    };
+    bool failed = false;
+    for (size_t wave = 0; wave < n_chunks && !failed; wave += (size_t)threads) {
+        const size_t in_wave = std::min<size_t>((size_t)threads, n_chunks - wave);
+        std::vector<std::unique_ptr<char[]>> bufs(in_wave);
+        std::vector<size_t> used(in_wave, 0);
+        auto work = [&](size_t w) {
+            const int64_t c0 = cuts[wave + w], c1 = cuts[wave + w + 1];
+            const int64_t n_ent = indptr[c1] - indptr[c0];
+            bufs[w].reset(new char[(size_t)n_ent * 44 + 16]);       // 20 + 1 + 10 + 1 + 11 + 1 bytes at most per line; not zero-filled
+            char* p = bufs[w].get();
+            for (int64_t j = c0; j < c1; j++) {
+                for (int64_t k = indptr[j]; k < indptr[j + 1]; k++) {
+                    p = put_uint(p, (uint64_t)(indices[k] + 1));
+                    *p++ = ' ';
+                    p = put_uint(p, (uint64_t)(j + 1));
+                    *p++ = ' ';
+                    int64_t v = data[k];
+                    if (v < 0) { *p++ = '-'; v = -v; }
+                    p = put_uint(p, (uint64_t)v);
+                    *p++ = '\n';
+                }
+            }
+            used[w] = (size_t)(p - bufs[w].get());
+        };
+        std::vector<std::thread> pool;
+        for (size_t w = 1; w < in_wave; w++) pool.emplace_back(work, w);
+        work(0);
+        for (auto& t : pool) t.join();
+        for (size_t w = 0; w < in_wave; w++)
+            if (used[w] && fwrite(bufs[w].get(), 1, used[w], f) != used[w]) failed = true;
+    }
+    if (fclose(f) != 0) failed = true;
+    if (failed) { set_error("write failed on %s", path); return CRATAC_ERR_IO; }
+    return CRATAC_OK;
+}
 
 }  // extern "C"

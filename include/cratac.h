@@ -211,6 +211,11 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
 int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uint64_t voff_end, char* out, int64_t cap, int64_t* nbytes);
 /* BGZF blocks are decoded by the library's own DEFLATE decoder (csrc/inflate.cpp); a block it declines goes to zlib.
  * Process-wide counters of both, and a switch for measurements (mode 0: zlib only, 1: own decoder first, the default). */
+/* Matrix Market coordinate body ("row col value" 1-based, column by column) after the caller's header lines: the per-entry
+ * loop of CountMatrix.save_mex (lib/cellranger/lib/python/cellranger/matrix.py:812-814), formatted on `threads` threads.
+ * Host arrays: indptr[n_cols + 1], indices / data [indptr[n_cols]]. */
+int cratac_write_mtx(const char* path, const char* header, int64_t n_cols, const int64_t* indptr, const int64_t* indices,
+                     const int32_t* data, int threads);
 int cratac_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks, int reset);
 int cratac_inflate_mode(int mode);
 /* synthetic text encoder (SoA on the device -> fragments.tsv text on the device), used by bench/tests

@@ -101,6 +101,35 @@ def test_mex_writer(tmp_path):
     assert open(os.path.join(d, "barcodes.tsv")).read() == "A-1\nB-1\nC-1\n"
 
 
+def test_native_mtx_writer_equals_per_entry_formatting(tmp_path):
+    """cratac_write_mtx against the per-entry "%i %i %i" formatting of CountMatrix.save_mex (cellranger/matrix.py:812-814):
+    random CSC matrices incl. empty columns, more chunks than threads, one thread."""
+    import time
+    from cratac import _ffi
+    rng = np.random.default_rng(6)
+    for n_rows, n_cols, nnz, threads in ((50, 40, 300, 3), (100000, 3000, 9_000_000, 4), (10, 0, 0, 2), (7, 5, 0, 1)):
+        per_col = np.bincount(rng.integers(0, max(n_cols, 1), size=nnz), minlength=n_cols)[:n_cols] if n_cols else np.zeros(0, dtype=np.int64)
+        indptr = np.concatenate(([0], np.cumsum(per_col))).astype(np.int64)
+        indices = rng.integers(0, n_rows, size=int(indptr[-1])).astype(np.int64)
+        data = rng.integers(1, 70000, size=int(indptr[-1])).astype(np.int32)
+        p = str(tmp_path / "m.mtx")
+        t0 = time.time()
+        _ffi.write_mtx(p, "%%header\n3 4 5\n", indptr, indices, data, threads=threads)
+        t_native = time.time() - t0
+        got = open(p, "rb").read()
+        assert got.startswith(b"%%header\n3 4 5\n")
+        body = got[len(b"%%header\n3 4 5\n"):]
+        if indptr[-1] <= 1000:
+            cols = np.repeat(np.arange(1, n_cols + 1), np.diff(indptr))
+            want = "".join("%i %i %i\n" % (r + 1, c, d) for r, c, d in zip(indices.tolist(), cols.tolist(), data.tolist()))
+            assert body == want.encode()
+        else:
+            arr = np.array(body.split(), dtype=np.int64).reshape(-1, 3)         # parse back, compare as numbers
+            cols = np.repeat(np.arange(1, n_cols + 1), np.diff(indptr))
+            assert np.array_equal(arr[:, 0], indices + 1) and np.array_equal(arr[:, 1], cols) and np.array_equal(arr[:, 2], data)
+            assert body.count(b"\n") == int(indptr[-1]) and t_native < 20
+
+
 def test_reference_manager(tmp_path):
     contigs = [("chr1", 1000), ("chr2", 500), ("chrX", 300), ("chrM", 16)]
     ref = str(tmp_path / "ref")
