@@ -107,7 +107,7 @@ def test_native_mtx_writer_equals_per_entry_formatting(tmp_path):
     import time
     from cratac import _ffi
     rng = np.random.default_rng(6)
-    for n_rows, n_cols, nnz, threads in ((50, 40, 300, 3), (100000, 3000, 9_000_000, 4), (10, 0, 0, 2), (7, 5, 0, 1)):
+    for n_rows, n_cols, nnz, threads in ((50, 40, 300, 3), (100000, 3000, 2_500_000, 4), (10, 0, 0, 2), (7, 5, 0, 1)):
         per_col = np.bincount(rng.integers(0, max(n_cols, 1), size=nnz), minlength=n_cols)[:n_cols] if n_cols else np.zeros(0, dtype=np.int64)
         indptr = np.concatenate(([0], np.cumsum(per_col))).astype(np.int64)
         indices = rng.integers(0, n_rows, size=int(indptr[-1])).astype(np.int64)
