@@ -78,21 +78,28 @@ def _attribute_msg(name, value):
 
 # --------------------------------------------------------------------------------------------- writer
 class _Writer(object):
-    def __init__(self):
-        self.buf = bytearray()
+    """Appends to the file as it goes (the 1.5 GB index / data arrays of a full-size matrix are written straight from the
+    numpy buffers, never copied into a staging bytearray); the superblock is patched in at the end."""
+
+    def __init__(self, f):
+        self.f = f
+        self.pos = 0
 
     def tell(self):
-        return len(self.buf)
+        return self.pos
 
     def alloc(self, blob, align=8):
-        self.buf += b"\0" * ((-len(self.buf)) % align)
-        addr = len(self.buf)
-        self.buf += blob
+        pad = (-self.pos) % align
+        if pad:
+            self.f.write(b"\0" * pad)
+        addr = self.pos + pad
+        self.f.write(blob)
+        self.pos = addr + (blob.nbytes if isinstance(blob, memoryview) else len(blob))
         return addr
 
     def dataset(self, arr):
         arr = np.ascontiguousarray(arr)
-        data_addr = self.alloc(arr.tobytes()) if arr.nbytes else UNDEF
+        data_addr = self.alloc(memoryview(arr.reshape(-1).view(np.uint8))) if arr.nbytes else UNDEF
         msgs = [
             _message(0x0001, _dataspace_msg(arr.shape)),
             _message(0x0003, _dtype_msg(arr.dtype), flags=1),                  # constant message
@@ -142,8 +149,9 @@ def write_matrix_h5(path, indptr, indices, data, n_features, barcodes, feature_i
     """CountMatrix.save_h5_file (cellranger/matrix.py:415-447) + FeatureReference.to_hdf5 (feature_ref.py:103-118)
     + atac from_peaks_bed (cellranger/atac/feature_ref.py:45-71: id = name = 'chr:start-end', type 'Peaks',
     tags genome / derivation='')."""
-    w = _Writer()
-    w.buf += b"\0" * 96                                                       # superblock placeholder
+    f = open(path, "wb")
+    w = _Writer(f)
+    w.alloc(b"\0" * 96)                                                      # superblock placeholder
     n_bc = len(barcodes)
     feats = {
         "_all_tag_keys": w.dataset(_string_array(["genome", "derivation"])),
@@ -165,16 +173,17 @@ def write_matrix_h5(path, indptr, indices, data, n_features, barcodes, feature_i
     mat_hdr, _, _ = w.group(matrix)
     root_hdr, root_tree, root_heap = w.group({"matrix": mat_hdr},
                                              attrs={"filetype": "matrix", "version": 2, "software_version": sw_version or ""})
-    eof = len(w.buf) + ((-len(w.buf)) % 8)
-    w.buf += b"\0" * (eof - len(w.buf))
+    pad = (-w.pos) % 8
+    if pad:
+        f.write(b"\0" * pad)
+    eof = w.pos + pad
     sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, GROUP_LEAF_K, GROUP_INTERNAL_K, 0)
     sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
     sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_tree, root_heap)   # root symbol table entry
     assert len(sb) == 96
-    w.buf[:96] = sb
-    with open(path, "wb") as f:
-        f.write(w.buf)
-
+    f.seek(0)
+    f.write(sb)
+    f.close()
 
 # --------------------------------------------------------------------------------------------- reader (same subset)
 class _Reader(object):
