@@ -94,6 +94,9 @@ SIGNATURES = {
     "cratac_inflate_file": (c_int, [c_cp, c_int, c_vp, c_i64, P(c_i64)]),
     "cratac_inflate_range": (c_int, [c_cp, c_int, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_i64, P(c_i64)]),
     "cratac_write_mtx": (c_int, [c_cp, c_cp, c_i64, c_vp, c_vp, c_vp, c_int]),
+    "cratac_write_bedgraph": (c_int, [c_cp, c_int, c_cp, c_i64, c_vp, c_vp, c_vp, c_int]),
+    "cratac_read_bedgraph": (c_int, [c_cp, c_int, P(c_cp), c_int, c_dbl, c_int, P(c_vp), P(c_vp), P(c_vp), P(c_i64)]),
+    "cratac_free_host": (None, [c_vp]),
     "cratac_inflate_stats": (c_int, [P(c_i64), P(c_i64), c_int]),
     "cratac_inflate_mode": (c_int, [c_int]),
     "cratac_encode_text_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, P(c_i64)]),
@@ -501,6 +504,34 @@ def write_mtx(path, header, indptr, indices, data, threads=None):
     data = np.ascontiguousarray(data[:nnz], dtype=np.int32)
     threads = threads or (os.cpu_count() or 1)
     check(load().cratac_write_mtx(path.encode(), header.encode("ascii"), max(indptr.size - 1, 0), _ptr(indptr), _ptr(indices), _ptr(data), threads))
+
+
+def write_bedgraph(path, contig, starts, ends, counts, append=True, threads=None):
+    """Append the rows "contig\\tstart\\tend\\tcount" of one contig to a bedgraph file."""
+    starts, ends, counts = (np.ascontiguousarray(a, dtype=np.int64) for a in (starts, ends, counts))
+    threads = threads or (os.cpu_count() or 1)
+    check(load().cratac_write_bedgraph(path.encode(), 1 if append else 0, contig.encode(), starts.size, _ptr(starts), _ptr(ends), _ptr(counts), threads))
+
+
+def read_bedgraph(path, contig_names, threshold=None, threads=None):
+    """Rows of a bedgraph with count >= threshold (all rows when threshold is None), in file order
+    -> (chrom int32 = index into contig_names, start int64, end int64)."""
+    lib = load()
+    threads = threads or (os.cpu_count() or 1)
+    names = (c_cp * len(contig_names))(*[n.encode() for n in contig_names])
+    pc, ps, pe, n = c_vp(), c_vp(), c_vp(), c_i64()
+    check(lib.cratac_read_bedgraph(path.encode(), len(contig_names), names, 0 if threshold is None else 1,
+                                   0.0 if threshold is None else float(threshold), threads,
+                                   ctypes.byref(pc), ctypes.byref(ps), ctypes.byref(pe), ctypes.byref(n)))
+    try:
+        k = n.value
+        chrom = np.ctypeslib.as_array(ctypes.cast(pc, P(c_i32)), shape=(max(k, 1),))[:k].copy()
+        start = np.ctypeslib.as_array(ctypes.cast(ps, P(c_i64)), shape=(max(k, 1),))[:k].copy()
+        end = np.ctypeslib.as_array(ctypes.cast(pe, P(c_i64)), shape=(max(k, 1),))[:k].copy()
+    finally:
+        for q in (pc, ps, pe):
+            lib.cratac_free_host(q)
+    return chrom, start, end
 
 
 def inflate_stats(reset=False):

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <unordered_map>
+#include <string>
 #include <memory>
 #include <thread>
 
@@ -1093,5 +1095,157 @@ int cratac_write_mtx(const char* path, const char* header, int64_t n_cols, const
     if (failed) { set_error("write failed on %s", path); return CRATAC_ERR_IO; }
     return CRATAC_OK;
 }
+
+// ---- the cut_sites bedgraph, the file between COUNT_CUT_SITES and DETECT_PEAKS (hundreds of millions of rows genome-wide)
+// rows "contig\tstart\tend\tcount\n" of one contig, appended to `path` (count_cut_sites/__init__.py:38-48 writes them one
+// Python format() at a time); formatted in chunks of 1 M rows on `threads` threads, written in order.
+int cratac_write_bedgraph(const char* path, int append, const char* contig, int64_t n, const int64_t* start, const int64_t* end,
+                          const int64_t* count, int threads) {
+    if (!path || !contig || n < 0) { set_error("cratac_write_bedgraph: bad argument"); return CRATAC_ERR_ARG; }
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) { set_error("cannot open %s for writing", path); return CRATAC_ERR_IO; }
+    if (threads < 1) threads = 1;
+    const size_t name_len = strlen(contig);
+    const int64_t chunk = 1 << 20;
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    auto put_int = [](char* p, int64_t x) -> char* {
+        char tmp[24];
+        int k = 0;
+        uint64_t v = x < 0 ? (uint64_t)(-x) : (uint64_t)x;
+        if (x < 0) *p++ = '-';
+        do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (k) *p++ = tmp[--k];
+        return p;
+    };
+    bool failed = false;
+    for (int64_t wave = 0; wave < n_chunks && !failed; wave += threads) {
+        const int64_t in_wave = std::min<int64_t>(threads, n_chunks - wave);
+        std::vector<std::unique_ptr<char[]>> bufs((size_t)in_wave);
+        std::vector<size_t> used((size_t)in_wave, 0);
+        auto work = [&](int64_t w) {
+            const int64_t r0 = (wave + w) * chunk, r1 = std::min<int64_t>(n, r0 + chunk);
+            bufs[(size_t)w].reset(new char[(size_t)(r1 - r0) * (name_len + 3 * 21 + 4) + 16]);
+            char* p = bufs[(size_t)w].get();
+            for (int64_t r = r0; r < r1; r++) {
+                memcpy(p, contig, name_len); p += name_len;
+                *p++ = '\t'; p = put_int(p, start[r]);
+                *p++ = '\t'; p = put_int(p, end[r]);
+                *p++ = '\t'; p = put_int(p, count[r]);
+                *p++ = '\n';
+            }
+            used[(size_t)w] = (size_t)(p - bufs[(size_t)w].get());
+        };
+        std::vector<std::thread> pool;
+        for (int64_t w = 1; w < in_wave; w++) pool.emplace_back(work, w);
+        work(0);
+        for (auto& t : pool) t.join();
+        for (int64_t w = 0; w < in_wave; w++)
+            if (used[(size_t)w] && fwrite(bufs[(size_t)w].get(), 1, used[(size_t)w], f) != used[(size_t)w]) failed = true;
+    }
+    if (fclose(f) != 0) failed = true;
+    if (failed) { set_error("write failed on %s", path); return CRATAC_ERR_IO; }
+    return CRATAC_OK;
+}
+
+// Rows of a bedgraph whose count is >= threshold (all rows when has_threshold is 0): the `for track in f` loop of
+// lib/python/utils.py:105-115 + the integer test of detect_peaks/__init__.py:49, on `threads` threads over a read-only
+// mapping of the file.  The arrays are allocated here (free them with cratac_free_host); chrom = index into contig_names.
+int cratac_read_bedgraph(const char* path, int n_contigs, const char* const* contig_names, int has_threshold, double threshold,
+                         int threads, int32_t** chrom_out, int64_t** start_out, int64_t** end_out, int64_t* n_out) {
+    if (!path || !chrom_out || !start_out || !end_out || !n_out) { set_error("cratac_read_bedgraph: null argument"); return CRATAC_ERR_ARG; }
+    *chrom_out = nullptr; *start_out = nullptr; *end_out = nullptr; *n_out = 0;
+    MappedFile mf;
+    if (!mf.open_path(path)) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
+    const char* base = reinterpret_cast<const char*>(mf.p);
+    const size_t size = mf.n;
+    if (threads < 1) threads = 1;
+    std::unordered_map<std::string, int> ids;
+    for (int i = 0; i < n_contigs; i++) ids.emplace(contig_names[i], i);
+    // cut the file into ranges that start right after a newline
+    const size_t n_ranges = size < ((size_t)1 << 20) ? 1 : (size_t)threads * 4;
+    std::vector<size_t> cut(n_ranges + 1, size);
+    cut[0] = 0;
+    for (size_t r = 1; r < n_ranges; r++) {
+        size_t p = size / n_ranges * r;
+        while (p < size && base[p] != '\n') p++;
+        cut[r] = p < size ? p + 1 : size;
+    }
+    struct Part { std::vector<int32_t> c; std::vector<int64_t> s, e; long long bad_line = -1; std::string bad_name; };
+    std::vector<Part> parts(n_ranges);
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const size_t r = next.fetch_add(1);
+            if (r >= n_ranges) break;
+            Part& out = parts[r];
+            const char* p = base + cut[r];
+            const char* const stop = base + cut[r + 1];
+            const char* last_name = nullptr;
+            size_t last_len = 0;
+            int last_id = -1;
+            while (p < stop) {
+                const char* line = p;
+                const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(stop - p)));
+                const char* eol = nl ? nl : stop;
+                p = nl ? nl + 1 : stop;
+                if (eol == line) { out.bad_line = (long long)(line - base); break; }      // `a, b, c, d = "".split()` raises as well
+                const char* t1 = static_cast<const char*>(memchr(line, '\t', (size_t)(eol - line)));
+                const char* t2 = t1 ? static_cast<const char*>(memchr(t1 + 1, '\t', (size_t)(eol - t1 - 1))) : nullptr;
+                const char* t3 = t2 ? static_cast<const char*>(memchr(t2 + 1, '\t', (size_t)(eol - t2 - 1))) : nullptr;
+                if (!t3 || memchr(t3 + 1, '\t', (size_t)(eol - t3 - 1))) { out.bad_line = (long long)(line - base); break; }
+                auto to_int = [](const char* b, const char* e, int64_t* v) -> bool {
+                    while (b < e && (*b == ' ' || *b == '\r')) b++;
+                    while (e > b && (e[-1] == ' ' || e[-1] == '\r')) e--;
+                    bool neg = false;
+                    if (b < e && (*b == '-' || *b == '+')) { neg = *b == '-'; b++; }
+                    if (b == e || e - b > 18) return false;
+                    int64_t x = 0;
+                    for (; b < e; b++) { if (*b < '0' || *b > '9') return false; x = x * 10 + (*b - '0'); }
+                    *v = neg ? -x : x;
+                    return true;
+                };
+                int64_t s, e, cnt;
+                if (!to_int(t1 + 1, t2, &s) || !to_int(t2 + 1, t3, &e) || !to_int(t3 + 1, eol, &cnt)) { out.bad_line = (long long)(line - base); break; }
+                if (has_threshold && (double)cnt < threshold) continue;
+                const size_t len = (size_t)(t1 - line);
+                if (!(last_name && len == last_len && memcmp(last_name, line, len) == 0)) {
+                    auto it = ids.find(std::string(line, len));
+                    if (it == ids.end()) { out.bad_line = (long long)(line - base); out.bad_name.assign(line, len); break; }
+                    last_name = line; last_len = len; last_id = it->second;
+                }
+                out.c.push_back(last_id); out.s.push_back(s); out.e.push_back(e);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    size_t total = 0;
+    for (const Part& q : parts) {
+        if (q.bad_line >= 0) {
+            if (!q.bad_name.empty()) set_error("bedgraph %s: contig '%s' (byte %lld) is not in the reference", path, q.bad_name.c_str(), q.bad_line);
+            else set_error("bedgraph %s: malformed row at byte %lld", path, q.bad_line);
+            return CRATAC_ERR_PARSE;
+        }
+        total += q.c.size();
+    }
+    int32_t* c = static_cast<int32_t*>(malloc(std::max<size_t>(total, 1) * sizeof(int32_t)));
+    int64_t* s = static_cast<int64_t*>(malloc(std::max<size_t>(total, 1) * sizeof(int64_t)));
+    int64_t* e = static_cast<int64_t*>(malloc(std::max<size_t>(total, 1) * sizeof(int64_t)));
+    if (!c || !s || !e) { free(c); free(s); free(e); set_error("out of memory reading %s", path); return CRATAC_ERR_IO; }
+    size_t at = 0;
+    for (const Part& q : parts) {
+        if (q.c.empty()) continue;
+        memcpy(c + at, q.c.data(), q.c.size() * sizeof(int32_t));
+        memcpy(s + at, q.s.data(), q.s.size() * sizeof(int64_t));
+        memcpy(e + at, q.e.data(), q.e.size() * sizeof(int64_t));
+        at += q.c.size();
+    }
+    *chrom_out = c; *start_out = s; *end_out = e; *n_out = (int64_t)total;
+    return CRATAC_OK;
+}
+
+void cratac_free_host(void* p) { free(p); }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ from __future__ import division
 import pickle
 from collections import Counter
 
-from cratac import stage_util
+from cratac import _ffi, stage_util
 
 __MRO__ = """
 stage COUNT_CUT_SITES(
@@ -54,13 +54,14 @@ def join(args, outs, chunk_defs, chunk_outs):
         pickle.dump(count_dict, f, protocol=2)
 
     # bedgraph of * windowed cutsites *, contigs in the chunk order of the reference (primary_contigs)
+    # (the rows are formatted natively on all cores, cratac_write_bedgraph: genome-wide there are hundreds of millions)
     wrote = False
-    with open(outs.cut_sites, 'w') as out:
-        for contig in mgr.primary_contigs(allow_sex_chromosomes=True):
-            starts, ends, counts = ctx.bedgraph_rows(contig)
-            for s, e, c in zip(starts.tolist(), ends.tolist(), counts.tolist()):
-                out.write('{}\t{}\t{}\t{}\n'.format(contig, s, e, c))
-                wrote = True
+    open(outs.cut_sites, 'w').close()
+    for contig in mgr.primary_contigs(allow_sex_chromosomes=True):
+        starts, ends, counts = ctx.bedgraph_rows(contig)
+        if starts.size:
+            _ffi.write_bedgraph(outs.cut_sites, contig, starts, ends, counts, append=True)
+            wrote = True
     ctx.close()
     if not wrote:
         outs.cut_sites = None

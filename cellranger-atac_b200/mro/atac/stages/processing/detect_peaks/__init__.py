@@ -14,7 +14,7 @@ import pickle
 
 import numpy as np
 
-from cratac import stage_util
+from cratac import _ffi, stage_util
 
 __MRO__ = """
 stage DETECT_PEAKS(
@@ -62,22 +62,10 @@ def main(args, outs):
         return
 
     mgr, ctx = stage_util.context_for_reference(args.reference_path)
-    cid = {name: i for i, name in enumerate(mgr.all_contigs)}
-    chrom, start, end = [], [], []
-    threshold = args.threshold
-    with open(args.cut_sites, 'r') as f:
-        for track in f:
-            c, s, e, count = track.split("\t")
-            # the reference compares the count STRING with the float threshold (utils.py:112), which never
-            # filters in Python 2; the integer test of detect_peaks/__init__.py:49 is the one that counts
-            if threshold is not None and int(count) < threshold:
-                continue
-            chrom.append(cid[c])
-            start.append(int(s))
-            end.append(int(e))
-    chrom = np.array(chrom, dtype=np.int32)
-    start = np.array(start, dtype=np.int64)
-    end = np.array(end, dtype=np.int64)
+    # the reference compares the count STRING with the float threshold (utils.py:112), which never filters in Python 2;
+    # the integer test of detect_peaks/__init__.py:49 is the one that counts.  The rows are parsed natively on all cores
+    # (cratac_read_bedgraph): genome-wide the bedgraph has hundreds of millions of them.
+    chrom, start, end = _ffi.read_bedgraph(args.cut_sites, list(mgr.all_contigs), args.threshold)
     order = np.lexsort((start, chrom))
     pc, ps, pe = ctx.peaks_from_rows(chrom[order], start[order], end[order])
     ctx.close()

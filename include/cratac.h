@@ -216,6 +216,16 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
  * Host arrays: indptr[n_cols + 1], indices / data [indptr[n_cols]]. */
 int cratac_write_mtx(const char* path, const char* header, int64_t n_cols, const int64_t* indptr, const int64_t* indices,
                      const int32_t* data, int threads);
+/* The cut_sites bedgraph is the FILE between COUNT_CUT_SITES and DETECT_PEAKS (the stage interface keeps it).  Rows
+ * "contig\tstart\tend\tcount" of one contig appended to `path` -- the per-row format() of count_cut_sites/__init__.py:38-48 --
+ * and the rows with count >= threshold read back -- the `for track in f` loop of lib/python/utils.py:105-115 with the
+ * integer test of detect_peaks/__init__.py:49 -- both on `threads` host threads.  cratac_read_bedgraph allocates its three
+ * result arrays (chrom = index into contig_names); release them with cratac_free_host. */
+int cratac_write_bedgraph(const char* path, int append, const char* contig, int64_t n, const int64_t* start, const int64_t* end,
+                          const int64_t* count, int threads);
+int cratac_read_bedgraph(const char* path, int n_contigs, const char* const* contig_names, int has_threshold, double threshold,
+                         int threads, int32_t** chrom_out, int64_t** start_out, int64_t** end_out, int64_t* n_out);
+void cratac_free_host(void* p);
 int cratac_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks, int reset);
 int cratac_inflate_mode(int mode);
 /* synthetic text encoder (SoA on the device -> fragments.tsv text on the device), used by bench/tests

@@ -130,6 +130,119 @@ def test_native_mtx_writer_equals_per_entry_formatting(tmp_path):
             assert body.count(b"\n") == int(indptr[-1]) and t_native < 20
 
 
+def test_count_cut_sites_and_detect_peaks_stage_files_on_cpu(tmp_path, monkeypatch):
+    """The two stage modules around the cut_sites bedgraph with the GPU context replaced by an oracle-backed fake: what
+    is exercised is the host side of the stages -- the Counter pickle, the natively written bedgraph (row for row the
+    reference writer's), the natively parsed and thresholded rows, peaks.bed and the metrics."""
+    from cratac import stage_util
+    from oracle import em as oracle_em, stages
+    contigs = [("chr1", 60000), ("chr2", 30000), ("chrM", 5000)]
+    primary = ["chr1", "chr2"]
+    ref = str(tmp_path / "ref")
+    refmgr.write_reference(ref, contigs)
+    defs_path = os.path.join(ref, "fasta", "contig-defs.json")
+    defs = json.load(open(defs_path))
+    defs["primary_contigs"] = primary
+    defs["non_nuclear_contigs"] = ["chrM"]
+    json.dump(defs, open(defs_path, "w"))
+    frags = synth.generate(contigs[:2], 9000, 25, 12, seed=21, background_factor=4)
+    rows = stages.parse_fragments(synth.to_text(frags).decode().splitlines())
+    by_contig = {c: [(s, e) for cc, s, e, _b, _d in rows if cc == c] for c in primary}
+    cuts = {c: stages.pileup(dict(contigs)[c], by_contig[c]) for c in primary}
+    count_dict = stages.merge_count_dicts([stages.count_dict_from_cuts(cuts[c]) for c in primary])
+    bed_rows = {c: stages.bedgraph_rows(c, dict(contigs)[c], cuts[c]) for c in primary}
+
+    class FakeCtx(object):
+        def count_cut_sites(self):
+            v = np.array(sorted(count_dict), dtype=np.int64)
+            return v, np.array([count_dict[k] for k in v.tolist()], dtype=np.int64)
+
+        def bedgraph_rows(self, contig):
+            r = bed_rows[contig]
+            return tuple(np.array([x[k] for x in r], dtype=np.int64) for k in (1, 2, 3))
+
+        def fit_threshold(self, values, weights, odds):
+            thr, params = oracle_em.estimate_final_threshold(dict(zip(values.tolist(), weights.tolist())), odds)
+            return (None if thr is None else int(thr)), params, {}
+
+        def peaks_from_rows(self, chrom, start, end):
+            out = []
+            for c, s, e in zip(chrom.tolist(), start.tolist(), end.tolist()):
+                if out and out[-1][0] == c and s - stage_util.PEAK_MERGE_DISTANCE <= out[-1][2]:
+                    out[-1][2] = max(out[-1][2], e)
+                else:
+                    out.append([c, s, e])
+            a = np.array(out, dtype=np.int64).reshape(-1, 3)
+            return a[:, 0].astype(np.int32), a[:, 1], a[:, 2]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(stage_util, "context_for_reference", lambda path, device=0: (refmgr.ReferenceManager(path), FakeCtx()))
+    monkeypatch.setattr(stage_util, "load_fragments", lambda ctx, path: None)
+    ccs, dp = load_stage("count_cut_sites"), load_stage("detect_peaks")
+    args = Record(reference_path=ref, fragments="fragments.tsv.gz", fragments_index="fragments.tsv.gz.tbi")
+    outs = Record(cut_sites=str(tmp_path / "cut_sites.bedgraph"), count_dict=str(tmp_path / "count_dict.pickle"))
+    ccs.join(args, outs, [], [])
+    assert dict(pickle.load(open(outs.count_dict, "rb"))) == dict(count_dict)
+    assert open(outs.cut_sites).read() == "".join(stages.format_bedgraph(bed_rows[c]) for c in primary)
+    args = Record(cut_sites=outs.cut_sites, reference_path=ref, count_dict=outs.count_dict)
+    sp = dp.split(args)
+    thr, _params = oracle_em.estimate_final_threshold(count_dict, stage_util.PEAK_ODDS_RATIO)
+    assert sp["chunks"][0]["threshold"] == int(thr)
+    chunk = Record(**sp["chunks"][0])
+    mouts = Record(peaks=str(tmp_path / "chunk_peaks.bed"), peak_metrics=str(tmp_path / "chunk_metrics.json"))
+    dp.main(Record(cut_sites=outs.cut_sites, reference_path=ref, count_dict=outs.count_dict, contig=None, params=chunk.params,
+                   threshold=float(chunk.threshold)), mouts)
+    want = [p for c in primary for p in stages.detect_peaks_contig(c, dict(contigs)[c], by_contig[c], int(thr))[3]]
+    assert len(want) > 0
+    assert open(mouts.peaks).read() == "".join("%s\t%d\t%d\n" % tuple(p) for p in want)
+    jouts = Record(peaks=str(tmp_path / "peaks.bed"), peak_metrics=str(tmp_path / "peak_metrics.json"))
+    dp.join(args, jouts, [chunk], [mouts])
+    metrics = json.load(open(jouts.peak_metrics))
+    assert metrics["total_peaks_detected"] == len(want) and metrics["bases_in_peaks"] == sum(p[2] - p[1] for p in want)
+
+
+def test_native_bedgraph_io(tmp_path):
+    """cratac_write_bedgraph / cratac_read_bedgraph against the per-row Python they replace (count_cut_sites/__init__.py:38-48,
+    utils.py:105-115 + detect_peaks/__init__.py:49): many rows, several contigs, every threshold form, error cases."""
+    from cratac import _ffi
+    rng = np.random.default_rng(10)
+    names = ["chr1", "chr2", "GL000219.1", "chrX"]
+    p = str(tmp_path / "cs.bedgraph")
+    open(p, "w").close()
+    want_lines = []
+    for c in ("chr1", "GL000219.1", "chrX"):
+        n = 1_300_000 if c == "chr1" else 700
+        s = np.cumsum(rng.integers(1, 40, size=n)).astype(np.int64)
+        e = s + rng.integers(1, 30, size=n)
+        v = rng.integers(1, 60, size=n).astype(np.int64)
+        _ffi.write_bedgraph(p, c, s, e, v, append=True, threads=3)
+        want_lines.append((c, s, e, v))
+    text = open(p).read()
+    assert text.count("\n") == sum(x[1].size for x in want_lines)
+    c, s, e, v = want_lines[1]
+    assert "".join("{}\t{}\t{}\t{}\n".format(c, a, b, d) for a, b, d in zip(s.tolist(), e.tolist(), v.tolist())) in text
+    assert text.startswith("chr1\t%d\t%d\t%d\n" % (want_lines[0][1][0], want_lines[0][2][0], want_lines[0][3][0]))
+    for thr in (None, 1.0, 17.0, 17.5, 1000.0):
+        gc, gs, ge = _ffi.read_bedgraph(p, names, thr, threads=4)
+        wc, ws, we = [], [], []
+        for c, s, e, v in want_lines:
+            keep = np.ones(s.size, dtype=bool) if thr is None else ~(v < thr)
+            wc.append(np.full(int(keep.sum()), names.index(c), dtype=np.int32)); ws.append(s[keep]); we.append(e[keep])
+        assert np.array_equal(gc, np.concatenate(wc)) and np.array_equal(gs, np.concatenate(ws)) and np.array_equal(ge, np.concatenate(we))
+    with pytest.raises(_ffi.CratacError):
+        _ffi.read_bedgraph(p, ["chr1", "chr2"], None)                    # contig not in the reference (KeyError in the Python loop)
+    open(p, "a").write("chr1\t5\t6\n")
+    with pytest.raises(_ffi.CratacError):
+        _ffi.read_bedgraph(p, names, None)                               # three fields: the unpacking of the Python loop raises
+    open(p, "w").write("chr1\t5\t9\t3")                                 # last line without a newline
+    gc, gs, ge = _ffi.read_bedgraph(p, names, 2.0)
+    assert gc.tolist() == [0] and gs.tolist() == [5] and ge.tolist() == [9]
+    open(p, "w").close()
+    assert _ffi.read_bedgraph(p, names, None)[0].size == 0
+
+
 def test_reference_manager(tmp_path):
     contigs = [("chr1", 1000), ("chr2", 500), ("chrX", 300), ("chrM", 16)]
     ref = str(tmp_path / "ref")
