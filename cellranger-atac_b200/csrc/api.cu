@@ -925,9 +925,17 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, 15 + 16) != Z_OK) { set_error("zlib init failed"); return CRATAC_ERR_IO; }
         std::vector<unsigned char> scratch(1 << 20);
-        zs.next_in = const_cast<unsigned char*>(buf); zs.avail_in = (uInt)fsz;
+        zs.next_in = const_cast<unsigned char*>(buf);
+        zs.avail_in = 0;
+        size_t fed = 0;                                   // input is handed over 1 GiB at a time (avail_in is 32 bits)
         int64_t produced = 0;
         for (;;) {
+            if (zs.avail_in == 0 && fed < (size_t)fsz) {
+                const size_t take = std::min<size_t>((size_t)fsz - fed, (size_t)1 << 30);
+                zs.next_in = const_cast<unsigned char*>(buf) + fed;
+                zs.avail_in = (uInt)take;
+                fed += take;
+            }
             bool counting = (cap == 0 || !out);
             zs.next_out = counting ? scratch.data() : reinterpret_cast<unsigned char*>(out) + produced;
             int64_t room = counting ? (int64_t)scratch.size() : cap - produced;
@@ -936,10 +944,11 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
             int rc = inflate(&zs, Z_NO_FLUSH);
             produced += before - zs.avail_out;
             if (rc == Z_STREAM_END) {
-                if (zs.avail_in == 0) break;
+                if (zs.avail_in == 0 && fed >= (size_t)fsz) break;
                 inflateReset(&zs);
                 continue;
             }
+            if (rc == Z_BUF_ERROR && zs.avail_in == 0 && fed < (size_t)fsz) continue;      // needs the next slice of input
             if (rc != Z_OK) { inflateEnd(&zs); set_error("corrupt gzip stream in %s", path); return CRATAC_ERR_IO; }
             if (!counting && produced >= cap && zs.avail_in > 0) { inflateEnd(&zs); set_error("inflate buffer too small"); return CRATAC_ERR_ARG; }
         }
