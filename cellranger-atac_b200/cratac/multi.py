@@ -111,6 +111,7 @@ def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set", trace=None)
             t_last[0] = now
 
     world, rank = dist.get_world_size(), dist.get_rank()
+    shard.check_stream()         # the collectives below must be ordered after the library's kernels
     n_frag, n_bc = shard.decode()
     mark("decode")
     # 1. histogram: queued, all-reduced in place (largest count and bins), fit queued behind it -- no host wait
@@ -213,6 +214,15 @@ class CudaShard(object):
         self.text_dev_ptr, self.text_host, self.nbytes = text_dev_ptr, text_host, nbytes
         self.merged = None
         self._side = None
+
+    def check_stream(self):
+        """step() queues NCCL collectives on torch's CURRENT stream between the library's kernels: that stream must be the
+        context's own (enter `torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream()))` first), else the all-reduce of the
+        histogram would not be ordered after the kernel that fills it and the fit would run on un-reduced bins."""
+        cur = self.torch.cuda.current_stream(self.device).cuda_stream
+        if int(cur) != int(self.ctx.stream()):
+            raise RuntimeError("cratac.multi.step: torch's current stream (0x%x) is not the context's stream (0x%x); wrap the call in "
+                               "torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream()))" % (int(cur), int(self.ctx.stream())))
 
     def decode(self):
         if self.text_dev_ptr is not None:

@@ -835,7 +835,32 @@ struct MappedFile {
 static std::atomic<long long> g_inflate_fast(0), g_inflate_zlib(0);
 static std::atomic<int> g_inflate_mode(1);          // 1: own decoder first, zlib when it declines; 0: zlib only
 
-// one BGZF block: raw DEFLATE `in` -> exactly `isize` bytes at `dst`
+
+// Header of the BGZF block at buf[0..avail): total block size (BSIZE + 1 of the 'BC' extra subfield), extra-field length
+// and ISIZE.  Every bound a damaged file could break is checked here: the block must hold its own header, extra field and
+// the 8-byte trailer, lie inside the buffer, and inflate to at most 64 KiB (the BGZF limit).  0: not a BGZF block / damaged.
+static bool bgzf_block_header(const unsigned char* b, size_t avail, size_t* bsize_out, unsigned* xlen_out, uint32_t* isize_out) {
+    if (avail < 18 + 8) return false;
+    if (!(b[0] == 31 && b[1] == 139 && b[2] == 8 && (b[3] & 4))) return false;
+    const unsigned xlen = b[10] | (b[11] << 8);
+    const size_t xend = 12 + (size_t)xlen;
+    if (xend + 8 > avail) return false;
+    long bsize = -1;
+    for (size_t q = 12; q + 4 <= xend;) {
+        const unsigned slen = b[q + 2] | (b[q + 3] << 8);
+        if (q + 4 + slen > xend) return false;
+        if (b[q] == 'B' && b[q + 1] == 'C' && slen == 2) bsize = (b[q + 4] | (b[q + 5] << 8)) + 1;
+        q += 4 + slen;
+    }
+    if (bsize < 0 || (size_t)bsize < xend + 8 || (size_t)bsize > avail) return false;
+    uint32_t isize;
+    memcpy(&isize, &b[bsize - 4], 4);
+    if (isize > 65536u) return false;
+    *bsize_out = (size_t)bsize; *xlen_out = xlen; *isize_out = isize;
+    return true;
+}
+
+// one BGZF block: raw DEFLATE `in` -> exactly `isize` bytes at `dst`; the CRC-32 of the trailer (in[csize..csize+4)) is checked like `gzip -d` does
 static bool inflate_block(z_stream* zs, uint32_t* scratch, const unsigned char* in, size_t csize, unsigned char* dst, uint32_t isize) {
     if (g_inflate_mode.load(std::memory_order_relaxed) && inflate_raw(in, csize, dst, isize, scratch)) {
         g_inflate_fast.fetch_add(1, std::memory_order_relaxed);
@@ -848,6 +873,12 @@ static bool inflate_block(z_stream* zs, uint32_t* scratch, const unsigned char* 
     zs->next_out = dst; zs->avail_out = isize;
     const int rc = inflate(zs, Z_FINISH);
     return rc == Z_STREAM_END && zs->avail_out == 0;
+}
+static bool inflate_block_checked(z_stream* zs, uint32_t* scratch, const unsigned char* in, size_t csize, unsigned char* dst, uint32_t isize) {
+    if (!inflate_block(zs, scratch, in, csize, dst, isize)) return false;
+    uint32_t want;
+    memcpy(&want, in + csize, 4);                       // trailer: CRC32, ISIZE
+    return (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, isize) == want;
 }
 
 int cratac_inflate_stats(int64_t* fast_blocks, int64_t* zlib_blocks, int reset) {
@@ -874,23 +905,12 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
     size_t p = 0;
     int64_t total = 0;
     bool bgzf = true;
-    while (p + 18 <= (size_t)fsz) {
-        const unsigned char* b = &buf[p];
-        if (!(b[0] == 31 && b[1] == 139 && b[2] == 8 && (b[3] & 4))) { bgzf = false; break; }
-        unsigned xlen = b[10] | (b[11] << 8);
-        size_t q = p + 12, xend = q + xlen;
-        long bsize = -1;
-        while (q + 4 <= xend && xend <= (size_t)fsz) {
-            unsigned slen = buf[q + 2] | (buf[q + 3] << 8);
-            if (buf[q] == 'B' && buf[q + 1] == 'C' && slen == 2) bsize = (buf[q + 4] | (buf[q + 5] << 8)) + 1;
-            q += 4 + slen;
-        }
-        if (bsize < 0 || p + (size_t)bsize > (size_t)fsz) { bgzf = false; break; }
-        uint32_t isize;
-        memcpy(&isize, &buf[p + bsize - 4], 4);
-        blocks.push_back(Blk{p + 12 + xlen, (size_t)bsize - 12 - xlen - 8, total, isize});
+    while (p < (size_t)fsz) {
+        size_t bsize; unsigned xlen; uint32_t isize;
+        if (!bgzf_block_header(&buf[p], (size_t)fsz - p, &bsize, &xlen, &isize)) { bgzf = false; break; }
+        blocks.push_back(Blk{p + 12 + xlen, bsize - 12 - xlen - 8, total, isize});
         total += isize;
-        p += (size_t)bsize;
+        p += bsize;
     }
     if (bgzf && p == (size_t)fsz) {
         *nbytes = total;
@@ -908,7 +928,7 @@ int cratac_inflate_file(const char* path, int threads, char* out, int64_t cap, i
                 size_t i = next.fetch_add(1);
                 if (i >= blocks.size()) break;
                 const Blk& k = blocks[i];
-                if (!inflate_block(&zs, scratch.data(), &buf[k.off], k.csize, reinterpret_cast<unsigned char*>(out) + k.out_off, k.isize)) { failed = 1; break; }
+                if (!inflate_block_checked(&zs, scratch.data(), &buf[k.off], k.csize, reinterpret_cast<unsigned char*>(out) + k.out_off, k.isize)) { failed = 1; break; }
             }
             inflateEnd(&zs);
         };
@@ -985,27 +1005,17 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
     size_t p = 0;
     int64_t total = 0;
     while (c_begin + p < c_end || (c_begin + p == c_end && u_end > 0)) {
-        if (p + 18 > buf_size) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
-        const unsigned char* b = &buf[p];
-        if (!(b[0] == 31 && b[1] == 139 && b[2] == 8 && (b[3] & 4))) { set_error("no BGZF block at offset %llu of %s", (unsigned long long)(c_begin + p), path); return CRATAC_ERR_IO; }
-        const unsigned xlen = b[10] | (b[11] << 8);
-        size_t q = p + 12;
-        const size_t xend = q + xlen;
-        long bsize = -1;
-        while (q + 4 <= xend && xend <= buf_size) {
-            const unsigned slen = buf[q + 2] | (buf[q + 3] << 8);
-            if (buf[q] == 'B' && buf[q + 1] == 'C' && slen == 2) bsize = (buf[q + 4] | (buf[q + 5] << 8)) + 1;
-            q += 4 + slen;
+        size_t bsize; unsigned xlen; uint32_t isize;
+        if (p >= buf_size || !bgzf_block_header(&buf[p], buf_size - p, &bsize, &xlen, &isize)) {
+            set_error("truncated or damaged BGZF block at offset %llu of %s", (unsigned long long)(c_begin + p), path);
+            return CRATAC_ERR_IO;
         }
-        if (bsize < 0 || p + (size_t)bsize > buf_size) { set_error("truncated BGZF block in %s", path); return CRATAC_ERR_IO; }
-        uint32_t isize;
-        memcpy(&isize, &buf[p + bsize - 4], 4);
         const uint64_t at = c_begin + p;
         uint32_t lo = at == c_begin ? u_begin : 0u, hi = at == c_end ? u_end : isize;
         if (hi > isize || lo > hi) { set_error("virtual offset beyond its block in %s", path); return CRATAC_ERR_ARG; }
-        blocks.push_back(Blk{p + 12 + xlen, (size_t)bsize - 12 - xlen - 8, total, isize, lo, hi});
+        blocks.push_back(Blk{p + 12 + xlen, bsize - 12 - xlen - 8, total, isize, lo, hi});
         total += hi - lo;
-        p += (size_t)bsize;
+        p += bsize;
     }
     *nbytes = total;
     if (cap == 0 || !out) return CRATAC_OK;
@@ -1026,7 +1036,7 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
             const bool whole = k.lo == 0 && k.hi == k.isize;
             if (!whole) part.resize(k.isize);
             unsigned char* dst = whole ? reinterpret_cast<unsigned char*>(out) + k.out_off : part.data();
-            if (!inflate_block(&zs, scratch.data(), &buf[k.off], k.csize, dst, k.isize)) { failed = 1; break; }
+            if (!inflate_block_checked(&zs, scratch.data(), &buf[k.off], k.csize, dst, k.isize)) { failed = 1; break; }
             if (!whole && k.hi > k.lo) memcpy(out + k.out_off, part.data() + k.lo, k.hi - k.lo);
         }
         inflateEnd(&zs);

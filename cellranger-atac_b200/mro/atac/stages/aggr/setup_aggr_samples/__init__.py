@@ -75,14 +75,14 @@ def main(args, outs):
             mask |= (cells['is_{}_cell_barcode'.format(species)] == 1).values
         sel = cells[mask]
         total = sel['total'] if 'total' in sel.columns else sel['passed_filters'] + sel['duplicate']
-        info['total_fragments_per_cell'] = np.median(total)
-        info['unique_fragments_per_cell'] = np.median(sel['passed_filters'])
+        info['total_fragments_per_cell'] = float(np.median(total))
+        info['unique_fragments_per_cell'] = float(np.median(sel['passed_filters']))
         if args.normalization in SIGNAL_NORMALIZATIONS:
             threshold, signal_mean = library_signal(args.reference_path, row['fragments'])
             info['original_threshold'] = threshold
             info['signal_mean'] = signal_mean
     with open(outs.library_info, 'wb') as f:
-        pickle.dump(library_info, f)
+        pickle.dump(library_info, f, protocol=2)      # py2 consumers (the rest of the 1.2.0 pipeline) read protocol <= 2
 
 
 def join(args, outs, chunk_defs, chunk_outs):
@@ -102,7 +102,7 @@ def join(args, outs, chunk_defs, chunk_outs):
             library_info[n]['kind'] = kind
             library_info[n]['rate'] = lowest / library_info[n][key]
     with open(outs.library_info, 'wb') as f:
-        pickle.dump(library_info, f)
+        pickle.dump(library_info, f, protocol=2)      # py2 consumers (the rest of the 1.2.0 pipeline) read protocol <= 2
     outs.gem_group_index = {"gem_group_index": {n: (library_info[n]['library_id'], 1) for n in library_info}}
     with open(outs.gem_group_index_json, 'w') as f:
         json.dump(outs.gem_group_index, f)

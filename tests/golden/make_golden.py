@@ -340,6 +340,45 @@ def make_em_cases():
     return cases
 
 
+def random_mixture_histogram(seed):
+    """Seeded window-count histogram drawn straight from a zero-noise + background-NB + signal mixture with
+    randomised sizes, dispersions and signal tails (60 of them pin the fit at 1e-8, tests/golden/em_random.json)."""
+    rng = np.random.default_rng(seed)
+    n_zero = int(rng.integers(50000, 600000))
+    n_bg = int(rng.integers(150000, 1200000))
+    n_sig = int(rng.integers(1500, 30000))
+    r = float(rng.uniform(2.0, 12.0))
+    p = float(rng.uniform(0.15, 0.6))
+    tail = float(rng.uniform(0.008, 0.05))
+    shift = int(rng.integers(5, 40))
+    vals = np.concatenate([rng.geometric(float(rng.uniform(0.3, 0.7)), size=n_zero),
+                           rng.negative_binomial(r, p, size=n_bg) + 1,
+                           rng.geometric(tail, size=n_sig) + shift])
+    b = np.bincount(vals)
+    return {int(k): int(b[k]) for k in np.nonzero(b)[0] if k > 0}
+
+
+def _fit_one_random(seed):
+    ref = reference_em()
+    cd = random_mixture_histogram(seed)
+    case = dict(name="random_%d" % seed, values=sorted(cd), weights=[cd[k] for k in sorted(cd)])
+    try:
+        thr, params = ref.estimate_final_threshold(dict(cd), 1 / 5)
+    except Exception as exc:
+        case["raises"] = type(exc).__name__
+        return case
+    case["threshold"] = None if thr is None else int(thr)
+    case["params"] = None if params is None else [float(x) for x in params]
+    return case
+
+
+def make_em_random_cases(n=60):
+    """The reference's own estimate_final_threshold (analysis/peaks.py, unmodified) on n seeded histograms."""
+    import multiprocessing
+    with multiprocessing.Pool(min(8, os.cpu_count() or 1)) as pool:
+        return pool.map(_fit_one_random, range(1000, 1000 + n))
+
+
 def make_matrix_cases(tmpdir):
     rng = np.random.default_rng(77)
     cases = []
@@ -817,6 +856,9 @@ def main():
         if not only or "insert_sizes" in only:
             with open(os.path.join(HERE, "insert_sizes.json"), "w") as f:
                 json.dump(make_insert_size_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "em_random" in only:
+            with open(os.path.join(HERE, "em_random.json"), "w") as f:
+                json.dump(make_em_random_cases(), f, separators=(",", ":"))
         if not only or "em" in only:
             with open(os.path.join(HERE, "em.json"), "w") as f:
                 json.dump(make_em_cases(), f, separators=(",", ":"))

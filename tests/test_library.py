@@ -198,9 +198,8 @@ def test_own_deflate_decoder_against_zlib(tmp_path):
 
 
 def test_corrupt_bgzf_blocks_fail_cleanly(tmp_path):
-    """Damaged payloads: the own decoder declines, zlib confirms -> an error (or, when the damage still decodes to the
-    right size, some output: BGZF's CRC is not checked here, as `gzip -dc | ...` consumers of a truncated pipe would not
-    see it either) -- never a crash or an out-of-bounds write."""
+    """Damaged payloads: the own decoder declines and zlib confirms, or the block's CRC-32 does not match -> an error;
+    never a crash or an out-of-bounds write (damage confined to header bytes gzip ignores may still decode)."""
     rng = np.random.default_rng(21)
     text = synth.to_text(synth.generate(synth.GRCH38[:1], 6000, 10, 20, seed=3))
     blob = bytearray(bgzf.compress(text, 6))
@@ -218,7 +217,49 @@ def test_corrupt_bgzf_blocks_fail_cleanly(tmp_path):
             outcomes["decoded"] += 1
         except _ffi.CratacError:
             outcomes["error"] += 1
-    assert outcomes["error"] > 100
+    assert outcomes["error"] > 250
+
+
+def test_malformed_bgzf_headers_fail_cleanly(tmp_path):
+    """a BSIZE smaller than the block's own header + trailer, an extra field running past the block, an ISIZE
+    above 64 KiB and a truncated last block must come back as errors (never an out-of-bounds read of the mapping); a
+    payload whose CRC-32 does not match the trailer is an error too, as it is for the reference's `gzip -c -d` pipe
+    (lib/python/tools/io.py:197-217)."""
+    import struct
+    text = synth.to_text(synth.generate(synth.GRCH38[:1], 4000, 10, 20, seed=5))
+    blob = bytearray(bgzf.compress(text, 6))
+    p = str(tmp_path / "bad.gz")
+
+    def expect_error(data, ranged=True, gzip_readable=False):
+        with open(p, "wb") as f:
+            f.write(data)
+        if gzip_readable:        # only the BGZF extra field is damaged: the file is still a valid multi-member gzip, which
+            assert _ffi.inflate_file(p, threads=2).tobytes() == text   # the sequential path reads as `gzip -d` would
+        else:
+            with pytest.raises(_ffi.CratacError):
+                _ffi.inflate_file(p, threads=2)
+        if ranged:
+            with pytest.raises(_ffi.CratacError):
+                _ffi.inflate_range(p, 0, (len(data) - 28) << 16, threads=2)
+
+    for bsize in (0, 3, 11, 17, 24):                     # BSIZE field = block size - 1: smaller than header + trailer
+        bad = bytearray(blob)
+        bad[16:18] = struct.pack("<H", bsize)
+        expect_error(bad, gzip_readable=True)
+    bad = bytearray(blob)
+    bad[10:12] = struct.pack("<H", 60000)                # XLEN beyond the block
+    expect_error(bad)
+    bad = bytearray(blob)
+    bs = struct.unpack("<H", bytes(blob[16:18]))[0] + 1
+    bad[bs - 4:bs] = struct.pack("<I", 1 << 20)          # ISIZE above the BGZF limit
+    expect_error(bad)
+    expect_error(blob[:bs - 3], ranged=False)            # file ends inside the first block
+    bad = bytearray(blob)
+    bad[bs - 8] ^= 0x5A                                  # CRC-32 of the first block
+    expect_error(bad)
+    with open(p, "wb") as f:                             # and the undamaged file still reads
+        f.write(blob)
+    assert _ffi.inflate_file(p, threads=2).tobytes() == text
 
 
 def test_own_deflate_decoder_under_sanitizers(tmp_path):

@@ -34,6 +34,9 @@ class OracleShard(object):
         self.contigs, self.primary, self.text, self.first_contig = contigs, primary, text, first_contig
         self.names = [c[0] for c in contigs]
 
+    def check_stream(self):
+        pass
+
     def decode(self):
         o = util.oracle_decode(self.text, self.names)
         self.o = o
