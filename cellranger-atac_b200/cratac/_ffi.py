@@ -48,6 +48,7 @@ SIGNATURES = {
     "cratac_destroy": (None, [c_vp]),
     "cratac_set_option": (c_int, [c_vp, c_cp, c_i64]),
     "cratac_launch_count": (c_i64, [c_vp, c_int]),
+    "cratac_decode_declined": (c_i64, [c_vp, c_int]),
     "cratac_synchronize": (c_int, [c_vp]),
     "cratac_stream": (c_int, [c_vp, P(ctypes.c_uint64)]),
     "cratac_num_stages": (c_int, []),
@@ -168,6 +169,10 @@ class Context(object):
 
     def launch_count(self, reset=False):
         return int(self._lib.cratac_launch_count(self._h, 1 if reset else 0))
+
+    def decode_declined(self, reset=False):
+        """Text ranges the single-pass decoder handed to the general parse kernel (0 on a clean file)."""
+        return int(self._lib.cratac_decode_declined(self._h, 1 if reset else 0))
 
     def synchronize(self):
         check(self._lib.cratac_synchronize(self._h))

@@ -142,6 +142,7 @@ int cratac_create(int device, int n_contigs, const char* const* contig_names, co
     if ((rc = c->d_status.reserve(sizeof(int64_t) * ST_SLOTS)) != CRATAC_OK) { delete h; return rc; }
     cudaMemsetAsync(c->d_status.p, 0, sizeof(int64_t) * ST_SLOTS, c->stream);
     if (cudaMallocHost(&c->h_status, sizeof(int64_t) * ST_SLOTS) != cudaSuccess) { set_error("cudaMallocHost failed"); delete h; return CRATAC_ERR_CUDA; }
+    if (cudaMallocHost(&c->h_sp_scalars, sizeof(int64_t) * 8) != cudaSuccess) { set_error("cudaMallocHost failed"); delete h; return CRATAC_ERR_CUDA; }
     memset(c->h_status, 0, sizeof(int64_t) * ST_SLOTS);
     if ((rc = upload_i64(c, c->d_contig_lens, c->contig_lens)) || (rc = upload_i64(c, c->d_contig_base, c->contig_base)) ||
         (rc = upload_i64(c, c->d_contig_tile_off, c->contig_tile_off)) || (rc = upload_i64(c, c->d_contig_pidx_off, c->contig_pidx_off))) {
@@ -167,6 +168,7 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
+    if (c->h_sp_scalars) cudaFreeHost(c->h_sp_scalars);
     if (c->h_bc_hash) cudaFreeHost(c->h_bc_hash);
     if (c->h_bc_order) cudaFreeHost(c->h_bc_order);
     if (c->h_c2d_pin) cudaFreeHost(c->h_c2d_pin);
@@ -195,6 +197,8 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "stream_decode")) { c->stream_decode = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
     if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
+    if (!strcmp(key, "decode_kernel")) { c->decode_kernel = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "decode_ctas_per_sm")) { c->sp_ctas_per_sm = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
         c->profile = value != 0;
@@ -202,6 +206,12 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     }
     set_error("unknown option '%s'", key);
     return CRATAC_ERR_ARG;
+}
+
+int64_t cratac_decode_declined(cratac_ctx* h, int reset) {
+    int64_t n = h->c.decode_declined;
+    if (reset) h->c.decode_declined = 0;
+    return n;
 }
 
 int64_t cratac_launch_count(cratac_ctx* h, int reset) {

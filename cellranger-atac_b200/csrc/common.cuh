@@ -164,6 +164,13 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;    // chunked H2D of a host text (decode_text_streamed)
     cudaEvent_t copy_event = nullptr;
     DevBuf d_stream_scalars;               // running line base + chunk total of the streamed decode
+    // single-pass decode (k_parse_stream): look-back words per tile, {ticket, declined ranges, line base}, declined ranges
+    DevBuf d_sp_state, d_sp_scalars, d_sp_irr;
+    int64_t sp_irr_cap = 0;
+    int64_t* h_sp_scalars = nullptr;       // pinned mirror of d_sp_scalars (4 words)
+    int decode_kernel = 1;                 // option "decode_kernel": 0 two passes (count + parse), 1 single pass with 16 KiB tiles, 2 with 32 KiB tiles
+    int sp_ctas_per_sm = 0;                // option "decode_ctas_per_sm": cap on resident CTAs of k_parse_stream (0: occupancy)
+    int64_t decode_declined = 0;           // text ranges the single-pass kernel handed to the general kernel (since creation)
     int stream_decode = 1;                 // option "stream_decode": 0 off, 1 overlap the H2D copy of a host text >= 64 MiB with its decode, 2 always
     int64_t stream_chunk_tiles = 0;        // option "stream_chunk_tiles": text tiles per chunk (0: 128 MiB worth)
     int defer_sync = 0;                    // 1: window_histogram / compact_histogram / fit_threshold_device only queue their work

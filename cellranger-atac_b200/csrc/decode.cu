@@ -128,7 +128,15 @@ struct DecodeArgs {
     int64_t tile0;
     const int64_t* line_base;
     int64_t line_cap;                 // capacity of the output arrays when the total is not known in advance (0: exact)
+    // the two-pass path uses DEC_TILE-byte tiles numbered by blockIdx; as the general-path fallback of k_parse_stream the
+    // kernel is given the list of byte ranges that kernel declined (each with its line count and first output line)
+    const struct IrrTile* irr;        // null: tile = blockIdx.x + tile0
 };
+// one range of text handed from k_parse_stream to k_parse_tiles: [byte_base, byte_base + nbytes) (nbytes a multiple of
+// 16, at most DEC_TILE), the lines whose '\n' lies inside it, the output index of the first of them, and how many of
+// them are already committed
+struct IrrTile { int64_t byte_base; int64_t out_base; int32_t nbytes; int32_t n_lines; int32_t skip; int32_t pad; };
+static_assert(sizeof(IrrTile) == 32, "IrrTile layout");
 
 __device__ __forceinline__ unsigned byte_at(const uint32_t* words, int p) { return (words[p >> 2] >> ((p & 3) * 8)) & 0xFFu; }
 
@@ -161,14 +169,21 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int64_t tile = (int64_t)blockIdx.x + a.tile0;
-    const int64_t tile_base = tile * DEC_TILE;
-    const int n_lines = a.tile_counts[tile];
+    int64_t tile_base, out_base;
+    int TB, n_lines, skip = 0;
+    if (a.irr) {
+        const IrrTile e = a.irr[blockIdx.x];
+        tile_base = e.byte_base; out_base = e.out_base; TB = e.nbytes; n_lines = e.n_lines; skip = e.skip;
+    } else {
+        const int64_t tile = (int64_t)blockIdx.x + a.tile0;
+        tile_base = tile * DEC_TILE; TB = DEC_TILE; n_lines = a.tile_counts[tile];
+        out_base = a.tile_offsets[tile] + (a.line_base ? *a.line_base : 0);
+    }
     if (n_lines == 0) return;   // uniform per CTA
     const int64_t src0 = tile_base - DEC_LOOKBACK;
 
-    // ---- stage bytes [src0, tile_base + DEC_TILE) into shared memory: one TMA bulk copy when the tile is interior
-    const bool full = a.use_tma && src0 >= 0 && tile_base + DEC_TILE <= a.nbytes;
+    // ---- stage bytes [src0, tile_base + TB) into shared memory: one TMA bulk copy when the tile is interior
+    const bool full = a.use_tma && src0 >= 0 && tile_base + TB <= a.nbytes && (src0 & 15) == 0;
     if (full) {
         if (tid == 0) {
             mbar_init(&bar, 1);
@@ -176,12 +191,12 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bar, DEC_LOOKBACK + DEC_TILE);
-            tma_load_1d(buf, a.text + src0, DEC_LOOKBACK + DEC_TILE, &bar);
+            mbar_expect_tx(&bar, DEC_LOOKBACK + TB);
+            tma_load_1d(buf, a.text + src0, DEC_LOOKBACK + TB, &bar);
         }
-        if (!mbar_wait(&bar, 0)) { if (tid == 0) raise_error(a.status, CRATAC_ERR_INTERNAL, -100 - tile); return; }
+        if (!mbar_wait(&bar, 0)) { if (tid == 0) raise_error(a.status, CRATAC_ERR_INTERNAL, -100 - tile_base / DEC_TILE); return; }
     } else {
-        for (int i = tid; i < DEC_LOOKBACK + DEC_TILE; i += DEC_THREADS) {
+        for (int i = tid; i < DEC_LOOKBACK + TB; i += DEC_THREADS) {
             int64_t p = src0 + i;
             unsigned char ch = '\n';
             if (p >= 0 && p < a.nbytes) ch = (unsigned char)a.text[p];
@@ -207,9 +222,10 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
             lb_masks[tid] = swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) | (swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << 16);
         }
     }
-    // bytes at or beyond n_eff are padding newlines of the last tile: they terminate nothing
+    // bytes at or beyond n_eff are padding newlines of the last tile: they terminate nothing; bytes at or beyond
+    // the tile's own TB bytes are not staged at all
     {
-        int64_t lim = a.n_eff - (tile_base + (int64_t)tid * PER_THREAD);
+        int64_t lim = min(a.n_eff, tile_base + TB) - (tile_base + (int64_t)tid * PER_THREAD);
         if (lim < PER_THREAD) {
             const unsigned long long keep = lim <= 0 ? 0ULL : ((1ULL << lim) - 1ULL);
             mask &= keep; tmask &= keep;
@@ -260,14 +276,13 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     }
     __syncthreads();
     if (n_lines > DEC_MAX_LINES || s_first_begin < 0) {
-        if (tid == 0) raise_error(a.status, CRATAC_ERR_PARSE, a.tile_offsets[tile]);
+        if (tid == 0) raise_error(a.status, CRATAC_ERR_PARSE, out_base);
         return;
     }
 
     // ---- one line per thread: tabs from the chunk masks, numbers and barcode a word at a time
-    const int64_t out_base = a.tile_offsets[tile] + (a.line_base ? *a.line_base : 0);
     int loc_maxpos = 0, loc_maxneg = 0;
-    for (int li = tid; li < n_lines; li += DEC_THREADS) {
+    for (int li = tid + skip; li < n_lines; li += DEC_THREADS) {
         int b = li == 0 ? s_first_begin : nlpos[li - 1] + 1;
         int e = nlpos[li];
         int64_t line_no = out_base + li;
@@ -361,6 +376,458 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     if (lane == 0) {
         if (loc_maxpos > 0) atomicMax(reinterpret_cast<long long*>(&a.status[ST_MAX_POS_LEN]), (long long)loc_maxpos);
         if (loc_maxneg > 0) atomicMax(reinterpret_cast<long long*>(&a.status[ST_MAX_NEG_LEN]), (long long)loc_maxneg);
+    }
+}
+
+// ------------------------------------------------------------------ single pass: k_parse_stream
+// One read of the text.  Persistent CTAs take tiles from a ticket counter, so tiles start in index order; the next tile is
+// already on its way into the second shared-memory buffer (TMA bulk copy) while the current one is parsed.  A tile is
+// [t * TB, (t + 1) * TB) with SP_LB look-back bytes in front of it; a line belongs to the tile that holds its '\n'.
+//
+//  1. separator bits (bytes below 0x0b: tab, newline and, never in a valid file, 0x00-0x08) of every 16-byte chunk, three
+//     integer instructions per word and one multiply to gather four flags; chunks are dealt round-robin to the threads
+//     (conflict-free 128-bit shared loads) and the 16-bit masks go through shared memory so that
+//  2. thread i owns the masks of CPT consecutive chunks: popcounts -> block scan -> ONE ordered list of separator positions.
+//     In a well-formed tile the separators of a line are five consecutive entries (four tabs, the newline) and the entry
+//     before them is the previous line's newline.  The five bytes are checked per line (and the tabs of the unfinished last
+//     line), so the structure is not assumed but verified; the look-back gives the number of tabs of the first line that lie
+//     before the tile.
+//  3. the tile's line count is published (decoupled look-back: aggregate first, inclusive prefix once known) and the last
+//     warp resolves the tile's first output line while the other warps already parse.
+//  4. groups of SP_THREADS lines: fields parsed a word at a time into registers, `bad` OR-reduced over the CTA, then the
+//     barcode table insert and the five coalesced stores.
+// Anything outside the common shape (a line longer than the look-back, a stray control byte, blanks for strip() to remove,
+// a field that does not parse, an unknown contig) is not handled here: the tile -- or what is left of it -- is handed to
+// k_parse_tiles (the general kernel above), which also raises the errors.  Nothing is committed for a line before its whole
+// group has parsed, so the hand-over is exact.
+constexpr int SP_THREADS = 256;
+constexpr int SP_LB = 64;                       // look-back bytes = the chunks of thread 0
+constexpr int SP_PAD = 16;                      // slack before and after the staged bytes (word windows may over-read)
+constexpr unsigned long long SP_FLAG_AGG = 1ULL << 62, SP_FLAG_INC = 2ULL << 62, SP_VALUE_MASK = (1ULL << 62) - 1ULL;
+
+struct StreamArgs {
+    DecodeArgs d;                 // text, tables, outputs, status (tile arrays unused)
+    int tile_bytes;               // TB: multiple of 16, SP_LB + TB <= SP_THREADS * CPT * 16
+    int64_t n_tiles;              // tiles of this launch: global tiles tile0 .. tile0 + n_tiles - 1
+    int64_t tile0;
+    unsigned long long* state;    // [n_tiles] look-back words of this launch (zeroed)
+    unsigned long long* ticket;   // zeroed
+    const int64_t* line_base;     // lines before this launch
+    int64_t* line_base_out;       // written by the last tile: lines before the next launch (a different word: earlier tiles may still read line_base)
+    IrrTile* irr;                 // declined ranges, appended
+    unsigned long long* n_irr;
+    int64_t irr_cap;
+};
+
+// separator flags (bit 7 of every byte below 0x0b), exact for all 256 byte values
+__device__ __forceinline__ uint32_t sp_sepflags(uint32_t w) {
+    const uint32_t x = (w & 0x7f7f7f7fu) + 0x75757575u;      // bit 7 set iff the low 7 bits are >= 0x0b
+    return ~(x | w) & 0x80808080u;
+}
+// the four flags (bits 7, 15, 23, 31) gathered into the top nibble: no two partial products meet
+__device__ __forceinline__ uint32_t sp_gather(uint32_t f) { return f * 0x00204081u; }
+__device__ __forceinline__ uint32_t sp_sepmask16(uint4 v) {
+    uint32_t m = sp_gather(sp_sepflags(v.w)) >> 28;
+    m = __funnelshift_l(sp_gather(sp_sepflags(v.z)), m, 4);
+    m = __funnelshift_l(sp_gather(sp_sepflags(v.y)), m, 4);
+    m = __funnelshift_l(sp_gather(sp_sepflags(v.x)), m, 4);
+    return m;
+}
+
+// decimal field of 1..10 digits ending at byte e (exclusive), 32-bit arithmetic only: the last 8 bytes are loaded as two
+// words, bytes in front of the field are replaced by '0', all 8 are checked to be digits and folded 1 -> 2 -> 4 -> 8 digits
+__device__ __forceinline__ bool sp_parse_uint(const uint32_t* words, int p, int e, int32_t* out) {
+    const int len = e - p;
+    if (len < 1 || len > 10) return false;
+    uint32_t lo = swar_get4(words, e - 8), hi = swar_get4(words, e - 4);
+    const int s = 8 * (8 - len);                                   // bits of (hi:lo) in front of the field (when len < 8)
+    if (s > 0) {
+        const uint32_t mlo = s >= 32 ? 0xFFFFFFFFu : ((1u << s) - 1u);
+        const uint32_t mhi = s > 32 ? ((1u << (s - 32)) - 1u) : 0u;
+        lo = (lo & ~mlo) | (0x30303030u & mlo);
+        hi = (hi & ~mhi) | (0x30303030u & mhi);
+    }
+    const uint32_t xl = lo ^ 0x30303030u, xh = hi ^ 0x30303030u;   // digits -> 0..9
+    uint32_t bad = ((xl + 0x76767676u) | xl | (xh + 0x76767676u) | xh) & 0x80808080u;
+    uint32_t a = (xl * 2561u) >> 8 & 0x00FF00FFu;                  // 10 * d0 + d1 per byte pair
+    a = (a * 6553601u) >> 16;                                      // 4 digits
+    uint32_t b = (xh * 2561u) >> 8 & 0x00FF00FFu;
+    b = (b * 6553601u) >> 16;
+    uint32_t val = a * 10000u + b;
+    if (len > 8) {                                                 // 9 or 10 digits: the leading one or two by hand
+        const uint32_t w = swar_get4(words, p);
+        uint32_t d0 = (w & 0xFFu) - 0x30u, head = d0;
+        bad |= (d0 > 9u) ? 1u : 0u;
+        if (len == 10) {
+            const uint32_t d1 = ((w >> 8) & 0xFFu) - 0x30u;
+            bad |= (d1 > 9u) ? 1u : 0u;
+            head = d0 * 10u + d1;
+            if (head > 21u || (head == 21u && val > 47483647u)) bad |= 1u;   // above INT32_MAX
+        }
+        val += head * 100000000u;
+    }
+    *out = (int32_t)val;
+    return bad == 0u;
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
+    constexpr int REGION_MAX = SP_THREADS * CPT * 16;              // look-back + tile bytes
+    constexpr int MAX_SEPS = REGION_MAX / 6;                       // 5 separators per line of >= 30 bytes (typical: 45)
+    extern __shared__ __align__(128) unsigned char sp_smem[];
+    uint32_t* bufw0 = reinterpret_cast<uint32_t*>(sp_smem);
+    uint32_t* bufw1 = bufw0 + (SP_PAD + REGION_MAX + SP_PAD) / 4;
+    uint16_t* masks = reinterpret_cast<uint16_t*>(bufw1 + (SP_PAD + REGION_MAX + SP_PAD) / 4);   // [SP_THREADS * CPT]
+    uint16_t* seplist = masks + SP_THREADS * CPT;                                                  // [MAX_SEPS]
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int warp_tot[SP_THREADS / 32];
+    __shared__ int64_t s_tile[2];
+    __shared__ int s_r, s_irregular;
+    __shared__ long long s_excl;
+    __shared__ int s_nl_parts[3];
+
+    const DecodeArgs& d = a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TB = a.tile_bytes;
+    const int region = SP_LB + TB;
+    const int n_chunks = region >> 4;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int c = tid; c < SP_THREADS * CPT; c += SP_THREADS) masks[c] = 0;    // chunks beyond the region stay empty
+    __syncthreads();
+
+    auto tile_is_tma = [&](int64_t t) -> bool {     // t: tile of this launch
+        const int64_t g = t + a.tile0;
+        return d.use_tma && g * TB - SP_LB >= 0 && (g + 1) * TB <= d.nbytes;
+    };
+    auto issue = [&](int64_t t, int b) {            // thread 0
+        uint32_t* w = b ? bufw1 : bufw0;
+        mbar_expect_tx(&bar[b], (uint32_t)region);
+        tma_load_1d(reinterpret_cast<unsigned char*>(w) + SP_PAD, d.text + (t + a.tile0) * TB - SP_LB, (uint32_t)region, &bar[b]);
+    };
+    if (tid == 0) {
+        const int64_t t = (int64_t)atomicAdd(a.ticket, 1ULL);
+        s_tile[0] = t;
+        if (t < a.n_tiles && tile_is_tma(t)) issue(t, 0);
+    }
+    __syncthreads();
+
+    uint32_t phase0 = 0, phase1 = 0;
+    int cur = 0;
+    unsigned long long ckey_cache = 0xFFFFFFFFFFFFFFFFULL;   // last contig name seen by this thread and its id
+    int32_t cid_cache = -1;
+    int loc_maxpos = 0, loc_maxneg = 0;
+
+    for (;;) {
+        const int64_t t = s_tile[cur];
+        if (t >= a.n_tiles) break;
+        const int64_t gt = t + a.tile0;
+        const int64_t tile_base = gt * TB;
+        uint32_t* const bufw = cur ? bufw1 : bufw0;
+        const uint32_t* const words = bufw + SP_PAD / 4;            // byte position 0 = first look-back byte
+        unsigned char* const bytes = reinterpret_cast<unsigned char*>(bufw) + SP_PAD;
+        if (tid == 0) {                                             // next tile: ticket now, bytes in flight while this one is parsed
+            const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
+            s_tile[cur ^ 1] = tn;
+            if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur ^ 1);
+        }
+        if (tile_is_tma(t)) {
+            const bool ok = mbar_wait(&bar[cur], cur ? phase1 : phase0);
+            if (cur) phase1 ^= 1; else phase0 ^= 1;
+            if (!ok) { if (tid == 0) raise_error(d.status, CRATAC_ERR_INTERNAL, -100 - gt); return; }
+        } else {
+            const int64_t src0 = tile_base - SP_LB;
+            for (int i = tid; i < region; i += SP_THREADS) {
+                const int64_t p = src0 + i;
+                bytes[i] = (p >= 0 && p < d.nbytes) ? (unsigned char)d.text[p] : (unsigned char)'\n';   // before the file / virtual terminator
+            }
+            __syncthreads();
+        }
+
+        // ---- 1. separator masks, chunk c -> thread c % SP_THREADS
+        const int64_t lim = d.n_eff - (tile_base - SP_LB);           // region bytes at or beyond it are padding
+        for (int c = tid; c < n_chunks; c += SP_THREADS) {
+            const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * c);
+            uint32_t m = sp_sepmask16(v);
+            if (lim < region) {                                      // last tile only
+                const int64_t keep = lim - 16 * (int64_t)c;
+                m = keep <= 0 ? 0u : (keep >= 16 ? m : (m & ((1u << keep) - 1u)));
+            }
+            masks[c] = (uint16_t)m;
+        }
+        __syncthreads();
+
+        // ---- 2. ordered separator list; thread i owns chunks [i * CPT, (i + 1) * CPT)
+        unsigned long long mk[CPT / 4];
+        int my_cnt = 0;
+#pragma unroll
+        for (int q = 0; q < CPT / 4; q++) {
+            const uint2 v = *reinterpret_cast<const uint2*>(masks + tid * CPT + 4 * q);
+            mk[q] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+            my_cnt += __popcll(mk[q]);
+        }
+        int incl = my_cnt;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lane >= dd) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        if (tid == 0) {
+            // first line of the tile: tabs after the last newline of the look-back (thread 0's chunks ARE the look-back
+            // when CPT == 4; with CPT == 8 the look-back is the first half of them)
+            unsigned long long lb = mk[0];
+            int r = 0, found = 0, irregular = 0;
+            while (lb) {
+                const int j = 63 - __clzll((long long)lb);
+                lb &= ~(1ULL << j);
+                const unsigned ch = bytes[j];
+                if (ch == '\n') { found = 1; break; }
+                if (ch != '\t' || ++r > 4) { irregular = 1; break; }
+            }
+            if (!found) irregular = 1;                               // a line longer than the look-back
+            s_r = r; s_irregular = irregular;
+        }
+        __syncthreads();
+        int woff = 0, s_all = 0;
+#pragma unroll
+        for (int w = 0; w < SP_THREADS / 32; w++) { const int x = warp_tot[w]; if (w < warp) woff += x; s_all += x; }
+        {
+            int idx = woff + incl - my_cnt;
+#pragma unroll
+            for (int q = 0; q < CPT / 4; q++) {
+                unsigned long long m = mk[q];
+                const int pos0 = (tid * CPT + 4 * q) * 16;
+                while (m) {
+                    const int j = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (idx < MAX_SEPS) seplist[idx] = (uint16_t)(pos0 + j);
+                    idx++;
+                }
+            }
+        }
+        __syncthreads();
+        // separators of the look-back (the first SP_LB bytes = the first 4 chunks), straight from their masks
+        int n_lb;
+        {
+            const uint2 v = *reinterpret_cast<const uint2*>(masks);
+            n_lb = __popc(v.x) + __popc(v.y);
+        }
+        const int first = n_lb - s_r;                                // list index of the first line's first separator
+        const int q_seps = s_all - first;
+        const int n_lines = q_seps / 5;
+        const int rem = q_seps - 5 * n_lines;
+        bool bad = s_irregular != 0 || s_all > MAX_SEPS;
+
+        // ---- structure check: tab tab tab tab newline for every line, tabs only after the last newline
+        if (!bad) {
+            for (int li = tid; li < n_lines; li += SP_THREADS) {
+                const int k = first + 5 * li;
+                const unsigned b0 = bytes[seplist[k]], b1 = bytes[seplist[k + 1]], b2 = bytes[seplist[k + 2]], b3 = bytes[seplist[k + 3]], b4 = bytes[seplist[k + 4]];
+                if ((b0 | (b1 << 8) | (b2 << 16) | (b3 << 24)) != 0x09090909u || b4 != '\n') bad = true;
+            }
+            if (tid == SP_THREADS - 1)
+                for (int k = 0; k < rem; k++) if (bytes[seplist[first + 5 * n_lines + k]] != '\t') bad = true;
+        }
+        const bool irregular = __syncthreads_or(bad ? 1 : 0) != 0;
+
+        // ---- exact line count of a declined tile: newlines of the tile region, per half (k_parse_tiles takes <= DEC_TILE bytes)
+        int tile_lines = n_lines;
+        const int half = ((TB / 2) + 15) & ~15;                      // first sub-range [0, half), second [half, TB)
+        if (irregular) {
+            int c0 = 0, c1 = 0;
+            for (int i = tid; i < TB; i += SP_THREADS) {
+                const int64_t p = tile_base + i;
+                const bool nl = p < d.n_eff && bytes[SP_LB + i] == '\n';
+                if (nl) { if (i < half) c0++; else c1++; }
+            }
+#pragma unroll
+            for (int dd = 16; dd; dd >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, dd); c1 += __shfl_xor_sync(0xffffffffu, c1, dd); }
+            if (tid == 0) { s_nl_parts[0] = 0; s_nl_parts[1] = 0; }
+            __syncthreads();
+            if (lane == 0) { atomicAdd(&s_nl_parts[0], c0); atomicAdd(&s_nl_parts[1], c1); }
+            __syncthreads();
+            tile_lines = s_nl_parts[0] + s_nl_parts[1];
+        }
+
+        // ---- 3. publish the count, resolve the first output line (last warp), meanwhile parse
+        if (warp == SP_THREADS / 32 - 1) {
+            if (lane == 0) st_release_u64(&a.state[t], SP_FLAG_AGG | (unsigned long long)tile_lines);
+            long long excl = 0;
+            if (t == 0) {
+                excl = *a.line_base;
+            } else {
+                int64_t look = t - 1;
+                for (;;) {
+                    const int64_t idx = look - lane;
+                    unsigned long long v;
+                    if (idx >= 0) {
+                        int spins = 0;
+                        do { v = ld_acquire_u64(&a.state[idx]); } while ((v >> 62) == 0 && ++spins < (1 << 24));
+                    } else {
+                        v = idx == -1 ? (SP_FLAG_INC | (unsigned long long)*a.line_base) : SP_FLAG_AGG;   // virtual tile before the launch
+                    }
+                    const unsigned has_inc = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const unsigned stuck = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+                    if (stuck) { if (lane == 0) raise_error(d.status, CRATAC_ERR_INTERNAL, -200 - gt); excl = -1; break; }
+                    long long contrib = (long long)(v & SP_VALUE_MASK);
+                    if (has_inc) {
+                        const int fp = __ffs(has_inc) - 1;           // nearest predecessor with an inclusive prefix
+                        if (lane > fp) contrib = 0;
+                    }
+#pragma unroll
+                    for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
+                    excl += contrib;
+                    if (has_inc) break;
+                    look -= 32;
+                }
+            }
+            if (lane == 0) {
+                if (excl >= 0) st_release_u64(&a.state[t], SP_FLAG_INC | (unsigned long long)(excl + tile_lines));
+                s_excl = excl;
+                if (excl >= 0 && t == a.n_tiles - 1) *a.line_base_out = excl + tile_lines;
+            }
+        }
+
+        if (irregular) {
+            __syncthreads();                                         // s_excl
+            if (tid == 0 && s_excl >= 0) {
+                const int n_parts = TB > DEC_TILE ? 2 : 1;
+                const unsigned long long at = atomicAdd(a.n_irr, (unsigned long long)n_parts);
+                if ((int64_t)(at + n_parts) <= a.irr_cap) {
+                    if (n_parts == 1) {
+                        a.irr[at] = IrrTile{tile_base, s_excl, TB, tile_lines, 0, 0};
+                    } else {
+                        a.irr[at] = IrrTile{tile_base, s_excl, half, s_nl_parts[0], 0, 0};
+                        a.irr[at + 1] = IrrTile{tile_base + half, s_excl + s_nl_parts[0], TB - half, s_nl_parts[1], 0, 0};
+                    }
+                } else {
+                    raise_error(d.status, CRATAC_ERR_INTERNAL, -300 - gt);
+                }
+            }
+            if (s_excl < 0) return;
+            cur ^= 1;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- 4. groups of SP_THREADS lines
+        bool published_seen = false;
+        for (int base = 0; base < n_lines; base += SP_THREADS) {
+            const int li = base + tid;
+            bool ok = true;
+            int32_t v_start = 0, v_end = 0, v_dup = 0, cid = -1;
+            unsigned long long key = 0;
+            int bc_pos = 0, bc_len = 0;
+            if (li < n_lines) {
+                const int k = first + 5 * li;
+                const int b = seplist[k - 1] + 1;
+                const int t0 = seplist[k], t1 = seplist[k + 1], t2 = seplist[k + 2], t3 = seplist[k + 3], e = seplist[k + 4];
+                bc_pos = t2 + 1; bc_len = t3 - t2 - 1;
+                key = barcode_key_words(words, bc_pos, bc_len);
+                ok = sp_parse_uint(words, t0 + 1, t1, &v_start) & sp_parse_uint(words, t1 + 1, t2, &v_end) & (t0 > b) & (bc_len > 0);
+                {                                                    // the duplicate count is a single digit nearly always
+                    const int dl = e - t3 - 1;
+                    if (dl == 1) { const unsigned dg = (unsigned)bytes[t3 + 1] - 0x30u; v_dup = (int32_t)dg; ok &= dg <= 9u; }
+                    else ok &= sp_parse_uint(words, t3 + 1, e, &v_dup);
+                }
+                const unsigned long long ch = swar_contig_key(words, b, t0 - b);
+                if (ch == ckey_cache) {
+                    cid = cid_cache;
+                } else {
+                    for (int s = (int)(swar_key_slot(ch) & (unsigned)d.contig_mask), probes = 0; probes <= d.contig_mask; s = (s + 1) & d.contig_mask, probes++) {
+                        const int4 raw = __ldg(reinterpret_cast<const int4*>(&d.contig_table[s]));
+                        const unsigned long long eh = (unsigned long long)(unsigned)raw.x | ((unsigned long long)(unsigned)raw.y << 32);
+                        if (!raw.w) break;
+                        if (eh == ch) { cid = raw.z; break; }
+                    }
+                    if (cid >= 0) { ckey_cache = ch; cid_cache = cid; }
+                }
+                ok &= cid >= 0;
+            }
+            const bool group_bad = __syncthreads_or(ok ? 0 : 1) != 0;  // also orders s_excl before its first use
+            if (!published_seen) { published_seen = true; if (s_excl < 0) return; }
+            const long long out0 = s_excl;
+            if (group_bad) {
+                // the lines before this group are committed; the general kernel takes the rest (and raises what is an error)
+                if (tid == 0) {
+                    const int n_parts = TB > DEC_TILE ? 2 : 1;
+                    const unsigned long long at = atomicAdd(a.n_irr, (unsigned long long)n_parts);
+                    if ((int64_t)(at + n_parts) <= a.irr_cap) {
+                        if (n_parts == 1) {
+                            a.irr[at] = IrrTile{tile_base, out0, TB, n_lines, base, 0};
+                        } else {
+                            // newlines of the first half: list entries below SP_LB + half that are line ends
+                            int n0 = 0;
+                            for (int q = 0; q < n_lines; q++) if (seplist[first + 5 * q + 4] < SP_LB + half) n0++; else break;
+                            a.irr[at] = IrrTile{tile_base, out0, half, n0, min(base, n0), 0};
+                            a.irr[at + 1] = IrrTile{tile_base + half, out0 + n0, TB - half, n_lines - n0, max(base - n0, 0), 0};
+                        }
+                    } else {
+                        raise_error(d.status, CRATAC_ERR_INTERNAL, -300 - gt);
+                    }
+                }
+                break;
+            }
+            if (li < n_lines) {
+                const long long line_no = out0 + li;
+                if (d.line_cap > 0 && line_no >= d.line_cap) {
+                    raise_error(d.status, CRATAC_ERR_CAPACITY, -7);  // more lines than estimated
+                } else {
+                    unsigned slot = (unsigned)(mix64(key)) & (unsigned)d.bc_mask;
+                    int probes = 0;
+                    bool placed = false;
+                    unsigned long long seen_first = 0xFFFFFFFFFFFFFFFFULL;
+                    while (probes <= d.bc_mask) {
+                        const ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&d.bc_tab[slot]);
+                        unsigned long long kk = sl.x;
+                        seen_first = sl.y;
+                        if (kk == BC_EMPTY) {
+                            const unsigned long long old = atomicCAS(&d.bc_tab[slot].key, BC_EMPTY, key);
+                            if (old == BC_EMPTY) {
+                                const long long off = tile_base - SP_LB + bc_pos;
+                                d.bc_textoff[slot] = (off << 8) | (long long)min(bc_len, 255);
+                                atomicAdd(reinterpret_cast<unsigned long long*>(&d.status[ST_N_BARCODES]), 1ULL);
+                                placed = true;
+                                break;
+                            }
+                            kk = old;
+                        }
+                        if (kk == key) { placed = true; break; }
+                        slot = (slot + 1) & (unsigned)d.bc_mask;
+                        probes++;
+                    }
+                    if (!placed) {
+                        raise_error(d.status, CRATAC_ERR_CAPACITY, line_no);
+                    } else {
+                        if (seen_first > (unsigned long long)line_no) atomicMin(&d.bc_tab[slot].first, (unsigned long long)line_no);
+                        atomicAdd(&d.bc_nfrag[slot], 1);
+                        d.chrom[line_no] = cid;
+                        d.start[line_no] = v_start;
+                        d.end[line_no] = v_end;
+                        d.bc[line_no] = (int32_t)slot;
+                        d.dup[line_no] = v_dup;
+                        const int dl = v_end - v_start;
+                        loc_maxpos = max(loc_maxpos, dl);
+                        loc_maxneg = max(loc_maxneg, -dl);
+                    }
+                }
+            }
+        }
+        if (n_lines == 0) { __syncthreads(); if (s_excl < 0) return; }
+        cur ^= 1;
+        __syncthreads();                                             // buffers, lists and s_* are reused by the next tile
+    }
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) {
+        loc_maxpos = max(loc_maxpos, __shfl_xor_sync(0xffffffffu, loc_maxpos, dd));
+        loc_maxneg = max(loc_maxneg, __shfl_xor_sync(0xffffffffu, loc_maxneg, dd));
+    }
+    if (lane == 0) {
+        if (loc_maxpos > 0) atomicMax(reinterpret_cast<long long*>(&d.status[ST_MAX_POS_LEN]), (long long)loc_maxpos);
+        if (loc_maxneg > 0) atomicMax(reinterpret_cast<long long*>(&d.status[ST_MAX_NEG_LEN]), (long long)loc_maxneg);
     }
 }
 
@@ -607,7 +1074,167 @@ static int barcode_prepare_device(Ctx* c) {
     return CRATAC_OK;
 }
 
+// ---- host side of k_parse_stream
+static int sp_cpt(const Ctx* c) { return c->decode_kernel == 2 ? 8 : 4; }
+static int sp_tile_bytes(const Ctx* c) { return SP_THREADS * sp_cpt(c) * 16 - SP_LB; }
+static size_t sp_smem_bytes(int cpt) {
+    const size_t region_max = (size_t)SP_THREADS * cpt * 16;
+    return 2 * (SP_PAD + region_max + SP_PAD) + 2 * (size_t)SP_THREADS * cpt + 2 * (region_max / 6) + 64;
+}
+
+// queue one launch over the tiles [tile0, tile0 + n_tiles) of the text described by `base`
+static int sp_launch(Ctx* c, const DecodeArgs& base, int64_t tile0, int64_t n_tiles, const int64_t* line_base, int64_t* line_base_out) {
+    const int cpt = sp_cpt(c);
+    StreamArgs a;
+    a.d = base;
+    a.tile_bytes = sp_tile_bytes(c);
+    a.n_tiles = n_tiles; a.tile0 = tile0;
+    a.state = c->d_sp_state.as<unsigned long long>() + tile0;
+    a.ticket = c->d_sp_scalars.as<unsigned long long>();
+    a.n_irr = c->d_sp_scalars.as<unsigned long long>() + 1;
+    a.irr = c->d_sp_irr.as<IrrTile>();
+    a.irr_cap = c->sp_irr_cap;
+    a.line_base = line_base; a.line_base_out = line_base_out;
+    CRATAC_CUDA(cudaMemsetAsync(a.state, 0, 8 * (size_t)n_tiles, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(a.ticket, 0, 8, c->stream));
+    const size_t smem = sp_smem_bytes(cpt);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[cpt == 8]) {
+        if (cpt == 8) CRATAC_CUDA(cudaFuncSetAttribute(k_parse_stream<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CRATAC_CUDA(cudaFuncSetAttribute(k_parse_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[cpt == 8] = true;
+    }
+    int per_sm = 0;
+    if (cpt == 8) CRATAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_parse_stream<8>, SP_THREADS, smem));
+    else CRATAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_parse_stream<4>, SP_THREADS, smem));
+    if (per_sm < 1) { set_error("k_parse_stream does not fit on an SM"); return CRATAC_ERR_INTERNAL; }
+    if (c->sp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->sp_ctas_per_sm);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)NUM_SMS * per_sm);   // every CTA resident: tiles wait on earlier tiles
+    if (cpt == 8) k_parse_stream<8><<<grid, SP_THREADS, smem, c->stream>>>(a);
+    else k_parse_stream<4><<<grid, SP_THREADS, smem, c->stream>>>(a);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+// buffers of the single-pass decode for a text of n_eff bytes
+static int sp_reserve(Ctx* c, int64_t n_eff, int64_t* n_tiles_out) {
+    const int TB = sp_tile_bytes(c);
+    int64_t n_tiles = (n_eff + TB - 1) / TB;
+    if (n_tiles == 0) n_tiles = 1;
+    CRATAC_TRY(c->d_sp_state.reserve(8 * (size_t)n_tiles));
+    CRATAC_TRY(c->d_sp_scalars.reserve(64));
+    c->sp_irr_cap = 2 * n_tiles;
+    CRATAC_TRY(c->d_sp_irr.reserve(sizeof(IrrTile) * (size_t)c->sp_irr_cap));
+    CRATAC_CUDA(cudaMemsetAsync(c->d_sp_scalars.p, 0, 64, c->stream));   // ticket, declined ranges, line base
+    *n_tiles_out = n_tiles;
+    return CRATAC_OK;
+}
+
+// the ranges k_parse_stream declined go through the general kernel; n_irr is on the host by now
+static int sp_run_declined(Ctx* c, DecodeArgs a, int64_t n_irr) {
+    if (n_irr <= 0) return CRATAC_OK;
+    if (n_irr > c->sp_irr_cap) { set_error("declined-tile list overflow"); return CRATAC_ERR_INTERNAL; }
+    a.irr = c->d_sp_irr.as<IrrTile>();
+    a.line_base = nullptr; a.tile0 = 0;
+    k_parse_tiles<<<(unsigned)n_irr, DEC_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+    c->decode_declined += n_irr;
+    CRATAC_CUDA(cudaGetLastError());
+    return CRATAC_OK;
+}
+
+static int decode_error(Ctx* c, int64_t err) {
+    const int64_t arg = c->h_status[ST_ERROR_ARG];
+    if (err == CRATAC_ERR_PARSE) set_error("malformed fragments line %lld (expected contig\\tstart\\tstop\\tbarcode\\tdup_count)", (long long)(arg + 1));
+    else if (err == CRATAC_ERR_CONTIG) set_error("fragments line %lld: contig is not in the reference", (long long)(arg + 1));
+    else if (err == CRATAC_ERR_CAPACITY) set_error("barcode table overflow at line %lld", (long long)(arg + 1));
+    else set_error("device error %lld (arg %lld) in decode", (long long)err, (long long)arg);
+    c->n_fragments = 0;
+    return (int)err;
+}
+
+static int decode_text_two_pass(Ctx* c, const char* d_text, int64_t nbytes);
+
+// Device text -> fragments in ONE pass over the text (k_parse_stream): the number of lines is not known in advance, so the
+// output arrays are sized from an estimate (a fragments.tsv line is rarely under 24 bytes); when that or the barcode table
+// does not hold, the table grows and / or the exact two-pass path takes over.
 int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
+    if (c->decode_kernel == 0) return decode_text_two_pass(c, d_text, nbytes);
+    if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
+    c->d_text = d_text;
+    c->text_bytes = nbytes;
+    c->bc_ready = false;
+    c->barcodes.clear();
+    int64_t* st = c->d_status.as<int64_t>();
+    char last = '\n';
+    if (nbytes > 0) CRATAC_CUDA(cudaMemcpyAsync(&last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t n_eff = nbytes + (last != '\n' ? 1 : 0);
+    int64_t n_tiles = 0;
+    CRATAC_TRY(sp_reserve(c, n_eff, &n_tiles));
+    const size_t held = std::min({c->d_chrom.cap, c->d_start.cap, c->d_end.cap, c->d_bc.cap, c->d_dup.cap}) / 4;
+    const int64_t line_cap = std::max<int64_t>(nbytes / 24 + 4096, (int64_t)held);
+    {
+        const size_t nn = (size_t)line_cap;
+        CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));
+        CRATAC_TRY(c->d_bc.reserve(4 * nn)); CRATAC_TRY(c->d_dup.reserve(4 * nn));
+    }
+    int64_t* line_base = c->d_sp_scalars.as<int64_t>() + 2;
+    for (int attempt = 0;; attempt++) {
+        const size_t cap = (size_t)c->bc_table_cap;
+        CRATAC_TRY(c->d_bc_keys.reserve(sizeof(BcSlot) * cap));
+        CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
+        CRATAC_TRY(c->d_bc_nfrag.reserve(4 * cap));
+        CRATAC_CUDA(cudaMemsetAsync(c->d_bc_nfrag.p, 0, 4 * cap, c->stream));
+        k_init_table<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_bc_keys.as<BcSlot>(), (int)cap);
+        c->launches++;
+        CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_BARCODES], 0, sizeof(int64_t) * 3, c->stream));
+        CRATAC_CUDA(cudaMemsetAsync(c->d_sp_scalars.p, 0, 64, c->stream));
+        DecodeArgs a;
+        a.text = d_text; a.nbytes = nbytes; a.n_eff = n_eff;
+        a.tile_offsets = nullptr; a.tile_counts = nullptr;
+        a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
+        a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
+        a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
+        a.bc_tab = c->d_bc_keys.as<BcSlot>(); a.bc_nfrag = c->d_bc_nfrag.as<int32_t>();
+        a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
+        a.status = st;
+        a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
+        a.tile0 = 0; a.line_base = nullptr; a.line_cap = line_cap; a.irr = nullptr;
+        c->stage_begin(SG_DECODE_PARSE);
+        CRATAC_TRY(sp_launch(c, a, 0, n_tiles, line_base, line_base + 1));
+        c->stage_end(SG_DECODE_PARSE);
+        CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+        CRATAC_CUDA(cudaMemcpyAsync(c->h_sp_scalars, c->d_sp_scalars.p, 32, cudaMemcpyDeviceToHost, c->stream));
+        CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+        c->host_mark("decode_stream_sync");
+        int64_t err = c->h_status[ST_ERROR];
+        if (err == 0 && c->h_sp_scalars[1] > 0) {
+            CRATAC_TRY(sp_run_declined(c, a, c->h_sp_scalars[1]));
+            CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+            CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+            err = c->h_status[ST_ERROR];
+        }
+        const int64_t nb = c->h_status[ST_N_BARCODES];
+        if (err == CRATAC_ERR_CAPACITY && c->h_status[ST_ERROR_ARG] == -7) return decode_text_two_pass(c, d_text, nbytes);   // more lines than estimated
+        const bool crowded = nb * 2 > (int64_t)c->bc_table_cap;
+        if ((err == CRATAC_ERR_CAPACITY || (err == 0 && crowded)) && attempt < 6 && c->bc_table_cap < (1 << 28)) {
+            c->bc_table_cap <<= 2;   // grow and decode again
+            continue;
+        }
+        if (err != 0) return decode_error(c, err);
+        c->n_fragments = c->h_sp_scalars[3];
+        c->n_barcodes = nb;
+        CRATAC_CUDA(cudaMemcpyAsync(&st[ST_N_FRAGMENTS], line_base + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+        break;
+    }
+    CRATAC_TRY(finalize_fragments(c));
+    return barcode_prepare_device(c);
+}
+
+static int decode_text_two_pass(Ctx* c, const char* d_text, int64_t nbytes) {
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     c->d_text = d_text;
     c->text_bytes = nbytes;
@@ -658,7 +1285,7 @@ int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
         a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
         a.status = st;
         a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
-        a.tile0 = 0; a.line_base = nullptr; a.line_cap = 0;
+        a.tile0 = 0; a.line_base = nullptr; a.line_cap = 0; a.irr = nullptr;
         c->stage_begin(SG_DECODE_PARSE);
         k_parse_tiles<<<(unsigned)n_tiles, DEC_THREADS, 0, c->stream>>>(a);
         c->stage_end(SG_DECODE_PARSE);
@@ -697,7 +1324,92 @@ __global__ void k_add_i64(int64_t* __restrict__ acc, const int64_t* __restrict__
 // has arrived, while the next chunk is in flight.  The number of lines is not known before the last chunk, so the output
 // arrays are sized from an estimate; returns CRATAC_ERR_CAPACITY when anything did not fit (table or estimate) -- the
 // caller then falls back to copy-all-then-decode.
+static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nbytes);
+
+// Same with the single-pass kernel: one k_parse_stream launch per chunk, the running line base stays on the device.
 int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
+    if (c->decode_kernel == 0) return decode_text_streamed_two_pass(c, h_text, nbytes);
+    if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
+    CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
+    char* d_text = c->d_text_own.as<char>();
+    c->d_text = d_text;
+    c->text_bytes = nbytes;
+    c->bc_ready = false;
+    c->barcodes.clear();
+    int64_t* st = c->d_status.as<int64_t>();
+    if (!c->copy_stream) {
+        CRATAC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CRATAC_CUDA(cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming));
+    }
+    const int64_t n_eff = nbytes + ((nbytes > 0 && h_text[nbytes - 1] != '\n') ? 1 : 0);
+    int64_t n_tiles = 0;
+    CRATAC_TRY(sp_reserve(c, n_eff, &n_tiles));
+    const int TB = sp_tile_bytes(c);
+    const size_t held = std::min({c->d_chrom.cap, c->d_start.cap, c->d_end.cap, c->d_bc.cap, c->d_dup.cap}) / 4;
+    const int64_t line_cap = std::max<int64_t>(nbytes / 24 + 4096, (int64_t)held);
+    {
+        const size_t nn = (size_t)line_cap;
+        CRATAC_TRY(c->d_chrom.reserve(4 * nn)); CRATAC_TRY(c->d_start.reserve(4 * nn)); CRATAC_TRY(c->d_end.reserve(4 * nn));
+        CRATAC_TRY(c->d_bc.reserve(4 * nn)); CRATAC_TRY(c->d_dup.reserve(4 * nn));
+    }
+    const size_t cap = (size_t)c->bc_table_cap;
+    CRATAC_TRY(c->d_bc_keys.reserve(sizeof(BcSlot) * cap));
+    CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
+    CRATAC_TRY(c->d_bc_nfrag.reserve(4 * cap));
+    CRATAC_CUDA(cudaMemsetAsync(c->d_bc_nfrag.p, 0, 4 * cap, c->stream));
+    k_init_table<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_bc_keys.as<BcSlot>(), (int)cap);
+    c->launches++;
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_BARCODES], 0, sizeof(int64_t) * 3, c->stream));
+    int64_t* line_base = c->d_sp_scalars.as<int64_t>() + 2;
+    DecodeArgs a;
+    a.text = d_text; a.nbytes = nbytes; a.n_eff = n_eff;
+    a.tile_offsets = nullptr; a.tile_counts = nullptr;
+    a.contig_table = c->d_contig_table.as<ContigEntry>(); a.contig_mask = c->contig_table_cap - 1;
+    a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>();
+    a.bc = c->d_bc.as<int32_t>(); a.dup = c->d_dup.as<int32_t>();
+    a.bc_tab = c->d_bc_keys.as<BcSlot>(); a.bc_nfrag = c->d_bc_nfrag.as<int32_t>();
+    a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
+    a.status = st;
+    a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
+    a.tile0 = 0; a.line_base = nullptr; a.line_cap = line_cap; a.irr = nullptr;
+    const int64_t chunk_bytes = c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles * DEC_TILE : (int64_t)(128 << 20);   // default: 128 MiB of text per chunk
+    const int64_t CHUNK_TILES = std::max<int64_t>(chunk_bytes / TB, 1);
+    int n_launches = 0;
+    c->stage_begin(SG_DECODE_PARSE);
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES) {
+        const int64_t t1 = std::min(n_tiles, t0 + CHUNK_TILES);
+        const int64_t b0 = t0 * TB, b1 = std::min(nbytes, t1 * TB);
+        if (b1 > b0) CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, h_text + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+        CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
+        CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->copy_event, 0));
+        CRATAC_TRY(sp_launch(c, a, t0, t1 - t0, line_base + (n_launches & 1), line_base + ((n_launches + 1) & 1)));
+        n_launches++;
+    }
+    c->stage_end(SG_DECODE_PARSE);
+    const int total_word = 2 + (n_launches & 1);       // the word the last launch wrote
+    CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(c->h_sp_scalars, c->d_sp_scalars.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_mark("decode_streamed_sync");
+    int64_t err = c->h_status[ST_ERROR];
+    if (err == 0 && c->h_sp_scalars[1] > 0) {
+        CRATAC_TRY(sp_run_declined(c, a, c->h_sp_scalars[1]));
+        CRATAC_CUDA(cudaMemcpyAsync(c->h_status, st, sizeof(int64_t) * ST_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+        CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+        err = c->h_status[ST_ERROR];
+    }
+    const int64_t nb = c->h_status[ST_N_BARCODES];
+    if (err == CRATAC_ERR_CAPACITY || (err == 0 && nb * 2 > (int64_t)c->bc_table_cap)) return CRATAC_ERR_CAPACITY;   // caller: exact path with a larger table
+    if (err != 0) return decode_error(c, err);
+    c->n_fragments = c->h_sp_scalars[total_word];
+    c->n_barcodes = nb;
+    CRATAC_CUDA(cudaMemcpyAsync(&st[ST_N_FRAGMENTS], c->d_sp_scalars.as<int64_t>() + total_word, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+    CRATAC_TRY(finalize_fragments(c));
+    return barcode_prepare_device(c);
+}
+
+static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nbytes) {
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
     char* d_text = c->d_text_own.as<char>();
@@ -745,7 +1457,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
     a.bc_textoff = c->d_bc_textoff.as<long long>(); a.bc_mask = c->bc_table_cap - 1;
     a.status = st;
     a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
-    a.line_base = line_base; a.line_cap = line_cap;
+    a.line_base = line_base; a.line_cap = line_cap; a.irr = nullptr;
     const int64_t CHUNK_TILES = c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles : (int64_t)(128 << 20) / DEC_TILE;   // default: 128 MiB of text per chunk
     c->stage_begin(SG_DECODE_PARSE);
     for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES) {

@@ -15,6 +15,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "nb_pmf.cuh"
 
 namespace cratac {
 
@@ -79,6 +80,8 @@ __device__ long long g_em_cycles[PH_COUNT];
 struct Theta { double p_zero, mean_bg, alpha_bg, p_signal, f_zero, f_bg; };
 
 __device__ __forceinline__ double nb_pmf(double k, double n, double p) {
+    // large size (dispersion near its 1e-6 floor): saddle-point form, the log-gamma terms would cancel to 1e-9 (nb_pmf.cuh)
+    if (n > NB_SADDLE_MIN) return nb_pmf_saddle(k, n, p, 1.0 - p);
     // legacy scipy nbinom._pmf: exp(gammaln(n+k) - gammaln(k+1) - gammaln(n) + n*log(p) + k*log1p(-p))
     return exp(lgamma(n + k) - lgamma(k + 1.0) - lgamma(n) + n * log(p) + k * log1p(-p));
 }

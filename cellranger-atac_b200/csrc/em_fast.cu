@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "nb_pmf.cuh"
 
 namespace cratac {
 
@@ -128,6 +129,9 @@ __device__ __forceinline__ double ef_lgamma(double x) {
 }
 
 // alpha j / (1 + alpha j) = 1 - 1 / (1 + alpha j)
+// out of line: the saddle-point pmf is the rare regime (dispersion at its floor) and must not lengthen the E-step body
+__device__ __noinline__ double ef_nb_saddle(double k, double n, double p) { return nb_pmf_saddle(k, n, p, 1.0 - p); }
+
 __device__ __forceinline__ double ef_frac(double alpha, double j) { return 1.0 - ef_rcp(fma(alpha, j, 1.0)); }
 
 // G(alpha) (em_fitting.py:41-56 with the sums swapped) at NP points held in s.pts, EF_THREADS / NP threads per point
@@ -451,10 +455,12 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         double acc[6] = {0, 0, 0, 0, 0, 0};
         double vmax1 = 0.0;
         const double f_sig = 1.0 - th.f_zero - th.f_bg;
-        double nn = 0.0, lgn = 0.0, nlogp = 0.0, l1p = 0.0, lz = 0.0, ls = 0.0;
+        double nn = 0.0, lgn = 0.0, nlogp = 0.0, l1p = 0.0, lz = 0.0, ls = 0.0, pp = 1.0;
+        bool saddle = false;      // uniform over the CTA: large 1/alpha takes the cancellation-free form (nb_pmf.cuh)
         if (!hard) {
             nn = 1.0 / th.alpha_bg;
-            const double pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+            pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+            saddle = nn > NB_SADDLE_MIN;
             lgn = lgamma(nn); nlogp = nn * log(pp); l1p = log1p(-pp);
             lz = log(1.0 - th.p_zero); ls = log(1.0 - th.p_signal);
         }
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
                 r2 = v > (double)t0 ? 1.0 : 0.0;
             } else {
                 const double z = exp((v - 1.0) * lz) * th.p_zero * th.f_zero;
-                const double b = exp(ef_lgamma(nn + v) - lgS[i] - lgn + nlogp + v * l1p) * th.f_bg;
+                const double b = (saddle ? ef_nb_saddle(v, nn, pp) : exp(ef_lgamma(nn + v) - lgS[i] - lgn + nlogp + v * l1p)) * th.f_bg;
                 const double g = exp((v - 1.0) * ls) * th.p_signal * f_sig;
                 const double t = z + b + g;
                 if (t == 0.0) { r0 = r1 = r2 = 0.0; } else { const double it = ef_rcp(t); r0 = z * it; r1 = b * it; r2 = g * it; }
@@ -657,7 +663,8 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
     for (int xi = tid; xi < 1000; xi += EF_THREADS) {
         double xv = (double)xi;
         double ysig = f_sig * (pow(1.0 - th.p_signal, xv) * th.p_signal);
-        double nb = exp(lgamma(nn + xv) - lgamma(xv + 1.0) - lgamma(nn) + nn * log(pp) + xv * log1p(-pp));
+        double nb = nn > NB_SADDLE_MIN ? ef_nb_saddle(xv, nn, pp)
+                                       : exp(lgamma(nn + xv) - lgamma(xv + 1.0) - lgamma(nn) + nn * log(pp) + xv * log1p(-pp));
         double ybg = th.f_zero * (pow(1.0 - th.p_zero, xv) * th.p_zero) + th.f_bg * nb;
         if (ysig / ybg < a.odds_ratio) best = fmax(best, xv);
     }

@@ -62,10 +62,15 @@ void cratac_destroy(cratac_ctx* ctx);
  * cratac_fit_threshold_result), "stream_decode" (0 off / 1 host texts of 64 MiB and more / 2 always: the host text is
  * copied in chunks and each chunk is decoded while the next one is on the PCIe bus), "stream_chunk_tiles" (16 KiB
  * text tiles per chunk, 0 = 128 MiB worth), "py2_device_min" (from this many distinct barcodes on the PY2SET column
- * order is worked out on the device instead of by the host simulation; default 300000) */
+ * order is worked out on the device instead of by the host simulation; default 300000), "decode_kernel" (1, default:
+ * the text is read ONCE by k_parse_stream, tiles it declines go through the general kernel; 2: same with 32 KiB tiles;
+ * 0: newline-count pass + general parse kernel), "decode_ctas_per_sm" (cap on resident CTAs of k_parse_stream) */
 int cratac_set_option(cratac_ctx* ctx, const char* key, int64_t value);
 /* kernels launched by this context since creation / last reset */
 int64_t cratac_launch_count(cratac_ctx* ctx, int reset);
+/* text ranges (of at most 16 KiB) the single-pass decoder handed to the general parse kernel since creation / last reset:
+ * 0 on a clean fragments.tsv (tools/io.py:75-92 shaped lines of at most 64 bytes) */
+int64_t cratac_decode_declined(cratac_ctx* ctx, int reset);
 int cratac_synchronize(cratac_ctx* ctx);
 /* the CUDA stream every kernel of this context is launched on (cudaStream_t as an integer) */
 int cratac_stream(cratac_ctx* ctx, uint64_t* stream_out);

@@ -578,3 +578,123 @@ def test_streamed_host_decode_falls_back_when_the_estimate_is_too_small():
     assert fr["start"].tolist() == [i // 3000 for i in range(1, 90000)] and fr["end"].tolist() == [i // 3000 + 1 for i in range(1, 90000)]
     assert len(text) // 24 + 4096 < len(lines)                   # i.e. the streamed attempt did run out of room
     ctx.close()
+
+
+# ----------------------------------------------------------------------------- single-pass decoder (k_parse_stream)
+def _decode_and_compare(ctx, text, names, host=True):
+    if host:
+        n, nb = ctx.decode_host(text)
+    else:
+        import torch
+        t = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+        n, nb = ctx.decode_device(t.data_ptr(), len(text))
+    o = util.oracle_decode(text, names)
+    assert n == o["start"].size and nb == len(o["first_seen"])
+    got = ctx.get_fragments()
+    for k in ("chrom", "start", "end", "dup"):
+        assert np.array_equal(got[k], o[k]), k
+    bcs = ctx.get_barcodes()
+    assert bcs == util.oracle_columns(o["first_seen"])
+    assert np.array_equal(np.array(bcs)[got["bc"]], np.array(o["barcodes"]))
+    return n
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 0])
+def test_single_pass_decode_clean_text_takes_no_fallback(kernel):
+    """A clean file of many tiles (9- and 10-digit positions included through a 2.2 Gb contig, multi-digit duplicate
+    counts): every decode kernel gives the oracle's arrays, and the single-pass ones hand nothing to the general kernel."""
+    contigs = [("chr1", 248956422), ("chr10", 2147480000), ("chrX", 156040895)]
+    frags = synth.generate(contigs, 400000, 300, 500, seed=77, background_factor=5)
+    frags["dup"] = (frags["dup"].astype(np.int64) * np.where(np.arange(frags["dup"].size) % 97 == 0, 1234567, 1)).astype(np.int32)
+    text = synth.to_text(frags)
+    names = [c[0] for c in contigs]
+    for tail in (text, text[:-1]):
+        for host in (True, False):
+            ctx = _ffi.Context(contigs)
+            ctx.set_option("decode_kernel", kernel)
+            ctx.set_option("stream_decode", 0)
+            assert _decode_and_compare(ctx, tail, names, host=host) == 400000
+            assert ctx.decode_declined() == 0
+            ctx.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_single_pass_decode_hands_odd_lines_to_the_general_kernel(kernel):
+    """Lines the fast path does not take (longer than its 64-byte look-back, CRLF, blanks for strip(), a generic barcode
+    next to 10x ones) scattered through a clean file: same arrays as the oracle, and the hand-over counter moved."""
+    contigs = synth.GRCH38[:2]
+    frags = synth.generate(contigs, 120000, 100, 200, seed=78, background_factor=5)
+    lines = synth.to_text(frags).decode().split("\n")[:-1]
+    rng = np.random.default_rng(5)
+    for i in rng.choice(len(lines), size=60, replace=False):
+        f = lines[i].split("\t")
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            f[3] = "long_generic_barcode_" + "x" * int(rng.integers(30, 150)) + "-1"
+        elif kind == 1:
+            f[4] = f[4] + "\r"
+        elif kind == 2:
+            f[4] = f[4] + "  "
+        elif kind == 3:
+            f[0] = " " + f[0]
+        else:
+            f[3] = "NNNN" + f[3][4:]
+        lines[i] = "\t".join(f)
+    text = ("\n".join(lines) + "\n").encode()
+    names = [c[0] for c in contigs]
+    for host, chunk in ((True, 0), (False, 0), (True, 5)):
+        ctx = _ffi.Context(contigs)
+        ctx.set_option("decode_kernel", kernel)
+        ctx.set_option("stream_decode", 2 if chunk else 0)
+        if chunk:
+            ctx.set_option("stream_chunk_tiles", chunk)
+        _decode_and_compare(ctx, text, names, host=host)
+        assert ctx.decode_declined() > 0
+        ctx.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_single_pass_decode_tile_borders_and_errors(kernel):
+    """Every alignment of the line grid against the tile grid (a first line of 1..70 bytes shifts all the others), texts
+    that end exactly on / one byte around a tile border, and errors raised from inside a large text with the right line."""
+    contigs = [("chr1", 248956422), ("padpadpad", 10)]
+    frags = synth.generate(contigs[:1], 3000, 20, 10, seed=79, background_factor=2)
+    body = synth.to_text(frags)
+    names = [c[0] for c in contigs]
+    ctx = _ffi.Context(contigs)
+    ctx.set_option("decode_kernel", kernel)
+    ctx.set_option("stream_decode", 0)
+    def filler(nbytes, head=b"chr1\t0\t1\t"):
+        """Lines with generic barcodes, `nbytes` bytes in all, none above 200: on chr1 at position 0 in front of the body,
+        on the contig after chr1 behind it (the file stays sorted)."""
+        out = []
+        while nbytes > 0:
+            take = nbytes if nbytes <= 200 else (100 if nbytes - 100 >= 30 else nbytes - 30)
+            assert take >= len(head) + 4
+            out.append(head + b"G" * (take - len(head) - 3) + b"\t1\n")
+            nbytes -= take
+        return b"".join(out)
+
+    tb = 16320 if kernel == 1 else 32704
+    for shift in list(range(14, 90, 3)) + [tb - 40, tb - 1, tb, tb + 1, 2 * tb - 1, 2 * tb, 2 * tb + 1]:
+        _decode_and_compare(ctx, filler(shift) + body, names)
+    whole = body[:body.rfind(b"\n", 0, 2 * tb - 400) + 1]
+    for total in (tb - 1, tb, tb + 1, 2 * tb - 1, 2 * tb, 2 * tb + 1):
+        for final_newline in (True, False):
+            keep = whole[:whole.rfind(b"\n", 0, total - 300) + 1]
+            last = filler(total - len(keep) + (0 if final_newline else 1), head=b"padpadpad\t0\t1\t")
+            text = keep + (last if final_newline else last[:-1])
+            assert len(text) == total
+            _decode_and_compare(ctx, text, names)
+    lines = body.decode().split("\n")[:-1]
+    for where in (0, 1, 377, 2998, 2999):
+        for mutate, code in ((lambda f: f[:1] + ["12x4"] + f[2:], _ffi.ERR_PARSE), (lambda f: ["chrUn"] + f[1:], _ffi.ERR_CONTIG),
+                             (lambda f: f[:4], _ffi.ERR_PARSE)):
+            bad = list(lines)
+            bad[where] = "\t".join(mutate(bad[where].split("\t")))
+            with pytest.raises(_ffi.CratacError) as e:
+                ctx.decode_host(("\n".join(bad) + "\n").encode())
+            assert e.value.code == code
+            import re
+            assert int(re.search(r"line (\d+)", str(e.value)).group(1)) == where + 1
+    ctx.close()

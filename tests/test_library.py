@@ -358,3 +358,25 @@ def test_synth_is_sorted_and_valid():
     dec = util.oracle_decode(text, [c[0] for c in contigs])
     assert np.array_equal(dec["start"], f["start"]) and np.array_equal(dec["end"], f["end"])
     assert dec["barcodes"] == synth.barcode_strings(f).tolist()
+
+
+def test_saddle_point_negative_binomial_pmf_against_scipy(tmp_path):
+    """csrc/nb_pmf.cuh (the NB pmf of the fit kernels when 1/alpha is large, i.e. the dispersion sits near its 1e-6
+    floor) compiled for the host: equal to scipy.stats.nbinom.pmf -- what analysis/peaks.py:57,75 calls -- to 5e-12
+    relative, where the log-gamma form is off by 1e-9."""
+    from scipy.stats import nbinom
+    exe = str(tmp_path / "nb_pmf_host_test")
+    build = subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "nb_pmf_host_test.cpp"), "-lm"],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    rows = []
+    for alpha in (1e-6, 1e-5, 1e-4, 5e-4, 9.9e-4):
+        for mu in (0.7, 1.5, 4.6, 12.0, 80.0, 300.0):
+            n, p = 1.0 / alpha, 1.0 / (1.0 + alpha * mu)
+            rows += [(k, n, p) for k in (0, 1, 2, 3, 5, 8, 13, 15, 16, 17, 20, 40, 100, 300, 999)]
+    run = subprocess.run([exe], input="\n".join("%d %.17g %.17g" % r for r in rows), capture_output=True, text=True)
+    assert run.returncode == 0
+    mine = np.array([float(x) for x in run.stdout.split()])
+    ref = np.array([nbinom.pmf(*r) for r in rows])
+    big = ref > 1e-290
+    assert big.sum() > 300 and np.max(np.abs(mine[big] - ref[big]) / ref[big]) < 5e-12
