@@ -91,22 +91,13 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------------------------- workload
-def shard_contigs(contigs, world):
-    """LPT bin-packing of contigs over ranks (kept for reference; the benchmark uses contiguous ranges,
-    cratac.multi.partition_contigs, so that matrix rows of different ranks never interleave)."""
-    loads = [0] * world
-    parts = [[] for _ in range(world)]
-    for i in sorted(range(len(contigs)), key=lambda k: -contigs[k][1]):
-        r = loads.index(min(loads))
-        parts[r].append(i)
-        loads[r] += contigs[i][1]
-    return [sorted(p) for p in parts]
-
-
-def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chrom_offset=0):
+def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chrom_offset=0, keep=None):
     """Seeded synthetic fragments generated ON the device (torch is plumbing here), sorted by
     (contig, start, stop) and rendered to fragments.tsv text by the library's encoder kernel.
-    Same distributions as cratac/synth.py."""
+    Same distributions as cratac/synth.py.
+    keep = (first, last_exclusive) contig range: the WHOLE library is generated (identical on every rank: one seed, no
+    rank in it) and only the fragments of those contigs are rendered -- the sharded runs at N = 1, 2, 4, 8 therefore work
+    on the same library and their results (bench line `result.checksum`) must agree."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     lens = torch.tensor([c[1] for c in contigs], dtype=torch.int64, device=device)
@@ -154,14 +145,19 @@ def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chr
     seqs = torch.randint(0, 1 << 32, (cells + n_bg,), generator=gb, device=device, dtype=torch.int64)
     seqs = torch.where(seqs >= (1 << 31), seqs - (1 << 32), seqs).to(torch.int32)
     seq = seqs[bc_idx].contiguous()
-    del bc_idx
+    if keep is not None:
+        lo = int((chrom < keep[0] + chrom_offset).sum().item())
+        hi = int((chrom < keep[1] + chrom_offset).sum().item())
+        chrom, start, end, dup, seq = (x[lo:hi].contiguous() for x in (chrom, start, end, dup, seq))
+        n = hi - lo
     torch.cuda.synchronize()   # the encoder runs on the library's stream
     nbytes = ctx.encode_text_device(n, chrom.data_ptr(), start.data_ptr(), end.data_ptr(), seq.data_ptr(), dup.data_ptr(), 0, 0)
+    del bc_idx
     text = torch.empty(nbytes + 16, dtype=torch.uint8, device=device)
     got = ctx.encode_text_device(n, chrom.data_ptr(), start.data_ptr(), end.data_ptr(), seq.data_ptr(), dup.data_ptr(), text.data_ptr(), nbytes)
     assert got == nbytes
     torch.cuda.synchronize()
-    return text, nbytes
+    return text, nbytes, n
 
 
 def algorithmic_bytes(T, N, G, P, K, nnz, B):
@@ -194,6 +190,13 @@ def cpu_sample(args):
     """Bounded CPU sample of the configured workload: one 1 Mb contig per host core (at most 24) at the configuration's
     fragment density, so that the reference's per-contig tasks keep every core busy as they do on the whole genome."""
     from cratac import synth
+    if args.config == 1:
+        # BASELINE.json configs[0] is the reference's own CPU-runnable case: run in FULL, no sampling, no extrapolation
+        contigs = synth.GRCH38[:1]
+        frags = synth.generate(contigs, args.config_fragments, args.cells, args.peaks, seed=1000, background_factor=20)
+        desc = ("the whole configuration: %d fragments on chr1 (%d bases), %d cells; reference-shaped flow (oracle/reference_flow.py) "
+                "on a multiprocessing pool" % (args.config_fragments, contigs[0][1], args.cells))
+        return (contigs, synth.to_text(frags)), desc
     k = max(1, min(os.cpu_count() or 1, 24))      # GRCh38 has 24 primary contigs: no more per-contig tasks than that
     contigs = [("chr%d" % (i + 1), CPU_SLICE) for i in range(k)]
     density = args.config_fragments / float(args.genome_bases)
@@ -239,6 +242,12 @@ def full_size_fit_seconds(args):
 
 
 def cpu_whole_job_estimate(args, n_sample, secs, fit_full):
+    if args.config == 1:          # measured in full
+        return n_sample / secs["total"], {"whole_job_seconds_measured": secs["total"]}
+    return _cpu_whole_job_estimate(args, n_sample, secs, fit_full)
+
+
+def _cpu_whole_job_estimate(args, n_sample, secs, fit_full):
     """fragments/s of the whole configured job on this host: the per-contig / per-chunk stages scale with the number of
     fragments (linear scaling: slightly generous to the CPU, DETECT_PEAKS.main re-reads the whole bedgraph per contig),
     the fit is paid once."""
@@ -252,8 +261,9 @@ def cpu_whole_job_estimate(args, n_sample, secs, fit_full):
 def cpu_baseline_block(args, n_sample, secs, fit_full, desc):
     value, model = cpu_whole_job_estimate(args, n_sample, secs, fit_full)
     return {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": desc + "; value = configured fragments / (sample's scalable stage time x fragments ratio + one fit on the "
-                             "full-size histogram)", "seconds_by_stage": secs, "model": model}
+            "sample": desc + ("; value = fragments / measured wall time" if args.config == 1 else
+                              "; value = configured fragments / (sample's scalable stage time x fragments ratio + one fit on the "
+                              "full-size histogram)"), "seconds_by_stage": secs, "model": model}
 
 
 def reference_arm(args, world, rank):
@@ -283,11 +293,68 @@ def reference_arm(args, world, rank):
 
 
 def workload_config(args):
-    return {"workload": "synthetic GRCh38-shape %d-cell run, %d fragments, whole GRCh38, %d latent peak centres"
-                        % (args.cells, args.config_fragments, args.peaks),
-            "fragments": args.config_fragments, "cells": args.cells, "latent_peaks": args.peaks, "genome": "GRCh38 chr1-22,X,Y",
+    genome = "GRCh38 chr1 only" if args.config == 1 else "GRCh38 chr1-22,X,Y"
+    return {"workload": "BASELINE.json configs[%d]: synthetic %d-cell run, %d fragments, %s, %d latent peak centres"
+                        % (args.config - 1, args.cells, args.config_fragments, genome, args.peaks),
+            "fragments": args.config_fragments, "cells": args.cells, "latent_peaks": args.peaks, "genome": genome,
             "l2": "inputs larger than L2 (text %.1f GB per step)" % (46.0 * args.config_fragments / 1e9),
+            "library": "one seeded library, identical for every --gpus N, cut by contig range" if not args.per_rank_library
+                       else "one seeded library per rank (its own contig range)",
             "parallelism": "genome-range sharding by contig, %d GPU(s)" % args.gpus}
+
+
+def apply_config(args, synth):
+    """BASELINE.json configs: 1 = configs[0] (chr1 only, 500 cells, 5 M fragments: the reference's own CPU-runnable case),
+    2 = configs[1] (the metric's configuration: 250 M fragments, 10 k cells, whole GRCh38), 4 = configs[3] (aggr shape:
+    2 B fragments, 80 k cells, 8 GPUs).  Explicit --fragments / --cells / --peaks win."""
+    defaults = {1: (5000000, 500, 8000), 2: (250000000, 10000, 100000), 4: (2000000000, 80000, 100000)}[args.config]
+    if args.fragments is None:
+        args.fragments = defaults[0]
+    if args.cells is None:
+        args.cells = defaults[1]
+    if args.peaks is None:
+        args.peaks = defaults[2]
+    args.config_fragments = args.fragments
+    contigs = synth.GRCH38[:1] if args.config == 1 else synth.GRCH38
+    args.genome_bases = sum(c[1] for c in contigs)
+    if args.config == 4:
+        args.per_rank_library = True      # 2 B fragments are generated shard by shard: no single GPU holds the generator's temporaries
+    return contigs
+
+
+# 64-bit mixing constants (as signed int64) of the result checksum
+_K1, _K2, _K3, _K4 = -7046029254386353131, -4417276706812531889, 1609587929392839161, -4658895280553007687
+
+
+def _mix_sum(torch, a, b, c):
+    """Order-independent 64-bit checksum of the triples (a, b, c): sum of a mixed word per triple, wrapping."""
+    if a.numel() == 0:
+        return 0
+    h = a.to(torch.int64) * _K1 + b.to(torch.int64) * _K2 + c.to(torch.int64) * _K3
+    h = (h ^ (h >> 29)) * _K4
+    h = h ^ (h >> 32)
+    return int(h.sum().item())
+
+
+def result_checksum(torch, dist, world, device, threshold, peaks, row_base, indptr, indices, data, col_keys):
+    """One 64-bit word over (threshold, peaks.bed rows, column order, indptr / indices / data): every rank adds the part
+    it holds -- its peaks with their global row numbers, its matrix entries with global (column, row) -- so that the sum is
+    the same for every way of sharding the same library.  Outside the timed region; torch is only the calculator here."""
+    c, s_, e = peaks
+    n = int(c.numel())
+    rows = torch.arange(n, dtype=torch.int64, device=device) + int(row_base)
+    part = _mix_sum(torch, rows * 64 + c.to(torch.int64), s_, e)
+    ncols = int(indptr.numel()) - 1
+    if int(indices.numel()) > 0:
+        cols = torch.repeat_interleave(torch.arange(ncols, dtype=torch.int64, device=device), (indptr[1:] - indptr[:-1]))
+        part += _mix_sum(torch, cols, indices, data)
+    t = torch.tensor([((part + (1 << 63)) % (1 << 64)) - (1 << 63)], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(t)                   # int64 sum wraps
+    total = int(t.item())
+    total += _mix_sum(torch, torch.arange(int(col_keys.numel()), dtype=torch.int64, device=device), col_keys, torch.zeros_like(col_keys))
+    total += int(threshold) * 1000003
+    return "%016x" % (total % (1 << 64))
 
 
 # --------------------------------------------------------------------------------------------- main
@@ -297,18 +364,22 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cratac", choices=["cratac", "reference"])
-    ap.add_argument("--fragments", type=int, default=250000000, help="total fragments of the workload (configs[1]: 250M)")
-    ap.add_argument("--cells", type=int, default=10000)
-    ap.add_argument("--peaks", type=int, default=100000)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4], help="BASELINE.json configuration (1-based): 1 chr1 / 5 M / 500 cells, "
+                    "2 (default, the metric's) whole GRCh38 / 250 M / 10 k cells, 4 aggr shape 2 B / 80 k cells")
+    ap.add_argument("--fragments", type=int, default=None, help="total fragments of the workload (default: the configuration's)")
+    ap.add_argument("--cells", type=int, default=None)
+    ap.add_argument("--peaks", type=int, default=None)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--per-rank-library", action="store_true", help="every rank generates only its own contig range (different libraries for different N)")
+    ap.add_argument("--ncu-csv", default=None, help="per-kernel CSV (tools/ncu_summary.py) of an `ncu --set full` capture of THIS command line: "
+                    "source of roofline.traffic; without it traffic is null")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-checksum", action="store_true")
     args = ap.parse_args()
-    args.config_fragments = args.fragments
 
     from cratac import synth
-    contigs_all = synth.GRCH38
-    args.genome_bases = sum(c[1] for c in contigs_all)
+    contigs_all = apply_config(args, synth)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -343,7 +414,11 @@ def main():
     # every rank knows all contigs (global ids); it piles up / calls peaks on its own range only
     ctx = _ffi.Context(contigs_all, primary=[c[0] for c in contigs], device=local_rank)
     ctx.set_option("profile", 1)
-    text, nbytes = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device, chrom_offset=first_c)
+    if args.per_rank_library:
+        text, nbytes, n_local = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device, chrom_offset=first_c)
+    else:
+        text, nbytes, n_local = make_workload(torch, ctx, contigs_all, args.fragments, args.cells, args.peaks, args.seed, device, keep=(first_c, last_c))
+    torch.cuda.empty_cache()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
     def barrier():

@@ -49,6 +49,7 @@ SIGNATURES = {
     "cratac_set_option": (c_int, [c_vp, c_cp, c_i64]),
     "cratac_launch_count": (c_i64, [c_vp, c_int]),
     "cratac_decode_declined": (c_i64, [c_vp, c_int]),
+    "cratac_decode_profile": (c_int, [c_vp, P(c_i64), c_int]),
     "cratac_synchronize": (c_int, [c_vp]),
     "cratac_stream": (c_int, [c_vp, P(ctypes.c_uint64)]),
     "cratac_num_stages": (c_int, []),
@@ -173,6 +174,13 @@ class Context(object):
     def decode_declined(self, reset=False):
         """Text ranges the single-pass decoder handed to the general parse kernel (0 on a clean file)."""
         return int(self._lib.cratac_decode_declined(self._h, 1 if reset else 0))
+
+    def decode_profile(self):
+        """SM cycles per phase of the single-pass decoder's tile loop (option decode_profile = 1) -> dict."""
+        out = (c_i64 * 9)()
+        check(self._lib.cratac_decode_profile(self._h, out, 9))
+        names = ["wait_tile", "separator_masks", "separator_list", "structure_check", "look_back", "field_parse", "commit", "tiles"]
+        return {k: int(v) for k, v in zip(names, out)}
 
     def synchronize(self):
         check(self._lib.cratac_synchronize(self._h))

@@ -198,6 +198,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
     if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_kernel")) { c->decode_kernel = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "decode_profile")) { c->decode_profile = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "decode_ctas_per_sm")) { c->sp_ctas_per_sm = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);
@@ -206,6 +207,17 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     }
     set_error("unknown option '%s'", key);
     return CRATAC_ERR_ARG;
+}
+
+int cratac_decode_profile(cratac_ctx* h, int64_t* cycles_out, int n) {
+    Ctx* c = &h->c;
+    if (!cycles_out || n < 1) { set_error("cratac_decode_profile: bad argument"); return CRATAC_ERR_ARG; }
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < n; i++) cycles_out[i] = 0;
+    if (!c->d_sp_scalars.p) return CRATAC_OK;
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    CRATAC_CUDA(cudaMemcpy(cycles_out, c->d_sp_scalars.as<int64_t>() + 8, sizeof(int64_t) * (size_t)std::min(n, 9), cudaMemcpyDeviceToHost));
+    return CRATAC_OK;
 }
 
 int64_t cratac_decode_declined(cratac_ctx* h, int reset) {

@@ -417,7 +417,25 @@ struct StreamArgs {
     IrrTile* irr;                 // declined ranges, appended
     unsigned long long* n_irr;
     int64_t irr_cap;
+    unsigned long long* prof;     // null, or SPP_COUNT cycle counters
 };
+
+// The look-back words carry their whole message in one aligned 64-bit value (flag + count), so they are read and written
+// relaxed: no fence, no L1 invalidation per spin (an acquire load at gpu scope costs both, on every lane, every spin).
+__device__ __forceinline__ unsigned long long sp_ld_state(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sp_st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// per-phase cycle counters (thread 0 / the look-back warp's lane 0), only when StreamArgs::prof is set (tools/decode_bench.py)
+enum { SPP_WAIT = 0, SPP_CLASSIFY, SPP_LIST, SPP_VERIFY, SPP_LOOKBACK, SPP_PARSE, SPP_COMMIT, SPP_TILES, SPP_COUNT };
+#define SP_PROF(slot)                                                                                 \
+    do {                                                                                              \
+        if (PROF && tid == 0) { const long long _t = clock64(); atomicAdd(&a.prof[slot], (unsigned long long)(_t - prof_t)); prof_t = _t; } \
+    } while (0)
 
 // separator flags (bit 7 of every byte below 0x0b), exact for all 256 byte values
 __device__ __forceinline__ uint32_t sp_sepflags(uint32_t w) {
@@ -470,7 +488,7 @@ __device__ __forceinline__ bool sp_parse_uint(const uint32_t* words, int p, int 
     return bad == 0u;
 }
 
-template <int CPT>
+template <int CPT, bool PROF>
 __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
     constexpr int REGION_MAX = SP_THREADS * CPT * 16;              // look-back + tile bytes
     constexpr int MAX_SEPS = REGION_MAX / 6;                       // 5 separators per line of >= 30 bytes (typical: 45)
@@ -520,6 +538,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
     int32_t cid_cache = -1;
     int loc_maxpos = 0, loc_maxneg = 0;
 
+    long long prof_t = PROF ? clock64() : 0;
     for (;;) {
         const int64_t t = s_tile[cur];
         if (t >= a.n_tiles) break;
@@ -546,6 +565,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             __syncthreads();
         }
 
+        SP_PROF(SPP_WAIT);
         // ---- 1. separator masks, chunk c -> thread c % SP_THREADS
         const int64_t lim = d.n_eff - (tile_base - SP_LB);           // region bytes at or beyond it are padding
         for (int c = tid; c < n_chunks; c += SP_THREADS) {
@@ -558,6 +578,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             masks[c] = (uint16_t)m;
         }
         __syncthreads();
+        SP_PROF(SPP_CLASSIFY);
 
         // ---- 2. ordered separator list; thread i owns chunks [i * CPT, (i + 1) * CPT)
         unsigned long long mk[CPT / 4];
@@ -609,6 +630,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             }
         }
         __syncthreads();
+        SP_PROF(SPP_LIST);
         // separators of the look-back (the first SP_LB bytes = the first 4 chunks), straight from their masks
         int n_lb;
         {
@@ -632,6 +654,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                 for (int k = 0; k < rem; k++) if (bytes[seplist[first + 5 * n_lines + k]] != '\t') bad = true;
         }
         const bool irregular = __syncthreads_or(bad ? 1 : 0) != 0;
+        SP_PROF(SPP_VERIFY);
 
         // ---- exact line count of a declined tile: newlines of the tile region, per half (k_parse_tiles takes <= DEC_TILE bytes)
         int tile_lines = n_lines;
@@ -654,8 +677,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
 
         // ---- 3. publish the count, resolve the first output line (last warp), meanwhile parse
         if (warp == SP_THREADS / 32 - 1) {
-            if (lane == 0) st_release_u64(&a.state[t], SP_FLAG_AGG | (unsigned long long)tile_lines);
+            if (lane == 0) sp_st_state(&a.state[t], SP_FLAG_AGG | (unsigned long long)tile_lines);
             long long excl = 0;
+            const long long lb_t0 = PROF ? clock64() : 0;
             if (t == 0) {
                 excl = *a.line_base;
             } else {
@@ -665,7 +689,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                     unsigned long long v;
                     if (idx >= 0) {
                         int spins = 0;
-                        do { v = ld_acquire_u64(&a.state[idx]); } while ((v >> 62) == 0 && ++spins < (1 << 24));
+                        do { v = sp_ld_state(&a.state[idx]); } while ((v >> 62) == 0 && ++spins < (1 << 24));
                     } else {
                         v = idx == -1 ? (SP_FLAG_INC | (unsigned long long)*a.line_base) : SP_FLAG_AGG;   // virtual tile before the launch
                     }
@@ -684,8 +708,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                     look -= 32;
                 }
             }
+            if (PROF && lane == 0) atomicAdd(&a.prof[SPP_LOOKBACK], (unsigned long long)(clock64() - lb_t0));
             if (lane == 0) {
-                if (excl >= 0) st_release_u64(&a.state[t], SP_FLAG_INC | (unsigned long long)(excl + tile_lines));
+                if (excl >= 0) sp_st_state(&a.state[t], SP_FLAG_INC | (unsigned long long)(excl + tile_lines));
                 s_excl = excl;
                 if (excl >= 0 && t == a.n_tiles - 1) *a.line_base_out = excl + tile_lines;
             }
@@ -748,6 +773,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                 ok &= cid >= 0;
             }
             const bool group_bad = __syncthreads_or(ok ? 0 : 1) != 0;  // also orders s_excl before its first use
+            SP_PROF(SPP_PARSE);
             if (!published_seen) { published_seen = true; if (s_excl < 0) return; }
             const long long out0 = s_excl;
             if (group_bad) {
@@ -819,6 +845,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         if (n_lines == 0) { __syncthreads(); if (s_excl < 0) return; }
         cur ^= 1;
         __syncthreads();                                             // buffers, lists and s_* are reused by the next tile
+        SP_PROF(SPP_COMMIT);
+        if (PROF && tid == 0) atomicAdd(&a.prof[SPP_TILES], 1ULL);
     }
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) {
@@ -1095,23 +1123,19 @@ static int sp_launch(Ctx* c, const DecodeArgs& base, int64_t tile0, int64_t n_ti
     a.irr = c->d_sp_irr.as<IrrTile>();
     a.irr_cap = c->sp_irr_cap;
     a.line_base = line_base; a.line_base_out = line_base_out;
+    a.prof = c->decode_profile ? c->d_sp_scalars.as<unsigned long long>() + 8 : nullptr;
     CRATAC_CUDA(cudaMemsetAsync(a.state, 0, 8 * (size_t)n_tiles, c->stream));
     CRATAC_CUDA(cudaMemsetAsync(a.ticket, 0, 8, c->stream));
     const size_t smem = sp_smem_bytes(cpt);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[cpt == 8]) {
-        if (cpt == 8) CRATAC_CUDA(cudaFuncSetAttribute(k_parse_stream<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CRATAC_CUDA(cudaFuncSetAttribute(k_parse_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[cpt == 8] = true;
-    }
+    void (*kern)(StreamArgs) = cpt == 8 ? (a.prof ? k_parse_stream<8, true> : k_parse_stream<8, false>)
+                                        : (a.prof ? k_parse_stream<4, true> : k_parse_stream<4, false>);
+    CRATAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    if (cpt == 8) CRATAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_parse_stream<8>, SP_THREADS, smem));
-    else CRATAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_parse_stream<4>, SP_THREADS, smem));
+    CRATAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SP_THREADS, smem));
     if (per_sm < 1) { set_error("k_parse_stream does not fit on an SM"); return CRATAC_ERR_INTERNAL; }
     if (c->sp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->sp_ctas_per_sm);
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)NUM_SMS * per_sm);   // every CTA resident: tiles wait on earlier tiles
-    if (cpt == 8) k_parse_stream<8><<<grid, SP_THREADS, smem, c->stream>>>(a);
-    else k_parse_stream<4><<<grid, SP_THREADS, smem, c->stream>>>(a);
+    kern<<<grid, SP_THREADS, smem, c->stream>>>(a);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     return CRATAC_OK;
@@ -1123,10 +1147,10 @@ static int sp_reserve(Ctx* c, int64_t n_eff, int64_t* n_tiles_out) {
     int64_t n_tiles = (n_eff + TB - 1) / TB;
     if (n_tiles == 0) n_tiles = 1;
     CRATAC_TRY(c->d_sp_state.reserve(8 * (size_t)n_tiles));
-    CRATAC_TRY(c->d_sp_scalars.reserve(64));
+    CRATAC_TRY(c->d_sp_scalars.reserve(256));
     c->sp_irr_cap = 2 * n_tiles;
     CRATAC_TRY(c->d_sp_irr.reserve(sizeof(IrrTile) * (size_t)c->sp_irr_cap));
-    CRATAC_CUDA(cudaMemsetAsync(c->d_sp_scalars.p, 0, 64, c->stream));   // ticket, declined ranges, line base
+    CRATAC_CUDA(cudaMemsetAsync(c->d_sp_scalars.p, 0, 256, c->stream));   // ticket, declined ranges, line base, cycle counters
     *n_tiles_out = n_tiles;
     return CRATAC_OK;
 }

@@ -71,6 +71,10 @@ int64_t cratac_launch_count(cratac_ctx* ctx, int reset);
 /* text ranges (of at most 16 KiB) the single-pass decoder handed to the general parse kernel since creation / last reset:
  * 0 on a clean fragments.tsv (tools/io.py:75-92 shaped lines of at most 64 bytes) */
 int64_t cratac_decode_declined(cratac_ctx* ctx, int reset);
+/* option "decode_profile" = 1: k_parse_stream adds up SM cycles per phase of its tile loop (one thread's clock per CTA);
+ * this reads the first n (<= 9) counters of the last decode: wait for the tile, separator masks, separator list, structure
+ * check, look-back, field parse, commit, tiles.  Diagnostics only (tools/decode_bench.py). */
+int cratac_decode_profile(cratac_ctx* ctx, int64_t* cycles_out, int n);
 int cratac_synchronize(cratac_ctx* ctx);
 /* the CUDA stream every kernel of this context is launched on (cudaStream_t as an integer) */
 int cratac_stream(cratac_ctx* ctx, uint64_t* stream_out);

@@ -28,7 +28,7 @@ def main():
     contigs = synth.GRCH38
     ctx = _ffi.Context(contigs, primary=[c[0] for c in contigs], device=0)
     ctx.set_option("profile", 1)
-    text, nbytes = bench.make_workload(torch, ctx, contigs, args.fragments, args.cells, 100000, 2, device)
+    text, nbytes, _n = bench.make_workload(torch, ctx, contigs, args.fragments, args.cells, 100000, 2, device)
     peak = bench.measured_peaks()[0]
     variants = [(0, 0), (1, 0), (1, 4), (1, 3), (1, 2), (2, 0), (2, 1)]
     for kernel, cap in variants:
@@ -48,6 +48,16 @@ def main():
                           "ms": round(ms, 3), "stages_ms": {k: round(v / args.reps, 3) for k, v in tot.items()},
                           "algorithmic_gbs": round(alg / 1e9 / (ms / 1e3), 1), "frac_of_measured_hbm": round(alg / 1e9 / (ms / 1e3) / peak, 3),
                           "declined_ranges": ctx.decode_declined(reset=True)}), flush=True)
+    # where the single-pass kernel's time goes: cycles per phase and tile (one thread's clock per CTA)
+    for kernel in (1, 2):
+        ctx.set_option("decode_kernel", kernel)
+        ctx.set_option("decode_ctas_per_sm", 0)
+        ctx.set_option("decode_profile", 1)
+        ctx.decode_device(text.data_ptr(), nbytes)
+        prof = ctx.decode_profile()
+        tiles = max(prof.pop("tiles"), 1)
+        print(json.dumps({"decode_kernel": kernel, "cycles_per_tile": {k: round(v / tiles) for k, v in prof.items()}, "tiles": tiles}), flush=True)
+        ctx.set_option("decode_profile", 0)
     ctx.close()
 
 

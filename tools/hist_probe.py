@@ -6,7 +6,7 @@ import bench
 frs=int(sys.argv[1]) if len(sys.argv)>1 else 250000000
 ctx=_ffi.Context(synth.GRCH38, device=0)
 dev=torch.device('cuda',0)
-text,nb=bench.make_workload(torch, ctx, synth.GRCH38, frs, 10000, 100000, 2, dev)
+text,nb,_n=bench.make_workload(torch, ctx, synth.GRCH38, frs, 10000, 100000, 2, dev)
 ctx.decode_device(text.data_ptr(), nb)
 v,w=ctx.count_cut_sites()
 print('bins',len(v),'vmax',int(v.max()),'sum',int(w.sum()))

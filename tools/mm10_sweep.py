@@ -48,7 +48,7 @@ def main():
             try:
                 ctx = _ffi.Context(contigs, primary=[c[0] for c in contigs], device=0)
                 ctx.set_option("profile", 1)
-                text, nbytes = bench.make_workload(torch, ctx, contigs, args.fragments, cells, n_peaks, 5, device)
+                text, nbytes, _n = bench.make_workload(torch, ctx, contigs, args.fragments, cells, n_peaks, 5, device)
                 stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
                 settings = [int(x) for x in args.py2_device_min.split(",") if x] or [None]
                 for si, setting in enumerate(settings):
