@@ -428,12 +428,14 @@ def main():
         torch.cuda.synchronize()
 
     trace = []
+    last_shard = [None]
 
     def step_device():
         if world == 1:
             return ctx.run(device_ptr=text.data_ptr(), nbytes=nbytes, odds_ratio=0.2)
         with torch.cuda.stream(stream):
             shard = multi.CudaShard(ctx, torch, device, text_dev_ptr=text.data_ptr(), nbytes=nbytes)
+            last_shard[0] = shard
             trace.clear()
             return multi.step(shard, torch, dist, device, trace=trace)
 
@@ -477,6 +479,22 @@ def main():
                                                 "slowest_step_phases": slow_trace[1] if slow_trace else None})
     total_frags = args.steps * args.fragments
     value = total_frags / (dev_ms / 1000.0)
+
+    # ---- checksum of the result (outside the timed region): equal for every --gpus N on the same library
+    checksum = None
+    if not args.no_checksum:
+        if world == 1:
+            pk = tuple(torch.from_numpy(x).to(device) for x in ctx.get_peaks(int(res.n_peaks)))
+            nnz1, ipp, ixp, dtp = ctx.matrix_device(int(res.nnz))
+            ip_t = multi.dev_tensor(torch, ipp, int(res.n_barcodes) + 1, "<i8", device)
+            ix_t = multi.dev_tensor(torch, ixp, nnz1, "<i8", device)
+            dt_t = multi.dev_tensor(torch, dtp, nnz1, "<i4", device)
+            keys = torch.from_numpy(np.array([multi.packed_barcode_key(b) for b in ctx.get_barcodes()], dtype=np.int64)).to(device)
+            checksum = result_checksum(torch, dist, 1, device, res.threshold, pk, 0, ip_t, ix_t, dt_t, keys)
+        else:
+            pk = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(device) for x in last_shard[0].peaks)
+            ip_t, ix_t, dt_t = last_shard[0].held_matrix()
+            checksum = result_checksum(torch, dist, world, device, res.threshold, pk, res.row_base, ip_t, ix_t, dt_t, res.col_keys)
 
     # ---- end to end from pinned host text to pinned host results
     e2e = None
@@ -548,11 +566,12 @@ def main():
     dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roofline = None
     traffic = None
-    ncu_csv = os.path.join(ROOT, "profiles", "r01g_kernels_full_250m.csv")
-    if dom and world == 1 and args.fragments == 250000000 and os.path.exists(ncu_csv):
-        # DRAM bytes of the dominant group's kernels from the committed `ncu --set full` capture of this same workload
+    ncu_csv = args.ncu_csv
+    if dom and ncu_csv and os.path.exists(ncu_csv):
+        # DRAM bytes of the dominant group's kernels from the `ncu --set full` capture named on the command line (a capture
+        # of this same command; tools/ncu_summary.py writes the CSV): one launch of each kernel of the group
         import csv
-        name_of = {"decode": ("k_count_newlines", "k_parse_tiles"), "pileup_window_hist": ("k_pileup<0>",), "pileup_call_peaks": ("k_pileup<1>",),
+        name_of = {"decode": ("k_parse_stream", "k_count_newlines", "k_parse_tiles"), "pileup_window_hist": ("k_pileup<0>",), "pileup_call_peaks": ("k_pileup<1>",),
                    "overlap": ("k_overlap(",), "sort_reduce": ("k_reduce_warp", "k_reduce_small", "k_reduce_large"),
                    "csc_build": ("k_csc_copy",)}[dom]
         rows = list(csv.reader(open(ncu_csv)))
@@ -563,12 +582,12 @@ def main():
                 if nm in r[0] and nm not in seen:               # one launch of each kernel
                     seen.add(nm)
                     total += float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")])
-        if len(seen) == len(name_of):
+        if seen:
             traffic = total * 1e9                               # the capture reports Gbyte
     if dom:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
                     "frac": kernels[dom]["frac"], "traffic": traffic,
-                    "traffic_note": "bytes per step: ncu dram__bytes_read.sum + dram__bytes_write.sum of the group's kernels, profiles/r01g_kernels_full_250m.csv" if traffic else None,
+                    "traffic_note": ("bytes per step: ncu dram__bytes_read.sum + dram__bytes_write.sum of the group's kernels, " + str(ncu_csv)) if traffic else "no --ncu-csv given: not measured by this run",
                     "peak_source": peak_src,
                     "note": "achieved = SURVEY section 8d algorithmic bytes of the stages the kernel replaces / CUDA-event time"}
 
@@ -605,7 +624,7 @@ def main():
             "kernels": kernels, "filter_peak_matrix": filter_info, "em_fit_ms": em_ms, "em_iterations": int(res.em_iterations), "em_inner_iterations": int(res.em_inner_iterations),
             "result": {"n_fragments": int(res.n_fragments), "n_fragments_rank0": int(n_frag_r0), "n_barcodes": int(res.n_barcodes),
                        "threshold": int(res.threshold), "n_peaks": int(res.n_peaks), "n_peaks_rank0": int(n_peaks_r0), "nnz": int(res.nnz),
-                       "nnz_rank0": int(nnz_r0), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes)},
+                       "nnz_rank0": int(nnz_r0), "hits_rank0": K_hits, "text_bytes_rank0": int(nbytes), "checksum": checksum},
             "wall_ms_per_step": 1000.0 * wall / args.steps, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
             "host_phases_last_step_ms": ctx.host_times()[-12:], "multi_phases_last_step_ms": traces_by_rank,
             "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},

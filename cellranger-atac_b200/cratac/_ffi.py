@@ -429,6 +429,12 @@ class Context(object):
         check(self._lib.cratac_matrix_device(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return nnz.value, a.value, b.value, c.value
 
+    def matrix_device(self, nnz):
+        """Device pointers of the current CSC -> (nnz, d_indptr, d_indices, d_data)."""
+        a, b, c = c_vp(), c_vp(), c_vp()
+        check(self._lib.cratac_matrix_device(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return int(nnz), a.value, b.value, c.value
+
     def merge_rank_csc(self, world, n_cols, d_indptr_all, d_rank_off, d_indices_all, d_data_all, total_nnz):
         check(self._lib.cratac_merge_rank_csc(self._h, int(world), int(n_cols), c_vp(int(d_indptr_all)), c_vp(int(d_rank_off)),
                                               c_vp(int(d_indices_all)), c_vp(int(d_data_all)), int(total_nnz)))

@@ -85,6 +85,16 @@ def global_columns(torch, keys_all, first_all, hash_all, valid_all, py2_order_fn
     return n, col_flat.reshape(valid_all.shape), uniq[col_to_uniq]
 
 
+def packed_barcode_key(bc):
+    """The library's 64-bit key of a 10x barcode "[ACGT]{16}-<group>": 2 bits per base (A 0, C 1, T 2, G 3; first base in
+    the top bits) | group << 32.  (Other strings are keyed by a 63-bit hash on the device; not reproduced here.)"""
+    seq, grp = bc.split("-")
+    v = 0
+    for ch in seq:
+        v = (v << 2) | ((ord(ch) >> 1) & 3)
+    return (int(grp) << 32) | v
+
+
 # --------------------------------------------------------------------------------------------- the step
 class StepResult(object):
     def __init__(self, **kw):

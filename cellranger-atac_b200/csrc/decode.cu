@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
 // group has parsed, so the hand-over is exact.
 constexpr int SP_THREADS = 256;
 constexpr int SP_LB = 64;                       // look-back bytes = the chunks of thread 0
+constexpr int SP_LOOK = 8;                     // look-back words per lane and round
 constexpr int SP_PAD = 16;                      // slack before and after the staged bytes (word windows may over-read)
 constexpr unsigned long long SP_FLAG_AGG = 1ULL << 62, SP_FLAG_INC = 2ULL << 62, SP_VALUE_MASK = (1ULL << 62) - 1ULL;
 
@@ -683,29 +684,42 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             if (t == 0) {
                 excl = *a.line_base;
             } else {
+                // Every tile of a wave looks back at the same time and none of them has its inclusive prefix yet, so the walk
+                // goes back through the whole wave (hundreds of tiles): each lane takes SP_LOOK consecutive words per round
+                // (independent loads, one memory round trip for 32 * SP_LOOK tiles).  Lane 0 holds the nearest words.
                 int64_t look = t - 1;
                 for (;;) {
-                    const int64_t idx = look - lane;
-                    unsigned long long v;
-                    if (idx >= 0) {
-                        int spins = 0;
-                        do { v = sp_ld_state(&a.state[idx]); } while ((v >> 62) == 0 && ++spins < (1 << 24));
-                    } else {
-                        v = idx == -1 ? (SP_FLAG_INC | (unsigned long long)*a.line_base) : SP_FLAG_AGG;   // virtual tile before the launch
+                    long long lane_sum = 0;
+                    bool lane_inc = false, lane_stuck = false;
+                    unsigned long long v[SP_LOOK];
+                    const int64_t top = look - (int64_t)lane * SP_LOOK;
+#pragma unroll
+                    for (int j = 0; j < SP_LOOK; j++) {
+                        const int64_t idx = top - j;
+                        v[j] = idx >= 0 ? sp_ld_state(&a.state[idx])
+                                        : (idx == -1 ? (SP_FLAG_INC | (unsigned long long)*a.line_base) : SP_FLAG_AGG);   // virtual tile before the launch
                     }
-                    const unsigned has_inc = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                    const unsigned stuck = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+#pragma unroll
+                    for (int j = 0; j < SP_LOOK; j++) {
+                        const int64_t idx = top - j;
+                        int spins = 0;
+                        while ((v[j] >> 62) == 0 && ++spins < (1 << 22)) v[j] = sp_ld_state(&a.state[idx]);
+                        if ((v[j] >> 62) == 0) lane_stuck = true;
+                        if (!lane_inc) { lane_sum += (long long)(v[j] & SP_VALUE_MASK); lane_inc = (v[j] >> 62) == 2; }
+                    }
+                    const unsigned has_inc = __ballot_sync(0xffffffffu, lane_inc);
+                    const unsigned stuck = __ballot_sync(0xffffffffu, lane_stuck);
                     if (stuck) { if (lane == 0) raise_error(d.status, CRATAC_ERR_INTERNAL, -200 - gt); excl = -1; break; }
-                    long long contrib = (long long)(v & SP_VALUE_MASK);
+                    long long contrib = lane_sum;
                     if (has_inc) {
-                        const int fp = __ffs(has_inc) - 1;           // nearest predecessor with an inclusive prefix
+                        const int fp = __ffs(has_inc) - 1;           // nearest lane that met an inclusive prefix
                         if (lane > fp) contrib = 0;
                     }
 #pragma unroll
                     for (int dd = 16; dd; dd >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, dd);
                     excl += contrib;
                     if (has_inc) break;
-                    look -= 32;
+                    look -= 32 * SP_LOOK;
                 }
             }
             if (PROF && lane == 0) atomicAdd(&a.prof[SPP_LOOKBACK], (unsigned long long)(clock64() - lb_t0));

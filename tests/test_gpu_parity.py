@@ -639,7 +639,7 @@ def test_single_pass_decode_hands_odd_lines_to_the_general_kernel(kernel):
         f = lines[i].split("\t")
         kind = int(rng.integers(0, 5))
         if kind == 0:
-            f[3] = "long_generic_barcode_" + "x" * int(rng.integers(30, 150)) + "-1"
+            f[3] = "long_generic_barcode_" + "x" * int(rng.integers(30, 39)) + "-1"      # line > 64 bytes, barcode <= 63
         elif kind == 1:
             f[4] = f[4] + "\r"
         elif kind == 2:
@@ -674,11 +674,11 @@ def test_single_pass_decode_tile_borders_and_errors(kernel):
     ctx.set_option("decode_kernel", kernel)
     ctx.set_option("stream_decode", 0)
     def filler(nbytes, head=b"chr1\t0\t1\t"):
-        """Lines with generic barcodes, `nbytes` bytes in all, none above 200: on chr1 at position 0 in front of the body,
-        on the contig after chr1 behind it (the file stays sorted)."""
+        """Lines with generic barcodes (<= 63 bytes, the library's limit), `nbytes` bytes in all: on chr1 at position 0 in
+        front of the body, on the contig after chr1 behind it (the file stays sorted)."""
         out = []
         while nbytes > 0:
-            take = nbytes if nbytes <= 200 else (100 if nbytes - 100 >= 30 else nbytes - 30)
+            take = nbytes if nbytes <= 70 else (50 if nbytes - 50 >= 30 else nbytes - 30)
             assert take >= len(head) + 4
             out.append(head + b"G" * (take - len(head) - 3) + b"\t1\n")
             nbytes -= take
