@@ -199,6 +199,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_kernel")) { c->decode_kernel = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "decode_profile")) { c->decode_profile = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "decode_mode")) { c->decode_mode = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "decode_ctas_per_sm")) { c->sp_ctas_per_sm = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "profile")) {
         if (value && !c->ev[0]) for (int i = 0; i < 2 * SG_COUNT; i++) cudaEventCreate(&c->ev[i]);

@@ -170,6 +170,7 @@ struct Ctx {
     int64_t* h_sp_scalars = nullptr;       // pinned mirror of d_sp_scalars (4 words)
     int decode_kernel = 1;                 // option "decode_kernel": 0 two passes (count + parse), 1 single pass with 16 KiB tiles, 2 with 32 KiB tiles
     int sp_ctas_per_sm = 0;                // option "decode_ctas_per_sm": cap on resident CTAs of k_parse_stream (0: occupancy)
+    int decode_mode = 0;                   // option "decode_mode": experiment bits of k_parse_stream (StreamArgs::mode)
     int decode_profile = 0;                // option "decode_profile": per-phase cycle counters of k_parse_stream (cratac_decode_profile)
     int64_t decode_declined = 0;           // text ranges the single-pass kernel handed to the general kernel (since creation)
     int stream_decode = 1;                 // option "stream_decode": 0 off, 1 overlap the H2D copy of a host text >= 64 MiB with its decode, 2 always

@@ -41,13 +41,13 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
 
 // ------------------------------------------------------------------ pass A: newline counts
 __global__ void __launch_bounds__(256) k_count_newlines(const char* __restrict__ text, int64_t nbytes, int64_t n_eff,
-                                                         int32_t* __restrict__ tile_counts, int64_t tile0) {
-    // one CTA per tile; 256 threads x 4 x 16 B
-    int64_t tile_base = ((int64_t)blockIdx.x + tile0) * DEC_TILE;
+                                                         int32_t* __restrict__ tile_counts, int64_t tile0, int tile_bytes) {
+    // one CTA per tile (tile_bytes: a multiple of 16, DEC_TILE on the two-pass path); 256 threads x 16 B per round
+    int64_t tile_base = ((int64_t)blockIdx.x + tile0) * tile_bytes;
     int cnt = 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(text) & 15) == 0);
-#pragma unroll
-    for (int k = 0; k < DEC_TILE / (256 * 16); k++) {
+    for (int k = 0; k * (256 * 16) < tile_bytes; k++) {
+        if ((k * 256 + (int)threadIdx.x) * 16 >= tile_bytes) break;
         int64_t off = tile_base + ((int64_t)k * 256 + threadIdx.x) * 16;
         if (aligned && off + 16 <= nbytes) {
             uint4 v = __ldg(reinterpret_cast<const uint4*>(text + off));
@@ -419,6 +419,8 @@ struct StreamArgs {
     unsigned long long* n_irr;
     int64_t irr_cap;
     unsigned long long* prof;     // null, or SPP_COUNT cycle counters
+    int mode;                     // bit 0: the next tile's ticket is taken when the tile starts (no prefetch of its bytes);
+                                  // bit 1: line numbers come from a count pass (d.tile_offsets): no publish, no look-back
 };
 
 // The look-back words carry their whole message in one aligned 64-bit value (flag + count), so they are read and written
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         uint32_t* const bufw = cur ? bufw1 : bufw0;
         const uint32_t* const words = bufw + SP_PAD / 4;            // byte position 0 = first look-back byte
         unsigned char* const bytes = reinterpret_cast<unsigned char*>(bufw) + SP_PAD;
-        if (tid == 0) {                                             // next tile: ticket now, bytes in flight while this one is parsed
+        if (tid == 0 && !(a.mode & 1)) {                            // next tile: ticket now, bytes in flight while this one is parsed
             const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
             s_tile[cur ^ 1] = tn;
             if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur ^ 1);
@@ -677,7 +679,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         }
 
         // ---- 3. publish the count, resolve the first output line (last warp), meanwhile parse
-        if (warp == SP_THREADS / 32 - 1) {
+        if (a.mode & 2) {
+            if (tid == 0) s_excl = d.tile_offsets[gt];
+        } else if (warp == SP_THREADS / 32 - 1) {
             if (lane == 0) sp_st_state(&a.state[t], SP_FLAG_AGG | (unsigned long long)tile_lines);
             long long excl = 0;
             const long long lb_t0 = PROF ? clock64() : 0;
@@ -703,7 +707,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                     for (int j = 0; j < SP_LOOK; j++) {
                         const int64_t idx = top - j;
                         int spins = 0;
-                        while ((v[j] >> 62) == 0 && ++spins < (1 << 22)) v[j] = sp_ld_state(&a.state[idx]);
+                        while ((v[j] >> 62) == 0 && ++spins < (1 << 22)) { __nanosleep(200); v[j] = sp_ld_state(&a.state[idx]); }
                         if ((v[j] >> 62) == 0) lane_stuck = true;
                         if (!lane_inc) { lane_sum += (long long)(v[j] & SP_VALUE_MASK); lane_inc = (v[j] >> 62) == 2; }
                     }
@@ -748,6 +752,11 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             }
             if (s_excl < 0) return;
             cur ^= 1;
+            if ((a.mode & 1) && tid == 0) {
+                const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
+                s_tile[cur] = tn;
+                if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur);
+            }
             __syncthreads();
             continue;
         }
@@ -858,6 +867,11 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         }
         if (n_lines == 0) { __syncthreads(); if (s_excl < 0) return; }
         cur ^= 1;
+        if ((a.mode & 1) && tid == 0) {                              // ticket taken when the tile starts: tiles start in index order
+            const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
+            s_tile[cur] = tn;
+            if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur);
+        }
         __syncthreads();                                             // buffers, lists and s_* are reused by the next tile
         SP_PROF(SPP_COMMIT);
         if (PROF && tid == 0) atomicAdd(&a.prof[SPP_TILES], 1ULL);
@@ -1138,6 +1152,18 @@ static int sp_launch(Ctx* c, const DecodeArgs& base, int64_t tile0, int64_t n_ti
     a.irr_cap = c->sp_irr_cap;
     a.line_base = line_base; a.line_base_out = line_base_out;
     a.prof = c->decode_profile ? c->d_sp_scalars.as<unsigned long long>() + 8 : nullptr;
+    a.mode = c->decode_mode;
+    if (a.mode & 2) {
+        // line numbers from a count pass over the same tiles (A/B of the look-back; one launch only: offsets are absolute)
+        CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
+        CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
+        c->stage_begin(SG_DECODE_COUNT);
+        k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(base.text, base.nbytes, base.n_eff, c->d_tile_counts.as<int32_t>(), tile0, a.tile_bytes);
+        c->stage_end(SG_DECODE_COUNT);
+        CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>(), c->d_tile_offsets.as<int64_t>(), n_tiles, line_base_out));
+        a.d.tile_offsets = c->d_tile_offsets.as<int64_t>();
+        c->launches++;
+    }
     CRATAC_CUDA(cudaMemsetAsync(a.state, 0, 8 * (size_t)n_tiles, c->stream));
     CRATAC_CUDA(cudaMemsetAsync(a.ticket, 0, 8, c->stream));
     const size_t smem = sp_smem_bytes(cpt);
@@ -1289,7 +1315,7 @@ static int decode_text_two_pass(Ctx* c, const char* d_text, int64_t nbytes) {
     CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
     CRATAC_TRY(c->d_tile_offsets.reserve(sizeof(int64_t) * (size_t)(n_tiles + 1)));
     c->stage_begin(SG_DECODE_COUNT);
-    k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), 0);
+    k_count_newlines<<<(unsigned)n_tiles, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), 0, DEC_TILE);
     c->stage_end(SG_DECODE_COUNT);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
@@ -1505,7 +1531,7 @@ static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nby
         CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
         CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->copy_event, 0));
         const unsigned nt = (unsigned)(t1 - t0);
-        k_count_newlines<<<nt, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), t0);
+        k_count_newlines<<<nt, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), t0, DEC_TILE);
         CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>() + t0, c->d_tile_offsets.as<int64_t>() + t0, t1 - t0, chunk_total));
         a.tile0 = t0;
         k_parse_tiles<<<nt, DEC_THREADS, 0, c->stream>>>(a);

@@ -30,10 +30,11 @@ def main():
     ctx.set_option("profile", 1)
     text, nbytes, _n = bench.make_workload(torch, ctx, contigs, args.fragments, args.cells, 100000, 2, device)
     peak = bench.measured_peaks()[0]
-    variants = [(0, 0), (1, 0), (2, 0)]
-    for kernel, cap in variants:
+    # (decode_kernel, decode_mode): mode bit 0 = ticket taken at tile start (no prefetch), bit 1 = line numbers from a count pass
+    variants = [(0, 0), (1, 0), (1, 1), (1, 2), (1, 3), (2, 1), (2, 2)]
+    for kernel, mode in variants:
         ctx.set_option("decode_kernel", kernel)
-        ctx.set_option("decode_ctas_per_sm", cap)
+        ctx.set_option("decode_mode", mode)
         tot = {}
         n = nb = 0
         for rep in range(args.reps + 2):
@@ -44,19 +45,19 @@ def main():
                         tot[k] = tot.get(k, 0.0) + v
         ms = sum(tot.values()) / args.reps
         alg = nbytes + 20 * n
-        print(json.dumps({"decode_kernel": kernel, "ctas_per_sm_cap": cap, "fragments": n, "barcodes": nb, "text_bytes": nbytes,
+        print(json.dumps({"decode_kernel": kernel, "decode_mode": mode, "fragments": n, "barcodes": nb, "text_bytes": nbytes,
                           "ms": round(ms, 3), "stages_ms": {k: round(v / args.reps, 3) for k, v in tot.items()},
                           "algorithmic_gbs": round(alg / 1e9 / (ms / 1e3), 1), "frac_of_measured_hbm": round(alg / 1e9 / (ms / 1e3) / peak, 3),
                           "declined_ranges": ctx.decode_declined(reset=True)}), flush=True)
     # where the single-pass kernel's time goes: cycles per phase and tile (one thread's clock per CTA)
-    for kernel in (1, 2):
+    for kernel, mode in ((1, 1), (1, 2), (2, 2)):
         ctx.set_option("decode_kernel", kernel)
-        ctx.set_option("decode_ctas_per_sm", 0)
+        ctx.set_option("decode_mode", mode)
         ctx.set_option("decode_profile", 1)
         ctx.decode_device(text.data_ptr(), nbytes)
         prof = ctx.decode_profile()
         tiles = max(prof.pop("tiles"), 1)
-        print(json.dumps({"decode_kernel": kernel, "cycles_per_tile": {k: round(v / tiles) for k, v in prof.items()}, "tiles": tiles}), flush=True)
+        print(json.dumps({"decode_kernel": kernel, "decode_mode": mode, "cycles_per_tile": {k: round(v / tiles) for k, v in prof.items()}, "tiles": tiles}), flush=True)
         ctx.set_option("decode_profile", 0)
     ctx.close()
 
