@@ -498,12 +498,11 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
     extern __shared__ __align__(128) unsigned char sp_smem[];
     uint32_t* bufw0 = reinterpret_cast<uint32_t*>(sp_smem);
     uint32_t* bufw1 = bufw0 + (SP_PAD + REGION_MAX + SP_PAD) / 4;
-    uint16_t* masks = reinterpret_cast<uint16_t*>(bufw1 + (SP_PAD + REGION_MAX + SP_PAD) / 4);   // [SP_THREADS * CPT]
-    uint16_t* seplist = masks + SP_THREADS * CPT;                                                  // [MAX_SEPS]
+    uint16_t* seplist = reinterpret_cast<uint16_t*>(bufw1 + (SP_PAD + REGION_MAX + SP_PAD) / 4);   // [MAX_SEPS]
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int warp_tot[SP_THREADS / 32];
     __shared__ int64_t s_tile[2];
-    __shared__ int s_r, s_irregular;
+    __shared__ int s_r, s_irregular, s_nlb;
     __shared__ long long s_excl;
     __shared__ int s_nl_parts[3];
 
@@ -516,7 +515,6 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int c = tid; c < SP_THREADS * CPT; c += SP_THREADS) masks[c] = 0;    // chunks beyond the region stay empty
     __syncthreads();
 
     auto tile_is_tma = [&](int64_t t) -> bool {     // t: tile of this launch
@@ -528,8 +526,12 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         mbar_expect_tx(&bar[b], (uint32_t)region);
         tma_load_1d(reinterpret_cast<unsigned char*>(w) + SP_PAD, d.text + (t + a.tile0) * TB - SP_LB, (uint32_t)region, &bar[b]);
     };
+    auto next_tile = [&](int64_t prev) -> int64_t {   // thread 0; prev < 0: the CTA's first tile
+        if (a.mode & 2) return prev < 0 ? (int64_t)blockIdx.x : prev + gridDim.x;   // no tile waits on another: static round-robin
+        return (int64_t)atomicAdd(a.ticket, 1ULL);
+    };
     if (tid == 0) {
-        const int64_t t = (int64_t)atomicAdd(a.ticket, 1ULL);
+        const int64_t t = next_tile(-1);
         s_tile[0] = t;
         if (t < a.n_tiles && tile_is_tma(t)) issue(t, 0);
     }
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         const uint32_t* const words = bufw + SP_PAD / 4;            // byte position 0 = first look-back byte
         unsigned char* const bytes = reinterpret_cast<unsigned char*>(bufw) + SP_PAD;
         if (tid == 0 && !(a.mode & 1)) {                            // next tile: ticket now, bytes in flight while this one is parsed
-            const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
+            const int64_t tn = next_tile(t);
             s_tile[cur ^ 1] = tn;
             if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur ^ 1);
         }
@@ -569,29 +571,35 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         }
 
         SP_PROF(SPP_WAIT);
-        // ---- 1. separator masks, chunk c -> thread c % SP_THREADS
+        // ---- 1. separator masks of my CPT consecutive 16-byte chunks (64 contiguous bytes per 4 chunks: the 128-bit shared
+        //         loads of a quarter-warp collide 4 ways, which costs less than a trip of the masks through shared memory
+        //         and the barrier that goes with it)
         const int64_t lim = d.n_eff - (tile_base - SP_LB);           // region bytes at or beyond it are padding
-        for (int c = tid; c < n_chunks; c += SP_THREADS) {
-            const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * c);
-            uint32_t m = sp_sepmask16(v);
-            if (lim < region) {                                      // last tile only
-                const int64_t keep = lim - 16 * (int64_t)c;
-                m = keep <= 0 ? 0u : (keep >= 16 ? m : (m & ((1u << keep) - 1u)));
-            }
-            masks[c] = (uint16_t)m;
-        }
-        __syncthreads();
-        SP_PROF(SPP_CLASSIFY);
-
-        // ---- 2. ordered separator list; thread i owns chunks [i * CPT, (i + 1) * CPT)
         unsigned long long mk[CPT / 4];
         int my_cnt = 0;
 #pragma unroll
         for (int q = 0; q < CPT / 4; q++) {
-            const uint2 v = *reinterpret_cast<const uint2*>(masks + tid * CPT + 4 * q);
-            mk[q] = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
-            my_cnt += __popcll(mk[q]);
+            unsigned long long m64 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = tid * CPT + 4 * q + k;
+                uint32_t m = 0;
+                if (c < n_chunks) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * c);
+                    m = sp_sepmask16(v);
+                    if (lim < region) {                              // last tile only
+                        const int64_t keep = lim - 16 * (int64_t)c;
+                        m = keep <= 0 ? 0u : (keep >= 16 ? m : (m & ((1u << keep) - 1u)));
+                    }
+                }
+                m64 |= (unsigned long long)m << (16 * k);
+            }
+            mk[q] = m64;
+            my_cnt += __popcll(m64);
         }
+        SP_PROF(SPP_CLASSIFY);
+
+        // ---- 2. ordered separator list
         int incl = my_cnt;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
@@ -603,6 +611,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             // first line of the tile: tabs after the last newline of the look-back (thread 0's chunks ARE the look-back
             // when CPT == 4; with CPT == 8 the look-back is the first half of them)
             unsigned long long lb = mk[0];
+            const int my_cnt_lb = __popcll(lb);                      // separators of the look-back (the first SP_LB bytes)
             int r = 0, found = 0, irregular = 0;
             while (lb) {
                 const int j = 63 - __clzll((long long)lb);
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                 if (ch != '\t' || ++r > 4) { irregular = 1; break; }
             }
             if (!found) irregular = 1;                               // a line longer than the look-back
-            s_r = r; s_irregular = irregular;
+            s_r = r; s_irregular = irregular; s_nlb = my_cnt_lb;
         }
         __syncthreads();
         int woff = 0, s_all = 0;
@@ -634,12 +643,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         }
         __syncthreads();
         SP_PROF(SPP_LIST);
-        // separators of the look-back (the first SP_LB bytes = the first 4 chunks), straight from their masks
-        int n_lb;
-        {
-            const uint2 v = *reinterpret_cast<const uint2*>(masks);
-            n_lb = __popc(v.x) + __popc(v.y);
-        }
+        const int n_lb = s_nlb;
         const int first = n_lb - s_r;                                // list index of the first line's first separator
         const int q_seps = s_all - first;
         const int n_lines = q_seps / 5;
@@ -868,7 +872,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         if (n_lines == 0) { __syncthreads(); if (s_excl < 0) return; }
         cur ^= 1;
         if ((a.mode & 1) && tid == 0) {                              // ticket taken when the tile starts: tiles start in index order
-            const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
+            const int64_t tn = next_tile(-2);
             s_tile[cur] = tn;
             if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur);
         }
@@ -1135,7 +1139,7 @@ static int sp_cpt(const Ctx* c) { return c->decode_kernel == 2 ? 8 : 4; }
 static int sp_tile_bytes(const Ctx* c) { return SP_THREADS * sp_cpt(c) * 16 - SP_LB; }
 static size_t sp_smem_bytes(int cpt) {
     const size_t region_max = (size_t)SP_THREADS * cpt * 16;
-    return 2 * (SP_PAD + region_max + SP_PAD) + 2 * (size_t)SP_THREADS * cpt + 2 * (region_max / 6) + 64;
+    return 2 * (SP_PAD + region_max + SP_PAD) + 2 * (region_max / 6) + 64;
 }
 
 // queue one launch over the tiles [tile0, tile0 + n_tiles) of the text described by `base`
