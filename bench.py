@@ -504,10 +504,12 @@ def main():
         torch.cuda.synchronize()
         nb = res.n_barcodes
         out_indptr = torch.empty(nb + 1, dtype=torch.int64, pin_memory=True)
-        cap_nnz = int(res.nnz * 1.05) + 1024 if (world == 1 or rank == 0) else 16
+        cap_nnz = int(getattr(res, "nnz_local", res.nnz) * 1.05) + 1024      # N > 1: every rank keeps and copies its own row block
         out_indices = torch.empty(cap_nnz, dtype=torch.int64, pin_memory=True)
         out_data = torch.empty(cap_nnz, dtype=torch.int32, pin_memory=True)
         outs = (out_indptr.numpy(), out_indices.numpy(), out_data.numpy())
+        out_indptr_global = torch.empty(nb + 1, dtype=torch.int64, pin_memory=True)
+        e2e_trace = []
 
         def step_e2e():
             if world == 1:
@@ -517,9 +519,14 @@ def main():
                 return r
             with torch.cuda.stream(stream):
                 shard = multi.CudaShard(ctx, torch, device, text_host=(host_text.data_ptr(), nbytes), nbytes=nbytes)
-                r = multi.step(shard, torch, dist, device)
+                e2e_trace.clear()
+                r = multi.step(shard, torch, dist, device, trace=e2e_trace)
+            # every rank copies ITS row block (CSC over the global columns) and its peaks to pinned host memory over its own
+            # PCIe link; the all-reduced indptr of the whole matrix goes with rank 0's
+            ctx.get_matrix_cols(r.n_barcodes, r.nnz_local, out=outs)
             if rank == 0:
-                ctx.get_matrix_cols(r.n_barcodes, r.nnz, out=outs)       # merged matrix -> pinned host memory
+                out_indptr_global.copy_(r.indptr_global)
+            e2e_trace.append(("d2h_block", 0.0))
             return r
 
         for _ in range(min(args.warmup, 2)):
@@ -536,13 +543,19 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        d2h = 12 * int(r.n_peaks) + 8 * (int(r.n_barcodes) + 1) + 12 * int(r.nnz)
+        d2h = 12 * int(r.n_peaks) + 8 * (int(r.n_barcodes) + 1) * (world + 1 if world > 1 else 1) + 12 * int(r.nnz)
+        e2e_traces = None
+        if world > 1:
+            e2e_traces = [None] * world
+            dist.all_gather_object(e2e_traces, {"rank": rank, "phases_last_step_ms": [(k, round(v, 2)) for k, v in e2e_trace]})
         nbytes_all = torch.tensor([nbytes], dtype=torch.int64, device=device)
         if world > 1:
             dist.all_reduce(nbytes_all)
         h2d_total = int(nbytes_all.item())
         e2e = {"value": total_frags / (ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms / args.steps}
+               "ms_per_step": ms / args.steps, "phases_by_rank": e2e_traces,
+               "ends_with": "peaks + CSC in pinned host memory" if world == 1 else
+                            "every rank's peaks + CSC row block (global columns) in its own pinned host memory, global indptr on rank 0"}
 
     if rank != 0:
         if world > 1:

@@ -90,6 +90,10 @@ SIGNATURES = {
     "cratac_barcode_table_device": (c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_i64)]),
     "cratac_set_column_map": (c_int, [c_vp, c_i64, c_vp]),
     "cratac_set_row_offset": (c_int, [c_vp, c_i64, c_i64]),
+    "cratac_union_columns": (c_int, [c_vp, c_int, c_i64, c_vp, P(c_i64), P(c_i64), ctypes.c_uint64, P(c_i64)]),
+    "cratac_column_keys_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
+    "cratac_peak_matrix_begin": (c_int, [c_vp]),
+    "cratac_peak_matrix_finish": (c_int, [c_vp, P(c_i64)]),
     "cratac_merge_rank_csc": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "cratac_py2_set_order_hashes": (c_int, [c_i64, c_vp, c_vp]),
     "cratac_py2_set_order_hashes_device": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_uint64]),
@@ -177,9 +181,10 @@ class Context(object):
 
     def decode_profile(self):
         """SM cycles per phase of the single-pass decoder's tile loop (option decode_profile = 1) -> dict."""
-        out = (c_i64 * 9)()
-        check(self._lib.cratac_decode_profile(self._h, out, 9))
-        names = ["wait_tile", "separator_masks", "separator_list", "structure_check", "look_back", "field_parse", "commit", "tiles"]
+        out = (c_i64 * 10)()
+        check(self._lib.cratac_decode_profile(self._h, out, 10))
+        names = ["wait_tile", "separator_masks", "separator_list", "structure_check", "look_back", "field_parse", "commit", "tiles",
+                 "look_back_rounds", "look_back_retries"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def synchronize(self):
@@ -420,6 +425,30 @@ class Context(object):
 
     def set_row_offset(self, row_base, total_rows):
         check(self._lib.cratac_set_row_offset(self._h, int(row_base), int(total_rows)))
+
+    def union_columns(self, world, max_b, d_gathered, n_fragments, n_barcodes, stream=0):
+        """Global columns from the all-gathered barcode tables of all shards -> n_cols (sets the column map)."""
+        nf = (c_i64 * world)(*[int(x) for x in n_fragments])
+        nb = (c_i64 * world)(*[int(x) for x in n_barcodes])
+        n = c_i64()
+        check(self._lib.cratac_union_columns(self._h, int(world), int(max_b), c_vp(int(d_gathered)), nf, nb, int(stream), ctypes.byref(n)))
+        return n.value
+
+    def column_keys_device(self):
+        p, n = c_vp(), c_i64()
+        check(self._lib.cratac_column_keys_device(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def peak_matrix_begin(self):
+        check(self._lib.cratac_peak_matrix_begin(self._h))
+
+    def peak_matrix_finish(self):
+        """-> (nnz, d_indptr, d_indices, d_data) of the CSC left on the device."""
+        nnz = c_i64()
+        check(self._lib.cratac_peak_matrix_finish(self._h, ctypes.byref(nnz)))
+        a, b, c = c_vp(), c_vp(), c_vp()
+        check(self._lib.cratac_matrix_device(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return nnz.value, a.value, b.value, c.value
 
     def peak_matrix_device(self):
         """Build the CSC on the device only -> (nnz, d_indptr, d_indices, d_data)."""

@@ -7,10 +7,14 @@ matrix rows of different ranks never interleave.  Exchanges, all small except th
   1. window-count histogram: all-reduce(max) of the largest count, all-reduce(sum) of the bins  -- replaces the
      `Counter +=` of count_cut_sites/__init__.py:77-81; the mixture fit then runs redundantly on every rank.
   2. peak counts and fragment counts: all-gather -> matrix row base and global line base of every rank.
-  3. barcode dictionary: all-gather of (64-bit key, first global line, CPython-2.7 hash); union -> the global
-     column order of generate_peak_matrix/__init__.py:44 and each rank's column -> local barcode map.
-  4. CSC column blocks: gathered to rank 0 and interleaved per column (rank order keeps rows ascending) --
-     replaces the hstack of generate_peak_matrix/__init__.py:62-72.
+  3. barcode dictionary: one all-gather of (64-bit key, first line in the shard, CPython-2.7 hash); the union, the
+     insertion order and the set order are computed by the library on every rank (cratac_union_columns,
+     csrc/multi.cu) -> the global column order of generate_peak_matrix/__init__.py:44 and each rank's column ->
+     local barcode map.
+  4. per-column entry counts: all-reduce(sum) -> the indptr of the whole matrix.  The CSC row blocks themselves stay
+     on their ranks (every rank copies its own block to the host over its own PCIe link; `stack_row_blocks` is the
+     writer's interleave); `gather=True` funnels them to rank 0 and interleaves them on the device instead -- the
+     hstack of generate_peak_matrix/__init__.py:62-72.
 
 `step()` is written against a small backend interface so that the exchange logic runs unchanged on CPU tensors
 with gloo (tests/test_multi_cpu.py, where the per-shard compute is played by the oracle) and on the GPU with the
@@ -59,32 +63,6 @@ def rank_text(fragments_path, contigs, rank, world, index=None, threads=None):
     return _ffi.inflate_contigs(fragments_path, [c[0] for c in contigs[first:last]], index=index, threads=threads), (first, last)
 
 
-# --------------------------------------------------------------------------------------------- barcode union
-def global_columns(torch, keys_all, first_all, hash_all, valid_all, py2_order_fn, order="py2set"):
-    """keys/first/hash: int64 tensors [world, maxB] (padded), valid_all: bool [world, maxB].
-    -> (n_cols, col_of[world, maxB] int64 with -1 on padding, uniq_keys in column order)."""
-    flat_valid = valid_all.reshape(-1)
-    keys = keys_all.reshape(-1)[flat_valid]
-    first = first_all.reshape(-1)[flat_valid]
-    hsh = hash_all.reshape(-1)[flat_valid]
-    uniq, inv = torch.unique(keys, return_inverse=True)
-    n = uniq.numel()
-    first_min = torch.full((n,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=keys.device)
-    first_min = first_min.scatter_reduce(0, inv, first, reduce="amin", include_self=True)
-    hash_u = torch.zeros(n, dtype=torch.int64, device=keys.device).scatter(0, inv, hsh)
-    by_first = torch.argsort(first_min)                      # insertion order of the reference's set
-    if order == "py2set":
-        perm = py2_order_fn(hash_u[by_first].contiguous())   # slot order of the CPython-2.7 set (tensor in, tensor out)
-        col_to_uniq = by_first[perm.to(torch.int64)]
-    else:
-        col_to_uniq = by_first
-    col_of_uniq = torch.empty(n, dtype=torch.int64, device=keys.device)
-    col_of_uniq[col_to_uniq] = torch.arange(n, dtype=torch.int64, device=keys.device)
-    col_flat = torch.full(flat_valid.shape, -1, dtype=torch.int64, device=keys.device)
-    col_flat[flat_valid] = col_of_uniq[inv]
-    return n, col_flat.reshape(valid_all.shape), uniq[col_to_uniq]
-
-
 def packed_barcode_key(bc):
     """The library's 64-bit key of a 10x barcode "[ACGT]{16}-<group>": 2 bits per base (A 0, C 1, T 2, G 3; first base in
     the top bits) | group << 32.  (Other strings are keyed by a 63-bit hash on the device; not reproduced here.)"""
@@ -108,9 +86,12 @@ def _all_gather_i64(torch, dist, values, device):
     return torch.stack(out).cpu().numpy()
 
 
-def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set", trace=None):
-    """One pass of the path on this rank's shard + the cross-rank exchanges.  `shard` implements the backend
-    interface (see CudaShard).  Returns a StepResult; the merged matrix lives on rank 0 (shard.merged)."""
+def step(shard, torch, dist, device, odds_ratio=0.2, trace=None, gather=False):
+    """One pass of the path on this rank's shard + the cross-rank exchanges.  `shard` implements the backend interface
+    (see CudaShard).  Every rank keeps its own CSC row block (global columns, global row numbers; rank order = row
+    order, so the whole matrix is the vertical stack of the blocks) together with the all-reduced per-column totals
+    (`StepResult.indptr_global`).  gather=True also funnels the blocks to rank 0 and interleaves them per column there
+    (shard.merged) -- the hstack of generate_peak_matrix/__init__.py:62-72 as ONE device array, used by the parity check."""
     import time
     t_last = [time.time()]
 
@@ -131,29 +112,23 @@ def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set", trace=None)
     dist.all_reduce(hist[: gmax + 1], op=dist.ReduceOp.SUM)  #  an 8 MB all-reduce of the whole table stalled NCCL for 50-150 ms now and then)
     shard.fit_launch(odds_ratio)
     mark("hist_fit_launch")
-    # 2. barcode dictionary, exchanged while the fit runs (side stream on a GPU: the fit occupies one SM)
+    # 2. barcode dictionary, exchanged and united while the fit runs (side stream on a GPU: the fit occupies one SM).
+    #    One all-gather of (key, first line, CPython-2.7 hash) per barcode; the union, the insertion order and the
+    #    set order are the library's (cratac_union_columns): same columns on every rank, no host-side tensor algebra.
     with shard.side_stream():
         counts = _all_gather_i64(torch, dist, [n_frag, n_bc], device)
         mark("d_gather_counts")
-        line_base = int(counts[:rank, 0].sum())
         keys, first, hsh = shard.barcode_table()             # int64 tensors [n_bc]
-        max_b = int(counts[:, 1].max())
-        pad = torch.zeros((3, max(max_b, 1)), dtype=torch.int64, device=device)
+        max_b = max(int(counts[:, 1].max()), 1)
+        pad = torch.zeros((3, max_b), dtype=torch.int64, device=device)
         pad[0, :n_bc] = keys
-        pad[1, :n_bc] = first + line_base
+        pad[1, :n_bc] = first
         pad[2, :n_bc] = hsh
-        gathered = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(gathered, pad)
-        if trace is not None: torch.cuda.current_stream().synchronize()
+        gathered = torch.empty((world, 3, max_b), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gathered.view(-1), pad.view(-1))
         mark("d_all_gather")
-        g = torch.stack(gathered)                            # [world, 3, maxB]
-        valid = torch.arange(max(max_b, 1), device=device)[None, :] < torch.as_tensor(counts[:, 1], device=device)[:, None]
-        n_cols, col_of, col_keys = global_columns(torch, g[:, 0], g[:, 1], g[:, 2], valid, shard.py2_order, order)
-        mark("d_global_columns")
-        c2d = torch.full((max(n_cols, 1),), -1, dtype=torch.int32, device=device)
-        mine = col_of[rank, :n_bc]
-        c2d[mine] = torch.arange(n_bc, dtype=torch.int32, device=device)
-    mark("dictionary")
+        n_cols = shard.union_columns(gathered, counts[:, 0], counts[:, 1], max_b)
+        mark("d_union_columns")
     # 3. threshold, peaks, row bases
     threshold, params = shard.fit_result()
     mark("fit_wait")
@@ -163,44 +138,70 @@ def step(shard, torch, dist, device, odds_ratio=0.2, order="py2set", trace=None)
     row_base = int(pk[:rank].sum())
     total_rows = int(pk.sum())
     shard.set_row_offset(row_base, total_rows)
-    shard.set_column_map(n_cols, c2d)
-    # 4. local CSC over the global columns, gathered to rank 0
-    mark("row_col_maps")
+    mark("row_bases")
+    # 4. local CSC over the global columns; per-column totals combined with one all-reduce (the file's indptr)
     indptr, indices, data = shard.peak_matrix(n_cols)        # tensors (views) on `device`
     mark("peak_matrix")
     nnz = int(indices.numel())
+    per_col = (indptr[1:] - indptr[:-1]).contiguous()
+    dist.all_reduce(per_col, op=dist.ReduceOp.SUM)
+    indptr_global = torch.zeros(n_cols + 1, dtype=torch.int64, device=device)
+    torch.cumsum(per_col, 0, out=indptr_global[1:])
     nnz_all = _all_gather_i64(torch, dist, [nnz], device)[:, 0]
     total_nnz = int(nnz_all.sum())
-    if rank == 0:
-        indptr_all = torch.empty(world * (n_cols + 1), dtype=torch.int64, device=device)
-        indices_all = torch.empty(max(total_nnz, 1), dtype=torch.int64, device=device)
-        data_all = torch.empty(max(total_nnz, 1), dtype=torch.int32, device=device)
-        offs = np.concatenate(([0], np.cumsum(nnz_all)))
-        indptr_all[: n_cols + 1] = indptr
-        indices_all[: nnz] = indices
-        data_all[: nnz] = data
-        ops = []
-        for r in range(1, world):                             # all receives posted at once: the transfers of the
-            ops.append(dist.P2POp(dist.irecv, indptr_all[r * (n_cols + 1):(r + 1) * (n_cols + 1)], r))   # ranks overlap
-            if nnz_all[r] > 0:
-                ops.append(dist.P2POp(dist.irecv, indices_all[offs[r]:offs[r + 1]], r))
-                ops.append(dist.P2POp(dist.irecv, data_all[offs[r]:offs[r + 1]], r))
-        for w in (dist.batch_isend_irecv(ops) if ops else []):
-            w.wait()
-        rank_off = torch.as_tensor(offs[:-1].astype(np.int64), device=device)
-        shard.merge(world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz)
-    else:
-        ops = [dist.P2POp(dist.isend, indptr.contiguous(), 0)]
-        if nnz > 0:
-            ops.append(dist.P2POp(dist.isend, indices.contiguous(), 0))
-            ops.append(dist.P2POp(dist.isend, data.contiguous(), 0))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    mark("gather_merge")
+    mark("column_totals")
+    if gather:
+        if rank == 0:
+            indptr_all = torch.empty(world * (n_cols + 1), dtype=torch.int64, device=device)
+            indices_all = torch.empty(max(total_nnz, 1), dtype=torch.int64, device=device)
+            data_all = torch.empty(max(total_nnz, 1), dtype=torch.int32, device=device)
+            offs = np.concatenate(([0], np.cumsum(nnz_all)))
+            indptr_all[: n_cols + 1] = indptr
+            indices_all[: nnz] = indices
+            data_all[: nnz] = data
+            ops = []
+            for r in range(1, world):                             # all receives posted at once: the transfers of the
+                ops.append(dist.P2POp(dist.irecv, indptr_all[r * (n_cols + 1):(r + 1) * (n_cols + 1)], r))   # ranks overlap
+                if nnz_all[r] > 0:
+                    ops.append(dist.P2POp(dist.irecv, indices_all[offs[r]:offs[r + 1]], r))
+                    ops.append(dist.P2POp(dist.irecv, data_all[offs[r]:offs[r + 1]], r))
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            rank_off = torch.as_tensor(offs[:-1].astype(np.int64), device=device)
+            shard.merge(world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz)
+        else:
+            ops = [dist.P2POp(dist.isend, indptr.contiguous(), 0)]
+            if nnz > 0:
+                ops.append(dist.P2POp(dist.isend, indices.contiguous(), 0))
+                ops.append(dist.P2POp(dist.isend, data.contiguous(), 0))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        mark("gather_merge")
     return StepResult(n_fragments=int(counts[:, 0].sum()), n_fragments_local=n_frag, n_barcodes=n_cols, threshold=threshold,
                       params=params, n_peaks=total_rows, n_peaks_local=n_peaks, row_base=row_base, nnz=total_nnz, nnz_local=nnz,
-                      col_keys=col_keys, em_iterations=getattr(shard, "em_iterations", 0),
+                      indptr_global=indptr_global, col_keys=shard.col_keys(n_cols), em_iterations=getattr(shard, "em_iterations", 0),
                       em_inner_iterations=getattr(shard, "em_inner_iterations", 0), n_hits=getattr(shard, "n_hits", 0))
+
+
+def stack_row_blocks(n_cols, blocks):
+    """The whole CSC from the ranks' row blocks [(indptr, indices, data), ...] in rank order (numpy, host): column j of
+    the result is column j of block 0, then of block 1, ... -- rows of different ranks never interleave, so the row
+    indices stay ascending.  What a writer does with the blocks every rank copied to the host over its own PCIe link."""
+    counts = sum(np.diff(b[0]) for b in blocks)
+    indptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+    indices = np.empty(int(indptr[-1]), dtype=np.int64)
+    data = np.empty(int(indptr[-1]), dtype=np.int32)
+    fill = indptr[:-1].copy()
+    for ip, ix, dt in blocks:
+        lens = np.diff(ip)
+        if ix.size == 0:
+            continue
+        # destination of every entry of this block: its column's running offset + position inside the column
+        dst = np.repeat(fill - ip[:-1], lens) + np.arange(ix.size, dtype=np.int64)
+        indices[dst] = ix
+        data[dst] = dt
+        fill += lens
+    return indptr, indices, data
 
 
 # --------------------------------------------------------------------------------------------- CUDA backend
@@ -276,29 +277,29 @@ class CudaShard(object):
     def barcode_table(self):
         k, f, h, n = self.ctx.barcode_table_device()
         t = self.torch
-        return (dev_tensor(t, k, n, "<i8", self.device).clone(), dev_tensor(t, f, n, "<i8", self.device).clone(),
-                dev_tensor(t, h, n, "<i8", self.device).clone())
+        return dev_tensor(t, k, n, "<i8", self.device), dev_tensor(t, f, n, "<i8", self.device), dev_tensor(t, h, n, "<i8", self.device)
 
-    def py2_order(self, hashes):
-        t = self.torch
-        out = t.empty(hashes.numel(), dtype=t.int32, device=self.device)
-        cur = t.cuda.current_stream(self.device)             # the side stream of step(): the fit has the context's own
-        cur.synchronize()                                    # `hashes` is complete before the library reads it
-        self.ctx.py2_set_order_hashes_device(hashes.numel(), hashes.data_ptr(), out.data_ptr(), stream=cur.cuda_stream)
-        return out
+    def union_columns(self, gathered, n_fragments, n_barcodes, max_b):
+        cur = self.torch.cuda.current_stream(self.device)    # the side stream of step(): the fit has the context's own
+        self._gathered = gathered                            # kept alive until the library has read it
+        return self.ctx.union_columns(len(n_fragments), max_b, gathered.data_ptr(), n_fragments, n_barcodes, stream=cur.cuda_stream)
 
-    def set_column_map(self, n_cols, c2d):
-        if self._side is not None:
-            self._side.synchronize()                          # c2d was computed there
-        self.torch.cuda.current_stream(self.device).synchronize()
-        self.ctx.set_column_map(n_cols, c2d.data_ptr())
+    def col_keys(self, n_cols):
+        p, n = self.ctx.column_keys_device()
+        return dev_tensor(self.torch, p, n, "<i8", self.device)
 
     def peak_matrix(self, n_cols):
-        nnz, ip, ix, dt = self.ctx.peak_matrix_device()
+        self.ctx.peak_matrix_begin()
+        nnz, ip, ix, dt = self.ctx.peak_matrix_finish()
         t = self.torch
         data = dev_tensor(t, dt, nnz, "<i4", self.device)
         self.n_hits = int(data.sum(dtype=t.int64).item()) if nnz else 0
-        return dev_tensor(t, ip, n_cols + 1, "<i8", self.device), dev_tensor(t, ix, nnz, "<i8", self.device), data
+        self._held = (dev_tensor(t, ip, n_cols + 1, "<i8", self.device), dev_tensor(t, ix, nnz, "<i8", self.device), data)
+        return self._held
+
+    def held_matrix(self):
+        """This rank's CSC row block (device tensors; overwritten on rank 0 by a gather=True step)."""
+        return self._held
 
     def merge(self, world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz):
         self.torch.cuda.current_stream(self.device).synchronize()

@@ -165,10 +165,15 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_em_params, &c->d_em_work, &c->d_chain, &c->d_tile_summary, &c->d_run_start, &c->d_run_end, &c->d_bridge, &c->d_fill,
                       &c->d_peak_chrom, &c->d_peak_start, &c->d_peak_end, &c->d_peak_row, &c->d_peak_off, &c->d_bc_hits, &c->d_seg_off,
                       &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
-                      &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc};
+                      &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc,
+                      &c->d_union, &c->d_col_keys, &c->d_sp_state, &c->d_sp_scalars, &c->d_sp_irr,
+                      &c->d_bg_W, &c->d_bg_tiles, &c->d_bg_start, &c->d_bg_end, &c->d_bg_count};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_sp_scalars) cudaFreeHost(c->h_sp_scalars);
+    if (c->h_union_hash) cudaFreeHost(c->h_union_hash);
+    if (c->h_union_perm) cudaFreeHost(c->h_union_perm);
+    if (c->union_event) cudaEventDestroy(c->union_event);
     if (c->h_bc_hash) cudaFreeHost(c->h_bc_hash);
     if (c->h_bc_order) cudaFreeHost(c->h_bc_order);
     if (c->h_c2d_pin) cudaFreeHost(c->h_c2d_pin);
@@ -217,7 +222,7 @@ int cratac_decode_profile(cratac_ctx* h, int64_t* cycles_out, int n) {
     for (int i = 0; i < n; i++) cycles_out[i] = 0;
     if (!c->d_sp_scalars.p) return CRATAC_OK;
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
-    CRATAC_CUDA(cudaMemcpy(cycles_out, c->d_sp_scalars.as<int64_t>() + 8, sizeof(int64_t) * (size_t)std::min(n, 9), cudaMemcpyDeviceToHost));
+    CRATAC_CUDA(cudaMemcpy(cycles_out, c->d_sp_scalars.as<int64_t>() + 8, sizeof(int64_t) * (size_t)std::min(n, 10), cudaMemcpyDeviceToHost));
     return CRATAC_OK;
 }
 
@@ -415,22 +420,37 @@ int cratac_window_counts(cratac_ctx* h, int contig, int32_t* W) {
 
 int cratac_bedgraph_rows(cratac_ctx* h, int contig, int64_t* start, int64_t* end, int64_t* count, int64_t cap, int64_t* n_rows) {
     Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
     if (contig < 0 || contig >= c->n_contigs) { set_error("contig index out of range"); return CRATAC_ERR_ARG; }
-    int64_t L = c->contig_lens[contig];
-    std::vector<int32_t> W((size_t)std::max<int64_t>(L, 1));
-    CRATAC_TRY(cratac_window_counts(h, contig, W.data()));
-    // run-length encode the non-zero bases; a zero never closes the open run (count_cut_sites/__init__.py:36-37)
-    int64_t n = 0, rs = 0, last = 0;
-    int32_t cur = 0;
-    for (int64_t p = 0; p < L; p++) {
-        int32_t v = W[p];
-        if (v == 0) continue;
-        if (v == cur) { last = p; continue; }
-        if (cur != 0) { if (n < cap) { start[n] = rs; end[n] = last + 1; count[n] = cur; } n++; }
-        cur = v; rs = p; last = p;
+    if (c->contig_tile_off[contig + 1] == c->contig_tile_off[contig]) { set_error("contig %d is not a primary contig", contig); return CRATAC_ERR_ARG; }
+    // rows are run-length encoded on the device (csrc/bedgraph.cu) and kept there: a first call with cap = 0 sizes the
+    // caller's arrays, the second one only copies
+    CRATAC_TRY(bedgraph_rows_device(c, contig));
+    const int64_t n = c->bg_rows;
+    if (n_rows) *n_rows = n;
+    if (n == 0 || cap < n || !start || !end || !count) return sync_status(c);
+    // 12 bytes per row cross PCIe; widened to the int64 of the interface on all host cores
+    std::vector<int32_t> tmp[3];
+    const void* src[3] = {c->d_bg_start.p, c->d_bg_end.p, c->d_bg_count.p};
+    int64_t* dst[3] = {start, end, count};
+    for (int k = 0; k < 3; k++) {
+        tmp[k].resize((size_t)n);
+        CRATAC_CUDA(cudaMemcpyAsync(tmp[k].data(), src[k], 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     }
-    if (cur != 0) { if (n < cap) { start[n] = rs; end[n] = last + 1; count[n] = cur; } n++; }
-    *n_rows = n;
+    CRATAC_TRY(sync_status(c));
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)std::thread::hardware_concurrency(), n / (1 << 16) + 1));
+    std::vector<std::thread> pool;
+    auto widen = [&](int t) {
+        const int64_t i0 = n * t / n_thr, i1 = n * (t + 1) / n_thr;
+        for (int k = 0; k < 3; k++) {
+            const int32_t* sp = tmp[k].data();
+            int64_t* dp = dst[k];
+            for (int64_t i = i0; i < i1; i++) dp[i] = sp[i];
+        }
+    };
+    for (int t = 1; t < n_thr; t++) pool.emplace_back(widen, t);
+    widen(0);
+    for (auto& t : pool) t.join();
     return CRATAC_OK;
 }
 
@@ -591,6 +611,38 @@ int cratac_peak_matrix(cratac_ctx* h, int64_t* nnz) {
     CRATAC_TRY(sync_status(c));
     if (c->peaks_on_device_count) { c->n_peaks = c->h_status[ST_N_PEAKS]; c->peaks_on_device_count = false; }
     if (nnz) *nnz = c->nnz;
+    return CRATAC_OK;
+}
+
+int cratac_peak_matrix_begin(cratac_ctx* h) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return peak_matrix_hits(c);
+}
+
+int cratac_peak_matrix_finish(cratac_ctx* h, int64_t* nnz) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    CRATAC_TRY(peak_matrix_csc(c));
+    CRATAC_TRY(sync_status(c));
+    if (c->peaks_on_device_count) { c->n_peaks = c->h_status[ST_N_PEAKS]; c->peaks_on_device_count = false; }
+    if (nnz) *nnz = c->nnz;
+    return CRATAC_OK;
+}
+
+int cratac_union_columns(cratac_ctx* h, int world, int64_t max_barcodes, const int64_t* d_gathered, const int64_t* n_fragments, const int64_t* n_barcodes,
+                         uint64_t stream, int64_t* n_cols) {
+    if (!h || world < 1 || max_barcodes < 0 || !n_fragments || !n_barcodes || !n_cols) { set_error("cratac_union_columns: bad argument"); return CRATAC_ERR_ARG; }
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return union_columns(c, world, max_barcodes, d_gathered, n_fragments, n_barcodes, stream ? (cudaStream_t)(uintptr_t)stream : c->stream, n_cols);
+}
+
+int cratac_column_keys_device(cratac_ctx* h, const int64_t** d_keys, int64_t* n_cols) {
+    Ctx* c = &h->c;
+    if (!c->global_cols) { set_error("cratac_column_keys_device: no global column map"); return CRATAC_ERR_ARG; }
+    if (d_keys) *d_keys = c->d_col_keys.as<int64_t>();
+    if (n_cols) *n_cols = c->n_global_cols;
     return CRATAC_OK;
 }
 

@@ -156,6 +156,15 @@ struct Ctx {
     int64_t n_global_cols = 0;
     int64_t row_range = 0;                 // rows of the global matrix (0 = the local peak count)
     DevBuf d_global_c2d, d_nnz_ordered, d_dense_bckey;
+    DevBuf d_bg_W, d_bg_tiles, d_bg_start, d_bg_end, d_bg_count;   // bedgraph rows of one contig (bedgraph.cu)
+    int64_t bg_rows = 0;
+    int bg_contig = -1;
+    bool bg_valid = false;                 // d_bg_* hold the rows of bg_contig for the current fragments
+    DevBuf d_union, d_col_keys;            // scratch of union_columns (multi.cu); 64-bit barcode keys in global column order
+    long long* h_union_hash = nullptr;     // pinned mirrors for the host simulation of the set order
+    int32_t* h_union_perm = nullptr;
+    size_t h_union_cap = 0;
+    cudaEvent_t union_event = nullptr;
     // misc
     DevBuf d_status;                       // int64[ST_SLOTS]
     DevBuf d_scan_tmp;
@@ -224,6 +233,11 @@ int window_histogram(Ctx* c);                                         // pileup.
 int call_peaks_device(Ctx* c);                                        // pileup.cu: K5 (threshold from d_status)
 int fit_threshold_device(Ctx* c, double odds_ratio);                  // em.cu: K4 on compact histogram
 int peak_matrix_device(Ctx* c);                                       // matrix.cu: K6-K8
+int peak_matrix_hits(Ctx* c);                                         // matrix.cu: K6 + K7 (no columns needed)
+int peak_matrix_csc(Ctx* c);                                          // matrix.cu: K8
+int bedgraph_rows_device(Ctx* c, int contig);                         // bedgraph.cu: K5b
+int union_columns(Ctx* c, int world, int64_t max_b, const int64_t* d_gathered, const int64_t* h_nfrag, const int64_t* h_nbc, cudaStream_t s,
+                  int64_t* n_cols_out);                               // multi.cu
 int sync_status(Ctx* c);                                              // api.cu: D2H of status words + error check
 
 }  // namespace cratac

@@ -434,7 +434,7 @@ __device__ __forceinline__ void sp_st_state(unsigned long long* p, unsigned long
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // per-phase cycle counters (thread 0 / the look-back warp's lane 0), only when StreamArgs::prof is set (tools/decode_bench.py)
-enum { SPP_WAIT = 0, SPP_CLASSIFY, SPP_LIST, SPP_VERIFY, SPP_LOOKBACK, SPP_PARSE, SPP_COMMIT, SPP_TILES, SPP_COUNT };
+enum { SPP_WAIT = 0, SPP_CLASSIFY, SPP_LIST, SPP_VERIFY, SPP_LOOKBACK, SPP_PARSE, SPP_COMMIT, SPP_TILES, SPP_ROUNDS, SPP_RETRIES, SPP_COUNT };
 #define SP_PROF(slot)                                                                                 \
     do {                                                                                              \
         if (PROF && tid == 0) { const long long _t = clock64(); atomicAdd(&a.prof[slot], (unsigned long long)(_t - prof_t)); prof_t = _t; } \
@@ -712,9 +712,11 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                         const int64_t idx = top - j;
                         int spins = 0;
                         while ((v[j] >> 62) == 0 && ++spins < (1 << 22)) { __nanosleep(200); v[j] = sp_ld_state(&a.state[idx]); }
+                        if (PROF && spins) atomicAdd(&a.prof[SPP_RETRIES], (unsigned long long)spins);
                         if ((v[j] >> 62) == 0) lane_stuck = true;
                         if (!lane_inc) { lane_sum += (long long)(v[j] & SP_VALUE_MASK); lane_inc = (v[j] >> 62) == 2; }
                     }
+                    if (PROF && lane == 0) atomicAdd(&a.prof[SPP_ROUNDS], 1ULL);
                     const unsigned has_inc = __ballot_sync(0xffffffffu, lane_inc);
                     const unsigned stuck = __ballot_sync(0xffffffffu, lane_stuck);
                     if (stuck) { if (lane == 0) raise_error(d.status, CRATAC_ERR_INTERNAL, -200 - gt); excl = -1; break; }
@@ -757,7 +759,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             if (s_excl < 0) return;
             cur ^= 1;
             if ((a.mode & 1) && tid == 0) {
-                const int64_t tn = (int64_t)atomicAdd(a.ticket, 1ULL);
+                const int64_t tn = next_tile(t);
                 s_tile[cur] = tn;
                 if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur);
             }
@@ -872,7 +874,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         if (n_lines == 0) { __syncthreads(); if (s_excl < 0) return; }
         cur ^= 1;
         if ((a.mode & 1) && tid == 0) {                              // ticket taken when the tile starts: tiles start in index order
-            const int64_t tn = next_tile(-2);
+            const int64_t tn = next_tile(t);
             s_tile[cur] = tn;
             if (tn < a.n_tiles && tile_is_tma(tn)) issue(tn, cur);
         }
@@ -1571,6 +1573,7 @@ int finalize_fragments(Ctx* c) {
     int64_t n = c->n_fragments;
     c->tile_desc_valid = false;
     c->tile_bound_valid = false;
+    c->bg_valid = false;
     int64_t* st = c->d_status.as<int64_t>();
     int nc = c->n_contigs;
     CRATAC_TRY(c->d_contig_frag_off.reserve(sizeof(int64_t) * (nc + 2)));

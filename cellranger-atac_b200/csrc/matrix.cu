@@ -498,7 +498,8 @@ int merge_rank_csc(Ctx* c, int world, int64_t n_cols, const int64_t* d_indptr_al
     return CRATAC_OK;
 }
 
-int peak_matrix_device(Ctx* c) {
+// K6 + K7: hit records and their per-barcode reduction.  Needs the peaks (and their row offset) but not the matrix columns.
+int peak_matrix_hits(Ctx* c) {
     cudaStream_t s = c->stream;
     int64_t* st = c->d_status.as<int64_t>();
     const int64_t n = c->n_fragments, nb = c->n_barcodes;
@@ -545,11 +546,7 @@ int peak_matrix_device(Ctx* c) {
     c->stage_end(SG_OVERLAP_SCATTER);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
-    // matrix column order: host work (CPython-2.7 set emulation over the barcode hashes) overlaps the kernels
-    // queued so far (pileup, fit, peaks, overlap)
     c->host_mark("matrix_launch");
-    if (!c->global_cols) CRATAC_TRY(build_barcodes(c));
-    c->host_mark("build_barcodes");
     int32_t* nnz_col = c->d_nnz_col.as<int32_t>();
     if (nb > 0) {
         static bool configured = false;
@@ -571,7 +568,20 @@ int peak_matrix_device(Ctx* c) {
         c->launches += 3;
         CRATAC_CUDA(cudaGetLastError());
     }
-    // columns: the shard's own barcodes in matrix order, or the global column map of a multi-GPU run
+    return CRATAC_OK;
+}
+
+// K8: CSC in column order.  The columns are the shard's own barcodes in matrix order, or the global column map of a
+// multi-GPU run (cratac_union_columns / cratac_set_column_map).
+int peak_matrix_csc(Ctx* c) {
+    cudaStream_t s = c->stream;
+    int64_t* st = c->d_status.as<int64_t>();
+    const int64_t nb = c->n_barcodes;
+    int32_t* nnz_col = c->d_nnz_col.as<int32_t>();
+    // matrix column order: host work (CPython-2.7 set emulation over the barcode hashes) overlaps the kernels
+    // queued so far (pileup, fit, peaks, overlap, reduce)
+    if (!c->global_cols) CRATAC_TRY(build_barcodes(c));
+    c->host_mark("build_barcodes");
     const int32_t* c2d = c->global_cols ? c->d_global_c2d.as<int32_t>() : c->d_col_to_dense.as<int32_t>();
     const int64_t n_cols = c->global_cols ? c->n_global_cols : nb;
     c->n_cols = n_cols;
@@ -594,7 +604,7 @@ int peak_matrix_device(Ctx* c) {
     if (n_cols > 0) {
         c->stage_begin(SG_CSC_BUILD);
         if (c->nnz > 0)
-            k_csc_copy<<<(unsigned)((c->nnz + CSC_CHUNK - 1) / CSC_CHUNK), 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), a.seg_off, c2d,
+            k_csc_copy<<<(unsigned)((c->nnz + CSC_CHUNK - 1) / CSC_CHUNK), 256, 0, s>>>(c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), c->d_seg_off.as<int64_t>(), c2d,
                                                                                        c->d_indptr.as<int64_t>(), n_cols, c->nnz, c->d_indices.as<int64_t>(),
                                                                                        c->d_data.as<int32_t>());
         c->stage_end(SG_CSC_BUILD);
@@ -602,6 +612,11 @@ int peak_matrix_device(Ctx* c) {
         CRATAC_CUDA(cudaGetLastError());
     }
     return CRATAC_OK;
+}
+
+int peak_matrix_device(Ctx* c) {
+    CRATAC_TRY(peak_matrix_hits(c));
+    return peak_matrix_csc(c);
 }
 
 // ---- FILTER_PEAK_MATRIX: m[:, cols] (+ drop the columns left without a positive entry) -----------------------------

@@ -72,8 +72,8 @@ int64_t cratac_launch_count(cratac_ctx* ctx, int reset);
  * 0 on a clean fragments.tsv (tools/io.py:75-92 shaped lines of at most 64 bytes) */
 int64_t cratac_decode_declined(cratac_ctx* ctx, int reset);
 /* option "decode_profile" = 1: k_parse_stream adds up SM cycles per phase of its tile loop (one thread's clock per CTA);
- * this reads the first n (<= 9) counters of the last decode: wait for the tile, separator masks, separator list, structure
- * check, look-back, field parse, commit, tiles.  Diagnostics only (tools/decode_bench.py). */
+ * this reads the first n (<= 10) counters of the last decode: wait for the tile, separator masks, separator list, structure
+ * check, look-back, field parse, commit, tiles, look-back rounds, look-back poll retries.  Diagnostics only (tools/decode_bench.py). */
 int cratac_decode_profile(cratac_ctx* ctx, int64_t* cycles_out, int n);
 int cratac_synchronize(cratac_ctx* ctx);
 /* the CUDA stream every kernel of this context is launched on (cudaStream_t as an integer) */
@@ -195,6 +195,23 @@ int cratac_compact_histogram(cratac_ctx* ctx);
 int cratac_barcode_table_device(cratac_ctx* ctx, const uint64_t** d_keys, const uint64_t** d_first, const int64_t** d_py2hash, int64_t* n);
 int cratac_set_column_map(cratac_ctx* ctx, int64_t n_cols, const int32_t* d_col_to_dense);   /* n_cols < 0 resets */
 int cratac_set_row_offset(cratac_ctx* ctx, int64_t row_base, int64_t total_rows);
+/* The barcode universe of all shards -> global matrix columns, on the device (csrc/multi.cu): replaces the `set` of
+ * generate_peak_matrix/__init__.py:44, which the reference fills by reading the whole fragments file.  d_gathered is the
+ * all-gather of every rank's cratac_barcode_table_device triple, laid out [world][3][max_barcodes] (keys, shard-local first
+ * lines, CPython-2.7 hashes; rows padded to max_barcodes); n_fragments / n_barcodes are host arrays [world].  Every rank
+ * computes the same columns (hash-table union with atomicMin on the first global line, insertion rank by bitmap +
+ * popcount, CPython-2.7 set order or first-seen order per option "barcode_order"); the context's column map is set as by
+ * cratac_set_column_map.  `stream` (0: the context's own) is where the work is queued: a side stream lets it run under the
+ * mixture fit; the context's stream is ordered behind it. */
+int cratac_union_columns(cratac_ctx* ctx, int world, int64_t max_barcodes, const int64_t* d_gathered, const int64_t* n_fragments,
+                         const int64_t* n_barcodes, uint64_t stream, int64_t* n_cols);
+/* 64-bit barcode keys of the global columns, in column order (device pointer, valid until the next union) */
+int cratac_column_keys_device(cratac_ctx* ctx, const int64_t** d_keys, int64_t* n_cols);
+/* cratac_peak_matrix in two halves: `begin` queues overlap + per-barcode reduction (generate_peak_matrix/__init__.py:107-119:
+ * needs the peaks, not the columns), `finish` builds the CSC in column order (:62-72) -- so a column order that is still
+ * being worked out (cratac_union_columns on a side stream, the host's set simulation) costs no GPU idle time */
+int cratac_peak_matrix_begin(cratac_ctx* ctx);
+int cratac_peak_matrix_finish(cratac_ctx* ctx, int64_t* nnz);
 int cratac_merge_rank_csc(cratac_ctx* ctx, int world, int64_t n_cols, const int64_t* d_indptr_all, const int64_t* d_rank_off,
                           const int64_t* d_indices_all, const int32_t* d_data_all, int64_t total_nnz);
 int cratac_py2_set_order_hashes(int64_t n, const int64_t* hashes, int32_t* order_out);

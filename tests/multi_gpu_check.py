@@ -17,14 +17,6 @@ sys.path.insert(0, os.path.join(ROOT, "cellranger-atac_b200"))
 from cratac import _ffi, multi, synth  # noqa: E402
 
 
-def packed_key(bc):
-    seq, grp = bc.split("-")
-    v = 0
-    for ch in seq:
-        v = (v << 2) | ((ord(ch) >> 1) & 3)
-    return (int(grp) << 32) | v
-
-
 def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,21 +35,30 @@ def main():
     ctx = _ffi.Context(contigs, primary=[c[0] for c in contigs[a:b]], device=local)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
     with torch.cuda.stream(stream):
+        # every rank keeps its row block ...
         shard = multi.CudaShard(ctx, torch, device, text_host=text, nbytes=len(text))
-        res = multi.step(shard, torch, dist, device)
+        res0 = multi.step(shard, torch, dist, device)
+        block = ctx.get_matrix_cols(res0.n_barcodes, res0.nnz_local)
+        indptr_global = res0.indptr_global.cpu().numpy()
+        # ... or the blocks are funnelled to rank 0 and interleaved on the device
+        shard = multi.CudaShard(ctx, torch, device, text_host=text, nbytes=len(text))
+        res = multi.step(shard, torch, dist, device, gather=True)
     peaks_local = np.stack(shard.peaks, axis=1) if res.n_peaks_local else np.zeros((0, 3), np.int32)
     gathered = [None] * world
     dist.all_gather_object(gathered, peaks_local)
+    blocks = [None] * world
+    dist.all_gather_object(blocks, block)
     ok = True
     if rank == 0:
         indptr, indices, data = ctx.get_matrix_cols(res.n_barcodes, res.nnz)
+        sip, six, sdt = multi.stack_row_blocks(res.n_barcodes, blocks)
         peaks = np.concatenate(gathered)
         ref = _ffi.Context(contigs, device=local)
         full = synth.to_text(frags)
         r1 = ref.run(text=full)
         c, s, e = ref.get_peaks(r1.n_peaks)
         rip, rix, rdt = ref.get_matrix(r1.nnz)
-        keys = [packed_key(x) for x in ref.get_barcodes()]
+        keys = [multi.packed_barcode_key(x) for x in ref.get_barcodes()]
         checks = {
             "threshold": res.threshold == r1.threshold,
             "n_peaks": res.n_peaks == r1.n_peaks,
@@ -66,6 +67,9 @@ def main():
             "indptr": np.array_equal(indptr, rip),
             "indices": np.array_equal(indices, rix),
             "data": np.array_equal(data, rdt),
+            "row_blocks_stacked": np.array_equal(sip, rip) and np.array_equal(six, rix) and np.array_equal(sdt, rdt),
+            "column_totals_all_reduced": np.array_equal(indptr_global, rip),
+            "same_without_funnel": (res0.threshold, res0.n_peaks, res0.nnz) == (res.threshold, res.n_peaks, res.nnz),
         }
         ok = all(checks.values())
         print("MULTI_GPU_CHECK world=%d fragments=%d peaks=%d nnz=%d %s %s" % (world, res.n_fragments, res.n_peaks, res.nnz,

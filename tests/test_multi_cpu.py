@@ -86,11 +86,30 @@ class OracleShard(object):
         hashes = np.array([py2set.py2_str_hash(b) for b in self.bc_list], dtype=np.int64)
         return torch.from_numpy(keys), torch.from_numpy(self.first.copy()), torch.from_numpy(hashes)
 
-    def py2_order(self, hashes):
-        return torch.from_numpy(_ffi.py2_set_order_hashes(hashes.numpy()).astype(np.int64))   # host-only entry point of libcratac
+    def union_columns(self, gathered, n_fragments, n_barcodes, max_b):
+        """What cratac_union_columns (csrc/multi.cu) does on the device, restated with numpy for the CPU backend: union
+        of the keys, smallest global first line per key, insertion order, CPython-2.7 set order of the hashes."""
+        g = gathered.numpy()
+        line_base = np.concatenate(([0], np.cumsum(n_fragments)[:-1]))
+        first_of, hash_of = {}, {}
+        for r in range(g.shape[0]):
+            for i in range(int(n_barcodes[r])):
+                k, f, h = int(g[r, 0, i]), int(g[r, 1, i]) + int(line_base[r]), int(g[r, 2, i])
+                first_of[k] = min(first_of.get(k, f), f)
+                hash_of[k] = h
+        by_first = sorted(first_of, key=first_of.get)
+        perm = _ffi.py2_set_order_hashes(np.array([hash_of[k] for k in by_first], dtype=np.int64))   # host-only entry point of libcratac
+        self.col_key_list = [by_first[j] for j in perm]
+        col_of = {k: j for j, k in enumerate(self.col_key_list)}
+        self.n_cols = len(self.col_key_list)
+        self.c2d = np.full(max(self.n_cols, 1), -1, dtype=np.int64)
+        my_keys = self.barcode_table()[0].numpy()
+        for d, k in enumerate(my_keys.tolist()):
+            self.c2d[col_of[k]] = d
+        return self.n_cols
 
-    def set_column_map(self, n_cols, c2d):
-        self.n_cols, self.c2d = n_cols, c2d.numpy().copy()
+    def col_keys(self, n_cols):
+        return torch.tensor(self.col_key_list, dtype=torch.int64)
 
     def peak_matrix(self, n_cols):
         d2c = np.full(len(self.bc_list), -1, dtype=np.int64)
@@ -99,6 +118,7 @@ class OracleShard(object):
                 d2c[d] = j
         indptr, indices, data = util.oracle_matrix(len(self.contigs), self.peaks, self.o["chrom"], self.o["start"], self.o["end"],
                                                    d2c[self.frag_bc].astype(np.int32), n_cols)
+        self.last_block = (indptr, indices + self.row_base, data.astype(np.int32))
         return torch.from_numpy(indptr), torch.from_numpy(indices + self.row_base), torch.from_numpy(data.astype(np.int32))
 
     def merge(self, world, n_cols, indptr_all, rank_off, indices_all, data_all, total_nnz):
@@ -135,7 +155,13 @@ def _worker(rank, world, port, out_dir):
     text = text.tobytes()
     assert text == synth.to_text(sub)
     shard = OracleShard(contigs, [c[0] for c in contigs[a:b]], text, a)
-    res = multi.step(shard, torch, dist, torch.device("cpu"))
+    # without the funnel: every rank keeps its row block; the blocks stacked on the host are the whole matrix
+    res0 = multi.step(shard, torch, dist, torch.device("cpu"))
+    block = tuple(np.asarray(x) for x in shard.last_block)
+    np.savez(os.path.join(out_dir, "block_%d.npz" % rank), indptr=block[0], indices=block[1], data=block[2],
+             indptr_global=res0.indptr_global.numpy())
+    res = multi.step(shard, torch, dist, torch.device("cpu"), gather=True)
+    assert (res.threshold, res.n_peaks, res.nnz) == (res0.threshold, res0.n_peaks, res0.nnz)
     if rank == 0:
         indptr, indices, data = shard.merged
         np.savez(os.path.join(out_dir, "merged.npz"), indptr=indptr, indices=indices, data=data, threshold=res.threshold,
@@ -176,3 +202,8 @@ def test_two_rank_step_matches_single_process_oracle(tmp_path):
     fcol = np.array([col_id[b] for b in o["barcodes"]], dtype=np.int32)
     oip, oix, od = util.oracle_matrix(len(contigs), peaks, o["chrom"], o["start"], o["end"], fcol, len(cols))
     assert np.array_equal(got["indptr"], oip) and np.array_equal(got["indices"], oix) and np.array_equal(got["data"], od)
+    # the row blocks every rank kept (gather=False), interleaved by the host helper, are the same matrix
+    blocks = [np.load(str(tmp_path / ("block_%d.npz" % r))) for r in range(world)]
+    sip, six, sdt = multi.stack_row_blocks(len(cols), [(b["indptr"], b["indices"], b["data"]) for b in blocks])
+    assert np.array_equal(sip, oip) and np.array_equal(six, oix) and np.array_equal(sdt, od)
+    assert all(np.array_equal(b["indptr_global"], oip) for b in blocks)      # all-reduced per-column totals
