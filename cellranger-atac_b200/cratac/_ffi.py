@@ -83,6 +83,8 @@ SIGNATURES = {
     "cratac_hist_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
+    "cratac_decode_file": (c_int, [c_vp, c_cp, c_int]),
+    "cratac_run_file": (c_int, [c_vp, c_cp, c_int, c_dbl, P(RunResult)]),
     "cratac_py2_set_order": (c_int, [c_i64, P(c_cp), c_vp]),
     "cratac_status_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
     "cratac_window_histogram": (c_int, [c_vp]),
@@ -224,6 +226,17 @@ class Context(object):
         addr, n, keep = _buffer(text)
         check(self._lib.cratac_decode_host(self._h, addr, n))
         return self.num_fragments()
+
+    def decode_file(self, path, threads=0):
+        """fragments.tsv.gz -> fragments in HBM: BGZF inflate on host threads, PCIe copy and parse overlapped."""
+        check(self._lib.cratac_decode_file(self._h, path.encode(), int(threads)))
+        return self.num_fragments()
+
+    def run_file(self, path, odds_ratio=0.2, threads=0):
+        """decode_file + the rest of the path -> RunResult."""
+        res = RunResult()
+        check(self._lib.cratac_run_file(self._h, path.encode(), int(threads), float(odds_ratio), ctypes.byref(res)))
+        return res
 
     def decode_device(self, dev_ptr, nbytes):
         check(self._lib.cratac_decode_device(self._h, c_vp(int(dev_ptr)), int(nbytes)))

@@ -18,10 +18,10 @@ def context_for_reference(reference_path, device=0):
 
 
 def load_fragments(ctx, fragments_path):
-    """fragments.tsv.gz -> SoA in HBM: multi-threaded BGZF inflate (replaces the `gzip -c -d` pipe of
-    lib/python/tools/io.py:197-217) + the GPU decoder (replaces io.py:75-79)."""
-    text = _ffi.inflate_file(fragments_path)
-    return ctx.decode_host(text)
+    """fragments.tsv.gz -> SoA in HBM (cratac_decode_file): BGZF blocks inflated on all host cores into a ring of pinned
+    chunks (replaces the `gzip -c -d` pipe of lib/python/tools/io.py:197-217), each chunk copied and parsed by the GPU
+    decoder (replaces io.py:75-79) while the next ones inflate."""
+    return ctx.decode_file(fragments_path)
 
 
 def read_bed3(path):

@@ -13,6 +13,9 @@
 #include <string>
 #include <memory>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <chrono>
 
 #include "common.cuh"
 
@@ -171,6 +174,7 @@ void cratac_destroy(cratac_ctx* h) {
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_sp_scalars) cudaFreeHost(c->h_sp_scalars);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
     if (c->h_union_hash) cudaFreeHost(c->h_union_hash);
     if (c->h_union_perm) cudaFreeHost(c->h_union_perm);
     if (c->union_event) cudaEventDestroy(c->union_event);
@@ -203,6 +207,7 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
     if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_kernel")) { c->decode_kernel = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "file_chunk_bytes")) { c->file_chunk_bytes = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_profile")) { c->decode_profile = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "decode_mode")) { c->decode_mode = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "decode_ctas_per_sm")) { c->sp_ctas_per_sm = (int)value; return CRATAC_OK; }
@@ -1124,6 +1129,203 @@ int cratac_inflate_range(const char* path, int threads, uint64_t voff_begin, uin
     return CRATAC_OK;
 }
 
+
+// ---- fragments.tsv.gz straight into the decoder -------------------------------------------------------------------
+// BgzfRing: the BGZF blocks of a file are inflated on host threads into a ring of pinned chunks, in file order; the
+// streamed decode (decode.cu) copies a chunk to the device and parses it as soon as all of its blocks are there, while the
+// threads are already filling the next slots.  Inflate of chunk i+1, the PCIe copy of chunk i and the parse of chunk i-1
+// overlap; a slot is refilled once the copy that read it has completed.  Replaces the `gzip -c -d` pipe and the per-line
+// split of lib/python/tools/io.py:197-217,75-92 for the whole file.
+namespace {
+struct BgzfBlk { size_t off, csize; int64_t out_off; uint32_t isize; };
+
+struct BgzfRing : cratac::HostTextSource {
+    const unsigned char* file = nullptr;
+    std::vector<BgzfBlk> blocks;
+    int64_t total = 0, chunk = 0;
+    int slots = 0;
+    char* ring = nullptr;                       // pinned, slots * chunk bytes
+    char last = '\n';
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv_done, cv_room;
+    std::vector<unsigned char> done;            // per block
+    size_t next_block = 0, done_prefix = 0;     // blocks [0, done_prefix) are inflated
+    int64_t released = 0;                       // text bytes below this offset have left the ring (their slot may be refilled)
+    bool failed = false, stop = false;
+    std::vector<cudaEvent_t> ev;                // per slot: the copy that read it
+    std::vector<int64_t> ev_end;                // text offset that copy ends at (0: none pending)
+
+    char* at(int64_t o) const { return ring + ((o / chunk) % slots) * chunk + (o % chunk); }
+
+    void worker() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { std::lock_guard<std::mutex> g(mu); failed = true; cv_done.notify_all(); return; }
+        std::vector<uint32_t> scratch(cratac::inflate_scratch_words());
+        std::vector<unsigned char> tmp(65536);
+        for (;;) {
+            size_t i;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                if (stop || failed || next_block >= blocks.size()) break;
+                i = next_block;
+                const BgzfBlk& k = blocks[i];
+                // room: the block's bytes must fit into slots whose previous content has been copied out
+                cv_room.wait(g, [&] { return stop || failed || k.out_off + (int64_t)k.isize <= released + (int64_t)slots * chunk; });
+                if (stop || failed) break;
+                if (i != next_block) continue;                 // another thread took it while this one waited
+                next_block++;
+            }
+            const BgzfBlk& k = blocks[i];
+            bool ok;
+            const bool straddles = k.isize > 0 && (k.out_off / chunk) != ((k.out_off + (int64_t)k.isize - 1) / chunk);
+            if (!straddles) {
+                ok = inflate_block_checked(&zs, scratch.data(), file + k.off, k.csize, reinterpret_cast<unsigned char*>(at(k.out_off)), k.isize);
+            } else {
+                ok = inflate_block_checked(&zs, scratch.data(), file + k.off, k.csize, tmp.data(), k.isize);
+                if (ok) {
+                    const int64_t first = chunk - (k.out_off % chunk);
+                    memcpy(at(k.out_off), tmp.data(), (size_t)first);
+                    memcpy(at(k.out_off + first), tmp.data() + first, (size_t)(k.isize - first));
+                }
+            }
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if (!ok) failed = true;
+                done[i] = 1;
+                while (done_prefix < blocks.size() && done[done_prefix]) done_prefix++;
+            }
+            cv_done.notify_all();
+        }
+        inflateEnd(&zs);
+    }
+
+    void poll_copies(bool block_on_oldest) {
+        // completed copies free their slots (in order)
+        for (;;) {
+            int best = -1;
+            for (int s = 0; s < slots; s++) if (ev_end[s] > 0 && (best < 0 || ev_end[s] < ev_end[best])) best = s;
+            if (best < 0) return;
+            cudaError_t q = block_on_oldest ? cudaEventSynchronize(ev[best]) : cudaEventQuery(ev[best]);
+            block_on_oldest = false;
+            if (q != cudaSuccess) { if (q != cudaErrorNotReady) { std::lock_guard<std::mutex> g(mu); failed = true; } return; }
+            {
+                std::lock_guard<std::mutex> g(mu);
+                released = std::max(released, ev_end[best]);
+            }
+            ev_end[best] = 0;
+            cv_room.notify_all();
+        }
+    }
+
+    char last_byte() override { return last; }
+
+    const char* acquire(int64_t b0, int64_t b1) override {
+        for (;;) {
+            poll_copies(false);
+            std::unique_lock<std::mutex> g(mu);
+            const int64_t ready = done_prefix < blocks.size() ? blocks[done_prefix].out_off : total;
+            if (failed) return nullptr;
+            if (ready >= b1) return at(b0);
+            // the writers may be waiting for room that only a finished copy gives: wake up regularly and look
+            cv_done.wait_for(g, std::chrono::microseconds(200));
+        }
+    }
+
+    int queued(int64_t b0, int64_t b1, cudaStream_t copy_stream) override {
+        const int s = (int)((b0 / chunk) % slots);
+        if (cudaEventRecord(ev[s], copy_stream) != cudaSuccess) return CRATAC_ERR_CUDA;
+        ev_end[s] = b1;
+        return CRATAC_OK;
+    }
+
+    void shutdown() {
+        { std::lock_guard<std::mutex> g(mu); stop = true; }
+        cv_room.notify_all(); cv_done.notify_all();
+        for (auto& t : pool) t.join();
+        pool.clear();
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
+    ~BgzfRing() override { shutdown(); }
+};
+}  // namespace
+
+int cratac_decode_file(cratac_ctx* h, const char* path, int threads) {
+    if (!h || !path) { set_error("cratac_decode_file: null argument"); return CRATAC_ERR_ARG; }
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    MappedFile mf;
+    if (!mf.open_path(path)) { set_error("cannot open %s", path); return CRATAC_ERR_IO; }
+    BgzfRing src;
+    src.file = mf.p;
+    size_t p = 0;
+    bool bgzf = mf.n > 0;
+    while (p < mf.n) {
+        size_t bsize; unsigned xlen; uint32_t isize;
+        if (!bgzf_block_header(mf.p + p, mf.n - p, &bsize, &xlen, &isize)) { bgzf = false; break; }
+        src.blocks.push_back(BgzfBlk{p + 12 + xlen, bsize - 12 - xlen - 8, src.total, isize});
+        src.total += isize;
+        p += bsize;
+    }
+    if (!bgzf) {
+        // plain gzip / text (or a damaged BGZF header, which the sequential reader reports): no block index to run in
+        // parallel on -- inflate the whole file, then the host-text path
+        int64_t n = 0;
+        CRATAC_TRY(cratac_inflate_file(path, threads, nullptr, 0, &n));
+        std::vector<char> text((size_t)std::max<int64_t>(n, 1));
+        CRATAC_TRY(cratac_inflate_file(path, threads, text.data(), n, &n));
+        return cratac_decode_host(h, text.data(), n);
+    }
+    c->bc_is_slot = true;
+    const int64_t nbytes = src.total;
+    // the last byte of the text decides whether a terminator is implied: inflate the last non-empty block first
+    for (size_t i = src.blocks.size(); i-- > 0;) {
+        const BgzfBlk& k = src.blocks[i];
+        if (k.isize == 0) continue;
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { set_error("zlib init failed"); return CRATAC_ERR_IO; }
+        std::vector<uint32_t> scratch(inflate_scratch_words());
+        std::vector<unsigned char> tmp(k.isize);
+        const bool ok = inflate_block_checked(&zs, scratch.data(), mf.p + k.off, k.csize, tmp.data(), k.isize);
+        inflateEnd(&zs);
+        if (!ok) { set_error("corrupt BGZF block in %s", path); return CRATAC_ERR_IO; }
+        src.last = (char)tmp[k.isize - 1];
+        break;
+    }
+    src.chunk = decode_stream_chunk_bytes(c, std::max<int64_t>(c->file_chunk_bytes, 3 * 65536));   // a block (<= 64 KiB) crosses at most one slot border
+    src.slots = 4;
+    const size_t ring_bytes = (size_t)src.slots * (size_t)src.chunk;
+    if (c->h_ring_cap < ring_bytes) {
+        if (c->h_ring) cudaFreeHost(c->h_ring);
+        c->h_ring = nullptr; c->h_ring_cap = 0;
+        if (cudaMallocHost(&c->h_ring, ring_bytes) != cudaSuccess) { set_error("cudaMallocHost failed for the inflate ring (%zu bytes)", ring_bytes); return CRATAC_ERR_CUDA; }
+        c->h_ring_cap = ring_bytes;
+    }
+    src.ring = c->h_ring;
+    src.done.assign(src.blocks.size(), 0);
+    src.ev.resize(src.slots);
+    src.ev_end.assign(src.slots, 0);
+    for (int s = 0; s < src.slots; s++) CRATAC_CUDA(cudaEventCreateWithFlags(&src.ev[s], cudaEventDisableTiming));
+    for (int t = 0; t < threads; t++) src.pool.emplace_back([&src] { src.worker(); });
+    int rc = nbytes > 0 ? decode_text_streamed_from(c, &src, nbytes, src.chunk) : decode_text(c, c->d_text_own.as<char>(), 0);
+    const bool bad = src.failed;
+    src.shutdown();
+    if (bad) { set_error("corrupt BGZF block in %s", path); return CRATAC_ERR_IO; }
+    if (rc == CRATAC_ERR_CAPACITY) rc = decode_text(c, c->d_text_own.as<char>(), nbytes);   // the text is on the device: exact path with a larger table
+    return rc;
+}
+
+int cratac_run_file(cratac_ctx* h, const char* path, int threads, double odds_ratio, cratac_run_result* result) {
+    if (!h || !path) { set_error("cratac_run_file: null argument"); return CRATAC_ERR_ARG; }
+    h->c.host_reset();
+    CRATAC_TRY(cratac_decode_file(h, path, threads));
+    h->c.host_mark("decode_file_total");
+    return run_tail(&h->c, odds_ratio, result);
+}
 
 // Matrix Market body: "row col value\n" (1-based) for every stored entry, column by column -- the per-entry Python loop
 // of CountMatrix.save_mex (cellranger/matrix.py:812-814).  `header` (the three header lines, already formatted) is written

@@ -156,6 +156,9 @@ struct Ctx {
     int64_t n_global_cols = 0;
     int64_t row_range = 0;                 // rows of the global matrix (0 = the local peak count)
     DevBuf d_global_c2d, d_nnz_ordered, d_dense_bckey;
+    char* h_ring = nullptr;                // pinned ring the BGZF blocks of cratac_decode_file are inflated into
+    size_t h_ring_cap = 0;
+    int64_t file_chunk_bytes = (int64_t)32 << 20;   // option "file_chunk_bytes": text bytes per ring slot / H2D copy / decode launch
     DevBuf d_bg_W, d_bg_tiles, d_bg_start, d_bg_end, d_bg_count;   // bedgraph rows of one contig (bedgraph.cu)
     int64_t bg_rows = 0;
     int bg_contig = -1;
@@ -177,7 +180,8 @@ struct Ctx {
     DevBuf d_sp_state, d_sp_scalars, d_sp_irr;
     int64_t sp_irr_cap = 0;
     int64_t* h_sp_scalars = nullptr;       // pinned mirror of d_sp_scalars (4 words)
-    int decode_kernel = 1;                 // option "decode_kernel": 0 two passes (count + parse), 1 single pass with 16 KiB tiles, 2 with 32 KiB tiles
+    int decode_kernel = 0;                 // option "decode_kernel": 0 (default) two passes (count + parse); 1 single pass (k_parse_stream) with
+                                           // 16 KiB tiles, 2 with 32 KiB tiles -- measured slower on B200, kept selectable
     int sp_ctas_per_sm = 0;                // option "decode_ctas_per_sm": cap on resident CTAs of k_parse_stream (0: occupancy)
     int decode_mode = 0;                   // option "decode_mode": experiment bits of k_parse_stream (StreamArgs::mode)
     int decode_profile = 0;                // option "decode_profile": per-phase cycle counters of k_parse_stream (cratac_decode_profile)
@@ -223,9 +227,20 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 int exclusive_scan_i64(Ctx* c, const int64_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total);
 int exclusive_scan_i32_to_i64(Ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total);
 
+// Where the streamed decode takes its host text from: a buffer that is all there (cratac_decode_host), or a ring of
+// pinned chunks that BGZF blocks are being inflated into on host threads (cratac_decode_file).
+struct HostTextSource {
+    virtual ~HostTextSource() {}
+    virtual char last_byte() = 0;                                  // last byte of the whole text ('\n' when it is empty)
+    virtual const char* acquire(int64_t b0, int64_t b1) = 0;       // blocks until text bytes [b0, b1) are in host memory; contiguous pointer (null: failed)
+    virtual int queued(int64_t b0, int64_t b1, cudaStream_t copy_stream) = 0;   // their H2D copy has been queued on copy_stream
+};
+
 // ---------------------------------------------------------------- stage entry points (host side)
 int decode_text(Ctx* c, const char* d_text, int64_t nbytes);          // decode.cu
 int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes); // decode.cu: host text, H2D overlapped with the decode
+int64_t decode_stream_chunk_bytes(Ctx* c, int64_t chunk_bytes_arg);   // decode.cu: the chunk size decode_text_streamed_from will use
+int decode_text_streamed_from(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes);   // decode.cu: same, chunks supplied as they become available
 int finalize_fragments(Ctx* c);                                       // decode.cu: contig offsets, pos index, checks
 int build_barcodes(Ctx* c);                                           // decode.cu: matrix column order (host half)
 int build_barcode_strings(Ctx* c);                                    // decode.cu: barcode strings in column order (lazy)

@@ -1394,11 +1394,33 @@ __global__ void k_add_i64(int64_t* __restrict__ acc, const int64_t* __restrict__
 // has arrived, while the next chunk is in flight.  The number of lines is not known before the last chunk, so the output
 // arrays are sized from an estimate; returns CRATAC_ERR_CAPACITY when anything did not fit (table or estimate) -- the
 // caller then falls back to copy-all-then-decode.
-static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nbytes);
+static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes);
+
+namespace {
+struct PlainHostText : HostTextSource {
+    const char* p; int64_t n;
+    PlainHostText(const char* p_, int64_t n_) : p(p_), n(n_) {}
+    char last_byte() override { return n > 0 ? p[n - 1] : '\n'; }
+    const char* acquire(int64_t b0, int64_t) override { return p + b0; }
+    int queued(int64_t, int64_t, cudaStream_t) override { return CRATAC_OK; }
+};
+}  // namespace
+
+// bytes per chunk the streamed decode will ask its source for, given the caller's wish (0: the default)
+int64_t decode_stream_chunk_bytes(Ctx* c, int64_t chunk_bytes_arg) {
+    const int64_t tile = c->decode_kernel == 0 ? DEC_TILE : sp_tile_bytes(c);
+    const int64_t want = chunk_bytes_arg > 0 ? chunk_bytes_arg : (c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles * DEC_TILE : (int64_t)(128 << 20));
+    return std::max<int64_t>(want / tile, 1) * tile;
+}
+
+int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
+    PlainHostText src(h_text, nbytes);
+    return decode_text_streamed_from(c, &src, nbytes, 0);
+}
 
 // Same with the single-pass kernel: one k_parse_stream launch per chunk, the running line base stays on the device.
-int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
-    if (c->decode_kernel == 0) return decode_text_streamed_two_pass(c, h_text, nbytes);
+int decode_text_streamed_from(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes_arg) {
+    if (c->decode_kernel == 0) return decode_text_streamed_two_pass(c, src, nbytes, chunk_bytes_arg);
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
     char* d_text = c->d_text_own.as<char>();
@@ -1411,7 +1433,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
         CRATAC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CRATAC_CUDA(cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming));
     }
-    const int64_t n_eff = nbytes + ((nbytes > 0 && h_text[nbytes - 1] != '\n') ? 1 : 0);
+    const int64_t n_eff = nbytes + ((nbytes > 0 && src->last_byte() != '\n') ? 1 : 0);
     int64_t n_tiles = 0;
     CRATAC_TRY(sp_reserve(c, n_eff, &n_tiles));
     const int TB = sp_tile_bytes(c);
@@ -1443,14 +1465,19 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
     a.status = st;
     a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
     a.tile0 = 0; a.line_base = nullptr; a.line_cap = line_cap; a.irr = nullptr;
-    const int64_t chunk_bytes = c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles * DEC_TILE : (int64_t)(128 << 20);   // default: 128 MiB of text per chunk
+    const int64_t chunk_bytes = chunk_bytes_arg > 0 ? chunk_bytes_arg : (c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles * DEC_TILE : (int64_t)(128 << 20));   // default: 128 MiB of text per chunk
     const int64_t CHUNK_TILES = std::max<int64_t>(chunk_bytes / TB, 1);
     int n_launches = 0;
     c->stage_begin(SG_DECODE_PARSE);
     for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES) {
         const int64_t t1 = std::min(n_tiles, t0 + CHUNK_TILES);
         const int64_t b0 = t0 * TB, b1 = std::min(nbytes, t1 * TB);
-        if (b1 > b0) CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, h_text + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+        if (b1 > b0) {
+            const char* hp = src->acquire(b0, b1);
+            if (!hp) return CRATAC_ERR_IO;
+            CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, hp, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+            CRATAC_TRY(src->queued(b0, b1, c->copy_stream));
+        }
         CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
         CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->copy_event, 0));
         CRATAC_TRY(sp_launch(c, a, t0, t1 - t0, line_base + (n_launches & 1), line_base + ((n_launches + 1) & 1)));
@@ -1479,7 +1506,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
     return barcode_prepare_device(c);
 }
 
-static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nbytes) {
+static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes_arg) {
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
     char* d_text = c->d_text_own.as<char>();
@@ -1492,7 +1519,7 @@ static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nby
         CRATAC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CRATAC_CUDA(cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming));
     }
-    const int64_t n_eff = nbytes + ((nbytes > 0 && h_text[nbytes - 1] != '\n') ? 1 : 0);
+    const int64_t n_eff = nbytes + ((nbytes > 0 && src->last_byte() != '\n') ? 1 : 0);
     int64_t n_tiles = (n_eff + DEC_TILE - 1) / DEC_TILE;
     if (n_tiles == 0) n_tiles = 1;
     CRATAC_TRY(c->d_tile_counts.reserve(sizeof(int32_t) * (size_t)n_tiles));
@@ -1528,12 +1555,18 @@ static int decode_text_streamed_two_pass(Ctx* c, const char* h_text, int64_t nby
     a.status = st;
     a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
     a.line_base = line_base; a.line_cap = line_cap; a.irr = nullptr;
-    const int64_t CHUNK_TILES = c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles : (int64_t)(128 << 20) / DEC_TILE;   // default: 128 MiB of text per chunk
+    const int64_t CHUNK_TILES = chunk_bytes_arg > 0 ? std::max<int64_t>(chunk_bytes_arg / DEC_TILE, 1)
+                                                    : (c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles : (int64_t)(128 << 20) / DEC_TILE);   // default: 128 MiB of text per chunk
     c->stage_begin(SG_DECODE_PARSE);
     for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES) {
         const int64_t t1 = std::min(n_tiles, t0 + CHUNK_TILES);
         const int64_t b0 = t0 * DEC_TILE, b1 = std::min(nbytes, t1 * DEC_TILE);
-        if (b1 > b0) CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, h_text + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+        if (b1 > b0) {
+            const char* hp = src->acquire(b0, b1);
+            if (!hp) return CRATAC_ERR_IO;
+            CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, hp, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+            CRATAC_TRY(src->queued(b0, b1, c->copy_stream));
+        }
         CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
         CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->copy_event, 0));
         const unsigned nt = (unsigned)(t1 - t0);

@@ -62,9 +62,10 @@ void cratac_destroy(cratac_ctx* ctx);
  * cratac_fit_threshold_result), "stream_decode" (0 off / 1 host texts of 64 MiB and more / 2 always: the host text is
  * copied in chunks and each chunk is decoded while the next one is on the PCIe bus), "stream_chunk_tiles" (16 KiB
  * text tiles per chunk, 0 = 128 MiB worth), "py2_device_min" (from this many distinct barcodes on the PY2SET column
- * order is worked out on the device instead of by the host simulation; default 300000), "decode_kernel" (1, default:
- * the text is read ONCE by k_parse_stream, tiles it declines go through the general kernel; 2: same with 32 KiB tiles;
- * 0: newline-count pass + general parse kernel), "decode_ctas_per_sm" (cap on resident CTAs of k_parse_stream) */
+ * order is worked out on the device instead of by the host simulation; default 300000), "decode_kernel" (0, default:
+ * newline-count pass + general parse kernel; 1: the text is read ONCE by k_parse_stream (decoupled look-back for the line
+ * numbers), tiles it declines go through the general kernel; 2: same with 32 KiB tiles -- both measured slower than 0 on
+ * B200), "decode_ctas_per_sm" (cap on resident CTAs of k_parse_stream) */
 int cratac_set_option(cratac_ctx* ctx, const char* key, int64_t value);
 /* kernels launched by this context since creation / last reset */
 int64_t cratac_launch_count(cratac_ctx* ctx, int reset);
@@ -184,6 +185,14 @@ int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_de
                cratac_run_result* result);
 /* same, starting from fragments already decoded in this context (SoA resident in HBM) */
 int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_result* result);
+/* fragments.tsv.gz (BGZF; plain gzip and plain text are read too) -> fragments in HBM.  Replaces, for the whole file, the
+ * `gzip -c -d` pipe of lib/python/tools/io.py:197-217 and the per-line split of :75-92: `threads` host threads (0: all
+ * cores) inflate the BGZF blocks with the library's own DEFLATE decoder (CRC-32 checked) into a ring of pinned chunks
+ * (option "file_chunk_bytes", default 32 MiB each, 4 slots); each chunk is copied to the device and parsed as soon as its
+ * blocks are there, so inflate, PCIe copy and parse overlap.  The inflated text never exists in host memory as a whole. */
+int cratac_decode_file(cratac_ctx* ctx, const char* fragments_path, int threads);
+/* cratac_decode_file + the rest of the path (as cratac_run) */
+int cratac_run_file(cratac_ctx* ctx, const char* fragments_path, int threads, double odds_ratio, cratac_run_result* result);
 
 /* ---- multi-GPU building blocks (one process per GPU, genome sharded by contiguous contig ranges; the
  *      exchanges are NCCL calls made by the host on these device buffers).  They replace the file-based

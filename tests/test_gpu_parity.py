@@ -709,3 +709,67 @@ def test_single_pass_decode_tile_borders_and_errors(kernel):
             import re
             assert int(re.search(r"line (\d+)", str(e.value)).group(1)) == where + 1
     ctx.close()
+
+
+# ----------------------------------------------------------------------------- file ingest (cratac_decode_file / cratac_run_file)
+def test_decode_file_equals_decode_of_the_inflated_text(tmp_path):
+    """fragments.tsv.gz through the pipelined path (BGZF blocks inflated into the pinned ring by host threads, chunks
+    copied and parsed as they complete; small chunks so that blocks straddle slots and the ring wraps many times) against
+    the decode of the same text handed over whole; then plain gzip, plain text and a damaged block."""
+    import gzip
+    from cratac import bgzf
+    contigs = synth.GRCH38[:3]
+    frags = synth.generate(contigs, 200000, 80, 300, seed=91, background_factor=5)
+    text = synth.to_text(frags)
+    ref = _ffi.Context(contigs)
+    ref.set_option("stream_decode", 0)
+    n0, nb0 = ref.decode_host(text)
+    want, want_bcs = ref.get_fragments(), ref.get_barcodes()
+    ref.close()
+    p = str(tmp_path / "fragments.tsv.gz")
+    for body, writer in ((text, "bgzf"), (text[:-1], "bgzf"), (text, "gzip"), (text, "plain")):
+        if writer == "bgzf":
+            bgzf.write(p, body, level=1)
+        elif writer == "gzip":
+            with gzip.open(p, "wb", compresslevel=1) as f:
+                f.write(body)
+        else:
+            with open(p, "wb") as f:
+                f.write(body)
+        for kernel, chunk, threads in ((0, 1 << 16, 3), (1, 100000, 8), (0, 0, 0)):
+            ctx = _ffi.Context(contigs)
+            ctx.set_option("decode_kernel", kernel)
+            if chunk:
+                ctx.set_option("file_chunk_bytes", chunk)
+            assert ctx.decode_file(p, threads=threads) == (n0, nb0)
+            got = ctx.get_fragments()
+            for k in ("chrom", "start", "end", "bc", "dup"):
+                assert np.array_equal(got[k], want[k]), (writer, kernel, k)
+            assert ctx.get_barcodes() == want_bcs
+            ctx.close()
+    blob = bytearray(bgzf.compress(text, 1))
+    blob[len(blob) // 2] ^= 0x55
+    with open(p, "wb") as f:
+        f.write(blob)
+    ctx = _ffi.Context(contigs)
+    with pytest.raises(_ffi.CratacError) as e:
+        ctx.decode_file(p, threads=4)
+    assert e.value.code == _ffi.ERR_IO
+    ctx.close()
+
+
+def test_run_file_equals_run_on_the_text(tmp_path):
+    from cratac import bgzf
+    contigs = [("chr1", 6000000), ("chr2", 3000000)]
+    frags = synth.generate(contigs, 300000, 60, 900, seed=92, background_factor=5)
+    text = synth.to_text(frags)
+    p = str(tmp_path / "fragments.tsv.gz")
+    bgzf.write(p, text, level=1)
+    a, b = _ffi.Context(contigs), _ffi.Context(contigs)
+    b.set_option("file_chunk_bytes", 1 << 20)
+    ra, rb = a.run(text=text), b.run_file(p, threads=4)
+    assert (ra.n_fragments, ra.n_barcodes, ra.threshold, ra.n_peaks, ra.nnz) == (rb.n_fragments, rb.n_barcodes, rb.threshold, rb.n_peaks, rb.nnz)
+    assert all(np.array_equal(x, y) for x, y in zip(a.get_peaks(ra.n_peaks), b.get_peaks(rb.n_peaks)))
+    assert all(np.array_equal(x, y) for x, y in zip(a.get_matrix(ra.nnz), b.get_matrix(rb.nnz)))
+    assert a.get_barcodes() == b.get_barcodes()
+    a.close(); b.close()
