@@ -84,6 +84,7 @@ SIGNATURES = {
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_decode_file": (c_int, [c_vp, c_cp, c_int]),
+    "cratac_write_bgzf": (c_int, [c_cp, c_vp, c_i64, c_int, c_int]),
     "cratac_run_file": (c_int, [c_vp, c_cp, c_int, c_dbl, P(RunResult)]),
     "cratac_py2_set_order": (c_int, [c_i64, P(c_cp), c_vp]),
     "cratac_status_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
@@ -555,6 +556,12 @@ def inflate_file(path, threads=None):
     out = np.empty(max(n.value, 1), dtype=np.uint8)
     check(lib.cratac_inflate_file(path.encode(), threads, _ptr(out), out.size, ctypes.byref(n)))
     return out[:n.value]
+
+
+def write_bgzf(path, text, level=1, threads=0):
+    """text (bytes / numpy uint8 / (address, nbytes)) -> BGZF file, deflated on `threads` host threads (0: all)."""
+    addr, n, keep = _buffer(text)
+    check(load().cratac_write_bgzf(path.encode(), addr, n, int(level), int(threads)))
 
 
 def write_mtx(path, header, indptr, indices, data, threads=None):

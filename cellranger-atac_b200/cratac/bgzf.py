@@ -35,6 +35,27 @@ def write(path, data, level=1):
         f.write(compress(data, level))
 
 
+def write_parallel(path, data, level=1, threads=None, batch=256):
+    """Same file as write(), compressed on `threads` threads (zlib releases the GIL): batches of `batch` blocks per
+    task, written in order.  For the multi-GB synthetic inputs of bench.py."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    mv = memoryview(data)
+    n = len(mv)
+    step = BLOCK_IN * batch
+    threads = threads or (os.cpu_count() or 1)
+
+    def task(i):
+        return b"".join(_block(bytes(mv[j:j + BLOCK_IN]), level) for j in range(i, min(n, i + step), BLOCK_IN))
+
+    with open(path, "wb") as f, ThreadPoolExecutor(threads) as pool:
+        starts = list(range(0, n, step))
+        for k in range(0, len(starts), 4 * threads):            # bounded number of compressed batches in memory
+            for blob in pool.map(task, starts[k:k + 4 * threads]):
+                f.write(blob)
+        f.write(EOF_BLOCK)
+
+
 def decompress(blob):
     """BGZF / multi-member gzip bytes -> bytes (host zlib; tests only, the product uses cratac_inflate_file)."""
     out = []

@@ -1327,6 +1327,69 @@ int cratac_run_file(cratac_ctx* h, const char* path, int threads, double odds_ra
     return run_tail(&h->c, odds_ratio, result);
 }
 
+// BGZF writer: `nbytes` of text -> blocks of at most 0xff00 input bytes, each a gzip member with the 'BC' extra field, closed
+// by the empty EOF block; compressed on `threads` threads, written in order.  (The container mark_duplicates writes
+// fragments.tsv.gz in, mark_duplicates/__init__.py:399; here it builds the synthetic inputs of bench.py and the tests.)
+int cratac_write_bgzf(const char* path, const char* data, int64_t nbytes, int level, int threads) {
+    if (!path || nbytes < 0 || (nbytes > 0 && !data)) { set_error("cratac_write_bgzf: bad argument"); return CRATAC_ERR_ARG; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("cannot open %s for writing", path); return CRATAC_ERR_IO; }
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int64_t BLOCK_IN = 0xff00;
+    const int64_t n_blocks = (nbytes + BLOCK_IN - 1) / BLOCK_IN;
+    const int64_t per_task = 64;                                        // blocks per task
+    const int64_t n_tasks = (n_blocks + per_task - 1) / per_task;
+    bool failed = false;
+    for (int64_t wave = 0; wave < n_tasks && !failed; wave += 4 * (int64_t)threads) {
+        const int64_t in_wave = std::min<int64_t>(4 * (int64_t)threads, n_tasks - wave);
+        std::vector<std::vector<unsigned char>> outs((size_t)in_wave);
+        std::atomic<int64_t> next(0);
+        std::atomic<int> bad(0);
+        auto work = [&]() {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+            for (;;) {
+                const int64_t t = next.fetch_add(1);
+                if (t >= in_wave) break;
+                std::vector<unsigned char>& out = outs[(size_t)t];
+                out.reserve((size_t)(per_task * 66000));
+                for (int64_t b = (wave + t) * per_task; b < std::min(n_blocks, (wave + t + 1) * per_task); b++) {
+                    const int64_t o = b * BLOCK_IN, len = std::min(BLOCK_IN, nbytes - o);
+                    const size_t at = out.size();
+                    out.resize(at + 18 + 65535 + 8);
+                    deflateReset(&zs);
+                    zs.next_in = reinterpret_cast<unsigned char*>(const_cast<char*>(data + o)); zs.avail_in = (uInt)len;
+                    zs.next_out = out.data() + at + 18; zs.avail_out = 65535 - 26;
+                    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad = 1; break; }
+                    const size_t clen = (65535 - 26) - zs.avail_out;
+                    const unsigned bsize = (unsigned)(clen + 25);       // BSIZE = block size - 1
+                    const unsigned char head[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (unsigned char)(bsize & 255), (unsigned char)(bsize >> 8)};
+                    memcpy(out.data() + at, head, 18);
+                    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char*>(data + o), (uInt)len);
+                    const uint32_t isz = (uint32_t)len;
+                    memcpy(out.data() + at + 18 + clen, &crc, 4);
+                    memcpy(out.data() + at + 18 + clen + 4, &isz, 4);
+                    out.resize(at + 18 + clen + 8);
+                }
+                if (bad) break;
+            }
+            deflateEnd(&zs);
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        if (bad) { failed = true; break; }
+        for (auto& o : outs) if (!o.empty() && fwrite(o.data(), 1, o.size(), f) != o.size()) { failed = true; break; }
+    }
+    static const unsigned char eof_block[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!failed && fwrite(eof_block, 1, 28, f) != 28) failed = true;
+    if (fclose(f) != 0) failed = true;
+    if (failed) { set_error("writing BGZF to %s failed", path); return CRATAC_ERR_IO; }
+    return CRATAC_OK;
+}
+
 // Matrix Market body: "row col value\n" (1-based) for every stored entry, column by column -- the per-entry Python loop
 // of CountMatrix.save_mex (cellranger/matrix.py:812-814).  `header` (the three header lines, already formatted) is written
 // first.  Columns are cut into chunks of about 1 M entries; `threads` chunks are formatted at a time and written in order.

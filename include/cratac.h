@@ -191,6 +191,9 @@ int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_res
  * (option "file_chunk_bytes", default 32 MiB each, 4 slots); each chunk is copied to the device and parsed as soon as its
  * blocks are there, so inflate, PCIe copy and parse overlap.  The inflated text never exists in host memory as a whole. */
 int cratac_decode_file(cratac_ctx* ctx, const char* fragments_path, int threads);
+/* text -> BGZF file (blocks of <= 0xff00 input bytes + the EOF block; the container of fragments.tsv.gz,
+ * mark_duplicates/__init__.py:399), deflated at `level` on `threads` host threads (0: all cores) */
+int cratac_write_bgzf(const char* path, const char* data, int64_t nbytes, int level, int threads);
 /* cratac_decode_file + the rest of the path (as cratac_run) */
 int cratac_run_file(cratac_ctx* ctx, const char* fragments_path, int threads, double odds_ratio, cratac_run_result* result);
 
