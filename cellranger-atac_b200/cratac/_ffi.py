@@ -83,6 +83,7 @@ SIGNATURES = {
     "cratac_hist_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
+    "cratac_speculation_stats": (c_int, [c_vp, P(c_i64), P(c_i64)]),
     "cratac_decode_file": (c_int, [c_vp, c_cp, c_int]),
     "cratac_write_bgzf": (c_int, [c_cp, c_vp, c_i64, c_int, c_int]),
     "cratac_run_file": (c_int, [c_vp, c_cp, c_int, c_dbl, P(RunResult)]),
@@ -177,6 +178,12 @@ class Context(object):
 
     def launch_count(self, reset=False):
         return int(self._lib.cratac_launch_count(self._h, 1 if reset else 0))
+
+    def speculation_stats(self):
+        """-> (runs whose speculative peaks + matrix were kept, runs that redid them)."""
+        a, b = c_i64(), c_i64()
+        check(self._lib.cratac_speculation_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def decode_declined(self, reset=False):
         """Text ranges the single-pass decoder handed to the general parse kernel (0 on a clean file)."""

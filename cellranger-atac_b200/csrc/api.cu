@@ -174,6 +174,10 @@ void cratac_destroy(cratac_ctx* h) {
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_sp_scalars) cudaFreeHost(c->h_sp_scalars);
+    if (c->bc_thread.joinable()) c->bc_thread.join();
+    if (c->h_spec) cudaFreeHost(const_cast<int64_t*>(c->h_spec));
+    if (c->spec_stream) cudaStreamDestroy(c->spec_stream);
+    if (c->fit_event) cudaEventDestroy(c->fit_event);
     if (c->h_ring) cudaFreeHost(c->h_ring);
     if (c->h_union_hash) cudaFreeHost(c->h_union_hash);
     if (c->h_union_perm) cudaFreeHost(c->h_union_perm);
@@ -207,6 +211,8 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
     if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_kernel")) { c->decode_kernel = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "speculate")) { c->speculate = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "spec_iter")) { c->spec_iter = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "file_chunk_bytes")) { c->file_chunk_bytes = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_profile")) { c->decode_profile = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "decode_mode")) { c->decode_mode = (int)value; return CRATAC_OK; }
@@ -228,6 +234,12 @@ int cratac_decode_profile(cratac_ctx* h, int64_t* cycles_out, int n) {
     if (!c->d_sp_scalars.p) return CRATAC_OK;
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     CRATAC_CUDA(cudaMemcpy(cycles_out, c->d_sp_scalars.as<int64_t>() + 8, sizeof(int64_t) * (size_t)std::min(n, 10), cudaMemcpyDeviceToHost));
+    return CRATAC_OK;
+}
+
+int cratac_speculation_stats(cratac_ctx* h, int64_t* kept, int64_t* redone) {
+    if (kept) *kept = h->c.spec_hits;
+    if (redone) *redone = h->c.spec_misses;
     return CRATAC_OK;
 }
 
@@ -719,13 +731,69 @@ int cratac_hist_device(cratac_ctx* h, const uint64_t** d_hist, int64_t* cap) {
 }
 
 // ------------------------------------------------------------------------------------------ whole path
+// Peaks + matrix started from the threshold the fit shows after `spec_iter` EM iterations, on a second stream, while the
+// fit (one CTA) runs to convergence on the context's own: the 147 other SMs would idle for those milliseconds.  The result
+// stands only if the fit ends on the very same threshold; otherwise (the estimate still moved, or the fit re-seeded itself,
+// peaks.py:183-191) peaks + matrix are simply done again.  -> 1: speculative result is in place, 0: not used.
+static int speculate_peaks_and_matrix(Ctx* c, int* used) {
+    *used = 0;
+    if (!c->spec_armed) return CRATAC_OK;
+    // wait for the tentative threshold or for the fit itself, whichever comes first
+    bool tentative = false;
+    for (;;) {
+        if (c->h_spec[1] == c->spec_seq) { tentative = true; break; }
+        const cudaError_t q = cudaEventQuery(c->fit_event);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { set_error("fit failed: %s", cudaGetErrorString(q)); return CRATAC_ERR_CUDA; }
+    }
+    if (!tentative || cudaEventQuery(c->fit_event) == cudaSuccess) return CRATAC_OK;   // nothing left to hide behind
+    const int64_t tent = c->h_spec[0];
+    cudaStream_t own = c->stream;
+    c->stream = c->spec_stream; c->thr_slot = ST_THRESHOLD_SPEC;
+    int rc = call_peaks_device(c);
+    if (rc == CRATAC_OK) rc = peak_matrix_device(c);
+    if (rc == CRATAC_OK) rc = sync_status(c);
+    c->stream = own; c->thr_slot = ST_THRESHOLD;
+    c->host_mark("speculative_peaks_matrix");
+    // the verdict: the fit's own threshold
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_CUDA(cudaEventSynchronize(c->fit_event));
+    CRATAC_CUDA(cudaMemcpyAsync(&c->h_status[ST_THRESHOLD], &st[ST_THRESHOLD], 8, cudaMemcpyDeviceToHost, c->stream));
+    CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+    if (rc == CRATAC_OK && c->h_status[ST_THRESHOLD] == tent) { *used = 1; c->spec_hits++; }
+    else c->spec_misses++;
+    return CRATAC_OK;     // an error of the speculative pass is not an error of the run: the pass is redone
+}
+
 static int run_tail(Ctx* c, double odds_ratio, cratac_run_result* r) {
+    build_barcodes_async(c);
     CRATAC_TRY(window_histogram(c));
+    c->spec_armed = c->speculate && c->em_fast >= 2 && !c->defer_sync;
+    if (c->spec_armed) {
+        if (!c->spec_stream) {
+            CRATAC_CUDA(cudaStreamCreateWithFlags(&c->spec_stream, cudaStreamNonBlocking));
+            CRATAC_CUDA(cudaEventCreateWithFlags(&c->fit_event, cudaEventDisableTiming));
+            void* hp = nullptr;
+            CRATAC_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+            c->h_spec = reinterpret_cast<volatile int64_t*>(hp);
+            c->h_spec[0] = 0; c->h_spec[1] = 0;
+        }
+        c->spec_seq++;
+    }
     CRATAC_TRY(fit_threshold_device(c, odds_ratio));
-    CRATAC_TRY(call_peaks_device(c));
-    c->host_mark("launch_hist_fit_peaks");
-    CRATAC_TRY(peak_matrix_device(c));
-    c->host_mark("peak_matrix_total");
+    int used = 0;
+    if (c->spec_armed) {
+        CRATAC_CUDA(cudaEventRecord(c->fit_event, c->stream));
+        // the speculative kernels read what the kernels before the fit wrote (histogram pass: tile bounds, summaries)
+        CRATAC_TRY(speculate_peaks_and_matrix(c, &used));
+        c->spec_armed = false;
+    }
+    if (!used) {
+        CRATAC_TRY(call_peaks_device(c));
+        c->host_mark("launch_hist_fit_peaks");
+        CRATAC_TRY(peak_matrix_device(c));
+        c->host_mark("peak_matrix_total");
+    }
     int rc = sync_status(c);
     c->host_mark("final_sync");
     if (rc == CRATAC_ERR_CAPACITY && c->run_cap < ((int64_t)1 << 30)) {

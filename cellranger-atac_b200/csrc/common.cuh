@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -60,6 +61,7 @@ enum StatusSlot {
     ST_TICKET2 = 18,
     ST_EM_DIRECT = 19,   // direct evaluations of the dispersion fixed-point map
     ST_EM_MODE = 20,     // 0 = fit pending, 1 = left to the generic kernel, 2 = done by the register-resident kernel
+    ST_THRESHOLD_SPEC = 21,   // threshold after the first `spec_iter` EM iterations (speculative peak calling, api.cu run_tail)
     ST_SLOTS = 24
 };
 
@@ -124,6 +126,8 @@ struct Ctx {
     std::vector<std::string> barcodes;     // matrix column order
     int bc_order = CRATAC_BC_ORDER_PY2SET;
     bool bc_ready = false;
+    std::thread bc_thread;                 // host simulation of the column order (build_barcodes_async)
+    volatile bool bc_thread_done = false;
     DevBuf d_py2_rank;                     // first-appearance rank of every matrix column (device column order)
     DevBuf d_bc_nfrag, d_dense_nfrag;      // fragments per table slot / per dense barcode (int32)
     bool dense_nfrag_valid = false;        // d_dense_nfrag matches the current fragments (decode fills it; set_fragments counts on demand)
@@ -188,6 +192,17 @@ struct Ctx {
     int64_t decode_declined = 0;           // text ranges the single-pass kernel handed to the general kernel (since creation)
     int stream_decode = 1;                 // option "stream_decode": 0 off, 1 overlap the H2D copy of a host text >= 64 MiB with its decode, 2 always
     int64_t stream_chunk_tiles = 0;        // option "stream_chunk_tiles": text tiles per chunk (0: 128 MiB worth)
+    // speculation: peaks + matrix are started from the threshold the fit shows after a few EM iterations, on a second
+    // stream, while the fit (one SM) runs on; kept when the fit ends on the same threshold, redone otherwise
+    int speculate = 1;                     // option "speculate"
+    int spec_iter = 32;                    // option "spec_iter": EM iteration after which the tentative threshold is published
+    int thr_slot = ST_THRESHOLD;           // status slot the peak kernels read their threshold from
+    cudaStream_t spec_stream = nullptr;
+    cudaEvent_t fit_event = nullptr;
+    volatile int64_t* h_spec = nullptr;    // pinned + mapped: {tentative threshold, sequence number} written by the fit kernel
+    int64_t spec_seq = 0;
+    bool spec_armed = false;               // the fit being launched publishes a tentative threshold
+    int64_t spec_hits = 0, spec_misses = 0;
     int defer_sync = 0;                    // 1: window_histogram / compact_histogram / fit_threshold_device only queue their work
     int em_fast = 2;                       // 0 plain fixed point, 1 accelerated (em.cu), 2 register-resident kernel first (em_fast.cu)
     bool profile = false;
@@ -242,6 +257,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes); // decode.
 int64_t decode_stream_chunk_bytes(Ctx* c, int64_t chunk_bytes_arg);   // decode.cu: the chunk size decode_text_streamed_from will use
 int decode_text_streamed_from(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes);   // decode.cu: same, chunks supplied as they become available
 int finalize_fragments(Ctx* c);                                       // decode.cu: contig offsets, pos index, checks
+void build_barcodes_async(Ctx* c);                                    // decode.cu: start the host half on a thread of its own
 int build_barcodes(Ctx* c);                                           // decode.cu: matrix column order (host half)
 int build_barcode_strings(Ctx* c);                                    // decode.cu: barcode strings in column order (lazy)
 int window_histogram(Ctx* c);                                         // pileup.cu: K2+K3 fused

@@ -1072,6 +1072,7 @@ static int build_contig_table(Ctx* c) {
 // (slot_to_dense, needed by the overlap kernels), CPython-2.7 hashes, first-appearance order; the small
 // results travel to pinned host memory asynchronously and an event marks their arrival.
 static int barcode_prepare_device(Ctx* c) {
+    if (c->bc_thread.joinable()) c->bc_thread.join();       // a column order still being simulated for the previous fragments
     int64_t* st = c->d_status.as<int64_t>();
     const int64_t nb = c->n_barcodes, n = c->n_fragments;
     size_t nn = (size_t)std::max<int64_t>(nb, 1);
@@ -1734,13 +1735,34 @@ static int fetch_barcode_strings(Ctx* c, std::vector<std::string>& names) {
 // caller queues GPU work first so that this overlaps it.
 int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_order_out);   // py2order.cu
 
+// The host simulation of the CPython-2.7 set (sequential, ~50 ns per key) on a thread of its own, started as soon as the
+// hashes are on their way to the host (right after the decode): by the time the CSC build asks for the column order the
+// answer is there, whatever the main thread was waiting for in between.
+void build_barcodes_async(Ctx* c) {
+    if (c->bc_ready || c->bc_thread.joinable()) return;
+    const int64_t nb = c->n_barcodes;
+    if (c->bc_order != CRATAC_BC_ORDER_PY2SET || nb <= 0 || (nb >= c->py2_device_min && c->d_hash_first) || !c->bc_event) return;
+    c->bc_thread_done = false;
+    c->bc_thread = std::thread([c, nb] {
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->bc_event) != cudaSuccess) return;
+        std::vector<int32_t> order;
+        py2_set_order_hashes(c->h_bc_hash, nb, order);
+        for (int64_t j = 0; j < nb; j++) c->h_c2d_pin[j] = c->h_bc_order[order[j]];
+        c->bc_thread_done = true;
+    });
+}
+
 int build_barcodes(Ctx* c) {
+    bool from_thread = false;
+    if (c->bc_thread.joinable()) { c->bc_thread.join(); from_thread = c->bc_thread_done && !c->bc_ready; }
     if (c->bc_ready) return CRATAC_OK;
     const int64_t nb = c->n_barcodes;
     cudaStream_t s = c->stream;
     CRATAC_CUDA(cudaEventSynchronize(c->bc_event));
     int32_t* c2d = c->h_c2d_pin;    // pinned: the upload below does not wait for the stream
-    if (c->bc_order == CRATAC_BC_ORDER_FIRST_SEEN) {
+    if (from_thread && c->bc_order == CRATAC_BC_ORDER_PY2SET) {
+        // c2d was filled by build_barcodes_async
+    } else if (c->bc_order == CRATAC_BC_ORDER_FIRST_SEEN) {
         for (int64_t j = 0; j < nb; j++) c2d[j] = c->h_bc_order[j];
     } else if (c->bc_order == CRATAC_BC_ORDER_SORTED) {
         std::vector<std::string> names;

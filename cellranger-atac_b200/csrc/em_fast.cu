@@ -40,6 +40,11 @@ struct EfArgs {
     // global scratch for histograms that do not fit shared memory
     double* g_w; double* g_lg; double* g_o1; double* g_T;
     int* g_v;
+    // speculation (api.cu run_tail): after EM iteration spec_iter of the first run the threshold of the current parameters
+    // goes to status[ST_THRESHOLD_SPEC] and, behind a system-wide fence, to the host-mapped words spec_host[0..1]
+    volatile long long* spec_host;   // null: off
+    long long spec_seq;
+    int spec_iter;
 };
 
 struct EfSmem {
@@ -131,6 +136,30 @@ __device__ __forceinline__ double ef_lgamma(double x) {
 // alpha j / (1 + alpha j) = 1 - 1 / (1 + alpha j)
 // out of line: the saddle-point pmf is the rare regime (dispersion at its floor) and must not lengthen the E-step body
 __device__ __noinline__ double ef_nb_saddle(double k, double n, double p) { return nb_pmf_saddle(k, n, p, 1.0 - p); }
+
+// estimate_threshold (peaks.py:43-63): largest x in [0, 1000) with sig / bg < odds, -1 when there is none.  Out of line:
+// called at the end of the fit and once inside the loop (speculation), and the loop body must stay small.
+__device__ __noinline__ double ef_estimate_threshold(Th th, double odds_ratio, double* red) {
+    const double f_sig = 1.0 - th.f_zero - th.f_bg;
+    const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+    double best = -1.0;
+    for (int xi = threadIdx.x; xi < 1000; xi += EF_THREADS) {
+        double xv = (double)xi;
+        double ysig = f_sig * (pow(1.0 - th.p_signal, xv) * th.p_signal);
+        double nb = nn > NB_SADDLE_MIN ? ef_nb_saddle(xv, nn, pp)
+                                       : exp(lgamma(nn + xv) - lgamma(xv + 1.0) - lgamma(nn) + nn * log(pp) + xv * log1p(-pp));
+        double ybg = th.f_zero * (pow(1.0 - th.p_zero, xv) * th.p_zero) + th.f_bg * nb;
+        if (ysig / ybg < odds_ratio) best = fmax(best, xv);
+    }
+    return ef_block_max(best, red);
+}
+__device__ __forceinline__ void ef_publish_tentative(const EfArgs& a, long long thr) {
+    a.status[ST_THRESHOLD_SPEC] = thr;
+    __threadfence_system();
+    a.spec_host[0] = thr;
+    __threadfence_system();
+    a.spec_host[1] = a.spec_seq;
+}
 
 __device__ __forceinline__ double ef_frac(double alpha, double j) { return 1.0 - ef_rcp(fma(alpha, j, 1.0)); }
 
@@ -643,6 +672,10 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
             }
             th = nt;
             hard = false;
+            if (a.spec_host && tries == 0 && i == a.spec_iter) {
+                const double tent = ef_estimate_threshold(th, a.odds_ratio, s.red);
+                if (tid == 0) ef_publish_tentative(a, tent < 0.0 ? 0 : (long long)tent);
+            }
         }
         iters += i;
         if (!(ok && (1.0 / th.p_zero < th.mean_bg) && tries < 3)) break;
@@ -657,18 +690,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
         return;
     }
     // ---- estimate_threshold (peaks.py:43-63)
-    const double f_sig = 1.0 - th.f_zero - th.f_bg;
-    const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
-    double best = -1.0;
-    for (int xi = tid; xi < 1000; xi += EF_THREADS) {
-        double xv = (double)xi;
-        double ysig = f_sig * (pow(1.0 - th.p_signal, xv) * th.p_signal);
-        double nb = nn > NB_SADDLE_MIN ? ef_nb_saddle(xv, nn, pp)
-                                       : exp(lgamma(nn + xv) - lgamma(xv + 1.0) - lgamma(nn) + nn * log(pp) + xv * log1p(-pp));
-        double ybg = th.f_zero * (pow(1.0 - th.p_zero, xv) * th.p_zero) + th.f_bg * nb;
-        if (ysig / ybg < a.odds_ratio) best = fmax(best, xv);
-    }
-    best = ef_block_max(best, s.red);
+    const double best = ef_estimate_threshold(th, a.odds_ratio, s.red);
     if (tid == 0) {
         a.status[ST_THRESHOLD] = best < 0.0 ? 0 : (int64_t)best;
         a.status[ST_HAS_PARAMS] = best < 0.0 ? 2 : 1;
@@ -694,6 +716,8 @@ int em_fast_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, in
     double* w = c->d_em_work.as<double>();
     a.g_w = w; a.g_lg = w + EF_MAXN; a.g_o1 = w + 2 * EF_MAXN; a.g_v = reinterpret_cast<int*>(w + 3 * EF_MAXN);
     a.g_T = w + 6 * (size_t)EF_MAXN + 2;      // the generic kernel's T region
+    a.spec_host = c->spec_armed ? reinterpret_cast<volatile long long*>(c->h_spec) : nullptr;
+    a.spec_seq = c->spec_seq; a.spec_iter = c->spec_iter;
     k_em_fit_fast<<<1, EF_THREADS, ef_smem_bytes(), c->stream>>>(a);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());

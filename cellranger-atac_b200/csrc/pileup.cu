@@ -67,6 +67,7 @@ struct PileupArgs {
     int32_t* tile_ne;
     int64_t* tile_src_s;            // per tile: where its events sit in evt_start / evt_end
     int64_t* tile_src_e;
+    int thr_slot;                   // status slot holding the threshold (ST_THRESHOLD, or ST_THRESHOLD_SPEC for a speculative pass)
     int4* tile_summary;             // first_nz_pos, first_nz_val, last_nz_pos, last_nz_val
     int32_t* tile_bound;            // per tile: an upper bound of its window counts.  MODE_HIST writes it (and the summary);
                                     // MODE_PEAKS skips the tiles whose bound is below the threshold (null: no skipping)
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
         for (int i = tid; i < PU_HB; i += PU_THREADS) hist_s[i] = 0;
     const int maxpos = (int)a.status[ST_MAX_POS_LEN];
     const int maxneg = (int)a.status[ST_MAX_NEG_LEN];
-    long long thr_ll = a.status[ST_THRESHOLD];
+    long long thr_ll = a.status[a.thr_slot];
     const int thr = thr_ll < 1 ? 1 : (thr_ll > 0x7fffffffLL ? 0x7fffffff : (int)thr_ll);
     int loc_max = 0;
     if (MODE == MODE_PEAKS && tid == 0) { s_cur_s = 0; s_cur_e = 0; }
@@ -531,11 +532,11 @@ __global__ void __launch_bounds__(256) k_gather_events(const int64_t* __restrict
 
 // zero gaps that span tile boundaries: last non-zero W of tile t vs first non-zero W of the next non-empty tile
 __global__ void k_cross_tile_gaps(const int4* __restrict__ summary, const int64_t* __restrict__ tile_off, const int64_t* __restrict__ contig_base,
-                                  int n_contigs, int64_t n_tiles, int64_t* status, int64_t* fills, int64_t fill_cap) {
+                                  int n_contigs, int64_t n_tiles, int64_t* status, int64_t* fills, int64_t fill_cap, int thr_slot) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     int4 me = summary[t];
-    long long thr_ll = status[ST_THRESHOLD];
+    long long thr_ll = status[thr_slot];
     int thr = thr_ll < 1 ? 1 : (thr_ll > 0x7fffffffLL ? 0x7fffffff : (int)thr_ll);
     if (me.z < 0 || me.w < thr) return;
     int lo = 0, hi = n_contigs;
@@ -627,7 +628,7 @@ static int fill_args(Ctx* c, PileupArgs& a) {
     a.pidx_off = c->d_contig_pidx_off.as<int64_t>(); a.contig_lens = c->d_contig_lens.as<int64_t>();
     a.contig_base = c->d_contig_base.as<int64_t>(); a.tile_off = c->d_contig_tile_off.as<int64_t>();
     a.n_contigs = c->n_contigs; a.n_tiles = c->contig_tile_off[c->n_contigs];
-    a.status = c->d_status.as<int64_t>();
+    a.status = c->d_status.as<int64_t>(); a.thr_slot = c->thr_slot;
     a.ghist = nullptr; a.evt_start = a.evt_end = nullptr; a.cta_cap = 0; a.tile_ns = a.tile_ne = nullptr;
     a.tile_src_s = a.tile_src_e = nullptr; a.tile_summary = nullptr; a.tile_bound = nullptr;
     a.fills = nullptr; a.fill_cap = 0; a.dump_W = nullptr; a.dump_contig = -1;
@@ -785,7 +786,7 @@ int call_peaks_device(Ctx* c) {
             k_gather_events<<<gg, 256, 0, c->stream>>>(a.evt_start, tile_ns, tile_src_s, tile_dst_s, n_tiles, cap, run_start, st);
             k_gather_events<<<gg, 256, 0, c->stream>>>(a.evt_end, tile_ne, tile_src_e, tile_dst_e, n_tiles, cap, run_end, st);
             k_cross_tile_gaps<<<(unsigned)((n_tiles + 127) / 128), 128, 0, c->stream>>>(a.tile_summary, a.tile_off, a.contig_base, c->n_contigs, n_tiles, st,
-                                                                                       fills, fill_cap);
+                                                                                       fills, fill_cap, c->thr_slot);
             c->launches += 3;
         }
         k_mark_bridges<<<32, 128, 0, c->stream>>>(fills, run_end, run_start, st, bridge, fill_cap);

@@ -185,6 +185,11 @@ int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_de
                cratac_run_result* result);
 /* same, starting from fragments already decoded in this context (SoA resident in HBM) */
 int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_result* result);
+/* cratac_run* start peak calling and the matrix from the threshold the mixture fit shows after option "spec_iter" (32) EM
+ * iterations, on a second stream, while the fit -- a single CTA, peaks.py:144-193 is sequential -- runs to convergence;
+ * the speculative result is kept only when the fit ends on the same threshold, otherwise both are done again (option
+ * "speculate" = 0 switches this off).  Counters since creation: runs whose speculative result was kept / redone. */
+int cratac_speculation_stats(cratac_ctx* ctx, int64_t* kept, int64_t* redone);
 /* fragments.tsv.gz (BGZF; plain gzip and plain text are read too) -> fragments in HBM.  Replaces, for the whole file, the
  * `gzip -c -d` pipe of lib/python/tools/io.py:197-217 and the per-line split of :75-92: `threads` host threads (0: all
  * cores) inflate the BGZF blocks with the library's own DEFLATE decoder (CRC-32 checked) into a ring of pinned chunks

@@ -774,3 +774,39 @@ def test_run_file_equals_run_on_the_text(tmp_path):
     assert all(np.array_equal(x, y) for x, y in zip(a.get_matrix(ra.nnz), b.get_matrix(rb.nnz)))
     assert a.get_barcodes() == b.get_barcodes()
     a.close(); b.close()
+
+
+# ----------------------------------------------------------------------------- speculative peaks + matrix (run_tail)
+def test_speculative_peaks_and_matrix_never_change_the_result():
+    """cratac_run starts peaks + matrix from the threshold of an early EM iterate while the fit runs on.  Whatever the
+    iterate (1: certainly off; 32: the default; 100000: never published) and with speculation off, the results are those
+    of the oracle; a wrong guess only costs a second pass."""
+    contigs = [("chr1", 6000000), ("chr2", 3000000)]
+    frags = synth.generate(contigs, 350000, 60, 900, seed=22, background_factor=5)
+    text = synth.to_text(frags)
+    names = [c[0] for c in contigs]
+    o = util.oracle_decode(text, names)
+    hist = util.oracle_hist(contigs, names, o["chrom"], o["start"], o["end"])
+    othr, _ = oracle_em.estimate_final_threshold(hist, 0.2)
+    peaks = util.oracle_peaks(contigs, names, o["chrom"], o["start"], o["end"], int(othr))
+    cols = util.oracle_columns(o["first_seen"])
+    col_id = {b: j for j, b in enumerate(cols)}
+    fcol = np.array([col_id[b] for b in o["barcodes"]], dtype=np.int32)
+    oip, oix, od = util.oracle_matrix(len(contigs), peaks, o["chrom"], o["start"], o["end"], fcol, len(cols))
+    outcomes = {}
+    for speculate, spec_iter in ((1, 1), (1, 32), (1, 100000), (0, 32)):
+        ctx = _ffi.Context(contigs)
+        ctx.set_option("speculate", speculate)
+        ctx.set_option("spec_iter", spec_iter)
+        for _rep in range(2):
+            res = ctx.run(text=text)
+            assert res.threshold == int(othr)
+            c, s, e = ctx.get_peaks(res.n_peaks)
+            assert list(zip(c.tolist(), s.tolist(), e.tolist())) == peaks
+            indptr, indices, data = ctx.get_matrix(res.nnz)
+            assert np.array_equal(indptr, oip) and np.array_equal(indices, oix) and np.array_equal(data, od)
+            assert ctx.get_barcodes() == cols
+        outcomes[(speculate, spec_iter)] = ctx.speculation_stats()
+        ctx.close()
+    assert outcomes[(0, 32)] == (0, 0) and outcomes[(1, 100000)] == (0, 0)
+    assert sum(outcomes[(1, 1)]) == 2 and sum(outcomes[(1, 32)]) == 2        # both runs speculated (kept or redone)
