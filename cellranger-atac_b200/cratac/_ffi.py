@@ -84,6 +84,9 @@ SIGNATURES = {
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_speculation_stats": (c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "cratac_low_targeting": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "cratac_insert_sizes": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp]),
+    "cratac_counts_by_barcode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "cratac_decode_file": (c_int, [c_vp, c_cp, c_int]),
     "cratac_write_bgzf": (c_int, [c_cp, c_vp, c_i64, c_int, c_int]),
     "cratac_run_file": (c_int, [c_vp, c_cp, c_int, c_dbl, P(RunResult)]),
@@ -178,6 +181,65 @@ class Context(object):
 
     def launch_count(self, reset=False):
         return int(self._lib.cratac_launch_count(self._h, 1 if reset else 0))
+
+    # ---- sibling scans
+    def _regions(self, rows):
+        """rows: iterable of (contig name, start, end[, minus]) -> arrays grouped by contig in reference order, tools/regions.py
+        order (sorted (start, end) pairs) inside a contig."""
+        cid = {nm: i for i, nm in enumerate(self.contig_names)}
+        rows = sorted(((cid[r[0]], int(r[1]), int(r[2]), int(r[3]) if len(r) > 3 else 0) for r in rows if r[0] in cid),
+                      key=lambda r: r[:3])           # stable: rows equal in (start, end) keep the caller's order (name, strand in the reference)
+        a = np.array(rows, dtype=np.int64).reshape(-1, 4)
+        return _i32(a[:, 0]), _i32(a[:, 1]), _i32(a[:, 2]), np.ascontiguousarray(a[:, 3], dtype=np.int8)
+
+    def low_targeting(self, regions, paddings=(0, 50000)):
+        """REMOVE_LOW_TARGETING_BARCODES.main over all contigs -> dict of int64 arrays in matrix column order:
+        fragments, targeted, lengths{padding}, covered{padding}.  regions: (contig, start, end) rows."""
+        c, s, e, _ = self._regions(regions)
+        _, nb = self.num_fragments()
+        pads = np.ascontiguousarray(paddings, dtype=np.int64)
+        out = np.zeros((2 + 2 * pads.size, max(nb, 1)), dtype=np.int64)
+        check(self._lib.cratac_low_targeting(self._h, c.size, _ptr(c), _ptr(s), _ptr(e), pads.size, _ptr(pads), _ptr(out)))
+        out = out[:, :nb]
+        return dict(fragments=out[0], targeted=out[1], lengths={int(p): out[2 + k] for k, p in enumerate(pads)},
+                    covered={int(p): out[2 + pads.size + k] for k, p in enumerate(pads)})
+
+    def insert_sizes(self, cols, exclude_non_primary=False):
+        """REPORT_INSERT_SIZES.main for the barcodes of the matrix columns `cols` -> int64[len(cols), 1001]."""
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        table = np.zeros((max(cols.size, 1), 1001), dtype=np.int64)
+        check(self._lib.cratac_insert_sizes(self._h, cols.size, _ptr(cols), int(bool(exclude_non_primary)), _ptr(table)))
+        return table[:cols.size]
+
+    COUNT_ROWS = ("passed_filters", "total", "duplicate", "peak_region_cutsites", "TSS_fragments", "DNase_sensitive_region_fragments",
+                  "enhancer_region_fragments", "promoter_region_fragments", "on_target_fragments", "blacklist_region_fragments",
+                  "peak_region_fragments")
+
+    def counts_by_barcode(self, tracks, only_contig=None, species_list=(), species_of_contig=None, rel_half=1 << 16):
+        """get_counts_by_barcode (tools/io.py:429-555).  tracks: dict with the keys tss, ctcf, dnase, enhancer, promoter,
+        blacklist, peaks -> rows (contig, start, end[, minus]) already padded as the reference pads them (TSS 2000, CTCF 250),
+        or None.  -> ({row name: int64[n_barcodes] in matrix column order}, tss profile {position: count}, ctcf profile)."""
+        order = ("tss", "ctcf", "dnase", "enhancer", "promoter", "blacklist", "peaks")
+        parts = [self._regions(tracks.get(k) or []) for k in order]
+        off = np.concatenate(([0], np.cumsum([p[0].size for p in parts]))).astype(np.int64)
+        rc, rs, re_, rm = (np.ascontiguousarray(np.concatenate([p[k] for p in parts])) for k in range(4))
+        n_sp = len(species_list) if species_of_contig is not None and len(species_list) > 1 else 0
+        sp = None
+        if n_sp:
+            sp = _i32([species_list.index(species_of_contig[nm]) if nm in species_of_contig else -1 for nm in self.contig_names])
+        _, nb = self.num_fragments()
+        rows = 11 + 2 * n_sp
+        out = np.zeros((rows, max(nb, 1)), dtype=np.int64)
+        rel = np.zeros((2, 2 * rel_half + 1), dtype=np.int64)
+        oc = -1 if only_contig is None else self.contig_names.index(only_contig)
+        check(self._lib.cratac_counts_by_barcode(self._h, _ptr(off), _ptr(rc), _ptr(rs), _ptr(re_), _ptr(rm), oc, n_sp, _ptr(sp), rel_half,
+                                                 _ptr(out), _ptr(rel)))
+        res = {name: out[k, :nb] for k, name in enumerate(self.COUNT_ROWS)}
+        for k, spn in enumerate(species_list if n_sp else ()):
+            res["passed_filters_" + spn] = out[11 + k, :nb]
+            res["peak_region_fragments_" + spn] = out[11 + n_sp + k, :nb]
+        prof = [{int(i) - rel_half: int(v) for i, v in zip(np.nonzero(rel[t])[0], rel[t][np.nonzero(rel[t])[0]])} for t in range(2)]
+        return res, prof[0], prof[1]
 
     def speculation_stats(self):
         """-> (runs whose speculative peaks + matrix were kept, runs that redid them)."""

@@ -170,7 +170,8 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
                       &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc,
                       &c->d_union, &c->d_col_keys, &c->d_sp_state, &c->d_sp_scalars, &c->d_sp_irr,
-                      &c->d_bg_W, &c->d_bg_tiles, &c->d_bg_start, &c->d_bg_end, &c->d_bg_count};
+                      &c->d_bg_W, &c->d_bg_tiles, &c->d_bg_start, &c->d_bg_end, &c->d_bg_count,
+                      &c->d_sib_perm, &c->d_sib_seg, &c->d_sib_tmp, &c->d_sib_hist};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_sp_scalars) cudaFreeHost(c->h_sp_scalars);
@@ -235,6 +236,33 @@ int cratac_decode_profile(cratac_ctx* h, int64_t* cycles_out, int n) {
     CRATAC_CUDA(cudaStreamSynchronize(c->stream));
     CRATAC_CUDA(cudaMemcpy(cycles_out, c->d_sp_scalars.as<int64_t>() + 8, sizeof(int64_t) * (size_t)std::min(n, 10), cudaMemcpyDeviceToHost));
     return CRATAC_OK;
+}
+
+// ---- sibling scans of the fragments (siblings.cu)
+int cratac_low_targeting(cratac_ctx* h, int64_t n_regions, const int32_t* chrom, const int32_t* start, const int32_t* end, int n_paddings,
+                         const int64_t* paddings, int64_t* out) {
+    if (!h || n_regions < 0 || (n_regions > 0 && (!chrom || !start || !end)) || !out || (n_paddings > 0 && !paddings)) { set_error("cratac_low_targeting: bad argument"); return CRATAC_ERR_ARG; }
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return low_targeting(c, n_regions, chrom, start, end, n_paddings, paddings, out);
+}
+
+int cratac_insert_sizes(cratac_ctx* h, int64_t n_sel, const int64_t* cols, int exclude_non_primary, int64_t* table_out) {
+    if (!h || n_sel < 0 || (n_sel > 0 && (!cols || !table_out))) { set_error("cratac_insert_sizes: bad argument"); return CRATAC_ERR_ARG; }
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    std::vector<int32_t> prim((size_t)c->n_contigs);
+    for (int k = 0; k < c->n_contigs; k++) prim[(size_t)k] = c->contig_tile_off[(size_t)k + 1] > c->contig_tile_off[(size_t)k] ? 1 : 0;
+    return insert_sizes(c, n_sel, cols, prim.data(), exclude_non_primary, table_out);
+}
+
+int cratac_counts_by_barcode(cratac_ctx* h, const int64_t* track_off, const int32_t* r_chrom, const int32_t* r_start, const int32_t* r_end,
+                             const int8_t* r_minus, int only_contig, int n_species, const int32_t* species_of_contig, int rel_half, int64_t* out,
+                             int64_t* relpos) {
+    if (!h || !track_off || !out || !relpos) { set_error("cratac_counts_by_barcode: bad argument"); return CRATAC_ERR_ARG; }
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return counts_by_barcode(c, track_off, r_chrom, r_start, r_end, r_minus, only_contig, n_species, species_of_contig, rel_half, out, relpos);
 }
 
 int cratac_speculation_stats(cratac_ctx* h, int64_t* kept, int64_t* redone) {

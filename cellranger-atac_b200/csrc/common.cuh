@@ -160,6 +160,9 @@ struct Ctx {
     int64_t n_global_cols = 0;
     int64_t row_range = 0;                 // rows of the global matrix (0 = the local peak count)
     DevBuf d_global_c2d, d_nnz_ordered, d_dense_bckey;
+    // sibling scans (siblings.cu): fragment indices grouped by barcode in file order, segment offsets, sort scratch
+    DevBuf d_sib_perm, d_sib_seg, d_sib_tmp, d_sib_hist;
+    bool sib_valid = false;
     char* h_ring = nullptr;                // pinned ring the BGZF blocks of cratac_decode_file are inflated into
     size_t h_ring_cap = 0;
     int64_t file_chunk_bytes = (int64_t)32 << 20;   // option "file_chunk_bytes": text bytes per ring slot / H2D copy / decode launch
@@ -266,6 +269,11 @@ int fit_threshold_device(Ctx* c, double odds_ratio);                  // em.cu: 
 int peak_matrix_device(Ctx* c);                                       // matrix.cu: K6-K8
 int peak_matrix_hits(Ctx* c);                                         // matrix.cu: K6 + K7 (no columns needed)
 int peak_matrix_csc(Ctx* c);                                          // matrix.cu: K8
+int low_targeting(Ctx* c, int64_t n_regions, const int32_t* chrom, const int32_t* start, const int32_t* end, int n_pad, const int64_t* paddings,
+                  int64_t* out);                                      // siblings.cu
+int insert_sizes(Ctx* c, int64_t n_sel, const int64_t* cols, const int32_t* h_primary, int exclude_non_primary, int64_t* table_out);
+int counts_by_barcode(Ctx* c, const int64_t* track_off, const int32_t* r_chrom, const int32_t* r_start, const int32_t* r_end, const int8_t* r_minus,
+                      int only_contig, int n_species, const int32_t* species_of_contig, int rel_half, int64_t* out, int64_t* relpos);
 int bedgraph_rows_device(Ctx* c, int contig);                         // bedgraph.cu: K5b
 int union_columns(Ctx* c, int world, int64_t max_b, const int64_t* d_gathered, const int64_t* h_nfrag, const int64_t* h_nbc, cudaStream_t s,
                   int64_t* n_cols_out);                               // multi.cu

@@ -156,8 +156,13 @@ __device__ __forceinline__ unsigned long long barcode_key_words(const uint32_t* 
     return h;
 }
 
+__device__ __forceinline__ bool sp_parse_uint(const uint32_t* words, int p, int e, int32_t* out);   // below: 32-bit arithmetic only
+
 __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
-    __shared__ __align__(128) uint32_t words[(DEC_LOOKBACK + DEC_TILE) / 4 + 4];   // text tile (+16 B slack for word over-reads)
+    // text tile with 16 B of slack on either side: the word windows of the field parsers may reach before the first byte
+    // (a number ending within the first 8 bytes) and past the last one
+    __shared__ __align__(128) uint32_t words_raw[4 + (DEC_LOOKBACK + DEC_TILE) / 4 + 4];
+    uint32_t* const words = words_raw + 4;
     __shared__ uint32_t lb_masks[DEC_LOOKBACK / 16];   // look-back chunks: newline bits (low half), tab bits (high half)
     __shared__ uint16_t nlpos[DEC_MAX_LINES];          // newline positions of the tile region, in order
     __shared__ uint16_t nltabs[DEC_MAX_LINES];         // tabs of the tile region before each of them
@@ -282,6 +287,8 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
 
     // ---- one line per thread: tabs from the chunk masks, numbers and barcode a word at a time
     int loc_maxpos = 0, loc_maxneg = 0;
+    unsigned long long ckey_cache = 0xFFFFFFFFFFFFFFFFULL;
+    int32_t cid_cache = -1;
     for (int li = tid + skip; li < n_lines; li += DEC_THREADS) {
         int b = li == 0 ? s_first_begin : nlpos[li - 1] + 1;
         int e = nlpos[li];
@@ -316,17 +323,23 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
         unsigned slot = (unsigned)(mix64(key)) & (unsigned)a.bc_mask;
         ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&a.bc_tab[slot]);   // key and first line in one 16-byte load
         int32_t v_start = 0, v_end = 0, v_dup = 0;
-        const bool ok = swar_parse_uint(words, t0 + 1, t1 - t0 - 1, &v_start) && swar_parse_uint(words, t1 + 1, t2 - t1 - 1, &v_end) &&
-                        swar_parse_uint(words, t3 + 1, e - t3 - 1, &v_dup) && (t0 > b) && (t3 > t2 + 1);
+        bool ok = sp_parse_uint(words, t0 + 1, t1, &v_start) & sp_parse_uint(words, t1 + 1, t2, &v_end) & (t0 > b) & (t3 > t2 + 1);
+        if (e - t3 == 2) { const unsigned dg = byte_at(words, t3 + 1) - 0x30u; v_dup = (int32_t)dg; ok &= dg <= 9u; }   // one digit nearly always
+        else ok &= sp_parse_uint(words, t3 + 1, e, &v_dup);
         if (!ok) { raise_error(a.status, CRATAC_ERR_PARSE, line_no); continue; }
-        // contig id
-        unsigned long long ch = swar_contig_key(words, b, t0 - b);
+        // contig id: the name of the previous line of this thread, else the table
+        const unsigned long long ch = swar_contig_key(words, b, t0 - b);
         int32_t cid = -1;
-        for (int s = (int)(swar_key_slot(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
-            const int4 raw = __ldg(reinterpret_cast<const int4*>(&a.contig_table[s]));   // small read-only table: L1
-            const unsigned long long eh = (unsigned long long)(unsigned)raw.x | ((unsigned long long)(unsigned)raw.y << 32);
-            if (!raw.w) break;
-            if (eh == ch) { cid = raw.z; break; }
+        if (ch == ckey_cache) {
+            cid = cid_cache;
+        } else {
+            for (int s = (int)(swar_key_slot(ch) & (unsigned)a.contig_mask), probes = 0; probes <= a.contig_mask; s = (s + 1) & a.contig_mask, probes++) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>(&a.contig_table[s]));   // small read-only table: L1
+                const unsigned long long eh = (unsigned long long)(unsigned)raw.x | ((unsigned long long)(unsigned)raw.y << 32);
+                if (!raw.w) break;
+                if (eh == ch) { cid = raw.z; break; }
+            }
+            if (cid >= 0) { ckey_cache = ch; cid_cache = cid; }
         }
         if (cid < 0) { raise_error(a.status, CRATAC_ERR_CONTIG, line_no); continue; }
         // barcode slot
@@ -1608,6 +1621,7 @@ int finalize_fragments(Ctx* c) {
     c->tile_desc_valid = false;
     c->tile_bound_valid = false;
     c->bg_valid = false;
+    c->sib_valid = false;
     int64_t* st = c->d_status.as<int64_t>();
     int nc = c->n_contigs;
     CRATAC_TRY(c->d_contig_frag_off.reserve(sizeof(int64_t) * (nc + 2)));

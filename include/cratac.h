@@ -185,6 +185,31 @@ int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_de
                cratac_run_result* result);
 /* same, starting from fragments already decoded in this context (SoA resident in HBM) */
 int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_result* result);
+/* ---- the fragment x region siblings of the peak matrix (csrc/siblings.cu).  They read the fragments the
+ *      context holds (cratac_decode_*), so one decode serves all of them; per-barcode results come in matrix column order
+ *      (cratac_get_barcodes).  Regions are given as (contig index, start, end) arrays grouped by contig in reference order
+ *      and, inside a contig, in the order lib/python/tools/regions.py keeps them (sorted (start, end) pairs). */
+/* REMOVE_LOW_TARGETING_BARCODES.main, cell_calling/remove_low_targeting_barcodes/__init__.py:176-245, summed over the contigs:
+ * out[2 + 2 * n_paddings][n_barcodes] = fragments; fragments whose interval overlaps a region (tools/regions.py:83-93);
+ * sum of padded, clipped fragment lengths per padding; bases covered by the union of the padded fragments per padding
+ * (per contig, in file order: __init__.py:212-241).  At most 4 paddings. */
+int cratac_low_targeting(cratac_ctx* ctx, int64_t n_regions, const int32_t* chrom, const int32_t* start, const int32_t* end, int n_paddings,
+                         const int64_t* paddings, int64_t* out);
+/* REPORT_INSERT_SIZES.main, stages/metrics/report_insert_sizes/__init__.py:76-113: table_out[n_sel][1001] for the barcodes of
+ * the matrix columns cols[]: column s - 1 = fragments of size s (1..1000), column 1000 = longer ones; size 0 is dropped;
+ * exclude_non_primary = 1 skips fragments on contigs that are not primary */
+int cratac_insert_sizes(cratac_ctx* ctx, int64_t n_sel, const int64_t* cols, int exclude_non_primary, int64_t* table_out);
+/* get_counts_by_barcode, lib/python/tools/io.py:429-555.  Seven tracks in this order: TSS (already padded by 2000), CTCF
+ * (padded by 250), DNase, enhancer, promoter, blacklist, peaks; track t owns regions [track_off[t], track_off[t + 1]) of the
+ * r_* arrays (r_minus: 1 for strand '-').  only_contig >= 0 restricts the scan to one contig.  out[11 + 2 * n_species]
+ * [n_barcodes]: passed_filters, total, duplicate, peak_region_cutsites, TSS_fragments, DNase_sensitive_region_fragments,
+ * enhancer_region_fragments, promoter_region_fragments, on_target_fragments, blacklist_region_fragments,
+ * peak_region_fragments, then passed_filters_<species> and peak_region_fragments_<species> per species
+ * (species_of_contig[n_contigs], null with one species).  relpos[2][2 * rel_half + 1]: cut sites by position relative to the
+ * TSS / CTCF region they fall in (index = position + rel_half; tools/regions.py:24-36). */
+int cratac_counts_by_barcode(cratac_ctx* ctx, const int64_t* track_off, const int32_t* r_chrom, const int32_t* r_start, const int32_t* r_end,
+                             const int8_t* r_minus, int only_contig, int n_species, const int32_t* species_of_contig, int rel_half, int64_t* out,
+                             int64_t* relpos);
 /* cratac_run* start peak calling and the matrix from the threshold the mixture fit shows after option "spec_iter" (32) EM
  * iterations, on a second stream, while the fit -- a single CTA, peaks.py:144-193 is sequential -- runs to convergence;
  * the speculative result is kept only when the fit ends on the same threshold, otherwise both are done again (option

@@ -810,3 +810,137 @@ def test_speculative_peaks_and_matrix_never_change_the_result():
         ctx.close()
     assert outcomes[(0, 32)] == (0, 0) and outcomes[(1, 100000)] == (0, 0)
     assert sum(outcomes[(1, 1)]) == 2 and sum(outcomes[(1, 32)]) == 2        # both runs speculated (kept or redone)
+
+
+# ----------------------------------------------------------------------------- sibling scans (csrc/siblings.cu)
+def _rows_to_text(rows):
+    return "".join("%s\t%d\t%d\t%s\t%d\n" % tuple(r) for r in rows).encode()
+
+
+LOW_TARGETING_CASES = _load("low_targeting.json")
+
+
+@pytest.mark.parametrize("case", LOW_TARGETING_CASES, ids=[c["name"] for c in LOW_TARGETING_CASES])
+def test_low_targeting_golden(case):
+    """cratac_low_targeting against the vectors of the reference's own REMOVE_LOW_TARGETING_BARCODES.main."""
+    contig = case["contig"]
+    rows = [r for r in case["fragments"] if r[0] == contig]
+    ctx = _ffi.Context([(contig, case["contig_len"])])
+    ctx.decode_host(_rows_to_text(rows))
+    got = ctx.low_targeting([p for p in case["peaks"] if p[0] == contig], paddings=(0, 50000))
+    bcs = ctx.get_barcodes()
+    want = case["expect"]
+    assert dict(zip(bcs, got["fragments"].tolist())) == want["fragment_counts"]
+    assert {b: v for b, v in zip(bcs, got["targeted"].tolist()) if v} == want["targeted_counts"]
+    for p in (0, 50000):
+        assert dict(zip(bcs, got["lengths"][p].tolist())) == want["fragment_lengths"][str(p)]
+        assert dict(zip(bcs, got["covered"][p].tolist())) == want["covered_bases"][str(p)]
+    ctx.close()
+
+
+def test_low_targeting_random_vs_oracle():
+    """Many barcodes with thousands of fragments each over three contigs (warp rounds, carries across rounds and contigs,
+    nested regions that leave the region ends unsorted) against the oracle restatement summed over the contigs."""
+    from collections import Counter
+    from oracle import stages as ostages
+    contigs = [("chr1", 3000000), ("chr2", 1200000), ("chr3", 400000)]
+    frags = synth.generate(contigs, 150000, 25, 300, seed=61, background_factor=3)
+    text = synth.to_text(frags)
+    rng = np.random.default_rng(6)
+    regions = []
+    for name, L in contigs:
+        for _ in range(200):
+            s = int(rng.integers(0, L - 5000))
+            regions.append((name, s, s + int(rng.integers(1, 4000))))
+        for _ in range(20):                                   # nested rows
+            s = int(rng.integers(0, L - 60000))
+            regions.append((name, s, s + 50000))
+            regions.append((name, s + 10, s + 20))
+    ctx = _ffi.Context(contigs)
+    ctx.decode_host(text)
+    got = ctx.low_targeting(regions, paddings=(0, 50000))
+    bcs = ctx.get_barcodes()
+    lines = [l.split("\t") for l in text.decode().split("\n") if l]
+    rows = [(l[0], int(l[1]), int(l[2]), l[3], int(l[4])) for l in lines]
+    tot = dict(fragments=Counter(), targeted=Counter(), lengths={0: Counter(), 50000: Counter()}, covered={0: Counter(), 50000: Counter()})
+    for name, L in contigs:
+        o = ostages.remove_low_targeting_contig(name, L, regions, rows)
+        tot["fragments"].update(o["fragment_counts"]); tot["targeted"].update(o["targeted_counts"])
+        for p in (0, 50000):
+            tot["lengths"][p].update(o["fragment_lengths"][p]); tot["covered"][p].update(o["covered_bases"][p])
+    assert dict(zip(bcs, got["fragments"].tolist())) == dict(tot["fragments"])
+    assert {b: v for b, v in zip(bcs, got["targeted"].tolist()) if v} == {b: v for b, v in tot["targeted"].items() if v}
+    for p in (0, 50000):
+        assert dict(zip(bcs, got["lengths"][p].tolist())) == dict(tot["lengths"][p])
+        assert dict(zip(bcs, got["covered"][p].tolist())) == dict(tot["covered"][p])
+    ctx.close()
+
+
+INSERT_SIZES = _load("insert_sizes.json")
+
+
+@pytest.mark.parametrize("case", INSERT_SIZES["cases"], ids=[c["name"] for c in INSERT_SIZES["cases"]])
+def test_insert_sizes_golden(case):
+    """cratac_insert_sizes against REPORT_INSERT_SIZES.main run by make_golden.py (rows of barcodes absent from the file stay 0)."""
+    rows = INSERT_SIZES["fragments"]
+    names = list(dict.fromkeys(r[0] for r in rows))
+    ctx = _ffi.Context([(n, 1 << 28) for n in names], primary=[n for n in names if n in case["primary"]])
+    ctx.decode_host(_rows_to_text(rows))
+    col = {b: j for j, b in enumerate(ctx.get_barcodes())}
+    present = [b for b in case["barcodes"] if b in col]
+    table = ctx.insert_sizes([col[b] for b in present], exclude_non_primary=case["exclude_non_nuclear"])
+    want = case["expect"]
+    total = np.zeros(1000, dtype=np.int64)
+    for b in case["barcodes"]:
+        hist = table[present.index(b)] if b in col else np.zeros(1001, dtype=np.int64)
+        got = {str(n + 1): int(v) for n, v in enumerate(hist[:1000]) if v}
+        if hist[1000]:
+            got[">1000"] = int(hist[1000])
+        assert got == want["table"][b]
+        total += hist[:1000]
+    assert total.tolist() == want["total"]
+    ctx.close()
+
+
+COUNTS_CASES = _load("counts_by_barcode.json")
+
+
+@pytest.mark.parametrize("case", COUNTS_CASES, ids=[c["name"] for c in COUNTS_CASES])
+def test_counts_by_barcode_golden(case):
+    """cratac_counts_by_barcode against the vectors of the reference's own get_counts_by_barcode (tools/io.py:429-555)."""
+    from oracle import stages as ostages
+    rows = case["fragments"]
+    names = list(dict.fromkeys([r[0] for r in rows] + list(case["species_of_contig"])))
+    ctx = _ffi.Context([(n, 1 << 28) for n in names])
+    ctx.decode_host(_rows_to_text(rows))
+
+    def track(text, padding=0):
+        if text is None:
+            return None
+        out = []
+        for contig, regs in ostages.tools_target_regions(text.splitlines(True), padding).items():
+            out += [(contig, r[0], r[1], 1 if r[3] == "-" else 0) for r in regs]       # already in tools/regions.py order
+        return out
+
+    t = case["tracks"]
+    tracks = dict(tss=track(t.get("tss"), 2000), ctcf=track(t.get("ctcf"), 250), dnase=track(t.get("dnase")), enhancer=track(t.get("enhancer")),
+                  promoter=track(t.get("promoter")), blacklist=track(t.get("blacklist")), peaks=track(case["peaks"]))
+    multi = case["known_cells"] is not None and len(case["species_list"]) > 1
+    res, tss_prof, ctcf_prof = ctx.counts_by_barcode(tracks, only_contig=case["contig"], species_list=list(case["species_list"]) if multi else (),
+                                                     species_of_contig=case["species_of_contig"] if multi else None)
+    want = case["expect"]
+    bcs = ctx.get_barcodes()
+    seen = set()
+    for j, b in enumerate(bcs):
+        if res["passed_filters"][j] == 0:
+            assert b not in want["counts_by_barcode"]          # no fragment of this barcode on the contig scanned
+            continue
+        seen.add(b)
+        w = want["counts_by_barcode"][b]
+        for key, arr in res.items():
+            assert int(arr[j]) == int(w.get(key, 0)), (b, key)
+    assert seen == set(want["counts_by_barcode"])
+    assert {str(k): v for k, v in tss_prof.items()} == want["tss_relpos"]
+    assert {str(k): v for k, v in ctcf_prof.items()} == want["ctcf_relpos"]
+    assert want["read_count"] == 2 * sum(int(v) for v in res["passed_filters"])
+    ctx.close()
