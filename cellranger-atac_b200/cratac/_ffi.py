@@ -84,6 +84,7 @@ SIGNATURES = {
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_speculation_stats": (c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "cratac_fit_cell_mixture": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, P(c_dbl)]),
     "cratac_low_targeting": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "cratac_insert_sizes": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp]),
     "cratac_counts_by_barcode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
@@ -181,6 +182,16 @@ class Context(object):
 
     def launch_count(self, reset=False):
         return int(self._lib.cratac_launch_count(self._h, 1 if reset else 0))
+
+    def fit_cell_mixture(self, values, weights, odds_ratio=20):
+        """DETECT_CELL_BARCODES mixture fit -> dict(params=(mu_noise, alpha_noise, mu_signal, alpha_signal, frac_noise),
+        simple_threshold, threshold (None when the reference returns None), em_iterations)."""
+        values = np.ascontiguousarray(values, dtype=np.int64)
+        weights = np.ascontiguousarray(weights, dtype=np.int64)
+        out = (c_dbl * 8)()
+        check(self._lib.cratac_fit_cell_mixture(self._h, _ptr(values), _ptr(weights), values.size, float(odds_ratio), out))
+        return dict(params=tuple(float(out[k]) for k in range(5)), simple_threshold=int(out[5]),
+                    threshold=None if out[6] < 0 else int(out[6]), em_iterations=int(out[7]))
 
     # ---- sibling scans (SURVEY 8f rank 3)
     def _regions(self, rows):

@@ -238,6 +238,13 @@ int cratac_decode_profile(cratac_ctx* h, int64_t* cycles_out, int n) {
     return CRATAC_OK;
 }
 
+int cratac_fit_cell_mixture(cratac_ctx* h, const int64_t* values, const int64_t* weights, int64_t n_bins, double odds_ratio, double out[8]) {
+    if (!h || !values || !weights || !out) { set_error("cratac_fit_cell_mixture: null argument"); return CRATAC_ERR_ARG; }
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    return cell_fit(c, values, weights, n_bins, odds_ratio, out);
+}
+
 // ---- sibling scans of the fragments (siblings.cu)
 int cratac_low_targeting(cratac_ctx* h, int64_t n_regions, const int32_t* chrom, const int32_t* start, const int32_t* end, int n_paddings,
                          const int64_t* paddings, int64_t* out) {

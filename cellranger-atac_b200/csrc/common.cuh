@@ -266,6 +266,7 @@ int build_barcode_strings(Ctx* c);                                    // decode.
 int window_histogram(Ctx* c);                                         // pileup.cu: K2+K3 fused
 int call_peaks_device(Ctx* c);                                        // pileup.cu: K5 (threshold from d_status)
 int fit_threshold_device(Ctx* c, double odds_ratio);                  // em.cu: K4 on compact histogram
+int cell_fit(Ctx* c, const int64_t* h_values, const int64_t* h_weights, int64_t n, double odds_ratio, double out[8]);   // em.cu: cell-caller mixture
 int peak_matrix_device(Ctx* c);                                       // matrix.cu: K6-K8
 int peak_matrix_hits(Ctx* c);                                         // matrix.cu: K6 + K7 (no columns needed)
 int peak_matrix_csc(Ctx* c);                                          // matrix.cu: K8

@@ -280,6 +280,9 @@ __device__ bool fixed_point_jump(const EmArgs& a, int jmax, double mu, double N1
 }
 
 // M-step (peaks.py:90-128).  Returns false when the reference would raise ZeroDivisionError.
+__device__ double dispersion_mle(const EmArgs& a, int n, double N1, double mu, double vmax1, double* sm, FixedPointSmem& fps, long long& inner_total,
+                                 long long& direct_total);
+
 __device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, FixedPointSmem& fps, long long& inner_total, long long& direct_total) {
     const int tid = threadIdx.x;
     PH_BEGIN();
@@ -306,8 +309,18 @@ __device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, FixedPoint
     double FT = N0 + N1 + N2;
     th.f_zero = N0 / FT;
     th.f_bg = N1 / FT;
-    // ---- MLE_dispersion (em_fitting.py:35-74)
-    if (N1 == 0.0) { th.alpha_bg = 1e-6; return true; }      // (counts <= 0).all() on an empty array
+    th.alpha_bg = dispersion_mle(a, n, N1, mu, vmax1, sm, fps, inner_total, direct_total);
+    return true;
+}
+
+// MLE_dispersion (em_fitting.py:35-74) of the component whose responsibilities are a.R1: N1 = sum of w * R1, mu its weighted
+// mean, vmax1 the largest value with a positive responsibility.  Shared by the peak fit (m_step above) and the cell-caller
+// fit (k_cell_fit below, which points a.R1 at the component in turn).
+__device__ double dispersion_mle(const EmArgs& a, int n, double N1, double mu, double vmax1, double* sm, FixedPointSmem& fps, long long& inner_total,
+                                 long long& direct_total) {
+    const int tid = threadIdx.x;
+    PH_BEGIN();
+    if (N1 == 0.0) return 1e-6;                               // (counts <= 0).all() on an empty array
     double sq[1] = {0.0};
     for (int i = tid; i < n; i += EM_THREADS) {
         double d = mu - a.vd[i];
@@ -316,7 +329,7 @@ __device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, FixedPoint
     block_sum<1>(sq, sm);
     double var = sq[0] / N1;
     double alpha = fmax(1e-6, (var - mu) / (mu * mu));        // MOM_dispersion
-    if (vmax1 > 1e8 || !(var > mu)) { th.alpha_bg = alpha; return true; }
+    if (vmax1 > 1e8 || !(var > mu)) return alpha;
     PH_END(PH_MSUMS);
     // tail weights T(j) = sum_{i: v_i > j} w_i R1_i  for j = 0 .. vmax1-1
     suffix_sums(a, n, sm);
@@ -363,8 +376,7 @@ __device__ bool m_step(const EmArgs& a, int n, Theta& th, double* sm, FixedPoint
     PH_END(PH_DIRECT);
     direct_total += direct;
     inner_total += it;
-    th.alpha_bg = newv;
-    return true;
+    return newv;
 }
 
 // E-step (peaks.py:66-87)
@@ -527,6 +539,191 @@ __global__ void __launch_bounds__(EM_THREADS) k_em_fit(EmArgs a) {
         a.params_out[3] = th.p_signal; a.params_out[4] = th.f_zero; a.params_out[5] = th.f_bg;
         for (int q = 0; q < PH_COUNT; q++) a.params_out[8 + q] = (double)g_em_cycles[q];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The cell caller's mixture: two negative binomials -- background barcodes and cell-containing barcodes --
+// fitted to the fragments-per-barcode histogram, mro/atac/stages/processing/cell_calling/detect_cell_barcodes/__init__.py:84-201.
+// Same weighted mean / MLE_dispersion as the peak fit (dispersion_mle above); E-step with the saddle-point NB pmf
+// (nb_pmf.cuh: values reach tens of thousands here).  One CTA; results: params_out[0..4] = mu_noise, alpha_noise, mu_signal,
+// alpha_signal, frac_noise; params_out[5] = initial threshold (simple_threshold_estimate), params_out[6] = threshold
+// (estimate_threshold; -1: None), params_out[7] = EM iterations.
+struct CellTheta { double mu_n, a_n, mu_s, a_s, f_n; };
+
+__device__ __forceinline__ double cell_nb(double k, double mu, double alpha) {
+    const double n = 1.0 / alpha, p = 1.0 / (1.0 + alpha * mu);
+    return nb_pmf_saddle(k, n, p, 1.0 - p);
+}
+
+// weighted_parameter_estimates (:105-122) from the responsibilities in a.R0 (noise) and a.R2 (signal)
+__device__ void cell_m_step(const EmArgs& a, int n, CellTheta& th, double* sm, FixedPointSmem& fps, long long& inner, long long& direct) {
+    const int tid = threadIdx.x;
+    double acc[4] = {0, 0, 0, 0};
+    double vmax_n = 0.0, vmax_s = 0.0;
+    for (int i = tid; i < n; i += EM_THREADS) {
+        const double v = a.vd[i], w = a.wd[i], rn = a.R0[i], rs = a.R2[i];
+        acc[0] += w * rn; acc[1] += v * (w * rn); acc[2] += w * rs; acc[3] += v * (w * rs);
+        if (rn > 0.0) vmax_n = fmax(vmax_n, v);
+        if (rs > 0.0) vmax_s = fmax(vmax_s, v);
+    }
+    block_sum<4>(acc, sm);
+    vmax_n = block_max(vmax_n, sm);
+    vmax_s = block_max(vmax_s, sm);
+    const double Nn = acc[0], Ns = acc[2];
+    CellTheta t;
+    t.mu_n = acc[1] / Nn; t.mu_s = acc[3] / Ns;
+    t.f_n = Nn / (Nn + Ns);
+    EmArgs b = a;
+    b.R1 = a.R0;
+    t.a_n = dispersion_mle(b, n, Nn, t.mu_n, vmax_n, sm, fps, inner, direct);
+    __syncthreads();
+    b.R1 = a.R2;
+    t.a_s = dispersion_mle(b, n, Ns, t.mu_s, vmax_s, sm, fps, inner, direct);
+    __syncthreads();
+    if (t.mu_n > t.mu_s) { CellTheta u; u.mu_n = t.mu_s; u.a_n = t.a_s; u.mu_s = t.mu_n; u.a_s = t.a_n; u.f_n = 1.0 - t.f_n; t = u; }   // normalize_parameters (:167-173)
+    th = t;
+}
+
+__global__ void __launch_bounds__(EM_THREADS) k_cell_fit(EmArgs a, double odds_ratio) {
+    __shared__ double sm[EM_WARPS * 8];
+    __shared__ double s_d[2];
+    __shared__ FixedPointSmem fps;
+    const int tid = threadIdx.x;
+    const int n = (int)a.n_bins_host;
+    long long inner = 0, direct = 0;
+    for (int q = tid; q < CH_M * CH_M; q += EM_THREADS) {
+        int k = q / CH_M, i = q % CH_M;
+        a.costab[q] = cos((double)k * 3.14159265358979323846 * ((double)i + 0.5) / (double)CH_M);
+    }
+    double vmax = 0.0;
+    for (int i = tid; i < n; i += EM_THREADS) {
+        a.vd[i] = (double)a.values[i]; a.wd[i] = (double)a.weights[i];
+        vmax = fmax(vmax, a.vd[i]);
+    }
+    vmax = block_max(vmax, sm);
+    if (n < 3 || n > a.work_n || (int64_t)vmax + 2 > a.work_v) { if (tid == 0) raise_error(a.status, n < 3 ? CRATAC_ERR_EM_INDEX : CRATAC_ERR_CAPACITY, n); return; }
+    {
+        const int jn = (int)vmax + 1;
+        for (int j = tid; j < jn; j += EM_THREADS) {
+            int lo = 0, hi = n;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (a.vd[mid] > (double)j) hi = mid; else lo = mid + 1; }
+            a.first_gt[j] = lo;
+        }
+    }
+    // ---- simple_threshold_estimate (:150-164), thread 0, exact integer sums
+    if (tid == 0) {
+        long long total = 0, cum = 0;
+        for (int i = 0; i < n; i++) total += a.values[i] * a.weights[i];
+        long long thr = -1;
+        for (int i = 0; i < n; i++) {
+            cum += a.values[i] * a.weights[i];
+            if ((double)cum / (double)total <= 0.01) thr = a.values[i];
+        }
+        if (thr < 0) thr = a.values[1];
+        if (thr < a.values[1]) thr = a.values[1];
+        if (thr > a.values[n - 2]) thr = a.values[n - 2];
+        s_d[0] = (double)thr;
+    }
+    __syncthreads();
+    const double thr0 = s_d[0];
+    // ---- estimate_parameters (:176-201)
+    for (int i = tid; i < n; i += EM_THREADS) { a.R0[i] = a.vd[i] <= thr0 ? 1.0 : 0.0; a.R2[i] = a.vd[i] > thr0 ? 1.0 : 0.0; }
+    __syncthreads();
+    CellTheta th;
+    cell_m_step(a, n, th, sm, fps, inner, direct);
+    CellTheta last = th;
+    bool have_last = false;
+    int it = 0;
+    auto moved = [](const CellTheta& l, const CellTheta& c) {
+        const double eps = 1e-6;
+        return fabs(l.mu_n - c.mu_n) / c.mu_n > eps || fabs(l.a_n - c.a_n) / c.a_n > eps || fabs(l.mu_s - c.mu_s) / c.mu_s > eps ||
+               fabs(l.a_s - c.a_s) / c.a_s > eps || fabs(l.f_n - c.f_n) / c.f_n > eps;
+    };
+    while (it < 250 && (!have_last || moved(last, th))) {
+        it++;
+        for (int i = tid; i < n; i += EM_THREADS) {       // calculate_probability_distribution (:84-102)
+            const double v = a.vd[i];
+            const double pn = th.f_n * cell_nb(v, th.mu_n, th.a_n), ps = (1.0 - th.f_n) * cell_nb(v, th.mu_s, th.a_s);
+            const double tot = pn + ps;
+            if (tot == 0.0) { a.R0[i] = 0.0; a.R2[i] = 0.0; } else { a.R0[i] = pn / tot; a.R2[i] = ps / tot; }
+        }
+        __syncthreads();
+        last = th;
+        have_last = true;
+        cell_m_step(a, n, th, sm, fps, inner, direct);
+    }
+    // ---- estimate_threshold (:125-147)
+    // low = max(int(mu_noise), nbinom.ppf(0.001, n_signal, p_signal)): smallest k with cdf(k) >= 0.001, by chunks of the CTA
+    double ppf = -1.0;
+    {
+        double carry = 0.0;
+        for (int base = 0; base < (1 << 22) && ppf < 0.0; base += EM_THREADS) {
+            const double pm = cell_nb((double)(base + tid), th.mu_s, th.a_s);
+            double incl = pm;
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { double y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            __syncthreads();
+            if (lane == 31) sm[warp] = incl;
+            __syncthreads();
+            double off = carry, tot = 0.0;
+            for (int w = 0; w < EM_WARPS; w++) { if (w < warp) off += sm[w]; tot += sm[w]; }
+            const double cdf = off + incl;
+            double hit = cdf >= 0.001 ? (double)(EM_THREADS - tid) : 0.0;   // block_max finds the smallest index
+            hit = block_max(hit, sm);
+            if (hit > 0.0) ppf = (double)(base + EM_THREADS - (int)hit);
+            carry += tot;
+        }
+    }
+    const long long low = (long long)fmax(floor(th.mu_n), ppf);
+    const long long top = (long long)floor(th.mu_s);          // test counts low .. top
+    double found = -1.0;
+    for (long long base = low; base <= top && found < 0.0; base += EM_THREADS) {
+        const long long k = base + tid;
+        double hit = 0.0;
+        if (k <= top) {
+            const double r = ((1.0 - th.f_n) * cell_nb((double)k, th.mu_s, th.a_s)) / (th.f_n * cell_nb((double)k, th.mu_n, th.a_n));
+            if (r >= odds_ratio) hit = (double)(EM_THREADS - tid);
+        }
+        hit = block_max(hit, sm);
+        if (hit > 0.0) found = (double)(base + EM_THREADS - (long long)hit);
+    }
+    if (tid == 0) {
+        a.params_out[0] = th.mu_n; a.params_out[1] = th.a_n; a.params_out[2] = th.mu_s; a.params_out[3] = th.a_s; a.params_out[4] = th.f_n;
+        a.params_out[5] = thr0;
+        a.params_out[6] = found >= 0.0 ? found : (top >= low ? (double)top : -1.0);   // the last test count when none passes; None on an empty range
+        a.params_out[7] = (double)it;
+    }
+    (void)inner; (void)direct;
+}
+
+int cell_fit(Ctx* c, const int64_t* h_values, const int64_t* h_weights, int64_t n, double odds_ratio, double out[8]) {
+    if (n < 3 || n > (1 << 16)) { set_error("cratac_fit_cell_mixture: between 3 and 65536 distinct counts are needed"); return CRATAC_ERR_ARG; }
+    const int64_t work_n = 1 << 16, work_v = HIST_CAP + 2;
+    size_t doubles = (size_t)work_n * 6 + 2 + (size_t)work_v + 64 * 64;
+    CRATAC_TRY(c->d_em_work.reserve(doubles * 8 + (size_t)work_v * 4));
+    CRATAC_TRY(c->d_em_params.reserve(8 * 32));
+    CRATAC_TRY(c->d_hist_values.reserve(sizeof(int64_t) * HIST_CAP));
+    CRATAC_TRY(c->d_hist_weights.reserve(sizeof(int64_t) * HIST_CAP));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_hist_values.p, h_values, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CRATAC_CUDA(cudaMemcpyAsync(c->d_hist_weights.p, h_weights, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    EmArgs a;
+    a.values = c->d_hist_values.as<int64_t>(); a.weights = c->d_hist_weights.as<int64_t>(); a.n_bins_host = n; a.status = c->d_status.as<int64_t>();
+    a.params_out = c->d_em_params.as<double>(); a.odds_ratio = odds_ratio;
+    double* w = c->d_em_work.as<double>();
+    a.vd = w; w += work_n; a.wd = w; w += work_n; a.R0 = w; w += work_n; a.R1 = w; w += work_n; a.R2 = w; w += work_n;
+    a.Q = w; w += work_n + 2; a.T = w; w += work_v;
+    a.costab = w; w += 64 * 64;
+    a.fast_fixed_point = c->em_fast ? 1 : 0;
+    a.first_gt = reinterpret_cast<int*>(w);
+    a.work_n = work_n; a.work_v = work_v;
+    int64_t* st = c->d_status.as<int64_t>();
+    CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+    k_cell_fit<<<1, EM_THREADS, 0, c->stream>>>(a, odds_ratio);
+    c->launches++;
+    CRATAC_CUDA(cudaGetLastError());
+    CRATAC_CUDA(cudaMemcpyAsync(out, c->d_em_params.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+    return sync_status(c);
 }
 
 int em_fast_launch(Ctx* c, const int64_t* d_values, const int64_t* d_weights, int64_t n_bins_host, double odds_ratio);   // em_fast.cu

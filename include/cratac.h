@@ -185,6 +185,11 @@ int cratac_run(cratac_ctx* ctx, const char* text, int64_t nbytes, int text_is_de
                cratac_run_result* result);
 /* same, starting from fragments already decoded in this context (SoA resident in HBM) */
 int cratac_run_from_fragments(cratac_ctx* ctx, double odds_ratio, cratac_run_result* result);
+/* The cell caller's mixture fit: two negative binomials (background / cell-containing barcodes) fitted to
+ * the histogram {fragments per barcode: barcodes} (ascending values), detect_cell_barcodes/__init__.py:84-201, with the same
+ * dispersion solver as the peak fit.  out = mu_noise, alpha_noise, mu_signal, alpha_signal, frac_noise (:50-51), the initial
+ * threshold (:150-164), the threshold of estimate_threshold (:125-147; -1 when it is None), EM iterations. */
+int cratac_fit_cell_mixture(cratac_ctx* ctx, const int64_t* values, const int64_t* weights, int64_t n_bins, double odds_ratio, double out[8]);
 /* ---- the fragment x region siblings of the peak matrix (csrc/siblings.cu).  They read the fragments the
  *      context holds (cratac_decode_*), so one decode serves all of them; per-barcode results come in matrix column order
  *      (cratac_get_barcodes).  Regions are given as (contig index, start, end) arrays grouped by contig in reference order

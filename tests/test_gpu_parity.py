@@ -825,6 +825,14 @@ def test_low_targeting_golden(case):
     """cratac_low_targeting against the vectors of the reference's own REMOVE_LOW_TARGETING_BARCODES.main."""
     contig = case["contig"]
     rows = [r for r in case["fragments"] if r[0] == contig]
+    # Two hand-written cases list the barcodes one after the other, so the file as a whole is not position-sorted (a real
+    # fragments.tsv.gz is: tools/io.py:333).  The result is per barcode and depends on the order of that barcode's own
+    # fragments only, which a stable sort by start keeps -- checked here before sorting.
+    per_bc = {}
+    for r in rows:
+        assert per_bc.get(r[3], -1) <= r[1]
+        per_bc[r[3]] = r[1]
+    rows = sorted(rows, key=lambda r: r[1])
     ctx = _ffi.Context([(contig, case["contig_len"])])
     ctx.decode_host(_rows_to_text(rows))
     got = ctx.low_targeting([p for p in case["peaks"] if p[0] == contig], paddings=(0, 50000))
@@ -943,4 +951,20 @@ def test_counts_by_barcode_golden(case):
     assert {str(k): v for k, v in tss_prof.items()} == want["tss_relpos"]
     assert {str(k): v for k, v in ctcf_prof.items()} == want["ctcf_relpos"]
     assert want["read_count"] == 2 * sum(int(v) for v in res["passed_filters"])
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------- cell-caller mixture fit
+CELL_EM_CASES = _load("cell_em.json")
+
+
+@pytest.mark.parametrize("case", CELL_EM_CASES, ids=[c["name"] for c in CELL_EM_CASES])
+def test_cell_mixture_fit_golden(case):
+    """cratac_fit_cell_mixture (two negative binomials over fragments per barcode) against the reference's own
+    DETECT_CELL_BARCODES functions run by make_golden.py: both thresholds equal, the five parameters to 1e-8."""
+    ctx = _ffi.Context([("chr1", 1000)])
+    got = ctx.fit_cell_mixture(case["values"], case["weights"], 20)
+    assert got["simple_threshold"] == case["simple_threshold"]
+    assert np.allclose(np.array(got["params"]), np.array(case["params"]), rtol=1e-8, atol=0), (got, case["params"])
+    assert got["threshold"] == case["threshold"]
     ctx.close()
