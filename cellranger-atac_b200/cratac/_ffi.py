@@ -90,6 +90,7 @@ SIGNATURES = {
     "cratac_counts_by_barcode": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "cratac_decode_file": (c_int, [c_vp, c_cp, c_int]),
     "cratac_write_bgzf": (c_int, [c_cp, c_vp, c_i64, c_int, c_int]),
+    "cratac_h5_filter_chunks": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),
     "cratac_run_file": (c_int, [c_vp, c_cp, c_int, c_dbl, P(RunResult)]),
     "cratac_py2_set_order": (c_int, [c_i64, P(c_cp), c_vp]),
     "cratac_status_device": (c_int, [c_vp, P(c_vp), P(c_i64)]),
@@ -642,6 +643,20 @@ def write_bgzf(path, text, level=1, threads=0):
     """text (bytes / numpy uint8 / (address, nbytes)) -> BGZF file, deflated on `threads` host threads (0: all)."""
     addr, n, keep = _buffer(text)
     check(load().cratac_write_bgzf(path.encode(), addr, n, int(level), int(threads)))
+
+
+def h5_filter_chunks(arr, chunk_elems, level=4, threads=0):
+    """HDF5 shuffle + deflate of every chunk of a 1-D array on host threads -> (buffer uint8, stride, sizes int64[n_chunks])."""
+    import zlib  # noqa: F401  (compressBound is not exposed; this bound is zlib's own formula)
+    arr = np.ascontiguousarray(arr).reshape(-1)
+    chunk_bytes = chunk_elems * arr.dtype.itemsize
+    stride = chunk_bytes + (chunk_bytes >> 12) + (chunk_bytes >> 14) + (chunk_bytes >> 25) + 13 + 64
+    n_chunks = (arr.size + chunk_elems - 1) // chunk_elems
+    out = np.empty(max(n_chunks, 1) * stride, dtype=np.uint8)
+    sizes = np.zeros(max(n_chunks, 1), dtype=np.int64)
+    check(load().cratac_h5_filter_chunks(_ptr(arr) if arr.size else None, arr.size, arr.dtype.itemsize, int(chunk_elems), int(level), int(threads),
+                                         _ptr(out), stride, _ptr(sizes)))
+    return out, stride, sizes[:n_chunks]
 
 
 def write_mtx(path, header, indptr, indices, data, threads=None):

@@ -11,13 +11,23 @@ subset of the format.  Layout written = what `cellranger.matrix.CountMatrix.load
     /matrix/{barcodes S<n>[B], data int32[nnz], indices int64[nnz], indptr int64[B+1], shape int32[2]}
     /matrix/features/{_all_tag_keys, derivation, feature_type, genome, id, name}  (S<n> each)
 
-Chunking/gzip/shuffle (matrix.py:441-447) are storage details no reader depends on; datasets are contiguous.
-The reader below understands exactly this subset and is what the tests use for round trips; compatibility
-with libhdf5 itself could not be exercised in the build image (stated in DESIGN.md).
+The four matrix arrays (data, indices, indptr, shape) are stored as the reference stores them (matrix.py:441-447):
+chunked (80000 elements), shuffle + gzip filters, unlimited maximum dimension -- a version-3 chunked layout message, a
+version-1 filter pipeline message and a version-1 B-tree (node type 1) over the chunks; string datasets are contiguous
+(cellranger/io.py:323-358 passes no storage options).  `compression=None` writes contiguous arrays instead.
+The reader below understands this subset -- contiguous and chunked layouts, shuffle and deflate filters, object-header
+continuation blocks -- so it also reads the arrays of a matrix written by the reference's h5py, and fails with a clear
+message on anything else; compatibility with libhdf5 itself could not be exercised in the build image (stated in
+DESIGN.md).
 """
 import struct
+import zlib
 
 import numpy as np
+
+CHUNK_ELEMS = 80000          # cellranger/matrix.py:29 HDF5_CHUNK_SIZE
+GZIP_LEVEL = 4               # h5py's default for compression='gzip' (matrix.py:27,446)
+ISTORE_K = 32                # chunk B-tree: up to 2 * 32 entries per node (the library default; a version-0 superblock cannot say otherwise)
 
 UNDEF = 0xFFFFFFFFFFFFFFFF
 GROUP_LEAF_K = 4
@@ -41,12 +51,24 @@ def _dtype_msg(dt):
     raise TypeError("unsupported dtype %r" % dt)
 
 
-def _dataspace_msg(shape):
-    # version 1: version, rank, flags, reserved(1), reserved(4), dims
-    body = struct.pack("<BBBBI", 1, len(shape), 0, 0, 0)
+def _dataspace_msg(shape, unlimited=False):
+    # version 1: version, rank, flags (bit 0: maximum dimensions present), reserved(1), reserved(4), dims[, max dims]
+    body = struct.pack("<BBBBI", 1, len(shape), 1 if unlimited else 0, 0, 0)
     for d in shape:
         body += struct.pack("<Q", int(d))
+    if unlimited:
+        for _ in shape:
+            body += struct.pack("<Q", UNDEF)                                  # H5S_UNLIMITED
     return body
+
+
+def _shuffle(raw, itemsize):
+    """HDF5 shuffle filter: byte j of every element, for j = 0 .. itemsize - 1."""
+    return np.frombuffer(raw, dtype=np.uint8).reshape(-1, itemsize).T.tobytes()
+
+
+def _unshuffle(raw, itemsize):
+    return np.frombuffer(raw, dtype=np.uint8).reshape(itemsize, -1).T.tobytes()
 
 
 def _message(mtype, body, flags=0):
@@ -108,6 +130,61 @@ class _Writer(object):
         ]
         return self.alloc(_object_header(msgs))
 
+    def dataset_chunked(self, arr, chunk=CHUNK_ELEMS, level=GZIP_LEVEL, threads=None):
+        """1-D array as the reference stores its matrix arrays: chunks of `chunk` elements (the last one padded with
+        zeros to full size, as the library does), each shuffled and deflated; a version-1 B-tree indexes the chunks."""
+        arr = np.ascontiguousarray(arr).reshape(-1)
+        item = arr.dtype.itemsize
+        n_chunks = (arr.size + chunk - 1) // chunk
+
+        # shuffle + deflate of all chunks on the host cores (libcratac: cratac_h5_filter_chunks), written in order
+        from . import _ffi
+        entries = []                                                          # (filtered size, element offset, address)
+        if n_chunks:
+            buf, stride, sizes = _ffi.h5_filter_chunks(arr, chunk, level, threads or 0)
+            mv = memoryview(buf)
+            for k in range(n_chunks):
+                entries.append((int(sizes[k]), k * chunk, self.alloc(mv[k * stride:k * stride + int(sizes[k])])))
+        key = lambda size, off: struct.pack("<IIQQ", size, 0, off, 0)         # chunk size, filter mask, offsets (element dim + the datatype dim)
+        end_off = n_chunks * chunk
+        node_bytes = 24 + 2 * ISTORE_K * 8 + (2 * ISTORE_K + 1) * 24          # nodes have their full size on disk
+        level_nodes = entries
+        node_level = 0
+        btree_addr = UNDEF
+        while level_nodes:
+            groups = [level_nodes[g:g + 2 * ISTORE_K] for g in range(0, len(level_nodes), 2 * ISTORE_K)]
+            pad = (-self.pos) % 8
+            base = self.pos + pad                                             # the nodes of one level sit side by side
+            blob = b""
+            parents = []
+            for gi, grp in enumerate(groups):
+                nxt = groups[gi + 1][0][1] if gi + 1 < len(groups) else end_off
+                left = base + (gi - 1) * node_bytes if gi > 0 else UNDEF
+                right = base + (gi + 1) * node_bytes if gi + 1 < len(groups) else UNDEF
+                node = b"TREE" + struct.pack("<BBHQQ", 1, node_level, len(grp), left, right)
+                for size, off, addr in grp:
+                    node += key(size, off) + struct.pack("<Q", addr)
+                node += key(0, nxt)
+                blob += node + b"\0" * (node_bytes - len(node))
+                parents.append((grp[0][0], grp[0][1], base + gi * node_bytes))
+            assert self.alloc(blob) == base
+            if len(parents) == 1:
+                btree_addr = parents[0][2]
+                break
+            level_nodes = parents
+            node_level += 1
+        filters = struct.pack("<BBHI", 1, 2, 0, 0)                            # pipeline v1, two filters
+        filters += struct.pack("<HHHH", 2, 0, 1, 1) + struct.pack("<I", item) + b"\0" * 4      # shuffle (optional), client data: element size
+        filters += struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<I", level) + b"\0" * 4     # deflate (optional), client data: level
+        msgs = [
+            _message(0x0001, _dataspace_msg(arr.shape, unlimited=True)),
+            _message(0x0003, _dtype_msg(arr.dtype), flags=1),
+            _message(0x0005, struct.pack("<BBBB", 2, 3, 2, 0)),                # fill value v2: incremental allocation, write if set, undefined
+            _message(0x000B, filters),
+            _message(0x0008, struct.pack("<BBBQII", 3, 2, 2, btree_addr, chunk, item)),   # layout v3, chunked: rank + 1, B-tree, chunk dims, element size
+        ]
+        return self.alloc(_object_header(msgs))
+
     def group(self, children, attrs=None):
         """children: dict name -> object header address.  Returns (header addr, btree addr, heap addr)."""
         names = sorted(children)                                              # SNOD entries are ordered by name
@@ -145,12 +222,14 @@ def _string_array(values):
     return np.array(enc, dtype="S%d" % n) if enc else np.zeros(0, dtype="S1")
 
 
-def write_matrix_h5(path, indptr, indices, data, n_features, barcodes, feature_ids, genome, sw_version=""):
+def write_matrix_h5(path, indptr, indices, data, n_features, barcodes, feature_ids, genome, sw_version="", compression="gzip"):
     """CountMatrix.save_h5_file (cellranger/matrix.py:415-447) + FeatureReference.to_hdf5 (feature_ref.py:103-118)
     + atac from_peaks_bed (cellranger/atac/feature_ref.py:45-71: id = name = 'chr:start-end', type 'Peaks',
-    tags genome / derivation='')."""
+    tags genome / derivation='').  compression="gzip" (default): the four matrix arrays chunked / shuffled / deflated as
+    save_h5_group does; None: contiguous."""
     f = open(path, "wb")
     w = _Writer(f)
+    arr = w.dataset_chunked if compression == "gzip" else w.dataset
     w.alloc(b"\0" * 96)                                                      # superblock placeholder
     n_bc = len(barcodes)
     feats = {
@@ -164,10 +243,10 @@ def write_matrix_h5(path, indptr, indices, data, n_features, barcodes, feature_i
     feat_hdr, _, _ = w.group(feats)
     matrix = {
         "barcodes": w.dataset(_string_array(barcodes)),
-        "data": w.dataset(np.asarray(data, dtype="<i4")),
-        "indices": w.dataset(np.asarray(indices, dtype="<i8")),
-        "indptr": w.dataset(np.asarray(indptr, dtype="<i8")),
-        "shape": w.dataset(np.array([n_features, n_bc], dtype="<i4")),
+        "data": arr(np.asarray(data, dtype="<i4")),
+        "indices": arr(np.asarray(indices, dtype="<i8")),
+        "indptr": arr(np.asarray(indptr, dtype="<i8")),
+        "shape": arr(np.array([n_features, n_bc], dtype="<i4")),
         "features": feat_hdr,
     }
     mat_hdr, _, _ = w.group(matrix)
@@ -194,13 +273,20 @@ class _Reader(object):
 
     def messages(self, addr):
         ver, _, n, _, size = struct.unpack_from("<BBHII", self.b, addr)
-        assert ver == 1
-        p = addr + 16
+        if ver != 1:
+            raise ValueError("object header version %d at %d: only version-1 headers (libver='earliest') are read" % (ver, addr))
+        blocks = [(addr + 16, size)]
         out = []
-        for _ in range(n):
-            mtype, msize, _flags = struct.unpack_from("<HHB", self.b, p)
-            out.append((mtype, self.b[p + 8:p + 8 + msize]))
-            p += 8 + msize
+        while blocks and len(out) < n:
+            p, left = blocks.pop(0)
+            while left >= 8 and len(out) < n:
+                mtype, msize, _flags = struct.unpack_from("<HHB", self.b, p)
+                body = self.b[p + 8:p + 8 + msize]
+                if mtype == 0x0010:                                            # continuation: more messages elsewhere
+                    blocks.append(struct.unpack_from("<QQ", body, 0))
+                out.append((mtype, body))
+                p += 8 + msize
+                left -= 8 + msize
         return out
 
     def children(self, hdr):
@@ -238,21 +324,95 @@ class _Reader(object):
                 out[name] = struct.unpack("<q", raw)[0] if cls == 0 else raw.rstrip(b"\0").decode("ascii")
         return out
 
+    def _chunks(self, node, out):
+        """(element offset, address, filtered size, filter mask) of every chunk below B-tree node `node` (1-D datasets)."""
+        if self.b[node:node + 4] != b"TREE" or self.b[node + 4] != 1:
+            raise ValueError("no chunk B-tree node at %d" % node)
+        level, used = struct.unpack_from("<BH", self.b, node + 5)
+        p = node + 24
+        for _ in range(used):
+            size, mask, off, _zero, child = struct.unpack_from("<IIQQQ", self.b, p)
+            if level == 0:
+                out.append((off, child, size, mask))
+            else:
+                self._chunks(child, out)
+            p += 32
+
     def dataset(self, hdr):
-        shape, dtype, addr, nbytes = (), None, UNDEF, 0
+        shape, dtype, layout, filters = (), None, None, []
         for mtype, body in self.messages(hdr):
             if mtype == 0x0001:
+                if body[0] != 1:
+                    raise ValueError("dataspace message version %d is not read" % body[0])
                 rank = body[1]
                 shape = struct.unpack_from("<%dQ" % rank, body, 8) if rank else ()
             elif mtype == 0x0003:
                 cls = body[0] & 0x0F
                 size = struct.unpack_from("<I", body, 4)[0]
-                dtype = np.dtype("<i%d" % size) if cls == 0 else np.dtype("S%d" % size)
+                if cls == 0:
+                    if body[1] & 1:
+                        raise ValueError("big-endian integers are not read")
+                    dtype = np.dtype("<%s%d" % ("i" if body[1] & 8 else "u", size))
+                elif cls == 3:
+                    dtype = np.dtype("S%d" % size)
+                else:
+                    raise ValueError("datatype class %d is not read (fixed-point and fixed-length strings only)" % cls)
+            elif mtype == 0x000B:
+                if body[0] != 1:
+                    raise ValueError("filter pipeline version %d is not read" % body[0])
+                p = 8
+                for _ in range(body[1]):
+                    fid, nlen, _fl, ncd = struct.unpack_from("<HHHH", body, p)
+                    p += 8 + (nlen + 7) // 8 * 8
+                    cd = struct.unpack_from("<%dI" % ncd, body, p)
+                    p += 4 * ncd + (4 if ncd % 2 else 0)
+                    filters.append((fid, cd))
             elif mtype == 0x0008:
-                addr, nbytes = struct.unpack_from("<QQ", body, 2)
-        if nbytes == 0:
-            return np.zeros(shape, dtype=dtype)
-        return np.frombuffer(self.b, dtype=dtype, count=int(np.prod(shape)), offset=addr).reshape(shape).copy()
+                if body[0] != 3:
+                    raise ValueError("data layout message version %d is not read" % body[0])
+                if body[1] == 1:
+                    layout = ("contiguous",) + struct.unpack_from("<QQ", body, 2)
+                elif body[1] == 2:
+                    ndim = body[2]
+                    if ndim != 2:
+                        raise ValueError("chunked datasets of rank %d are not read (1-D only)" % (ndim - 1))
+                    layout = ("chunked", struct.unpack_from("<Q", body, 3)[0]) + struct.unpack_from("<II", body, 11)
+                elif body[1] == 0:
+                    n = struct.unpack_from("<H", body, 2)[0]
+                    layout = ("compact", bytes(body[4:4 + n]))
+                else:
+                    raise ValueError("data layout class %d is not read" % body[1])
+        if layout is None or dtype is None:
+            raise ValueError("dataset header at %d lacks a datatype or layout message" % hdr)
+        count = int(np.prod(shape)) if shape else 1
+        if layout[0] == "contiguous":
+            if layout[2] == 0 or layout[1] == UNDEF:
+                return np.zeros(shape, dtype=dtype)
+            return np.frombuffer(self.b, dtype=dtype, count=count, offset=layout[1]).reshape(shape).copy()
+        if layout[0] == "compact":
+            return np.frombuffer(layout[1], dtype=dtype, count=count).reshape(shape).copy()
+        _, tree, chunk, item = layout
+        out = np.zeros(count, dtype=dtype)
+        if tree == UNDEF or count == 0:
+            return out.reshape(shape)
+        chunks = []
+        self._chunks(tree, chunks)
+        for off, addr, size, mask in chunks:
+            raw = bytes(self.b[addr:addr + size])
+            for k, (fid, cd) in reversed(list(enumerate(filters))):           # undo the pipeline back to front
+                if mask & (1 << k):
+                    continue                                                   # this filter was skipped for this chunk
+                if fid == 1:
+                    raw = zlib.decompress(raw)
+                elif fid == 2:
+                    raw = _unshuffle(raw, cd[0] if cd else item)
+                else:
+                    raise ValueError("filter %d is not read (deflate and shuffle only)" % fid)
+            vals = np.frombuffer(raw, dtype=dtype)
+            take = min(vals.size, count - off)
+            if take > 0:
+                out[off:off + take] = vals[:take]
+        return out.reshape(shape)
 
 
 def read_matrix_h5(path):

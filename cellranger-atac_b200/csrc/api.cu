@@ -1430,6 +1430,44 @@ int cratac_run_file(cratac_ctx* h, const char* path, int threads, double odds_ra
     return run_tail(&h->c, odds_ratio, result);
 }
 
+// HDF5 chunk filters on all host cores: chunk k = elements [k * chunk_elems, (k + 1) * chunk_elems) of `data` (the last one
+// padded with zeros to full size), byte-shuffled (item_size) and deflated (zlib stream) into out + k * stride;
+// sizes[k] = its filtered length.  What h5py does one chunk at a time for compression='gzip', shuffle=True
+// (cellranger/matrix.py:441-447); cratac/h5.py lays the chunks out and indexes them.
+int cratac_h5_filter_chunks(const void* data, int64_t n_elems, int item_size, int64_t chunk_elems, int level, int threads, unsigned char* out,
+                            int64_t stride, int64_t* sizes) {
+    if (n_elems < 0 || item_size < 1 || chunk_elems < 1 || (n_elems > 0 && (!data || !out || !sizes))) { set_error("cratac_h5_filter_chunks: bad argument"); return CRATAC_ERR_ARG; }
+    const int64_t chunk_bytes = chunk_elems * item_size;
+    if (stride < (int64_t)compressBound((uLong)chunk_bytes)) { set_error("cratac_h5_filter_chunks: stride below compressBound"); return CRATAC_ERR_ARG; }
+    const int64_t n_chunks = (n_elems + chunk_elems - 1) / chunk_elems;
+    if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<int64_t> next(0);
+    std::atomic<int> bad(0);
+    auto work = [&]() {
+        std::vector<unsigned char> shuf((size_t)chunk_bytes);
+        for (;;) {
+            const int64_t k = next.fetch_add(1);
+            if (k >= n_chunks) break;
+            const int64_t e0 = k * chunk_elems, ne = std::min(chunk_elems, n_elems - e0);
+            const unsigned char* src = static_cast<const unsigned char*>(data) + e0 * item_size;
+            if (ne < chunk_elems) memset(shuf.data(), 0, (size_t)chunk_bytes);
+            for (int j = 0; j < item_size; j++) {
+                unsigned char* dst = shuf.data() + (size_t)j * (size_t)chunk_elems;
+                for (int64_t i = 0; i < ne; i++) dst[i] = src[i * item_size + j];
+            }
+            uLongf out_len = (uLongf)stride;
+            if (compress2(out + k * stride, &out_len, shuf.data(), (uLong)chunk_bytes, level) != Z_OK) { bad = 1; break; }
+            sizes[k] = (int64_t)out_len;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (bad) { set_error("deflate failed"); return CRATAC_ERR_IO; }
+    return CRATAC_OK;
+}
+
 // BGZF writer: `nbytes` of text -> blocks of at most 0xff00 input bytes, each a gzip member with the 'BC' extra field, closed
 // by the empty EOF block; compressed on `threads` threads, written in order.  (The container mark_duplicates writes
 // fragments.tsv.gz in, mark_duplicates/__init__.py:399; here it builds the synthetic inputs of bench.py and the tests.)

@@ -229,6 +229,11 @@ int cratac_decode_file(cratac_ctx* ctx, const char* fragments_path, int threads)
 /* text -> BGZF file (blocks of <= 0xff00 input bytes + the EOF block; the container of fragments.tsv.gz,
  * mark_duplicates/__init__.py:399), deflated at `level` on `threads` host threads (0: all cores) */
 int cratac_write_bgzf(const char* path, const char* data, int64_t nbytes, int level, int threads);
+/* HDF5 chunk filters (shuffle + deflate) of a 1-D array on `threads` host threads (0: all cores): chunk k of chunk_elems
+ * elements (the last one zero-padded) -> out + k * stride (stride >= zlib's compressBound of a chunk), sizes[k] its filtered
+ * length.  The storage of the matrix arrays in cellranger/matrix.py:441-447 (chunks of 80000, gzip, shuffle). */
+int cratac_h5_filter_chunks(const void* data, int64_t n_elems, int item_size, int64_t chunk_elems, int level, int threads, unsigned char* out,
+                            int64_t stride, int64_t* sizes);
 /* cratac_decode_file + the rest of the path (as cratac_run) */
 int cratac_run_file(cratac_ctx* ctx, const char* fragments_path, int threads, double odds_ratio, cratac_run_result* result);
 
