@@ -415,8 +415,27 @@ class _Reader(object):
         return out.reshape(shape)
 
 
+def _read_with_h5py(path):
+    import h5py
+    with h5py.File(path, "r") as f:
+        attrs = {}
+        for k, v in f.attrs.items():
+            attrs[k] = v.decode() if isinstance(v, bytes) else (int(v) if np.issubdtype(type(v), np.integer) else v)
+        m = f["matrix"]
+        out = dict(attrs=attrs, features={k: m["features"][k][()] for k in m["features"]})
+        for k in ("indptr", "indices", "data", "shape", "barcodes"):
+            out[k] = m[k][()]
+    return out
+
+
 def read_matrix_h5(path):
-    """-> dict(attrs, indptr, indices, data, shape, barcodes, features={name: array})."""
+    """-> dict(attrs, indptr, indices, data, shape, barcodes, features={name: array}).  Where h5py is installed (any
+    cellranger installation) it does the reading; otherwise the reader above, which raises ValueError with the reason on
+    a file outside its subset."""
+    try:
+        return _read_with_h5py(path)
+    except ImportError:
+        pass
     with open(path, "rb") as f:
         r = _Reader(f.read())
     root = r.children(r.root_hdr)

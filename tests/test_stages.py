@@ -90,6 +90,48 @@ def test_h5_round_trip(tmp_path):
     assert m["indptr"].tolist() == [0] and m["indices"].size == 0 and m["shape"].tolist() == [0, 0]
 
 
+def test_h5_matrix_arrays_are_stored_like_the_reference_stores_them(tmp_path):
+    """cellranger/matrix.py:441-447: chunks of 80000, gzip, shuffle, unlimited maximum dimension.  The bytes are checked
+    against the HDF5 file format specification by hand (no libhdf5 in the image): version-3 chunked layout message,
+    version-1 filter pipeline (shuffle, then deflate level 4), version-1 chunk B-tree whose leaves hold at most 64 chunks
+    -- 200 chunks here, so the tree has two levels -- and every chunk is a zlib stream of the byte-shuffled, zero-padded
+    80000 elements.  Contiguous storage (compression=None) reads back the same."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(9)
+    nnz, n_bc = 200 * 80000 - 12345, 3000
+    counts = rng.multinomial(nnz, np.ones(n_bc) / n_bc)
+    indptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+    indices = rng.integers(0, 124000, size=nnz).astype(np.int64)
+    data = rng.integers(1, 4, size=nnz).astype(np.int32)
+    p = str(tmp_path / "m.h5")
+    for comp in ("gzip", None):
+        h5.write_matrix_h5(p, indptr, indices, data, 124000, ["B%d-1" % i for i in range(n_bc)], [], "GRCh38", compression=comp)
+        m = h5.read_matrix_h5(p)
+        assert np.array_equal(m["indptr"], indptr) and np.array_equal(m["indices"], indices) and np.array_equal(m["data"], data)
+    h5.write_matrix_h5(p, indptr, indices, data, 124000, ["B%d-1" % i for i in range(n_bc)], [], "GRCh38")
+    blob = open(p, "rb").read()
+    r = h5._Reader(blob)
+    mat = r.children(r.children(r.root_hdr)["matrix"])
+    msgs = dict(r.messages(mat["indices"]))
+    layout = msgs[0x0008]
+    assert layout[:3] == bytes([3, 2, 2]) and struct.unpack_from("<II", layout, 11) == (80000, 8)          # v3, chunked, rank + 1, chunk dims
+    assert msgs[0x0001][:3] == bytes([1, 1, 1]) and struct.unpack_from("<QQ", msgs[0x0001], 8) == (nnz, 0xFFFFFFFFFFFFFFFF)
+    pipe = msgs[0x000B]
+    assert pipe[:2] == bytes([1, 2]) and struct.unpack_from("<HHHHI", pipe, 8) == (2, 0, 1, 1, 8) and struct.unpack_from("<HHHHI", pipe, 24) == (1, 0, 1, 1, 4)
+    root = struct.unpack_from("<Q", layout, 3)[0]
+    assert blob[root:root + 4] == b"TREE" and blob[root + 4] == 1 and blob[root + 5] == 1                  # chunk tree, level 1
+    n_leaves = struct.unpack_from("<H", blob, root + 6)[0]
+    assert n_leaves == 4                                                                                    # ceil(200 / 64)
+    leaf0 = struct.unpack_from("<Q", blob, root + 24 + 24)[0]
+    assert blob[leaf0 + 5] == 0 and struct.unpack_from("<H", blob, leaf0 + 6)[0] == 64
+    assert struct.unpack_from("<QQ", blob, leaf0 + 8) == (0xFFFFFFFFFFFFFFFF, struct.unpack_from("<Q", blob, root + 24 + 32 + 24)[0])   # siblings
+    size, mask, off, zero, addr = struct.unpack_from("<IIQQQ", blob, leaf0 + 24 + 32)                       # second chunk of the first leaf
+    assert (mask, off, zero) == (0, 80000, 0)
+    raw = zlib.decompress(blob[addr:addr + size])
+    assert np.array_equal(np.frombuffer(raw, dtype=np.uint8).reshape(8, 80000).T.copy().view("<i8").ravel(), indices[80000:160000])
+
+
 def test_mex_writer(tmp_path):
     d = str(tmp_path / "mex")
     mex.save_mex(d, [0, 2, 2, 3], [0, 2, 1], [4, 1, 7], 3, ["A-1", "B-1", "C-1"], ["chr1:1-5", "chr1:9-20", "chr2:0-3"], "1.2.0")
