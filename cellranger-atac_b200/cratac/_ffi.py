@@ -84,6 +84,9 @@ SIGNATURES = {
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_speculation_stats": (c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "cratac_fit_speculative_launch": (c_int, [c_vp, c_dbl]),
+    "cratac_fit_tentative": (c_int, [c_vp, P(c_int), P(c_i64)]),
+    "cratac_speculation_scope": (c_int, [c_vp, c_int, P(ctypes.c_uint64)]),
     "cratac_fit_cell_mixture": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, P(c_dbl)]),
     "cratac_low_targeting": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "cratac_insert_sizes": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp]),
@@ -252,6 +255,21 @@ class Context(object):
             res["peak_region_fragments_" + spn] = out[11 + n_sp + k, :nb]
         prof = [{int(i) - rel_half: int(v) for i, v in zip(np.nonzero(rel[t])[0], rel[t][np.nonzero(rel[t])[0]])} for t in range(2)]
         return res, prof[0], prof[1]
+
+    def fit_speculative_launch(self, odds_ratio=0.2):
+        check(self._lib.cratac_fit_speculative_launch(self._h, float(odds_ratio)))
+
+    def fit_tentative(self):
+        """-> the tentative threshold the running fit published, or None when it ended without publishing one."""
+        pub, thr = c_int(), c_i64()
+        check(self._lib.cratac_fit_tentative(self._h, ctypes.byref(pub), ctypes.byref(thr)))
+        return thr.value if pub.value else None
+
+    def speculation_scope(self, on):
+        """-> the stream the library's calls are queued on from now on."""
+        s = ctypes.c_uint64()
+        check(self._lib.cratac_speculation_scope(self._h, 1 if on else 0, ctypes.byref(s)))
+        return s.value
 
     def speculation_stats(self):
         """-> (runs whose speculative peaks + matrix were kept, runs that redid them)."""

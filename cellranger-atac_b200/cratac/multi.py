@@ -129,27 +129,40 @@ def step(shard, torch, dist, device, odds_ratio=0.2, trace=None, gather=False):
         mark("d_all_gather")
         n_cols = shard.union_columns(gathered, counts[:, 0], counts[:, 1], max_b)
         mark("d_union_columns")
-    # 3. threshold, peaks, row bases
+    # 3. peaks, row bases, local CSC over the global columns, per-column totals combined with one all-reduce (the file's
+    #    indptr).  Every rank fits the same histogram, so every rank sees the same tentative threshold a few EM iterations
+    #    into the fit (and the same answer to "was one published at all"): peaks + matrix start from it on the speculation
+    #    stream while the fit -- one CTA -- runs on, and are kept iff the fit ends on that threshold.
+    def peaks_and_matrix(tag):
+        n_peaks = shard.call_peaks()
+        mark(tag + "call_peaks")
+        pk = _all_gather_i64(torch, dist, [n_peaks], device)[:, 0]
+        row_base = int(pk[:rank].sum())
+        total_rows = int(pk.sum())
+        shard.set_row_offset(row_base, total_rows)
+        mark(tag + "row_bases")
+        indptr, indices, data = shard.peak_matrix(n_cols)    # tensors (views) on `device`
+        mark(tag + "peak_matrix")
+        nnz = int(indices.numel())
+        per_col = (indptr[1:] - indptr[:-1]).contiguous()
+        dist.all_reduce(per_col, op=dist.ReduceOp.SUM)
+        indptr_global = torch.zeros(n_cols + 1, dtype=torch.int64, device=device)
+        torch.cumsum(per_col, 0, out=indptr_global[1:])
+        nnz_all = _all_gather_i64(torch, dist, [nnz], device)[:, 0]
+        mark(tag + "column_totals")
+        return n_peaks, row_base, total_rows, indptr, indices, data, nnz, indptr_global, nnz_all
+
+    tentative = shard.fit_tentative()                        # None: the fit published nothing (same on every rank)
+    out = None
+    if tentative is not None:
+        with shard.speculating():
+            out = peaks_and_matrix("spec_")
     threshold, params = shard.fit_result()
     mark("fit_wait")
-    n_peaks = shard.call_peaks()
-    mark("call_peaks")
-    pk = _all_gather_i64(torch, dist, [n_peaks], device)[:, 0]
-    row_base = int(pk[:rank].sum())
-    total_rows = int(pk.sum())
-    shard.set_row_offset(row_base, total_rows)
-    mark("row_bases")
-    # 4. local CSC over the global columns; per-column totals combined with one all-reduce (the file's indptr)
-    indptr, indices, data = shard.peak_matrix(n_cols)        # tensors (views) on `device`
-    mark("peak_matrix")
-    nnz = int(indices.numel())
-    per_col = (indptr[1:] - indptr[:-1]).contiguous()
-    dist.all_reduce(per_col, op=dist.ReduceOp.SUM)
-    indptr_global = torch.zeros(n_cols + 1, dtype=torch.int64, device=device)
-    torch.cumsum(per_col, 0, out=indptr_global[1:])
-    nnz_all = _all_gather_i64(torch, dist, [nnz], device)[:, 0]
+    if out is None or threshold != tentative:
+        out = peaks_and_matrix("")
+    n_peaks, row_base, total_rows, indptr, indices, data, nnz, indptr_global, nnz_all = out
     total_nnz = int(nnz_all.sum())
-    mark("column_totals")
     if gather:
         if rank == 0:
             indptr_all = torch.empty(world * (n_cols + 1), dtype=torch.int64, device=device)
@@ -225,6 +238,7 @@ class CudaShard(object):
         self.text_dev_ptr, self.text_host, self.nbytes = text_dev_ptr, text_host, nbytes
         self.merged = None
         self._side = None
+        self.speculate = True
 
     def check_stream(self):
         """step() queues NCCL collectives on torch's CURRENT stream between the library's kernels: that stream must be the
@@ -251,8 +265,25 @@ class CudaShard(object):
     def fit_launch(self, odds_ratio):
         # the all-reduces were queued by torch on the current stream; the library's stream must be that stream
         self.ctx.compact_histogram()
-        self.ctx.fit_threshold_device(odds_ratio)
+        self.ctx.fit_speculative_launch(odds_ratio)          # queued only; publishes a tentative threshold on its way
         self.ctx.set_option("defer_sync", 0)
+
+    def fit_tentative(self):
+        return self.ctx.fit_tentative() if self.speculate else None
+
+    def speculating(self):
+        """Library calls and torch collectives go to the speculation stream, the peak kernels read the tentative threshold."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            s = self.ctx.speculation_scope(True)
+            try:
+                with self.torch.cuda.stream(self.torch.cuda.ExternalStream(s, device=self.device)):
+                    yield
+            finally:
+                self.ctx.speculation_scope(False)
+        return scope()
 
     def side_stream(self):
         if self._side is None:

@@ -178,7 +178,10 @@ void cratac_destroy(cratac_ctx* h) {
     if (c->bc_thread.joinable()) c->bc_thread.join();
     if (c->h_spec) cudaFreeHost(const_cast<int64_t*>(c->h_spec));
     if (c->spec_stream) cudaStreamDestroy(c->spec_stream);
+    if (c->count_stream) cudaStreamDestroy(c->count_stream);
+    if (c->count_event) cudaEventDestroy(c->count_event);
     if (c->fit_event) cudaEventDestroy(c->fit_event);
+    if (c->spec_done_event) cudaEventDestroy(c->spec_done_event);
     if (c->h_ring) cudaFreeHost(c->h_ring);
     if (c->h_union_hash) cudaFreeHost(c->h_union_hash);
     if (c->h_union_perm) cudaFreeHost(c->h_union_perm);
@@ -211,7 +214,9 @@ int cratac_set_option(cratac_ctx* h, const char* key, int64_t value) {
     if (!strcmp(key, "stream_decode")) { c->stream_decode = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "stream_chunk_tiles")) { c->stream_chunk_tiles = value; return CRATAC_OK; }
     if (!strcmp(key, "py2_device_min")) { c->py2_device_min = value; return CRATAC_OK; }
+    if (!strcmp(key, "union_device_min")) { c->union_device_min = value; return CRATAC_OK; }
     if (!strcmp(key, "decode_kernel")) { c->decode_kernel = (int)value; return CRATAC_OK; }
+    if (!strcmp(key, "decode_pipeline")) { c->decode_pipeline = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "speculate")) { c->speculate = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "spec_iter")) { c->spec_iter = (int)value; return CRATAC_OK; }
     if (!strcmp(key, "file_chunk_bytes")) { c->file_chunk_bytes = value; return CRATAC_OK; }
@@ -800,21 +805,81 @@ static int speculate_peaks_and_matrix(Ctx* c, int* used) {
     return CRATAC_OK;     // an error of the speculative pass is not an error of the run: the pass is redone
 }
 
+// the next fit launched publishes a tentative threshold (stream, event and the host-mapped words are made on first use)
+static int arm_speculation(Ctx* c) {
+    if (!c->spec_stream) {
+        CRATAC_CUDA(cudaStreamCreateWithFlags(&c->spec_stream, cudaStreamNonBlocking));
+        CRATAC_CUDA(cudaEventCreateWithFlags(&c->fit_event, cudaEventDisableTiming));
+        void* hp = nullptr;
+        CRATAC_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+        c->h_spec = reinterpret_cast<volatile int64_t*>(hp);
+        c->h_spec[0] = 0; c->h_spec[1] = 0;
+    }
+    c->spec_seq++;
+    c->spec_armed = true;
+    return CRATAC_OK;
+}
+
+// ---- the same speculation as building blocks (multi-GPU step, cratac/multi.py): every rank fits the same all-reduced
+//      histogram, so the tentative threshold -- and whether one is published at all -- is the same on every rank
+int cratac_fit_speculative_launch(cratac_ctx* h, double odds_ratio) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (c->em_fast < 2) { set_error("speculation needs the register-resident fit kernel (em_fast = 2)"); return CRATAC_ERR_ARG; }
+    CRATAC_TRY(arm_speculation(c));
+    const int rc = fit_threshold_device(c, odds_ratio);
+    c->spec_armed = false;
+    CRATAC_TRY(rc);
+    CRATAC_CUDA(cudaEventRecord(c->fit_event, c->stream));
+    return CRATAC_OK;
+}
+
+// waits for the tentative threshold or for the end of the fit; *published = 1 and *threshold set iff the fit published one
+// (a property of the histogram, not of timing: a fit of fewer than spec_iter iterations publishes none)
+int cratac_fit_tentative(cratac_ctx* h, int* published, int64_t* threshold) {
+    Ctx* c = &h->c;
+    if (!c->fit_event || !published || !threshold) { set_error("cratac_fit_tentative: no speculative fit in flight"); return CRATAC_ERR_ARG; }
+    for (;;) {
+        if (c->h_spec[1] == c->spec_seq) break;
+        const cudaError_t q = cudaEventQuery(c->fit_event);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { set_error("fit failed: %s", cudaGetErrorString(q)); return CRATAC_ERR_CUDA; }
+    }
+    *published = c->h_spec[1] == c->spec_seq ? 1 : 0;
+    *threshold = *published ? c->h_spec[0] : -1;
+    return CRATAC_OK;
+}
+
+// on = 1: the library's calls are queued on the speculation stream and the peak kernels read the tentative threshold;
+// on = 0: back to the context's own stream and the fitted threshold.  *stream_out: the stream now in use.
+int cratac_speculation_scope(cratac_ctx* h, int on, uint64_t* stream_out) {
+    Ctx* c = &h->c;
+    CRATAC_CUDA(cudaSetDevice(c->device));
+    if (on) {
+        if (!c->spec_stream) { set_error("cratac_speculation_scope: no speculative fit was launched"); return CRATAC_ERR_ARG; }
+        if (!c->own_stream_saved) { c->own_stream_saved = c->stream; c->stream = c->spec_stream; }
+        c->thr_slot = ST_THRESHOLD_SPEC;
+        // the column map may still be on its way on the side stream of cratac_union_columns
+        if (c->union_event) CRATAC_CUDA(cudaStreamWaitEvent(c->spec_stream, c->union_event, 0));
+    } else {
+        if (c->own_stream_saved) {
+            // whatever follows on the context's own stream sees the speculative results
+            if (!c->spec_done_event) CRATAC_CUDA(cudaEventCreateWithFlags(&c->spec_done_event, cudaEventDisableTiming));
+            CRATAC_CUDA(cudaEventRecord(c->spec_done_event, c->spec_stream));
+            CRATAC_CUDA(cudaStreamWaitEvent(c->own_stream_saved, c->spec_done_event, 0));
+            c->stream = c->own_stream_saved; c->own_stream_saved = nullptr;
+        }
+        c->thr_slot = ST_THRESHOLD;
+    }
+    if (stream_out) *stream_out = (uint64_t)(uintptr_t)c->stream;
+    return CRATAC_OK;
+}
+
 static int run_tail(Ctx* c, double odds_ratio, cratac_run_result* r) {
     build_barcodes_async(c);
     CRATAC_TRY(window_histogram(c));
-    c->spec_armed = c->speculate && c->em_fast >= 2 && !c->defer_sync;
-    if (c->spec_armed) {
-        if (!c->spec_stream) {
-            CRATAC_CUDA(cudaStreamCreateWithFlags(&c->spec_stream, cudaStreamNonBlocking));
-            CRATAC_CUDA(cudaEventCreateWithFlags(&c->fit_event, cudaEventDisableTiming));
-            void* hp = nullptr;
-            CRATAC_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
-            c->h_spec = reinterpret_cast<volatile int64_t*>(hp);
-            c->h_spec[0] = 0; c->h_spec[1] = 0;
-        }
-        c->spec_seq++;
-    }
+    c->spec_armed = false;
+    if (c->speculate && c->em_fast >= 2 && !c->defer_sync) CRATAC_TRY(arm_speculation(c));
     CRATAC_TRY(fit_threshold_device(c, odds_ratio));
     int used = 0;
     if (c->spec_armed) {

@@ -120,6 +120,8 @@ struct Ctx {
     cudaEvent_t bc_event = nullptr;
     const long long* d_hash_first = nullptr;   // device copies of the two mirrors above (inside d_bc_bitmap)
     const int32_t* d_order_first = nullptr;
+    int64_t union_device_min = 20000;      // option "union_device_min": same for the union of the shards' barcodes (multi.cu), where the host
+                                           // simulation would be the critical path of the step
     int64_t py2_device_min = 300000;       // option "py2_device_min": from this many barcodes on, the column order is worked out on the device
     std::vector<int32_t> h_c2d;
     bool bc_strings_ready = false;
@@ -182,6 +184,9 @@ struct Ctx {
     int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
     cudaStream_t copy_stream = nullptr;    // chunked H2D of a host text (decode_text_streamed)
     cudaEvent_t copy_event = nullptr;
+    cudaStream_t count_stream = nullptr;   // high priority: newline counts + scans of the next chunk under the parse of the current one
+    cudaEvent_t count_event = nullptr;
+    int decode_pipeline = 1;               // option "decode_pipeline": device-resident texts of 64 MiB and more are decoded chunk by chunk on two streams
     DevBuf d_stream_scalars;               // running line base + chunk total of the streamed decode
     // single-pass decode (k_parse_stream): look-back words per tile, {ticket, declined ranges, line base}, declined ranges
     DevBuf d_sp_state, d_sp_scalars, d_sp_irr;
@@ -201,7 +206,9 @@ struct Ctx {
     int spec_iter = 32;                    // option "spec_iter": EM iteration after which the tentative threshold is published
     int thr_slot = ST_THRESHOLD;           // status slot the peak kernels read their threshold from
     cudaStream_t spec_stream = nullptr;
+    cudaStream_t own_stream_saved = nullptr;   // the context's stream while cratac_speculation_scope(1) is in force
     cudaEvent_t fit_event = nullptr;
+    cudaEvent_t spec_done_event = nullptr;
     volatile int64_t* h_spec = nullptr;    // pinned + mapped: {tentative threshold, sequence number} written by the fit kernel
     int64_t spec_seq = 0;
     bool spec_armed = false;               // the fit being launched publishes a tentative threshold

@@ -1239,12 +1239,29 @@ static int decode_error(Ctx* c, int64_t err) {
 }
 
 static int decode_text_two_pass(Ctx* c, const char* d_text, int64_t nbytes);
+static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes, const char* d_resident);
 
 // Device text -> fragments in ONE pass over the text (k_parse_stream): the number of lines is not known in advance, so the
 // output arrays are sized from an estimate (a fragments.tsv line is rarely under 24 bytes); when that or the barcode table
 // does not hold, the table grows and / or the exact two-pass path takes over.
 int decode_text(Ctx* c, const char* d_text, int64_t nbytes) {
-    if (c->decode_kernel == 0) return decode_text_two_pass(c, d_text, nbytes);
+    if (c->decode_kernel == 0) {
+        if (nbytes > 0 && (c->decode_pipeline == 2 || (c->decode_pipeline == 1 && nbytes >= ((int64_t)64 << 20)))) {
+            // large text: count passes of the next chunk under the parse of the current one
+            struct ResidentText : HostTextSource {
+                char last;
+                char last_byte() override { return last; }
+                const char* acquire(int64_t, int64_t) override { return nullptr; }
+                int queued(int64_t, int64_t, cudaStream_t) override { return CRATAC_OK; }
+            } src;
+            src.last = '\n';
+            CRATAC_CUDA(cudaMemcpyAsync(&src.last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+            CRATAC_CUDA(cudaStreamSynchronize(c->stream));
+            const int rc = decode_text_streamed_two_pass(c, &src, nbytes, 0, d_text);
+            if (rc != CRATAC_ERR_CAPACITY) return rc;       // estimate or table too small: the exact path below
+        }
+        return decode_text_two_pass(c, d_text, nbytes);
+    }
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     c->d_text = d_text;
     c->text_bytes = nbytes;
@@ -1408,7 +1425,7 @@ __global__ void k_add_i64(int64_t* __restrict__ acc, const int64_t* __restrict__
 // has arrived, while the next chunk is in flight.  The number of lines is not known before the last chunk, so the output
 // arrays are sized from an estimate; returns CRATAC_ERR_CAPACITY when anything did not fit (table or estimate) -- the
 // caller then falls back to copy-all-then-decode.
-static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes);
+static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes, const char* d_resident);
 
 namespace {
 struct PlainHostText : HostTextSource {
@@ -1434,7 +1451,7 @@ int decode_text_streamed(Ctx* c, const char* h_text, int64_t nbytes) {
 
 // Same with the single-pass kernel: one k_parse_stream launch per chunk, the running line base stays on the device.
 int decode_text_streamed_from(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes_arg) {
-    if (c->decode_kernel == 0) return decode_text_streamed_two_pass(c, src, nbytes, chunk_bytes_arg);
+    if (c->decode_kernel == 0) return decode_text_streamed_two_pass(c, src, nbytes, chunk_bytes_arg, nullptr);
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
     CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
     char* d_text = c->d_text_own.as<char>();
@@ -1520,10 +1537,13 @@ int decode_text_streamed_from(Ctx* c, HostTextSource* src, int64_t nbytes, int64
     return barcode_prepare_device(c);
 }
 
-static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes_arg) {
+// Chunk by chunk on two streams: the newline count + scan of chunk k + 1 (HBM-bound, a high-priority side stream) run
+// under the parse of chunk k (issue-bound, the context's stream); for a host text the H2D copy of the chunk comes first.
+// d_resident: the text is already in HBM at this address (no copies, src is only asked for the last byte).
+static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nbytes, int64_t chunk_bytes_arg, const char* d_resident) {
     if (c->contig_table_cap == 0) CRATAC_TRY(build_contig_table(c));
-    CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
-    char* d_text = c->d_text_own.as<char>();
+    if (!d_resident) CRATAC_TRY(c->d_text_own.reserve((size_t)nbytes + 16));
+    char* d_text = d_resident ? const_cast<char*>(d_resident) : c->d_text_own.as<char>();
     c->d_text = d_text;
     c->text_bytes = nbytes;
     c->bc_ready = false;
@@ -1550,9 +1570,18 @@ static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nb
     CRATAC_TRY(c->d_bc_textoff.reserve(8 * cap)); CRATAC_TRY(c->d_slot_to_dense.reserve(4 * cap));
     CRATAC_TRY(c->d_bc_nfrag.reserve(4 * cap));
     CRATAC_CUDA(cudaMemsetAsync(c->d_bc_nfrag.p, 0, 4 * cap, c->stream));
-    CRATAC_TRY(c->d_stream_scalars.reserve(64));
+    const int64_t CHUNK_TILES = chunk_bytes_arg > 0 ? std::max<int64_t>(chunk_bytes_arg / DEC_TILE, 1)
+                                                    : (c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles : (int64_t)(128 << 20) / DEC_TILE);   // default: 128 MiB of text per chunk
+    const int64_t n_chunks = (n_tiles + CHUNK_TILES - 1) / CHUNK_TILES;
+    CRATAC_TRY(c->d_stream_scalars.reserve(8 * (size_t)(n_chunks + 4)));
     int64_t* line_base = c->d_stream_scalars.as<int64_t>();
-    int64_t* chunk_total = line_base + 1;
+    int64_t* chunk_totals = line_base + 2;                   // one word per chunk: the counts run ahead of the parses
+    if (!c->count_stream) {
+        int lo = 0, hi = 0;
+        CRATAC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CRATAC_CUDA(cudaStreamCreateWithPriority(&c->count_stream, cudaStreamNonBlocking, hi));
+        CRATAC_CUDA(cudaEventCreateWithFlags(&c->count_event, cudaEventDisableTiming));
+    }
     k_init_table<<<(unsigned)((cap + 255) / 256), 256, 0, c->stream>>>(c->d_bc_keys.as<BcSlot>(), (int)cap);
     c->launches++;
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
@@ -1569,26 +1598,36 @@ static int decode_text_streamed_two_pass(Ctx* c, HostTextSource* src, int64_t nb
     a.status = st;
     a.use_tma = ((reinterpret_cast<uintptr_t>(d_text) & 15) == 0) ? 1 : 0;
     a.line_base = line_base; a.line_cap = line_cap; a.irr = nullptr;
-    const int64_t CHUNK_TILES = chunk_bytes_arg > 0 ? std::max<int64_t>(chunk_bytes_arg / DEC_TILE, 1)
-                                                    : (c->stream_chunk_tiles > 0 ? c->stream_chunk_tiles : (int64_t)(128 << 20) / DEC_TILE);   // default: 128 MiB of text per chunk
     c->stage_begin(SG_DECODE_PARSE);
-    for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES) {
+    // the side stream starts where the context's stream stands now (whatever produced the text, the table reset above)
+    CRATAC_CUDA(cudaEventRecord(c->count_event, c->stream));
+    CRATAC_CUDA(cudaStreamWaitEvent(c->count_stream, c->count_event, 0));
+    cudaStream_t own = c->stream;
+    int64_t k = 0;
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += CHUNK_TILES, k++) {
         const int64_t t1 = std::min(n_tiles, t0 + CHUNK_TILES);
         const int64_t b0 = t0 * DEC_TILE, b1 = std::min(nbytes, t1 * DEC_TILE);
-        if (b1 > b0) {
-            const char* hp = src->acquire(b0, b1);
-            if (!hp) return CRATAC_ERR_IO;
-            CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, hp, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
-            CRATAC_TRY(src->queued(b0, b1, c->copy_stream));
+        if (!d_resident) {
+            if (b1 > b0) {
+                const char* hp = src->acquire(b0, b1);
+                if (!hp) return CRATAC_ERR_IO;
+                CRATAC_CUDA(cudaMemcpyAsync(d_text + b0, hp, (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+                CRATAC_TRY(src->queued(b0, b1, c->copy_stream));
+            }
+            CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
+            CRATAC_CUDA(cudaStreamWaitEvent(c->count_stream, c->copy_event, 0));
         }
-        CRATAC_CUDA(cudaEventRecord(c->copy_event, c->copy_stream));
-        CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->copy_event, 0));
         const unsigned nt = (unsigned)(t1 - t0);
-        k_count_newlines<<<nt, 256, 0, c->stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), t0, DEC_TILE);
-        CRATAC_TRY(exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>() + t0, c->d_tile_offsets.as<int64_t>() + t0, t1 - t0, chunk_total));
+        k_count_newlines<<<nt, 256, 0, c->count_stream>>>(d_text, nbytes, n_eff, c->d_tile_counts.as<int32_t>(), t0, DEC_TILE);
+        c->stream = c->count_stream;                        // the scan helper queues on the context's current stream
+        const int rc_scan = exclusive_scan_i32_to_i64(c, c->d_tile_counts.as<int32_t>() + t0, c->d_tile_offsets.as<int64_t>() + t0, t1 - t0, chunk_totals + k);
+        c->stream = own;
+        CRATAC_TRY(rc_scan);
+        CRATAC_CUDA(cudaEventRecord(c->count_event, c->count_stream));
+        CRATAC_CUDA(cudaStreamWaitEvent(c->stream, c->count_event, 0));      // (captures this record: the event is recorded again for the next chunk)
         a.tile0 = t0;
         k_parse_tiles<<<nt, DEC_THREADS, 0, c->stream>>>(a);
-        k_add_i64<<<1, 1, 0, c->stream>>>(line_base, chunk_total);
+        k_add_i64<<<1, 1, 0, c->stream>>>(line_base, chunk_totals + k);
         c->launches += 3;
         CRATAC_CUDA(cudaGetLastError());
     }

@@ -194,7 +194,7 @@ int union_columns(Ctx* c, int world, int64_t max_b, const int64_t* d_gathered, c
         CRATAC_CUDA(cudaGetLastError());
         const int32_t* rank_of_col = nullptr;
         if (c->bc_order == CRATAC_BC_ORDER_PY2SET) {
-            if (n_cols >= c->py2_device_min) {
+            if (n_cols >= c->union_device_min) {
                 CRATAC_TRY(py2_set_order_device(c, n_cols, reinterpret_cast<const int64_t*>(hash_by_rank), perm));
             } else {
                 // host simulation of the set (sequential, ~50 ns per key): runs while the GPU is busy with the fit

@@ -220,6 +220,13 @@ int cratac_counts_by_barcode(cratac_ctx* ctx, const int64_t* track_off, const in
  * the speculative result is kept only when the fit ends on the same threshold, otherwise both are done again (option
  * "speculate" = 0 switches this off).  Counters since creation: runs whose speculative result was kept / redone. */
 int cratac_speculation_stats(cratac_ctx* ctx, int64_t* kept, int64_t* redone);
+/* The same as building blocks for the multi-GPU step (every rank fits the same all-reduced histogram, so all ranks see the
+ * same tentative threshold): launch the fit so that it publishes one; wait for it (published = 0 when the fit ended before
+ * its spec_iter-th iteration -- then there is nothing to speculate on, on any rank); route the library's calls to the
+ * speculation stream with the tentative threshold (on = 1) and back (on = 0). */
+int cratac_fit_speculative_launch(cratac_ctx* ctx, double odds_ratio);
+int cratac_fit_tentative(cratac_ctx* ctx, int* published, int64_t* threshold);
+int cratac_speculation_scope(cratac_ctx* ctx, int on, uint64_t* stream_out);
 /* fragments.tsv.gz (BGZF; plain gzip and plain text are read too) -> fragments in HBM.  Replaces, for the whole file, the
  * `gzip -c -d` pipe of lib/python/tools/io.py:197-217 and the per-line split of :75-92: `threads` host threads (0: all
  * cores) inflate the BGZF blocks with the library's own DEFLATE decoder (CRC-32 checked) into a ring of pinned chunks

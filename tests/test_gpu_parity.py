@@ -628,6 +628,15 @@ def test_single_pass_decode_clean_text_takes_no_fallback(kernel):
             assert _decode_and_compare(ctx, tail, names, host=host) == 400000
             assert ctx.decode_declined() == 0
             ctx.close()
+    if kernel == 0:
+        # device-resident text decoded chunk by chunk on two streams (count + scan of chunk k + 1 under the parse of chunk k);
+        # chunks of 3 tiles so that lines and line numbers cross hundreds of chunk borders
+        for tail in (text, text[:-1]):
+            ctx = _ffi.Context(contigs)
+            ctx.set_option("decode_pipeline", 2)
+            ctx.set_option("stream_chunk_tiles", 3)
+            assert _decode_and_compare(ctx, tail, names, host=False) == 400000
+            ctx.close()
 
 
 @pytest.mark.parametrize("kernel", [1, 2])

@@ -61,6 +61,9 @@ class OracleShard(object):
     def fit_launch(self, odds):
         self.odds = odds
 
+    def fit_tentative(self):
+        return None                 # the CPU backend does not speculate
+
     def side_stream(self):
         import contextlib
         return contextlib.nullcontext()
