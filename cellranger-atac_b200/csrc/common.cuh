@@ -186,7 +186,8 @@ struct Ctx {
     cudaEvent_t copy_event = nullptr;
     cudaStream_t count_stream = nullptr;   // high priority: newline counts + scans of the next chunk under the parse of the current one
     cudaEvent_t count_event = nullptr;
-    int decode_pipeline = 1;               // option "decode_pipeline": device-resident texts of 64 MiB and more are decoded chunk by chunk on two streams
+    int decode_pipeline = 0;               // option "decode_pipeline": 1 = device-resident texts of 64 MiB and more are decoded chunk by chunk on two
+                                           // streams (2: any size); measured slower than one count + one parse launch: off
     DevBuf d_stream_scalars;               // running line base + chunk total of the streamed decode
     // single-pass decode (k_parse_stream): look-back words per tile, {ticket, declined ranges, line base}, declined ranges
     DevBuf d_sp_state, d_sp_scalars, d_sp_irr;
