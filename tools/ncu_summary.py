@@ -33,7 +33,8 @@ def launches(src, dst):
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += v
-    ours = {k: v for k, v in agg.items() if "cratac::" in k}
+    # libcratac's kernels: "cratac::k_..." in a full launch list, bare "k_..." when the capture was filtered with -k regex:^k_
+    ours = {k: v for k, v in agg.items() if "cratac::" in k or k.startswith("k_") or k.startswith("void k_")}
     tot = sum(v[1] for v in ours.values())
     with open(dst, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: libcratac kernels only (torch data-generation kernels dropped)\n")
