@@ -216,11 +216,16 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
     unsigned long long mask = 0, tmask = 0;
     {
         const int c0 = DEC_LOOKBACK / 16 + tid * (PER_THREAD / 16);
+        // a thread's four chunks are 64 bytes apart from its neighbour's: taken in the same order by every lane, the eight
+        // lanes of a quarter-warp would meet in two groups of banks (16-way conflicts, measured: 46 % of the kernel's
+        // shared-memory wavefronts).  Rotating the order by lane / 2 spreads a quarter-warp over all 32 banks.
+        const int rot = (lane >> 1) & 3;
 #pragma unroll
         for (int k = 0; k < PER_THREAD / 16; k++) {
-            const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * (c0 + k));
-            mask |= (unsigned long long)swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) << (16 * k);
-            tmask |= (unsigned long long)swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << (16 * k);
+            const int kk = (k + rot) & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * (c0 + kk));
+            mask |= (unsigned long long)swar_eqmask16(v.x, v.y, v.z, v.w, 0x0a0a0a0au) << (16 * kk);
+            tmask |= (unsigned long long)swar_eqmask16(v.x, v.y, v.z, v.w, 0x09090909u) << (16 * kk);
         }
         if (tid < DEC_LOOKBACK / 16) {
             const uint4 v = *reinterpret_cast<const uint4*>(words + 4 * tid);
@@ -504,13 +509,13 @@ __device__ __forceinline__ bool sp_parse_uint(const uint32_t* words, int p, int 
     return bad == 0u;
 }
 
-template <int CPT, bool PROF>
-__global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
+template <int CPT, bool PROF, int MINB>
+__global__ void __launch_bounds__(SP_THREADS, MINB) k_parse_stream(StreamArgs a) {
     constexpr int REGION_MAX = SP_THREADS * CPT * 16;              // look-back + tile bytes
     constexpr int MAX_SEPS = REGION_MAX / 6;                       // 5 separators per line of >= 30 bytes (typical: 45)
     extern __shared__ __align__(128) unsigned char sp_smem[];
     uint32_t* bufw0 = reinterpret_cast<uint32_t*>(sp_smem);
-    uint32_t* bufw1 = bufw0 + (SP_PAD + REGION_MAX + SP_PAD) / 4;
+    uint32_t* bufw1 = (a.mode & 4) ? bufw0 : bufw0 + (SP_PAD + REGION_MAX + SP_PAD) / 4;            // one-tile mode: a single buffer
     uint16_t* seplist = reinterpret_cast<uint16_t*>(bufw1 + (SP_PAD + REGION_MAX + SP_PAD) / 4);   // [MAX_SEPS]
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int warp_tot[SP_THREADS / 32];
@@ -540,6 +545,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         tma_load_1d(reinterpret_cast<unsigned char*>(w) + SP_PAD, d.text + (t + a.tile0) * TB - SP_LB, (uint32_t)region, &bar[b]);
     };
     auto next_tile = [&](int64_t prev) -> int64_t {   // thread 0; prev < 0: the CTA's first tile
+        if (a.mode & 4) return prev < 0 ? (int64_t)blockIdx.x : a.n_tiles;          // one tile per CTA (grid = tiles): no prefetch, one buffer
         if (a.mode & 2) return prev < 0 ? (int64_t)blockIdx.x : prev + gridDim.x;   // no tile waits on another: static round-robin
         return (int64_t)atomicAdd(a.ticket, 1ULL);
     };
@@ -594,7 +600,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
         for (int q = 0; q < CPT / 4; q++) {
             unsigned long long m64 = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k0 = 0; k0 < 4; k0++) {
+                const int k = (k0 + ((lane >> 1) & 3)) & 3;          // rotated per lane: a quarter-warp's 128-bit loads cover all banks
                 const int c = tid * CPT + 4 * q + k;
                 uint32_t m = 0;
                 if (c < n_chunks) {
@@ -788,12 +795,17 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
             int32_t v_start = 0, v_end = 0, v_dup = 0, cid = -1;
             unsigned long long key = 0;
             int bc_pos = 0, bc_len = 0;
+            unsigned pre_slot = 0;
+            ulonglong2 pre = make_ulonglong2(0ULL, 0ULL);
             if (li < n_lines) {
                 const int k = first + 5 * li;
                 const int b = seplist[k - 1] + 1;
                 const int t0 = seplist[k], t1 = seplist[k + 1], t2 = seplist[k + 2], t3 = seplist[k + 3], e = seplist[k + 4];
                 bc_pos = t2 + 1; bc_len = t3 - t2 - 1;
                 key = barcode_key_words(words, bc_pos, bc_len);
+                // the barcode's table slot (a random 16-byte access) is requested now: it arrives while the numbers parse
+                pre_slot = (unsigned)(mix64(key)) & (unsigned)d.bc_mask;
+                pre = *reinterpret_cast<const ulonglong2*>(&d.bc_tab[pre_slot]);
                 ok = sp_parse_uint(words, t0 + 1, t1, &v_start) & sp_parse_uint(words, t1 + 1, t2, &v_end) & (t0 > b) & (bc_len > 0);
                 {                                                    // the duplicate count is a single digit nearly always
                     const int dl = e - t3 - 1;
@@ -844,12 +856,13 @@ __global__ void __launch_bounds__(SP_THREADS) k_parse_stream(StreamArgs a) {
                 if (d.line_cap > 0 && line_no >= d.line_cap) {
                     raise_error(d.status, CRATAC_ERR_CAPACITY, -7);  // more lines than estimated
                 } else {
-                    unsigned slot = (unsigned)(mix64(key)) & (unsigned)d.bc_mask;
+                    unsigned slot = pre_slot;
                     int probes = 0;
                     bool placed = false;
                     unsigned long long seen_first = 0xFFFFFFFFFFFFFFFFULL;
                     while (probes <= d.bc_mask) {
-                        const ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&d.bc_tab[slot]);
+                        // a key never changes once written, so the early read is final when it shows our key; anything else is re-checked
+                        const ulonglong2 sl = probes == 0 ? pre : *reinterpret_cast<const ulonglong2*>(&d.bc_tab[slot]);
                         unsigned long long kk = sl.x;
                         seen_first = sl.y;
                         if (kk == BC_EMPTY) {
@@ -1186,15 +1199,17 @@ static int sp_launch(Ctx* c, const DecodeArgs& base, int64_t tile0, int64_t n_ti
     }
     CRATAC_CUDA(cudaMemsetAsync(a.state, 0, 8 * (size_t)n_tiles, c->stream));
     CRATAC_CUDA(cudaMemsetAsync(a.ticket, 0, 8, c->stream));
-    const size_t smem = sp_smem_bytes(cpt);
-    void (*kern)(StreamArgs) = cpt == 8 ? (a.prof ? k_parse_stream<8, true> : k_parse_stream<8, false>)
-                                        : (a.prof ? k_parse_stream<4, true> : k_parse_stream<4, false>);
+    const bool one_tile = (a.mode & 4) != 0;
+    const size_t smem = sp_smem_bytes(cpt) - (one_tile ? (SP_PAD + (size_t)SP_THREADS * cpt * 16 + SP_PAD) : 0);
+    void (*kern)(StreamArgs) = one_tile ? (cpt == 8 ? k_parse_stream<8, false, 3> : k_parse_stream<4, false, 6>)
+                                        : cpt == 8 ? (a.prof ? k_parse_stream<8, true, 2> : k_parse_stream<8, false, 2>)
+                                                   : (a.prof ? k_parse_stream<4, true, 4> : k_parse_stream<4, false, 5>);
     CRATAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CRATAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SP_THREADS, smem));
     if (per_sm < 1) { set_error("k_parse_stream does not fit on an SM"); return CRATAC_ERR_INTERNAL; }
     if (c->sp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->sp_ctas_per_sm);
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)NUM_SMS * per_sm);   // every CTA resident: tiles wait on earlier tiles
+    const unsigned grid = one_tile ? (unsigned)n_tiles : (unsigned)std::min<int64_t>(n_tiles, (int64_t)NUM_SMS * per_sm);   // persistent: every CTA resident, tiles wait on earlier tiles
     kern<<<grid, SP_THREADS, smem, c->stream>>>(a);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());

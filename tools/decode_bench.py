@@ -30,8 +30,8 @@ def main():
     ctx.set_option("profile", 1)
     text, nbytes, _n = bench.make_workload(torch, ctx, contigs, args.fragments, args.cells, 100000, 2, device)
     peak = bench.measured_peaks()[0]
-    # (decode_kernel, decode_mode): mode bit 0 = ticket taken at tile start (no prefetch), bit 1 = line numbers from a count pass
-    variants = [(0, 0), (1, 1), (1, 2)]
+    # (decode_kernel, decode_mode): mode bit 0 = ticket taken at tile start (no prefetch), bit 1 = line numbers from a count pass, bit 2 = one tile per CTA
+    variants = [(0, 0), (1, 1), (1, 2), (1, 6), (2, 6)]
     for kernel, mode in variants:
         ctx.set_option("decode_kernel", kernel)
         ctx.set_option("decode_mode", mode)
@@ -50,7 +50,7 @@ def main():
                           "algorithmic_gbs": round(alg / 1e9 / (ms / 1e3), 1), "frac_of_measured_hbm": round(alg / 1e9 / (ms / 1e3) / peak, 3),
                           "declined_ranges": ctx.decode_declined(reset=True)}), flush=True)
     # where the single-pass kernel's time goes: cycles per phase and tile (one thread's clock per CTA)
-    for kernel, mode in ((1, 1), (1, 0)):
+    for kernel, mode in ((1, 2),):
         ctx.set_option("decode_kernel", kernel)
         ctx.set_option("decode_mode", mode)
         ctx.set_option("decode_profile", 1)
