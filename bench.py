@@ -555,6 +555,11 @@ def main():
                                                 "slowest_step_phases": slow_trace[1] if slow_trace else None})
     total_frags = args.steps * args.fragments
     value = total_frags / (dev_ms / 1000.0)
+    free_b, total_b = torch.cuda.mem_get_info(device)
+    hbm_used = torch.tensor([(total_b - free_b) / 1e9], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(hbm_used, op=dist.ReduceOp.MAX)
+    hbm_used_gb = float(hbm_used.item())      # per GPU, largest over the ranks: text + SoA + matrix buffers + the generator's leftovers
 
     # ---- checksum of the result (outside the timed region): equal for every --gpus N on the same library
     checksum = None
@@ -714,7 +719,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload_config(args),
-            "clocks": clocks, "e2e": e2e, "e2e_file": e2e_file, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "e2e": e2e, "e2e_file": e2e_file, "hbm_used_gb_per_gpu_max": hbm_used_gb, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": kernels, "filter_peak_matrix": filter_info, "em_fit_ms": em_ms, "em_iterations": int(res.em_iterations), "em_inner_iterations": int(res.em_inner_iterations),
             "result": {"n_fragments": int(res.n_fragments), "n_fragments_rank0": int(n_frag_r0), "n_barcodes": int(res.n_barcodes),
                        "threshold": int(res.threshold), "n_peaks": int(res.n_peaks), "n_peaks_rank0": int(n_peaks_r0), "nnz": int(res.nnz),
