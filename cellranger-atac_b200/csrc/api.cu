@@ -171,7 +171,7 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc,
                       &c->d_union, &c->d_col_keys, &c->d_sp_state, &c->d_sp_scalars, &c->d_sp_irr,
                       &c->d_bg_W, &c->d_bg_tiles, &c->d_bg_start, &c->d_bg_end, &c->d_bg_count,
-                      &c->d_sib_perm, &c->d_sib_seg, &c->d_sib_tmp, &c->d_sib_hist};
+                      &c->d_sib_perm, &c->d_sib_seg, &c->d_sib_tmp, &c->d_sib_hist, &c->d_slot_seg};
     for (DevBuf* b : bufs) b->release();
     if (c->h_status) cudaFreeHost(c->h_status);
     if (c->h_sp_scalars) cudaFreeHost(c->h_sp_scalars);

@@ -151,6 +151,7 @@ struct Ctx {
     bool peaks_on_device_count = false;    // n_peaks lives in d_status[ST_N_PEAKS] until fetched
     // matrix
     DevBuf d_bc_hits, d_seg_off, d_cursor, d_hits, d_out_row, d_out_cnt, d_nnz_col;
+    DevBuf d_slot_seg;                     // segment offsets and cursors indexed by hash-table slot + dense id -> slot (overlap pass after a decode)
     DevBuf d_indptr, d_indices, d_data;
     DevBuf d_sel_indptr, d_sel_indices, d_sel_data, d_sel_kept, d_sel_scratch;   // result of select_columns (FILTER_PEAK_MATRIX)
     int64_t n_sel_cols = 0, sel_nnz = 0;

@@ -403,9 +403,10 @@ __global__ void __launch_bounds__(DEC_THREADS) k_parse_tiles(DecodeArgs a) {
 // [t * TB, (t + 1) * TB) with SP_LB look-back bytes in front of it; a line belongs to the tile that holds its '\n'.
 //
 //  1. separator bits (bytes below 0x0b: tab, newline and, never in a valid file, 0x00-0x08) of every 16-byte chunk, three
-//     integer instructions per word and one multiply to gather four flags; chunks are dealt round-robin to the threads
-//     (conflict-free 128-bit shared loads) and the 16-bit masks go through shared memory so that
-//  2. thread i owns the masks of CPT consecutive chunks: popcounts -> block scan -> ONE ordered list of separator positions.
+//     integer instructions per word and one multiply to gather four flags.  Thread i reads its own CPT consecutive chunks
+//     (the chunk order is rotated by lane so the 128-bit shared loads of a quarter-warp fall in different banks) and the
+//     16-bit masks stay in its registers;
+//  2. popcounts of those masks -> block scan -> ONE ordered list of separator positions in shared memory.
 //     In a well-formed tile the separators of a line are five consecutive entries (four tabs, the newline) and the entry
 //     before them is the previous line's newline.  The five bytes are checked per line (and the tabs of the unfinished last
 //     line), so the structure is not assumed but verified; the look-back gives the number of tabs of the first line that lie

@@ -118,40 +118,78 @@ __global__ void __launch_bounds__(MX_THREADS) k_overlap(OverlapArgs a) {
             }
         }
         __syncthreads();
-        for (int64_t i = i0 + threadIdx.x; i < i1; i += MX_THREADS) {
-            int b = a.bc[i];
-            if (a.slot_to_dense) b = a.slot_to_dense[b];
-            int r0, r1;
-            if (w >= 0) {
-                int pos[2] = {a.start[i], a.end[i]};
-                int r[2];
+        // two fragments per thread and round: their bisections interleave and both cursor atomics are in flight together
+        // (the kernel waits on returning L2 atomics: 24 % issue at full occupancy, profiles/r02e_kernels_full_250m.csv)
+        for (int64_t ia = i0 + threadIdx.x; ia < i1; ia += 2 * MX_THREADS) {
+            int64_t idx[2] = {ia, ia + MX_THREADS};
+            int b[2], r0[2], r1[2];
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    int lo = 0, hi = w;                   // first staged start > pos
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (pos[q] < s_start[mid]) hi = mid; else lo = mid + 1; }
-                    r[q] = (lo > 0 && pos[q] < s_end[lo - 1]) ? s_row[lo - 1] : -1;
+            for (int u = 0; u < 2; u++) {
+                b[u] = -1; r0[u] = -1; r1[u] = -1;
+                const int64_t i = idx[u];
+                if (i >= i1) continue;
+                b[u] = a.bc[i];                               // table slot or dense id: the cursors are indexed by whichever it is
+                if (w >= 0) {
+                    int pos[2] = {a.start[i], a.end[i]};
+                    int r[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        int lo = 0, hi = w;                   // first staged start > pos
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (pos[q] < s_start[mid]) hi = mid; else lo = mid + 1; }
+                        r[q] = (lo > 0 && pos[q] < s_end[lo - 1]) ? s_row[lo - 1] : -1;
+                    }
+                    r0[u] = r[0]; r1[u] = r[1];
+                } else {
+                    const int c = a.chrom[i];
+                    r0[u] = find_peak(a, c, a.start[i]);
+                    r1[u] = find_peak(a, c, a.end[i]);
                 }
-                r0 = r[0]; r1 = r[1];
-            } else {
-                const int c = a.chrom[i];
-                r0 = find_peak(a, c, a.start[i]);
-                r1 = find_peak(a, c, a.end[i]);
             }
             // one record per (fragment, peak): value = row << 1 | (both ends in that peak).  Most fragments that hit
             // a peak lie inside it, so this nearly halves the scattered 4-byte stores that bound the scatter pass.
-            const bool same = r0 >= 0 && r1 == r0;
-            const int nrec = (r0 >= 0) + (r1 >= 0 && !same);
-            if (nrec == 0 || b < 0) continue;
-            my_hits += (r0 >= 0) + (r1 >= 0);
-            unsigned int p = atomicAdd(&a.cursor[b], (unsigned)nrec);
-            int64_t o = a.seg_off[b] + p;
-            if (r0 >= 0) a.hits[o++] = (r0 << 1) | (int)same;
-            if (r1 >= 0 && !same) a.hits[o] = r1 << 1;
+            bool same[2];
+            int nrec[2];
+            unsigned int p[2] = {0, 0};
+            int64_t so[2] = {0, 0};
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                same[u] = r0[u] >= 0 && r1[u] == r0[u];
+                nrec[u] = (r0[u] >= 0) + (r1[u] >= 0 && !same[u]);
+                if (b[u] < 0) nrec[u] = 0;
+                if (nrec[u]) {
+                    my_hits += (r0[u] >= 0) + (r1[u] >= 0);
+                    p[u] = atomicAdd(&a.cursor[b[u]], (unsigned)nrec[u]);
+                    so[u] = a.seg_off[b[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!nrec[u]) continue;
+                int64_t o = so[u] + p[u];
+                if (r0[u] >= 0) a.hits[o++] = (r0[u] << 1) | (int)same[u];
+                if (r1[u] >= 0 && !same[u]) a.hits[o] = r1[u] << 1;
+            }
         }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
     if ((threadIdx.x & 31) == 0 && my_hits) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_hits), (unsigned long long)my_hits);
+}
+
+// the overlap kernel indexes cursors and segment offsets by what bc[] holds.  After a decode that is the barcode's hash-table
+// slot: mapping it to the dense id first would put one more dependent L2 access in front of every cursor atomic.
+__global__ void k_slot_segments(const int32_t* __restrict__ slot_to_dense, int cap, const int64_t* __restrict__ seg_off, int64_t* __restrict__ slot_seg_off,
+                                int32_t* __restrict__ dense_slot) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cap) return;
+    const int d = slot_to_dense[s];
+    if (d < 0) return;
+    slot_seg_off[s] = seg_off[d];
+    dense_slot[d] = s;
+}
+__global__ void k_slot_cursors(const unsigned int* __restrict__ slot_cursor, const int32_t* __restrict__ dense_slot, int64_t nb, unsigned int* __restrict__ cursor) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < nb) cursor[d] = slot_cursor[dense_slot[d]];
 }
 
 // segment capacities: a barcode with f fragments has at most 2 f hit records
@@ -532,17 +570,36 @@ int peak_matrix_hits(Ctx* c) {
     CRATAC_TRY(c->d_hits.reserve(4 * kk)); CRATAC_TRY(c->d_out_row.reserve(4 * kk)); CRATAC_TRY(c->d_out_cnt.reserve(4 * kk));
     OverlapArgs a;
     a.n = n; a.chrom = c->d_chrom.as<int32_t>(); a.start = c->d_start.as<int32_t>(); a.end = c->d_end.as<int32_t>(); a.bc = c->d_bc.as<int32_t>();
-    a.slot_to_dense = c->bc_is_slot ? c->d_slot_to_dense.as<int32_t>() : nullptr;
+    a.slot_to_dense = nullptr;
     a.peak_off = c->d_peak_off.as<int64_t>();
     a.pk_start = c->d_peak_start.as<int32_t>(); a.pk_end = c->d_peak_end.as<int32_t>(); a.pk_row = c->d_peak_row.as<int32_t>();
     a.maxpos = c->h_status[ST_MAX_POS_LEN]; a.maxneg = c->h_status[ST_MAX_NEG_LEN];
     a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>(); a.hits = c->d_hits.as<int32_t>();
     a.n_hits = &st[ST_N_HITS];
+    const bool by_slot = c->bc_is_slot && nb > 0;
+    if (by_slot) {
+        const size_t cap = (size_t)c->bc_table_cap;
+        CRATAC_TRY(c->d_slot_seg.reserve(8 * cap + 4 * cap + 4 * nbb));
+        int64_t* slot_seg_off = c->d_slot_seg.as<int64_t>();
+        unsigned int* slot_cursor = reinterpret_cast<unsigned int*>(slot_seg_off + cap);
+        int32_t* dense_slot = reinterpret_cast<int32_t*>(slot_cursor + cap);
+        CRATAC_CUDA(cudaMemsetAsync(slot_cursor, 0, 4 * cap, s));
+        k_slot_segments<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(c->d_slot_to_dense.as<int32_t>(), (int)cap, a.seg_off, slot_seg_off, dense_slot);
+        c->launches++;
+        a.seg_off = slot_seg_off; a.cursor = slot_cursor;
+    }
     CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_HITS], 0, sizeof(int64_t), s));
     int grid = (int)std::min<int64_t>((n + OV_TILE - 1) / OV_TILE, (int64_t)NUM_SMS * 8);
     if (grid < 1) grid = 1;
     c->stage_begin(SG_OVERLAP_SCATTER);
     k_overlap<<<grid, MX_THREADS, 0, s>>>(a);
+    if (by_slot) {
+        const size_t cap = (size_t)c->bc_table_cap;
+        unsigned int* slot_cursor = reinterpret_cast<unsigned int*>(c->d_slot_seg.as<int64_t>() + cap);
+        k_slot_cursors<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(slot_cursor, reinterpret_cast<int32_t*>(slot_cursor + cap), nb, c->d_cursor.as<unsigned int>());
+        c->launches++;
+        a.seg_off = c->d_seg_off.as<int64_t>(); a.cursor = c->d_cursor.as<unsigned int>();
+    }
     c->stage_end(SG_OVERLAP_SCATTER);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
