@@ -26,7 +26,7 @@ constexpr int MX_THREADS = 256;
 constexpr int SORT_SMALL = 4096;        // bitonic path capacity
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARP = 1024;         // segments up to this length are sorted by a single warp
-constexpr int COUNT_RANGE = 24576;      // counters per pass on the dense path (96 KiB)
+constexpr int COUNT_RANGE = 16384;      // counter words per pass on the dense path (64 KiB; 8-, 16- or 32-bit counters in them)
 constexpr int COUNT_THREADS = 512;
 
 struct OverlapArgs {
@@ -316,99 +316,109 @@ __global__ void __launch_bounds__(SORT_THREADS) k_reduce_warp(const int32_t* __r
     }
 }
 
-// long segments: counting over peak-row ranges of COUNT_RANGE rows held in shared memory
-__global__ void __launch_bounds__(COUNT_THREADS) k_reduce_large(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off, const unsigned int* __restrict__ seg_len,
+// long segments: counting over ranges of peak rows whose counters are held in shared memory.  The counters are packed
+// PACK to a 32-bit word and a pass covers PACK * COUNT_RANGE rows: 8-bit counters first (a (barcode, peak) count above
+// 255 is rare: the whole GRCh38 matrix is one pass instead of three with 16-bit counters), and a segment in which one
+// overflows is counted again with 16-bit (fewer than 32768 records, each worth 1 or 2: cannot overflow) or 32-bit ones.
+__global__ void __launch_bounds__(COUNT_THREADS, 3) k_reduce_large(const int32_t* __restrict__ hits, const int64_t* __restrict__ seg_off, const unsigned int* __restrict__ seg_len,
                                                                  int64_t n_bc, const int64_t* __restrict__ status, int64_t n_peaks_host,
                                                                  int32_t* __restrict__ out_row, int32_t* __restrict__ out_cnt,
                                                                  int32_t* __restrict__ nnz_col) {
-    extern __shared__ int cnt[];           // COUNT_RANGE counter words, then 2 * COUNT_RANGE / 32 bitmap words
+    extern __shared__ int cnt[];           // COUNT_RANGE counter words, then 4 * COUNT_RANGE / 32 bitmap words
     unsigned* bm = reinterpret_cast<unsigned*>(cnt + COUNT_RANGE);
     __shared__ int warp_tot[COUNT_THREADS / 32];
-    __shared__ int s_base;
+    __shared__ int s_base, s_overflow;
     const int64_t n_peaks = n_peaks_host >= 0 ? n_peaks_host : status[ST_N_PEAKS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // counters and bitmap start clean and are cleaned again as they are emitted: no clearing pass per range
-    for (int i = threadIdx.x; i < COUNT_RANGE + 2 * COUNT_RANGE / 32; i += COUNT_THREADS) cnt[i] = 0;
+    for (int i = threadIdx.x; i < COUNT_RANGE + 4 * COUNT_RANGE / 32; i += COUNT_THREADS) cnt[i] = 0;
+    if (threadIdx.x == 0) s_overflow = 0;
     for (int64_t b = blockIdx.x; b < n_bc; b += gridDim.x) {
         const int64_t o0 = seg_off[b];
         const int64_t len = seg_len[b];
         if (len <= SORT_SMALL) continue;
         if (len > 0x7fffffffLL) { if (threadIdx.x == 0) raise_error(const_cast<int64_t*>(status), CRATAC_ERR_CAPACITY, b); continue; }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base = 0;
-        // a segment of fewer than 32768 records (each worth 1 or 2) cannot overflow 16-bit counters: two per word,
-        // twice the rows per pass
-        const bool half = len < 32768;
-        const int range = half ? 2 * COUNT_RANGE : COUNT_RANGE;
-        for (int64_t r0 = 0; r0 < n_peaks; r0 += range) {
-            // count; the first hit of a row also sets its bit in the occupancy bitmap.  Eight loads in flight per
-            // thread: the loop is bound by the latency of the global loads otherwise.
-            constexpr int UN = 8;
-            const int32_t* __restrict__ seg = hits + o0;
-            const int len32 = (int)len, r0_32 = (int)r0;
-            for (int i0 = threadIdx.x; i0 < len32; i0 += UN * COUNT_THREADS) {
-                unsigned r[UN];
-                int inc[UN];
+        int lg = 2;                            // log2(PACK): 8-bit counters first
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_base = 0;
+            const int bits = 32 >> lg;
+            const unsigned fmask = lg ? (1u << bits) - 1u : 0xFFFFFFFFu;
+            const int range = COUNT_RANGE << lg;
+            bool overflow = false;
+            for (int64_t r0 = 0; r0 < n_peaks && !overflow; r0 += range) {
+                // count; the first hit of a row also sets its bit in the occupancy bitmap.  Eight loads in flight per
+                // thread: the loop is bound by the latency of the global loads otherwise.
+                constexpr int UN = 8;
+                const int32_t* __restrict__ seg = hits + o0;
+                const int len32 = (int)len, r0_32 = (int)r0;
+                bool over = false;
+                for (int i0 = threadIdx.x; i0 < len32; i0 += UN * COUNT_THREADS) {
+                    unsigned r[UN];
+                    int inc[UN];
 #pragma unroll
-                for (int u = 0; u < UN; u++) {
-                    const int i = i0 + u * COUNT_THREADS;
-                    const int v = i < len32 ? seg[i] : -1;
-                    r[u] = v >= 0 ? (unsigned)((v >> 1) - r0_32) : 0xFFFFFFFFu;
-                    inc[u] = 1 + (v & 1);
-                }
-                unsigned old[UN];
+                    for (int u = 0; u < UN; u++) {
+                        const int i = i0 + u * COUNT_THREADS;
+                        const int v = i < len32 ? seg[i] : -1;
+                        r[u] = v >= 0 ? (unsigned)((v >> 1) - r0_32) : 0xFFFFFFFFu;
+                        inc[u] = 1 + (v & 1);
+                    }
+                    unsigned old[UN];
 #pragma unroll
-                for (int u = 0; u < UN; u++) {
-                    old[u] = 1u;
-                    if (r[u] < (unsigned)range) {
-                        if (half) {
-                            const int sh = 16 * (r[u] & 1u);
-                            old[u] = ((unsigned)atomicAdd(&cnt[r[u] >> 1], inc[u] << sh) >> sh) & 0xFFFFu;
-                        } else {
-                            old[u] = (unsigned)atomicAdd(&cnt[r[u]], inc[u]);
+                    for (int u = 0; u < UN; u++) {
+                        old[u] = 1u;
+                        if (r[u] < (unsigned)range) {
+                            const int sh = bits * (int)(r[u] & ((1u << lg) - 1u));
+                            old[u] = ((unsigned)atomicAdd(&cnt[r[u] >> lg], inc[u] << sh) >> sh) & fmask;
+                            // the first overflow of a word sees an intact field: enough to notice that one happened
+                            over |= lg == 2 && old[u] + (unsigned)inc[u] > 255u;
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < UN; u++)
+                        if (old[u] == 0u) atomicOr(&bm[r[u] >> 5], 1u << (r[u] & 31u));
                 }
-#pragma unroll
-                for (int u = 0; u < UN; u++)
-                    if (old[u] == 0u) atomicOr(&bm[r[u] >> 5], 1u << (r[u] & 31u));
-            }
-            __syncthreads();
-            // emit the set bits in row order
-            for (int w0 = 0; w0 < range / 32; w0 += COUNT_THREADS) {
-                const int wi = w0 + threadIdx.x;
-                unsigned word = wi < range / 32 ? bm[wi] : 0u;
-                const unsigned word0 = word;
-                int c = __popc(word);
-                int x = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-                if (lane == 31) warp_tot[warp] = x;
+                if (over) s_overflow = 1;
                 __syncthreads();
-                int off = s_base;
-                for (int w = 0; w < warp; w++) off += warp_tot[w];
-                int64_t pos = o0 + off + x - c;
-                while (word) {
-                    const int bit = __ffs(word) - 1;
-                    word &= word - 1;
-                    const int row = wi * 32 + bit;
-                    out_row[pos] = (int32_t)(r0 + row);
-                    out_cnt[pos] = half ? (int)(((unsigned)cnt[row >> 1] >> (16 * (row & 1))) & 0xFFFFu) : cnt[row];
-                    pos++;
-                }
-                if (word0) {   // this thread owns the 32 rows of its bitmap word: clean up behind it
-                    bm[wi] = 0u;
-                    word = word0;
+                overflow = s_overflow != 0;
+                if (overflow) break;
+                // emit the set bits in row order
+                for (int w0 = 0; w0 < range / 32; w0 += COUNT_THREADS) {
+                    const int wi = w0 + threadIdx.x;
+                    unsigned word = wi < range / 32 ? bm[wi] : 0u;
+                    const unsigned word0 = word;
+                    int c = __popc(word);
+                    int x = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+                    if (lane == 31) warp_tot[warp] = x;
+                    __syncthreads();
+                    int off = s_base;
+                    for (int w = 0; w < warp; w++) off += warp_tot[w];
+                    int64_t pos = o0 + off + x - c;
                     while (word) {
-                        const int row = wi * 32 + __ffs(word) - 1;
+                        const int bit = __ffs(word) - 1;
                         word &= word - 1;
-                        cnt[half ? row >> 1 : row] = 0;
+                        const int row = wi * 32 + bit;
+                        out_row[pos] = (int32_t)(r0 + row);
+                        out_cnt[pos] = (int)(((unsigned)cnt[row >> lg] >> (bits * (row & ((1 << lg) - 1)))) & fmask);
+                        pos++;
                     }
+                    if (word0) {   // this thread owns the 32 rows of its bitmap word (whole counter words): clean up behind it
+                        bm[wi] = 0u;
+                        for (int k = 0; k < (32 >> lg); k++) cnt[((wi * 32) >> lg) + k] = 0;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x == COUNT_THREADS - 1) s_base = off + x;
+                    __syncthreads();
                 }
-                __syncthreads();
-                if (threadIdx.x == COUNT_THREADS - 1) s_base = off + x;
-                __syncthreads();
             }
+            if (!overflow) break;
+            // an 8-bit counter overflowed: wipe everything and count this segment again with wider counters
+            __syncthreads();
+            for (int i = threadIdx.x; i < COUNT_RANGE + 4 * COUNT_RANGE / 32; i += COUNT_THREADS) cnt[i] = 0;
+            if (threadIdx.x == 0) s_overflow = 0;
+            lg = len < 32768 ? 1 : 0;
         }
         if (threadIdx.x == 0) nnz_col[b] = s_base;
     }
@@ -608,7 +618,7 @@ int peak_matrix_hits(Ctx* c) {
     if (nb > 0) {
         static bool configured = false;
         if (!configured) {
-            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4 + COUNT_RANGE / 4));
+            CRATAC_CUDA(cudaFuncSetAttribute(k_reduce_large, cudaFuncAttributeMaxDynamicSharedMemorySize, COUNT_RANGE * 4 + COUNT_RANGE / 2));
             configured = true;
         }
         int g1 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 32);
@@ -617,8 +627,8 @@ int peak_matrix_hits(Ctx* c) {
         k_reduce_small<<<g1, SORT_THREADS, 0, s>>>(a.hits, a.seg_off, a.cursor, nb, c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_SMALL);
         c->stage_begin(SG_REDUCE_LARGE);
-        int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 2);
-        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 4, s>>>(a.hits, a.seg_off, a.cursor, nb, st,
+        int g2 = (int)std::min<int64_t>(nb, (int64_t)NUM_SMS * 3);          // 72 KiB of shared memory: three CTAs per SM
+        k_reduce_large<<<g2, COUNT_THREADS, COUNT_RANGE * 4 + COUNT_RANGE / 2, s>>>(a.hits, a.seg_off, a.cursor, nb, st,
                                                                  c->row_range > 0 ? c->row_range : (c->peaks_on_device_count ? -1 : c->n_peaks),
                                                                  c->d_out_row.as<int32_t>(), c->d_out_cnt.as<int32_t>(), nnz_col);
         c->stage_end(SG_REDUCE_LARGE);

@@ -250,12 +250,13 @@ def test_matrix_overlapping_peaks_rejected():
 
 
 @pytest.mark.parametrize("seed,n_peaks,n_bc,n_frag", [(5, 300, 40, 20000), (6, 40000, 12, 60000), (7, 5, 3000, 30000),
-                                                        (8, 2000, 6, 400000), (9, 60000, 200, 300000), (10, 50, 400, 200000)])
+                                                        (8, 2000, 6, 400000), (9, 60000, 200, 300000), (10, 50, 400, 200000),
+                                                        (11, 150000, 5, 400000)])
 def test_matrix_random_vs_oracle(seed, n_peaks, n_bc, n_frag):
     """Every reduce path: segments of a few records (one warp each), 1025..4096 records (bitonic sort by a CTA),
-    longer ones (range counting: 16-bit counters below 32768 records -- seeds 6, 8 -- and 32-bit ones above -- seed 8's
-    deep barcode), > 49 152 peaks (several counting ranges, seed 9), few wide peaks (large counts, most fragments with
-    both ends in one peak, seed 10), unsorted user peak order."""
+    longer ones (range counting with 8-bit counters; a count above 255 sends the segment to 16-bit counters below 32768
+    records and 32-bit ones above -- seeds 8 and 10: few wide peaks, large counts, most fragments with both ends in one
+    peak), > 131 072 peaks (two counting ranges, seed 11), unsorted user peak order."""
     rng = np.random.default_rng(seed)
     contigs = [("a", 3000000), ("b", 2000000)]
     peaks = []
