@@ -449,6 +449,7 @@ def main():
                     "source of roofline.traffic; without it traffic is null")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="cratac_set_option on the context (experiments; recorded in config)")
     ap.add_argument("--no-checksum", action="store_true")
     ap.add_argument("--no-e2e-file", action="store_true")
     ap.add_argument("--e2e-file-steps", type=int, default=2)
@@ -490,6 +491,8 @@ def main():
     # every rank knows all contigs (global ids); it piles up / calls peaks on its own range only
     ctx = _ffi.Context(contigs_all, primary=[c[0] for c in contigs], device=local_rank)
     ctx.set_option("profile", 1)
+    for kv in args.option:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if args.per_rank_library:
         text, nbytes, n_local = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device, chrom_offset=first_c)
     else:
@@ -728,6 +731,12 @@ def main():
             "host_phases_last_step_ms": ctx.host_times()[-12:], "multi_phases_last_step_ms": traces_by_rank,
             "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},
             "n_bins": int(getattr(res, "n_bins", 0))}
+    hits, misses = ctx.speculation_stats()
+    line["speculation"] = {"kept": int(hits), "redone": int(misses),
+                           "note": "peaks + matrix computed from an early iterate's threshold while the fit finishes; redone when the final "
+                                   "threshold differs (cumulative over warm-up, timed and e2e steps; at N > 1 the multi-GPU step keeps its own count)"}
+    if args.option:
+        line["config"]["options"] = list(args.option)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
