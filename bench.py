@@ -91,7 +91,7 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------------------------- workload
-def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chrom_offset=0, keep=None):
+def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chrom_offset=0, keep=None, in_peak_frac=0.5):
     """Seeded synthetic fragments generated ON the device (torch is plumbing here), sorted by
     (contig, start, stop) and rendered to fragments.tsv text by the library's encoder kernel.
     Same distributions as cratac/synth.py.
@@ -105,7 +105,7 @@ def make_workload(torch, ctx, contigs, n_frag, cells, n_peaks, seed, device, chr
     total = int(cum[-1].item())
     n = int(n_frag)
     centres = torch.randint(0, total, (max(int(n_peaks), 1),), generator=g, device=device, dtype=torch.int64)
-    in_peak = torch.rand(n, generator=g, device=device) < 0.5
+    in_peak = torch.rand(n, generator=g, device=device) < in_peak_frac
     pick = torch.randint(0, centres.numel(), (n,), generator=g, device=device, dtype=torch.int64)
     gpos = centres[pick] + (torch.randn(n, generator=g, device=device) * 150.0).to(torch.int64)
     del pick
@@ -300,6 +300,7 @@ def workload_config(args):
             "l2": "inputs larger than L2 (text %.1f GB per step)" % (46.0 * args.config_fragments / 1e9),
             "library": "one seeded library, identical for every --gpus N, cut by contig range" if not args.per_rank_library
                        else "one seeded library per rank (its own contig range)",
+            "in_peak_frac": args.in_peak_frac,
             "parallelism": "genome-range sharding by contig, %d GPU(s)" % args.gpus}
 
 
@@ -444,6 +445,7 @@ def main():
     ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--peaks", type=int, default=None)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--in-peak-frac", type=float, default=0.5, help="share of the fragments placed around latent peak centres; the rest is uniform background")
     ap.add_argument("--per-rank-library", action="store_true", help="every rank generates only its own contig range (different libraries for different N)")
     ap.add_argument("--ncu-csv", default=None, help="per-kernel CSV (tools/ncu_summary.py) of an `ncu --set full` capture of THIS command line: "
                     "source of roofline.traffic; without it traffic is null")
@@ -494,9 +496,9 @@ def main():
     for kv in args.option:
         ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if args.per_rank_library:
-        text, nbytes, n_local = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device, chrom_offset=first_c)
+        text, nbytes, n_local = make_workload(torch, ctx, contigs, n_local, args.cells, peaks_local, args.seed + 17 * rank, device, chrom_offset=first_c, in_peak_frac=args.in_peak_frac)
     else:
-        text, nbytes, n_local = make_workload(torch, ctx, contigs_all, args.fragments, args.cells, args.peaks, args.seed, device, keep=(first_c, last_c))
+        text, nbytes, n_local = make_workload(torch, ctx, contigs_all, args.fragments, args.cells, args.peaks, args.seed, device, keep=(first_c, last_c), in_peak_frac=args.in_peak_frac)
     torch.cuda.empty_cache()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
@@ -732,7 +734,7 @@ def main():
             "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},
             "n_bins": int(getattr(res, "n_bins", 0))}
     hits, misses = ctx.speculation_stats()
-    line["speculation"] = {"kept": int(hits), "redone": int(misses),
+    line["speculation"] = {"kept": int(hits), "redone": int(misses), "second_guesses": ctx.speculation_second_guesses(),
                            "note": "peaks + matrix computed from an early iterate's threshold while the fit finishes; redone when the final "
                                    "threshold differs (cumulative over warm-up, timed and e2e steps; at N > 1 the multi-GPU step keeps its own count)"}
     if args.option:

@@ -84,6 +84,8 @@ SIGNATURES = {
     "cratac_run": (c_int, [c_vp, c_vp, c_i64, c_int, c_dbl, P(RunResult)]),
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_speculation_stats": (c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "cratac_speculation_second_guesses": (c_i64, [c_vp]),
+    "cratac_fit_revised": (c_int, [c_vp, P(c_int), P(c_i64)]),
     "cratac_fit_speculative_launch": (c_int, [c_vp, c_dbl]),
     "cratac_fit_tentative": (c_int, [c_vp, P(c_int), P(c_i64)]),
     "cratac_speculation_scope": (c_int, [c_vp, c_int, P(ctypes.c_uint64)]),
@@ -265,11 +267,22 @@ class Context(object):
         check(self._lib.cratac_fit_tentative(self._h, ctypes.byref(pub), ctypes.byref(thr)))
         return thr.value if pub.value else None
 
+    def fit_revised(self):
+        """-> the fit's second guess (it extrapolated where its threshold is heading and that is not the tentative one), or
+        None when it ended without correcting itself."""
+        pub, thr = c_int(), c_i64()
+        check(self._lib.cratac_fit_revised(self._h, ctypes.byref(pub), ctypes.byref(thr)))
+        return thr.value if pub.value else None
+
     def speculation_scope(self, on):
-        """-> the stream the library's calls are queued on from now on."""
+        """on = 1: tentative threshold, 2: the fit's second guess, 0: off -> the stream the library's calls are queued on from now on."""
         s = ctypes.c_uint64()
-        check(self._lib.cratac_speculation_scope(self._h, 1 if on else 0, ctypes.byref(s)))
+        check(self._lib.cratac_speculation_scope(self._h, int(on), ctypes.byref(s)))
         return s.value
+
+    def speculation_second_guesses(self):
+        """Runs in which the fit corrected its tentative threshold while it was still running."""
+        return int(self._lib.cratac_speculation_second_guesses(self._h))
 
     def speculation_stats(self):
         """-> (runs whose speculative peaks + matrix were kept, runs that redid them)."""

@@ -157,6 +157,13 @@ def step(shard, torch, dist, device, odds_ratio=0.2, trace=None, gather=False):
     if tentative is not None:
         with shard.speculating():
             out = peaks_and_matrix("spec_")
+        # the fit extrapolates where its threshold is heading and says so when that is not the tentative one (same on every
+        # rank, at most once): the pass is queued again behind the first, still beside the fit
+        revised = shard.fit_revised()
+        if revised is not None and revised != tentative:
+            tentative = revised
+            with shard.speculating(second=True):
+                out = peaks_and_matrix("spec2_")
     threshold, params = shard.fit_result()
     mark("fit_wait")
     if out is None or threshold != tentative:
@@ -271,13 +278,17 @@ class CudaShard(object):
     def fit_tentative(self):
         return self.ctx.fit_tentative() if self.speculate else None
 
-    def speculating(self):
-        """Library calls and torch collectives go to the speculation stream, the peak kernels read the tentative threshold."""
+    def fit_revised(self):
+        return self.ctx.fit_revised() if self.speculate else None
+
+    def speculating(self, second=False):
+        """Library calls and torch collectives go to the speculation stream, the peak kernels read the tentative threshold
+        (second: the fit's second guess)."""
         import contextlib
 
         @contextlib.contextmanager
         def scope():
-            s = self.ctx.speculation_scope(True)
+            s = self.ctx.speculation_scope(2 if second else 1)
             try:
                 with self.torch.cuda.stream(self.torch.cuda.ExternalStream(s, device=self.device)):
                     yield

@@ -29,7 +29,7 @@ def seq_to_str(seq):
     return _BASES[codes]
 
 
-def generate(contigs, n_fragments, cells, n_peaks, seed, background_factor=20):
+def generate(contigs, n_fragments, cells, n_peaks, seed, background_factor=20, in_peak_frac=0.5):
     """-> dict(chrom, start, end, dup (int32), bc_seq (uint32 per fragment), n_contigs)."""
     rng = np.random.default_rng(seed)
     lens = np.array([c[1] for c in contigs], dtype=np.int64)
@@ -38,7 +38,7 @@ def generate(contigs, n_fragments, cells, n_peaks, seed, background_factor=20):
     n = int(n_fragments)
     # latent peaks
     centres = np.sort(rng.integers(0, total, size=max(int(n_peaks), 1)))
-    in_peak = rng.random(n) < 0.5
+    in_peak = rng.random(n) < in_peak_frac
     gpos = np.where(in_peak, centres[rng.integers(0, centres.size, size=n)] + rng.normal(0, 150, size=n).astype(np.int64),
                     rng.integers(0, total, size=n))
     gpos = np.clip(gpos, 0, total - 1)

@@ -283,6 +283,8 @@ int cratac_speculation_stats(cratac_ctx* h, int64_t* kept, int64_t* redone) {
     return CRATAC_OK;
 }
 
+int64_t cratac_speculation_second_guesses(cratac_ctx* h) { return h->c.spec_second; }
+
 int64_t cratac_decode_declined(cratac_ctx* h, int reset) {
     int64_t n = h->c.decode_declined;
     if (reset) h->c.decode_declined = 0;
@@ -787,14 +789,32 @@ static int speculate_peaks_and_matrix(Ctx* c, int* used) {
         if (q != cudaErrorNotReady) { set_error("fit failed: %s", cudaGetErrorString(q)); return CRATAC_ERR_CUDA; }
     }
     if (!tentative || cudaEventQuery(c->fit_event) == cudaSuccess) return CRATAC_OK;   // nothing left to hide behind
-    const int64_t tent = c->h_spec[0];
+    int64_t tent = c->h_spec[0];
     cudaStream_t own = c->stream;
     c->stream = c->spec_stream; c->thr_slot = ST_THRESHOLD_SPEC;
     int rc = call_peaks_device(c);
     if (rc == CRATAC_OK) rc = peak_matrix_device(c);
+    // the fit may correct itself while it runs on (second guess, em_fast.cu): the pass is queued again behind the first
+    // one, still beside the fit
+    for (;;) {
+        if (c->h_spec[3] == c->spec_seq) {
+            tent = c->h_spec[2];
+            c->thr_slot = ST_THRESHOLD_SPEC2;
+            c->spec_second++;
+            rc = call_peaks_device(c);
+            if (rc == CRATAC_OK) rc = peak_matrix_device(c);
+            break;
+        }
+        const cudaError_t q = cudaEventQuery(c->fit_event);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { c->stream = own; c->thr_slot = ST_THRESHOLD; set_error("fit failed: %s", cudaGetErrorString(q)); return CRATAC_ERR_CUDA; }
+    }
     if (rc == CRATAC_OK) rc = sync_status(c);
+    else cudaStreamSynchronize(c->spec_stream);     // whatever was queued must not run into the pass that replaces it
     c->stream = own; c->thr_slot = ST_THRESHOLD;
     c->host_mark("speculative_peaks_matrix");
+    // the status words are shared with the fit: an error it raised meanwhile is the run's error, not the pass's
+    if (rc == CRATAC_ERR_EM_ZERODIV || rc == CRATAC_ERR_EM_INDEX) return rc;
     // the verdict: the fit's own threshold
     int64_t* st = c->d_status.as<int64_t>();
     CRATAC_CUDA(cudaEventSynchronize(c->fit_event));
@@ -813,7 +833,7 @@ static int arm_speculation(Ctx* c) {
         void* hp = nullptr;
         CRATAC_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
         c->h_spec = reinterpret_cast<volatile int64_t*>(hp);
-        c->h_spec[0] = 0; c->h_spec[1] = 0;
+        c->h_spec[0] = 0; c->h_spec[1] = 0; c->h_spec[2] = 0; c->h_spec[3] = 0;
     }
     c->spec_seq++;
     c->spec_armed = true;
@@ -850,15 +870,33 @@ int cratac_fit_tentative(cratac_ctx* h, int* published, int64_t* threshold) {
     return CRATAC_OK;
 }
 
-// on = 1: the library's calls are queued on the speculation stream and the peak kernels read the tentative threshold;
-// on = 0: back to the context's own stream and the fitted threshold.  *stream_out: the stream now in use.
+// waits for the fit's second guess or for the end of the fit; *published = 1 and *threshold set iff the fit corrected its
+// tentative threshold (again a property of the histogram: the same on every rank of a sharded run)
+int cratac_fit_revised(cratac_ctx* h, int* published, int64_t* threshold) {
+    Ctx* c = &h->c;
+    if (!c->fit_event || !published || !threshold) { set_error("cratac_fit_revised: no speculative fit in flight"); return CRATAC_ERR_ARG; }
+    for (;;) {
+        if (c->h_spec[3] == c->spec_seq) break;
+        const cudaError_t q = cudaEventQuery(c->fit_event);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { set_error("fit failed: %s", cudaGetErrorString(q)); return CRATAC_ERR_CUDA; }
+    }
+    *published = c->h_spec[3] == c->spec_seq ? 1 : 0;
+    *threshold = *published ? c->h_spec[2] : -1;
+    if (*published) c->spec_second++;
+    return CRATAC_OK;
+}
+
+// on = 1: the library's calls are queued on the speculation stream and the peak kernels read the tentative threshold
+// (on = 2: the fit's second guess); on = 0: back to the context's own stream and the fitted threshold.
+// *stream_out: the stream now in use.
 int cratac_speculation_scope(cratac_ctx* h, int on, uint64_t* stream_out) {
     Ctx* c = &h->c;
     CRATAC_CUDA(cudaSetDevice(c->device));
     if (on) {
         if (!c->spec_stream) { set_error("cratac_speculation_scope: no speculative fit was launched"); return CRATAC_ERR_ARG; }
         if (!c->own_stream_saved) { c->own_stream_saved = c->stream; c->stream = c->spec_stream; }
-        c->thr_slot = ST_THRESHOLD_SPEC;
+        c->thr_slot = on == 2 ? ST_THRESHOLD_SPEC2 : ST_THRESHOLD_SPEC;
         // the column map may still be on its way on the side stream of cratac_union_columns
         if (c->union_event) CRATAC_CUDA(cudaStreamWaitEvent(c->spec_stream, c->union_event, 0));
     } else {

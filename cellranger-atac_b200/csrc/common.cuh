@@ -62,6 +62,7 @@ enum StatusSlot {
     ST_EM_DIRECT = 19,   // direct evaluations of the dispersion fixed-point map
     ST_EM_MODE = 20,     // 0 = fit pending, 1 = left to the generic kernel, 2 = done by the register-resident kernel
     ST_THRESHOLD_SPEC = 21,   // threshold after the first `spec_iter` EM iterations (speculative peak calling, api.cu run_tail)
+    ST_THRESHOLD_SPEC2 = 22,  // the fit's second guess: the threshold its crossing is converging to, when that is not the first (em_fast.cu)
     ST_SLOTS = 24
 };
 
@@ -211,10 +212,10 @@ struct Ctx {
     cudaStream_t own_stream_saved = nullptr;   // the context's stream while cratac_speculation_scope(1) is in force
     cudaEvent_t fit_event = nullptr;
     cudaEvent_t spec_done_event = nullptr;
-    volatile int64_t* h_spec = nullptr;    // pinned + mapped: {tentative threshold, sequence number} written by the fit kernel
+    volatile int64_t* h_spec = nullptr;    // pinned + mapped: {tentative threshold, sequence number, second guess, sequence number} written by the fit kernel
     int64_t spec_seq = 0;
     bool spec_armed = false;               // the fit being launched publishes a tentative threshold
-    int64_t spec_hits = 0, spec_misses = 0;
+    int64_t spec_hits = 0, spec_misses = 0, spec_second = 0;   // runs kept / redone / runs in which the fit's second guess started a second pass
     int defer_sync = 0;                    // 1: window_histogram / compact_histogram / fit_threshold_device only queue their work
     int em_fast = 2;                       // 0 plain fixed point, 1 accelerated (em.cu), 2 register-resident kernel first (em_fast.cu)
     bool profile = false;

@@ -41,7 +41,9 @@ struct EfArgs {
     double* g_w; double* g_lg; double* g_o1; double* g_T;
     int* g_v;
     // speculation (api.cu run_tail): after EM iteration spec_iter of the first run the threshold of the current parameters
-    // goes to status[ST_THRESHOLD_SPEC] and, behind a system-wide fence, to the host-mapped words spec_host[0..1]
+    // goes to status[ST_THRESHOLD_SPEC] and, behind a system-wide fence, to the host-mapped words spec_host[0..1].  Every
+    // eighth iteration after that the fit extrapolates where its threshold is heading; once that is certain and is not the
+    // first guess, the second guess goes to status[ST_THRESHOLD_SPEC2] and spec_host[2..3] (at most once per fit).
     volatile long long* spec_host;   // null: off
     long long spec_seq;
     int spec_iter;
@@ -153,12 +155,53 @@ __device__ __noinline__ double ef_estimate_threshold(Th th, double odds_ratio, d
     }
     return ef_block_max(best, red);
 }
-__device__ __forceinline__ void ef_publish_tentative(const EfArgs& a, long long thr) {
-    a.status[ST_THRESHOLD_SPEC] = thr;
+__device__ __forceinline__ void ef_publish_tentative(const EfArgs& a, long long thr, int shot) {
+    a.status[shot ? ST_THRESHOLD_SPEC2 : ST_THRESHOLD_SPEC] = thr;
     __threadfence_system();
-    a.spec_host[0] = thr;
+    a.spec_host[2 * shot] = thr;
     __threadfence_system();
-    a.spec_host[1] = a.spec_seq;
+    a.spec_host[2 * shot + 1] = a.spec_seq;
+}
+
+// estimate_threshold as a real number: *t_out = the threshold t of the current parameters (largest x < 1000 with
+// sig / bg < odds, -1 when there is none) and, returned, the x in [t, t + 1) at which the log ratio -- interpolated linearly
+// between t and t + 1 -- crosses log(odds).  The integer moves in steps while EM converges; this moves smoothly, so its limit
+// can be extrapolated.  Only speculation reads it: the fitted threshold itself comes from ef_estimate_threshold.
+__device__ __noinline__ double ef_crossing(Th th, double odds_ratio, double* red, double* t_out) {
+    const double f_sig = 1.0 - th.f_zero - th.f_bg;
+    const double nn = 1.0 / th.alpha_bg, pp = 1.0 / (1.0 + th.alpha_bg * th.mean_bg);
+    double ratio[2] = {-1.0, -1.0};
+    double best = -1.0;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int xi = threadIdx.x + q * EF_THREADS;
+        if (xi >= 1000) continue;
+        const double xv = (double)xi;
+        const double ysig = f_sig * (pow(1.0 - th.p_signal, xv) * th.p_signal);
+        const double nb = nn > NB_SADDLE_MIN ? ef_nb_saddle(xv, nn, pp)
+                                             : exp(lgamma(nn + xv) - lgamma(xv + 1.0) - lgamma(nn) + nn * log(pp) + xv * log1p(-pp));
+        const double ybg = th.f_zero * (pow(1.0 - th.p_zero, xv) * th.p_zero) + th.f_bg * nb;
+        ratio[q] = ysig / ybg;
+        if (ratio[q] < odds_ratio) best = fmax(best, xv);
+    }
+    best = ef_block_max(best, red);
+    *t_out = best;
+    if (best < 0.0) return -1.0;
+    const int t = (int)best;
+    __syncthreads();
+    if (threadIdx.x == 0) { red[64] = -1.0; red[65] = -1.0; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int xi = threadIdx.x + q * EF_THREADS;
+        if (xi == t) red[64] = ratio[q];
+        if (xi == t + 1 && xi < 1000) red[65] = ratio[q];
+    }
+    __syncthreads();
+    const double r0 = red[64], r1 = red[65];
+    __syncthreads();
+    if (!(r0 > 0.0) || !(r1 > r0) || !(r1 < 1e300)) return best + 0.5;
+    return best + (log(odds_ratio) - log(r0)) / (log(r1) - log(r0));
 }
 
 __device__ __forceinline__ double ef_frac(double alpha, double j) { return 1.0 - ef_rcp(fma(alpha, j, 1.0)); }
@@ -652,6 +695,9 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
     th.p_zero = th.mean_bg = th.alpha_bg = th.p_signal = th.f_zero = th.f_bg = 0.0;
     bool ok = true, hard = true;
     int tries = 0;
+    double cross1 = -1.0, cross2 = -1.0;   // speculation: crossings 8 and 16 iterates ago
+    long long shot1 = -1;
+    bool settled = false;
     for (;;) {
         Th last = th;
         bool have_last = false;
@@ -672,9 +718,34 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
             }
             th = nt;
             hard = false;
-            if (a.spec_host && tries == 0 && i == a.spec_iter) {
-                const double tent = ef_estimate_threshold(th, a.odds_ratio, s.red);
-                if (tid == 0) ef_publish_tentative(a, tent < 0.0 ? 0 : (long long)tent);
+            // speculation: the first guess is the threshold of iterate spec_iter.  Where the integer is still on its way (a
+            // slowly drifting crossing passes an integer at iterate 40, 90, ...) the crossings of three iterates eight apart
+            // give the limit (Aitken); it counts once no integer lies between the current crossing and the limit pushed half
+            // as far again, and goes out as the second guess if it is not the first.
+            if (a.spec_host && tries == 0 && !settled && i + 16 >= a.spec_iter && i <= a.spec_iter + 192 && ((i - a.spec_iter) & 7) == 0) {
+                double tent;
+                const double cx = ef_crossing(th, a.odds_ratio, s.red, &tent);
+                if (i == a.spec_iter) {
+                    shot1 = tent < 0.0 ? 0 : (long long)tent;
+                    if (tid == 0) ef_publish_tentative(a, shot1, 0);
+                } else if (i > a.spec_iter && cx >= 0.0 && cross1 >= 0.0 && cross2 >= 0.0) {
+                    const double d1 = cross1 - cross2, d2 = cx - cross1;
+                    double limit = cx;
+                    bool have = fabs(d2) < 1e-9;
+                    if (!have && d1 != 0.0) {
+                        const double r = d2 / d1;
+                        if (r > 0.0 && r < 0.95) { limit = cx + d2 * r / (1.0 - r); have = true; }
+                    }
+                    if (have) {
+                        const double far = limit + 0.5 * (limit - cx) + (limit >= cx ? 0.02 : -0.02);
+                        if (floor(fmin(cx, far)) == floor(fmax(cx, far))) {
+                            const long long guess = (long long)floor(limit);
+                            if (guess != shot1 && tid == 0) ef_publish_tentative(a, guess, 1);
+                            settled = true;
+                        }
+                    }
+                }
+                cross2 = cross1; cross1 = cx;
             }
         }
         iters += i;

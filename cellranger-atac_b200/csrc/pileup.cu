@@ -765,7 +765,8 @@ int call_peaks_device(Ctx* c) {
         CRATAC_CUDA(cudaMemsetAsync(c->d_chain.p, 0, nt * 8, c->stream));   // tile_ns, tile_ne
         CRATAC_CUDA(cudaMemsetAsync(bridge, 0, 4 * (size_t)cap, c->stream));
         CRATAC_CUDA(cudaMemsetAsync(&st[ST_N_RUNS], 0, sizeof(int64_t) * 3, c->stream));   // runs, fills, peaks
-        CRATAC_CUDA(cudaMemsetAsync(&st[ST_ERROR], 0, sizeof(int64_t) * 2, c->stream));
+        // the error slot is NOT cleared here: an error of the fit queued before this pass (a mixture component without
+        // weight) must still be there when the host reads the status; sync_status clears the slot when it reports one
         PileupArgs a;
         fill_args(c, a);
         int64_t* run_start = c->d_run_start.as<int64_t>();

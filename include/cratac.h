@@ -218,14 +218,21 @@ int cratac_counts_by_barcode(cratac_ctx* ctx, const int64_t* track_off, const in
 /* cratac_run* start peak calling and the matrix from the threshold the mixture fit shows after option "spec_iter" (32) EM
  * iterations, on a second stream, while the fit -- a single CTA, peaks.py:144-193 is sequential -- runs to convergence;
  * the speculative result is kept only when the fit ends on the same threshold, otherwise both are done again (option
- * "speculate" = 0 switches this off).  Counters since creation: runs whose speculative result was kept / redone. */
+ * "speculate" = 0 switches this off).  An integer threshold that is still on its way at iteration 32 (the real-valued
+ * crossing of peaks.py:43-63 drifts past an integer later) is caught by the fit itself: every eighth iteration it
+ * extrapolates the crossing's limit and, once no integer lies between here and there, publishes that threshold as its
+ * second guess if it differs from the first; peaks + matrix are then queued once more, still beside the fit.
+ * Counters since creation: runs whose speculative result was kept / redone; runs with a second guess. */
 int cratac_speculation_stats(cratac_ctx* ctx, int64_t* kept, int64_t* redone);
+int64_t cratac_speculation_second_guesses(cratac_ctx* ctx);
 /* The same as building blocks for the multi-GPU step (every rank fits the same all-reduced histogram, so all ranks see the
  * same tentative threshold): launch the fit so that it publishes one; wait for it (published = 0 when the fit ended before
  * its spec_iter-th iteration -- then there is nothing to speculate on, on any rank); route the library's calls to the
- * speculation stream with the tentative threshold (on = 1) and back (on = 0). */
+ * speculation stream with the tentative threshold (on = 1; on = 2: with the fit's second guess) and back (on = 0).
+ * cratac_fit_revised waits for the second guess or the end of the fit (published = 0: the fit did not correct itself). */
 int cratac_fit_speculative_launch(cratac_ctx* ctx, double odds_ratio);
 int cratac_fit_tentative(cratac_ctx* ctx, int* published, int64_t* threshold);
+int cratac_fit_revised(cratac_ctx* ctx, int* published, int64_t* threshold);
 int cratac_speculation_scope(cratac_ctx* ctx, int on, uint64_t* stream_out);
 /* fragments.tsv.gz (BGZF; plain gzip and plain text are read too) -> fragments in HBM.  Replaces, for the whole file, the
  * `gzip -c -d` pipe of lib/python/tools/io.py:197-217 and the per-line split of :75-92: `threads` host threads (0: all

@@ -332,8 +332,8 @@ def test_decode_parity_and_barcode_order():
 def test_column_order_worked_out_on_the_device_for_many_barcodes():
     """From `py2_device_min` barcodes on, the list(set(...)) column order comes from the device rebuild of the set
     (py2order.cu) instead of the host simulation: same columns, same per-fragment column ids, same matrix."""
-    contigs = [("chr1", 400000), ("chr2", 250000)]
-    frags = synth.generate(contigs, 90000, 2500, 60, seed=41, background_factor=8)   # ~20k distinct barcodes
+    contigs = [("chr1", 4000000), ("chr2", 2500000)]    # (on 650 kb no window holds <= 15 cut sites and the fit fails like the reference's)
+    frags = synth.generate(contigs, 90000, 2500, 60, seed=41, background_factor=8)   # ~14k distinct barcodes
     text = synth.to_text(frags)
     results = []
     for device_min in (1 << 40, 0):
@@ -403,6 +403,28 @@ def test_decode_many_tiles_and_table_growth():
     ctx.close()
 
 
+def test_decode_table_with_fewer_slots_than_barcodes_is_left_quickly():
+    """More distinct barcodes than the table has slots: the launch gives up on the crowded table (instead of probing it end to
+    end for every new key), the host grows it twice, and the result is the same."""
+    import time
+    contigs = synth.GRCH38[:1]
+    frags = synth.generate(contigs, 400000, 4000, 50, seed=14, background_factor=20)
+    text = synth.to_text(frags)
+    o = util.oracle_decode(text, [c[0] for c in contigs])
+    assert len(o["first_seen"]) > 40000
+    ctx = _ffi.Context(contigs)
+    ctx.set_option("barcode_table_slots", 16384)
+    t = time.time()
+    n, nb = ctx.decode_host(text)
+    assert time.time() - t < 5.0
+    assert n == o["start"].size and nb == len(o["first_seen"])
+    assert ctx.get_barcodes() == util.oracle_columns(o["first_seen"])
+    got = ctx.get_fragments()
+    bcs = ctx.get_barcodes()
+    assert [bcs[j] for j in got["bc"][:5000]] == o["barcodes"][:5000]
+    ctx.close()
+
+
 # ----------------------------------------------------------------------------- whole path
 def _run_and_compare(contigs, primary, text, odds=1 / 5):
     names = [c[0] for c in contigs]
@@ -445,6 +467,26 @@ def test_whole_path_fitted_threshold():
     frags = synth.generate(contigs, 350000, 60, 900, seed=22, background_factor=5)
     res = _run_and_compare(contigs, ["chr1", "chr2"], synth.to_text(frags))
     assert res.has_params == 1 and res.n_peaks > 100 and res.em_iterations > 0
+
+
+def test_whole_path_library_eight_times_as_deep_fails_like_the_reference():
+    """BASELINE.json configs[3] (2 B fragments on GRCh38) has the depth of 2.58 M fragments on 4 Mb.  With the generator's
+    uniform background no +-200 bp window holds 15 cut sites or fewer, the zero-noise component of the initial M-step is
+    empty and the reference divides by zero (peaks.py:90-128 via em_fitting.py:77-87).  The library reports exactly that
+    (CRATAC_ERR_EM_ZERODIV) instead of inventing a threshold."""
+    contigs = [("chr1", 4000000)]
+    frags = synth.generate(contigs, int(4000000 * 2e9 / 3.1e9), 50, 130, seed=3)
+    text = synth.to_text(frags)
+    o = util.oracle_decode(text, ["chr1"])
+    hist = util.oracle_hist(contigs, ["chr1"], o["chrom"], o["start"], o["end"])
+    assert min(hist) > 15
+    with pytest.raises(ZeroDivisionError):
+        oracle_em.estimate_final_threshold(hist, 1 / 5)
+    ctx = _ffi.Context(contigs, primary=["chr1"])
+    with pytest.raises(_ffi.CratacError) as err:
+        ctx.run(text=text, odds_ratio=1 / 5)
+    assert err.value.code == _ffi.ERR_EM_ZERODIV
+    ctx.close()
 
 
 def test_whole_path_config1_chr1_5m_fragments():
@@ -820,6 +862,34 @@ def test_speculative_peaks_and_matrix_never_change_the_result():
         ctx.close()
     assert outcomes[(0, 32)] == (0, 0) and outcomes[(1, 100000)] == (0, 0)
     assert sum(outcomes[(1, 1)]) == 2 and sum(outcomes[(1, 32)]) == 2        # both runs speculated (kept or redone)
+
+
+def test_fit_corrects_a_tentative_threshold_that_is_still_on_its_way():
+    """A library of the depth and peak density of the 20 000-peak mm10 points of BASELINE.json configs[4]: the integer threshold
+    is 41 at EM iterate 32 and reaches its final 39 only around iterate 45.  The fit extrapolates the real-valued crossing,
+    publishes 39 as its second guess, peaks + matrix are queued again beside the fit and kept: no pass after the fit."""
+    contigs = [("chr1", 12000000)]
+    frags = synth.generate(contigs, int(12e6 * 100e6 / 2.73e9), 50, 87, seed=5)
+    text = synth.to_text(frags)
+    o = util.oracle_decode(text, ["chr1"])
+    hist = util.oracle_hist(contigs, ["chr1"], o["chrom"], o["start"], o["end"])
+    othr, _ = oracle_em.estimate_final_threshold(hist, 0.2)
+    peaks = util.oracle_peaks(contigs, ["chr1"], o["chrom"], o["start"], o["end"], int(othr))
+    ctx = _ffi.Context(contigs)
+    res = ctx.run(text=text)
+    assert res.threshold == int(othr)
+    c, s_, e = ctx.get_peaks(res.n_peaks)
+    assert list(zip(c.tolist(), s_.tolist(), e.tolist())) == peaks
+    assert ctx.speculation_second_guesses() == 1 and ctx.speculation_stats() == (1, 0)
+    # the building blocks of the multi-GPU step see the same two guesses
+    ctx.set_option("defer_sync", 1)
+    ctx.window_histogram()
+    ctx.fit_speculative_launch(0.2)
+    ctx.set_option("defer_sync", 0)
+    first, second = ctx.fit_tentative(), ctx.fit_revised()
+    thr, _params, _ = ctx.fit_threshold_result()
+    assert thr == int(othr) and first is not None and first != thr and second == thr
+    ctx.close()
 
 
 # ----------------------------------------------------------------------------- sibling scans (SURVEY 8f rank 3, csrc/siblings.cu)

@@ -58,20 +58,44 @@ class OracleShard(object):
         self.mx = torch.tensor([max(h) if h else 0], dtype=torch.int64)
         return self.hist, self.mx
 
+    # guesses = (d1, d2): what a speculating fit would publish, as offsets from the fitted threshold (None: nothing)
+    guesses = (None, None)
+
     def fit_launch(self, odds):
         self.odds = odds
 
+    def _final(self):
+        gmax = int(self.mx.item())
+        cd = {int(v): int(self.hist[v]) for v in range(1, gmax + 1) if int(self.hist[v]) > 0}
+        return oracle_em.estimate_final_threshold(cd, self.odds)
+
     def fit_tentative(self):
-        return None                 # the CPU backend does not speculate
+        if self.guesses[0] is None:
+            return None             # no speculation
+        self._tent = int(self._final()[0]) + self.guesses[0]
+        return self._tent
+
+    def fit_revised(self):
+        if self.guesses[1] is None:
+            return None
+        self._rev = int(self._final()[0]) + self.guesses[1]
+        return self._rev
+
+    def speculating(self, second=False):
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            self.thr = self._rev if second else self._tent
+            yield
+        return scope()
 
     def side_stream(self):
         import contextlib
         return contextlib.nullcontext()
 
     def fit_result(self):
-        gmax = int(self.mx.item())
-        cd = {int(v): int(self.hist[v]) for v in range(1, gmax + 1) if int(self.hist[v]) > 0}
-        thr, params = oracle_em.estimate_final_threshold(cd, self.odds)
+        thr, params = self._final()
         self.thr = int(thr)
         return self.thr, params
 
@@ -163,6 +187,17 @@ def _worker(rank, world, port, out_dir):
     block = tuple(np.asarray(x) for x in shard.last_block)
     np.savez(os.path.join(out_dir, "block_%d.npz" % rank), indptr=block[0], indices=block[1], data=block[2],
              indptr_global=res0.indptr_global.numpy())
+    # speculation: a right first guess is kept; a wrong one corrected by the fit's second guess costs a second pass beside
+    # the fit; an uncorrected wrong one (or a wrong correction) is redone after the fit.  Same result every time.
+    for guesses, want in (((0, None), ["spec_"]), ((1, 0), ["spec_", "spec2_"]), ((1, None), ["spec_", ""]), ((0, 2), ["spec_", "spec2_", ""]),
+                          ((3, 3), ["spec_", ""])):
+        shard.guesses = guesses
+        trace = []
+        r = multi.step(shard, torch, dist, torch.device("cpu"), trace=trace)
+        assert (r.threshold, r.n_peaks, r.nnz) == (res0.threshold, res0.n_peaks, res0.nnz)
+        assert all(np.array_equal(x, y) for x, y in zip(shard.last_block, block))
+        assert [name[:-len("call_peaks")] for name, _ in trace if name.endswith("call_peaks")] == want
+    shard.guesses = (None, None)
     res = multi.step(shard, torch, dist, torch.device("cpu"), gather=True)
     assert (res.threshold, res.n_peaks, res.nnz) == (res0.threshold, res0.n_peaks, res0.nnz)
     if rank == 0:

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--cells", default="1000,10000,100000")
     ap.add_argument("--py2-device-min", default="", help="comma list of values of the library option of that name: every point is timed "
                                                          "once per value on the same text (empty: library default only)")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="cratac_set_option on every point's context")
     args = ap.parse_args()
 
     import torch
@@ -48,6 +49,9 @@ def main():
             try:
                 ctx = _ffi.Context(contigs, primary=[c[0] for c in contigs], device=0)
                 ctx.set_option("profile", 1)
+                for kv in args.option:
+                    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+                    point[kv.split("=")[0]] = int(kv.split("=")[1])
                 text, nbytes, _n = bench.make_workload(torch, ctx, contigs, args.fragments, cells, n_peaks, 5, device)
                 stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
                 settings = [int(x) for x in args.py2_device_min.split(",") if x] or [None]
@@ -76,7 +80,8 @@ def main():
                             groups[name] = {"ms": round(gms, 3), "frac": round(alg[name] / 1e9 / (gms / 1e3) / peak_gbs, 3)}
                     point.update({"ms_per_step": round(ms, 3), "fragments_per_s": args.fragments / (ms / 1e3), "threshold": int(res.threshold),
                                   "n_peaks": int(res.n_peaks), "n_barcodes": int(res.n_barcodes), "nnz": int(res.nnz),
-                                  "em_fit_ms": round(stage_ms.get("em_fit", 0.0) / args.steps, 3), "kernels": groups})
+                                  "em_fit_ms": round(stage_ms.get("em_fit", 0.0) / args.steps, 3), "em_iterations": int(res.em_iterations),
+                                  "speculation_kept_redone": list(ctx.speculation_stats()), "second_guesses": ctx.speculation_second_guesses(), "kernels": groups})
                     if si + 1 < len(settings):
                         print(json.dumps(point))
                         sys.stdout.flush()
