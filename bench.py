@@ -526,6 +526,20 @@ def main():
         res = step_device()
     stage_ms = {}
     sampler = ClockSampler(local_rank)
+    # host hygiene: the objects of the set-up (workload, contexts) leave the collector's generations, so that a collection
+    # inside the timed region has little to walk; what the collector still costs there is measured and reported
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc_pause = {"t": 0.0, "ms": 0.0, "n": 0}
+
+    def on_gc(phase, info):
+        if phase == "start":
+            gc_pause["t"] = time.time()
+        else:
+            gc_pause["ms"] += 1e3 * (time.time() - gc_pause["t"])
+            gc_pause["n"] += 1
+    gc.callbacks.append(on_gc)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -545,6 +559,7 @@ def main():
         loop_ms.append((round(1e3 * (t_b - t_a), 2), round(1e3 * (time.time() - t_b), 2)))
     ev1.record(stream)
     barrier()
+    gc.callbacks.remove(on_gc)
     wall = time.time() - wall0
     clocks = sampler.stop()
     launches = ctx.launch_count(reset=True)
@@ -556,7 +571,7 @@ def main():
     traces_by_rank = None
     if world > 1:
         traces_by_rank = [None] * world
-        dist.all_gather_object(traces_by_rank, {"rank": rank, "dev_ms_per_step": ev0.elapsed_time(ev1) / args.steps, "phases": [(k, round(v, 2)) for k, v in trace], "loop_ms": loop_ms,
+        dist.all_gather_object(traces_by_rank, {"rank": rank, "dev_ms_per_step": ev0.elapsed_time(ev1) / args.steps, "phases": [(k, round(v, 2)) for k, v in trace], "loop_ms": loop_ms, "gc_collections": gc_pause["n"], "gc_ms": round(gc_pause["ms"], 2),
                                                 "slowest_step_phases": slow_trace[1] if slow_trace else None})
     total_frags = args.steps * args.fragments
     value = total_frags / (dev_ms / 1000.0)
@@ -733,6 +748,7 @@ def main():
             "host_phases_last_step_ms": ctx.host_times()[-12:], "multi_phases_last_step_ms": traces_by_rank,
             "em_cycles_per_iteration": {k: round(v / max(int(res.em_iterations), 1)) for k, v in ctx.em_debug().items()},
             "n_bins": int(getattr(res, "n_bins", 0))}
+    line["host_gc_in_timed_region"] = {"collections": gc_pause["n"], "ms": round(gc_pause["ms"], 2)}
     hits, misses = ctx.speculation_stats()
     line["speculation"] = {"kept": int(hits), "redone": int(misses), "second_guesses": ctx.speculation_second_guesses(),
                            "note": "peaks + matrix computed from an early iterate's threshold while the fit finishes; redone when the final "

@@ -107,17 +107,24 @@ def step(shard, torch, dist, device, odds_ratio=0.2, trace=None, gather=False):
     mark("decode")
     # 1. histogram: queued, all-reduced in place (largest count and bins), fit queued behind it -- no host wait
     hist, mx = shard.window_histogram()                      # int64 tensors: bins [cap], largest count [1]
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    gmax = int(mx.item())                                    # (waits for the histogram pass; only the used bins are exchanged:
-    dist.all_reduce(hist[: gmax + 1], op=dist.ReduceOp.SUM)  #  an 8 MB all-reduce of the whole table stalled NCCL for 50-150 ms now and then)
+    # one small all-gather carries everything the ranks need to know of each other at this point: the largest window count
+    # (only the used bins are all-reduced: an 8 MB all-reduce of the whole table stalled NCCL for 50-150 ms now and then) and
+    # the fragment / barcode counts of the dictionary exchange below -- every host-synchronised collective less is one
+    # exposure less to a late peer
+    mine = torch.cat([mx.to(torch.int64).reshape(1), torch.tensor([n_frag, n_bc], dtype=torch.int64, device=device)])
+    info = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(info, mine)
+    info = torch.stack(info).cpu().numpy()                   # (waits for the histogram pass)
+    gmax = int(info[:, 0].max())
+    counts = info[:, 1:3]
+    mx.fill_(gmax)                                           # the fit reads the largest count from here
+    dist.all_reduce(hist[: gmax + 1], op=dist.ReduceOp.SUM)
     shard.fit_launch(odds_ratio)
     mark("hist_fit_launch")
     # 2. barcode dictionary, exchanged and united while the fit runs (side stream on a GPU: the fit occupies one SM).
     #    One all-gather of (key, first line, CPython-2.7 hash) per barcode; the union, the insertion order and the
     #    set order are the library's (cratac_union_columns): same columns on every rank, no host-side tensor algebra.
     with shard.side_stream():
-        counts = _all_gather_i64(torch, dist, [n_frag, n_bc], device)
-        mark("d_gather_counts")
         keys, first, hsh = shard.barcode_table()             # int64 tensors [n_bc]
         max_b = max(int(counts[:, 1].max()), 1)
         pad = torch.zeros((3, max_b), dtype=torch.int64, device=device)

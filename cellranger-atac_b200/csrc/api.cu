@@ -22,6 +22,7 @@
 namespace cratac {
 
 static thread_local char g_err[1024] = "";
+thread_local Lane* tl_lane = nullptr;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -168,7 +169,7 @@ void cratac_destroy(cratac_ctx* h) {
                       &c->d_em_params, &c->d_em_work, &c->d_chain, &c->d_tile_summary, &c->d_run_start, &c->d_run_end, &c->d_bridge, &c->d_fill,
                       &c->d_peak_chrom, &c->d_peak_start, &c->d_peak_end, &c->d_peak_row, &c->d_peak_off, &c->d_bc_hits, &c->d_seg_off,
                       &c->d_cursor, &c->d_hits, &c->d_out_row, &c->d_out_cnt, &c->d_nnz_col, &c->d_indptr, &c->d_indices, &c->d_data,
-                      &c->d_status, &c->d_scan_tmp, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc,
+                      &c->d_status, &c->d_scan_tmp, &c->d_scan_tmp_bc, &c->d_global_c2d, &c->d_nnz_ordered, &c->d_dense_bckey, &c->d_tile_desc,
                       &c->d_union, &c->d_col_keys, &c->d_sp_state, &c->d_sp_scalars, &c->d_sp_irr,
                       &c->d_bg_W, &c->d_bg_tiles, &c->d_bg_start, &c->d_bg_end, &c->d_bg_count,
                       &c->d_sib_perm, &c->d_sib_seg, &c->d_sib_tmp, &c->d_sib_hist, &c->d_slot_seg};
@@ -190,6 +191,7 @@ void cratac_destroy(cratac_ctx* h) {
     if (c->h_bc_order) cudaFreeHost(c->h_bc_order);
     if (c->h_c2d_pin) cudaFreeHost(c->h_c2d_pin);
     if (c->bc_event) cudaEventDestroy(c->bc_event);
+    if (c->bc_stream) cudaStreamDestroy(c->bc_stream);
     cudaStreamDestroy(c->stream);
     delete h;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -182,8 +183,10 @@ struct Ctx {
     // misc
     DevBuf d_status;                       // int64[ST_SLOTS]
     DevBuf d_scan_tmp;
+    DevBuf d_scan_tmp_bc;                  // the same for the barcode-order thread (its scans run beside the main thread's)
+    cudaStream_t bc_stream = nullptr;      // stream of that thread
     int64_t* h_status = nullptr;           // pinned mirror
-    int64_t launches = 0;                  // kernels launched since last reset (bench "gpu_launches")
+    std::atomic<int64_t> launches{0};      // kernels launched since last reset (bench "gpu_launches"); the barcode thread counts too
     cudaStream_t copy_stream = nullptr;    // chunked H2D of a host text (decode_text_streamed)
     cudaEvent_t copy_event = nullptr;
     cudaStream_t count_stream = nullptr;   // high priority: newline counts + scans of the next chunk under the parse of the current one
@@ -254,6 +257,14 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 // exclusive prefix sum of n int64 (in -> out, may alias); total written to *d_total if non-null.
 int exclusive_scan_i64(Ctx* c, const int64_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total);
 int exclusive_scan_i32_to_i64(Ctx* c, const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total);
+
+// A helper thread of the library (build_barcodes_async: the column order of very many barcodes, rebuilt on the device)
+// queues its kernels on a stream of its own and scans with scratch of its own; the functions it shares with the main
+// thread (scan.cu, py2order.cu) ask here which ones to use.
+struct Lane { cudaStream_t stream; DevBuf* scan_tmp; };
+extern thread_local Lane* tl_lane;
+inline cudaStream_t lane_stream(Ctx* c) { return tl_lane ? tl_lane->stream : c->stream; }
+inline DevBuf& lane_scan_tmp(Ctx* c) { return tl_lane ? *tl_lane->scan_tmp : c->d_scan_tmp; }
 
 // Where the streamed decode takes its host text from: a buffer that is all there (cratac_decode_host), or a ring of
 // pinned chunks that BGZF blocks are being inflated into on host threads (cratac_decode_file).

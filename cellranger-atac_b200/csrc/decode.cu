@@ -1819,8 +1819,31 @@ int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_
 void build_barcodes_async(Ctx* c) {
     if (c->bc_ready || c->bc_thread.joinable()) return;
     const int64_t nb = c->n_barcodes;
-    if (c->bc_order != CRATAC_BC_ORDER_PY2SET || nb <= 0 || (nb >= c->py2_device_min && c->d_hash_first) || !c->bc_event) return;
+    if (c->bc_order != CRATAC_BC_ORDER_PY2SET || nb <= 0 || !c->bc_event) return;
     c->bc_thread_done = false;
+    if (nb >= c->py2_device_min && c->d_hash_first) {
+        // very many barcodes: the set is rebuilt on the device (py2order.cu: a dozen table generations, each a few kernel
+        // rounds and a host look at a flag -- 10 ms for 2 M keys).  On this thread, a stream and scan scratch of its own, it
+        // runs beside the histogram pass and the fit instead of between the reduce and the CSC build.
+        if (!c->bc_stream && cudaStreamCreateWithFlags(&c->bc_stream, cudaStreamNonBlocking) != cudaSuccess) { c->bc_stream = nullptr; return; }
+        if (c->d_py2_rank.reserve(4 * (size_t)nb) != CRATAC_OK) return;
+        c->bc_thread = std::thread([c, nb] {
+            if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->bc_event) != cudaSuccess) return;
+            Lane lane{c->bc_stream, &c->d_scan_tmp_bc};
+            tl_lane = &lane;
+            const int rc = py2_set_order_device(c, nb, reinterpret_cast<const int64_t*>(c->d_hash_first), c->d_py2_rank.as<int32_t>());
+            tl_lane = nullptr;
+            if (rc != CRATAC_OK) return;                       // the main thread does it again and reports the error
+            const unsigned g = (unsigned)((nb + 255) / 256);
+            k_compose_order<<<g, 256, 0, c->bc_stream>>>(c->d_py2_rank.as<int32_t>(), c->d_order_first, nb, c->d_col_to_dense.as<int32_t>());
+            k_invert_order<<<g, 256, 0, c->bc_stream>>>(c->d_col_to_dense.as<int32_t>(), nb, c->d_dense_to_col.as<int32_t>());
+            c->launches += 2;
+            if (cudaMemcpyAsync(c->h_c2d_pin, c->d_col_to_dense.p, 4 * (size_t)nb, cudaMemcpyDeviceToHost, c->bc_stream) != cudaSuccess) return;
+            if (cudaStreamSynchronize(c->bc_stream) != cudaSuccess) return;
+            c->bc_thread_done = true;
+        });
+        return;
+    }
     c->bc_thread = std::thread([c, nb] {
         if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->bc_event) != cudaSuccess) return;
         std::vector<int32_t> order;
@@ -1838,7 +1861,12 @@ int build_barcodes(Ctx* c) {
     cudaStream_t s = c->stream;
     CRATAC_CUDA(cudaEventSynchronize(c->bc_event));
     int32_t* c2d = c->h_c2d_pin;    // pinned: the upload below does not wait for the stream
-    if (from_thread && c->bc_order == CRATAC_BC_ORDER_PY2SET) {
+    if (from_thread && c->bc_order == CRATAC_BC_ORDER_PY2SET && nb >= c->py2_device_min && nb > 0 && c->d_hash_first) {
+        // the thread rebuilt the set on the device: both maps are in HBM (its stream was synchronised), c2d is their host copy
+        c->h_c2d.assign(c2d, c2d + nb);
+        c->bc_ready = true;
+        return CRATAC_OK;
+    } else if (from_thread && c->bc_order == CRATAC_BC_ORDER_PY2SET) {
         // c2d was filled by build_barcodes_async
     } else if (c->bc_order == CRATAC_BC_ORDER_FIRST_SEEN) {
         for (int64_t j = 0; j < nb; j++) c2d[j] = c->h_bc_order[j];

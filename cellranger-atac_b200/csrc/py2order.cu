@@ -71,7 +71,7 @@ __global__ void k_p2_iota(int32_t* __restrict__ seq, int from, int to) {
 int py2_set_order_device(Ctx* c, int64_t n, const int64_t* d_hashes, int32_t* d_order_out) {
     if (n <= 0) return CRATAC_OK;
     if (n >= (int64_t)1 << 30) { set_error("py2_set_order_device: too many keys"); return CRATAC_ERR_ARG; }
-    cudaStream_t s = c->stream;
+    cudaStream_t s = lane_stream(c);
     // largest table: the growth rule applied to n keys
     uint64_t max_size = 8;
     {

@@ -72,22 +72,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* in, int6
 template <typename TIn>
 static int scan_impl(Ctx* c, const TIn* d_in, int64_t* d_out, int64_t n, int64_t* d_total, int64_t* tmp, size_t tmp_elems) {
     if (n <= 0) {
-        if (d_total) CRATAC_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), c->stream));
+        if (d_total) CRATAC_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), lane_stream(c)));
         return CRATAC_OK;
     }
     int64_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (nblocks == 1) {
-        k_scan_apply<TIn><<<1, SCAN_THREADS, 0, c->stream>>>(d_in, n, nullptr, d_out, d_total);
+        k_scan_apply<TIn><<<1, SCAN_THREADS, 0, lane_stream(c)>>>(d_in, n, nullptr, d_out, d_total);
         c->launches++;
         CRATAC_CUDA(cudaGetLastError());
         return CRATAC_OK;
     }
     if ((size_t)nblocks > tmp_elems) { set_error("scan scratch too small"); return CRATAC_ERR_INTERNAL; }
-    k_scan_reduce<TIn><<<(unsigned)nblocks, SCAN_THREADS, 0, c->stream>>>(d_in, n, tmp);
+    k_scan_reduce<TIn><<<(unsigned)nblocks, SCAN_THREADS, 0, lane_stream(c)>>>(d_in, n, tmp);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     CRATAC_TRY(scan_impl<int64_t>(c, tmp, tmp, nblocks, nullptr, tmp + nblocks, tmp_elems - nblocks));
-    k_scan_apply<TIn><<<(unsigned)nblocks, SCAN_THREADS, 0, c->stream>>>(d_in, n, tmp, d_out, d_total);
+    k_scan_apply<TIn><<<(unsigned)nblocks, SCAN_THREADS, 0, lane_stream(c)>>>(d_in, n, tmp, d_out, d_total);
     c->launches++;
     CRATAC_CUDA(cudaGetLastError());
     return CRATAC_OK;
@@ -97,8 +97,8 @@ static int scan_scratch(Ctx* c, int64_t n, int64_t** tmp, size_t* elems) {
     size_t need = 0;
     for (int64_t m = (n + SCAN_TILE - 1) / SCAN_TILE; m > 1; m = (m + SCAN_TILE - 1) / SCAN_TILE) need += (size_t)m;
     need += 8;
-    CRATAC_TRY(c->d_scan_tmp.reserve(need * sizeof(int64_t)));
-    *tmp = c->d_scan_tmp.as<int64_t>();
+    CRATAC_TRY(lane_scan_tmp(c).reserve(need * sizeof(int64_t)));
+    *tmp = lane_scan_tmp(c).as<int64_t>();
     *elems = need;
     return CRATAC_OK;
 }

@@ -81,7 +81,8 @@ def main():
                     point.update({"ms_per_step": round(ms, 3), "fragments_per_s": args.fragments / (ms / 1e3), "threshold": int(res.threshold),
                                   "n_peaks": int(res.n_peaks), "n_barcodes": int(res.n_barcodes), "nnz": int(res.nnz),
                                   "em_fit_ms": round(stage_ms.get("em_fit", 0.0) / args.steps, 3), "em_iterations": int(res.em_iterations),
-                                  "speculation_kept_redone": list(ctx.speculation_stats()), "second_guesses": ctx.speculation_second_guesses(), "kernels": groups})
+                                  "speculation_kept_redone": list(ctx.speculation_stats()), "second_guesses": ctx.speculation_second_guesses(),
+                                  "host_phases_last_step_ms": ctx.host_times()[-10:], "stage_ms": {k: round(v / args.steps, 3) for k, v in stage_ms.items()}, "kernels": groups})
                     if si + 1 < len(settings):
                         print(json.dumps(point))
                         sys.stdout.flush()
