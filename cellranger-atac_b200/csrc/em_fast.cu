@@ -718,31 +718,42 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
             }
             th = nt;
             hard = false;
-            // speculation: the first guess is the threshold of iterate spec_iter.  Where the integer is still on its way (a
-            // slowly drifting crossing passes an integer at iterate 40, 90, ...) the crossings of three iterates eight apart
-            // give the limit (Aitken); it counts once no integer lies between the current crossing and the limit pushed half
-            // as far again, and goes out as the second guess if it is not the first.
+            // speculation.  Every eighth iterate from spec_iter - 16 on: the real-valued crossing behind the integer threshold
+            // (ef_crossing).  From spec_iter on the crossings of three check points give its limit (Aitken: geometric
+            // convergence, ratio 0 < r < 0.95, or no movement at all); the limit is trusted once no integer lies between the
+            // current crossing and the limit pushed half as far again.  First guess: the trusted limit's threshold if there is
+            // one; nothing yet while the crossing still has more than an integer to travel (at most 64 iterates of patience);
+            // otherwise the iterate's own threshold.  After that the first trusted limit either confirms the guess or goes out
+            // as the second guess, and the question is settled.
             if (a.spec_host && tries == 0 && !settled && i + 16 >= a.spec_iter && i <= a.spec_iter + 192 && ((i - a.spec_iter) & 7) == 0) {
                 double tent;
                 const double cx = ef_crossing(th, a.odds_ratio, s.red, &tent);
-                if (i == a.spec_iter) {
-                    shot1 = tent < 0.0 ? 0 : (long long)tent;
-                    if (tid == 0) ef_publish_tentative(a, shot1, 0);
-                } else if (i > a.spec_iter && cx >= 0.0 && cross1 >= 0.0 && cross2 >= 0.0) {
-                    const double d1 = cross1 - cross2, d2 = cx - cross1;
+                if (i >= a.spec_iter) {
+                    bool valid = false, trusted = false;
                     double limit = cx;
-                    bool have = fabs(d2) < 1e-9;
-                    if (!have && d1 != 0.0) {
-                        const double r = d2 / d1;
-                        if (r > 0.0 && r < 0.95) { limit = cx + d2 * r / (1.0 - r); have = true; }
-                    }
-                    if (have) {
-                        const double far = limit + 0.5 * (limit - cx) + (limit >= cx ? 0.02 : -0.02);
-                        if (floor(fmin(cx, far)) == floor(fmax(cx, far))) {
-                            const long long guess = (long long)floor(limit);
-                            if (guess != shot1 && tid == 0) ef_publish_tentative(a, guess, 1);
-                            settled = true;
+                    if (cx >= 0.0 && cross1 >= 0.0 && cross2 >= 0.0) {
+                        const double d1 = cross1 - cross2, d2 = cx - cross1;
+                        if (fabs(d2) < 1e-9) valid = true;
+                        else if (d1 != 0.0) {
+                            const double r = d2 / d1;
+                            if (r > 0.0 && r < 0.95) { limit = cx + d2 * r / (1.0 - r); valid = true; }
                         }
+                        if (valid) {
+                            const double far = limit + 0.5 * (limit - cx) + (limit >= cx ? 0.02 : -0.02);
+                            trusted = floor(fmin(cx, far)) == floor(fmax(cx, far));
+                        }
+                    }
+                    const long long raw = tent < 0.0 ? 0 : (long long)tent;
+                    const long long lim = limit < 0.0 ? 0 : (long long)floor(limit);
+                    if (shot1 < 0) {
+                        const bool on_its_way = valid && !trusted && fabs(limit - cx) > 1.0 && i < a.spec_iter + 64;
+                        if (!on_its_way) {
+                            shot1 = trusted ? lim : raw;
+                            if (tid == 0) ef_publish_tentative(a, shot1, 0);
+                        }
+                    } else if (trusted) {
+                        if (lim != shot1 && tid == 0) ef_publish_tentative(a, lim, 1);
+                        settled = true;
                     }
                 }
                 cross2 = cross1; cross1 = cx;

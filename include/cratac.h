@@ -220,8 +220,10 @@ int cratac_counts_by_barcode(cratac_ctx* ctx, const int64_t* track_off, const in
  * the speculative result is kept only when the fit ends on the same threshold, otherwise both are done again (option
  * "speculate" = 0 switches this off).  An integer threshold that is still on its way at iteration 32 (the real-valued
  * crossing of peaks.py:43-63 drifts past an integer later) is caught by the fit itself: every eighth iteration it
- * extrapolates the crossing's limit and, once no integer lies between here and there, publishes that threshold as its
- * second guess if it differs from the first; peaks + matrix are then queued once more, still beside the fit.
+ * extrapolates the crossing's limit.  While that limit is more than an integer away the first guess is held back (at most
+ * 64 iterations); a limit that can be trusted -- no integer between here and there -- is the guess; and after a first
+ * guess the first trusted limit either confirms it or is published as the second guess, for which peaks + matrix are
+ * queued once more, still beside the fit.
  * Counters since creation: runs whose speculative result was kept / redone; runs with a second guess. */
 int cratac_speculation_stats(cratac_ctx* ctx, int64_t* kept, int64_t* redone);
 int64_t cratac_speculation_second_guesses(cratac_ctx* ctx);
