@@ -43,22 +43,27 @@ def measured_peaks():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (one light query
-    every 50 ms; spawning nvidia-smi per rank stalls the driver for the first timed steps of an 8-GPU run)."""
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML: one light query per GPU every
+    50 ms, from ONE process (rank 0 watches all GPUs of the run).  Spawning nvidia-smi per rank stalled the driver for the
+    first timed steps of an 8-GPU run, and eight in-process NVML clients starting together still cost the first step 10-30 ms."""
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
+    def __init__(self, gpu_indices):
         self.samples, self.reasons = [], set()
         self.smax = None
         self.stop_flag = threading.Event()
         self.thread = None
+        self.handles = []
+        self.err = "not sampled on this rank"
+        if not gpu_indices:
+            self.nv = None
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in gpu_indices]
+            self.smax = float(min(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM) for h in self.handles))
         except Exception as e:                                # noqa: BLE001 - reported in the JSON line
             self.nv = None
             self.err = "NVML unavailable: %s" % (e,)
@@ -66,14 +71,15 @@ class ClockSampler(object):
     def _loop(self):
         nv = self.nv
         while not self.stop_flag.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for bit, name in self.REASONS:
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:                                 # noqa: BLE001
-                pass
+            for h in self.handles:
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    for bit, name in self.REASONS:
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:                             # noqa: BLE001
+                    pass
             self.stop_flag.wait(0.05)
 
     def start(self):
@@ -525,7 +531,7 @@ def main():
     for _ in range(args.warmup):
         res = step_device()
     stage_ms = {}
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])   # single-node runs: local GPU index = rank
     # host hygiene: the objects of the set-up (workload, contexts) leave the collector's generations, so that a collection
     # inside the timed region has little to walk; what the collector still costs there is measured and reported
     import gc
