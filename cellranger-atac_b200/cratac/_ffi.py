@@ -85,6 +85,7 @@ SIGNATURES = {
     "cratac_run_from_fragments": (c_int, [c_vp, c_dbl, P(RunResult)]),
     "cratac_speculation_stats": (c_int, [c_vp, P(c_i64), P(c_i64)]),
     "cratac_speculation_second_guesses": (c_i64, [c_vp]),
+    "cratac_pileup_tile_bases": (c_i64, []),
     "cratac_fit_revised": (c_int, [c_vp, P(c_int), P(c_i64)]),
     "cratac_fit_speculative_launch": (c_int, [c_vp, c_dbl]),
     "cratac_fit_tentative": (c_int, [c_vp, P(c_int), P(c_i64)]),

@@ -287,6 +287,8 @@ int cratac_speculation_stats(cratac_ctx* h, int64_t* kept, int64_t* redone) {
 
 int64_t cratac_speculation_second_guesses(cratac_ctx* h) { return h->c.spec_second; }
 
+int64_t cratac_pileup_tile_bases(void) { return pileup_tile_bases(); }
+
 int64_t cratac_decode_declined(cratac_ctx* h, int reset) {
     int64_t n = h->c.decode_declined;
     if (reset) h->c.decode_declined = 0;

@@ -12,8 +12,8 @@
 // per CTA); mode PEAKS emits the boundaries of the runs W >= threshold into CTA-private regions, tile by tile
 // (k_gather_events restores genome order from the per-tile counts: no CTA waits for another) plus what the zero-gap rule of
 // write_chrom_bedgraph (count_cut_sites/__init__.py:36-37) needs; mode DUMP writes W (tests, bedgraph).
-// Mode HIST also leaves, per tile, an upper bound of W and the first / last non-zero window: mode PEAKS skips the
-// tiles whose bound is below the threshold (most of the genome) without staging them.
+// Mode HIST also leaves, per tile, the largest W of its own bases and the first / last non-zero window: mode PEAKS skips
+// the tiles that cannot hold a run (largest W below the threshold) without staging them.
 // HBM traffic: 8 B per fragment (start, end) x (1 + halo overhead); everything per-base is on chip.
 #include <algorithm>
 
@@ -69,7 +69,7 @@ struct PileupArgs {
     int64_t* tile_src_e;
     int thr_slot;                   // status slot holding the threshold (ST_THRESHOLD, or ST_THRESHOLD_SPEC for a speculative pass)
     int4* tile_summary;             // first_nz_pos, first_nz_val, last_nz_pos, last_nz_val
-    int32_t* tile_bound;            // per tile: an upper bound of its window counts.  MODE_HIST writes it (and the summary);
+    int32_t* tile_bound;            // per tile: the largest window count of its own bases.  MODE_HIST writes it (and the summary);
                                     // MODE_PEAKS skips the tiles whose bound is below the threshold (null: no skipping)
     int64_t* fills;                 // pairs (g0, g1)
     int64_t fill_cap;
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
             sm.z = (int)(s_lastp >> 32); sm.w = (int)(s_lastp & 0xFFFFFFFFULL);
         }
         a.tile_summary[prev_tile] = sm;
+        a.tile_bound[prev_tile] = s_bound;     // the largest window count of the tile's own bases and the base before them (exact: the walk saw them all)
     };
     while (true) {
         __syncthreads();
@@ -288,20 +289,19 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
                 else raise_error(a.status, CRATAC_ERR_CAPACITY, v);
             };
             // Common case: no window count of the tile can reach PU_HB (bounded from the prefix sums: every W of my
-            // chunk is at most S[k0 + chunk + 401] - S[k0]) -> no range check, no max tracking, and bin 0 may
+            // chunk is at most S[k0 + chunk + 401] - S[k0]) -> no range check, no global-max tracking, and bin 0 may
             // collect garbage (it is never read); the checked path handles the few tiles over the bound.
             const int hi = min(k0 + PU_OWN_CHUNK + 401, PU_N - 1);
             const int bound = k0 < own ? sc[hi] - sc[k0] : 0;
-            if (a.tile_bound) {   // for the peak pass: an upper bound of the tile's window counts
-                const int wb = __reduce_max_sync(0xffffffffu, bound);
-                if ((tid & 31) == 0 && wb > 0) atomicMax(&s_bound, wb);
-            }
             const bool fast = !__syncthreads_or(bound >= PU_HB);
-            if (a.tile_bound && tid == 0) a.tile_bound[tile] = s_bound;
             int w_first = 0;          // W of my first base (captured by the walkers below at no cost)
+            int wmax = 0;             // for the peak pass: the tile's largest window count.  The bound above is too loose for
+                                      // that: over 256 chunks of pure background it reaches the threshold by noise alone, and
+                                      // the peak pass then piles up tiles that hold no peak
             if (fast) {
                 auto body = [&](int k, int w) {
                     if (k == k0) w_first = w;
+                    wmax = max(wmax, w);
                     const bool changed = w != cur;
                     if (changed) asm volatile("red.shared::cta.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * (uint32_t)cur), "r"(runlen) : "memory");
                     runlen = changed ? 1 : runlen + 1;
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
                         else flush_slow(cur, runlen);
                     }
                     loc_max = max(loc_max, w);
+                    wmax = max(wmax, w);
                     runlen = changed ? 1 : runlen + 1;
                     cur = w;
                 });
@@ -328,6 +329,11 @@ __global__ void __launch_bounds__(PU_THREADS, PU_CTAS_PER_SM) k_pileup(PileupArg
                 }
             }
             if (a.tile_bound) {
+                // the peak pass also closes, at the tile's first base, a run that ended on the last base of the tile before:
+                // that base counts for this tile too
+                if (tid == 0 && ta > 0) wmax = max(wmax, sc[401] - sc[0]);
+                const int wm = __reduce_max_sync(0xffffffffu, wmax);
+                if ((tid & 31) == 0 && wm > 0) atomicMax(&s_bound, wm);
                 // first / last base of the tile with a non-zero window count and their counts, for the peak pass's
                 // zero-gap logic.  Almost always my chunk's own ends, whose counts the walk has just produced (w_first,
                 // cur); thread 0 writes the tile's summary after the next barrier (loop top).

@@ -226,6 +226,9 @@ int cratac_counts_by_barcode(cratac_ctx* ctx, const int64_t* track_off, const in
  * queued once more, still beside the fit.
  * Counters since creation: runs whose speculative result was kept / redone; runs with a second guess. */
 int cratac_speculation_stats(cratac_ctx* ctx, int64_t* kept, int64_t* redone);
+/* Genome bases per pileup tile (one CTA pass of K2/K3/K5; count_cut_sites/__init__.py:94-104 has no tiles): for tests that put
+ * run ends and zero gaps on tile borders. */
+int64_t cratac_pileup_tile_bases(void);
 int64_t cratac_speculation_second_guesses(cratac_ctx* ctx);
 /* The same as building blocks for the multi-GPU step (every rank fits the same all-reduced histogram, so all ranks see the
  * same tentative threshold): launch the fit so that it publishes one; wait for it (published = 0 when the fit ended before

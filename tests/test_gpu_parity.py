@@ -120,6 +120,28 @@ def test_zero_gap_across_tiles():
     ctx.close()
 
 
+def test_run_that_ends_on_the_last_base_of_a_tile():
+    """The peak pass skips tiles whose largest window count (left by the histogram pass) is below the threshold.  A run that
+    ends exactly on a tile's last base is closed by the NEXT tile, at its first base: that tile must not be skipped although
+    none of its own windows reaches the threshold (its maximum includes the base before it)."""
+    T = _ffi.load().cratac_pileup_tile_bases()
+    L = 4 * T
+    for boundary in (T, 2 * T):
+        # cut sites at boundary - 501 and boundary - 201: windows >= 20 on [boundary - 701, boundary - 1], nothing after
+        start = np.full(20, boundary - 501, dtype=np.int32)
+        end = np.full(20, boundary - 201, dtype=np.int32)
+        ctx = _ffi.Context([("chrZ", L)])
+        ctx.set_fragments(np.zeros(20, np.int32), start, end, np.zeros(20, np.int32), None, ["BC"])
+        W = cfast.window_counts(L, start, end)
+        assert W[boundary - 1] == 20 and W[boundary:].max() == 0
+        ctx.window_histogram()               # leaves the per-tile maxima the peak pass skips by
+        for thr in (1, 20, 21, 40, 41):
+            c, s, e = ctx.call_peaks(thr)
+            ps, pe = cfast.call_peaks_contig(L, start, end, thr)
+            assert list(zip(s.tolist(), e.tolist())) == list(zip(ps.tolist(), pe.tolist())), "threshold %d" % thr
+        ctx.close()
+
+
 # ----------------------------------------------------------------------------- threshold fit
 @pytest.mark.parametrize("case", EM_CASES, ids=[c["name"] for c in EM_CASES])
 def test_em_golden(case):
