@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "nb_pmf.cuh"
+#include "spec_rule.cuh"
 
 namespace cratac {
 
@@ -695,9 +696,7 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
     th.p_zero = th.mean_bg = th.alpha_bg = th.p_signal = th.f_zero = th.f_bg = 0.0;
     bool ok = true, hard = true;
     int tries = 0;
-    double cross1 = -1.0, cross2 = -1.0;   // speculation: crossings 8 and 16 iterates ago
-    long long shot1 = -1;
-    bool settled = false;
+    SpecRule rule;                         // speculation: when to tell the host which threshold the fit is heading for
     for (;;) {
         Th last = th;
         bool have_last = false;
@@ -718,45 +717,14 @@ __global__ void __launch_bounds__(EF_THREADS) k_em_fit_fast(EfArgs a) {
             }
             th = nt;
             hard = false;
-            // speculation.  Every eighth iterate from spec_iter - 16 on: the real-valued crossing behind the integer threshold
-            // (ef_crossing).  From spec_iter on the crossings of three check points give its limit (Aitken: geometric
-            // convergence, ratio 0 < r < 0.95, or no movement at all); the limit is trusted once no integer lies between the
-            // current crossing and the limit pushed half as far again.  First guess: the trusted limit's threshold if there is
-            // one; nothing yet while the crossing still has more than an integer to travel (at most 64 iterates of patience);
-            // otherwise the iterate's own threshold.  After that the first trusted limit either confirms the guess or goes out
-            // as the second guess, and the question is settled.
-            if (a.spec_host && tries == 0 && !settled && i + 16 >= a.spec_iter && i <= a.spec_iter + 192 && ((i - a.spec_iter) & 7) == 0) {
+            // speculation: every eighth iterate the rule of spec_rule.cuh sees the threshold of the current parameters and the
+            // real-valued crossing behind it, and says whether a first or a second guess goes out to the host
+            if (a.spec_host && tries == 0 && spec_rule_due(rule, i, a.spec_iter)) {
                 double tent;
                 const double cx = ef_crossing(th, a.odds_ratio, s.red, &tent);
-                if (i >= a.spec_iter) {
-                    bool valid = false, trusted = false;
-                    double limit = cx;
-                    if (cx >= 0.0 && cross1 >= 0.0 && cross2 >= 0.0) {
-                        const double d1 = cross1 - cross2, d2 = cx - cross1;
-                        if (fabs(d2) < 1e-9) valid = true;
-                        else if (d1 != 0.0) {
-                            const double r = d2 / d1;
-                            if (r > 0.0 && r < 0.95) { limit = cx + d2 * r / (1.0 - r); valid = true; }
-                        }
-                        if (valid) {
-                            const double far = limit + 0.5 * (limit - cx) + (limit >= cx ? 0.02 : -0.02);
-                            trusted = floor(fmin(cx, far)) == floor(fmax(cx, far));
-                        }
-                    }
-                    const long long raw = tent < 0.0 ? 0 : (long long)tent;
-                    const long long lim = limit < 0.0 ? 0 : (long long)floor(limit);
-                    if (shot1 < 0) {
-                        const bool on_its_way = valid && !trusted && fabs(limit - cx) > 1.0 && i < a.spec_iter + 64;
-                        if (!on_its_way) {
-                            shot1 = trusted ? lim : raw;
-                            if (tid == 0) ef_publish_tentative(a, shot1, 0);
-                        }
-                    } else if (trusted) {
-                        if (lim != shot1 && tid == 0) ef_publish_tentative(a, lim, 1);
-                        settled = true;
-                    }
-                }
-                cross2 = cross1; cross1 = cx;
+                long long guess = 0;
+                const int action = spec_rule_step(rule, i, a.spec_iter, tent, cx, &guess);
+                if (action != SPEC_NOTHING && tid == 0) ef_publish_tentative(a, guess, action == SPEC_SECOND_GUESS ? 1 : 0);
             }
         }
         iters += i;

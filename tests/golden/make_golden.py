@@ -379,6 +379,85 @@ def make_em_random_cases(n=60):
         return pool.map(_fit_one_random, range(1000, 1000 + n))
 
 
+def _library_histogram(genome, density, peaks_per_gb, seed):
+    """Window-count histogram of a synthetic library (cratac/synth.py, the generator of bench.py) on a small genome at a
+    given fragment density and latent-peak density."""
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "cellranger-atac_b200"))
+    from cratac import synth
+    contigs = [("chr1", genome)]
+    fr = synth.generate(contigs, int(genome * density), 50, max(int(peaks_per_gb * genome / 1e9), 1), seed)
+    cuts = np.concatenate([fr["start"], fr["end"]]).astype(np.int64)
+    c = np.bincount(cuts, minlength=genome + 1)
+    S = np.concatenate(([0], np.cumsum(c)))
+    pos = np.arange(genome)
+    W = S[np.minimum(pos + 201, genome + 1)] - S[np.maximum(pos - 200, 0)]
+    b = np.bincount(W[W > 0])
+    return {int(k): int(b[k]) for k in np.nonzero(b)[0]}
+
+
+def _one_trajectory(args):
+    """The reference's own EM loop (analysis/peaks.py:144-170, replayed iterate by iterate with its own functions) on one
+    histogram: the threshold of every iterate's parameters (estimate_threshold, :43-63) and the real-valued crossing behind
+    it (log sig/bg interpolated between t and t + 1 against log odds), and the threshold estimate_final_threshold ends on."""
+    name, genome, density, peaks_per_gb, seed = args
+    ref = reference_em()
+    from scipy import stats
+    cd = _library_histogram(genome, density, peaks_per_gb, seed)
+    odds = 1 / 5
+    final, _ = ref.estimate_final_threshold(dict(cd), odds)
+
+    def crossing(params):
+        x = np.arange(1000)
+        f_sig = 1 - params.frac_zero_noise - params.frac_bg_noise
+        y_zero = params.frac_zero_noise * stats.geom.pmf(x, params.p_zero_noise, loc=-1)
+        y_bg = params.frac_bg_noise * stats.nbinom.pmf(x, 1 / params.alpha_bg_noise, 1 / (1 + params.alpha_bg_noise * params.mean_bg_noise))
+        y_sig = f_sig * stats.geom.pmf(x, params.p_signal, loc=-1)
+        with np.errstate(all="ignore"):
+            r = y_sig / (y_zero + y_bg)
+        idx = np.nonzero(r < odds)[0]
+        if len(idx) == 0:
+            return -1, -1.0
+        t = int(idx[-1])
+        if t + 1 >= 1000 or not (r[t] > 0) or not (r[t + 1] > r[t]) or not np.isfinite(r[t + 1]):
+            return t, t + 0.5
+        return t, float(t + (np.log(odds) - np.log(r[t])) / (np.log(r[t + 1]) - np.log(r[t])))
+
+    threshold = ref.simple_threshold_estimate(cd)
+    count_values = np.array(sorted(cd))
+    pm = np.empty((3, len(count_values)), dtype=float)
+    pm[0, :] = count_values <= ref.DEFAULT_THRESHOLD
+    pm[1, :] = (count_values <= threshold) & (count_values > ref.DEFAULT_THRESHOLD)
+    pm[2, :] = count_values > threshold
+    params = ref.weighted_parameter_estimates(cd, pm)
+    last, i, traj = None, 0, []
+    while i < 500 and (last is None or any(abs(last[k] - params[k]) / params[k] > 1e-6 for k in range(len(params)))):
+        i += 1
+        pm = ref.calculate_probability_distribution(cd, params)
+        last = params
+        params = ref.normalize_params(ref.weighted_parameter_estimates(cd, pm))
+        t, c = crossing(params)
+        assert t == (-1 if ref.estimate_threshold(params, odds) is None else int(ref.estimate_threshold(params, odds)))
+        traj.append([t, round(c, 9)])
+    reseeded = 1 / params.p_zero_noise < params.mean_bg_noise
+    print("trajectory %-22s iterates=%3d final=%s reseeded=%s" % (name, len(traj), final, reseeded), flush=True)
+    return dict(name=name, final=None if final is None else int(final), reseeded=bool(reseeded), trajectory=traj)
+
+
+def make_spec_trajectories():
+    """EM trajectories for the speculation rule (csrc/spec_rule.cuh): libraries at the depth and peak density of the bench
+    workloads (BASELINE.json configs[1] and the mm10 sweep of configs[4]) on a 12 Mb genome, four seeds each."""
+    import multiprocessing
+    g = 12000000
+    jobs = []
+    for seed in (2, 5, 7, 11):
+        for name, dens, ppg in (("grch38_250m_100k", 250e6 / 3.1e9, 100000 / 3.1), ("mm10_100m_20k", 100e6 / 2.73e9, 20000 / 2.73),
+                                ("mm10_100m_100k", 100e6 / 2.73e9, 100000 / 2.73), ("mm10_100m_300k", 100e6 / 2.73e9, 300000 / 2.73),
+                                ("grch38_120m_30k", 120e6 / 3.1e9, 30000 / 3.1)):
+            jobs.append(("%s_seed%d" % (name, seed), g, dens, ppg, seed))
+    with multiprocessing.Pool(min(8, os.cpu_count() or 1)) as pool:
+        return pool.map(_one_trajectory, jobs)
+
+
 def make_matrix_cases(tmpdir):
     rng = np.random.default_rng(77)
     cases = []
@@ -856,6 +935,9 @@ def main():
         if not only or "insert_sizes" in only:
             with open(os.path.join(HERE, "insert_sizes.json"), "w") as f:
                 json.dump(make_insert_size_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "spec_trajectories" in only:
+            with open(os.path.join(HERE, "spec_trajectories.json"), "w") as f:
+                json.dump(make_spec_trajectories(), f, separators=(",", ":"))
         if not only or "em_random" in only:
             with open(os.path.join(HERE, "em_random.json"), "w") as f:
                 json.dump(make_em_random_cases(), f, separators=(",", ":"))

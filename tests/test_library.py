@@ -380,3 +380,37 @@ def test_saddle_point_negative_binomial_pmf_against_scipy(tmp_path):
     ref = np.array([nbinom.pmf(*r) for r in rows])
     big = ref > 1e-290
     assert big.sum() > 300 and np.max(np.abs(mine[big] - ref[big]) / ref[big]) < 5e-12
+
+def test_speculation_rule_on_recorded_em_trajectories(tmp_path):
+    """csrc/spec_rule.cuh -- when the fit kernel tells the host which threshold it is heading for -- compiled for the host
+    and fed the reference's own EM trajectories (tests/golden/spec_trajectories.json: analysis/peaks.py replayed iterate by
+    iterate on 20 libraries at the depth and peak density of the bench workloads).  The last guess it publishes is the
+    threshold the fit ends on, in every case; a guess never goes out before iterate spec_iter; a second guess differs from
+    the first.  With the fixed iterate of round 2's first version (threshold of iterate 32, nothing else) 9 of the 20
+    would have been redone."""
+    import json
+    exe = str(tmp_path / "spec_rule_host_test")
+    build = subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "spec_rule_host_test.cpp"), "-lm"],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "spec_trajectories.json")))
+    assert len(cases) == 20 and not any(c["reseeded"] for c in cases)
+    spec_iter = 32
+    text = "".join("%d %d\n" % (spec_iter, len(c["trajectory"])) + "".join("%d %.9f\n" % (t, x) for t, x in c["trajectory"]) for c in cases)
+    run = subprocess.run([exe], input=text, capture_output=True, text=True)
+    assert run.returncode == 0
+    rows = [[int(v) for v in line.split()] for line in run.stdout.strip().splitlines()]
+    assert len(rows) == len(cases)
+    fixed_iterate_right = second_guesses = 0
+    for c, (g1, i1, g2, i2) in zip(cases, rows):
+        assert i1 >= spec_iter and g1 >= 0, c["name"]
+        last = g2 if i2 >= 0 else g1
+        assert last == c["final"], (c["name"], g1, i1, g2, i2)
+        if i2 >= 0:
+            assert g2 != g1 and i2 > i1
+            second_guesses += 1
+        fixed_iterate_right += c["trajectory"][spec_iter - 1][0] == c["final"]
+    assert fixed_iterate_right < 12 and 0 < second_guesses < 10
+    # a fit that ends before iterate spec_iter publishes nothing; spec_iter = 1 publishes the first iterate's threshold
+    run = subprocess.run([exe], input="32 3\n40 40.5\n41 41.5\n41 41.6\n1 2\n40 40.5\n41 41.5\n", capture_output=True, text=True)
+    assert [line.split() for line in run.stdout.strip().splitlines()] == [["-1", "-1", "-1", "-1"], ["40", "1", "-1", "-1"]]
