@@ -458,6 +458,83 @@ def make_spec_trajectories():
         return pool.map(_one_trajectory, jobs)
 
 
+def make_setup_aggr_cases(tmpdir):
+    """reference SETUP_AGGR_SAMPLES main + join (mro/atac/stages/aggr/setup_aggr_samples/__init__.py, executed as it stands)
+    on an aggregation of two small libraries, once per normalisation mode."""
+    import pandas as pd
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "cellranger-atac_b200"))
+    from cratac import synth
+    ref_peaks = reference_em()
+    contigs = [("chr1", 260000), ("chr2", 180000), ("chrM", 16000)]
+    libs = []
+    for lib, (n_frag, seed) in enumerate(((2600, 5), (4200, 6))):
+        fr = synth.generate(contigs, n_frag, 30, 40, seed=seed, background_factor=5)
+        rows = [[int(c), int(a), int(b)] for c, a, b in zip(fr["chrom"], fr["start"], fr["end"])]
+        cells_csv = "barcode,total,duplicate,passed_filters,is__cell_barcode\n" + "".join(
+            "BC%d-1,%d,%d,%d,%d\n" % (k, 1000 + 10 * k + 37 * lib, 100 + k, 700 + 5 * k + 11 * lib, 1 if k % 2 == 0 else 0) for k in range(50))
+        libs.append(dict(library_id="lib%d" % lib, fragments=rows, cells_csv=cells_csv))
+
+    class RefMgr(object):
+        def __init__(self, path):
+            pass
+
+        def get_contig_lengths(self):
+            return dict(contigs)
+
+        def list_species(self):
+            return [""]
+
+    class Martian(object):
+        @staticmethod
+        def exit(msg):
+            raise SystemExit(msg)
+
+    frag_files, cell_files = {}, {}
+    for i, lib in enumerate(libs):
+        cells = os.path.join(tmpdir, "singlecell_%d.csv" % i)
+        with open(cells, "w") as f:
+            f.write(lib["cells_csv"])
+        frag_files["fragments_%d.tsv.gz" % i] = lib["fragments"]
+        cell_files[i] = cells
+    aggr_csv = os.path.join(tmpdir, "aggr.csv")
+    with open(aggr_csv, "w") as f:
+        f.write("library_id,fragments,cells\n" + "".join("%s,fragments_%d.tsv.gz,%s\n" % (lib["library_id"], i, cell_files[i]) for i, lib in enumerate(libs)))
+
+    def open_fragment_file(filename=None):
+        for c, a, b in frag_files[filename]:
+            yield contigs[c][0], a, b, "BC", 1
+
+    def plain(v):
+        if isinstance(v, (np.floating, float)):
+            return float(v)
+        if isinstance(v, (np.integer, int)):
+            return int(v)
+        return v
+
+    cases = []
+    for normalization in (None, "unique", "total", "signal_mean", "signal_noise_threshold"):
+        fp = FakePickle()
+        ns = {"pd": pd, "np": np, "Counter": Counter, "pickle": fp, "json": json, "martian": Martian,
+              "estimate_final_threshold": ref_peaks.estimate_final_threshold, "ReferenceManager": RefMgr,
+              "open_fragment_file": open_fragment_file, "WINDOW_SIZE": 400, "PEAK_ODDS_RATIO": 1 / 5}
+        load_reference_module("mro/atac/stages/aggr/setup_aggr_samples/__init__.py", ns)
+        chunk_outs = []
+        for n in range(len(libs)):
+            outs = Record(library_info=os.path.join(tmpdir, "li_%s_%d.pickle" % (normalization, n)))
+            ns["main"](Record(aggr_csv=aggr_csv, normalization=normalization, reference_path="ref", n=n), outs)
+            chunk_outs.append(outs)
+        outs = Record(library_info=os.path.join(tmpdir, "li_%s.pickle" % normalization), gem_group_index=None,
+                      gem_group_index_json=os.path.join(tmpdir, "ggi_%s.json" % normalization))
+        ns["join"](Record(aggr_csv=aggr_csv, normalization=normalization, reference_path="ref"), outs, None, chunk_outs)
+        info = fp.store[outs.library_info]
+        info = {str(k): {kk: plain(vv) for kk, vv in v.items() if kk not in ("fragments", "cells")} for k, v in info.items()}
+        ggi = {str(k): list(v) for k, v in outs.gem_group_index["gem_group_index"].items()}
+        print("setup_aggr %-24s %s" % (normalization, {k: (v.get("original_threshold"), v.get("rate")) for k, v in info.items()}), flush=True)
+        cases.append(dict(normalization=normalization, library_info=info, gem_group_index=ggi,
+                          gem_group_index_json=json.load(open(outs.gem_group_index_json))))
+    return dict(contigs=[list(c) for c in contigs], libraries=libs, cases=cases)
+
+
 def make_matrix_cases(tmpdir):
     rng = np.random.default_rng(77)
     cases = []
@@ -935,6 +1012,9 @@ def main():
         if not only or "insert_sizes" in only:
             with open(os.path.join(HERE, "insert_sizes.json"), "w") as f:
                 json.dump(make_insert_size_cases(tmpdir), f, separators=(",", ":"))
+        if not only or "setup_aggr" in only:
+            with open(os.path.join(HERE, "setup_aggr.json"), "w") as f:
+                json.dump(make_setup_aggr_cases(tmpdir), f, separators=(",", ":"))
         if not only or "spec_trajectories" in only:
             with open(os.path.join(HERE, "spec_trajectories.json"), "w") as f:
                 json.dump(make_spec_trajectories(), f, separators=(",", ":"))

@@ -444,3 +444,82 @@ def test_setup_aggr_samples_signal_normalization(tmp_path):
         assert abs(info[lib_id]['rate'] - lowest / sm) < 1e-6
     assert info[1]['total_fragments_per_cell'] == float(np.median([1000 + 10 * k for k in range(0, 50, 2)]))
     assert outs.gem_group_index == {"gem_group_index": {1: ("lib0", 1), 2: ("lib1", 1)}}
+
+# ----------------------------------------------------------------------------- SETUP_AGGR_SAMPLES against the reference's own run
+SETUP_AGGR = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "setup_aggr.json")))
+
+
+def _aggr_library_text(lib):
+    names = [c[0] for c in SETUP_AGGR["contigs"]]
+    return "".join("%s\t%d\t%d\tAAACGAAAGAAACGAA-1\t1\n" % (names[c], a, b) for c, a, b in lib["fragments"]).encode()
+
+
+def test_setup_aggr_golden_pins_the_oracle():
+    """tests/golden/setup_aggr.json holds what the reference's SETUP_AGGR_SAMPLES main + join (executed as they stand by
+    make_golden.py) make of two small libraries in every normalisation mode.  The oracle's histogram over ALL contigs + fit
+    gives the same thresholds and signal means; the rates follow setup_aggr_samples/__init__.py:150-154."""
+    from oracle import em as oracle_em
+    contigs = [tuple(c) for c in SETUP_AGGR["contigs"]]
+    names = [c[0] for c in contigs]
+    want = {c["normalization"]: c for c in SETUP_AGGR["cases"]}
+    fitted = {}
+    for i, lib in enumerate(SETUP_AGGR["libraries"]):
+        o = util.oracle_decode(_aggr_library_text(lib), names)
+        hist = util.oracle_hist(contigs, names, o["chrom"], o["start"], o["end"])
+        thr, params = oracle_em.estimate_final_threshold(hist, 1 / 5.0)
+        fitted[str(i + 1)] = (int(thr), 1.0 / params[3])
+    for mode in ("signal_mean", "signal_noise_threshold"):
+        info = want[mode]["library_info"]
+        for lib_id, (thr, sm) in fitted.items():
+            assert info[lib_id]["original_threshold"] == thr
+            assert abs(info[lib_id]["signal_mean"] - sm) <= 1e-9 * sm
+        key = "signal_mean" if mode == "signal_mean" else "original_threshold"
+        lowest = min(info[k][key] for k in info)
+        assert all(abs(info[k]["rate"] - lowest / info[k][key]) < 1e-12 and info[k]["kind"] == "unique" for k in info)
+    assert all(v["rate"] == 1.0 and v["kind"] == "unique" for v in want[None]["library_info"].values())
+    assert {k: v["kind"] for k, v in want["total"]["library_info"].items()} == {"1": "total", "2": "total"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [None, "unique", "total", "signal_mean", "signal_noise_threshold"])
+def test_setup_aggr_samples_stage_equals_the_reference_run(tmp_path, mode):
+    """The drop-in stage (GPU pileup over every contig + fit) on the golden's libraries: library_info after join and the gem
+    group index equal what the reference wrote (floats to 1e-8: the fit)."""
+    spec = importlib.util.spec_from_file_location("stage_setup_aggr", os.path.join(util.PKG, "mro", "atac", "stages", "aggr", "setup_aggr_samples", "__init__.py"))
+    sas = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sas)
+    contigs = [tuple(c) for c in SETUP_AGGR["contigs"]]
+    ref = str(tmp_path / "ref")
+    refmgr.write_reference(ref, contigs)
+    rows = []
+    for i, lib in enumerate(SETUP_AGGR["libraries"]):
+        fpath = str(tmp_path / ("fragments_%d.tsv.gz" % i))
+        bgzf.write(fpath, _aggr_library_text(lib))
+        cells = str(tmp_path / ("singlecell_%d.csv" % i))
+        with open(cells, "w") as f:
+            f.write(lib["cells_csv"])
+        rows.append("%s,%s,%s" % (lib["library_id"], fpath, cells))
+    csv = str(tmp_path / "aggr.csv")
+    with open(csv, "w") as f:
+        f.write("library_id,fragments,cells\n" + "\n".join(rows) + "\n")
+    want = [c for c in SETUP_AGGR["cases"] if c["normalization"] == mode][0]
+    s = sas.split(Record(aggr_csv=csv, normalization=mode, reference_path=ref))
+    chunk_outs = []
+    for c in s['chunks']:
+        outs = Record(library_info=str(tmp_path / ("lib_%d.pickle" % c['n'])))
+        sas.main(Record(aggr_csv=csv, normalization=mode, reference_path=ref, n=c['n']), outs)
+        chunk_outs.append(outs)
+    outs = Record(library_info=str(tmp_path / "library_info.pickle"), gem_group_index=None, gem_group_index_json=str(tmp_path / "ggi.json"))
+    sas.join(Record(aggr_csv=csv, normalization=mode, reference_path=ref), outs, s['chunks'], chunk_outs)
+    info = pickle.load(open(outs.library_info, "rb"))
+    assert sorted(str(k) for k in info) == sorted(want["library_info"])
+    for lib_id, ref_info in want["library_info"].items():
+        got = info[int(lib_id)]
+        assert sorted(k for k in got if k not in ("fragments", "cells")) == sorted(ref_info)
+        for key, val in ref_info.items():
+            if isinstance(val, float):
+                assert abs(got[key] - val) <= 1e-8 * abs(val), (lib_id, key, got[key], val)
+            else:
+                assert got[key] == val, (lib_id, key, got[key], val)
+    assert {str(k): list(v) for k, v in outs.gem_group_index["gem_group_index"].items()} == want["gem_group_index"]
+    assert json.load(open(outs.gem_group_index_json)) == want["gem_group_index_json"]
