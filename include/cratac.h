@@ -92,7 +92,10 @@ int cratac_em_debug(cratac_ctx* ctx, double* out);
 /* ---- (1) fragment decode: replaces lib/python/tools/io.py:75-79 (open_fragment_file) and
  *      :82-92 (parsed_fragments_from_contig).  `text` is the DECOMPRESSED fragments.tsv
  *      (contig \t start \t stop \t barcode \t dup_count \n), position sorted.  Produces SoA int32
- *      (chrom, start, end, barcode index, dup count) in HBM plus the barcode dictionary. */
+ *      (chrom, start, end, barcode index, dup count) in HBM plus the barcode dictionary.
+ *      Limits the reference's line.split() does not have: a line of more than 256 bytes is reported as malformed
+ *      (CRATAC_ERR_PARSE with its line number; a text tile sees 256 bytes of what precedes it), a barcode field of more
+ *      than 63 bytes likewise; positions are int32.  Lines of cellranger-atac's own fragments.tsv.gz are 40-60 bytes. */
 int cratac_decode_host(cratac_ctx* ctx, const char* text, int64_t nbytes);
 int cratac_decode_device(cratac_ctx* ctx, const char* d_text, int64_t nbytes);
 /* already-parsed fragments (host SoA, n each); bc = index into `barcodes` (n_barcodes C strings,
