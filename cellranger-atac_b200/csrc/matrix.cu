@@ -463,7 +463,24 @@ __global__ void __launch_bounds__(256) k_csc_copy(const int32_t* __restrict__ ou
         const int64_t d = col_to_dense ? col_to_dense[j] : j;
         const int64_t src = seg_off[d] + (a - c0);
         const int len = (int)(b - a);
-        for (int k = me; k < len; k += width) {
+        // destination-aligned groups of four entries: two 16-byte stores of row indices (widened to int64) and one of counts;
+        // the source segment starts wherever the reduce left it, so its loads stay scalar
+        const int head = (int)(((a + 3) & ~(int64_t)3) - a) < len ? (int)(((a + 3) & ~(int64_t)3) - a) : len;
+        const int groups = (len - head) >> 2;
+        for (int k = me; k < head; k += width) {
+            indices[a + k] = (int64_t)out_row[src + k];
+            data[a + k] = out_cnt[src + k];
+        }
+        for (int g = me; g < groups; g += width) {
+            const int k = head + 4 * g;
+            const int r0 = out_row[src + k], r1 = out_row[src + k + 1], r2 = out_row[src + k + 2], r3 = out_row[src + k + 3];
+            const int4 cn = make_int4(out_cnt[src + k], out_cnt[src + k + 1], out_cnt[src + k + 2], out_cnt[src + k + 3]);
+            longlong2* ip = reinterpret_cast<longlong2*>(indices + a + k);
+            ip[0] = make_longlong2((long long)r0, (long long)r1);
+            ip[1] = make_longlong2((long long)r2, (long long)r3);
+            *reinterpret_cast<int4*>(data + a + k) = cn;
+        }
+        for (int k = head + 4 * groups + me; k < len; k += width) {
             indices[a + k] = (int64_t)out_row[src + k];
             data[a + k] = out_cnt[src + k];
         }
