@@ -414,3 +414,41 @@ def test_speculation_rule_on_recorded_em_trajectories(tmp_path):
     # a fit that ends before iterate spec_iter publishes nothing; spec_iter = 1 publishes the first iterate's threshold
     run = subprocess.run([exe], input="32 3\n40 40.5\n41 41.5\n41 41.6\n1 2\n40 40.5\n41 41.5\n", capture_output=True, text=True)
     assert [line.split() for line in run.stdout.strip().splitlines()] == [["-1", "-1", "-1", "-1"], ["40", "1", "-1", "-1"]]
+
+def test_tabix_reader_takes_what_htslib_adds(tmp_path):
+    """An index as htslib writes it carries, per reference, the pseudo-bin 37450 (two "chunks" that are not chunks: the
+    virtual-offset range of the reference, then the record counts) and, after the last reference, the number of records
+    without coordinates.  The module's own writer emits neither; here both are added to one of its indexes (serialised by
+    hand from the format description of tbx.c / the tabix paper) and the reader must give the same spans and ranges."""
+    import struct
+    from cratac import tabix
+    contigs = [("chr1", 3000000), ("chr2", 2000000), ("chr3", 500000)]
+    text = synth.to_text(synth.generate(contigs, 30000, 20, 80, seed=19))
+    p = str(tmp_path / "fragments.tsv.gz")
+    bgzf.write(p, text)
+    plain = tabix.read_index(tabix.build_index(p))
+    spans = tabix.contig_spans(plain)
+    n_records = {n: sum(1 for ln in text.split(b"\n")[:-1] if ln.split(b"\t")[0].decode() == n) for n in plain["names"]}
+    nm = b"".join(x.encode() + b"\x00" for x in plain["names"])
+    out = [tabix.MAGIC, struct.pack("<8i", len(plain["names"]), plain["format"], plain["col_seq"], plain["col_beg"], plain["col_end"],
+                                     plain["meta"], plain["skip"], len(nm)), nm]
+    for name, ref in zip(plain["names"], plain["refs"]):
+        bins = dict(ref["bins"])
+        bins[tabix.PSEUDO_BIN] = [spans[name], (n_records[name], 0)]          # (ref_beg, ref_end), (n_mapped, n_unmapped)
+        out.append(struct.pack("<i", len(bins)))
+        for b in sorted(bins, reverse=True):                                  # htslib's hash order is arbitrary: not ascending
+            out.append(struct.pack("<Ii", b, len(bins[b])))
+            out += [struct.pack("<QQ", c0, c1) for c0, c1 in bins[b]]
+        out.append(struct.pack("<i", len(ref["linear"])))
+        out.append(struct.pack("<%dQ" % len(ref["linear"]), *ref["linear"]))
+    out.append(struct.pack("<Q", 0))                                          # n_no_coor
+    p2 = str(tmp_path / "htslib_style.tbi")
+    with open(p2, "wb") as f:
+        f.write(bgzf.compress(b"".join(out), 6))
+    styled = tabix.read_index(p2)
+    assert styled["names"] == plain["names"] and tabix.contig_spans(styled) == spans
+    assert all(tabix.PSEUDO_BIN in r["bins"] for r in styled["refs"])
+    assert tabix.range_span(styled, ["chr2", "chr3"]) == tabix.range_span(plain, ["chr2", "chr3"])
+    beg, end = tabix.range_span(styled, ["chr2"])
+    got = _ffi.inflate_range(p, beg, end, threads=2).tobytes()
+    assert got == b"".join(ln + b"\n" for ln in text.split(b"\n")[:-1] if ln.startswith(b"chr2\t"))
